@@ -1,0 +1,185 @@
+"""Seeded synthetic workloads shared by the golden generator, the tests and bench.py.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Nothing here reads the
+reference; everything is reproducible from integer seeds with CPU
+``torch.Generator`` streams (identical across hosts for one torch version; the
+golden files carry checksums so that drift would be detected).
+"""
+
+import math
+
+import torch
+
+from . import flow_oracle as fo
+
+
+def seeded_state(masks, seed, dtype=torch.float32, weight_norm=True, gain=1.0, prefix=''):
+    """Random conditioner parameters with the key names of the reference ``state_dict``.
+
+    Distribution of nn.Linear's default init (U(+-1/sqrt(fan_in)), as used by
+    nn/masked.py:164-176), masked, then g = ||v||_row as in nn/masked.py:391-392,
+    optionally scaled by ``gain`` to make the transformer parameters more varied.
+    """
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for li, mask in enumerate(masks):
+        out_f, in_f = mask.shape
+        bound = 1.0 / math.sqrt(in_f)
+        w = (torch.rand(out_f, in_f, generator=g, dtype=torch.float64) * 2 - 1) * bound
+        b = (torch.rand(out_f, generator=g, dtype=torch.float64) * 2 - 1) * bound
+        w = (w * mask.double()).to(dtype)
+        key = f'{prefix}_conditioner.layers.{2 * li}.'
+        if weight_norm:
+            sd[key + 'weight_v'] = w
+            sd[key + 'weight_g'] = (torch.linalg.norm(w.double(), dim=1, keepdim=True) * gain).to(dtype)
+        else:
+            sd[key + 'weight'] = w * gain
+        sd[key + 'bias'] = b.to(dtype)
+    return sd
+
+
+def checksum(sd):
+    return float(sum(v.double().abs().sum() for v in sd.values()))
+
+
+def uniform(shape, seed, lo, hi, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(*shape, generator=g, dtype=torch.float64) * (hi - lo) + lo).to(dtype)
+
+
+def normal(shape, seed, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g, dtype=torch.float64).to(dtype)
+
+
+# ---------------------------------------------------------------------------
+# transformer-level cases: name -> (spec factory, n_features, x generator)
+# ---------------------------------------------------------------------------
+
+def _spline(n, dtype, **kw):
+    x0 = kw.pop('x0', -2.0)
+    xf = kw.pop('xf', 2.0)
+    return fo.Spline(x0=torch.full((n,), x0, dtype=dtype), xf=torch.full((n,), xf, dtype=dtype), **kw)
+
+
+def transformer_cases(dtype=torch.float32):
+    """name -> (spec, n_features, x, params); small and cheap."""
+    B = 24
+    cases = {}
+
+    def add(name, spec, n, x, pscale=1.0, seed=11):
+        par = normal((B, len(spec.identity_params(n))), seed, dtype) * pscale
+        cases[name] = (spec, n, x, par)
+
+    add('affine', fo.Affine(), 7, normal((B, 7), 1, dtype))
+    add('spline_k8', _spline(6, dtype, n_bins=8), 6, normal((B, 6), 2, dtype) * 1.5)      # some in the tails
+    add('spline_k5_circular', _spline(5, dtype, n_bins=5, circular=True, x0=-math.pi, xf=math.pi), 5,
+        uniform((B, 5), 3, -math.pi, math.pi, dtype) * 0.999, pscale=1.5)
+    add('spline_k4_idslopes', _spline(4, dtype, n_bins=4, identity_boundary_slopes=True), 4, normal((B, 4), 4, dtype))
+    add('spline_k4_circ_idslopes', _spline(4, dtype, n_bins=4, circular=True, identity_boundary_slopes=True), 4,
+        uniform((B, 4), 5, -2.0, 2.0, dtype) * 0.999)
+    add('spline_k6_learn_lower', _spline(3, dtype, n_bins=6, learn_lower_bound=True), 3, normal((B, 3), 6, dtype),
+        pscale=0.5)
+    add('spline_k6_learn_upper', _spline(3, dtype, n_bins=6, learn_upper_bound=True), 3, normal((B, 3), 7, dtype),
+        pscale=0.5)
+    add('spline_k3_learn_both', _spline(3, dtype, n_bins=3, learn_lower_bound=True, learn_upper_bound=True), 3,
+        normal((B, 3), 8, dtype), pscale=0.5)
+    add('sos2', fo.SOS(2), 5, normal((B, 5), 9, dtype))
+    add('sos3', fo.SOS(3), 5, normal((B, 5), 10, dtype))
+    add('moebius_d3', fo.Moebius(dimension=3), 6, normal((B, 6), 12, dtype))
+    add('moebius_d2', fo.Moebius(dimension=2), 6, normal((B, 6), 13, dtype))
+    add('moebius_d4_unit', fo.Moebius(dimension=4, unit_sphere=True), 8,
+        torch.nn.functional.normalize(normal((B, 2, 4), 14, dtype), dim=-1).reshape(B, 8))
+    mixed = fo.Mixed([_spline(2, dtype, n_bins=4, circular=True, x0=-math.pi, xf=math.pi),
+                      fo.Affine(), _spline(3, dtype, n_bins=4, x0=-4.0, xf=4.0)],
+                     [[1, 4], [0, 6], [2, 3, 5]])
+    xm = normal((B, 7), 15, dtype)
+    xm[:, [1, 4]] = uniform((B, 2), 16, -math.pi, math.pi, dtype) * 0.999
+    add('mixed', mixed, 7, xm)
+    return cases
+
+
+# ---------------------------------------------------------------------------
+# MAF-level cases
+# ---------------------------------------------------------------------------
+
+def maf_cases(dtype=torch.float32):
+    """name -> dict(degrees_in, spec, hidden_layers, weight_norm, x, seed[, invertible])."""
+    B = 16
+    c = {}
+
+    def add(name, degrees_in, spec, x, hidden_layers=2, weight_norm=True, seed=100, invertible=True, gain=2.0):
+        c[name] = dict(degrees_in=torch.as_tensor(degrees_in), spec=spec, hidden_layers=hidden_layers,
+                       weight_norm=weight_norm, x=x, seed=seed, invertible=invertible, gain=gain)
+
+    add('affine_asc', fo.gen_degrees(8), fo.Affine(), normal((B, 8), 21, dtype))
+    add('affine_desc_nown', fo.gen_degrees(8, order='descending'), fo.Affine(), normal((B, 8), 22, dtype),
+        weight_norm=False)
+    add('affine_cond_h1', fo.gen_degrees(9, conditioning_indices=[0, 4]), fo.Affine(), normal((B, 9), 23, dtype),
+        hidden_layers=1)
+    add('affine_h4', fo.gen_degrees(6, order='descending'), fo.Affine(), normal((B, 6), 24, dtype), hidden_layers=4)
+    add('spline_circ', fo.gen_degrees(6), _spline(6, dtype, n_bins=8, circular=True, x0=-math.pi, xf=math.pi),
+        uniform((B, 6), 25, -math.pi, math.pi, dtype) * 0.999)
+    add('spline_desc_cond', fo.gen_degrees(7, order='descending', conditioning_indices=[2]),
+        _spline(6, dtype, n_bins=5, x0=-4.0, xf=4.0), normal((B, 7), 26, dtype))
+    add('sos2', fo.gen_degrees(6), fo.SOS(2), normal((B, 6), 27, dtype), invertible=False, gain=1.0)
+    add('moebius_d3', fo.gen_degrees(6, repeats=3), fo.Moebius(dimension=3), normal((B, 6), 28, dtype))
+    add('moebius_d2_cond', fo.gen_degrees(8, conditioning_indices=[0, 1], repeats=2, order='descending'),
+        fo.Moebius(dimension=2), normal((B, 8), 29, dtype))
+    mixed = fo.Mixed([_spline(2, dtype, n_bins=4, circular=True, x0=-math.pi, xf=math.pi),
+                      _spline(4, dtype, n_bins=4, x0=-4.0, xf=4.0)], [[2, 5], [0, 1, 3, 4]])
+    xm = normal((B, 6), 30, dtype)
+    xm[:, [2, 5]] = uniform((B, 2), 31, -math.pi, math.pi, dtype) * 0.999
+    add('mixed_splines', fo.gen_degrees(6), mixed, xm)
+    add('repeated_degrees', torch.tensor([0, 0, 1, 2, 2, 2, 1]), fo.Affine(), normal((B, 7), 32, dtype))
+    return c
+
+
+def build_oracle(case, dtype=torch.float32):
+    m = fo.MafOracle(case['degrees_in'], case['spec'], hidden_layers=case['hidden_layers'],
+                     weight_norm=case['weight_norm'])
+    sd = seeded_state([k.to(dtype) for k in m.masks], case['seed'], dtype, case['weight_norm'], case['gain'])
+    return m.load(sd), sd
+
+
+# ---------------------------------------------------------------------------
+# BASELINE.json configurations
+# ---------------------------------------------------------------------------
+
+def cfg_flow(name, dtype=torch.float32, n_layers=None, D=None):
+    """Return a list of (MafOracle, state_dict) for a BASELINE.json configuration."""
+    if name == 'cfg1':           # 2 x MAF Affine, D=66
+        D, L = D or 66, n_layers or 2
+        mk = lambda: fo.Affine()
+    elif name == 'cfg2':         # 4 x MAF circular spline K=8, D=66
+        D, L = D or 66, n_layers or 4
+        mk = lambda: fo.Spline(x0=torch.full((D,), -math.pi, dtype=dtype), xf=torch.full((D,), math.pi, dtype=dtype),
+                               n_bins=8, circular=True)
+    elif name == 'cfg5':         # 8 x MAF spline K=8 (non circular), D=3000 (scaled down in tests)
+        D, L = D or 3000, n_layers or 8
+        mk = lambda: fo.Spline(x0=torch.full((D,), -5.0, dtype=dtype), xf=torch.full((D,), 5.0, dtype=dtype), n_bins=8)
+    elif name == 'cfg3':         # 3 x SOS(2) + 3 x Moebius(d=3), D=300
+        D, L = D or 300, n_layers or 6
+        mk = None
+    else:
+        raise ValueError(name)
+    flows = []
+    for l in range(L):
+        order = 'ascending' if l % 2 == 0 else 'descending'
+        if name == 'cfg3':
+            if l < L // 2:
+                spec, deg = fo.SOS(2), fo.gen_degrees(D, order=order)
+            else:
+                spec, deg = fo.Moebius(dimension=3), fo.gen_degrees(D, order=order, repeats=3)
+        else:
+            spec, deg = mk(), fo.gen_degrees(D, order=order)
+        m = fo.MafOracle(deg, spec)
+        sd = seeded_state([k.to(dtype) for k in m.masks], 1234 + l, dtype)
+        flows.append((m.load(sd), sd))
+    return flows
+
+
+def cfg_input(name, batch, dtype=torch.float32, D=None):
+    if name == 'cfg2':
+        return uniform((batch, D or 66), 0, -math.pi, math.pi, dtype) * 0.999
+    return normal((batch, D or {'cfg1': 66, 'cfg3': 300, 'cfg5': 3000}[name]), 0, dtype)
