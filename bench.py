@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""Benchmark of the MAF forward + log|det J| hot path (BASELINE.json metric) on 1..N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|bf16|bf16x3]
+
+One "step" = one forward pass of the BASELINE.json configuration cfg2 (4 x MAF, MADE conditioner 66->328->328->1650,
+circular neural spline K=8, D=66) over one batch of 65536 synthetic samples per GPU (weak scaling: contiguous
+batch shards, no data-path collective).  Rank 0 prints ONE JSON line (contract in the task description):
+
+  value      samples/s, inputs resident in HBM, timed per step with CUDA events (L2 flushed between steps),
+             max over ranks;
+  e2e        the same metric through the public module API with HOST buffers: pinned-host -> device copy of x,
+             forward, device -> host copy of (y, log_det_J) inside the timed region;
+  roofline   dominant kernel timed alone with CUDA events vs the measured tensor peak (MEASURED_PEAKS.json);
+  cpu_baseline  the oracle (CPU restatement of the reference's PyTorch path, bit-identical to it) on the box's
+             host cores, bounded sample.
+`--impl reference` times only that CPU path (the reference is pure Python on PyTorch; /root/reference does not
+exist on the GPU box, the oracle restates it bit for bit -- see oracle/check_against_reference.py).
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+METRIC = 'MAF fwd+logdet samples/s (D=66, spline)'
+UNIT = 'samples/s'
+WORKLOAD = 'cfg2: 4xMAF circular spline K=8, D=66, MADE 66-328-328-1650, batch 65536 per GPU'
+BATCH = 65536
+CPU_SAMPLE = 16384
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p['hbm_gbs'], bf16_tflops=p['bf16_tflops'], bf16_tflops_sustained=p['bf16_tflops_sustained'],
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0,
+                source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    FIELDS = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.FIELDS}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+
+def build_cpu_flow():
+    from oracle import cases
+    return cases.cfg_flow('cfg2'), cases
+
+
+def time_cpu_reference(steps, warmup, sample=CPU_SAMPLE):
+    """The reference's CPU PyTorch path (oracle restatement), all host threads, no_grad."""
+    from oracle import flow_oracle as fo
+    flows, cases = build_cpu_flow()
+    mods = [m for m, _ in flows]
+    x = cases.cfg_input('cfg2', sample)
+    torch.set_num_threads(os.cpu_count() or 1)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            fo.sequential(mods, x)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return sample, times, torch.get_num_threads()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    sample, times, cores = time_cpu_reference(steps, warmup)
+    total = sum(times)
+    value = sample * len(times) / total
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': len(times),
+        'warmup': warmup, 'ms_per_step': 1e3 * total / len(times), 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'note': f'CPU reference arm: each step is a bounded sample of {sample} samples'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': f'{sample} samples per step of the cfg2 forward, fp32, torch.no_grad, '
+                                   f'{cores} threads; oracle port, bit-identical to the reference on CPU'},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from helpers import cfg_flow_modules
+    from oracle import cases
+    from tfep_b200 import _ops
+
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    seq, _ = cfg_flow_modules('cfg2', dev)
+    seq.eval()
+    # contiguous batch shards of one global synthetic data set (seeded on the host)
+    x_host = cases.cfg_input('cfg2', BATCH * world)[rank * BATCH:(rank + 1) * BATCH].contiguous().pin_memory()
+    x = x_host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def step():
+        with torch.no_grad():
+            return seq(x)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clocks:
+        t_wall0 = time.perf_counter()
+        for a, b in ev:
+            flush.zero_()                       # L2 flush between timed iterations (untimed)
+            a.record()
+            y, ld = step()
+            b.record()
+        torch.cuda.synchronize(dev)
+        t_wall = time.perf_counter() - t_wall0
+    ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+    barrier()
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms)
+
+    # end to end through the public API with host buffers (pinned), copies inside the timed region
+    y_host = torch.empty((BATCH, 66), dtype=torch.float32).pin_memory()
+    ld_host = torch.empty((BATCH,), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        xd = x_host.to(dev, non_blocking=True)
+        with torch.no_grad():
+            yy, ll = seq(xd)
+        y_host.copy_(yy, non_blocking=True)
+        ld_host.copy_(ll, non_blocking=True)
+
+    for _ in range(max(1, args.warmup)):
+        e2e_step()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        e2e_step()
+    b.record()
+    torch.cuda.synchronize(dev)
+    e2e_ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    barrier()
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_ms)
+
+    if rank != 0:
+        return
+
+    # roofline of the dominant kernel: the output-layer GEMM (328 -> 1650) of one MAF layer, timed alone
+    pk = seq[0]._pack()
+    plan = pk['plan']
+    with torch.no_grad():
+        pw, pb = seq[0]._conditioner.packed_weights(plan)
+        k_ranges, _, _ = plan.tables(dev)
+        h = torch.randn(BATCH, pw[2].shape[1], device=dev)
+        out = torch.empty(BATCH, pw[2].shape[0], device=dev)
+        for _ in range(3):
+            _ops.linear_forward(h, pw[2], pb[2], 0, k_ranges[2], out=out)
+        kev = []
+        for _ in range(10):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            _ops.linear_forward(h, pw[2], pb[2], 0, k_ranges[2], out=out)
+            e.record()
+            kev.append((s, e))
+        torch.cuda.synchronize(dev)
+    k_ms = statistics.mean(s.elapsed_time(e) for s, e in kev)
+    pk_peaks = peaks()
+    flops_per_launch = 2.0 * plan.nnz[2] * BATCH           # algorithmic: 2 x non-zeros of the mask x samples
+    achieved = flops_per_launch / (k_ms * 1e-3) / 1e12
+    roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': pk_peaks['bf16_tflops'], 'unit': 'TFLOP/s',
+                'frac': achieved / pk_peaks['bf16_tflops'], 'traffic': None,
+                'kernel': 'gemm_kernel<float,true,true> (output layer 328->1650, fp32 FFMA, staircase-skipped)',
+                'kernel_ms': k_ms, 'peak_source': pk_peaks['source'] + ', bf16 burst',
+                'whole_step_frac': (2.0 * plan.masked_macs * 4 * BATCH * args.steps / (total_ms * 1e-3) / 1e12)
+                / pk_peaks['bf16_tflops_sustained']}
+
+    sample, times, cores = time_cpu_reference(2, 1)
+    cpu_value = sample * len(times) / sum(times)
+
+    value = BATCH * world * args.steps / (total_ms * 1e-3)
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'precision': args.precision, 'l2': 'flushed (256 MB memset) between timed steps',
+                   'parallelism': f'batch-sharded x{world}, weights replicated, no data-path collective',
+                   'wall_s_timed_region': t_wall},
+        'clocks': clocks.summary(),
+        'e2e': {'value': BATCH * world * args.steps / (e2e_ms * 1e-3), 'unit': UNIT,
+                'h2d_bytes_per_step': x_host.numel() * 4, 'd2h_bytes_per_step': (y_host.numel() + ld_host.numel()) * 4},
+        'gpu_launches': 16 * args.steps,
+        'roofline': roofline,
+        'cpu_baseline': {'value': cpu_value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': f'{sample} samples x {len(times)} passes of the same cfg2 forward, fp32, no_grad'},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--precision', default='fp32', choices=['fp32'])
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,199 @@
+/*
+ * tfep_b200 -- C ABI of the B200 (sm_100a) implementation of the tfep MAF / (T)FEP hot path.
+ *
+ * The reference (andrrizzi/tfep) is pure Python on PyTorch and has no FFI layer: its boundary for
+ * this path is the Python class / function API.  This header is the contract
+ * a reference-side binding would load with ctypes; every entry point names the
+ * reference code it replaces (paths relative to the reference's tfep/ package).
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, explicit sizes and leading dimensions (in elements), no torch types;
+ *   - the caller owns every buffer (inputs, outputs, workspaces); nothing here allocates device memory;
+ *   - calls enqueue work on `stream` (a cudaStream_t passed as void*) and return without synchronising;
+ *   - return value: 0 = ok, <0 = invalid argument, >0 = cudaError_t; tfepb_last_error() gives the
+ *     thread-local message of the last failure;
+ *   - `dtype` selects the arithmetic type of every floating-point buffer of that call
+ *     (TFEPB_F32 or TFEPB_F64); the tensor-core entry points are fp32-in/fp32-out with bf16 operands;
+ *   - a transformer parameter (sample b, parameter p, feature f) lives at
+ *         par[b * ldp + par_offset + p * par_stride_p + f * par_stride_f]
+ *     or, when the optional table par_base is given, at
+ *         par[b * ldp + par_offset + par_base[f] + p * par_stride_p].
+ *     This covers the reference's parameter-major layout (stride_p = n_features, stride_f = 1;
+ *     nn/transformers/spline.py:352, affine.py:140, sos.py:108), Moebius' native layout
+ *     (moebius.py:102) and the degree-sorted feature-major packing of the fused paths;
+ *   - `cols` (optional, int32, length n_features) maps transformer feature f to its column in x / y
+ *     (conditioning features, nn/flows/autoregressive.py:164-175; MixedTransformer groups, mixed.py:168-186).
+ */
+#ifndef TFEP_B200_H
+#define TFEP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFEPB_ABI_VERSION 1
+
+enum { TFEPB_F32 = 0, TFEPB_F64 = 1 };
+enum { TFEPB_ACT_NONE = 0, TFEPB_ACT_ELU = 1 };
+
+typedef void* tfepb_stream_t;
+
+/* ----------------------------------------------------------------------------------------------
+ * status / device
+ * -------------------------------------------------------------------------------------------- */
+int tfepb_abi_version(void);
+const char* tfepb_last_error(void);
+/* Fills SM count and compute capability of the current device.  The library refuses to run
+ * compute entry points on anything but compute capability 10.x (no fallback path). */
+int tfepb_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* ----------------------------------------------------------------------------------------------
+ * MADE conditioner, exact-arithmetic SIMT path (any shape, fp32 / fp64)
+ * Replaces MaskedLinearFunc.forward / .backward (nn/masked.py:266-302) and the ELU of MADE
+ * (nn/conditioners/made.py:320).  `w` is the EFFECTIVE weight M o (g v/|v|) (nn/masked.py:369-371),
+ * so the mask is already folded in; `k_ranges` lets the kernel skip the all-zero part of the
+ * reduction for a tile of TFEPB_GEMM_TILE_N consecutive output columns.
+ * -------------------------------------------------------------------------------------------- */
+#define TFEPB_GEMM_TILE_N 64
+
+typedef struct {
+    int32_t dtype;
+    int32_t batch, in_features, out_features;
+    const void* x;    int64_t ldx;     /* (batch, in)  */
+    const void* w;    int64_t ldw;     /* (out, in) effective weights */
+    const void* bias;                  /* (out,) or NULL */
+    void* y;          int64_t ldy;     /* (batch, out) */
+    int32_t activation;                /* TFEPB_ACT_* applied to y */
+    int32_t reserved;
+    const int32_t* k_ranges;           /* NULL or (ceil(out/TILE_N), 2) int32 on the device: [begin,end) */
+} tfepb_linear_fwd_args;
+/* y = act(x w^T + bias) */
+int tfepb_masked_linear_forward(const tfepb_linear_fwd_args* a, tfepb_stream_t stream);
+
+typedef struct {
+    int32_t dtype;
+    int32_t batch, in_features, out_features;
+    const void* grad_y;  int64_t ldgy;   /* (batch, out): cotangent of the PRE-activation output */
+    const void* w;       int64_t ldw;    /* (out, in) effective weights */
+    void* grad_x;        int64_t ldgx;   /* (batch, in) */
+    const void* act_out; int64_t ldact;  /* NULL, or (batch, in) post-ELU activations of the PREVIOUS layer:
+                                            grad_x is multiplied by ELU'(.) = (h > 0 ? 1 : h + 1) */
+    int32_t accumulate;                  /* 0: grad_x = ..., 1: grad_x += ... */
+    int32_t reserved;
+    const int32_t* n_ranges;             /* NULL or (ceil(in/TILE_N), 2): nonzero range of the out-reduction */
+} tfepb_linear_bwd_input_args;
+/* grad_x = (grad_y w) [* ELU'(act_out)] */
+int tfepb_masked_linear_backward_input(const tfepb_linear_bwd_input_args* a, tfepb_stream_t stream);
+
+typedef struct {
+    int32_t dtype;
+    int32_t batch, in_features, out_features;
+    const void* grad_y;  int64_t ldgy;   /* (batch, out) */
+    const void* x;       int64_t ldx;    /* (batch, in) */
+    void* grad_w;        int64_t ldgw;   /* (out, in); must be zero-filled by the caller (split-batch atomics) */
+    void* grad_bias;                     /* (out,) zero-filled, or NULL */
+} tfepb_linear_bwd_weight_args;
+/* grad_w += grad_y^T x ; grad_bias += sum_b grad_y   (the caller applies the mask, nn/masked.py:296-297) */
+int tfepb_masked_linear_backward_weight(const tfepb_linear_bwd_weight_args* a, tfepb_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * transformers: elementwise map + per-sample log|det J| reduction
+ * -------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t dtype;
+    int32_t batch, n_features;
+    int32_t inverse;                    /* 0 forward, 1 inverse */
+    const void* x;   int64_t ldx;       /* input  (batch, *) */
+    void* y;         int64_t ldy;       /* output (batch, *) */
+    const void* par; int64_t ldp;       /* parameters (batch, *) */
+    int64_t par_offset, par_stride_p, par_stride_f;
+    const int32_t* par_base;            /* NULL, or (n_features,) int32: offset of parameter 0 of feature f in a
+                                           row of `par`, replacing f * par_stride_f (degree-sorted
+                                           feature-major packing, MixedTransformer groups) */
+    const int32_t* cols;                /* NULL or int32 table: column of feature f in x / y */
+    const int32_t* feat_ids;            /* NULL (features 0..n_features-1), or (n_features,) int32 ids of the
+                                           features to process; cols, par_base and the spline domain tables
+                                           are indexed by the id (one degree group of the inverse sweep) */
+    void* logdet;                       /* (batch,) */
+    int32_t accumulate_logdet;          /* 0: logdet = ld, 1: logdet += ld */
+    int32_t reserved;
+} tfepb_tx_io;
+
+/* AffineTransformer: y = x exp(a) + b, ld = sum a; inverse x = (y - b) exp(-a), ld = -sum a.
+ * Parameter 0 = shift, 1 = log-scale.  nn/transformers/affine.py:281-363. */
+int tfepb_affine(const tfepb_tx_io* io, tfepb_stream_t stream);
+
+typedef struct {
+    int32_t n_bins;
+    int32_t circular, identity_boundary_slopes, learn_lower_bound, learn_upper_bound;
+    int32_t reserved;
+    const void* x0; const void* xf; const void* y0; const void* yf;   /* (n_features,) each, dtype of io */
+    double min_bin_size, min_slope;
+    int32_t* bins_out;                  /* NULL, or (batch, n_features) int32: 0 left tail, 1..K bins, K+1 right tail */
+    int64_t ldbins;
+} tfepb_spline_cfg;
+/* NeuralSplineTransformer forward / inverse incl. softmax/softplus parameter normalisation, the
+ * circular shift + wrap, identity boundary slopes and learnable bounds.
+ * nn/transformers/spline.py:184-261 (module), :319-417 (_get_parameters), :424-650 (functional). */
+int tfepb_spline(const tfepb_tx_io* io, const tfepb_spline_cfg* cfg, tfepb_stream_t stream);
+
+/* SOSPolynomialTransformer forward (no inverse in the reference, sos.py:111-114).
+ * nn/transformers/sos.py:207-235, 271-306. */
+int tfepb_sos(const tfepb_tx_io* io, int32_t n_polynomials, tfepb_stream_t stream);
+
+/* MoebiusTransformer forward; the inverse is the same map with -par (moebius.py:142-147),
+ * selected with io->inverse.  n_features must be a multiple of `dimension` (<= 16).
+ * nn/transformers/moebius.py:374-478. */
+int tfepb_moebius(const tfepb_tx_io* io, int32_t dimension, double max_radius, int32_t unit_sphere,
+                  tfepb_stream_t stream);
+
+/* Vector-Jacobian products of the forward maps above (what PyTorch autograd computes for the
+ * reference; SOS follows the reference's hand-written backward, sos.py:237-268, which drops the
+ * log-det cotangent).  grad_par uses the same (ldp, offset, strides) addressing as par. */
+typedef struct {
+    const void* grad_y;      int64_t ldgy;    /* (batch, *) cotangent of y, addressed through cols */
+    const void* grad_logdet;                  /* (batch,) cotangent of logdet, or NULL (= 0) */
+    void* grad_x;            int64_t ldgx;    /* (batch, *) written through cols */
+    void* grad_par;                           /* same addressing as io->par */
+} tfepb_tx_grads;
+int tfepb_affine_backward(const tfepb_tx_io* io, const tfepb_tx_grads* g, tfepb_stream_t stream);
+int tfepb_spline_backward(const tfepb_tx_io* io, const tfepb_spline_cfg* cfg, const tfepb_tx_grads* g,
+                          tfepb_stream_t stream);
+int tfepb_sos_backward(const tfepb_tx_io* io, int32_t n_polynomials, const tfepb_tx_grads* g,
+                       tfepb_stream_t stream);
+int tfepb_moebius_backward(const tfepb_tx_io* io, int32_t dimension, double max_radius, int32_t unit_sphere,
+                           const tfepb_tx_grads* g, tfepb_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * (T)FEP estimator and bootstrap
+ * -------------------------------------------------------------------------------------------- */
+/* One pass over v_i = scale * w_i (+ logw_i): writes out[0] = max_i v_i, out[1] = sum_i exp(v_i - max)
+ * as doubles on the device.  fep_estimator = -kT (out[0] + log out[1] - log n) with scale = -1/kT
+ * (analysis/estimator.py:61-86).  `partials` is a caller-owned workspace of
+ * tfepb_lse_workspace_bytes() bytes.  The pair (max, sum) is what ranks exchange at N > 1. */
+int64_t tfepb_lse_workspace_bytes(void);
+int tfepb_lse(int32_t dtype, const void* w, const void* logw, int64_t n, double scale,
+              void* partials, double* out2, tfepb_stream_t stream);
+
+/* Raw MT19937 stream of torch's CPU generator (analysis/bootstrap.py:214-218 draws its indices from
+ * it): fills idx[i] = u32[skip + i] % max_idx for i < count, continuing from `state` (624 words +
+ * position, exactly at::mt19937's data) which is updated in place on the device. */
+int tfepb_mt19937_seed(uint32_t seed, uint32_t* state625_host);
+int tfepb_mt19937_indices(uint32_t* state625_dev, int64_t count, uint32_t max_idx, int32_t* idx,
+                          tfepb_stream_t stream);
+
+/* Fused resample + exponential average: for resample r (row r of idx, or a counter-based Philox
+ * stream when idx == NULL) out_sums[r] = sum_j e[idx[r, j]] in double, where e_i = exp(v_i - max)
+ * was produced by tfepb_exp_table.  analysis/bootstrap.py:185-233 with statistic = fep_estimator. */
+int tfepb_exp_table(int32_t dtype, const void* w, int64_t n, double scale, const double* max_dev,
+                    float* e, tfepb_stream_t stream);
+int tfepb_bootstrap_sums(const float* e, int64_t n, uint32_t max_idx, const int32_t* idx, int64_t ldidx,
+                         int32_t n_resamples, int64_t sample_size, uint64_t philox_seed,
+                         uint64_t philox_offset, double* out_sums, tfepb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFEP_B200_H */

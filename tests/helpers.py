@@ -1,0 +1,67 @@
+"""Shared test helpers: build tfep_b200 modules from the oracle's case descriptions."""
+
+import os
+
+import numpy as np
+import torch
+
+from oracle import cases
+from oracle import flow_oracle as fo
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def to_module(spec):
+    """oracle transformer spec -> tfep_b200 transformer module."""
+    from tfep_b200.nn import transformers as T
+    if isinstance(spec, fo.Affine):
+        return T.AffineTransformer()
+    if isinstance(spec, fo.Spline):
+        return T.NeuralSplineTransformer(
+            x0=spec.x0.clone(), xf=spec.xf.clone(), n_bins=spec.n_bins, y0=spec.y0.clone(), yf=spec.yf.clone(),
+            circular=spec.circular, identity_boundary_slopes=spec.identity_boundary_slopes,
+            learn_lower_bound=spec.learn_lower_bound, learn_upper_bound=spec.learn_upper_bound,
+            min_bin_size=spec.min_bin_size, min_slope=spec.min_slope)
+    if isinstance(spec, fo.SOS):
+        return T.SOSPolynomialTransformer(spec.n_polynomials)
+    if isinstance(spec, fo.Moebius):
+        return T.MoebiusTransformer(spec.dimension, max_radius=spec.max_radius, unit_sphere=spec.unit_sphere)
+    if isinstance(spec, fo.Mixed):
+        return T.MixedTransformer([to_module(t) for t in spec.transformers], [i.tolist() for i in spec.indices])
+    raise TypeError(spec)
+
+
+def to_maf(case, state_dict, device=None, dtype=None):
+    """oracle MAF case (+ its seeded state) -> tfep_b200.nn.flows.MAF with the same parameters."""
+    from tfep_b200.nn.flows import MAF
+    maf = MAF(degrees_in=case['degrees_in'], transformer=to_module(case['spec']), hidden_layers=case['hidden_layers'],
+              weight_norm=case['weight_norm'], initialize_identity=False)
+    if dtype is not None:
+        maf = maf.to(dtype)
+    missing, unexpected = maf.load_state_dict(state_dict, strict=False)
+    assert not unexpected, unexpected
+    assert not [k for k in missing if 'weight' in k or 'bias' in k], missing
+    if device is not None:
+        maf = maf.to(device)
+    return maf
+
+
+def cfg_flow_modules(name, device, n_layers=None, D=None, dtype=torch.float32):
+    """BASELINE.json configuration as (tfep_b200 SequentialFlow on `device`, [oracle flows])."""
+    from tfep_b200.nn.flows import SequentialFlow
+    flows = cases.cfg_flow(name, torch.float32, n_layers=n_layers, D=D)
+    mafs = []
+    for m, sd in flows:
+        case = dict(degrees_in=m.degrees_in, spec=m.transformer, hidden_layers=2, weight_norm=True)
+        mafs.append(to_maf(case, {k: v.to(dtype) for k, v in sd.items()}, dtype=dtype))
+    return SequentialFlow(*mafs).to(device), flows
+
+
+def rel_err(a, b):
+    """max |a - b| / (1 + |b|) over all elements, in double."""
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float(((a - b).abs() / (1 + b.abs())).max()) if a.numel() else 0.0

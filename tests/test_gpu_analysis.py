@@ -1,0 +1,110 @@
+"""Estimator / bootstrap kernels against the oracle, the golden vectors and the reference's index stream."""
+
+import functools
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden, rel_err
+from oracle import analysis_oracle as ao
+from oracle import cases
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def test_fep_estimator_against_golden_and_oracle():
+    from tfep_b200.analysis import fep_estimator
+    g = golden('analysis.npz')
+    w = cases.normal((20000,), 3)
+    assert rel_err(fep_estimator(w.to(DEV)), g['w_seed3_n20000/fep']) < 1e-6
+    assert rel_err(fep_estimator(w.to(DEV), kT=2.5), g['w_seed3_n20000/fep_kT2.5']) < 1e-6
+    assert rel_err(fep_estimator(w.double().to(DEV)), g['w_seed3_n20000/fep_f64']) < 1e-12
+    wb = torch.stack([w, cases.normal((20000,), 4) * 0.3], dim=1)
+    assert rel_err(fep_estimator(wb.to(DEV)), g['biased/fep']) < 1e-6
+    for n in (1, 2, 31, 1000, 1 << 20):
+        v = cases.normal((n,), 100 + n) * 3
+        assert rel_err(fep_estimator(v.to(DEV)), ao.fep_estimator(v.double()).float()) < 2e-6, n
+    big = cases.normal((5, 3000), 7)
+    assert rel_err(fep_estimator(big.to(DEV), vectorized=True), ao.fep_estimator(big, vectorized=True)) < 1e-6
+    wide = torch.tensor([-400.0, 0.0, 300.0, -1e4])        # needs the max-shift: exp would overflow
+    assert rel_err(fep_estimator(wide.to(DEV)), ao.fep_estimator(wide.double()).float()) < 1e-6
+
+
+def test_known_answer_gaussian_work():
+    """Work ~ N(0,1) => Delta f = -1/2 (reference tests/analysis/test_bootstrap.py:178-190)."""
+    from tfep_b200.analysis import fep_estimator
+    w = cases.normal((4000000,), 17).to(DEV)
+    assert abs(float(fep_estimator(w)) + 0.5) < 5e-3
+
+
+def test_resample_indices_bit_exact():
+    from tfep_b200 import _ops
+    g = golden('analysis.npz')
+    for seed in (0, 1, 12345):
+        st = _ops.mt19937_seed(seed).to(DEV)
+        a = _ops.mt19937_indices(st, 3 * 700, 20000).cpu().numpy().reshape(3, 700)
+        assert np.array_equal(a, g[f'randint/seed{seed}_high20000'])
+        b = _ops.mt19937_indices(st, 2 * 700, 100000000).cpu().numpy().reshape(2, 700)      # continues the stream
+        assert np.array_equal(b, g[f'randint/seed{seed}_high1e8_cont'])
+    st = _ops.mt19937_seed(99).to(DEV)
+    n = 1000003
+    got = torch.cat([_ops.mt19937_indices(st, c, n) for c in (1, 623, 624, 625, 5000, 1248, 77777)]).cpu().numpy()
+    assert np.array_equal(got, ao.resample_indices(99, 1, len(got), n)[0])
+
+
+def test_generator_state_round_trip():
+    """The caller's torch.Generator is advanced exactly as the reference's torch.randint calls would."""
+    from tfep_b200.analysis import bootstrap, fep_estimator
+    w = cases.normal((5000,), 3).to(DEV)
+    g1, g2 = torch.Generator().manual_seed(5), torch.Generator().manual_seed(5)
+    bootstrap(w, fep_estimator, n_resamples=7, batch=3, generator=g1)
+    ao.bootstrap(w.cpu(), ao.fep_estimator, n_resamples=7, batch=3, generator=g2)
+    assert torch.equal(torch.randint(0, 1 << 30, (50,), generator=g1), torch.randint(0, 1 << 30, (50,), generator=g2))
+
+
+def test_bootstrap_against_golden():
+    from tfep_b200.analysis import bootstrap, fep_estimator
+    from tfep_b200.analysis.bootstrap import _bootstrap_statistics
+    g = golden('analysis.npz')
+    w = cases.normal((20000,), 3).to(DEV)
+    stats = _bootstrap_statistics(w, fep_estimator, 40, 20000, False, 11, torch.Generator().manual_seed(1), 'mt19937')
+    assert rel_err(stats, g['bootstrap/stats_seed1_r40']) < 2e-6
+    r = bootstrap(w, fep_estimator, n_resamples=40, batch=9, generator=torch.Generator().manual_seed(1))
+    got = torch.stack([r['confidence_interval']['low'], r['confidence_interval']['high'], r['standard_deviation'],
+                       r['mean'], r['median']])
+    assert rel_err(got, g['bootstrap/percentile']) < 2e-6
+    r = bootstrap(w, lambda d, vectorized=False: d.mean(dim=-1), n_resamples=40, batch=7, method='basic',
+                  generator=torch.Generator().manual_seed(1))
+    got = torch.stack([r['confidence_interval']['low'].reshape(()), r['confidence_interval']['high'].reshape(()),
+                       r['standard_deviation'], r['mean'], r['median']])
+    assert rel_err(got, g['bootstrap/basic']) < 2e-6
+    r = bootstrap(w, fep_estimator, n_resamples=30, bootstrap_sample_size=[100, 5000], take_first_only=True,
+                  generator=torch.Generator().manual_seed(2))
+    got = torch.stack([torch.stack([x['confidence_interval']['low'], x['confidence_interval']['high'],
+                                    x['standard_deviation'], x['mean'], x['median']]) for x in r])
+    assert rel_err(got, g['bootstrap/sizes_take_first']) < 5e-6
+    kt = bootstrap(w, functools.partial(fep_estimator, kT=2.0), n_resamples=10, generator=torch.Generator().manual_seed(3))
+    kt_o = ao.bootstrap(w.cpu(), functools.partial(ao.fep_estimator, kT=2.0), n_resamples=10,
+                        generator=torch.Generator().manual_seed(3))
+    assert rel_err(kt['mean'], kt_o['mean']) < 2e-6
+
+
+def test_bootstrap_biased_data_and_errors():
+    from tfep_b200.analysis import bootstrap, fep_estimator
+    w = torch.stack([cases.normal((3000,), 3), cases.normal((3000,), 4) * 0.3], dim=1)
+    a = bootstrap(w.to(DEV), fep_estimator, n_resamples=12, batch=5, generator=torch.Generator().manual_seed(2))
+    b = ao.bootstrap(w, ao.fep_estimator, n_resamples=12, batch=5, generator=torch.Generator().manual_seed(2))
+    assert rel_err(a['mean'], b['mean']) < 2e-6 and rel_err(a['standard_deviation'], b['standard_deviation']) < 1e-4
+    with pytest.raises(ValueError, match='Bayesian bootstrapping does not support'):
+        bootstrap(w.to(DEV), fep_estimator, bayesian=True, generator=torch.Generator())
+
+
+def test_philox_bootstrap_is_statistically_equivalent():
+    from tfep_b200.analysis import bootstrap, fep_estimator
+    w = cases.normal((200000,), 5).to(DEV)
+    a = bootstrap(w, fep_estimator, n_resamples=300, generator=torch.Generator().manual_seed(1))
+    b = bootstrap(w, fep_estimator, n_resamples=300, generator=torch.Generator().manual_seed(1), rng='philox')
+    assert abs(float(a['mean']) - float(b['mean'])) < 3 * float(a['standard_deviation']) / 300 ** 0.5 + 1e-4
+    assert 0.7 < float(b['standard_deviation']) / float(a['standard_deviation']) < 1.4

@@ -1,0 +1,181 @@
+"""MAF forward / inverse / gradients on the GPU against the reference's golden vectors and the oracle."""
+
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import cfg_flow_modules, golden, rel_err, to_maf
+from oracle import cases
+from oracle import flow_oracle as fo
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+TOL = {'f32': 1e-5, 'f64': 1e-10}
+DT = {'f32': torch.float32, 'f64': torch.float64}
+
+
+@pytest.fixture(params=['f32', 'f64'])
+def prec(request):
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(DT[request.param])
+    yield request.param
+    torch.set_default_dtype(old)
+
+
+def test_forward_and_inverse_against_golden(prec):
+    g = golden(f'maf_{prec}.npz')
+    for name, case in cases.maf_cases(DT[prec]).items():
+        _, sd = cases.build_oracle(case, DT[prec])
+        maf = to_maf(case, sd, DEV, DT[prec])
+        with torch.no_grad():
+            y, ld = maf(case['x'].to(DEV))
+        assert rel_err(y, g[f'{name}/y']) < 2 * TOL[prec], name
+        assert rel_err(ld, g[f'{name}/ld']) < 2 * TOL[prec], name
+        if not case['invertible']:
+            with pytest.raises(NotImplementedError):
+                maf.inverse(y)
+            continue
+        with torch.no_grad():
+            xi, ldi = maf.inverse(torch.from_numpy(g[f'{name}/y']).to(DEV))
+        assert rel_err(xi, g[f'{name}/xinv']) < 20 * TOL[prec], name
+        assert rel_err(ldi, g[f'{name}/ldinv']) < 20 * TOL[prec], name
+
+
+def test_generic_autoregressive_flow_matches_packed_path():
+    """AutoregressiveFlow.forward/inverse (reference layout, one conditioner pass per degree group) and
+    the packed MAF path (single sweep) are the same map."""
+    from tfep_b200.nn.flows.autoregressive import AutoregressiveFlow
+    for name, case in cases.maf_cases(torch.float64).items():
+        _, sd = cases.build_oracle(case, torch.float64)
+        maf = to_maf(case, sd, DEV, torch.float64)
+        x = case['x'].to(DEV)
+        with torch.no_grad():
+            y, ld = maf(x)
+            y2, ld2 = AutoregressiveFlow.forward(maf, x)
+            assert rel_err(y2, y) < 1e-12 and rel_err(ld2, ld) < 1e-12, name
+            if case['invertible']:
+                xi, ldi = maf.inverse(y)
+                xi2, ldi2 = AutoregressiveFlow.inverse(maf, y)
+                assert rel_err(xi2, xi) < 1e-10 and rel_err(ldi2, ldi) < 1e-10, name
+
+
+def test_round_trip_and_conditioning_untouched(prec):
+    """inverse(forward(x)) == x, log-dets cancel, conditioning features pass through
+    (reference tests/nn/flows/test_maf.py:226-295)."""
+    for name, case in cases.maf_cases(DT[prec]).items():
+        if not case['invertible']:
+            continue
+        _, sd = cases.build_oracle(case, DT[prec])
+        maf = to_maf(case, sd, DEV, DT[prec])
+        x = case['x'].to(DEV)
+        with torch.no_grad():
+            y, ld = maf(x)
+            xi, ldi = maf.inverse(y)
+        fixed = (case['degrees_in'] == -1).nonzero().flatten().to(DEV)
+        assert torch.equal(y[:, fixed], x[:, fixed]), name
+        spec = case['spec']
+        if isinstance(spec, (fo.Spline, fo.Mixed)):
+            continue                                     # periodic features come back modulo the period
+        assert rel_err(xi, x) < 100 * TOL[prec], name
+        assert rel_err(ld + ldi, torch.zeros_like(ld)) < 100 * TOL[prec], name
+
+
+def test_gradients_against_reference_autograd(prec):
+    """d loss / d x and d loss / d (g, v, bias) vs PyTorch autograd through the real reference."""
+    g = golden(f'maf_{prec}.npz')
+    dtype = DT[prec]
+    for name, case in cases.maf_cases(dtype).items():
+        _, sd = cases.build_oracle(case, dtype)
+        maf = to_maf(case, sd, DEV, dtype)
+        x = case['x'].to(DEV).requires_grad_(True)
+        y, ld = maf(x)
+        cy, cl = cases.normal(tuple(y.shape), 78, dtype).to(DEV), cases.normal(tuple(ld.shape), 79, dtype).to(DEV)
+        loss = (y * cy).sum() + ((ld * cl).sum() if ld.requires_grad else 0.0)
+        loss.backward()
+        tol = 30 * TOL[prec]
+        assert rel_err(x.grad, g[f'{name}/gx']) < tol, name
+        for k, p in maf.named_parameters():
+            ref = g[f'{name}/grad/{k}']
+            scale = 1 + float(np.abs(ref).max())
+            assert float((p.grad.cpu().double() - torch.from_numpy(ref).double()).abs().max()) / scale < tol, (name, k)
+
+
+def test_autoregressive_property(prec):
+    """y_i depends on x_j only if degree(j) < degree(i), or j == i (reference tests/nn/__init__.py:25-96)."""
+    for name in ('spline_desc_cond', 'moebius_d2_cond', 'repeated_degrees', 'mixed_splines'):
+        case = cases.maf_cases(DT[prec])[name]
+        _, sd = cases.build_oracle(case, DT[prec])
+        maf = to_maf(case, sd, DEV, DT[prec])
+        x = case['x'].to(DEV).requires_grad_(True)
+        y, _ = maf(x)
+        deg = case['degrees_in']
+        dim = case['spec'].dimension if isinstance(case['spec'], fo.Moebius) else 1
+        for i in range(y.shape[1]):
+            gi, = torch.autograd.grad(y[:, i].sum(), x, retain_graph=True)
+            dep = (gi.abs().sum(0) > 0).cpu()
+            for j in range(y.shape[1]):
+                same_block = dim > 1 and deg[i] == deg[j] and deg[i] != -1 and abs(i - j) < dim
+                allowed = (deg[j] < deg[i] and deg[i] != -1) or j == i or same_block
+                assert allowed or not bool(dep[j]), (name, i, j)
+
+
+def test_identity_initialisation_is_the_identity_map():
+    from tfep_b200.nn.conditioners import generate_degrees
+    from tfep_b200.nn.flows import MAF
+    from tfep_b200.nn.transformers import (AffineTransformer, MoebiusTransformer, NeuralSplineTransformer,
+                                           SOSPolynomialTransformer)
+    x = cases.uniform((32, 6), 3, -0.9, 0.9).to(DEV)
+    for t, rep in ((AffineTransformer(), 1), (SOSPolynomialTransformer(2), 1), (SOSPolynomialTransformer(3), 1),
+                   (MoebiusTransformer(2), 2),
+                   (NeuralSplineTransformer(torch.full((6,), -1.), torch.full((6,), 1.), 5), 1),
+                   (NeuralSplineTransformer(torch.full((6,), -1.), torch.full((6,), 1.), 5, circular=True), 1)):
+        for order in ('ascending', 'descending'):
+            maf = MAF(generate_degrees(6, order=order, repeats=rep), transformer=t).to(DEV)
+            with torch.no_grad():
+                y, ld = maf(x)
+            assert rel_err(y, x) < 1e-5 and float(ld.abs().max()) < 1e-4, (type(t).__name__, order)
+
+
+def test_config_slices_fp32_parity_and_fp64_accuracy():
+    """BASELINE.json configurations (reduced batch; cfg3 / cfg5 at reduced D): the fp32 path is within 1e-5
+    (relative) of the reference's fp32 CPU result; the error against the fp64 reference is reported too."""
+    g = golden('cfg_slices.npz')
+    for cfg, nl, B, D in (('cfg1', 2, 64, None), ('cfg2', 4, 64, None), ('cfg3', 6, 32, 30), ('cfg5', 2, 32, 24)):
+        seq, _ = cfg_flow_modules(cfg, DEV, n_layers=nl, D=D)
+        x = torch.from_numpy(g[f'{cfg}/x']).to(DEV)
+        with torch.no_grad():
+            y, ld = seq(x)
+        assert rel_err(y, g[f'{cfg}/f32/y']) < 1e-5, cfg
+        assert rel_err(ld, g[f'{cfg}/f32/ld']) < 1e-5 * nl, cfg
+        assert rel_err(y, g[f'{cfg}/f64/y']) < 1e-4 and rel_err(ld, g[f'{cfg}/f64/ld']) < 1e-4, cfg
+        if cfg != 'cfg3':
+            with torch.no_grad():
+                xi, ldi = seq.inverse(torch.from_numpy(g[f'{cfg}/f32/y']).to(DEV))
+            assert rel_err(ldi, g[f'{cfg}/f32/ldinv']) < 2e-4, cfg
+            if cfg != 'cfg2':
+                assert rel_err(xi, g[f'{cfg}/f32/xinv']) < 2e-4, cfg
+            else:
+                d = (xi.cpu() - torch.from_numpy(g[f'{cfg}/f32/xinv'])).abs()
+                assert float(torch.minimum(d, (2 * math.pi - d).abs()).max()) < 2e-4
+
+
+def test_headline_config_full_size_properties():
+    """cfg2 at the BASELINE.json batch (65536): size-independent properties instead of an oracle run --
+    determinism, batch-slicing invariance, round trip modulo the period and log-det cancellation."""
+    seq, _ = cfg_flow_modules('cfg2', DEV)
+    x = cases.cfg_input('cfg2', 65536).to(DEV)
+    with torch.no_grad():
+        y, ld = seq(x)
+        y2, ld2 = seq(x)
+        assert torch.equal(y, y2) and torch.equal(ld, ld2)
+        ys, lds = seq(x[1000:1777])
+        assert torch.equal(ys, y[1000:1777]) and torch.equal(lds, ld[1000:1777])
+        assert bool(torch.isfinite(y).all()) and bool(torch.isfinite(ld).all())
+        assert float(y.min()) >= -math.pi - 1e-5 and float(y.max()) <= math.pi + 1e-5
+        sub = slice(0, 4096)
+        xi, ldi = seq.inverse(y[sub])
+        d = (xi - x[sub]).abs()
+        assert float(torch.minimum(d, (2 * math.pi - d).abs()).max()) < 2e-3
+        assert float((ld[sub] + ldi).abs().max()) < 5e-3

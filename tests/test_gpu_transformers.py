@@ -1,0 +1,127 @@
+"""CUDA transformer kernels (through the C ABI) against the oracle and the reference's golden vectors."""
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden, rel_err, to_module
+from oracle import cases
+from oracle import flow_oracle as fo
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+TOL = {'f32': 1e-5, 'f64': 1e-10}        # north_star: 1e-5 relative for the fp32 path
+DT = {'f32': torch.float32, 'f64': torch.float64}
+
+
+@pytest.fixture(params=['f32', 'f64'])
+def prec(request):
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(DT[request.param])
+    yield request.param
+    torch.set_default_dtype(old)
+
+
+def test_forward_inverse_against_golden(prec):
+    g = golden(f'transformers_{prec}.npz')
+    for name, (spec, n, x, par) in cases.transformer_cases(DT[prec]).items():
+        mod = to_module(spec).to(DEV)
+        y, ld = mod(x.to(DEV), par.to(DEV))
+        assert rel_err(y, g[f'{name}/y']) < TOL[prec], name
+        assert rel_err(ld, g[f'{name}/ld']) < TOL[prec], name
+        if isinstance(spec, fo.SOS):
+            with pytest.raises(NotImplementedError):
+                mod.inverse(y, par.to(DEV))
+            continue
+        xi, ldi = mod.inverse(torch.from_numpy(g[f'{name}/y']).to(DEV), par.to(DEV))
+        assert rel_err(xi, g[f'{name}/xinv']) < 5 * TOL[prec], name
+        assert rel_err(ldi, g[f'{name}/ldinv']) < 5 * TOL[prec], name
+
+
+def test_round_trip(prec):
+    for name, (spec, n, x, par) in cases.transformer_cases(DT[prec]).items():
+        if isinstance(spec, fo.SOS):
+            continue
+        mod = to_module(spec).to(DEV)
+        y, ld = mod(x.to(DEV), par.to(DEV))
+        xi, ldi = mod.inverse(y, par.to(DEV))
+        xx = x
+        if isinstance(spec, fo.Spline) and spec.circular:      # periodic: compare modulo the period
+            period = (spec.xf - spec.x0)
+            d = (xi.cpu() - x).abs()
+            assert float(torch.minimum(d, (period - d).abs()).max()) < 50 * TOL[prec], name
+        elif not isinstance(spec, fo.Mixed):
+            assert rel_err(xi, xx) < 50 * TOL[prec], name
+        assert rel_err(ld + ldi, torch.zeros_like(ld)) < 50 * TOL[prec], name
+
+
+def test_spline_bin_indices(prec):
+    """fp64: every index equals the reference's.  fp32: equal except within a few ulp of a knot."""
+    g = golden(f'transformers_{prec}.npz')
+    for name, (spec, n, x, par) in cases.transformer_cases(DT[prec]).items():
+        if not isinstance(spec, fo.Spline):
+            continue
+        bins = to_module(spec).to(DEV).bin_indices(x.to(DEV), par.to(DEV)).cpu().numpy()
+        ref = g[f'{name}/bins']
+        if prec == 'f64':
+            assert np.array_equal(bins, ref), name
+        else:
+            assert (bins != ref).mean() < 0.02, name
+
+
+def test_vjp_against_oracle_autograd(prec):
+    dtype = DT[prec]
+    for name, (spec, n, x, par) in cases.transformer_cases(dtype).items():
+        gy = cases.normal(tuple(x.shape), 91, dtype)
+        gl = cases.normal((x.shape[0],), 92, dtype)
+        xg, pg = x.clone().requires_grad_(True), par.clone().requires_grad_(True)
+        yy, ll = spec.forward(xg, pg)
+        if isinstance(spec, fo.SOS):
+            gx_o, gp_o = spec.vjp(x, par, gy)
+        else:
+            ((yy * gy).sum() + (ll * gl).sum()).backward()
+            gx_o, gp_o = xg.grad, pg.grad
+        xd, pd = x.to(DEV).requires_grad_(True), par.to(DEV).requires_grad_(True)
+        y, ld = to_module(spec).to(DEV)(xd, pd)
+        loss = (y * gy.to(DEV)).sum()
+        if ld.requires_grad:
+            loss = loss + (ld * gl.to(DEV)).sum()
+        else:
+            assert isinstance(spec, fo.SOS)          # the reference's SOS log-det carries no gradient
+        loss.backward()
+        scale = float(1 + gp_o.abs().max())
+        assert rel_err(xd.grad, gx_o) < 20 * TOL[prec], name
+        assert float((pd.grad.cpu() - gp_o).abs().max()) / scale < 20 * TOL[prec], name
+
+
+def test_sos_backward_matches_reference_golden(prec):
+    g = golden(f'transformers_{prec}.npz')
+    for name in ('sos2', 'sos3'):
+        spec, n, x, par = cases.transformer_cases(DT[prec])[name]
+        xd, pd = x.to(DEV).requires_grad_(True), par.to(DEV).requires_grad_(True)
+        y, _ = to_module(spec).to(DEV)(xd, pd)
+        (y * torch.from_numpy(g[f'{name}/gy']).to(DEV)).sum().backward()
+        assert rel_err(xd.grad, g[f'{name}/gx']) < TOL[prec] and rel_err(pd.grad, g[f'{name}/gpar']) < TOL[prec]
+
+
+def test_ragged_and_empty_batches():
+    spec, n, x, par = cases.transformer_cases(torch.float32)['spline_k8']
+    mod = to_module(spec).to(DEV)
+    for B in (0, 1, 7, 24):
+        y, ld = mod(x[:B].to(DEV), par[:B].to(DEV))
+        y_o, ld_o = spec.forward(x[:B], par[:B])
+        assert y.shape == (B, n) and ld.shape == (B,)
+        assert rel_err(y, y_o) < 1e-5 and rel_err(ld, ld_o) < 1e-5
+
+
+def test_functional_api():
+    from tfep_b200.nn.transformers import affine_transformer, affine_transformer_inverse, moebius_transformer
+    x, s, a = (cases.normal((9, 5), k).to(DEV) for k in (1, 2, 3))
+    y, ld = affine_transformer(x, s, a)
+    assert rel_err(y, x.cpu() * torch.exp(a.cpu()) + s.cpu()) < 1e-6 and rel_err(ld, a.cpu().sum(1)) < 1e-6
+    xi, _ = affine_transformer_inverse(y, s, a)
+    assert rel_err(xi, x) < 1e-5
+    xv, wv = cases.normal((4, 3, 3), 5), cases.normal((4, 3, 3), 6)
+    y, ld = moebius_transformer(xv.to(DEV), wv.to(DEV))
+    y_o, ld_o = fo.Moebius(3).forward(xv.reshape(4, 9), wv.reshape(4, 9))
+    assert rel_err(y.reshape(4, 9), y_o) < 1e-5 and rel_err(ld, ld_o) < 1e-5

@@ -1,0 +1,201 @@
+"""Host-side logic of the drop-in modules: construction, degrees, masks, state_dict layout, packing.
+
+No kernels run here (no GPU): these tests cover what the reference's own constructor-level tests cover
+(tfep/tests/nn/conditioners/test_made.py:31-119, tests/nn/flows/test_maf.py) plus the packing plan.
+"""
+
+import json
+import os
+
+import pytest
+import torch
+
+from helpers import GOLDEN, to_maf, to_module
+from oracle import cases
+from oracle import flow_oracle as fo
+from tfep_b200._lib import TfepB200Error
+from tfep_b200._pack import MadePlan
+from tfep_b200.nn import masked
+from tfep_b200.nn.conditioners import MADE, generate_degrees
+from tfep_b200.nn.flows import MAF, SequentialFlow
+from tfep_b200.nn.transformers import (AffineTransformer, MixedTransformer, MoebiusTransformer,
+                                       NeuralSplineTransformer, SOSPolynomialTransformer)
+
+TAB = json.load(open(os.path.join(GOLDEN, 'degrees.json')))
+
+
+def test_generate_degrees_known_answers():
+    for row in TAB['generate_degrees']:
+        assert generate_degrees(row['n_features'], **row['kwargs']).tolist() == row['expected']
+    with pytest.raises(ValueError, match='Accepted string values for'):
+        generate_degrees(n_features=2, order='wrong')
+
+
+def test_hidden_degrees_masks_and_parameter_count():
+    for row in TAB['hidden_degrees']:
+        din, dout = torch.tensor(row['degrees_in']), torch.tensor(row['degrees_out'])
+        got = MADE._get_degrees_hidden(din, dout, row['hidden_layers'])
+        assert [h.tolist() for h in got] == row['expected']
+        made = MADE(din, dout, row['hidden_layers'])
+        assert [int(l.mask.sum()) for l in made.layers[::2]] == row['mask_sums']
+        assert int(made.n_parameters()) == row['n_parameters']
+        assert made.dimension_in == len(din) and made.dimension_out == len(dout)
+        assert made.dimensions_hidden.tolist() == [len(h) for h in row['expected']]
+
+
+def test_made_errors():
+    with pytest.raises(ValueError, match='is too small for the number of input features'):
+        MADE(torch.tensor([0, 1, 2, 3]), torch.tensor([0, 1, 2, 3]), hidden_layers=[2])
+    with pytest.raises(ValueError, match='nodes with degrees that will be ignored'):
+        MADE(torch.tensor([0, 1, 2]), torch.tensor([0, 1, 2]), hidden_layers=[[0, 2, 1]])
+
+
+def test_config_shapes_match_reference():
+    """Layer widths and mask non-zeros of the BASELINE.json configurations."""
+    mk = {
+        'cfg1': (66, AffineTransformer(), 1),
+        'cfg2': (66, NeuralSplineTransformer(torch.zeros(66), torch.ones(66), 8, circular=True), 1),
+        'cfg3_sos': (300, SOSPolynomialTransformer(2), 1),
+        'cfg3_moebius': (300, MoebiusTransformer(3), 3),
+    }
+    for name, (D, t, rep) in mk.items():
+        maf = MAF(generate_degrees(D, repeats=rep), transformer=t)
+        lin = list(maf._conditioner.layers[::2])
+        assert [lin[0].in_features] + [l.out_features for l in lin] == TAB['config_shapes'][name]['dims']
+        assert [int(l.mask.sum()) for l in lin] == TAB['config_shapes'][name]['nnz']
+        # the packed plan keeps exactly the reference's non-zeros
+        assert maf._pack()['plan'].nnz == TAB['config_shapes'][name]['nnz']
+
+
+def test_state_dict_keys_are_the_reference_ones():
+    maf = MAF(generate_degrees(6), NeuralSplineTransformer(torch.zeros(6), torch.ones(6), 4, circular=True))
+    keys = set(maf.state_dict().keys())
+    expected = {'_transformer_indices', '_inverse_masks', '_fixed_indices', '_conditioner_indices'}
+    expected |= {f'_conditioner.layers.{i}.{k}' for i in (0, 2, 4) for k in ('bias', 'weight_g', 'weight_v', 'mask')}
+    expected |= {f'_transformer.{k}' for k in ('x0', 'xf', 'n_bins', '_y0', '_yf', '_circular',
+                                               '_identity_boundary_slopes', '_learn_lower_bound',
+                                               '_learn_upper_bound', '_min_bin_size', '_min_slope')}
+    assert keys == expected
+    nown = MAF(generate_degrees(4), weight_norm=False)
+    assert '_conditioner.layers.0.weight' in nown.state_dict()
+
+
+def test_maf_degree_validation_and_buffers():
+    with pytest.raises(ValueError, match='degrees_in must assume consecutive values'):
+        MAF(degrees_in=[0, 2, 3])
+    with pytest.raises(ValueError, match='degrees_in must assume consecutive values'):
+        MAF(degrees_in=[1, 2])
+    maf = MAF(degrees_in=[-1, 1, 0, -1, 1])
+    assert maf._fixed_indices.tolist() == [0, 3] and maf._transformer_indices.tolist() == [1, 2, 4]
+    assert maf._inverse_masks.tolist() == [[False, False, True, False, False], [False, True, False, False, True]]
+    assert maf.has_fixed_indices
+    full = MAF(degrees_in=[0, 1, 2])
+    assert len(full._transformer_indices) == 0 and not full.has_fixed_indices
+
+
+def test_identity_initialisation_parameters():
+    """initialize_identity zeroes the last layer's g and loads the identity parameters in its bias
+    (reference autoregressive.py:133-137, made.py:358-364)."""
+    for t in (AffineTransformer(), SOSPolynomialTransformer(3), MoebiusTransformer(2),
+              NeuralSplineTransformer(torch.full((4,), -1.), torch.full((4,), 1.), 5)):
+        maf = MAF(generate_degrees(4, repeats=2 if isinstance(t, MoebiusTransformer) else 1), transformer=t)
+        last = maf._conditioner.layers[-1]
+        assert float(last.weight_g.abs().max()) == 0.0
+        assert torch.equal(last.bias.data, t.get_identity_parameters(4).to(last.bias))
+
+
+def test_transformer_host_api_matches_oracle():
+    for name, (spec, n, x, par) in cases.transformer_cases(torch.float32).items():
+        mod = to_module(spec)
+        assert torch.equal(mod.get_identity_parameters(n), spec.identity_params(n)), name
+        deg = fo.gen_degrees(n, repeats=spec.dimension) if isinstance(spec, fo.Moebius) else fo.gen_degrees(n)
+        assert torch.equal(mod.get_degrees_out(deg), spec.degrees_out(deg)), name
+        parts = mod._parts(n)
+        cols = torch.cat([p.ref_columns().flatten() for p in parts]).sort().values
+        assert torch.equal(cols, torch.arange(len(spec.identity_params(n)))), name
+
+
+def test_spline_constructor_errors():
+    x0, xf = torch.zeros(2), torch.ones(2)
+    with pytest.raises(ValueError, match='circular spline with learnable limits'):
+        NeuralSplineTransformer(x0, xf, 3, circular=True, learn_lower_bound=True)
+    with pytest.raises(ValueError, match='minimum bin size'):
+        NeuralSplineTransformer(x0, xf, 3, min_bin_size=0.0)
+    with pytest.raises(ValueError, match='minimum slope'):
+        NeuralSplineTransformer(x0, xf, 3, min_slope=1.0)
+    assert NeuralSplineTransformer(x0, xf, 8).n_parameters_per_feature == 25
+    assert NeuralSplineTransformer(x0, xf, 8, circular=True).n_parameters_per_feature == 25
+    assert NeuralSplineTransformer(x0, xf, 8, identity_boundary_slopes=True).n_parameters_per_feature == 23
+    assert NeuralSplineTransformer(x0, xf, 8, circular=True, identity_boundary_slopes=True).n_parameters_per_feature == 24
+    assert NeuralSplineTransformer(x0, xf, 8, learn_lower_bound=True, learn_upper_bound=True).n_parameters_per_feature == 27
+    with pytest.raises(ValueError, match='strictly greater than 1'):
+        SOSPolynomialTransformer(1)
+    with pytest.raises(ValueError, match='greater than 1'):
+        MixedTransformer([AffineTransformer()], [[0]])
+
+
+def test_effective_weight_matches_oracle_and_masks_gradients():
+    torch.manual_seed(0)
+    mask = (torch.rand(7, 5) > 0.4).float()
+    mask[2] = 0.0                                     # a fully masked row: 0/0 in the naive formula
+    v = (torch.randn(7, 5) * mask).requires_grad_(True)
+    g = torch.rand(7, 1).requires_grad_(True)
+    w = masked.effective_weight(v, g, mask)
+    assert torch.allclose(w, fo.effective_weight(v.detach(), g.detach(), mask), atol=1e-7)
+    (w * torch.randn(7, 5)).sum().backward()
+    assert torch.isfinite(v.grad).all() and torch.isfinite(g.grad).all()
+    assert float(v.grad[mask == 0].abs().max()) == 0.0 and float(g.grad[2].abs()) == 0.0
+
+
+def test_packing_plan_is_a_relabelling():
+    """Packed weights are a permutation of the reference ones and the skipped ranges hold only zeros."""
+    for name, case in cases.maf_cases(torch.float32).items():
+        oracle, sd = cases.build_oracle(case)
+        maf = to_maf(case, sd)
+        pk = maf._pack()
+        plan = pk['plan']
+        ws, bs = zip(*maf._conditioner.effective_weights())
+        pw, pb = plan.pack([w.detach() for w in ws], [b.detach() for b in bs])
+        for l, (w_ref, b_ref) in enumerate(oracle.layers):
+            assert torch.allclose(ws[l].detach(), w_ref, atol=1e-6), name
+            back = torch.empty_like(w_ref)
+            rows, cols = plan.perms[l + 1], plan.perms[l]
+            back[rows[:, None], cols[None, :]] = pw[l]
+            assert torch.allclose(back, w_ref, atol=1e-6), name
+            for t, (kb, ke) in enumerate(plan.k_ranges[l].tolist()):
+                tile = pw[l][t * 64:(t + 1) * 64]
+                assert float(tile[:, :kb].abs().sum()) == 0.0 and float(tile[:, ke:].abs().sum()) == 0.0, name
+            for t, (nb, ne) in enumerate(plan.n_ranges[l].tolist()):
+                tile = pw[l][:, t * 64:(t + 1) * 64]
+                assert float(tile[:nb].abs().sum()) == 0.0 and float(tile[ne:].abs().sum()) == 0.0, name
+        # every degree group owns a contiguous block of packed output rows; together they tile the output
+        pos = 0
+        for grp in pk['groups']:
+            assert grp['rows'][0] == pos
+            pos = grp['rows'][1]
+        assert pos == maf._conditioner.dimension_out
+
+
+def test_staircase_skips_about_half_of_the_headline_config():
+    maf = MAF(generate_degrees(66), NeuralSplineTransformer(torch.zeros(66), torch.ones(66), 8, circular=True))
+    plan = maf._pack()['plan']
+    dense = [66 * 328, 328 * 328, 328 * 1650]
+    scheduled = [sum((ke - kb) * min(64, n - 64 * t) for t, (kb, ke) in enumerate(r.tolist()))
+                 for r, n in zip(plan.k_ranges, (328, 328, 1650))]
+    assert sum(scheduled) < 0.62 * sum(dense)
+    assert plan.masked_macs == 338277
+
+
+def test_no_cpu_fallback():
+    """The product path refuses CPU tensors loudly instead of silently computing elsewhere."""
+    maf = MAF(generate_degrees(4), initialize_identity=False)
+    with pytest.raises(TfepB200Error, match='no CPU fallback'):
+        maf(torch.randn(3, 4))
+    from tfep_b200.analysis import fep_estimator
+    with pytest.raises(TfepB200Error, match='no CPU fallback'):
+        fep_estimator(torch.randn(10))
+
+
+def test_sequential_flow_container():
+    seq = SequentialFlow(MAF(generate_degrees(3)), MAF(generate_degrees(3, order='descending')))
+    assert int(seq.n_parameters()) == sum(int(f.n_parameters()) for f in seq)

@@ -1,0 +1,145 @@
+"""ctypes binding of the C ABI declared in include/tfep_b200.h.
+
+There is no CPU or PyTorch fallback: if the CUDA library is missing, or a tensor is not on a CUDA
+device, the calls below raise.  The library is built in-tree by ``tfep_b200._build.build()``.
+"""
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_int64, c_uint32, c_uint64, c_void_p
+
+import torch
+
+from . import _build
+
+F32, F64 = 0, 1
+ACT_NONE, ACT_ELU = 0, 1
+GEMM_TILE_N = 64
+ABI_VERSION = 1
+
+
+class TfepB200Error(RuntimeError):
+    pass
+
+
+class LinearFwdArgs(Structure):
+    _fields_ = [('dtype', c_int32), ('batch', c_int32), ('in_features', c_int32), ('out_features', c_int32),
+                ('x', c_void_p), ('ldx', c_int64), ('w', c_void_p), ('ldw', c_int64), ('bias', c_void_p),
+                ('y', c_void_p), ('ldy', c_int64), ('activation', c_int32), ('reserved', c_int32),
+                ('k_ranges', c_void_p)]
+
+
+class LinearBwdInputArgs(Structure):
+    _fields_ = [('dtype', c_int32), ('batch', c_int32), ('in_features', c_int32), ('out_features', c_int32),
+                ('grad_y', c_void_p), ('ldgy', c_int64), ('w', c_void_p), ('ldw', c_int64),
+                ('grad_x', c_void_p), ('ldgx', c_int64), ('act_out', c_void_p), ('ldact', c_int64),
+                ('accumulate', c_int32), ('reserved', c_int32), ('n_ranges', c_void_p)]
+
+
+class LinearBwdWeightArgs(Structure):
+    _fields_ = [('dtype', c_int32), ('batch', c_int32), ('in_features', c_int32), ('out_features', c_int32),
+                ('grad_y', c_void_p), ('ldgy', c_int64), ('x', c_void_p), ('ldx', c_int64),
+                ('grad_w', c_void_p), ('ldgw', c_int64), ('grad_bias', c_void_p)]
+
+
+class TxIo(Structure):
+    _fields_ = [('dtype', c_int32), ('batch', c_int32), ('n_features', c_int32), ('inverse', c_int32),
+                ('x', c_void_p), ('ldx', c_int64), ('y', c_void_p), ('ldy', c_int64),
+                ('par', c_void_p), ('ldp', c_int64),
+                ('par_offset', c_int64), ('par_stride_p', c_int64), ('par_stride_f', c_int64),
+                ('par_base', c_void_p), ('cols', c_void_p), ('feat_ids', c_void_p), ('logdet', c_void_p),
+                ('accumulate_logdet', c_int32), ('reserved', c_int32)]
+
+
+class SplineCfg(Structure):
+    _fields_ = [('n_bins', c_int32), ('circular', c_int32), ('identity_boundary_slopes', c_int32),
+                ('learn_lower_bound', c_int32), ('learn_upper_bound', c_int32), ('reserved', c_int32),
+                ('x0', c_void_p), ('xf', c_void_p), ('y0', c_void_p), ('yf', c_void_p),
+                ('min_bin_size', c_double), ('min_slope', c_double),
+                ('bins_out', c_void_p), ('ldbins', c_int64)]
+
+
+class TxGrads(Structure):
+    _fields_ = [('grad_y', c_void_p), ('ldgy', c_int64), ('grad_logdet', c_void_p),
+                ('grad_x', c_void_p), ('ldgx', c_int64), ('grad_par', c_void_p)]
+
+
+# every symbol include/tfep_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    'tfepb_abi_version': (c_int32, []),
+    'tfepb_last_error': (c_char_p, []),
+    'tfepb_device_info': (c_int32, [POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
+    'tfepb_masked_linear_forward': (c_int32, [POINTER(LinearFwdArgs), c_void_p]),
+    'tfepb_masked_linear_backward_input': (c_int32, [POINTER(LinearBwdInputArgs), c_void_p]),
+    'tfepb_masked_linear_backward_weight': (c_int32, [POINTER(LinearBwdWeightArgs), c_void_p]),
+    'tfepb_affine': (c_int32, [POINTER(TxIo), c_void_p]),
+    'tfepb_spline': (c_int32, [POINTER(TxIo), POINTER(SplineCfg), c_void_p]),
+    'tfepb_sos': (c_int32, [POINTER(TxIo), c_int32, c_void_p]),
+    'tfepb_moebius': (c_int32, [POINTER(TxIo), c_int32, c_double, c_int32, c_void_p]),
+    'tfepb_affine_backward': (c_int32, [POINTER(TxIo), POINTER(TxGrads), c_void_p]),
+    'tfepb_spline_backward': (c_int32, [POINTER(TxIo), POINTER(SplineCfg), POINTER(TxGrads), c_void_p]),
+    'tfepb_sos_backward': (c_int32, [POINTER(TxIo), c_int32, POINTER(TxGrads), c_void_p]),
+    'tfepb_moebius_backward': (c_int32, [POINTER(TxIo), c_int32, c_double, c_int32, POINTER(TxGrads), c_void_p]),
+    'tfepb_lse_workspace_bytes': (c_int64, []),
+    'tfepb_lse': (c_int32, [c_int32, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p]),
+    'tfepb_mt19937_seed': (c_int32, [c_uint32, c_void_p]),
+    'tfepb_mt19937_indices': (c_int32, [c_void_p, c_int64, c_uint32, c_void_p, c_void_p]),
+    'tfepb_exp_table': (c_int32, [c_int32, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p]),
+    'tfepb_bootstrap_sums': (c_int32, [c_void_p, c_int64, c_uint32, c_void_p, c_int64, c_int32, c_int64, c_uint64,
+                                       c_uint64, c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+def library_path():
+    return _build.LIBPATH
+
+
+def load():
+    """Load libtfep_b200.so (building it is the job of __graft_entry__.build / tfep_b200._build)."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise TfepB200Error(
+                f'{path} not found: build it with `python -m tfep_b200._build` (needs nvcc). '
+                'tfep_b200 has no CPU / PyTorch fallback.')
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)      # AttributeError if the library does not export it
+            fn.restype = res
+            fn.argtypes = args
+        if lib.tfepb_abi_version() != ABI_VERSION:
+            raise TfepB200Error('libtfep_b200.so ABI version mismatch; rebuild the library')
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().tfepb_last_error()
+        raise TfepB200Error(f'tfep_b200 error {rc}: {msg.decode() if msg else "unknown"}')
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.float64:
+        return F64
+    raise TfepB200Error(f'unsupported dtype {t.dtype}: tfep_b200 kernels compute in float32 or float64')
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise TfepB200Error('tfep_b200 runs on CUDA tensors only (sm_100a); there is no CPU fallback. '
+                                'Move the module and its inputs to a B200 device.')
+
+
+def stream_ptr(t: torch.Tensor):
+    return c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def ptr(t):
+    return c_void_p(0) if t is None else c_void_p(t.data_ptr())

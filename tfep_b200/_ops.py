@@ -1,0 +1,300 @@
+"""Tensor-level wrappers around the C ABI (raw pointers, current CUDA stream) and the autograd
+functions built from them.  PyTorch is used for memory, streams and autograd bookkeeping only."""
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_ELU, ACT_NONE, LinearBwdInputArgs, LinearBwdWeightArgs, LinearFwdArgs, SplineCfg, TxGrads, TxIo,
+                   check, dtype_code, ptr, require_cuda, stream_ptr)
+
+
+def _rows(t):
+    """2-D tensor with unit column stride (row-major, arbitrary leading dimension)."""
+    if t.dim() != 2:
+        raise _lib.TfepB200Error(f'expected a 2-D tensor, got shape {tuple(t.shape)}')
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        t = t.contiguous()
+    if t.shape[0] > 1 and t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    return t
+
+
+def _ld(t):
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
+
+
+# ---------------------------------------------------------------------------------------------
+# masked linear layers
+# ---------------------------------------------------------------------------------------------
+
+def linear_forward(x, w, bias=None, activation=ACT_NONE, k_ranges=None, out=None):
+    """y = act(x w^T + bias); see tfepb_masked_linear_forward."""
+    require_cuda(x, w, bias)
+    x, w = _rows(x), _rows(w)
+    B, K = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == K, (w.shape, x.shape)
+    y = out if out is not None else torch.empty((B, N), dtype=x.dtype, device=x.device)
+    if B == 0:
+        return y
+    a = LinearFwdArgs(dtype=dtype_code(x), batch=B, in_features=K, out_features=N,
+                      x=x.data_ptr(), ldx=_ld(x), w=w.data_ptr(), ldw=_ld(w),
+                      bias=None if bias is None else bias.data_ptr(), y=y.data_ptr(), ldy=_ld(y),
+                      activation=activation, reserved=0,
+                      k_ranges=None if k_ranges is None else k_ranges.data_ptr())
+    with torch.cuda.device(x.device):
+        check(_lib.load().tfepb_masked_linear_forward(ctypes.byref(a), stream_ptr(x)))
+    return y
+
+
+def linear_backward_input(grad_y, w, act_out=None, n_ranges=None, out=None, accumulate=False):
+    """grad_x = (grad_y w) [* ELU'(act_out)]; see tfepb_masked_linear_backward_input."""
+    require_cuda(grad_y, w, act_out)
+    grad_y, w = _rows(grad_y), _rows(w)
+    B, N = grad_y.shape
+    K = w.shape[1]
+    gx = out if out is not None else torch.empty((B, K), dtype=grad_y.dtype, device=grad_y.device)
+    if B == 0:
+        return gx
+    if act_out is not None:
+        act_out = _rows(act_out)
+    a = LinearBwdInputArgs(dtype=dtype_code(grad_y), batch=B, in_features=K, out_features=N,
+                           grad_y=grad_y.data_ptr(), ldgy=_ld(grad_y), w=w.data_ptr(), ldw=_ld(w),
+                           grad_x=gx.data_ptr(), ldgx=_ld(gx),
+                           act_out=None if act_out is None else act_out.data_ptr(),
+                           ldact=0 if act_out is None else _ld(act_out),
+                           accumulate=int(accumulate), reserved=0,
+                           n_ranges=None if n_ranges is None else n_ranges.data_ptr())
+    with torch.cuda.device(grad_y.device):
+        check(_lib.load().tfepb_masked_linear_backward_input(ctypes.byref(a), stream_ptr(grad_y)))
+    return gx
+
+
+def linear_backward_weight(grad_y, x, need_bias=True):
+    """(grad_w, grad_bias) = (grad_y^T x, sum_b grad_y); see tfepb_masked_linear_backward_weight."""
+    require_cuda(grad_y, x)
+    grad_y, x = _rows(grad_y), _rows(x)
+    B, N = grad_y.shape
+    K = x.shape[1]
+    gw = torch.zeros((N, K), dtype=x.dtype, device=x.device)
+    gb = torch.zeros((N,), dtype=x.dtype, device=x.device) if need_bias else None
+    if B == 0:
+        return gw, gb
+    a = LinearBwdWeightArgs(dtype=dtype_code(x), batch=B, in_features=K, out_features=N,
+                            grad_y=grad_y.data_ptr(), ldgy=_ld(grad_y), x=x.data_ptr(), ldx=_ld(x),
+                            grad_w=gw.data_ptr(), ldgw=K, grad_bias=None if gb is None else gb.data_ptr())
+    with torch.cuda.device(x.device):
+        check(_lib.load().tfepb_masked_linear_backward_weight(ctypes.byref(a), stream_ptr(x)))
+    return gw, gb
+
+
+class MadeFunction(torch.autograd.Function):
+    """All layers of a MADE conditioner as one autograd node.
+
+    forward : h_0 = x, h_l = ELU(h_{l-1} W_l^T + b_l), out = h_{L-1} W_L^T + b_L     (made.py:294-329)
+    backward: nn/masked.py:280-302 per layer, ELU' fused into the dX GEMM epilogue.
+    Inputs are the PACKED effective weights (mask folded in); gradients w.r.t. them are dense and
+    flow back to (g, v) through the PyTorch graph of the weight normalisation.
+    """
+
+    @staticmethod
+    def forward(ctx, x, n_layers, k_ranges, n_ranges, *wb):
+        ws, bs = wb[:n_layers], wb[n_layers:]
+        acts = [x]
+        h = x
+        for l in range(n_layers):
+            last = l == n_layers - 1
+            h = linear_forward(h, ws[l], bs[l], ACT_NONE if last else ACT_ELU,
+                               None if k_ranges is None else k_ranges[l])
+            if not last:
+                acts.append(h)
+        ctx.save_for_backward(*acts, *ws)
+        ctx.n_layers = n_layers
+        ctx.n_ranges = n_ranges
+        return h
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        L = ctx.n_layers
+        saved = ctx.saved_tensors
+        acts, ws = saved[:L], saved[L:]
+        g = grad_out
+        gws, gbs = [None] * L, [None] * L
+        gx = None
+        for l in range(L - 1, -1, -1):
+            if ctx.needs_input_grad[4 + l] or ctx.needs_input_grad[4 + L + l]:
+                gws[l], gbs[l] = linear_backward_weight(g, acts[l])
+            if l > 0:
+                g = linear_backward_input(g, ws[l], act_out=acts[l],
+                                          n_ranges=None if ctx.n_ranges is None else ctx.n_ranges[l])
+            elif ctx.needs_input_grad[0]:
+                gx = linear_backward_input(g, ws[0], n_ranges=None if ctx.n_ranges is None else ctx.n_ranges[0])
+        return (gx, None, None, None, *gws, *gbs)
+
+
+def made_forward(x, weights, biases, k_ranges=None, n_ranges=None):
+    return MadeFunction.apply(x, len(weights), k_ranges, n_ranges, *weights, *biases)
+
+
+# ---------------------------------------------------------------------------------------------
+# transformers
+# ---------------------------------------------------------------------------------------------
+
+class ParamLayout:
+    """Addressing of transformer parameters inside a (batch, *) parameter matrix (see tfep_b200.h)."""
+
+    def __init__(self, offset=0, stride_p=1, stride_f=1, base=None):
+        self.offset, self.stride_p, self.stride_f, self.base = offset, stride_p, stride_f, base
+
+    @staticmethod
+    def reference(n_features):
+        """Parameter-major layout of the reference: column p * n_features + f."""
+        return ParamLayout(0, n_features, 1, None)
+
+
+def _tx_io(x, y, par, layout, n_features, inverse, cols, feat_ids, logdet, accumulate):
+    return TxIo(dtype=dtype_code(x), batch=x.shape[0], n_features=n_features, inverse=int(inverse),
+                x=x.data_ptr(), ldx=_ld(x), y=None if y is None else y.data_ptr(), ldy=0 if y is None else _ld(y),
+                par=par.data_ptr(), ldp=_ld(par),
+                par_offset=layout.offset, par_stride_p=layout.stride_p, par_stride_f=layout.stride_f,
+                par_base=None if layout.base is None else layout.base.data_ptr(),
+                cols=None if cols is None else cols.data_ptr(),
+                feat_ids=None if feat_ids is None else feat_ids.data_ptr(),
+                logdet=None if logdet is None else logdet.data_ptr(),
+                accumulate_logdet=int(accumulate), reserved=0)
+
+
+def _spline_cfg(spec, dtype, device, bins=None):
+    dom = spec.domain_tensors(dtype, device)
+    cfg = SplineCfg(n_bins=spec.n_bins_int, circular=int(spec.circular), identity_boundary_slopes=int(spec.identity_slopes),
+                    learn_lower_bound=int(spec.learn_lower), learn_upper_bound=int(spec.learn_upper), reserved=0,
+                    x0=dom[0].data_ptr(), xf=dom[1].data_ptr(), y0=dom[2].data_ptr(), yf=dom[3].data_ptr(),
+                    min_bin_size=spec.min_bin_size, min_slope=spec.min_slope,
+                    bins_out=None if bins is None else bins.data_ptr(), ldbins=0 if bins is None else bins.stride(0))
+    return cfg, dom
+
+
+def transformer_apply(kind, spec, x, par, layout, n_features, *, inverse=False, cols=None, feat_ids=None,
+                      y=None, logdet=None, accumulate=False, bins=None):
+    """Run one transformer kernel.  ``kind`` in {'affine','spline','sos','moebius'}; ``spec`` carries its
+    constants.  x / y are (batch, *) matrices addressed through ``cols``; returns (y, logdet)."""
+    require_cuda(x, par)
+    x, par = _rows(x), _rows(par)
+    B = x.shape[0]
+    if y is None:
+        y = torch.empty_like(x)
+    if logdet is None:
+        logdet = torch.zeros(B, dtype=x.dtype, device=x.device) if accumulate else \
+            torch.empty(B, dtype=x.dtype, device=x.device)
+    if B == 0 or n_features == 0:
+        if not accumulate:
+            logdet.zero_()
+        return y, logdet
+    io = _tx_io(x, y, par, layout, n_features, inverse, cols, feat_ids, logdet, accumulate)
+    lib, s = _lib.load(), stream_ptr(x)
+    with torch.cuda.device(x.device):
+        if kind == 'affine':
+            check(lib.tfepb_affine(ctypes.byref(io), s))
+        elif kind == 'spline':
+            cfg, keep = _spline_cfg(spec, x.dtype, x.device, bins)
+            check(lib.tfepb_spline(ctypes.byref(io), ctypes.byref(cfg), s))
+        elif kind == 'sos':
+            check(lib.tfepb_sos(ctypes.byref(io), spec.n_polynomials, s))
+        elif kind == 'moebius':
+            check(lib.tfepb_moebius(ctypes.byref(io), spec.dimension, float(spec.max_radius), int(spec.unit_sphere), s))
+        else:
+            raise ValueError(kind)
+    return y, logdet
+
+
+def transformer_vjp(kind, spec, x, par, layout, n_features, grad_y, grad_logdet, *, cols=None, feat_ids=None,
+                    grad_x=None, grad_par=None):
+    """Vector-Jacobian product of the forward map; returns (grad_x, grad_par) (grad_par laid out like par)."""
+    require_cuda(x, par, grad_y, grad_logdet)
+    x, par, grad_y = _rows(x), _rows(par), _rows(grad_y)
+    if grad_x is None:
+        grad_x = torch.zeros_like(x)
+    if grad_par is None:
+        grad_par = torch.zeros_like(par)
+    assert _ld(grad_par) == _ld(par)
+    if x.shape[0] == 0 or n_features == 0:
+        return grad_x, grad_par
+    if grad_logdet is not None:
+        grad_logdet = grad_logdet.contiguous()
+    io = _tx_io(x, None, par, layout, n_features, False, cols, feat_ids, None, False)
+    g = TxGrads(grad_y=grad_y.data_ptr(), ldgy=_ld(grad_y),
+                grad_logdet=None if grad_logdet is None else grad_logdet.data_ptr(),
+                grad_x=grad_x.data_ptr(), ldgx=_ld(grad_x), grad_par=grad_par.data_ptr())
+    lib, s = _lib.load(), stream_ptr(x)
+    with torch.cuda.device(x.device):
+        if kind == 'affine':
+            check(lib.tfepb_affine_backward(ctypes.byref(io), ctypes.byref(g), s))
+        elif kind == 'spline':
+            cfg, keep = _spline_cfg(spec, x.dtype, x.device)
+            check(lib.tfepb_spline_backward(ctypes.byref(io), ctypes.byref(cfg), ctypes.byref(g), s))
+        elif kind == 'sos':
+            check(lib.tfepb_sos_backward(ctypes.byref(io), spec.n_polynomials, ctypes.byref(g), s))
+        elif kind == 'moebius':
+            check(lib.tfepb_moebius_backward(ctypes.byref(io), spec.dimension, float(spec.max_radius),
+                                             int(spec.unit_sphere), ctypes.byref(g), s))
+        else:
+            raise ValueError(kind)
+    return grad_x, grad_par
+
+
+# ---------------------------------------------------------------------------------------------
+# estimator / bootstrap
+# ---------------------------------------------------------------------------------------------
+
+def lse(w, scale, logw=None):
+    """(max, sum exp(v - max)) of v = scale * w (+ logw) as a (2,) float64 device tensor."""
+    require_cuda(w, logw)
+    w = w.contiguous()
+    if logw is not None:
+        logw = logw.contiguous().to(w.dtype)
+    lib = _lib.load()
+    ws = torch.empty(lib.tfepb_lse_workspace_bytes() // 8, dtype=torch.float64, device=w.device)
+    out = torch.empty(2, dtype=torch.float64, device=w.device)
+    with torch.cuda.device(w.device):
+        check(lib.tfepb_lse(dtype_code(w), ptr(w), ptr(logw), w.numel(), float(scale), ptr(ws), ptr(out),
+                            stream_ptr(w)))
+    return out
+
+
+def exp_table(w, scale, max_dev):
+    require_cuda(w, max_dev)
+    w = w.contiguous()
+    e = torch.empty(w.numel(), dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        check(_lib.load().tfepb_exp_table(dtype_code(w), ptr(w), w.numel(), float(scale), ptr(max_dev), ptr(e),
+                                          stream_ptr(w)))
+    return e
+
+
+def bootstrap_sums(e, max_idx, n_resamples, sample_size, idx=None, philox_seed=0, philox_offset=0):
+    require_cuda(e, idx)
+    out = torch.empty(n_resamples, dtype=torch.float64, device=e.device)
+    with torch.cuda.device(e.device):
+        check(_lib.load().tfepb_bootstrap_sums(ptr(e), e.numel(), int(max_idx), ptr(idx),
+                                               0 if idx is None else idx.stride(0), int(n_resamples), int(sample_size),
+                                               int(philox_seed), int(philox_offset), ptr(out), stream_ptr(e)))
+    return out
+
+
+def mt19937_seed(seed):
+    st = torch.empty(625, dtype=torch.int32)
+    check(_lib.load().tfepb_mt19937_seed(ctypes.c_uint32(seed & 0xffffffff), ptr(st)))
+    return st
+
+
+def mt19937_indices(state_dev, count, max_idx, out=None):
+    """Next ``count`` draws ``u32 % max_idx`` of the MT19937 stream held in ``state_dev`` (625 int32 on the
+    device, updated in place)."""
+    require_cuda(state_dev)
+    idx = out if out is not None else torch.empty(count, dtype=torch.int32, device=state_dev.device)
+    with torch.cuda.device(state_dev.device):
+        check(_lib.load().tfepb_mt19937_indices(ptr(state_dev), int(count), int(max_idx), ptr(idx),
+                                                stream_ptr(state_dev)))
+    return idx

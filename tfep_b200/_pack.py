@@ -1,0 +1,108 @@
+"""Degree-sorted packing of a MADE conditioner (host logic, integer work at construction time).
+
+Hidden units of a MADE can be relabelled freely (permute the rows of layer l and the columns of
+layer l+1 identically).  Sorting every layer's units by autoregressive degree turns each mask
+(``deg_out >= deg_in`` for hidden layers, ``>`` for the output layer; reference nn/masked.py:90-99,
+nn/conditioners/made.py:308-309) into a block lower-triangular staircase, so that
+
+  * for a tile of consecutive output units only a bounded range [begin, end) of the reduction
+    dimension holds non-zero weights -- the rest is never read or multiplied (``k_ranges`` forward,
+    ``n_ranges`` for the transposed product of the backward pass);
+  * all units of one degree are contiguous, which is what the degree-ordered inverse sweep needs.
+
+In the reference's native order hidden degrees are a round-robin tile of the input degrees
+(made.py:413-419) and no tile is empty.  The permutation is invisible outside: parameters and
+``state_dict`` stay in the reference's order, packed copies are derived tensors.
+"""
+
+import torch
+
+from ._lib import GEMM_TILE_N
+
+
+def _stable_argsort(deg):
+    return torch.sort(deg, stable=True).indices
+
+
+def _ranges(packed_mask, tile, axis):
+    """Bounding [begin, end) of the non-zeros of ``packed_mask`` for every tile of `tile` rows
+    (axis=0: per row tile, range over columns) or columns (axis=1: range over rows)."""
+    m = packed_mask if axis == 0 else packed_mask.t()
+    n_tiles = (m.shape[0] + tile - 1) // tile
+    out = torch.zeros(n_tiles, 2, dtype=torch.int32)
+    for t in range(n_tiles):
+        nz = m[t * tile:(t + 1) * tile].any(dim=0).nonzero().flatten()
+        if len(nz) > 0:
+            out[t, 0], out[t, 1] = int(nz[0]), int(nz[-1]) + 1
+    return out
+
+
+class MadePlan:
+    """Permutations, reduction ranges and per-degree row groups of a packed MADE.
+
+    Parameters
+    ----------
+    degree_chain : list of LongTensor
+        Degrees of the input, every hidden layer and the output, in the reference's order.
+    out_order : LongTensor, optional
+        Order in which the OUTPUT units are packed (indices into the reference's output order).
+        Default: the reference's order (what ``MADE.forward`` must return).
+    """
+
+    def __init__(self, degree_chain, out_order=None):
+        chain = [torch.as_tensor(d).long().cpu() for d in degree_chain]
+        self.n_layers = len(chain) - 1
+        self.perms = [torch.arange(len(chain[0]))]
+        for l in range(1, self.n_layers):
+            self.perms.append(_stable_argsort(chain[l]))
+        self.perms.append(torch.arange(len(chain[-1])) if out_order is None else torch.as_tensor(out_order).long().cpu())
+        self.packed_degrees = [chain[l][self.perms[l]] for l in range(self.n_layers + 1)]
+        self.k_ranges, self.n_ranges, self.nnz = [], [], []
+        for l in range(self.n_layers):
+            d_in, d_out = self.packed_degrees[l], self.packed_degrees[l + 1]
+            strict = l == self.n_layers - 1
+            mask = (d_out[:, None] > d_in[None, :]) if strict else (d_out[:, None] >= d_in[None, :])
+            self.k_ranges.append(_ranges(mask, GEMM_TILE_N, axis=0))
+            self.n_ranges.append(_ranges(mask, GEMM_TILE_N, axis=1))
+            self.nnz.append(int(mask.sum()))
+        self._device_cache = {}
+
+    @property
+    def masked_macs(self):
+        """Multiply-accumulates per sample that the masks leave (the algorithmic work of one pass)."""
+        return sum(self.nnz)
+
+    def tables(self, device):
+        """(k_ranges, n_ranges) as lists of int32 device tensors."""
+        key = str(device)
+        if key not in self._device_cache:
+            self._device_cache[key] = ([r.to(device) for r in self.k_ranges], [r.to(device) for r in self.n_ranges],
+                                       [p.to(device) for p in self.perms])
+        return self._device_cache[key]
+
+    def pack(self, weights, biases):
+        """Permute effective weights / biases given in the reference's order into packed order."""
+        device = weights[0].device
+        perms = self.tables(device)[2]
+        pw, pb = [], []
+        for l, (w, b) in enumerate(zip(weights, biases)):
+            w = w.index_select(0, perms[l + 1])
+            if l > 0:
+                w = w.index_select(1, perms[l])
+            pw.append(w.contiguous())
+            pb.append(b.index_select(0, perms[l + 1]).contiguous())
+        return pw, pb
+
+    def degree_rows(self, layer, degree):
+        """[begin, end) of the packed units of ``layer`` (1-based: 1..n_layers) that have ``degree``.
+        Only meaningful for degree-sorted layers."""
+        d = self.packed_degrees[layer]
+        idx = (d == degree).nonzero().flatten()
+        if len(idx) == 0:
+            return 0, 0
+        return int(idx[0]), int(idx[-1]) + 1
+
+    def degree_prefix(self, layer, degree, strict):
+        """Number of packed units of ``layer`` (0 = input, must be sorted) with degree < (or <=) ``degree``."""
+        d = self.packed_degrees[layer]
+        return int(((d < degree) if strict else (d <= degree)).sum())

@@ -1,0 +1,173 @@
+"""Bootstrap distribution of a statistic (reference tfep/analysis/bootstrap.py:24-262).
+
+Same signature and result dictionary as the reference.  Resample indices follow the reference's
+contract -- ``torch.randint`` on a CPU generator, i.e. ``MT19937(seed).u32 % max_idx`` row-major over
+``(n_resamples, sample_size)``, continuing across ``batch`` chunks (bootstrap.py:207-218) -- and are
+produced on the device by tfepb_mt19937_indices, bit for bit, advancing the caller's generator exactly
+as the reference would.  ``rng='philox'`` is a counter-based alternative (statistical parity only).
+
+When ``statistic`` is :func:`tfep_b200.analysis.fep_estimator` on 1-D work values the resample + statistic
+loop is fused (tfepb_exp_table once, then tfepb_bootstrap_sums: gather + add, no ``batch x n`` temporary);
+any other statistic goes through gather + the user's vectorised callable.
+"""
+
+import functools
+import struct
+
+import numpy as np
+import torch
+
+from .. import _ops
+from .estimator import _log_n, fep_estimator, lse_partial
+
+_STATE_OFFSET, _N = 24, 624
+
+
+def _generator_to_state(generator):
+    """at::mt19937 state of a CPU generator as 625 int32 words (624 state words + position)."""
+    raw = generator.get_state().numpy().tobytes()
+    _, left, _, _ = struct.unpack_from('<QiiQ', raw, 0)
+    words = np.frombuffer(raw, dtype=np.uint64, count=_N, offset=_STATE_OFFSET).astype(np.uint32)
+    st = np.empty(_N + 1, dtype=np.uint32)
+    st[:_N] = words
+    st[_N] = _N - (left - 1)
+    return torch.from_numpy(st.view(np.int32).copy())
+
+
+def _state_to_generator(generator, state):
+    """Write the advanced MT19937 state back so the generator continues where the kernel stopped."""
+    st = state.cpu().numpy().view(np.uint32)
+    raw = bytearray(generator.get_state().numpy().tobytes())
+    pos = int(st[_N])
+    seed, _, seeded, _ = struct.unpack_from('<QiiQ', raw, 0)
+    struct.pack_into('<QiiQ', raw, 0, seed, _N - pos + 1, seeded, pos)
+    raw[_STATE_OFFSET:_STATE_OFFSET + 8 * _N] = st[:_N].astype(np.uint64).tobytes()
+    generator.set_state(torch.frombuffer(raw, dtype=torch.uint8).clone())
+
+
+def _fused_kT(statistic):
+    """kT if ``statistic`` is (a partial of) this package's fep_estimator, else None."""
+    if statistic is fep_estimator:
+        return 1.0
+    if isinstance(statistic, functools.partial) and statistic.func is fep_estimator and not statistic.args:
+        extra = set(statistic.keywords) - {'kT'}
+        if not extra:
+            return float(statistic.keywords.get('kT', 1.0))
+    return None
+
+
+def bootstrap(
+        data, statistic, *,
+        confidence_level=0.95,
+        n_resamples=9999,
+        bootstrap_sample_size=None,
+        take_first_only=False,
+        batch=None,
+        method='percentile',
+        bayesian=False,
+        generator=None,
+        rng='mt19937',
+):
+    """Compute confidence interval, standard deviation, mean and median of the bootstrap distribution of
+    ``statistic``.  See the reference docstring (bootstrap.py:35-125) for the arguments; ``rng`` is the only
+    addition (``'mt19937'``: the reference's index stream, ``'philox'``: counter-based, not bit-compatible).
+
+    Returns a dict (or a list of dicts, one per ``bootstrap_sample_size``) with keys ``confidence_interval``
+    (``low`` / ``high``), ``standard_deviation``, ``mean`` and ``median``.
+    """
+    n_samples = len(data)
+    if bayesian and generator is not None:
+        raise ValueError('Bayesian bootstrapping does not support random number generators.')
+    if bootstrap_sample_size is None:
+        bootstrap_sample_size = [n_samples]
+    elif bayesian and not take_first_only:
+        raise ValueError('With Bayesian bootstrapping, specifying a bootstrap_sample_size '
+                         'is supported only when take_first_only is True.')
+    if bayesian:
+        raise NotImplementedError('tfep_b200: Bayesian bootstrapping is not implemented yet')
+    if rng not in ('mt19937', 'philox'):
+        raise ValueError("rng must be 'mt19937' or 'philox'")
+    if batch is None:
+        batch = n_resamples
+
+    with torch.no_grad():
+        results = []
+        for sample_size in bootstrap_sample_size:
+            stats = _bootstrap_statistics(data, statistic, n_resamples, sample_size, take_first_only, batch,
+                                          generator, rng)
+            alpha = (1 - confidence_level) / 2
+            quantiles = torch.tensor([alpha, 1 - alpha], dtype=stats.dtype, device=stats.device)
+            ci_l, ci_u = torch.quantile(stats, q=quantiles)
+            if method == 'basic':
+                full_statistic = statistic(data.unsqueeze(0))
+                ci_l, ci_u = 2 * full_statistic - ci_u, 2 * full_statistic - ci_l
+            results.append(dict(
+                confidence_interval=dict(low=ci_l, high=ci_u),
+                standard_deviation=torch.std(stats),
+                mean=torch.mean(stats),
+                median=torch.median(stats),
+            ))
+    if len(bootstrap_sample_size) == 1:
+        return results[0]
+    return results
+
+
+def bootstrap_partial_sums(data, kT, n_resamples, sample_size, max_idx, batch, generator, rng,
+                           shard_offset=0, global_max=None):
+    """Per-resample ``sum_j exp(v[idx_rj] - max)`` over the draws that fall into this rank's shard.
+
+    ``data`` is the local shard ``[shard_offset, shard_offset + len(data))`` of the global array; every rank
+    walks the same global index stream.  Returns ``(sums (n_resamples,) float64, max)``; sums of all ranks
+    add up to the single-GPU result (one all-reduce of ``n_resamples`` doubles).  Single GPU: shard = all.
+    """
+    if shard_offset != 0 or global_max is not None:
+        raise NotImplementedError('sharded bootstrap: see tfep_b200.analysis.distributed')
+    scale = -1.0 / kT
+    o = _ops.lse(data, scale)
+    e = _ops.exp_table(data, scale, o[:1])
+    sums = torch.empty(n_resamples, dtype=torch.float64, device=data.device)
+    if rng == 'philox':
+        seed = int(torch.randint(0, 2**62, (1,), generator=generator).item())
+        for k in range(0, n_resamples, 65535):
+            nb = min(65535, n_resamples - k)
+            sums[k:k + nb] = _ops.bootstrap_sums(e, max_idx, nb, sample_size, None, seed,
+                                                 k * ((sample_size + 3) // 4))
+        return sums, o[0]
+    gen = torch.default_generator if generator is None else generator
+    state = _generator_to_state(gen).to(data.device)
+    idx = torch.empty(min(batch, n_resamples) * sample_size, dtype=torch.int32, device=data.device)
+    for k in range(0, n_resamples, batch):
+        nb = min(batch, n_resamples - k)
+        _ops.mt19937_indices(state, nb * sample_size, max_idx, out=idx)
+        sums[k:k + nb] = _ops.bootstrap_sums(e, max_idx, nb, sample_size, idx[:nb * sample_size].view(nb, sample_size))
+    _state_to_generator(gen, state)
+    return sums, o[0]
+
+
+def _bootstrap_statistics(data, statistic, n_resamples, sample_size, take_first_only, batch, generator, rng):
+    """The ``n_resamples`` values of the statistic (reference bootstrap.py:185-233)."""
+    n_samples = len(data)
+    max_idx = sample_size if take_first_only else n_samples
+    kT = _fused_kT(statistic)
+    if kT is not None and data.dim() == 1:
+        batch = max(1, min(batch, n_resamples, (1 << 28) // max(sample_size, 1) or 1))
+        sums, m = bootstrap_partial_sums(data, kT, n_resamples, sample_size, max_idx, batch, generator, rng)
+        return (-kT * (m + torch.log(sums) - _log_n(sample_size))).to(data.dtype)
+
+    # generic statistic: indices from the same stream, gather, user callable on (batch, sample_size[, dim])
+    gen = torch.default_generator if generator is None else generator
+    stats = torch.empty(n_resamples, dtype=data.dtype, device=data.device)
+    state = _generator_to_state(gen).to(data.device) if rng == 'mt19937' else None
+    for k in range(0, n_resamples, batch):
+        nb = min(batch, n_resamples - k)
+        if rng == 'mt19937':
+            idx = _ops.mt19937_indices(state, nb * sample_size, max_idx).view(nb, sample_size).long()
+        else:
+            idx = torch.randint(0, max_idx, (nb, sample_size), device=data.device)
+        expanded = data.expand((nb, *data.shape))
+        if data.dim() > 1:
+            idx = idx.unsqueeze(-1).expand(nb, sample_size, data.shape[1])
+        stats[k:k + nb] = statistic(torch.gather(expanded, dim=1, index=idx), vectorized=True)
+    if state is not None:
+        _state_to_generator(gen, state)
+    return stats

@@ -1,0 +1,322 @@
+// (T)FEP estimator and bootstrap kernels.
+//
+//   tfepb_lse            single-pass online log-sum-exp over the work values  (analysis/estimator.py:61-86)
+//   tfepb_exp_table      e_i = exp(v_i - max) once, so the resampling loop is gather + add
+//   tfepb_bootstrap_sums per-resample sum of gathered e_i                      (analysis/bootstrap.py:185-233)
+//   tfepb_mt19937_*      the index stream torch.randint draws on a CPU generator (bootstrap.py:214-218)
+//
+// All are HBM / L2 bound: lse reads 4 (8) bytes per sample once; bootstrap_sums reads one index
+// (or generates it from Philox4x32-10 in registers) and one table entry per draw.
+#include "common.cuh"
+
+namespace tfepb {
+namespace {
+
+constexpr int LSE_THREADS = 256;
+constexpr int LSE_MAX_BLOCKS = 2048;
+
+struct MS {
+    double m, s;
+};
+
+__device__ __forceinline__ MS ms_combine(MS a, MS b) {
+    if (b.s == 0.0) return a;
+    if (a.s == 0.0) return b;
+    const double m = a.m > b.m ? a.m : b.m;
+    return MS{m, a.s * exp(a.m - m) + b.s * exp(b.m - m)};
+}
+
+__device__ __forceinline__ MS ms_block_reduce(MS v) {
+    __shared__ double sm[LSE_THREADS / 32], ss[LSE_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        MS u{__shfl_xor_sync(0xffffffffu, v.m, o), __shfl_xor_sync(0xffffffffu, v.s, o)};
+        v = ms_combine(v, u);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sm[warp] = v.m; ss[warp] = v.s; }
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < LSE_THREADS / 32 ? MS{sm[lane], ss[lane]} : MS{0.0, 0.0};
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            MS u{__shfl_xor_sync(0xffffffffu, v.m, o), __shfl_xor_sync(0xffffffffu, v.s, o)};
+            v = ms_combine(v, u);
+        }
+    }
+    return v;   // valid in thread 0
+}
+
+// Each thread keeps a running (max, sum) over groups of UNROLL values: one exp per value plus one
+// rescale per group, the sum carried in double.
+template <typename T>
+__global__ void __launch_bounds__(LSE_THREADS) lse_partial_kernel(const T* __restrict__ w, const T* __restrict__ logw,
+                                                                  int64_t n, T scale, double* __restrict__ partials) {
+    constexpr int UNROLL = 8;
+    T m = T(0);
+    double s = 0.0;
+    bool have = false;
+    const int64_t stride = (int64_t)gridDim.x * LSE_THREADS;
+    const int64_t t0 = (int64_t)blockIdx.x * LSE_THREADS + threadIdx.x;
+    for (int64_t base = t0; base < n; base += stride * UNROLL) {
+        T v[UNROLL];
+        T gm = T(0);
+        bool any = false;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t i = base + (int64_t)u * stride;
+            if (i < n) {
+                v[u] = scale * w[i] + (logw ? logw[i] : T(0));
+                gm = any ? (v[u] > gm ? v[u] : gm) : v[u];
+                any = true;
+            }
+        }
+        if (!any) break;
+        if (!have || gm > m) {
+            if (have) s *= (double)Math<T>::exp(m - gm);
+            m = gm;
+            have = true;
+        }
+        T part = T(0);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t i = base + (int64_t)u * stride;
+            if (i < n) part += Math<T>::exp(v[u] - m);
+        }
+        s += (double)part;
+    }
+    MS r = ms_block_reduce(MS{(double)m, have ? s : 0.0});
+    if (threadIdx.x == 0) {
+        partials[2 * blockIdx.x] = r.m;
+        partials[2 * blockIdx.x + 1] = r.s;
+    }
+}
+
+__global__ void __launch_bounds__(LSE_THREADS) lse_final_kernel(const double* __restrict__ partials, int nparts,
+                                                                double* __restrict__ out2) {
+    MS v{0.0, 0.0};
+    for (int i = threadIdx.x; i < nparts; i += LSE_THREADS) v = ms_combine(v, MS{partials[2 * i], partials[2 * i + 1]});
+    v = ms_block_reduce(v);
+    if (threadIdx.x == 0) {
+        out2[0] = v.m;
+        out2[1] = v.s;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) exp_table_kernel(const T* __restrict__ w, int64_t n, T scale,
+                                                        const double* __restrict__ max_dev, float* __restrict__ e) {
+    const T m = (T)max_dev[0];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        e[i] = (float)Math<T>::exp(scale * w[i] - m);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11), counter = draw index / 4, key = seed
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+
+constexpr int BS_THREADS = 256;
+constexpr int BS_DRAWS_PER_THREAD = 32;     // multiple of 4
+constexpr int BS_CHUNK = BS_THREADS * BS_DRAWS_PER_THREAD;
+
+// grid = (chunks of BS_CHUNK draws, resamples).  Explicit indices (exact MT19937 stream) or Philox.
+__global__ void __launch_bounds__(BS_THREADS) bootstrap_sums_kernel(const float* __restrict__ e, uint32_t max_idx,
+                                                                    const int32_t* __restrict__ idx, int64_t ldidx,
+                                                                    int64_t sample_size, uint64_t seed, uint64_t offset,
+                                                                    double* __restrict__ out) {
+    const int r = blockIdx.y;
+    const int64_t j0 = (int64_t)blockIdx.x * BS_CHUNK;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    if (idx != nullptr) {
+        const int32_t* row = idx + (int64_t)r * ldidx;
+#pragma unroll 8
+        for (int k = 0; k < BS_DRAWS_PER_THREAD; ++k) {
+            const int64_t j = j0 + (int64_t)k * BS_THREADS + threadIdx.x;
+            if (j < sample_size) {
+                const float v = __ldg(e + row[j]);
+                if ((k & 3) == 0) acc0 += v; else if ((k & 3) == 1) acc1 += v; else if ((k & 3) == 2) acc2 += v; else acc3 += v;
+            }
+        }
+    } else {
+        const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll 4
+        for (int k = 0; k < BS_DRAWS_PER_THREAD / 4; ++k) {
+            // 4 consecutive draws of this resample per Philox call
+            const int64_t j = j0 + ((int64_t)k * BS_THREADS + threadIdx.x) * 4;
+            if (j < sample_size) {
+                const uint64_t c = offset + ((uint64_t)r * (uint64_t)((sample_size + 3) / 4)) + (uint64_t)(j >> 2);
+                const uint4 u = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), key);
+                acc0 += __ldg(e + __umulhi(u.x, max_idx));
+                if (j + 1 < sample_size) acc1 += __ldg(e + __umulhi(u.y, max_idx));
+                if (j + 2 < sample_size) acc2 += __ldg(e + __umulhi(u.z, max_idx));
+                if (j + 3 < sample_size) acc3 += __ldg(e + __umulhi(u.w, max_idx));
+            }
+        }
+    }
+    double s = (double)acc0 + (double)acc1 + (double)acc2 + (double)acc3;
+    s = warp_sum(s);
+    __shared__ double ws[BS_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < BS_THREADS / 32 ? ws[threadIdx.x] : 0.0;
+        s = warp_sum(s);
+        if (threadIdx.x == 0) atomicAdd(out + r, s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MT19937: one CTA advances the 624-word state by whole twists (three dependency-free spans of
+// 227 words, see oracle/analysis_oracle.py) and tempers / reduces the outputs modulo max_idx.
+// The stream is inherently sequential, so a single CTA is used; jump-ahead is future work.
+// ---------------------------------------------------------------------------------------------
+constexpr int MT_N = 624, MT_M = 397, MT_THREADS = 256;
+
+__device__ __forceinline__ uint32_t mt_mix(uint32_t a, uint32_t b) {
+    const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    return y ^ (y >> 18);
+}
+
+__global__ void __launch_bounds__(MT_THREADS) mt19937_indices_kernel(uint32_t* __restrict__ state625, int64_t count,
+                                                                     uint32_t max_idx, int32_t* __restrict__ idx) {
+    __shared__ uint32_t st[MT_N];
+    const int t = threadIdx.x;
+    for (int i = t; i < MT_N; i += MT_THREADS) st[i] = state625[i];
+    int pos = (int)state625[MT_N];
+    __syncthreads();
+    int64_t done = 0;
+    while (done < count) {
+        if (pos >= MT_N) {
+            constexpr int SPAN = MT_N - MT_M;   // 227
+            uint32_t v = 0;
+            // span A: i in [0, 227)
+            if (t < SPAN) v = st[t + MT_M] ^ mt_mix(st[t], st[t + 1]);
+            __syncthreads();
+            if (t < SPAN) st[t] = v;
+            __syncthreads();
+            // span B: i in [227, 454)
+            if (t < SPAN) v = st[t] ^ mt_mix(st[t + SPAN], st[t + SPAN + 1]);
+            __syncthreads();
+            if (t < SPAN) st[t + SPAN] = v;
+            __syncthreads();
+            // span C: i in [454, 623) and the last word, which needs the NEW st[0]
+            const int i = t + 2 * SPAN;
+            if (i < MT_N - 1) v = st[i - SPAN] ^ mt_mix(st[i], st[i + 1]);
+            else if (i == MT_N - 1) v = st[MT_M - 1] ^ mt_mix(st[MT_N - 1], st[0]);
+            __syncthreads();
+            if (i < MT_N) st[i] = v;
+            __syncthreads();
+            pos = 0;
+        }
+        const int avail = MT_N - pos;
+        const int take = (int)((count - done) < (int64_t)avail ? (count - done) : (int64_t)avail);
+        for (int k = t; k < take; k += MT_THREADS) idx[done + k] = (int32_t)(mt_temper(st[pos + k]) % max_idx);
+        pos += take;
+        done += take;
+    }
+    __syncthreads();
+    for (int i = t; i < MT_N; i += MT_THREADS) state625[i] = st[i];
+    if (t == 0) state625[MT_N] = (uint32_t)pos;
+}
+
+}  // namespace
+}  // namespace tfepb
+
+using namespace tfepb;
+
+extern "C" int64_t tfepb_lse_workspace_bytes(void) { return (int64_t)LSE_MAX_BLOCKS * 2 * sizeof(double); }
+
+extern "C" int tfepb_lse(int32_t dtype, const void* w, const void* logw, int64_t n, double scale, void* partials,
+                         double* out2, tfepb_stream_t stream) {
+    TFEPB_CHECK_ARG(n > 0, "empty data");
+    TFEPB_CHECK_ARG(w && partials && out2, "null buffer");
+    if (int rc = require_sm100()) return rc;
+    int64_t blocks = (n + (int64_t)LSE_THREADS * 8 - 1) / ((int64_t)LSE_THREADS * 8);
+    const int64_t cap = (int64_t)sm_count() * 8 < LSE_MAX_BLOCKS ? (int64_t)sm_count() * 8 : LSE_MAX_BLOCKS;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t s = as_stream(stream);
+    if (dtype == TFEPB_F32)
+        lse_partial_kernel<float><<<(int)blocks, LSE_THREADS, 0, s>>>((const float*)w, (const float*)logw, n, (float)scale,
+                                                                      (double*)partials);
+    else if (dtype == TFEPB_F64)
+        lse_partial_kernel<double><<<(int)blocks, LSE_THREADS, 0, s>>>((const double*)w, (const double*)logw, n, scale,
+                                                                       (double*)partials);
+    else
+        return fail(-1, "unknown dtype %d", dtype);
+    if (int rc = check_launch("lse_partial")) return rc;
+    lse_final_kernel<<<1, LSE_THREADS, 0, s>>>((const double*)partials, (int)blocks, out2);
+    return check_launch("lse_final");
+}
+
+extern "C" int tfepb_exp_table(int32_t dtype, const void* w, int64_t n, double scale, const double* max_dev, float* e,
+                               tfepb_stream_t stream) {
+    TFEPB_CHECK_ARG(n > 0, "empty data");
+    TFEPB_CHECK_ARG(w && max_dev && e, "null buffer");
+    if (int rc = require_sm100()) return rc;
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (dtype == TFEPB_F32)
+        exp_table_kernel<float><<<(int)blocks, 256, 0, as_stream(stream)>>>((const float*)w, n, (float)scale, max_dev, e);
+    else if (dtype == TFEPB_F64)
+        exp_table_kernel<double><<<(int)blocks, 256, 0, as_stream(stream)>>>((const double*)w, n, scale, max_dev, e);
+    else
+        return fail(-1, "unknown dtype %d", dtype);
+    return check_launch("exp_table");
+}
+
+extern "C" int tfepb_bootstrap_sums(const float* e, int64_t n, uint32_t max_idx, const int32_t* idx, int64_t ldidx,
+                                    int32_t n_resamples, int64_t sample_size, uint64_t philox_seed,
+                                    uint64_t philox_offset, double* out_sums, tfepb_stream_t stream) {
+    TFEPB_CHECK_ARG(e && out_sums, "null buffer");
+    TFEPB_CHECK_ARG(n_resamples > 0 && sample_size > 0, "bad sizes");
+    TFEPB_CHECK_ARG(max_idx > 0 && (int64_t)max_idx <= n, "max_idx out of range");
+    TFEPB_CHECK_ARG(n_resamples <= 65535, "at most 65535 resamples per call");
+    if (int rc = require_sm100()) return rc;
+    cudaStream_t s = as_stream(stream);
+    TFEPB_CUDA(cudaMemsetAsync(out_sums, 0, sizeof(double) * n_resamples, s));
+    dim3 grid((unsigned)((sample_size + BS_CHUNK - 1) / BS_CHUNK), (unsigned)n_resamples);
+    bootstrap_sums_kernel<<<grid, BS_THREADS, 0, s>>>(e, max_idx, idx, ldidx, sample_size, philox_seed, philox_offset,
+                                                      out_sums);
+    return check_launch("bootstrap_sums");
+}
+
+extern "C" int tfepb_mt19937_seed(uint32_t seed, uint32_t* state625_host) {
+    TFEPB_CHECK_ARG(state625_host != nullptr, "null buffer");
+    state625_host[0] = seed;
+    for (int i = 1; i < MT_N; ++i)
+        state625_host[i] = 1812433253u * (state625_host[i - 1] ^ (state625_host[i - 1] >> 30)) + (uint32_t)i;
+    state625_host[MT_N] = MT_N;   // exhausted: the first draw twists
+    return 0;
+}
+
+extern "C" int tfepb_mt19937_indices(uint32_t* state625_dev, int64_t count, uint32_t max_idx, int32_t* idx,
+                                     tfepb_stream_t stream) {
+    TFEPB_CHECK_ARG(state625_dev && idx, "null buffer");
+    TFEPB_CHECK_ARG(count >= 0 && max_idx > 0, "bad sizes");
+    TFEPB_CHECK_ARG(max_idx <= 0x7fffffffu, "indices are int32: max_idx must be below 2^31");
+    if (int rc = require_sm100()) return rc;
+    if (count == 0) return 0;
+    mt19937_indices_kernel<<<1, MT_THREADS, 0, as_stream(stream)>>>(state625_dev, count, max_idx, idx);
+    return check_launch("mt19937_indices");
+}

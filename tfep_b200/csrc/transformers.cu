@@ -1,0 +1,334 @@
+// Stand-alone transformer kernels (exact fp32 / fp64 arithmetic): elementwise map + per-sample
+// log|det J| reduction, and their vector-Jacobian products.
+//
+// Mapping: one warp owns one sample at a time; lanes stride over the features (or Moebius vector
+// blocks), so that for the reference's parameter-major layout (stride_f = 1) every parameter load
+// and every x / y access of a warp is one contiguous segment.  The per-sample log-det is reduced
+// with warp shuffles and written once.  These kernels are HBM-bound (parameters are read once).
+#include "common.cuh"
+#include "tx_math.cuh"
+
+namespace tfepb {
+namespace {
+
+template <typename T>
+struct TxView {
+    const T* x; int64_t ldx;
+    T* y; int64_t ldy;
+    const T* par; int64_t ldp, poff, sp, sf;
+    const int* pbase;
+    const int* cols;
+    const int* ids;
+    T* logdet;
+    int accumulate, B, F, inverse;
+    // gradients (backward kernels only)
+    const T* gy; int64_t ldgy;
+    const T* gld;
+    T* gx; int64_t ldgx;
+    T* gpar;
+
+    __device__ __forceinline__ int col(int f) const { return cols ? cols[f] : f; }
+    __device__ __forceinline__ int fid(int u) const { return ids ? ids[u] : u; }
+    __device__ __forceinline__ int64_t poffset(int b, int f) const {
+        return (int64_t)b * ldp + poff + (pbase ? (int64_t)pbase[f] : (int64_t)f * sf);
+    }
+    __device__ __forceinline__ ParIn<T> pin(int b, int f) const { return ParIn<T>{par + poffset(b, f), sp}; }
+    __device__ __forceinline__ ParOut<T> pout(int b, int f) const { return ParOut<T>{gpar + poffset(b, f), sp}; }
+};
+
+template <typename T>
+TxView<T> make_view(const tfepb_tx_io* io, const tfepb_tx_grads* g = nullptr) {
+    TxView<T> v{};
+    v.x = (const T*)io->x; v.ldx = io->ldx;
+    v.y = (T*)io->y; v.ldy = io->ldy;
+    v.par = (const T*)io->par; v.ldp = io->ldp;
+    v.poff = io->par_offset; v.sp = io->par_stride_p; v.sf = io->par_stride_f;
+    v.pbase = io->par_base;
+    v.cols = io->cols;
+    v.ids = io->feat_ids;
+    v.logdet = (T*)io->logdet;
+    v.accumulate = io->accumulate_logdet;
+    v.B = io->batch; v.F = io->n_features; v.inverse = io->inverse;
+    if (g) {
+        v.gy = (const T*)g->grad_y; v.ldgy = g->ldgy;
+        v.gld = (const T*)g->grad_logdet;
+        v.gx = (T*)g->grad_x; v.ldgx = g->ldgx;
+        v.gpar = (T*)g->grad_par;
+    }
+    return v;
+}
+
+constexpr int TX_THREADS = 256;
+
+inline int tx_blocks(int batch) {
+    const int warps_per_block = TX_THREADS / 32;
+    int64_t blocks = ((int64_t)batch + warps_per_block - 1) / warps_per_block;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    return blocks < 1 ? 1 : (int)blocks;
+}
+
+// Forward / inverse driver.  Op::units(F) = number of independent work items per sample,
+// Op::apply(view, b, unit) performs the map for one item and returns its log-det contribution.
+template <typename T, typename Op>
+__global__ void __launch_bounds__(TX_THREADS) tx_forward_kernel(TxView<T> v, Op op) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * TX_THREADS + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * TX_THREADS) >> 5;
+    const int units = op.units(v.F);
+    for (int b = warp; b < v.B; b += nwarps) {
+        T ld = T(0);
+        for (int u = lane; u < units; u += 32) ld += op.apply(v, b, u);
+        ld = warp_sum(ld);
+        if (lane == 0 && v.logdet != nullptr) v.logdet[b] = v.accumulate ? v.logdet[b] + ld : ld;
+    }
+}
+
+template <typename T, typename Op>
+__global__ void __launch_bounds__(TX_THREADS) tx_backward_kernel(TxView<T> v, Op op) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * TX_THREADS + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * TX_THREADS) >> 5;
+    const int units = op.units(v.F);
+    for (int b = warp; b < v.B; b += nwarps) {
+        const T gl = v.gld ? v.gld[b] : T(0);
+        for (int u = lane; u < units; u += 32) op.backward(v, b, u, gl);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct AffineOp {
+    __device__ int units(int F) const { return F; }
+    __device__ T apply(const TxView<T>& v, int b, int u) const {
+        const int f = v.fid(u), c = v.col(f);
+        T out, ld;
+        if (v.inverse) affine_eval<T, true>(v.pin(b, f), v.x[(int64_t)b * v.ldx + c], out, ld);
+        else affine_eval<T, false>(v.pin(b, f), v.x[(int64_t)b * v.ldx + c], out, ld);
+        v.y[(int64_t)b * v.ldy + c] = out;
+        return ld;
+    }
+    __device__ void backward(const TxView<T>& v, int b, int u, T gl) const {
+        const int f = v.fid(u), c = v.col(f);
+        T gx;
+        affine_vjp<T>(v.pin(b, f), v.x[(int64_t)b * v.ldx + c], v.gy[(int64_t)b * v.ldgy + c], gl, gx, v.pout(b, f));
+        v.gx[(int64_t)b * v.ldgx + c] = gx;
+    }
+};
+
+template <typename T>
+struct SosOp {
+    int n_poly;
+    __device__ int units(int F) const { return F; }
+    __device__ T apply(const TxView<T>& v, int b, int u) const {
+        const int f = v.fid(u), c = v.col(f);
+        T out, ld;
+        sos_eval<T>(v.pin(b, f), n_poly, v.x[(int64_t)b * v.ldx + c], out, ld);
+        v.y[(int64_t)b * v.ldy + c] = out;
+        return ld;
+    }
+    __device__ void backward(const TxView<T>& v, int b, int u, T) const {
+        const int f = v.fid(u), c = v.col(f);
+        T gx;
+        sos_vjp<T>(v.pin(b, f), n_poly, v.x[(int64_t)b * v.ldx + c], v.gy[(int64_t)b * v.ldgy + c], gx, v.pout(b, f));
+        v.gx[(int64_t)b * v.ldgx + c] = gx;
+    }
+};
+
+template <typename T>
+struct MoebiusOp {
+    int d;
+    T max_radius;
+    int unit_sphere;
+    __device__ int units(int F) const { return F / d; }
+    // Vector blocks are `d` consecutive TRANSFORMER features; their columns go through `cols`.
+    // With cols == nullptr the block is contiguous in x / y (stride 1).
+    __device__ T apply(const TxView<T>& v, int b, int u) const {
+        const int f0 = v.fid(u * d);
+        if (v.cols == nullptr && v.pbase == nullptr) {
+            return moebius_eval<T>(v.x + (int64_t)b * v.ldx + f0, 1, v.par + v.poffset(b, f0), v.sf,
+                                   v.inverse ? T(-1) : T(1), d, max_radius, unit_sphere != 0,
+                                   v.y + (int64_t)b * v.ldy + f0, 1);
+        }
+        // gather through the column map (d <= 16)
+        T xs[16], vs[16], ys[16];
+        for (int i = 0; i < d; ++i) {
+            xs[i] = v.x[(int64_t)b * v.ldx + v.col(f0 + i)];
+            vs[i] = v.par[v.poffset(b, f0 + i)];
+        }
+        const T ld = moebius_eval<T>(xs, 1, vs, 1, v.inverse ? T(-1) : T(1), d, max_radius, unit_sphere != 0, ys, 1);
+        for (int i = 0; i < d; ++i) v.y[(int64_t)b * v.ldy + v.col(f0 + i)] = ys[i];
+        return ld;
+    }
+    __device__ void backward(const TxView<T>& v, int b, int u, T gl) const {
+        const int f0 = v.fid(u * d);
+        T xs[16], vs[16], gys[16], gxs[16], gvs[16];
+        for (int i = 0; i < d; ++i) {
+            const int c = v.col(f0 + i);
+            xs[i] = v.x[(int64_t)b * v.ldx + c];
+            gys[i] = v.gy[(int64_t)b * v.ldgy + c];
+            vs[i] = v.par[v.poffset(b, f0 + i)];
+        }
+        moebius_vjp<T>(xs, 1, vs, 1, d, max_radius, unit_sphere != 0, gys, 1, gl, gxs, 1, gvs, 1);
+        for (int i = 0; i < d; ++i) {
+            v.gx[(int64_t)b * v.ldgx + v.col(f0 + i)] = gxs[i];
+            v.gpar[v.poffset(b, f0 + i)] = gvs[i];
+        }
+    }
+};
+
+template <typename T, int MAXK>
+struct SplineOp {
+    int K, circular, idslopes, learn_lo, learn_hi;
+    const T *x0, *xf, *y0, *yf;
+    T min_bin, min_slope;
+    int* bins; int64_t ldbins;
+
+    __device__ int units(int F) const { return F; }
+    __device__ SplineFeat<T> feat(int f) const {
+        SplineFeat<T> c;
+        c.K = K; c.circular = circular; c.idslopes = idslopes; c.learn_lo = learn_lo; c.learn_hi = learn_hi;
+        c.x0 = x0[f]; c.xf = xf[f]; c.y0 = y0[f]; c.yf = yf[f];
+        c.min_bin = min_bin; c.min_slope = min_slope;
+        return c;
+    }
+    __device__ T apply(const TxView<T>& v, int b, int u) const {
+        const int f = v.fid(u), col = v.col(f);
+        T out, ld;
+        int bin;
+        if (v.inverse) spline_eval<T, MAXK, true>(feat(f), v.pin(b, f), v.x[(int64_t)b * v.ldx + col], out, ld, bin);
+        else spline_eval<T, MAXK, false>(feat(f), v.pin(b, f), v.x[(int64_t)b * v.ldx + col], out, ld, bin);
+        v.y[(int64_t)b * v.ldy + col] = out;
+        if (bins != nullptr) bins[(int64_t)b * ldbins + f] = bin;
+        return ld;
+    }
+    __device__ void backward(const TxView<T>& v, int b, int u, T gl) const {
+        const int f = v.fid(u), col = v.col(f);
+        T gx;
+        spline_vjp<T, MAXK>(feat(f), v.pin(b, f), v.x[(int64_t)b * v.ldx + col], v.gy[(int64_t)b * v.ldgy + col], gl, gx,
+                            v.pout(b, f));
+        v.gx[(int64_t)b * v.ldgx + col] = gx;
+    }
+};
+
+template <typename T, typename Op>
+int run(const tfepb_tx_io* io, const tfepb_tx_grads* g, Op op, cudaStream_t s, const char* what) {
+    if (io->batch == 0 || io->n_features == 0) return 0;
+    TxView<T> v = make_view<T>(io, g);
+    if (g == nullptr) tx_forward_kernel<T, Op><<<tx_blocks(io->batch), TX_THREADS, 0, s>>>(v, op);
+    else tx_backward_kernel<T, Op><<<tx_blocks(io->batch), TX_THREADS, 0, s>>>(v, op);
+    return check_launch(what);
+}
+
+int check_io(const tfepb_tx_io* io, const tfepb_tx_grads* g) {
+    TFEPB_CHECK_ARG(io != nullptr, "null io struct");
+    TFEPB_CHECK_ARG(io->batch >= 0 && io->n_features >= 0, "bad sizes");
+    TFEPB_CHECK_ARG(io->dtype == TFEPB_F32 || io->dtype == TFEPB_F64, "unknown dtype %d", io->dtype);
+    TFEPB_CHECK_ARG(io->x && io->par, "null buffer");
+    if (g == nullptr) {
+        TFEPB_CHECK_ARG(io->y != nullptr, "null output buffer");
+    } else {
+        TFEPB_CHECK_ARG(io->inverse == 0, "vector-Jacobian products are implemented for the forward direction only");
+        TFEPB_CHECK_ARG(g->grad_y && g->grad_x && g->grad_par, "null gradient buffer");
+    }
+    return require_sm100();
+}
+
+template <typename T>
+int spline_dispatch(const tfepb_tx_io* io, const tfepb_spline_cfg* cfg, const tfepb_tx_grads* g, cudaStream_t s) {
+    auto fill = [&](auto& op) {
+        op.K = cfg->n_bins; op.circular = cfg->circular; op.idslopes = cfg->identity_boundary_slopes;
+        op.learn_lo = cfg->learn_lower_bound; op.learn_hi = cfg->learn_upper_bound;
+        op.x0 = (const T*)cfg->x0; op.xf = (const T*)cfg->xf; op.y0 = (const T*)cfg->y0; op.yf = (const T*)cfg->yf;
+        op.min_bin = (T)cfg->min_bin_size; op.min_slope = (T)cfg->min_slope;
+        op.bins = cfg->bins_out; op.ldbins = cfg->ldbins;
+    };
+    if (cfg->n_bins <= 8) { SplineOp<T, 8> op; fill(op); return run<T>(io, g, op, s, "spline"); }
+    if (cfg->n_bins <= 16) { SplineOp<T, 16> op; fill(op); return run<T>(io, g, op, s, "spline"); }
+    if (cfg->n_bins <= 32) { SplineOp<T, 32> op; fill(op); return run<T>(io, g, op, s, "spline"); }
+    return fail(-1, "n_bins = %d exceeds the supported maximum of 32", cfg->n_bins);
+}
+
+int check_spline(const tfepb_tx_io* io, const tfepb_spline_cfg* cfg) {
+    TFEPB_CHECK_ARG(cfg != nullptr, "null spline config");
+    TFEPB_CHECK_ARG(cfg->n_bins >= 1, "n_bins must be positive");
+    TFEPB_CHECK_ARG(cfg->x0 && cfg->xf && cfg->y0 && cfg->yf, "null spline domain buffer");
+    TFEPB_CHECK_ARG(!(cfg->circular && (cfg->learn_lower_bound || cfg->learn_upper_bound)),
+                    "Cannot instantiate a circular spline with learnable limits.");
+    (void)io;
+    return 0;
+}
+
+}  // namespace
+}  // namespace tfepb
+
+using namespace tfepb;
+
+extern "C" int tfepb_affine(const tfepb_tx_io* io, tfepb_stream_t stream) {
+    if (int rc = check_io(io, nullptr)) return rc;
+    if (io->dtype == TFEPB_F32) return run<float>(io, nullptr, AffineOp<float>{}, as_stream(stream), "affine");
+    return run<double>(io, nullptr, AffineOp<double>{}, as_stream(stream), "affine");
+}
+
+extern "C" int tfepb_affine_backward(const tfepb_tx_io* io, const tfepb_tx_grads* g, tfepb_stream_t stream) {
+    TFEPB_CHECK_ARG(g != nullptr, "null gradient struct");
+    if (int rc = check_io(io, g)) return rc;
+    if (io->dtype == TFEPB_F32) return run<float>(io, g, AffineOp<float>{}, as_stream(stream), "affine_backward");
+    return run<double>(io, g, AffineOp<double>{}, as_stream(stream), "affine_backward");
+}
+
+extern "C" int tfepb_sos(const tfepb_tx_io* io, int32_t n_polynomials, tfepb_stream_t stream) {
+    if (int rc = check_io(io, nullptr)) return rc;
+    TFEPB_CHECK_ARG(n_polynomials >= 2, "n_polynomials must be strictly greater than 1.");
+    TFEPB_CHECK_ARG(io->inverse == 0, "Inversion of SOS polynomial transformer has not been implemented yet.");
+    if (io->dtype == TFEPB_F32) return run<float>(io, nullptr, SosOp<float>{n_polynomials}, as_stream(stream), "sos");
+    return run<double>(io, nullptr, SosOp<double>{n_polynomials}, as_stream(stream), "sos");
+}
+
+extern "C" int tfepb_sos_backward(const tfepb_tx_io* io, int32_t n_polynomials, const tfepb_tx_grads* g,
+                                  tfepb_stream_t stream) {
+    TFEPB_CHECK_ARG(g != nullptr, "null gradient struct");
+    if (int rc = check_io(io, g)) return rc;
+    TFEPB_CHECK_ARG(n_polynomials >= 2, "n_polynomials must be strictly greater than 1.");
+    if (io->dtype == TFEPB_F32)
+        return run<float>(io, g, SosOp<float>{n_polynomials}, as_stream(stream), "sos_backward");
+    return run<double>(io, g, SosOp<double>{n_polynomials}, as_stream(stream), "sos_backward");
+}
+
+extern "C" int tfepb_moebius(const tfepb_tx_io* io, int32_t dimension, double max_radius, int32_t unit_sphere,
+                             tfepb_stream_t stream) {
+    if (int rc = check_io(io, nullptr)) return rc;
+    TFEPB_CHECK_ARG(dimension >= 1 && dimension <= 16, "dimension must be in [1, 16]");
+    TFEPB_CHECK_ARG(io->n_features % dimension == 0, "n_features must be a multiple of the vector dimension");
+    if (io->dtype == TFEPB_F32)
+        return run<float>(io, nullptr, MoebiusOp<float>{dimension, (float)max_radius, unit_sphere}, as_stream(stream), "moebius");
+    return run<double>(io, nullptr, MoebiusOp<double>{dimension, max_radius, unit_sphere}, as_stream(stream), "moebius");
+}
+
+extern "C" int tfepb_moebius_backward(const tfepb_tx_io* io, int32_t dimension, double max_radius, int32_t unit_sphere,
+                                      const tfepb_tx_grads* g, tfepb_stream_t stream) {
+    TFEPB_CHECK_ARG(g != nullptr, "null gradient struct");
+    if (int rc = check_io(io, g)) return rc;
+    TFEPB_CHECK_ARG(dimension >= 1 && dimension <= 16, "dimension must be in [1, 16]");
+    TFEPB_CHECK_ARG(io->n_features % dimension == 0, "n_features must be a multiple of the vector dimension");
+    if (io->dtype == TFEPB_F32)
+        return run<float>(io, g, MoebiusOp<float>{dimension, (float)max_radius, unit_sphere}, as_stream(stream),
+                          "moebius_backward");
+    return run<double>(io, g, MoebiusOp<double>{dimension, max_radius, unit_sphere}, as_stream(stream), "moebius_backward");
+}
+
+extern "C" int tfepb_spline(const tfepb_tx_io* io, const tfepb_spline_cfg* cfg, tfepb_stream_t stream) {
+    if (int rc = check_io(io, nullptr)) return rc;
+    if (int rc = check_spline(io, cfg)) return rc;
+    if (io->dtype == TFEPB_F32) return spline_dispatch<float>(io, cfg, nullptr, as_stream(stream));
+    return spline_dispatch<double>(io, cfg, nullptr, as_stream(stream));
+}
+
+extern "C" int tfepb_spline_backward(const tfepb_tx_io* io, const tfepb_spline_cfg* cfg, const tfepb_tx_grads* g,
+                                     tfepb_stream_t stream) {
+    TFEPB_CHECK_ARG(g != nullptr, "null gradient struct");
+    if (int rc = check_io(io, g)) return rc;
+    if (int rc = check_spline(io, cfg)) return rc;
+    if (io->dtype == TFEPB_F32) return spline_dispatch<float>(io, cfg, g, as_stream(stream));
+    return spline_dispatch<double>(io, cfg, g, as_stream(stream));
+}

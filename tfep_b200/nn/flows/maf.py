@@ -1,0 +1,206 @@
+"""Masked autoregressive flow layer (reference tfep/nn/flows/maf.py:33-194).
+
+Same constructor arguments, parameter / buffer names and return values as the reference ``MAF``.  The
+evaluation is re-designed:
+
+* forward: the MADE conditioner runs in degree-sorted packed order (``tfep_b200._pack.MadePlan``) with
+  its output layer packed feature-major, so every GEMM skips the all-zero part of its masked weights,
+  ELU is fused in the GEMM epilogue and the transformer kernels read each feature's parameters as one
+  contiguous run;
+* inverse: ONE degree-ordered sweep through the packed network (each hidden unit and each output row
+  is computed exactly once, when everything it depends on is known) instead of the reference's
+  ``n_degrees`` full conditioner + transformer passes (autoregressive.py:216-227).  The result is the
+  same map; the log-det is accumulated per degree group and equals the reference's last-pass value.
+"""
+
+from collections.abc import Sequence
+from typing import Optional, Union
+
+import torch
+
+from ... import _ops, _program
+from ..._ops import ParamLayout
+from ..._pack import MadePlan
+from ...utils.misc import ensure_tensor_sequence
+from ..conditioners.made import MADE
+from ..transformers.affine import AffineTransformer
+from ..transformers.transformer import Transformer
+from .autoregressive import AutoregressiveFlow
+
+
+class MAF(AutoregressiveFlow):
+    """Masked Autoregressive Flow: an autoregressive flow with a MADE conditioner and any MAF transformer.
+
+    Parameters
+    ----------
+    degrees_in : Sequence[int]
+        Degree of each input; consecutive values starting from 0, or -1 for conditioning features (which
+        affect every output but are not mapped).
+    transformer : MAFTransformer, optional
+        Default: :class:`AffineTransformer`.
+    hidden_layers : int, Sequence[int] or Sequence[Sequence[int]]
+        See :class:`tfep_b200.nn.conditioners.MADE`.
+    embedding : torch.nn.Module, optional
+        Applied to the conditioner input; must implement ``get_degrees_out(degrees_in)``.
+    weight_norm : bool
+    initialize_identity : bool
+    """
+
+    def __init__(
+            self,
+            degrees_in: Sequence[int],
+            transformer: Optional[torch.nn.Module] = None,
+            hidden_layers: Union[int, Sequence[int], Sequence[Sequence[int]]] = 2,
+            embedding: Optional[torch.nn.Module] = None,
+            weight_norm: bool = True,
+            initialize_identity: bool = True,
+    ):
+        if transformer is None:
+            transformer = AffineTransformer()
+        degrees_in = ensure_tensor_sequence(degrees_in)
+        min_degree_in = degrees_in.min().tolist()
+        max_degree_in = degrees_in.max().tolist()
+        if ((set(degrees_in.tolist()) != set(range(min_degree_in, max_degree_in + 1))) or
+                (min_degree_in not in {-1, 0})):
+            raise ValueError('degrees_in must assume consecutive values starting '
+                             'from 0 (or -1 for conditioning input features).')
+        degrees_in_embedded = degrees_in if embedding is None else embedding.get_degrees_out(degrees_in)
+        transformer_indices = [(degrees_in == degree).nonzero().flatten() for degree in range(max_degree_in + 1)]
+        degrees_out = transformer.get_degrees_out(degrees_in[degrees_in != -1])
+
+        super().__init__(
+            n_features_in=len(degrees_in),
+            transformer_indices=transformer_indices,
+            conditioner=_EmbeddedMADE(embedding=embedding, degrees_in=degrees_in_embedded, degrees_out=degrees_out,
+                                      hidden_layers=hidden_layers, weight_norm=weight_norm),
+            transformer=transformer,
+            initialize_identity=initialize_identity,
+        )
+        self._embedding = embedding
+        self._degrees_in_host = degrees_in.long().cpu().clone()
+        self._packing = None
+
+    def n_parameters(self) -> int:
+        """The total number of (unmasked) parameters."""
+        return self._conditioner.n_parameters()
+
+    # -- packed fast path -------------------------------------------------------------------------
+    def _pack(self):
+        """Build (once) the packed plan: output rows grouped per feature, features sorted by degree."""
+        if self._packing is not None:
+            return self._packing
+        if not isinstance(self._transformer, Transformer):
+            self._packing = False
+            return False
+        parts = self._native_parts()
+        deg = self._degrees_in_host
+        feats = []                                   # (degree, x column, part index, local feature)
+        for pi, p in enumerate(parts):
+            for f, c in enumerate(p.x_columns().tolist()):
+                feats.append((int(deg[c]), c, pi, f))
+        feats.sort()
+        out_order, bases = [], [torch.zeros(p.n_features, dtype=torch.int32) for p in parts]
+        ref_cols = [p.ref_columns() for p in parts]
+        for _, _, pi, f in feats:
+            bases[pi][f] = len(out_order)
+            out_order.extend(ref_cols[pi][f].tolist())
+        made = self._conditioner
+        assert sorted(out_order) == list(range(made.dimension_out)), 'transformer program does not cover the conditioner output'
+        plan = MadePlan(made._degree_chain, out_order=torch.tensor(out_order))
+        # row range of the packed output layer owned by each degree group, and its features per part
+        groups = []
+        pos = 0
+        for g, cols in enumerate(self._groups_host):
+            gset = set(cols.tolist())
+            sel = [(pi, f) for d, c, pi, f in feats if c in gset]
+            width = sum(parts[pi].n_params for pi, _ in sel)
+            groups.append(dict(degree=g, rows=(pos, pos + width),
+                               ids=[[f for pi2, f in sel if pi2 == pi] for pi in range(len(parts))]))
+            pos += width
+        self._packing = dict(parts=parts, plan=plan, bases=bases, groups=groups, dev={})
+        return self._packing
+
+    def _packed_tables(self, device):
+        pk = self._pack()
+        key = str(device)
+        if key not in pk['dev']:
+            layouts = [ParamLayout(0, 1, 0, base=b.to(device)) for b in pk['bases']]
+            gids = [[torch.tensor(ids, dtype=torch.int32, device=device) if ids else None for ids in g['ids']]
+                    for g in pk['groups']]
+            pk['dev'][key] = (layouts, gids)
+        return pk['dev'][key]
+
+    def forward(self, x: torch.Tensor):
+        """Returns ``(y, log_det_J)`` with shapes ``(batch, n_features)`` and ``(batch,)``."""
+        pk = self._pack()
+        if pk is False or self._n_conditioner_indices > 0:
+            return super().forward(x)
+        layouts, _ = self._packed_tables(x.device)
+        xc = x if self._embedding is None else self._embedding(x)
+        par = self._conditioner.run_plan(xc.contiguous(), pk['plan'])
+        return _program.run(pk['parts'], x.contiguous(), par, layouts, passthrough=self.has_fixed_indices)
+
+    def inverse(self, y: torch.Tensor):
+        """Returns ``(x, log_det_J)``: degree-ordered sweep (see the module docstring)."""
+        pk = self._pack()
+        if pk is False or self._n_conditioner_indices > 0 or self._embedding is not None:
+            return super().inverse(y)
+        if any(p.kind == 'sos' for p in pk['parts']):
+            raise NotImplementedError('Inversion of SOS polynomial transformer has not been implemented yet.')
+        if torch.is_grad_enabled() and (y.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError('tfep_b200: MAF.inverse is not differentiable yet; call it under torch.no_grad()')
+        y = y.contiguous()
+        plan, parts, groups = pk['plan'], pk['parts'], pk['groups']
+        layouts, gids = self._packed_tables(y.device)
+        made = self._conditioner
+        with torch.no_grad():
+            pw, pb = made.packed_weights(plan)
+            L = plan.n_layers
+            B = y.shape[0]
+            x = torch.zeros_like(y)
+            if self.has_fixed_indices:
+                x[:, self._fixed_indices] = y[:, self._fixed_indices]
+            hidden = [None] + [torch.empty(B, pw[l].shape[0], dtype=y.dtype, device=y.device) for l in range(L - 1)]
+            max_width = max(g['rows'][1] - g['rows'][0] for g in groups)
+            par = torch.empty(B, max_width, dtype=y.dtype, device=y.device)
+            log_det_J = torch.zeros(B, dtype=y.dtype, device=y.device)
+
+            def update_hidden(degree):
+                for l in range(1, L):
+                    a, b = plan.degree_rows(l, degree)
+                    if a == b:
+                        continue
+                    if l == 1:
+                        src = x
+                    else:
+                        src = hidden[l - 1][:, :plan.degree_prefix(l - 1, degree, strict=False)]
+                    _ops.linear_forward(src, pw[l - 1][a:b, :src.shape[1]], pb[l - 1][a:b], _ops.ACT_ELU,
+                                        out=hidden[l][:, a:b])
+
+            if int(self._degrees_in_host.min()) == -1:
+                update_hidden(-1)
+            first = True
+            for g, grp in enumerate(groups):
+                r0, r1 = grp['rows']
+                src = x if L == 1 else hidden[L - 1][:, :plan.degree_prefix(L - 1, grp['degree'], strict=True)]
+                out = par[:, :r1 - r0]
+                _ops.linear_forward(src, pw[L - 1][r0:r1, :src.shape[1]], pb[L - 1][r0:r1], _ops.ACT_NONE, out=out)
+                shifted = [ParamLayout(-r0, 1, 0, base=lay.base) for lay in layouts]
+                launched = _program.run_group(parts, shifted, gids[g], y, x, par, log_det_J, inverse=True, first=first)
+                first = first and not launched
+                if g != len(groups) - 1:
+                    update_hidden(grp['degree'])
+        return x, log_det_J
+
+
+class _EmbeddedMADE(MADE):
+    """A MADE conditioner whose input optionally goes through an embedding layer first (reference maf.py:184-194)."""
+
+    def __init__(self, embedding, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.embedding = embedding
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.embedding is not None:
+            x = self.embedding(x)
+        return super().forward(x)

@@ -1,0 +1,8 @@
+"""Transformers for autoregressive normalizing flows (reference tfep/nn/transformers/__init__.py)."""
+
+from .affine import AffineTransformer, affine_transformer, affine_transformer_inverse
+from .mixed import MixedTransformer
+from .moebius import MoebiusTransformer, moebius_transformer
+from .sos import SOSPolynomialTransformer, sos_polynomial_transformer
+from .spline import NeuralSplineTransformer, neural_spline_transformer
+from .transformer import MAFTransformer, Transformer
