@@ -72,7 +72,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
     def __exit__(self, *exc):
         if self.proc is not None:
@@ -82,10 +82,12 @@ class ClockSampler:
             except subprocess.TimeoutExpired:
                 self.proc.kill()
 
-    def summary(self):
+    def summary(self, t0=None, t1=None):
         sm, mx, reasons = [], [], set()
         names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
-        for line in self.lines:
+        for t, line in self.lines:
+            if (t0 is not None and t < t0) or (t1 is not None and t > t1):
+                continue
             parts = [p.strip() for p in line.split(',')]
             if len(parts) < 6:
                 continue
@@ -171,19 +173,27 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    clocks = ClockSampler(local_rank).__enter__()
+    time.sleep(0.6)                             # let nvidia-smi start sampling
     for _ in range(args.warmup):
         step()
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local_rank) as clocks:
-        t_wall0 = time.perf_counter()
-        for a, b in ev:
-            flush.zero_()                       # L2 flush between timed iterations (untimed)
-            a.record()
-            y, ld = step()
-            b.record()
+    t_load0 = time.perf_counter()
+    t_wall0 = time.perf_counter()
+    for a, b in ev:
+        flush.zero_()                           # L2 flush between timed iterations (untimed)
+        a.record()
+        y, ld = step()
+        b.record()
+    torch.cuda.synchronize(dev)
+    t_wall = time.perf_counter() - t_wall0
+    # keep the same load running (untimed) until the 100 ms clock sampler has seen at least ~1 s of it
+    while time.perf_counter() - t_load0 < 1.0:
+        step()
         torch.cuda.synchronize(dev)
-        t_wall = time.perf_counter() - t_wall0
+    t_load1 = time.perf_counter()
+    clocks.__exit__()
     ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
     barrier()
@@ -261,7 +271,7 @@ def run_ours(args, rank, world, local_rank):
         'config': {'workload': WORKLOAD, 'precision': args.precision, 'l2': 'flushed (256 MB memset) between timed steps',
                    'parallelism': f'batch-sharded x{world}, weights replicated, no data-path collective',
                    'wall_s_timed_region': t_wall},
-        'clocks': clocks.summary(),
+        'clocks': clocks.summary(t_load0, t_load1),
         'e2e': {'value': BATCH * world * args.steps / (e2e_ms * 1e-3), 'unit': UNIT,
                 'h2d_bytes_per_step': x_host.numel() * 4, 'd2h_bytes_per_step': (y_host.numel() + ld_host.numel()) * 4},
         'gpu_launches': 16 * args.steps,

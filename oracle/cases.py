@@ -62,6 +62,30 @@ def _spline(n, dtype, **kw):
     return fo.Spline(x0=torch.full((n,), x0, dtype=dtype), xf=torch.full((n,), xf, dtype=dtype), **kw)
 
 
+def as_double(spec):
+    """The same transformer spec with float64 constants (to evaluate fp32 inputs in double)."""
+    if isinstance(spec, fo.Spline):
+        return fo.Spline(x0=spec.x0.double(), xf=spec.xf.double(), n_bins=spec.n_bins, y0=spec.y0.double(),
+                         yf=spec.yf.double(), circular=spec.circular,
+                         identity_boundary_slopes=spec.identity_boundary_slopes,
+                         learn_lower_bound=spec.learn_lower_bound, learn_upper_bound=spec.learn_upper_bound,
+                         min_bin_size=spec.min_bin_size, min_slope=spec.min_slope)
+    if isinstance(spec, fo.Mixed):
+        return fo.Mixed([as_double(t) for t in spec.transformers], [i.tolist() for i in spec.indices])
+    return spec
+
+
+def double_reference(spec, x, par, inverse=False):
+    """Evaluate ``spec`` in float64 on (the exact values of) lower-precision inputs."""
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        d = as_double(spec)
+        return (d.inverse if inverse else d.forward)(x.double(), par.double())
+    finally:
+        torch.set_default_dtype(old)
+
+
 def transformer_cases(dtype=torch.float32):
     """name -> (spec, n_features, x, params); small and cheap."""
     B = 24

@@ -104,7 +104,9 @@ def test_bootstrap_biased_data_and_errors():
 def test_philox_bootstrap_is_statistically_equivalent():
     from tfep_b200.analysis import bootstrap, fep_estimator
     w = cases.normal((200000,), 5).to(DEV)
-    a = bootstrap(w, fep_estimator, n_resamples=300, generator=torch.Generator().manual_seed(1))
-    b = bootstrap(w, fep_estimator, n_resamples=300, generator=torch.Generator().manual_seed(1), rng='philox')
-    assert abs(float(a['mean']) - float(b['mean'])) < 3 * float(a['standard_deviation']) / 300 ** 0.5 + 1e-4
-    assert 0.7 < float(b['standard_deviation']) / float(a['standard_deviation']) < 1.4
+    R = 2000
+    a = bootstrap(w, fep_estimator, n_resamples=R, batch=100, generator=torch.Generator().manual_seed(1))
+    b = bootstrap(w, fep_estimator, n_resamples=R, generator=torch.Generator().manual_seed(1), rng='philox')
+    # two independent bootstrap means differ by ~ sqrt(2) sigma / sqrt(R); allow 5 of those
+    assert abs(float(a['mean']) - float(b['mean'])) < 5 * 2 ** 0.5 * float(a['standard_deviation']) / R ** 0.5
+    assert 0.85 < float(b['standard_deviation']) / float(a['standard_deviation']) < 1.18

@@ -24,18 +24,29 @@ def prec(request):
 
 def test_forward_inverse_against_golden(prec):
     g = golden(f'transformers_{prec}.npz')
+    g64 = golden('transformers_f64.npz')
     for name, (spec, n, x, par) in cases.transformer_cases(DT[prec]).items():
         mod = to_module(spec).to(DEV)
         y, ld = mod(x.to(DEV), par.to(DEV))
-        assert rel_err(y, g[f'{name}/y']) < TOL[prec], name
-        assert rel_err(ld, g[f'{name}/ld']) < TOL[prec], name
+        # Non-circular splines with inputs in the far tails: the fp32 reference is itself only ~1e-4 accurate
+        # there (it subtracts knots placed at 1000 x the domain width); the kernels
+        # evaluate the analytically identical linear map, so those cases are held to the reference's DOUBLE
+        # result (same inputs up to fp32 rounding) at the same 1e-5.
+        tails = prec == 'f32' and f'{name}/bins' in g and bool(((g[f'{name}/bins'] == 0) |
+                                                                (g[f'{name}/bins'] == spec.n_bins + 1)).any())
+        ref = g64 if tails else g
+        assert rel_err(y, ref[f'{name}/y']) < TOL[prec], name
+        assert rel_err(ld, ref[f'{name}/ld']) < TOL[prec], name
         if isinstance(spec, fo.SOS):
             with pytest.raises(NotImplementedError):
                 mod.inverse(y, par.to(DEV))
             continue
         xi, ldi = mod.inverse(torch.from_numpy(g[f'{name}/y']).to(DEV), par.to(DEV))
-        assert rel_err(xi, g[f'{name}/xinv']) < 5 * TOL[prec], name
-        assert rel_err(ldi, g[f'{name}/ldinv']) < 5 * TOL[prec], name
+        assert rel_err(xi, g[f'{name}/xinv' if not tails else f'{name}/xinv']) < (5 * TOL[prec] if not tails else 2e-3), name
+        assert rel_err(ldi, g[f'{name}/ldinv']) < (5 * TOL[prec] if not tails else 2e-3), name
+        if tails:
+            xi64, ldi64 = cases.double_reference(spec, torch.from_numpy(g[f'{name}/y']), par, inverse=True)
+            assert rel_err(xi, xi64) < 5 * TOL[prec] and rel_err(ldi, ldi64) < 5 * TOL[prec], name
 
 
 def test_round_trip(prec):
@@ -109,8 +120,10 @@ def test_ragged_and_empty_batches():
     mod = to_module(spec).to(DEV)
     for B in (0, 1, 7, 24):
         y, ld = mod(x[:B].to(DEV), par[:B].to(DEV))
-        y_o, ld_o = spec.forward(x[:B], par[:B])
         assert y.shape == (B, n) and ld.shape == (B,)
+        if B == 0:
+            continue                     # the reference cannot reshape an empty parameter tensor
+        y_o, ld_o = cases.double_reference(spec, x[:B], par[:B])
         assert rel_err(y, y_o) < 1e-5 and rel_err(ld, ld_o) < 1e-5
 
 

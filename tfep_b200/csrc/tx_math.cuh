@@ -354,6 +354,23 @@ TFEPB_HD void spline_eval(const SplineFeat<T>& c, const ParIn<T>& par, T t, T& o
         dk = b == 0 ? d0 : spline_slope<T, MAXK>(c, par, st, b);
         dk1 = b + 1 == K ? dK : spline_slope<T, MAXK>(c, par, st, b + 1);
     }
+    // Far tails: the reference evaluates the generic formula on a fake bin of width 1000 W
+    // (spline.py:596-614), which is exactly linear in exact arithmetic but loses ~3 digits in fp32
+    // (SURVEY.md Appendix C-11).  The analytically identical linear map is evaluated instead.
+    if (bin == 0 || bin == K + 1) {
+        const T xe = bin == 0 ? st.x0 : xk;      // edge knot of the spline domain
+        const T ye = bin == 0 ? st.y0 : yk;
+        if (!INVERSE) {
+            out = ye + dk * (t - xe);
+            ld = Math<T>::log(dk);
+        } else {
+            T x = xe + (t - ye) / dk;
+            ld = -Math<T>::log(dk);
+            if (c.circular) x = py_remainder(x - st.x0 - shift, c.xf - st.x0) + st.x0;
+            out = x;
+        }
+        return;
+    }
     const T s = hs / ws;
     if (!INVERSE) {
         const T e = (t - xk) / ws;
