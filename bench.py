@@ -158,6 +158,8 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     seq, _ = cfg_flow_modules('cfg2', dev)
     seq.eval()
+    for maf in seq:
+        maf.precision = args.precision
     # contiguous batch shards of one global synthetic data set (seeded on the host)
     x_host = cases.cfg_input('cfg2', BATCH * world)[rank * BATCH:(rank + 1) * BATCH].contiguous().pin_memory()
     x = x_host.to(dev)
@@ -230,32 +232,53 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
 
-    # roofline of the dominant kernel: the output-layer GEMM (328 -> 1650) of one MAF layer, timed alone
+    pk_peaks = peaks()
     pk = seq[0]._pack()
     plan = pk['plan']
-    with torch.no_grad():
-        pw, pb = seq[0]._conditioner.packed_weights(plan)
-        k_ranges, _, _ = plan.tables(dev)
-        h = torch.randn(BATCH, pw[2].shape[1], device=dev)
-        out = torch.empty(BATCH, pw[2].shape[0], device=dev)
-        for _ in range(3):
-            _ops.linear_forward(h, pw[2], pb[2], 0, k_ranges[2], out=out)
-        kev = []
-        for _ in range(10):
-            flush.zero_()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            _ops.linear_forward(h, pw[2], pb[2], 0, k_ranges[2], out=out)
-            e.record()
-            kev.append((s, e))
-        torch.cuda.synchronize(dev)
-    k_ms = statistics.mean(s.elapsed_time(e) for s, e in kev)
-    pk_peaks = peaks()
-    flops_per_launch = 2.0 * plan.nnz[2] * BATCH           # algorithmic: 2 x non-zeros of the mask x samples
+    if args.precision == 'bf16':
+        # dominant (only) kernel: the fused MAF-layer kernel, one launch per layer, timed alone
+        fused = seq[0]._fused
+        with torch.no_grad():
+            for _ in range(3):
+                fused.forward(seq[0], x)
+            kev = []
+            for _ in range(10):
+                flush.zero_()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                fused.forward(seq[0], x)
+                e.record()
+                kev.append((s, e))
+            torch.cuda.synchronize(dev)
+        k_ms = statistics.mean(s.elapsed_time(e) for s, e in kev)
+        flops_per_launch = 2.0 * plan.masked_macs * BATCH        # algorithmic: 2 x non-zeros of the three masks
+        kernel = 'maf_spline_fwd_kernel (one MAF layer: 3 masked GEMMs on tcgen05 + ELU + spline epilogue)'
+        launches_per_step = len(seq)
+    else:
+        # dominant kernel of the exact path: the output-layer GEMM (328 -> 1650) of one MAF layer, timed alone
+        with torch.no_grad():
+            pw, pb = seq[0]._conditioner.packed_weights(plan)
+            k_ranges, _, _ = plan.tables(dev)
+            h = torch.randn(BATCH, pw[2].shape[1], device=dev)
+            out = torch.empty(BATCH, pw[2].shape[0], device=dev)
+            for _ in range(3):
+                _ops.linear_forward(h, pw[2], pb[2], 0, k_ranges[2], out=out)
+            kev = []
+            for _ in range(10):
+                flush.zero_()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                _ops.linear_forward(h, pw[2], pb[2], 0, k_ranges[2], out=out)
+                e.record()
+                kev.append((s, e))
+            torch.cuda.synchronize(dev)
+        k_ms = statistics.mean(s.elapsed_time(e) for s, e in kev)
+        flops_per_launch = 2.0 * plan.nnz[2] * BATCH           # algorithmic: 2 x non-zeros of the mask x samples
+        kernel = 'gemm_kernel<float,true,true> (output layer 328->1650, fp32 FFMA, staircase-skipped)'
+        launches_per_step = 16
     achieved = flops_per_launch / (k_ms * 1e-3) / 1e12
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': pk_peaks['bf16_tflops'], 'unit': 'TFLOP/s',
-                'frac': achieved / pk_peaks['bf16_tflops'], 'traffic': None,
-                'kernel': 'gemm_kernel<float,true,true> (output layer 328->1650, fp32 FFMA, staircase-skipped)',
+                'frac': achieved / pk_peaks['bf16_tflops'], 'traffic': None, 'kernel': kernel,
                 'kernel_ms': k_ms, 'peak_source': pk_peaks['source'] + ', bf16 burst',
                 'whole_step_frac': (2.0 * plan.masked_macs * 4 * BATCH * args.steps / (total_ms * 1e-3) / 1e12)
                 / pk_peaks['bf16_tflops_sustained']}
@@ -267,14 +290,14 @@ def run_ours(args, rank, world, local_rank):
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32', 'data': 'synthetic',
+        'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'precision': args.precision, 'l2': 'flushed (256 MB memset) between timed steps',
                    'parallelism': f'batch-sharded x{world}, weights replicated, no data-path collective',
                    'wall_s_timed_region': t_wall},
         'clocks': clocks.summary(t_load0, t_load1),
         'e2e': {'value': BATCH * world * args.steps / (e2e_ms * 1e-3), 'unit': UNIT,
                 'h2d_bytes_per_step': x_host.numel() * 4, 'd2h_bytes_per_step': (y_host.numel() + ld_host.numel()) * 4},
-        'gpu_launches': 16 * args.steps,
+        'gpu_launches': launches_per_step * args.steps,
         'roofline': roofline,
         'cpu_baseline': {'value': cpu_value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': f'{sample} samples x {len(times)} passes of the same cfg2 forward, fp32, no_grad'},
@@ -288,7 +311,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--precision', default='fp32', choices=['fp32'])
+    ap.add_argument('--precision', default='bf16', choices=['fp32', 'bf16'])
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))

@@ -167,6 +167,44 @@ int tfepb_moebius_backward(const tfepb_tx_io* io, int32_t dimension, double max_
                            const tfepb_tx_grads* g, tfepb_stream_t stream);
 
 /* ----------------------------------------------------------------------------------------------
+ * Fused MAF layer forward on the tensor cores (tcgen05 / TMEM / bulk-copy engine), bf16 operands with
+ * fp32 accumulation: y, logdet = T(x ; MADE(x)) for a MADE with two hidden layers and a circular
+ * neural-spline transformer with 8 bins.  Replaces, in one launch per MAF layer,
+ * AutoregressiveFlow.forward (nn/flows/autoregressive.py:144-177): the three masked linear layers
+ * (nn/masked.py:266-277), the two ELUs (nn/conditioners/made.py:320) and NeuralSplineTransformer.forward
+ * (nn/transformers/spline.py:184-241).  The caller packs the degree-sorted effective weights into
+ * shared-memory-image blocks and lists the non-zero blocks in `ops` (tfep_b200/_fused.py documents the
+ * format); masked blocks are simply absent from the schedule.
+ * -------------------------------------------------------------------------------------------- */
+typedef struct {
+    uint32_t w_off, w_bytes;             /* block position in `weights` (bytes, multiple of 16) and size */
+    uint16_t n, tmem_col, ksteps, a_slab0;
+    uint32_t flags;                      /* 1 first block of accumulator, 2 commit, 4 accumulator 1,
+                                            16 wait for A operand, 32 wait for drained accumulator */
+} tfepb_fused_op;
+
+typedef struct {
+    int32_t col;                         /* column of the feature in x / y; -1 = padding slot */
+    float x0, period, inv_period, rescaled_width, rescaled_height, y0;
+} tfepb_fused_feature;
+
+typedef struct {
+    const void* x; void* y; void* logdet;          /* fp32 (batch, n_features), (batch, n_features), (batch,) */
+    int32_t batch, n_features;
+    int32_t k1, hidden_padded, n_chunks, n_ops;
+    const tfepb_fused_op* ops;                     /* device */
+    const void* weights;                           /* device, packed bf16 blocks */
+    const float* bias;                             /* device: [hidden_padded | hidden_padded | n_chunks * 208] */
+    const tfepb_fused_feature* feats;              /* device: n_chunks * 8 */
+    float min_bin_size, min_slope, slope_offset;   /* slope_offset = log(exp(1 - min_slope) - 1) */
+    int32_t reserved;
+    int32_t* error_flag;                           /* device int, set if an internal wait times out; may be NULL */
+    float* debug_params;                           /* NULL, or (batch, n_chunks * 208): conditioner outputs (+bias)
+                                                      in packed order, for parity tests of the GEMM chain */
+} tfepb_fused_args;
+int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------------
  * (T)FEP estimator and bootstrap
  * -------------------------------------------------------------------------------------------- */
 /* One pass over v_i = scale * w_i (+ logw_i): writes out[0] = max_i v_i, out[1] = sum_i exp(v_i - max)

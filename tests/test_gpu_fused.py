@@ -1,0 +1,95 @@
+"""Fused tcgen05 / TMEM / bulk-copy MAF layer (precision='bf16') against the oracle.
+
+Stated tolerance of the bf16 tensor-core variant (north_star: "within a stated tolerance against an fp64
+reference"): operands (x, weights, hidden activations) are rounded to bf16 (8-bit mantissa), accumulation
+and the whole spline epilogue are fp32.  Against the fp64 reference of one MAF layer of the headline
+configuration that gives |dy| <= 2e-2 (mean ~6e-4) modulo the period and |d logdet| <= 5e-2 (mean ~3e-3);
+against a reference that applies the SAME bf16 roundings the kernel must agree to 2e-3 (summation order and
+fast-math intrinsics only) -- that second check is what pins the GEMM chain, layouts and schedule.
+"""
+
+import math
+
+import pytest
+import torch
+
+from helpers import cfg_flow_modules
+from oracle import cases
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).double()
+
+
+def _emulated_layer(oracle, x):
+    """One MAF layer in double with the kernel's bf16 operand roundings."""
+    (w1, b1), (w2, b2), (w3, b3) = [(w.double(), b.double()) for w, b in oracle.layers]
+    h = torch.nn.functional.elu(_bf(x) @ _bf(w1).T + b1)
+    h = torch.nn.functional.elu(_bf(h.float()) @ _bf(w2).T + b2)
+    par = _bf(h.float()) @ _bf(w3).T + b3
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        return cases.as_double(oracle.transformer).forward(x.double(), par)
+    finally:
+        torch.set_default_dtype(old)
+
+
+def _circ(a, b):
+    d = (a.double().cpu() - b.double().cpu()).abs()
+    return torch.minimum(d, (2 * math.pi - d).abs())
+
+
+@pytest.mark.parametrize('batch', [1, 127, 128, 300, 1000])
+def test_layers_against_bf16_emulation_and_fp64(batch):
+    seq, flows = cfg_flow_modules('cfg2', DEV, n_layers=2)
+    x = cases.cfg_input('cfg2', batch)
+    for maf, (oracle, _) in zip(seq, flows):        # ascending and descending degree layers
+        maf.precision = 'bf16'
+        with torch.no_grad():
+            y, ld = maf(x.to(DEV))
+        y_e, ld_e = _emulated_layer(oracle, x)
+        assert float(_circ(y, y_e).max()) < 2e-3 and float((ld.cpu().double() - ld_e).abs().max()) < 2e-3
+        y64, ld64 = oracle.forward(x)               # fp32 oracle ~ fp64 at this scale
+        assert float(_circ(y, y64).max()) < 2e-2 and float(_circ(y, y64).mean()) < 2e-3
+        assert float((ld.cpu() - ld64).abs().max()) < 5e-2 and float((ld.cpu() - ld64).abs().mean()) < 8e-3
+        assert y.shape == (batch, 66) and ld.shape == (batch,)
+
+
+def test_full_batch_properties_and_agreement_with_fp32_path():
+    seq, _ = cfg_flow_modules('cfg2', DEV)
+    x = cases.cfg_input('cfg2', 65536).to(DEV)
+    with torch.no_grad():
+        y32, ld32 = seq(x)
+        for maf in seq:
+            maf.precision = 'bf16'
+        y, ld = seq(x)
+        y2, ld2 = seq(x)
+        assert torch.equal(y, y2) and torch.equal(ld, ld2)                       # deterministic
+        ys, lds = seq(x[4096:4096 + 777])
+        assert torch.equal(ys, y[4096:4096 + 777]) and torch.equal(lds, ld[4096:4096 + 777])   # tile-position invariant
+    assert bool(torch.isfinite(y).all()) and bool(torch.isfinite(ld).all())
+    # Four stacked layers: a sample whose intermediate y lands within the bf16 error of the +-pi seam is
+    # wrapped to the other side and then follows a different (equally valid) branch of the NEXT layer's
+    # conditioner, so agreement is stated for the bulk of the samples.
+    d = _circ(y, y32).max(dim=1).values
+    assert float(d.median()) < 5e-3
+    assert float((d < 5e-2).float().mean()) > 0.97
+    assert float((ld - ld32).abs().median()) < 2e-2
+
+
+def test_inference_only_and_eligibility():
+    from tfep_b200._lib import TfepB200Error
+    from tfep_b200.nn.conditioners import generate_degrees
+    from tfep_b200.nn.flows import MAF
+    seq, _ = cfg_flow_modules('cfg2', DEV, n_layers=1)
+    seq[0].precision = 'bf16'
+    with pytest.raises(NotImplementedError, match='inference path'):
+        seq[0](cases.cfg_input('cfg2', 8).to(DEV))          # parameters require grad and grad mode is on
+    affine = MAF(generate_degrees(6), initialize_identity=False).to(DEV)
+    affine.precision = 'bf16'
+    with pytest.raises(TfepB200Error, match='fused bf16 path unavailable'), torch.no_grad():
+        affine(torch.randn(4, 6, device=DEV))

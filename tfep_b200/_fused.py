@@ -1,0 +1,225 @@
+"""Host side of the fused tensor-core MAF layer (tfepb_maf_spline_forward_bf16).
+
+Builds, once per MAF layer, the block schedule the kernel walks and, whenever the parameters change,
+the packed bf16 weight stream:
+
+* hidden units degree-sorted, output layer feature-major with features sorted by degree
+  (tfep_b200/_pack.py), zero-padded to multiples of 16;
+* every GEMM is cut into blocks of at most 208 rows x 64 k; a block is stored as the exact image of its
+  shared-memory layout (K-major core matrices: for each group of 8 k-values, all rows x 16 bytes), so the
+  bulk-copy engine moves it with one linear copy;
+* the schedule lists only blocks that intersect the staircase of the autoregressive mask
+  (``deg_out >= deg_in`` for hidden layers, ``>`` for the output layer; reference nn/masked.py:90-99):
+  for a tile of output rows the reduction stops at the last input unit they may see.
+"""
+
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+TILE_M = 128
+STAGE_BYTES = 208 * 64 * 2
+FEATS_PER_CHUNK = 8
+NPAR = 25
+CHUNK_N = 208
+ACC1_COL = 256
+OP_FIRST, OP_COMMIT, OP_ACC1, OP_WAIT_A, OP_WAIT_EMPTY = 1, 2, 4, 16, 32
+
+OP_DTYPE = np.dtype([('w_off', '<u4'), ('w_bytes', '<u4'), ('n', '<u2'), ('tmem_col', '<u2'), ('ksteps', '<u2'),
+                     ('a_slab0', '<u2'), ('flags', '<u4')])
+FEAT_DTYPE = np.dtype([('col', '<i4'), ('x0', '<f4'), ('period', '<f4'), ('inv_period', '<f4'), ('rw', '<f4'),
+                       ('rh', '<f4'), ('y0', '<f4')])
+
+
+def _ceil16(n):
+    return (n + 15) // 16 * 16
+
+
+def eligibility(maf):
+    """None if the fused kernel covers this MAF layer, else the reason it does not."""
+    from .nn.transformers.spline import NeuralSplineTransformer
+    t = maf._transformer
+    if not isinstance(t, NeuralSplineTransformer):
+        return 'transformer is not a NeuralSplineTransformer'
+    if not (t.circular and t.n_bins_int == 8 and not t.identity_slopes):
+        return 'only circular splines with 8 bins and free boundary slopes are fused'
+    if maf._embedding is not None or maf._n_conditioner_indices > 0:
+        return 'embeddings / conditioner_indices are not fused'
+    if len(maf._conditioner._linear_layers()) != 3:
+        return 'the fused kernel is built for two hidden layers'
+    D = len(maf._degrees_in_host)
+    if (D * 4 * TILE_M) % 16 != 0:
+        return 'row length not supported'
+    return None
+
+
+class FusedSplinePlan:
+    def __init__(self, maf):
+        why = eligibility(maf)
+        if why is not None:
+            raise _lib.TfepB200Error(f'fused bf16 path unavailable: {why}')
+        pk = maf._pack()
+        plan = pk['plan']
+        t = maf._transformer
+        self.D = len(maf._degrees_in_host)
+        self.K1 = _ceil16(self.D)
+        deg_h1, deg_h2 = plan.packed_degrees[1], plan.packed_degrees[2]
+        H1, H2 = len(deg_h1), len(deg_h2)
+        if H1 != H2:
+            raise _lib.TfepB200Error('fused bf16 path needs equal hidden widths')
+        self.H = H1
+        self.HP = _ceil16(H1)
+        if self.HP > 464:
+            raise _lib.TfepB200Error('hidden width exceeds the tensor-memory plan of the fused kernel')
+        self.perm1, self.perm2 = plan.perms[1], plan.perms[2]
+
+        # hidden-layer row chunks (<= 160 rows so that a GEMM1 block fits a ring stage)
+        n_hc = max(1, math.ceil(self.HP / 160))
+        hc = _ceil16(math.ceil(self.HP / n_hc))
+        self.hidden_chunks = [(r, min(r + hc, self.HP)) for r in range(0, self.HP, hc)]
+        assert all((b - a) * self.K1 * 2 <= STAGE_BYTES for a, b in self.hidden_chunks)
+
+        # sorted features -> chunks of 8 slots
+        part = pk['parts'][0]
+        cols = part.x_columns().tolist()
+        deg_in = maf._degrees_in_host
+        order = sorted(range(part.n_features), key=lambda f: (int(deg_in[cols[f]]), cols[f]))
+        self.n_chunks = math.ceil(len(order) / FEATS_PER_CHUNK)
+        ref_cols = part.ref_columns()                       # (F, 25) rows of the reference output layer
+        x0, xf, y0, yf = (b.detach().float().cpu() for b in (t.x0, t.xf, t._y0, t._yf))
+        feats = np.zeros(self.n_chunks * FEATS_PER_CHUNK, dtype=FEAT_DTYPE)
+        feats['col'] = -1
+        w3_rows = torch.full((self.n_chunks * CHUNK_N,), -1, dtype=torch.long)     # -1 -> zero row
+        chunk_maxdeg = []
+        for slot, f in enumerate(order):
+            c, j = divmod(slot, FEATS_PER_CHUNK)
+            L = float(xf[f] - x0[f])
+            mi = 8 * t.min_bin_size
+            feats[slot] = (cols[f], float(x0[f]), L, 1.0 / L, np.float32(L) - np.float32(mi),
+                           np.float32(float(yf[f] - y0[f])) - np.float32(mi), float(y0[f]))
+            w3_rows[c * CHUNK_N + j * NPAR:c * CHUNK_N + (j + 1) * NPAR] = ref_cols[f]
+        for c in range(self.n_chunks):
+            fs = order[c * FEATS_PER_CHUNK:(c + 1) * FEATS_PER_CHUNK]
+            chunk_maxdeg.append(max(int(deg_in[cols[f]]) for f in fs))
+        self.feats_host = feats
+        self.w3_rows = w3_rows
+
+        # ---- schedule ----
+        ops, gather = [], []           # gather: per op, index tensor into the concatenated padded matrices
+        off1, off2 = self.HP * self.K1, self.HP * self.K1 + self.HP * self.HP
+        w_off = 0
+
+        def add(n, tmem_col, kb, kmax_block, a_slab0, flags, base, ld, r0):
+            nonlocal w_off
+            ksteps = kmax_block // 16
+            rows = torch.arange(r0, r0 + n)
+            ks = torch.arange(kb, kb + kmax_block)
+            idx = (base + rows[:, None] * ld + ks[None, :]).reshape(n, 2 * ksteps, 8).permute(1, 0, 2).reshape(-1)
+            gather.append(idx)
+            nbytes = n * kmax_block * 2
+            assert nbytes <= STAGE_BYTES and nbytes % 16 == 0
+            ops.append((w_off, nbytes, n, tmem_col, ksteps, a_slab0, flags))
+            w_off += nbytes
+
+        # GEMM1: full K1 per row chunk (the first layer is tiny; no staircase)
+        for i, (a, b) in enumerate(self.hidden_chunks):
+            fl = OP_FIRST | (OP_WAIT_A if i == 0 else 0) | (OP_COMMIT if i == len(self.hidden_chunks) - 1 else 0)
+            add(b - a, a, 0, self.K1, 0, fl, 0, self.K1, a)
+        # GEMM2: rows see layer-1 units of degree <= their own
+        first = True
+        for i, (a, b) in enumerate(self.hidden_chunks):
+            real = deg_h2[a:min(b, self.H)]
+            kmax = max(16, _ceil16(int((deg_h1 <= int(real.max())).sum()))) if len(real) else 16
+            blocks = list(range(0, kmax, 64))
+            for bi, kb in enumerate(blocks):
+                fl = (OP_FIRST if bi == 0 else 0) | (OP_WAIT_A if first else 0)
+                if i == len(self.hidden_chunks) - 1 and bi == len(blocks) - 1:
+                    fl |= OP_COMMIT
+                first = False
+                add(b - a, a, kb, min(64, kmax - kb), kb // 8, fl, off1, self.HP, a)
+        # GEMM3: a chunk of features sees layer-2 units of degree < its largest degree
+        for c in range(self.n_chunks):
+            kmax = max(16, _ceil16(int((deg_h2 < chunk_maxdeg[c]).sum())))
+            blocks = list(range(0, kmax, 64))
+            acc = c & 1
+            for bi, kb in enumerate(blocks):
+                fl = (OP_ACC1 if acc else 0)
+                if bi == 0:
+                    fl |= OP_FIRST | OP_WAIT_EMPTY | (OP_WAIT_A if c == 0 else 0)
+                if bi == len(blocks) - 1:
+                    fl |= OP_COMMIT
+                add(CHUNK_N, ACC1_COL if acc else 0, kb, min(64, kmax - kb), kb // 8, fl, off2, self.HP, c * CHUNK_N)
+        self.ops_host = np.array(ops, dtype=OP_DTYPE)
+        self.gather_host = torch.cat(gather)
+        self.weight_bytes = w_off
+        self.mma_columns = int(sum(int(o[2]) * int(o[4]) for o in ops))          # sum of N x ksteps over all blocks
+        self.min_bin, self.min_slope = float(t.min_bin_size), float(t.min_slope)
+        self.slope_offset = float(math.log(math.exp(1.0 - t.min_slope) - 1.0))
+        self._dev = {}
+        self._cache = None
+
+    # ---------------------------------------------------------------------------------------------
+    def _tables(self, device):
+        key = str(device)
+        if key not in self._dev:
+            ops = torch.from_numpy(self.ops_host.view(np.uint8).copy()).to(device)
+            feats = torch.from_numpy(self.feats_host.view(np.uint8).copy()).to(device)
+            self._dev[key] = dict(ops=ops, feats=feats, gather=self.gather_host.to(device),
+                                  w3_rows=self.w3_rows.to(device), perm1=self.perm1.to(device),
+                                  perm2=self.perm2.to(device), err=torch.zeros(1, dtype=torch.int32, device=device))
+        return self._dev[key]
+
+    def pack(self, maf):
+        """Packed bf16 weight stream + fp32 biases from the current parameters (cached by parameter version)."""
+        made = maf._conditioner
+        key = made._param_versions()
+        if self._cache is not None and self._cache[0] == key:
+            return self._cache[1]
+        with torch.no_grad():
+            (w1, b1), (w2, b2), (w3, b3) = made.effective_weights()
+            dev = w1.device
+            tb = self._tables(dev)
+            H, HP, K1, D = self.H, self.HP, self.K1, self.D
+            W1p = torch.zeros(HP, K1, device=dev)
+            W1p[:H, :D] = w1.index_select(0, tb['perm1'])
+            W2p = torch.zeros(HP, HP, device=dev)
+            W2p[:H, :H] = w2.index_select(0, tb['perm2']).index_select(1, tb['perm1'])
+            rows = tb['w3_rows']
+            w3e = torch.cat([w3, torch.zeros(1, H, device=dev)], dim=0)
+            W3p = torch.zeros(len(rows), HP, device=dev)
+            W3p[:, :H] = w3e.index_select(0, torch.where(rows < 0, torch.full_like(rows, w3.shape[0]), rows)) \
+                .index_select(1, tb['perm2'])
+            src = torch.cat([W1p.flatten(), W2p.flatten(), W3p.flatten()]).to(torch.bfloat16)
+            packed = src.index_select(0, tb['gather']).contiguous()
+            b3e = torch.cat([b3, torch.zeros(1, device=dev)])
+            bias = torch.zeros(2 * HP + len(rows), device=dev)
+            bias[:H] = b1.index_select(0, tb['perm1'])
+            bias[HP:HP + H] = b2.index_select(0, tb['perm2'])
+            bias[2 * HP:] = b3e.index_select(0, torch.where(rows < 0, torch.full_like(rows, len(b3)), rows))
+        self._cache = (key, (packed, bias))
+        return self._cache[1]
+
+    def forward(self, maf, x, debug_params=None):
+        """y, log_det_J = fused layer on a contiguous fp32 CUDA tensor (no autograd)."""
+        _lib.require_cuda(x)
+        if x.dtype != torch.float32:
+            raise _lib.TfepB200Error('the fused bf16 path takes float32 inputs')
+        x = x.contiguous()
+        packed, bias = self.pack(maf)
+        tb = self._tables(x.device)
+        y = torch.empty_like(x)
+        ld = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        args = _lib.FusedArgs(x=x.data_ptr(), y=y.data_ptr(), logdet=ld.data_ptr(), batch=x.shape[0], n_features=self.D,
+                              k1=self.K1, hidden_padded=self.HP, n_chunks=self.n_chunks, n_ops=len(self.ops_host),
+                              ops=tb['ops'].data_ptr(), weights=packed.data_ptr(), bias=bias.data_ptr(),
+                              feats=tb['feats'].data_ptr(), min_bin_size=self.min_bin, min_slope=self.min_slope,
+                              slope_offset=self.slope_offset, reserved=0, error_flag=tb['err'].data_ptr(),
+                              debug_params=None if debug_params is None else debug_params.data_ptr())
+        with torch.cuda.device(x.device):
+            check(_lib.load().tfepb_maf_spline_forward_bf16(ctypes.byref(args), stream_ptr(x)))
+        return y, ld

@@ -64,6 +64,14 @@ class TxGrads(Structure):
                 ('grad_x', c_void_p), ('ldgx', c_int64), ('grad_par', c_void_p)]
 
 
+class FusedArgs(Structure):
+    _fields_ = [('x', c_void_p), ('y', c_void_p), ('logdet', c_void_p), ('batch', c_int32), ('n_features', c_int32),
+                ('k1', c_int32), ('hidden_padded', c_int32), ('n_chunks', c_int32), ('n_ops', c_int32),
+                ('ops', c_void_p), ('weights', c_void_p), ('bias', c_void_p), ('feats', c_void_p),
+                ('min_bin_size', c_float), ('min_slope', c_float), ('slope_offset', c_float), ('reserved', c_int32),
+                ('error_flag', c_void_p), ('debug_params', c_void_p)]
+
+
 # every symbol include/tfep_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     'tfepb_abi_version': (c_int32, []),
@@ -80,6 +88,7 @@ SYMBOLS = {
     'tfepb_spline_backward': (c_int32, [POINTER(TxIo), POINTER(SplineCfg), POINTER(TxGrads), c_void_p]),
     'tfepb_sos_backward': (c_int32, [POINTER(TxIo), c_int32, POINTER(TxGrads), c_void_p]),
     'tfepb_moebius_backward': (c_int32, [POINTER(TxIo), c_int32, c_double, c_int32, POINTER(TxGrads), c_void_p]),
+    'tfepb_maf_spline_forward_bf16': (c_int32, [POINTER(FusedArgs), c_void_p]),
     'tfepb_lse_workspace_bytes': (c_int64, []),
     'tfepb_lse': (c_int32, [c_int32, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p]),
     'tfepb_mt19937_seed': (c_int32, [c_uint32, c_void_p]),

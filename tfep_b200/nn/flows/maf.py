@@ -79,6 +79,10 @@ class MAF(AutoregressiveFlow):
         self._embedding = embedding
         self._degrees_in_host = degrees_in.long().cpu().clone()
         self._packing = None
+        self._fused = None
+        #: 'fp32' (exact FFMA path, parity <= 1e-5 with the reference) or 'bf16' (fused tcgen05 tensor-core
+        #: kernel: bf16 operands, fp32 accumulation and epilogue; inference only, see tfep_b200/_fused.py)
+        self.precision = 'fp32'
 
     def n_parameters(self) -> int:
         """The total number of (unmasked) parameters."""
@@ -133,12 +137,26 @@ class MAF(AutoregressiveFlow):
     def forward(self, x: torch.Tensor):
         """Returns ``(y, log_det_J)`` with shapes ``(batch, n_features)`` and ``(batch,)``."""
         pk = self._pack()
+        if self.precision == 'bf16':
+            return self._forward_fused(x)
+        if self.precision != 'fp32':
+            raise ValueError("precision must be 'fp32' or 'bf16'")
         if pk is False or self._n_conditioner_indices > 0:
             return super().forward(x)
         layouts, _ = self._packed_tables(x.device)
         xc = x if self._embedding is None else self._embedding(x)
         par = self._conditioner.run_plan(xc.contiguous(), pk['plan'])
         return _program.run(pk['parts'], x.contiguous(), par, layouts, passthrough=self.has_fixed_indices)
+
+    def _forward_fused(self, x):
+        """Tensor-core path: the whole layer in one kernel launch (no autograd, no silent fallback)."""
+        from ... import _fused
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("tfep_b200: precision='bf16' is an inference path; use torch.no_grad() "
+                                      "or precision='fp32' for training")
+        if self._fused is None:
+            self._fused = _fused.FusedSplinePlan(self)
+        return self._fused.forward(self, x)
 
     def inverse(self, y: torch.Tensor):
         """Returns ``(x, log_det_J)``: degree-ordered sweep (see the module docstring)."""
