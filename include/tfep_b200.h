@@ -174,7 +174,8 @@ int tfepb_moebius_backward(const tfepb_tx_io* io, int32_t dimension, double max_
  * (nn/masked.py:266-277), the two ELUs (nn/conditioners/made.py:320) and NeuralSplineTransformer.forward
  * (nn/transformers/spline.py:184-241).  The caller packs the degree-sorted effective weights into
  * shared-memory-image blocks and lists the non-zero blocks in `ops` (tfep_b200/_fused.py documents the
- * format); masked blocks are simply absent from the schedule.
+ * format); masked blocks are simply absent from the schedule.  Biases travel inside the weight blocks
+ * (two constant-one columns in every A operand), softmax / softplus rows are pre-scaled by log2(e).
  * -------------------------------------------------------------------------------------------- */
 typedef struct {
     uint32_t w_off, w_bytes;             /* block position in `weights` (bytes, multiple of 16) and size */
@@ -185,7 +186,7 @@ typedef struct {
 
 typedef struct {
     int32_t col;                         /* column of the feature in x / y; -1 = padding slot */
-    float x0, period, inv_period, rescaled_width, rescaled_height, y0;
+    float x0, period, inv_period, rescaled_width, rescaled_height, y0, reserved;
 } tfepb_fused_feature;
 
 typedef struct {
@@ -194,12 +195,11 @@ typedef struct {
     int32_t k1, hidden_padded, n_chunks, n_ops;
     const tfepb_fused_op* ops;                     /* device */
     const void* weights;                           /* device, packed bf16 blocks */
-    const float* bias;                             /* device: [hidden_padded | hidden_padded | n_chunks * 208] */
     const tfepb_fused_feature* feats;              /* device: n_chunks * 8 */
     float min_bin_size, min_slope, slope_offset;   /* slope_offset = log(exp(1 - min_slope) - 1) */
     int32_t reserved;
     int32_t* error_flag;                           /* device int, set if an internal wait times out; may be NULL */
-    float* debug_params;                           /* NULL, or (batch, n_chunks * 208): conditioner outputs (+bias)
+    float* debug_params;                           /* NULL, or (batch, n_chunks * 256): conditioner outputs (+bias)
                                                       in packed order, for parity tests of the GEMM chain */
 } tfepb_fused_args;
 int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_stream_t stream);

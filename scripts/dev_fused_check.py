@@ -33,7 +33,7 @@ with torch.no_grad():
     for li, maf in enumerate(seq):
         plan = _fused.FusedSplinePlan(maf)
         maf._fused = plan
-        dbg = torch.zeros(B, plan.n_chunks * 208, device=dev)
+        dbg = torch.zeros(B, plan.n_chunks * 256, device=dev)
         y, ld = plan.forward(maf, cur, debug_params=dbg)
         torch.cuda.synchronize()
         err = int(plan._tables(torch.device(dev))['err'].item())
@@ -42,7 +42,7 @@ with torch.no_grad():
         rows = plan.w3_rows
         exp = torch.zeros(B, len(rows), dtype=torch.double)
         valid = rows >= 0
-        exp[:, valid] = par_ref[:, rows[valid]]
+        exp[:, valid] = par_ref[:, rows[valid]] * plan.w3_scale[valid].double()
         got = dbg.cpu().double()
         d = (got[:, valid] - exp[:, valid]).abs()
         print(f'layer {li}: watchdog={err} params max abs err {d.max():.3e} mean {d.mean():.3e} (scale {exp.abs().mean():.3f})')

@@ -4,7 +4,7 @@ Stated tolerance of the bf16 tensor-core variant (north_star: "within a stated t
 reference"): operands (x, weights, hidden activations) are rounded to bf16 (8-bit mantissa), accumulation
 and the whole spline epilogue are fp32.  Against the fp64 reference of one MAF layer of the headline
 configuration that gives |dy| <= 2e-2 (mean ~6e-4) modulo the period and |d logdet| <= 5e-2 (mean ~3e-3);
-against a reference that applies the SAME bf16 roundings the kernel must agree to 2e-3 (summation order and
+against a reference that applies the SAME bf16 roundings the kernel must agree to 2e-3 (y) / 5e-3 (logdet) (summation order and
 fast-math intrinsics only) -- that second check is what pins the GEMM chain, layouts and schedule.
 """
 
@@ -29,7 +29,11 @@ def _emulated_layer(oracle, x):
     (w1, b1), (w2, b2), (w3, b3) = [(w.double(), b.double()) for w, b in oracle.layers]
     h = torch.nn.functional.elu(_bf(x) @ _bf(w1).T + b1)
     h = torch.nn.functional.elu(_bf(h.float()) @ _bf(w2).T + b2)
-    par = _bf(h.float()) @ _bf(w3).T + b3
+    # rows feeding softmax / softplus (parameters 0..23 of every feature) are stored pre-multiplied by log2(e)
+    n_feat = w3.shape[0] // 25
+    scale = torch.ones(w3.shape[0], dtype=torch.double)
+    scale[:24 * n_feat] = 1.4426950408889634
+    par = (_bf(h.float()) @ _bf((w3 * scale[:, None]).float()).T) / scale + b3
     old = torch.get_default_dtype()
     torch.set_default_dtype(torch.float64)
     try:
@@ -52,7 +56,7 @@ def test_layers_against_bf16_emulation_and_fp64(batch):
         with torch.no_grad():
             y, ld = maf(x.to(DEV))
         y_e, ld_e = _emulated_layer(oracle, x)
-        assert float(_circ(y, y_e).max()) < 2e-3 and float((ld.cpu().double() - ld_e).abs().max()) < 2e-3
+        assert float(_circ(y, y_e).max()) < 2e-3 and float((ld.cpu().double() - ld_e).abs().max()) < 5e-3
         y64, ld64 = oracle.forward(x)               # fp32 oracle ~ fp64 at this scale
         assert float(_circ(y, y64).max()) < 2e-2 and float(_circ(y, y64).mean()) < 2e-3
         assert float((ld.cpu() - ld64).abs().max()) < 5e-2 and float((ld.cpu() - ld64).abs().mean()) < 8e-3

@@ -42,8 +42,11 @@ def test_forward_inverse_against_golden(prec):
                 mod.inverse(y, par.to(DEV))
             continue
         xi, ldi = mod.inverse(torch.from_numpy(g[f'{name}/y']).to(DEV), par.to(DEV))
-        assert rel_err(xi, g[f'{name}/xinv' if not tails else f'{name}/xinv']) < (5 * TOL[prec] if not tails else 2e-3), name
-        assert rel_err(ldi, g[f'{name}/ldinv']) < (5 * TOL[prec] if not tails else 2e-3), name
+        # The inverse amplifies the last-ulp differences of exp / log between hosts and devices by 1 / slope
+        # (slopes go down to min_slope = 1e-4 in these cases): 2e-3 in fp32, still 5e-10 in fp64.
+        inv_tol = 2e-3 if prec == 'f32' and isinstance(spec, (fo.Spline, fo.Mixed)) else 5 * TOL[prec]
+        assert rel_err(xi, g[f'{name}/xinv']) < inv_tol, name
+        assert rel_err(ldi, g[f'{name}/ldinv']) < inv_tol, name
         if tails:
             xi64, ldi64 = cases.double_reference(spec, torch.from_numpy(g[f'{name}/y']), par, inverse=True)
             # (the fp32 golden y fed to the inverse carries the reference's own ~1e-4 tail error)

@@ -5,9 +5,15 @@ the packed bf16 weight stream:
 
 * hidden units degree-sorted, output layer feature-major with features sorted by degree
   (tfep_b200/_pack.py), zero-padded to multiples of 16;
-* every GEMM is cut into blocks of at most 208 rows x 64 k; a block is stored as the exact image of its
-  shared-memory layout (K-major core matrices: for each group of 8 k-values, all rows x 16 bytes), so the
-  bulk-copy engine moves it with one linear copy;
+* every GEMM is cut into blocks of at most 24 KB (256 rows x 48 k for the output layer); a block is stored
+  as the exact image of its shared-memory layout (K-major core matrices: for each group of 8 k-values, all
+  rows x 16 bytes), so the bulk-copy engine moves it with one linear copy;
+* biases travel inside the GEMMs: packed unit 0 and 1 of every layer input are constant ones (columns D,
+  D+1 of the x operand; two extra hidden units whose own weights reproduce the one) and the weight blocks
+  hold bf16(b) and bf16(b - bf16(b)) in those columns;
+* each feature owns 32 consecutive output rows (25 spline parameters + 7 zero rows) so that the epilogue
+  reads them with one aligned tensor-memory load; rows feeding softmax / softplus are pre-multiplied by
+  log2(e);
 * the schedule lists only blocks that intersect the staircase of the autoregressive mask
   (``deg_out >= deg_in`` for hidden layers, ``>`` for the output layer; reference nn/masked.py:90-99):
   for a tile of output rows the reduction stops at the last input unit they may see.
@@ -23,17 +29,20 @@ from . import _lib
 from ._lib import check, ptr, stream_ptr
 
 TILE_M = 128
-STAGE_BYTES = 208 * 64 * 2
+STAGE_BYTES = 256 * 48 * 2
 FEATS_PER_CHUNK = 8
 NPAR = 25
-CHUNK_N = 208
+PSTRIDE = 32
+CHUNK_N = FEATS_PER_CHUNK * PSTRIDE
 ACC1_COL = 256
+KB_OUT = 48
+LOG2E = 1.4426950408889634
 OP_FIRST, OP_COMMIT, OP_ACC1, OP_WAIT_A, OP_WAIT_EMPTY = 1, 2, 4, 16, 32
 
 OP_DTYPE = np.dtype([('w_off', '<u4'), ('w_bytes', '<u4'), ('n', '<u2'), ('tmem_col', '<u2'), ('ksteps', '<u2'),
                      ('a_slab0', '<u2'), ('flags', '<u4')])
 FEAT_DTYPE = np.dtype([('col', '<i4'), ('x0', '<f4'), ('period', '<f4'), ('inv_period', '<f4'), ('rw', '<f4'),
-                       ('rh', '<f4'), ('y0', '<f4')])
+                       ('rh', '<f4'), ('y0', '<f4'), ('reserved', '<f4')])
 
 
 def _ceil16(n):
@@ -67,13 +76,13 @@ class FusedSplinePlan:
         plan = pk['plan']
         t = maf._transformer
         self.D = len(maf._degrees_in_host)
-        self.K1 = _ceil16(self.D)
+        self.K1 = _ceil16(self.D + 2)                 # + two constant-one columns carrying the bias
         deg_h1, deg_h2 = plan.packed_degrees[1], plan.packed_degrees[2]
         H1, H2 = len(deg_h1), len(deg_h2)
         if H1 != H2:
             raise _lib.TfepB200Error('fused bf16 path needs equal hidden widths')
         self.H = H1
-        self.HP = _ceil16(H1)
+        self.HP = _ceil16(H1 + 2)                     # packed units 0, 1 are the constant ones
         if self.HP > 464:
             raise _lib.TfepB200Error('hidden width exceeds the tensor-memory plan of the fused kernel')
         self.perm1, self.perm2 = plan.perms[1], plan.perms[2]
@@ -101,13 +110,17 @@ class FusedSplinePlan:
             L = float(xf[f] - x0[f])
             mi = 8 * t.min_bin_size
             feats[slot] = (cols[f], float(x0[f]), L, 1.0 / L, np.float32(L) - np.float32(mi),
-                           np.float32(float(yf[f] - y0[f])) - np.float32(mi), float(y0[f]))
-            w3_rows[c * CHUNK_N + j * NPAR:c * CHUNK_N + (j + 1) * NPAR] = ref_cols[f]
+                           np.float32(float(yf[f] - y0[f])) - np.float32(mi), float(y0[f]), 0.0)
+            w3_rows[c * CHUNK_N + j * PSTRIDE:c * CHUNK_N + j * PSTRIDE + NPAR] = ref_cols[f]
         for c in range(self.n_chunks):
             fs = order[c * FEATS_PER_CHUNK:(c + 1) * FEATS_PER_CHUNK]
             chunk_maxdeg.append(max(int(deg_in[cols[f]]) for f in fs))
         self.feats_host = feats
         self.w3_rows = w3_rows
+        scale = torch.ones(len(w3_rows))
+        for i in range(24):                                # widths, heights, slopes: log2 domain; shift: not
+            scale[i::PSTRIDE] = LOG2E
+        self.w3_scale = scale
 
         # ---- schedule ----
         ops, gather = [], []           # gather: per op, index tensor into the concatenated padded matrices
@@ -133,8 +146,8 @@ class FusedSplinePlan:
         # GEMM2: rows see layer-1 units of degree <= their own
         first = True
         for i, (a, b) in enumerate(self.hidden_chunks):
-            real = deg_h2[a:min(b, self.H)]
-            kmax = max(16, _ceil16(int((deg_h1 <= int(real.max())).sum()))) if len(real) else 16
+            real = deg_h2[max(a - 2, 0):max(min(b - 2, self.H), 0)]      # packed position = 2 + sorted index
+            kmax = _ceil16(2 + int((deg_h1 <= int(real.max())).sum())) if len(real) else 16
             blocks = list(range(0, kmax, 64))
             for bi, kb in enumerate(blocks):
                 fl = (OP_FIRST if bi == 0 else 0) | (OP_WAIT_A if first else 0)
@@ -144,8 +157,8 @@ class FusedSplinePlan:
                 add(b - a, a, kb, min(64, kmax - kb), kb // 8, fl, off1, self.HP, a)
         # GEMM3: a chunk of features sees layer-2 units of degree < its largest degree
         for c in range(self.n_chunks):
-            kmax = max(16, _ceil16(int((deg_h2 < chunk_maxdeg[c]).sum())))
-            blocks = list(range(0, kmax, 64))
+            kmax = _ceil16(2 + int((deg_h2 < chunk_maxdeg[c]).sum()))
+            blocks = list(range(0, kmax, KB_OUT))
             acc = c & 1
             for bi, kb in enumerate(blocks):
                 fl = (OP_ACC1 if acc else 0)
@@ -153,7 +166,7 @@ class FusedSplinePlan:
                     fl |= OP_FIRST | OP_WAIT_EMPTY | (OP_WAIT_A if c == 0 else 0)
                 if bi == len(blocks) - 1:
                     fl |= OP_COMMIT
-                add(CHUNK_N, ACC1_COL if acc else 0, kb, min(64, kmax - kb), kb // 8, fl, off2, self.HP, c * CHUNK_N)
+                add(CHUNK_N, ACC1_COL if acc else 0, kb, min(KB_OUT, kmax - kb), kb // 8, fl, off2, self.HP, c * CHUNK_N)
         self.ops_host = np.array(ops, dtype=OP_DTYPE)
         self.gather_host = torch.cat(gather)
         self.weight_bytes = w_off
@@ -170,7 +183,8 @@ class FusedSplinePlan:
             ops = torch.from_numpy(self.ops_host.view(np.uint8).copy()).to(device)
             feats = torch.from_numpy(self.feats_host.view(np.uint8).copy()).to(device)
             self._dev[key] = dict(ops=ops, feats=feats, gather=self.gather_host.to(device),
-                                  w3_rows=self.w3_rows.to(device), perm1=self.perm1.to(device),
+                                  w3_rows=self.w3_rows.to(device), w3_scale=self.w3_scale.to(device),
+                                  perm1=self.perm1.to(device),
                                   perm2=self.perm2.to(device), err=torch.zeros(1, dtype=torch.int32, device=device))
         return self._dev[key]
 
@@ -185,23 +199,29 @@ class FusedSplinePlan:
             dev = w1.device
             tb = self._tables(dev)
             H, HP, K1, D = self.H, self.HP, self.K1, self.D
+
+            def hi_lo(b):
+                hi = b.to(torch.bfloat16).float()
+                return hi, b - hi
+
             W1p = torch.zeros(HP, K1, device=dev)
-            W1p[:H, :D] = w1.index_select(0, tb['perm1'])
+            W1p[2:2 + H, :D] = w1.index_select(0, tb['perm1'])
+            W1p[2:2 + H, D], W1p[2:2 + H, D + 1] = hi_lo(b1.index_select(0, tb['perm1']))
+            W1p[0, D] = W1p[1, D] = 1.0                   # hidden units 0, 1 = ELU(1 * 1) = 1
             W2p = torch.zeros(HP, HP, device=dev)
-            W2p[:H, :H] = w2.index_select(0, tb['perm2']).index_select(1, tb['perm1'])
-            rows = tb['w3_rows']
+            W2p[2:2 + H, 2:2 + H] = w2.index_select(0, tb['perm2']).index_select(1, tb['perm1'])
+            W2p[2:2 + H, 0], W2p[2:2 + H, 1] = hi_lo(b2.index_select(0, tb['perm2']))
+            W2p[0, 0] = W2p[1, 0] = 1.0
+            rows, scale = tb['w3_rows'], tb['w3_scale']
+            safe = torch.where(rows < 0, torch.full_like(rows, w3.shape[0]), rows)
             w3e = torch.cat([w3, torch.zeros(1, H, device=dev)], dim=0)
+            b3e = torch.cat([b3, torch.zeros(1, device=dev)])
             W3p = torch.zeros(len(rows), HP, device=dev)
-            W3p[:, :H] = w3e.index_select(0, torch.where(rows < 0, torch.full_like(rows, w3.shape[0]), rows)) \
-                .index_select(1, tb['perm2'])
+            W3p[:, 2:2 + H] = w3e.index_select(0, safe).index_select(1, tb['perm2']) * scale[:, None]
+            W3p[:, 0], W3p[:, 1] = hi_lo(b3e.index_select(0, safe) * scale)
             src = torch.cat([W1p.flatten(), W2p.flatten(), W3p.flatten()]).to(torch.bfloat16)
             packed = src.index_select(0, tb['gather']).contiguous()
-            b3e = torch.cat([b3, torch.zeros(1, device=dev)])
-            bias = torch.zeros(2 * HP + len(rows), device=dev)
-            bias[:H] = b1.index_select(0, tb['perm1'])
-            bias[HP:HP + H] = b2.index_select(0, tb['perm2'])
-            bias[2 * HP:] = b3e.index_select(0, torch.where(rows < 0, torch.full_like(rows, len(b3)), rows))
-        self._cache = (key, (packed, bias))
+        self._cache = (key, packed)
         return self._cache[1]
 
     def forward(self, maf, x, debug_params=None):
@@ -210,13 +230,13 @@ class FusedSplinePlan:
         if x.dtype != torch.float32:
             raise _lib.TfepB200Error('the fused bf16 path takes float32 inputs')
         x = x.contiguous()
-        packed, bias = self.pack(maf)
+        packed = self.pack(maf)
         tb = self._tables(x.device)
         y = torch.empty_like(x)
         ld = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
         args = _lib.FusedArgs(x=x.data_ptr(), y=y.data_ptr(), logdet=ld.data_ptr(), batch=x.shape[0], n_features=self.D,
                               k1=self.K1, hidden_padded=self.HP, n_chunks=self.n_chunks, n_ops=len(self.ops_host),
-                              ops=tb['ops'].data_ptr(), weights=packed.data_ptr(), bias=bias.data_ptr(),
+                              ops=tb['ops'].data_ptr(), weights=packed.data_ptr(),
                               feats=tb['feats'].data_ptr(), min_bin_size=self.min_bin, min_slope=self.min_slope,
                               slope_offset=self.slope_offset, reserved=0, error_flag=tb['err'].data_ptr(),
                               debug_params=None if debug_params is None else debug_params.data_ptr())

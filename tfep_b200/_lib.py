@@ -67,7 +67,7 @@ class TxGrads(Structure):
 class FusedArgs(Structure):
     _fields_ = [('x', c_void_p), ('y', c_void_p), ('logdet', c_void_p), ('batch', c_int32), ('n_features', c_int32),
                 ('k1', c_int32), ('hidden_padded', c_int32), ('n_chunks', c_int32), ('n_ops', c_int32),
-                ('ops', c_void_p), ('weights', c_void_p), ('bias', c_void_p), ('feats', c_void_p),
+                ('ops', c_void_p), ('weights', c_void_p), ('feats', c_void_p),
                 ('min_bin_size', c_float), ('min_slope', c_float), ('slope_offset', c_float), ('reserved', c_int32),
                 ('error_flag', c_void_p), ('debug_params', c_void_p)]
 

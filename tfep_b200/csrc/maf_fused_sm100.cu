@@ -19,8 +19,14 @@
 // global memory as exact images of their shared-memory layout and streamed by the bulk-copy (TMA) engine
 // through an mbarrier ring.
 //
-// Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 idle,
-// warps 4..11 = epilogue (two warpgroups; TMEM lane quadrant = warp % 4).
+// Biases ride in the GEMMs: every A operand carries two constant-one columns and the weight blocks hold
+// bf16(b) and bf16(b - bf16(b)) in the matching columns, so the epilogues never load a bias.  The rows of
+// the output layer that feed softmax / softplus are pre-multiplied by log2(e), so the epilogue uses the
+// hardware ex2 / lg2 directly.
+//
+// Warp roles: warp 0 = TMEM allocator + bulk-copy producer, warp 1 = MMA issuer, warps 2..17 = epilogue
+// (four warpgroups of 128 threads: thread <-> sample row, TMEM lane quadrant = warp % 4; the warpgroups
+// split the columns of a hidden layer / the feature slots of a chunk).
 #include "common.cuh"
 
 #include <cuda_bf16.h>
@@ -29,15 +35,18 @@ namespace tfepb {
 namespace fused {
 
 constexpr int TILE_M = 128;
-constexpr int EPI_THREADS = 256;
-constexpr int THREADS = 128 + EPI_THREADS;
+constexpr int EPI_WGS = 4;                      // epilogue warpgroups
+constexpr int EPI_THREADS = EPI_WGS * 128;
+constexpr int THREADS = 64 + EPI_THREADS;
 constexpr int STAGES = 3;
-constexpr int STAGE_BYTES = 208 * 64 * 2;      // one weight block: <= 208 rows x 64 k x bf16
+constexpr int STAGE_BYTES = 256 * 48 * 2;      // one weight block: <= 256 rows x 48 k x bf16
 constexpr int SLAB_BYTES = TILE_M * 16;        // 8 k-values of 128 rows
 constexpr int FEATS_PER_CHUNK = 8;
 constexpr int NPAR = 25;                        // circular spline, K = 8: 8 widths, 8 heights, 8 slopes, shift
-constexpr int CHUNK_N = 208;                    // 8 * 25 = 200 columns + 8 zero columns (N % 16 == 0)
+constexpr int PSTRIDE = 32;                     // accumulator columns per feature slot (25 used)
+constexpr int CHUNK_N = FEATS_PER_CHUNK * PSTRIDE;   // 256
 constexpr int ACC1_COL = 256;                   // TMEM column of the second GEMM3 accumulator buffer
+constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 constexpr uint64_t WATCHDOG_CYCLES = 4000000000ull;
 
 struct Op {                 // one weight block = one ring stage
@@ -57,9 +66,9 @@ enum : uint32_t {
     OP_WAIT_EMPTY = 32u,    // wait until the epilogue drained accumulator `acc` (GEMM3 chunks)
 };
 
-struct FeatConst {          // per sorted feature
+struct __align__(16) FeatConst {   // per sorted feature
     int col;                // column in x / y, -1 = padding
-    float x0, L, invL, Rw, Rh, y0;
+    float x0, L, invL, Rw, Rh, y0, pad;
 };
 
 struct Params {
@@ -71,9 +80,8 @@ struct Params {
     int n_ops;
     const Op* ops;
     const uint8_t* weights;     // packed bf16 weight blocks
-    const float* bias;          // [HP | HP | n_chunks * CHUNK_N]
     const FeatConst* feats;     // n_chunks * FEATS_PER_CHUNK
-    float min_bin, min_slope, slope_offset;
+    float min_bin, min_slope, slope_offset2;   // slope_offset2 = log2(e) * log(exp(1 - min_slope) - 1)
     int* error;                 // device int: set on watchdog timeout
     float* debug_params;        // optional (batch, n_chunks * CHUNK_N): conditioner outputs as seen by the epilogue
 };
@@ -142,6 +150,16 @@ __device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t* r) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(addr));
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(addr));
+}
 __device__ __forceinline__ void tmem_wait8(uint32_t* r) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
@@ -177,13 +195,29 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float fast_elu(float v) { return v > 0.f ? v : __expf(v) - 1.f; }
-__device__ __forceinline__ float fast_softplus(float v) { return v > 20.f ? v : __logf(1.f + __expf(v)); }
+__device__ __forceinline__ float ex2(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float lg2(float v) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float rcp(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float fast_elu(float v) { return v > 0.f ? v : ex2(v * LOG2E) - 1.f; }
+// softplus of a log2-domain argument z = log2(e) * v: log(1 + e^v) = ln2 * lg2(1 + 2^z)
+__device__ __forceinline__ float softplus_l2(float z) { return z > 28.85f ? z * LN2 : LN2 * lg2(1.f + ex2(z)); }
 
 // ------------------------------------------------------------------------------------------------
 // shared memory plan
 // ------------------------------------------------------------------------------------------------
-constexpr int MAX_OPS = 96;
+constexpr int MAX_OPS = 128;
 struct Smem {
     Op ops[MAX_OPS];
     uint64_t w_full[STAGES], w_empty[STAGES];
@@ -193,110 +227,78 @@ struct Smem {
     uint32_t pad[3];
 };
 
-// Spline epilogue for ONE feature of one sample: p[0..24] = conditioner outputs (bias already added).
-// Circular spline with K = 8 (nn/transformers/spline.py:184-241, 319-417, 424-501); the far tails cannot be
-// reached after the wrap, and x exactly on the first knot gives the same value through the first bin.
-__device__ __forceinline__ float spline8_circular(const float (&p)[NPAR], float x, const FeatConst& fc, float min_bin,
-                                                  float min_slope, float slope_offset, float& y) {
+// Spline epilogue for ONE feature of one sample.  r[0..24] = conditioner outputs of the feature (bias
+// included by the GEMM); widths r[0..7], heights r[8..15] and slopes r[16..23] arrive pre-multiplied by
+// log2(e), the shift r[24] does not.  Circular spline with K = 8 (reference nn/transformers/spline.py:
+// 184-241, 319-417, 424-501): after the wrap the far tails cannot be reached, and x exactly on the first
+// knot gives the same value through the first bin.
+__device__ __forceinline__ float spline8_circular(const uint32_t (&r)[32], float x, const FeatConst& fc, float min_bin,
+                                                  float min_slope, float slope_offset2, float& y) {
+    float p[NPAR];
+#pragma unroll
+    for (int i = 0; i < NPAR; ++i) p[i] = __uint_as_float(r[i]);
     // wrap: (x - x0 + shift) mod L, result in [0, L)
     float t = x - fc.x0 + p[24];
     t = t - fc.L * floorf(t * fc.invL);
     t = (t < 0.f) ? t + fc.L : t;
     t = (t >= fc.L) ? t - fc.L : t;
-    // softmax numerators
-    float mw = p[0], mh = p[8];
-#pragma unroll
-    for (int k = 1; k < 8; ++k) { mw = fmaxf(mw, p[k]); mh = fmaxf(mh, p[8 + k]); }
+    // softmax numerators (log2 domain)
+    float mw = fmaxf(fmaxf(fmaxf(p[0], p[1]), fmaxf(p[2], p[3])), fmaxf(fmaxf(p[4], p[5]), fmaxf(p[6], p[7])));
+    float mh = fmaxf(fmaxf(fmaxf(p[8], p[9]), fmaxf(p[10], p[11])), fmaxf(fmaxf(p[12], p[13]), fmaxf(p[14], p[15])));
     float ew[8], eh[8], sw = 0.f, sh = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        ew[k] = __expf(p[k] - mw); sw += ew[k];
-        eh[k] = __expf(p[8 + k] - mh); sh += eh[k];
+        ew[k] = ex2(p[k] - mw); sw += ew[k];
+        eh[k] = ex2(p[8 + k] - mh); sh += eh[k];
     }
-    const float rw = __fdividef(fc.Rw, sw), rh = __fdividef(fc.Rh, sh);
+    const float rw = fc.Rw * rcp(sw), rh = fc.Rh * rcp(sh);
     // walk the knots (relative to x0 / y0): last bin whose left knot is below t
     float left = 0.f, bottom = 0.f;
-    float w_sel = ew[0] * rw + min_bin, h_sel = eh[0] * rh + min_bin, xk = 0.f, yk = 0.f;
+    float w_sel = fmaf(ew[0], rw, min_bin), h_sel = fmaf(eh[0], rh, min_bin), xk = 0.f, yk = 0.f;
     float raw0 = p[16], raw1 = p[17];
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
-        left += ew[k] * rw + min_bin;
-        bottom += eh[k] * rh + min_bin;
+        left += fmaf(ew[k], rw, min_bin);
+        bottom += fmaf(eh[k], rh, min_bin);
         const bool adv = t > left;
-        const float wk = ew[k + 1] * rw + min_bin, hk = eh[k + 1] * rh + min_bin;
-        w_sel = adv ? wk : w_sel;
-        h_sel = adv ? hk : h_sel;
+        w_sel = adv ? fmaf(ew[k + 1], rw, min_bin) : w_sel;
+        h_sel = adv ? fmaf(eh[k + 1], rh, min_bin) : h_sel;
         xk = adv ? left : xk;
         yk = adv ? bottom : yk;
         raw0 = adv ? p[16 + k + 1] : raw0;
         raw1 = adv ? p[16 + ((k + 2) & 7)] : raw1;       // knot 8 is tied to knot 0 (circular)
     }
-    const float dk = fast_softplus(raw0 + slope_offset) + min_slope;
-    const float dk1 = fast_softplus(raw1 + slope_offset) + min_slope;
-    const float iw = __fdividef(1.f, w_sel);
+    const float dk = softplus_l2(raw0 + slope_offset2) + min_slope;
+    const float dk1 = softplus_l2(raw1 + slope_offset2) + min_slope;
+    const float iw = rcp(w_sel);
     const float e = (t - xk) * iw;
     const float s = h_sel * iw;
     const float ome = 1.f - e, u = e * ome, e2 = e * e;
     const float q = dk1 + dk - 2.f * s;
-    const float den = s + q * u;
-    const float iden = __fdividef(1.f, den);
-    y = fc.y0 + yk + h_sel * (s * e2 + dk * u) * iden;
-    const float nn = dk1 * e2 + 2.f * s * u + dk * ome * ome;
-    const float r = s * iden;
-    return __logf(nn * r * r);
-}
-
-// Feature slot J of a chunk: its 25 parameters sit at accumulator columns [25 J, 25 J + 25).  The four
-// aligned groups of 8 columns covering them are read and the values picked with compile-time offsets.
-template <int J>
-__device__ __forceinline__ float spline_slot(uint32_t acc_addr, const FeatConst* feats, const float* bias, float* xrow,
-                                             const Params& p, float* dbg) {
-    constexpr int START = NPAR * J, A0 = (START / 8) * 8, OFF = START - A0;
-    static_assert(OFF + NPAR <= 32, "parameters of one feature must fit in four aligned 8-column groups");
-    uint32_t r[32];
-    tmem_ld8(acc_addr + A0, r);
-    tmem_ld8(acc_addr + A0 + 8, r + 8);
-    tmem_ld8(acc_addr + A0 + 16, r + 16);
-    tmem_ld8(acc_addr + A0 + 24, r + 24);
-    tmem_wait8(r);
-    tmem_wait8(r + 8);
-    tmem_wait8(r + 16);
-    tmem_wait8(r + 24);
-    const FeatConst fc = feats[J];
-    if (fc.col < 0) return 0.f;
-    float par[NPAR];
-#pragma unroll
-    for (int i = 0; i < NPAR; ++i) par[i] = __uint_as_float(r[OFF + i]) + bias[START + i];
-    if (dbg != nullptr) {
-#pragma unroll
-        for (int i = 0; i < NPAR; ++i) dbg[START + i] = par[i];
-    }
-    float yv;
-    const float ld = spline8_circular(par, xrow[fc.col], fc, p.min_bin, p.min_slope, p.slope_offset, yv);
-    xrow[fc.col] = yv;
-    return ld;
+    const float den = fmaf(q, u, s);
+    const float iden = rcp(den);
+    y = fc.y0 + yk + h_sel * fmaf(s, e2, dk * u) * iden;
+    const float nn = fmaf(dk1, e2, fmaf(2.f * s, u, dk * ome * ome));
+    const float rr = s * iden;
+    return LN2 * lg2(nn * rr * rr);
 }
 
 __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve-up (all offsets multiples of 1024 except the small tables at the end)
     const int a_slabs = max(p.K1, p.HP) / 8;
     uint8_t* sA = smem_raw;                                         // A operand: a_slabs x 2048 B
     uint8_t* sW = sA + (size_t)a_slabs * SLAB_BYTES;                // weight ring
     float* sX = reinterpret_cast<float*>(sW + (size_t)STAGES * STAGE_BYTES);   // x / y tile, row-major [128][D]
     const int x_tile_bytes = TILE_M * p.D * 4;
-    float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sX) + ((x_tile_bytes + 127) & ~127));
-    const int n_bias = 2 * p.HP + p.n_chunks * CHUNK_N;
-    FeatConst* sFeat = reinterpret_cast<FeatConst*>(sBias + ((n_bias + 31) & ~31));
+    FeatConst* sFeat = reinterpret_cast<FeatConst*>(reinterpret_cast<uint8_t*>(sX) + ((x_tile_bytes + 127) & ~127));
     const int n_feat = p.n_chunks * FEATS_PER_CHUNK;
-    float* sLd = reinterpret_cast<float*>(sFeat + n_feat);          // [128] log-det partials of warpgroup 1
-    Smem* sm = reinterpret_cast<Smem*>(sLd + TILE_M);
+    float* sLd = reinterpret_cast<float*>(sFeat + n_feat);          // [EPI_WGS - 1][128] log-det partials
+    Smem* sm = reinterpret_cast<Smem*>(sLd + (EPI_WGS - 1) * TILE_M);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_tiles = (p.batch + TILE_M - 1) / TILE_M;
 
     // ---- one-time setup ----
-    for (int i = tid; i < n_bias; i += THREADS) sBias[i] = p.bias[i];
     for (int i = tid; i < n_feat; i += THREADS) sFeat[i] = p.feats[i];
     for (int i = tid; i < p.n_ops; i += THREADS) sm->ops[i] = p.ops[i];
     if (warp == 1 && lane == 0) {
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
         for (int b = 0; b < 2; ++b) { mbar_init(&sm->acc_full[b], 1); mbar_init(&sm->acc_empty[b], EPI_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) tmem_alloc(&sm->tmem_base, 512);
+    if (warp == 0) tmem_alloc(&sm->tmem_base, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -370,33 +372,34 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
                 }
             }
         }
-    } else if (warp >= 4) {
+    } else {
         // =========================== epilogue warps ===========================
-        const int et = tid - 128;                 // 0..255
-        const int wg = et >> 7;                   // warpgroup 0 / 1
-        const int row = et & 127;                 // sample row of the tile = TMEM lane
+        const int et = tid - 64;                  // 0..511
+        const int wg = et >> 7;                   // warpgroup 0..3
+        const int row = (warp & 3) * 32 + lane;   // sample row of the tile = TMEM lane
         const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t full_cnt[2] = {0, 0}, tcount = 0;
         const int groups = p.HP / 8;              // 8-column groups of a hidden layer
-        const int g_lo = wg == 0 ? 0 : groups / 2, g_hi = wg == 0 ? groups / 2 : groups;
+        const int g_lo = wg * groups / EPI_WGS, g_hi = (wg + 1) * groups / EPI_WGS;
+        float* xrow = sX + row * p.D;
 
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
             const int rows = min(TILE_M, p.batch - tile * TILE_M);
-            // ---- x tile -> A0 ----
+            // ---- x tile -> A0 (two constant-one columns after the D inputs carry the biases) ----
             mbar_wait(&sm->x_full, tcount & 1, p.error, 6);
             if (rows < TILE_M) {
                 const float* src = p.x + (size_t)tile * TILE_M * p.D;
                 for (int i = et; i < TILE_M * p.D; i += EPI_THREADS) sX[i] = i < rows * p.D ? src[i] : 0.f;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, 512;" ::: "memory");
             }
             {
                 const int slabs1 = p.K1 / 8;
-                for (int j = wg; j < slabs1; j += 2) {
+                for (int j = wg; j < slabs1; j += EPI_WGS) {
                     float v[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int k = j * 8 + i;
-                        v[i] = k < p.D ? sX[row * p.D + k] : 0.f;
+                        v[i] = k < p.D ? xrow[k] : (k < p.D + 2 ? 1.f : 0.f);
                     }
                     uint4 q = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
                     *reinterpret_cast<uint4*>(sA + (size_t)j * SLAB_BYTES + row * 16) = q;
@@ -404,19 +407,18 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
                 fence_async_smem();
                 mbar_arrive(&sm->a_ready);
             }
-            // ---- two hidden layers: +bias, ELU, bf16 -> A ----
+            // ---- two hidden layers: ELU, bf16 -> A (bias already in the accumulator) ----
             for (int layer = 0; layer < 2; ++layer) {
                 mbar_wait(&sm->acc_full[0], full_cnt[0] & 1, p.error, 7);
                 ++full_cnt[0];
                 tc_fence_after();
-                const float* bias = sBias + layer * p.HP;
                 for (int g = g_lo; g < g_hi; ++g) {
                     uint32_t r[8];
                     tmem_ld8(lane_addr + g * 8, r);
                     tmem_wait8(r);
                     float v[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = fast_elu(__uint_as_float(r[i]) + bias[g * 8 + i]);
+                    for (int i = 0; i < 8; ++i) v[i] = fast_elu(__uint_as_float(r[i]));
                     uint4 q = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
                     *reinterpret_cast<uint4*>(sA + (size_t)g * SLAB_BYTES + row * 16) = q;
                 }
@@ -426,48 +428,54 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
             }
             // ---- output layer chunks: spline transformer straight out of TMEM ----
             float ld = 0.f;
-            const float* bias3 = sBias + 2 * p.HP;
             for (int c = 0; c < p.n_chunks; ++c) {
                 const int b = c & 1;
                 mbar_wait(&sm->acc_full[b], full_cnt[b] & 1, p.error, 8);
                 ++full_cnt[b];
                 tc_fence_after();
                 const uint32_t col0 = lane_addr + (b ? ACC1_COL : 0);
-                float* dbg = (p.debug_params != nullptr && row < rows)
-                                 ? p.debug_params + ((size_t)tile * TILE_M + row) * p.n_chunks * CHUNK_N + c * CHUNK_N
-                                 : nullptr;
-                if (wg == 0) {
-                    ld += spline_slot<0>(col0, sFeat + c * FEATS_PER_CHUNK, bias3 + c * CHUNK_N, sX + row * p.D, p, dbg);
-                    ld += spline_slot<1>(col0, sFeat + c * FEATS_PER_CHUNK, bias3 + c * CHUNK_N, sX + row * p.D, p, dbg);
-                    ld += spline_slot<2>(col0, sFeat + c * FEATS_PER_CHUNK, bias3 + c * CHUNK_N, sX + row * p.D, p, dbg);
-                    ld += spline_slot<3>(col0, sFeat + c * FEATS_PER_CHUNK, bias3 + c * CHUNK_N, sX + row * p.D, p, dbg);
-                } else {
-                    ld += spline_slot<4>(col0, sFeat + c * FEATS_PER_CHUNK, bias3 + c * CHUNK_N, sX + row * p.D, p, dbg);
-                    ld += spline_slot<5>(col0, sFeat + c * FEATS_PER_CHUNK, bias3 + c * CHUNK_N, sX + row * p.D, p, dbg);
-                    ld += spline_slot<6>(col0, sFeat + c * FEATS_PER_CHUNK, bias3 + c * CHUNK_N, sX + row * p.D, p, dbg);
-                    ld += spline_slot<7>(col0, sFeat + c * FEATS_PER_CHUNK, bias3 + c * CHUNK_N, sX + row * p.D, p, dbg);
+#pragma unroll 1
+                for (int jj = 0; jj < FEATS_PER_CHUNK / EPI_WGS; ++jj) {
+                    const int slot = wg * (FEATS_PER_CHUNK / EPI_WGS) + jj;
+                    uint32_t r[32];
+                    tmem_ld32(col0 + slot * PSTRIDE, r);
+                    tmem_wait8(r); tmem_wait8(r + 8); tmem_wait8(r + 16); tmem_wait8(r + 24);
+                    const FeatConst fc = sFeat[c * FEATS_PER_CHUNK + slot];
+                    if (fc.col >= 0) {
+                        if (p.debug_params != nullptr && row < rows) {
+                            float* dbg = p.debug_params + ((size_t)tile * TILE_M + row) * p.n_chunks * CHUNK_N + c * CHUNK_N +
+                                         slot * PSTRIDE;
+#pragma unroll
+                            for (int i = 0; i < NPAR; ++i) dbg[i] = __uint_as_float(r[i]);
+                        }
+                        float yv;
+                        ld += spline8_circular(r, xrow[fc.col], fc, p.min_bin, p.min_slope, p.slope_offset2, yv);
+                        xrow[fc.col] = yv;
+                    }
                 }
                 tc_fence_before();
                 mbar_arrive(&sm->acc_empty[b]);
             }
-            // ---- log-det: combine the two warpgroups, store; y tile leaves with one bulk store ----
-            if (wg == 1) sLd[row] = ld;
+            // ---- log-det: combine the warpgroups, store; y tile leaves with one bulk store ----
+            if (wg > 0) sLd[(wg - 1) * TILE_M + row] = ld;
             fence_async_smem();                      // y tile writes -> visible to the bulk-copy engine
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, 512;" ::: "memory");
             if (wg == 0) {
-                if (row < rows) p.logdet[(size_t)tile * TILE_M + row] = ld + sLd[row];
-                if (rows == TILE_M) {
-                    if (et == 0) {
-                        bulk_s2g(p.y + (size_t)tile * TILE_M * p.D, sX, (uint32_t)x_tile_bytes);
-                        bulk_wait_read();
-                        mbar_arrive(&sm->x_empty);
-                    }
+                if (row < rows) {
+#pragma unroll
+                    for (int g = 0; g < EPI_WGS - 1; ++g) ld += sLd[g * TILE_M + row];
+                    p.logdet[(size_t)tile * TILE_M + row] = ld;
+                }
+                if (rows == TILE_M && et == 0) {
+                    bulk_s2g(p.y + (size_t)tile * TILE_M * p.D, sX, (uint32_t)x_tile_bytes);
+                    bulk_wait_read();
+                    mbar_arrive(&sm->x_empty);
                 }
             }
             if (rows < TILE_M) {
                 float* dst = p.y + (size_t)tile * TILE_M * p.D;
                 for (int i = et; i < rows * p.D; i += EPI_THREADS) dst[i] = sX[i];
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, 512;" ::: "memory");
                 if (et == 0) mbar_arrive(&sm->x_empty);
             }
         }
@@ -476,18 +484,16 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
     // ---- teardown ----
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem, 512);
+    if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 size_t smem_bytes(const Params& p) {
     const size_t a_slabs = (size_t)(p.K1 > p.HP ? p.K1 : p.HP) / 8;
     size_t s = a_slabs * SLAB_BYTES + (size_t)STAGES * STAGE_BYTES;
     s += ((size_t)TILE_M * p.D * 4 + 127) & ~(size_t)127;
-    const size_t n_bias = 2 * (size_t)p.HP + (size_t)p.n_chunks * CHUNK_N;
-    s += ((n_bias + 31) & ~(size_t)31) * 4;
     s += (size_t)p.n_chunks * FEATS_PER_CHUNK * sizeof(FeatConst);
-    s += TILE_M * 4 + sizeof(Smem);
-    return s + 1024;     // slack for the 1024-byte alignment of the dynamic segment
+    s += (EPI_WGS - 1) * TILE_M * 4 + sizeof(Smem);
+    return s + 256;
 }
 
 }  // namespace fused
@@ -500,9 +506,9 @@ static_assert(sizeof(fused::FeatConst) == sizeof(tfepb_fused_feature), "feature 
 
 extern "C" int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_stream_t stream) {
     TFEPB_CHECK_ARG(a != nullptr, "null argument struct");
-    TFEPB_CHECK_ARG(a->x && a->y && a->logdet && a->ops && a->weights && a->bias && a->feats, "null buffer");
+    TFEPB_CHECK_ARG(a->x && a->y && a->logdet && a->ops && a->weights && a->feats, "null buffer");
     TFEPB_CHECK_ARG(a->batch >= 0 && a->n_features > 0, "bad sizes");
-    TFEPB_CHECK_ARG(a->k1 % 16 == 0 && a->k1 >= a->n_features, "k1 must be n_features rounded up to 16");
+    TFEPB_CHECK_ARG(a->k1 % 16 == 0 && a->k1 >= a->n_features + 2, "k1 must hold n_features + 2 bias columns, rounded up to 16");
     TFEPB_CHECK_ARG(a->hidden_padded % 16 == 0 && a->hidden_padded > 0 && a->hidden_padded <= 512, "bad hidden width");
     TFEPB_CHECK_ARG(a->n_chunks > 0 && a->n_ops > 0 && a->n_ops <= fused::MAX_OPS, "bad schedule length");
     TFEPB_CHECK_ARG((a->n_features * 4 * fused::TILE_M) % 16 == 0, "tile of x must be a multiple of 16 bytes");
@@ -514,9 +520,9 @@ extern "C" int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_st
     p.x = (const float*)a->x; p.y = (float*)a->y; p.logdet = (float*)a->logdet;
     p.batch = a->batch; p.D = a->n_features; p.K1 = a->k1; p.HP = a->hidden_padded;
     p.n_chunks = a->n_chunks; p.n_ops = a->n_ops;
-    p.ops = (const fused::Op*)a->ops; p.weights = (const uint8_t*)a->weights; p.bias = (const float*)a->bias;
+    p.ops = (const fused::Op*)a->ops; p.weights = (const uint8_t*)a->weights;
     p.feats = (const fused::FeatConst*)a->feats;
-    p.min_bin = a->min_bin_size; p.min_slope = a->min_slope; p.slope_offset = a->slope_offset;
+    p.min_bin = a->min_bin_size; p.min_slope = a->min_slope; p.slope_offset2 = a->slope_offset * fused::LOG2E;
     p.error = a->error_flag;
     p.debug_params = a->debug_params;
     const size_t smem = fused::smem_bytes(p);

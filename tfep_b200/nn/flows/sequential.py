@@ -17,8 +17,10 @@ class SequentialFlow(torch.nn.Sequential):
         return self._pass(y, inverse=True)
 
     def _pass(self, x, inverse):
-        cumulative_log_det_J = torch.zeros(x.size(0)).to(x)
+        cumulative_log_det_J = None
         for flow in (reversed(self) if inverse else self):
             x, log_det_J = flow.inverse(x) if inverse else flow(x)
-            cumulative_log_det_J = cumulative_log_det_J + log_det_J
+            cumulative_log_det_J = log_det_J if cumulative_log_det_J is None else cumulative_log_det_J + log_det_J
+        if cumulative_log_det_J is None:
+            cumulative_log_det_J = torch.zeros(x.size(0), dtype=x.dtype, device=x.device)
         return x, cumulative_log_det_J
