@@ -178,10 +178,13 @@ int tfepb_moebius_backward(const tfepb_tx_io* io, int32_t dimension, double max_
  * (two constant-one columns in every A operand), softmax / softplus rows are pre-scaled by log2(e).
  * -------------------------------------------------------------------------------------------- */
 typedef struct {
-    uint32_t w_off, w_bytes;             /* block position in `weights` (bytes, multiple of 16) and size */
-    uint16_t n, tmem_col, ksteps, a_slab0;
-    uint32_t flags;                      /* 1 first block of accumulator, 2 commit, 4 accumulator 1,
+    uint32_t w_off;                      /* block position in `weights` (bytes, multiple of 16) */
+    uint16_t w_bytes16;                  /* block size in units of 16 bytes */
+    uint16_t n, tmem_col, a_col;         /* MMA N, accumulator column, first A column (2 k-values per column) */
+    uint8_t ksteps;                      /* K = 16 steps in the block */
+    uint8_t flags;                       /* 1 first block of accumulator, 2 commit, 4 accumulator 1,
                                             16 wait for A operand, 32 wait for drained accumulator */
+    uint16_t reserved;
 } tfepb_fused_op;
 
 typedef struct {
@@ -193,13 +196,13 @@ typedef struct {
     const void* x; void* y; void* logdet;          /* fp32 (batch, n_features), (batch, n_features), (batch,) */
     int32_t batch, n_features;
     int32_t k1, hidden_padded, n_chunks, n_ops;
-    const tfepb_fused_op* ops;                     /* device */
+    const tfepb_fused_op* ops;                     /* HOST array of n_ops <= 112 entries (copied into the launch) */
     const void* weights;                           /* device, packed bf16 blocks */
     const tfepb_fused_feature* feats;              /* device: n_chunks * 8 */
     float min_bin_size, min_slope, slope_offset;   /* slope_offset = log(exp(1 - min_slope) - 1) */
     int32_t reserved;
     int32_t* error_flag;                           /* device int, set if an internal wait times out; may be NULL */
-    float* debug_params;                           /* NULL, or (batch, n_chunks * 256): conditioner outputs (+bias)
+    float* debug_params;                           /* NULL, or (batch, n_chunks * 128): conditioner outputs (+bias)
                                                       in packed order, for parity tests of the GEMM chain */
 } tfepb_fused_args;
 int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_stream_t stream);

@@ -33,7 +33,7 @@ with torch.no_grad():
     for li, maf in enumerate(seq):
         plan = _fused.FusedSplinePlan(maf)
         maf._fused = plan
-        dbg = torch.zeros(B, plan.n_chunks * 256, device=dev)
+        dbg = torch.zeros(B, plan.n_chunks * 128, device=dev)
         y, ld = plan.forward(maf, cur, debug_params=dbg)
         torch.cuda.synchronize()
         err = int(plan._tables(torch.device(dev))['err'].item())

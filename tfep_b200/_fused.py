@@ -21,6 +21,7 @@ the packed bf16 weight stream:
 
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -29,18 +30,24 @@ from . import _lib
 from ._lib import check, ptr, stream_ptr
 
 TILE_M = 128
-STAGE_BYTES = 256 * 48 * 2
-FEATS_PER_CHUNK = 8
+STAGE_BYTES = 32768
+FEATS_PER_CHUNK = 4
 NPAR = 25
 PSTRIDE = 32
 CHUNK_N = FEATS_PER_CHUNK * PSTRIDE
-ACC1_COL = 256
-KB_OUT = 48
+ACC1_COL = CHUNK_N
+KB_OUT = 128
+KB_HID = 80
 LOG2E = 1.4426950408889634
 OP_FIRST, OP_COMMIT, OP_ACC1, OP_WAIT_A, OP_WAIT_EMPTY = 1, 2, 4, 16, 32
 
-OP_DTYPE = np.dtype([('w_off', '<u4'), ('w_bytes', '<u4'), ('n', '<u2'), ('tmem_col', '<u2'), ('ksteps', '<u2'),
-                     ('a_slab0', '<u2'), ('flags', '<u4')])
+OP_DTYPE = np.dtype([('w_off', '<u4'), ('w_bytes16', '<u2'), ('n', '<u2'), ('tmem_col', '<u2'), ('a_col', '<u2'),
+                     ('ksteps', 'u1'), ('flags', 'u1'), ('reserved', '<u2')])
+
+
+def _idesc(n):
+    """kind::f16 instruction descriptor: D = fp32 (bit 4), A = B = bf16 (bits 7, 10), K-major, N >> 3 at 17, M >> 4 at 24."""
+    return (1 << 4) | (1 << 7) | (1 << 10) | ((n >> 3) << 17) | ((TILE_M >> 4) << 24)
 FEAT_DTYPE = np.dtype([('col', '<i4'), ('x0', '<f4'), ('period', '<f4'), ('inv_period', '<f4'), ('rw', '<f4'),
                        ('rh', '<f4'), ('y0', '<f4'), ('reserved', '<f4')])
 
@@ -83,12 +90,12 @@ class FusedSplinePlan:
             raise _lib.TfepB200Error('fused bf16 path needs equal hidden widths')
         self.H = H1
         self.HP = _ceil16(H1 + 2)                     # packed units 0, 1 are the constant ones
-        if self.HP > 464:
-            raise _lib.TfepB200Error('hidden width exceeds the tensor-memory plan of the fused kernel')
+        if self.HP > 336 or self.K1 > 352:
+            raise _lib.TfepB200Error('layer widths exceed the tensor-memory plan of the fused kernel')
         self.perm1, self.perm2 = plan.perms[1], plan.perms[2]
 
         # hidden-layer row chunks (<= 160 rows so that a GEMM1 block fits a ring stage)
-        n_hc = max(1, math.ceil(self.HP / 160))
+        n_hc = max(1, math.ceil(self.HP / 192))
         hc = _ceil16(math.ceil(self.HP / n_hc))
         self.hidden_chunks = [(r, min(r + hc, self.HP)) for r in range(0, self.HP, hc)]
         assert all((b - a) * self.K1 * 2 <= STAGE_BYTES for a, b in self.hidden_chunks)
@@ -136,7 +143,7 @@ class FusedSplinePlan:
             gather.append(idx)
             nbytes = n * kmax_block * 2
             assert nbytes <= STAGE_BYTES and nbytes % 16 == 0
-            ops.append((w_off, nbytes, n, tmem_col, ksteps, a_slab0, flags))
+            ops.append((w_off, nbytes // 16, n, tmem_col, a_slab0 * 4, ksteps, flags, 0))
             w_off += nbytes
 
         # GEMM1: full K1 per row chunk (the first layer is tiny; no staircase)
@@ -148,13 +155,13 @@ class FusedSplinePlan:
         for i, (a, b) in enumerate(self.hidden_chunks):
             real = deg_h2[max(a - 2, 0):max(min(b - 2, self.H), 0)]      # packed position = 2 + sorted index
             kmax = _ceil16(2 + int((deg_h1 <= int(real.max())).sum())) if len(real) else 16
-            blocks = list(range(0, kmax, 64))
+            blocks = list(range(0, kmax, KB_HID))
             for bi, kb in enumerate(blocks):
                 fl = (OP_FIRST if bi == 0 else 0) | (OP_WAIT_A if first else 0)
                 if i == len(self.hidden_chunks) - 1 and bi == len(blocks) - 1:
                     fl |= OP_COMMIT
                 first = False
-                add(b - a, a, kb, min(64, kmax - kb), kb // 8, fl, off1, self.HP, a)
+                add(b - a, a, kb, min(KB_HID, kmax - kb), kb // 8, fl, off1, self.HP, a)
         # GEMM3: a chunk of features sees layer-2 units of degree < its largest degree
         for c in range(self.n_chunks):
             kmax = _ceil16(2 + int((deg_h2 < chunk_maxdeg[c]).sum()))
@@ -170,7 +177,7 @@ class FusedSplinePlan:
         self.ops_host = np.array(ops, dtype=OP_DTYPE)
         self.gather_host = torch.cat(gather)
         self.weight_bytes = w_off
-        self.mma_columns = int(sum(int(o[2]) * int(o[4]) for o in ops))          # sum of N x ksteps over all blocks
+        self.mma_columns = int(sum(int(o[2]) * int(o[5]) for o in ops))          # sum of N x ksteps over all blocks
         self.min_bin, self.min_slope = float(t.min_bin_size), float(t.min_slope)
         self.slope_offset = float(math.log(math.exp(1.0 - t.min_slope) - 1.0))
         self._dev = {}
@@ -180,9 +187,8 @@ class FusedSplinePlan:
     def _tables(self, device):
         key = str(device)
         if key not in self._dev:
-            ops = torch.from_numpy(self.ops_host.view(np.uint8).copy()).to(device)
             feats = torch.from_numpy(self.feats_host.view(np.uint8).copy()).to(device)
-            self._dev[key] = dict(ops=ops, feats=feats, gather=self.gather_host.to(device),
+            self._dev[key] = dict(feats=feats, gather=self.gather_host.to(device),
                                   w3_rows=self.w3_rows.to(device), w3_scale=self.w3_scale.to(device),
                                   perm1=self.perm1.to(device),
                                   perm2=self.perm2.to(device), err=torch.zeros(1, dtype=torch.int32, device=device))
@@ -236,9 +242,9 @@ class FusedSplinePlan:
         ld = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
         args = _lib.FusedArgs(x=x.data_ptr(), y=y.data_ptr(), logdet=ld.data_ptr(), batch=x.shape[0], n_features=self.D,
                               k1=self.K1, hidden_padded=self.HP, n_chunks=self.n_chunks, n_ops=len(self.ops_host),
-                              ops=tb['ops'].data_ptr(), weights=packed.data_ptr(),
+                              ops=self.ops_host.ctypes.data, weights=packed.data_ptr(),
                               feats=tb['feats'].data_ptr(), min_bin_size=self.min_bin, min_slope=self.min_slope,
-                              slope_offset=self.slope_offset, reserved=0, error_flag=tb['err'].data_ptr(),
+                              slope_offset=self.slope_offset, reserved=int(os.environ.get('TFEPB_FUSED_DEBUG_MODE', '0')), error_flag=tb['err'].data_ptr(),
                               debug_params=None if debug_params is None else debug_params.data_ptr())
         with torch.cuda.device(x.device):
             check(_lib.load().tfepb_maf_spline_forward_bf16(ctypes.byref(args), stream_ptr(x)))

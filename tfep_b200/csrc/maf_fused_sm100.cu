@@ -5,13 +5,15 @@
 //                                                  nn/conditioners/made.py:294-329, nn/transformers/spline.py)
 //
 // One persistent CTA per SM walks over tiles of 128 samples.  For one tile:
-//   x tile (fp32)  --bulk copy-->  smem  --convert-->  A0 (bf16, UMMA K-major core-matrix layout)
-//   GEMM1  D1 = A0 W1^T   (tcgen05.mma, accumulator in TMEM)   -> epilogue: +b1, ELU, bf16 -> A1 (smem)
-//   GEMM2  D2 = A1 W2^T                                         -> epilogue: +b2, ELU, bf16 -> A2 (smem)
-//   GEMM3  chunk c: 8 features x 25 spline parameters = 200 (+8 pad) columns, double-buffered in TMEM;
+//   x tile (fp32)  --bulk copy-->  smem  --bf16, tcgen05.st-->  A0 in TENSOR MEMORY
+//   GEMM1  D1 = A0 W1^T   (tcgen05.mma, A from TMEM, B from smem, D in TMEM)  -> epilogue: ELU, bf16 -> A1 (TMEM)
+//   GEMM2  D2 = A1 W2^T                                                         -> epilogue: ELU, bf16 -> A2 (TMEM)
+//   GEMM3  chunk c: 4 features x 32 columns (25 spline parameters each), double-buffered accumulators;
 //          epilogue: softmax / softplus / bin search / rational-quadratic map + log-det straight out of TMEM,
-//          so the (batch, 1650) parameter tensor never exists in memory.
+//          so neither the hidden activations nor the (batch, 1650) parameter tensor ever exist in memory.
 //   y tile is written in place over the x tile in smem and leaves with one bulk store.
+// Keeping the A operand in tensor memory matters: with both operands in shared memory the MMAs ran at half
+// rate (measured, profiles/r01_*), because A and B compete for the shared-memory operand port.
 //
 // Hidden units are degree-sorted and the output layer is packed feature-major (tfep_b200/_pack.py), so the
 // autoregressive masks are block lower-triangular: the host-built schedule only lists the weight blocks
@@ -30,6 +32,7 @@
 #include "common.cuh"
 
 #include <cuda_bf16.h>
+#include <string.h>
 
 namespace tfepb {
 namespace fused {
@@ -38,25 +41,29 @@ constexpr int TILE_M = 128;
 constexpr int EPI_WGS = 4;                      // epilogue warpgroups
 constexpr int EPI_THREADS = EPI_WGS * 128;
 constexpr int THREADS = 64 + EPI_THREADS;
-constexpr int STAGES = 3;
-constexpr int STAGE_BYTES = 256 * 48 * 2;      // one weight block: <= 256 rows x 48 k x bf16
-constexpr int SLAB_BYTES = TILE_M * 16;        // 8 k-values of 128 rows
-constexpr int FEATS_PER_CHUNK = 8;
+constexpr int STAGES = 4;
+constexpr int STAGE_BYTES = 32768;              // one weight block (<= 256 rows, bf16)
+constexpr int FEATS_PER_CHUNK = 4;
 constexpr int NPAR = 25;                        // circular spline, K = 8: 8 widths, 8 heights, 8 slopes, shift
 constexpr int PSTRIDE = 32;                     // accumulator columns per feature slot (25 used)
-constexpr int CHUNK_N = FEATS_PER_CHUNK * PSTRIDE;   // 256
-constexpr int ACC1_COL = 256;                   // TMEM column of the second GEMM3 accumulator buffer
+constexpr int CHUNK_N = FEATS_PER_CHUNK * PSTRIDE;   // 128
+constexpr int ACC_COLS = 336;                   // TMEM columns [0, 336): accumulators
+constexpr int A_COL = 336;                      // TMEM columns [336, 512): bf16 A operand (2 k-values per column)
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
 constexpr uint64_t WATCHDOG_CYCLES = 4000000000ull;
 
-struct Op {                 // one weight block = one ring stage
+constexpr int MAX_OPS = 112;
+struct Op {                 // one weight block = one ring stage (16 bytes; the table travels in the kernel parameters,
+                            // so that the issuing warps read it through the constant bank into uniform registers)
     uint32_t w_off;         // byte offset into the packed weights (multiple of 16)
-    uint32_t w_bytes;
+    uint16_t w_bytes16;     // block size / 16
     uint16_t n;             // MMA N of this block (rows of the weight block)
     uint16_t tmem_col;      // destination accumulator column
-    uint16_t ksteps;        // K = 16 steps in this block
-    uint16_t a_slab0;       // first A slab (8 k-values) this block multiplies
-    uint32_t flags;
+    uint16_t a_col;         // first A column (two k-values each) this block multiplies
+    uint8_t ksteps;         // K = 16 steps in this block
+    uint8_t flags;
+    uint16_t reserved;
 };
 enum : uint32_t {
     OP_FIRST = 1u,          // first block of its accumulator: overwrite instead of accumulate
@@ -74,16 +81,17 @@ struct __align__(16) FeatConst {   // per sorted feature
 struct Params {
     const float* x; float* y; float* logdet;
     int batch, D;               // D = row length of x / y
-    int K1;                     // D padded to a multiple of 16
-    int HP;                     // hidden width padded to a multiple of 16
+    int K1;                     // D + 2 padded to a multiple of 16
+    int HP;                     // hidden width (+2) padded to a multiple of 16
     int n_chunks;               // GEMM3 chunks
     int n_ops;
-    const Op* ops;
     const uint8_t* weights;     // packed bf16 weight blocks
     const FeatConst* feats;     // n_chunks * FEATS_PER_CHUNK
     float min_bin, min_slope, slope_offset2;   // slope_offset2 = log2(e) * log(exp(1 - min_slope) - 1)
     int* error;                 // device int: set on watchdog timeout
     float* debug_params;        // optional (batch, n_chunks * CHUNK_N): conditioner outputs as seen by the epilogue
+    int debug_mode;             // development only (timing experiments)
+    Op ops[MAX_OPS];
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -143,12 +151,15 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
-// TMEM -> registers: 8 consecutive columns of this thread's lane.  The values are only defined after
-// tmem_wait(), which takes the registers as read-write operands so that no use can be scheduled above it.
-__device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t* r) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(addr));
+// TMEM -> registers (this thread's lane, consecutive columns).  The values are only defined after the
+// matching tmem_wait*(), which takes the registers as read-write operands so that no use can be
+// scheduled above it.
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(addr));
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t* r) {
     asm volatile(
@@ -160,32 +171,53 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t* r) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(addr));
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(addr));
+}
+__device__ __forceinline__ void tmem_ld1(uint32_t addr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(addr));
+}
+__device__ __forceinline__ void tmem_wait1(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]) :: "memory");
+}
 __device__ __forceinline__ void tmem_wait8(uint32_t* r) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
                  :: "memory");
 }
+// registers -> TMEM: 8 consecutive columns of this thread's lane
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// K-major, no-swizzle operand descriptor: core matrix = 8 rows x 16 bytes stored contiguously (128 B);
-// SBO = distance between 8-row groups, LBO = distance between the two 8-element K halves of one MMA.
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-    d |= (uint64_t)1 << 46;         // descriptor version of sm_100
-    return d;                        // base offset 0, layout type 0 = no swizzle
+// D[tmem] (+)= A[tmem] . B[smem]^T : A = 128 rows x 16 bf16 (8 TMEM columns, two k-values per column),
+// B = N rows x 16 bf16, K-major no-swizzle core matrices in shared memory.
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
 // kind::f16, A = B = bf16, D = fp32, both operands K-major, M = 128.
 __device__ __forceinline__ uint32_t make_idesc(uint32_t n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
-__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// One lane of a converged warp; everything the elected lane consumes is computed warp-uniformly outside,
+// so the compiler keeps descriptors in uniform registers instead of emitting a per-lane election loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred) :: "memory");
+    return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -217,9 +249,7 @@ __device__ __forceinline__ float softplus_l2(float z) { return z > 28.85f ? z * 
 // ------------------------------------------------------------------------------------------------
 // shared memory plan
 // ------------------------------------------------------------------------------------------------
-constexpr int MAX_OPS = 128;
 struct Smem {
-    Op ops[MAX_OPS];
     uint64_t w_full[STAGES], w_empty[STAGES];
     uint64_t x_full, x_empty, a_ready;
     uint64_t acc_full[2], acc_empty[2];
@@ -283,12 +313,20 @@ __device__ __forceinline__ float spline8_circular(const uint32_t (&r)[32], float
     return LN2 * lg2(nn * rr * rr);
 }
 
+// development aid: CTA 0 stamps clock64() of key events into debug_params (as long long) when debug_mode & 16
+__device__ __forceinline__ void trace(const Params& p, int role, int& slot, int tag) {
+    if ((p.debug_mode & 16) && blockIdx.x == 0 && slot < 400) {
+        long long* t = reinterpret_cast<long long*>(p.debug_params) + role * 800 + 2 * slot;
+        t[0] = clock64();
+        t[1] = tag;
+        ++slot;
+    }
+}
+
 __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const int a_slabs = max(p.K1, p.HP) / 8;
-    uint8_t* sA = smem_raw;                                         // A operand: a_slabs x 2048 B
-    uint8_t* sW = sA + (size_t)a_slabs * SLAB_BYTES;                // weight ring
-    float* sX = reinterpret_cast<float*>(sW + (size_t)STAGES * STAGE_BYTES);   // x / y tile, row-major [128][D]
+    uint8_t* sW = smem_raw;                                                     // weight ring
+    float* sX = reinterpret_cast<float*>(sW + (size_t)STAGES * STAGE_BYTES);    // x / y tile, row-major [128][D]
     const int x_tile_bytes = TILE_M * p.D * 4;
     FeatConst* sFeat = reinterpret_cast<FeatConst*>(reinterpret_cast<uint8_t*>(sX) + ((x_tile_bytes + 127) & ~127));
     const int n_feat = p.n_chunks * FEATS_PER_CHUNK;
@@ -300,7 +338,6 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
 
     // ---- one-time setup ----
     for (int i = tid; i < n_feat; i += THREADS) sFeat[i] = p.feats[i];
-    for (int i = tid; i < p.n_ops; i += THREADS) sm->ops[i] = p.ops[i];
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&sm->w_full[s], 1); mbar_init(&sm->w_empty[s], 1); }
         mbar_init(&sm->x_full, 1);
@@ -317,59 +354,80 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
 
     if (warp == 0) {
         // =========================== producer: x tiles + weight blocks ===========================
-        if (lane == 0) {
-            uint32_t stage = 0, wphase = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-                const int rows = min(TILE_M, p.batch - tile * TILE_M);
-                mbar_wait(&sm->x_empty, (tcount & 1) ^ 1, p.error, 1);
+        // The whole warp walks the schedule (warp-uniform control flow); one elected lane issues the copies.
+        uint32_t stage = 0, wphase = 0, tcount = 0;
+        int ts = lane == 0 ? 0 : 1000000;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+            const int rows = min(TILE_M, p.batch - tile * TILE_M);
+            mbar_wait(&sm->x_empty, (tcount & 1) ^ 1, p.error, 1);
+            trace(p, 0, ts, 1001);
+            if (elect_one()) {
                 if (rows == TILE_M) {
                     mbar_expect_tx(&sm->x_full, (uint32_t)x_tile_bytes);
                     bulk_g2s(sX, p.x + (size_t)tile * TILE_M * p.D, (uint32_t)x_tile_bytes, &sm->x_full);
                 } else {
                     mbar_arrive(&sm->x_full);       // ragged last tile: the epilogue warps copy it themselves
                 }
-                for (int i = 0; i < p.n_ops; ++i) {
-                    const uint32_t bytes = sm->ops[i].w_bytes;
-                    mbar_wait(&sm->w_empty[stage], wphase ^ 1, p.error, 2);
-                    mbar_expect_tx(&sm->w_full[stage], bytes);
-                    bulk_g2s(sW + (size_t)stage * STAGE_BYTES, p.weights + sm->ops[i].w_off, bytes, &sm->w_full[stage]);
-                    if (++stage == STAGES) { stage = 0; wphase ^= 1; }
+            }
+            __syncwarp();
+            for (int i = 0; i < p.n_ops; ++i) {
+                const uint32_t bytes = (uint32_t)p.ops[i].w_bytes16 * 16u;
+                const uint32_t w_off = p.ops[i].w_off;
+                mbar_wait(&sm->w_empty[stage], wphase ^ 1, p.error, 2);
+                trace(p, 0, ts, i);
+                if (elect_one()) {
+                    if (p.debug_mode & 1) {
+                        mbar_arrive(&sm->w_full[stage]);
+                    } else {
+                        mbar_expect_tx(&sm->w_full[stage], bytes);
+                        bulk_g2s(sW + (size_t)stage * STAGE_BYTES, p.weights + w_off, bytes, &sm->w_full[stage]);
+                    }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; wphase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
-            uint32_t stage = 0, wphase = 0, a_cnt = 0, empty_cnt[2] = {0, 0};
-            const uint32_t a_base = smem_u32(sA);
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int i = 0; i < p.n_ops; ++i) {
-                    const Op op = sm->ops[i];
-                    const uint32_t acc = (op.flags & OP_ACC1) ? 1u : 0u;
-                    if (op.flags & OP_WAIT_A) {
-                        mbar_wait(&sm->a_ready, a_cnt & 1, p.error, 3);
-                        ++a_cnt;
-                        tc_fence_after();
-                    }
-                    if (op.flags & OP_WAIT_EMPTY) {
-                        mbar_wait(&sm->acc_empty[acc], (empty_cnt[acc] & 1) ^ 1, p.error, 4);
-                        ++empty_cnt[acc];
-                        tc_fence_after();
-                    }
-                    mbar_wait(&sm->w_full[stage], wphase, p.error, 5);
-                    tc_fence_after();
-                    const uint32_t b_base = smem_u32(sW + (size_t)stage * STAGE_BYTES);
-                    const uint32_t idesc = make_idesc(op.n);
-                    const uint32_t b_lbo = (uint32_t)op.n * 16u;
-                    for (uint32_t ks = 0; ks < op.ksteps; ++ks) {
-                        const uint64_t da = make_desc(a_base + (op.a_slab0 + 2 * ks) * SLAB_BYTES, SLAB_BYTES, 128);
-                        const uint64_t db = make_desc(b_base + ks * 2 * b_lbo, b_lbo, 128);
-                        umma(tmem + op.tmem_col, da, db, idesc, ((op.flags & OP_FIRST) && ks == 0) ? 0u : 1u);
+        // Warp-uniform walk over the schedule; one elected lane issues the tcgen05.mma / commit instructions.
+        uint32_t stage = 0, wphase = 0, a_cnt = 0, empty_cnt0 = 0, empty_cnt1 = 0;
+        int ts = lane == 0 ? 0 : 1000000;
+        const uint32_t w_base16 = smem_u32(sW) >> 4;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int i = 0; i < p.n_ops; ++i) {
+                const uint32_t flags = p.ops[i].flags, n = p.ops[i].n;
+                const uint32_t acc = (flags & OP_ACC1) ? 1u : 0u;
+                if (flags & OP_WAIT_A) {
+                    mbar_wait(&sm->a_ready, a_cnt & 1, p.error, 3);
+                    ++a_cnt;
+                }
+                if (flags & OP_WAIT_EMPTY) {
+                    if (acc) { mbar_wait(&sm->acc_empty[1], (empty_cnt1 & 1) ^ 1, p.error, 4); ++empty_cnt1; }
+                    else { mbar_wait(&sm->acc_empty[0], (empty_cnt0 & 1) ^ 1, p.error, 4); ++empty_cnt0; }
+                }
+                trace(p, 1, ts, 2000 + i);
+                mbar_wait(&sm->w_full[stage], wphase, p.error, 5);
+                tc_fence_after();
+                trace(p, 1, ts, i);
+                // B descriptor: high word constant (SBO = 128 B, version 1); low word = address >> 4 | LBO >> 4 << 16,
+                // advanced per k-step by two 8-k slabs of n rows x 16 B.  A: 8 TMEM columns per k-step.
+                const uint32_t b_lo = w_base16 + stage * (STAGE_BYTES >> 4) + (n << 16);
+                const uint32_t a_tmem = tmem + A_COL + p.ops[i].a_col;
+                const uint32_t ksteps = (p.debug_mode & 8) ? 1u : (uint32_t)p.ops[i].ksteps;
+                const uint32_t d_tmem = tmem + p.ops[i].tmem_col;
+                const uint32_t idesc = make_idesc(n);
+                if (elect_one()) {
+                    uint32_t accumulate = (flags & OP_FIRST) ? 0u : 1u;
+                    for (uint32_t ks = 0; ks < ksteps; ++ks) {
+                        const uint64_t db = ((uint64_t)DESC_HI << 32) | (b_lo + ks * 2u * n);
+                        umma_ts(d_tmem, a_tmem + ks * 8u, db, idesc, accumulate);
+                        accumulate = 1u;
                     }
                     umma_commit(&sm->w_empty[stage]);                   // frees the ring stage when the MMAs retire
-                    if (op.flags & OP_COMMIT) umma_commit(&sm->acc_full[acc]);
-                    if (++stage == STAGES) { stage = 0; wphase ^= 1; }
+                    if (flags & OP_COMMIT) umma_commit(&sm->acc_full[acc]);
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; wphase ^= 1; }
             }
         }
     } else {
@@ -379,52 +437,60 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
         const int row = (warp & 3) * 32 + lane;   // sample row of the tile = TMEM lane
         const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t full_cnt[2] = {0, 0}, tcount = 0;
-        const int groups = p.HP / 8;              // 8-column groups of a hidden layer
-        const int g_lo = wg * groups / EPI_WGS, g_hi = (wg + 1) * groups / EPI_WGS;
         float* xrow = sX + row * p.D;
+        int ts = (et == 0) ? 0 : 1000000;
 
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
             const int rows = min(TILE_M, p.batch - tile * TILE_M);
-            // ---- x tile -> A0 (two constant-one columns after the D inputs carry the biases) ----
+            // ---- x tile -> A0 in tensor memory (bf16 pairs; columns D, D+1 are the constant ones) ----
             mbar_wait(&sm->x_full, tcount & 1, p.error, 6);
+            trace(p, 2, ts, 3001);
             if (rows < TILE_M) {
                 const float* src = p.x + (size_t)tile * TILE_M * p.D;
                 for (int i = et; i < TILE_M * p.D; i += EPI_THREADS) sX[i] = i < rows * p.D ? src[i] : 0.f;
                 asm volatile("bar.sync 1, 512;" ::: "memory");
             }
-            {
-                const int slabs1 = p.K1 / 8;
-                for (int j = wg; j < slabs1; j += EPI_WGS) {
-                    float v[8];
+            for (int c0 = wg * 8; c0 < p.K1 / 2; c0 += EPI_WGS * 8) {      // 8 TMEM columns = 16 inputs per step
+                uint32_t q[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int k = j * 8 + i;
-                        v[i] = k < p.D ? xrow[k] : (k < p.D + 2 ? 1.f : 0.f);
-                    }
-                    uint4 q = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                    *reinterpret_cast<uint4*>(sA + (size_t)j * SLAB_BYTES + row * 16) = q;
+                for (int i = 0; i < 8; ++i) {
+                    const int k = (c0 + i) * 2;
+                    const float v0 = k < p.D ? xrow[k] : (k < p.D + 2 ? 1.f : 0.f);
+                    const float v1 = k + 1 < p.D ? xrow[k + 1] : (k + 1 < p.D + 2 ? 1.f : 0.f);
+                    q[i] = pack_bf16(v0, v1);
                 }
-                fence_async_smem();
-                mbar_arrive(&sm->a_ready);
+                tmem_st8(lane_addr + A_COL + c0, q);
             }
-            // ---- two hidden layers: ELU, bf16 -> A (bias already in the accumulator) ----
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&sm->a_ready);
+            trace(p, 2, ts, 3002);
+            // ---- two hidden layers: ELU, bf16 -> A operand of the next GEMM (tensor memory) ----
             for (int layer = 0; layer < 2; ++layer) {
                 mbar_wait(&sm->acc_full[0], full_cnt[0] & 1, p.error, 7);
                 ++full_cnt[0];
                 tc_fence_after();
-                for (int g = g_lo; g < g_hi; ++g) {
-                    uint32_t r[8];
-                    tmem_ld8(lane_addr + g * 8, r);
-                    tmem_wait8(r);
-                    float v[8];
+                trace(p, 2, ts, 3010 + layer);
+                // 16 accumulator columns per step; the load of the next step is in flight while this one is processed
+                uint32_t r[16], rn[16];
+                int c0 = wg * 16;
+                if (c0 < p.HP) tmem_ld16(lane_addr + c0, r);
+                for (; c0 < p.HP; c0 += EPI_WGS * 16) {
+                    tmem_wait8(r); tmem_wait8(r + 8);
+                    const int cn = c0 + EPI_WGS * 16;
+                    if (cn < p.HP) tmem_ld16(lane_addr + cn, rn);
+                    uint32_t q[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = fast_elu(__uint_as_float(r[i]));
-                    uint4 q = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                    *reinterpret_cast<uint4*>(sA + (size_t)g * SLAB_BYTES + row * 16) = q;
+                    for (int i = 0; i < 8; ++i)
+                        q[i] = pack_bf16(fast_elu(__uint_as_float(r[2 * i])), fast_elu(__uint_as_float(r[2 * i + 1])));
+                    tmem_st8(lane_addr + A_COL + c0 / 2, q);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) r[i] = rn[i];
                 }
-                fence_async_smem();
+                tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&sm->a_ready);
+                trace(p, 2, ts, 3020 + layer);
             }
             // ---- output layer chunks: spline transformer straight out of TMEM ----
             float ld = 0.f;
@@ -433,16 +499,28 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
                 mbar_wait(&sm->acc_full[b], full_cnt[b] & 1, p.error, 8);
                 ++full_cnt[b];
                 tc_fence_after();
-                const uint32_t col0 = lane_addr + (b ? ACC1_COL : 0);
-#pragma unroll 1
-                for (int jj = 0; jj < FEATS_PER_CHUNK / EPI_WGS; ++jj) {
-                    const int slot = wg * (FEATS_PER_CHUNK / EPI_WGS) + jj;
+                trace(p, 2, ts, 3100 + c);
+                {
+                    const int slot = wg;                                   // one feature slot per warpgroup
                     uint32_t r[32];
-                    tmem_ld32(col0 + slot * PSTRIDE, r);
-                    tmem_wait8(r); tmem_wait8(r + 8); tmem_wait8(r + 16); tmem_wait8(r + 24);
+                    if (p.debug_mode & 4) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) r[i] = 0x3c000000u + i * 1234567u + row;
+                    } else {
+                        const uint32_t a0 = lane_addr + b * CHUNK_N + slot * PSTRIDE;
+                        tmem_ld16(a0, r);                  // 25 parameters: 16 + 8 + 1 columns
+                        tmem_ld8(a0 + 16, r + 16);
+                        tmem_ld1(a0 + 24, r + 24);
+                        tmem_wait8(r); tmem_wait8(r + 8); tmem_wait8(r + 16); tmem_wait1(r + 24);
+                    }
                     const FeatConst fc = sFeat[c * FEATS_PER_CHUNK + slot];
-                    if (fc.col >= 0) {
-                        if (p.debug_params != nullptr && row < rows) {
+                    if (p.debug_mode & 2) {
+                        float acc = 0.f;
+#pragma unroll
+                        for (int i = 0; i < NPAR; ++i) acc += __uint_as_float(r[i]);
+                        ld += acc;
+                    } else if (fc.col >= 0) {
+                        if (p.debug_params != nullptr && !(p.debug_mode & 16) && row < rows) {
                             float* dbg = p.debug_params + ((size_t)tile * TILE_M + row) * p.n_chunks * CHUNK_N + c * CHUNK_N +
                                          slot * PSTRIDE;
 #pragma unroll
@@ -455,6 +533,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
                 }
                 tc_fence_before();
                 mbar_arrive(&sm->acc_empty[b]);
+                trace(p, 2, ts, 3200 + c);
             }
             // ---- log-det: combine the warpgroups, store; y tile leaves with one bulk store ----
             if (wg > 0) sLd[(wg - 1) * TILE_M + row] = ld;
@@ -470,6 +549,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
                     bulk_s2g(p.y + (size_t)tile * TILE_M * p.D, sX, (uint32_t)x_tile_bytes);
                     bulk_wait_read();
                     mbar_arrive(&sm->x_empty);
+                    trace(p, 2, ts, 3300);
                 }
             }
             if (rows < TILE_M) {
@@ -488,8 +568,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
 }
 
 size_t smem_bytes(const Params& p) {
-    const size_t a_slabs = (size_t)(p.K1 > p.HP ? p.K1 : p.HP) / 8;
-    size_t s = a_slabs * SLAB_BYTES + (size_t)STAGES * STAGE_BYTES;
+    size_t s = (size_t)STAGES * STAGE_BYTES;
     s += ((size_t)TILE_M * p.D * 4 + 127) & ~(size_t)127;
     s += (size_t)p.n_chunks * FEATS_PER_CHUNK * sizeof(FeatConst);
     s += (EPI_WGS - 1) * TILE_M * 4 + sizeof(Smem);
@@ -509,7 +588,9 @@ extern "C" int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_st
     TFEPB_CHECK_ARG(a->x && a->y && a->logdet && a->ops && a->weights && a->feats, "null buffer");
     TFEPB_CHECK_ARG(a->batch >= 0 && a->n_features > 0, "bad sizes");
     TFEPB_CHECK_ARG(a->k1 % 16 == 0 && a->k1 >= a->n_features + 2, "k1 must hold n_features + 2 bias columns, rounded up to 16");
-    TFEPB_CHECK_ARG(a->hidden_padded % 16 == 0 && a->hidden_padded > 0 && a->hidden_padded <= 512, "bad hidden width");
+    TFEPB_CHECK_ARG(a->hidden_padded % 16 == 0 && a->hidden_padded > 0 && a->hidden_padded <= fused::ACC_COLS,
+                    "hidden width (padded) must be a multiple of 16 and at most 336 (tensor-memory plan)");
+    TFEPB_CHECK_ARG(a->k1 <= 2 * (512 - fused::A_COL), "too many input features for the tensor-memory plan");
     TFEPB_CHECK_ARG(a->n_chunks > 0 && a->n_ops > 0 && a->n_ops <= fused::MAX_OPS, "bad schedule length");
     TFEPB_CHECK_ARG((a->n_features * 4 * fused::TILE_M) % 16 == 0, "tile of x must be a multiple of 16 bytes");
     TFEPB_CHECK_ARG(((uintptr_t)a->x % 16 == 0) && ((uintptr_t)a->y % 16 == 0) && ((uintptr_t)a->weights % 16 == 0),
@@ -520,11 +601,13 @@ extern "C" int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_st
     p.x = (const float*)a->x; p.y = (float*)a->y; p.logdet = (float*)a->logdet;
     p.batch = a->batch; p.D = a->n_features; p.K1 = a->k1; p.HP = a->hidden_padded;
     p.n_chunks = a->n_chunks; p.n_ops = a->n_ops;
-    p.ops = (const fused::Op*)a->ops; p.weights = (const uint8_t*)a->weights;
+    memcpy(p.ops, a->ops, sizeof(fused::Op) * (size_t)a->n_ops);
+    p.weights = (const uint8_t*)a->weights;
     p.feats = (const fused::FeatConst*)a->feats;
     p.min_bin = a->min_bin_size; p.min_slope = a->min_slope; p.slope_offset2 = a->slope_offset * fused::LOG2E;
     p.error = a->error_flag;
     p.debug_params = a->debug_params;
+    p.debug_mode = a->reserved;
     const size_t smem = fused::smem_bytes(p);
     TFEPB_CHECK_ARG(smem <= 227 * 1024, "shared memory plan of %zu bytes exceeds 227 KB", smem);
     static thread_local size_t configured = 0;
