@@ -120,8 +120,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded wait: a protocol bug must end in a trap (error return), never in a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* error, int tag) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t polls = 0;
+    long long t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if ((++polls & 0xfffu) != 0) continue;          // look at the clock every 4096 failed polls only
+        if (t0 == 0) t0 = clock64();
         if ((uint64_t)(clock64() - t0) > WATCHDOG_CYCLES) {
             if (error) atomicExch(error, tag);
             __threadfence_system();
@@ -314,7 +317,9 @@ __device__ __forceinline__ float spline8_circular(const uint32_t (&r)[32], float
 }
 
 // development aid: CTA 0 stamps clock64() of key events into debug_params (as long long) when debug_mode & 16
+template <bool DEBUG>
 __device__ __forceinline__ void trace(const Params& p, int role, int& slot, int tag) {
+    if (!DEBUG) return;
     if ((p.debug_mode & 16) && blockIdx.x == 0 && slot < 400) {
         long long* t = reinterpret_cast<long long*>(p.debug_params) + role * 800 + 2 * slot;
         t[0] = clock64();
@@ -323,7 +328,9 @@ __device__ __forceinline__ void trace(const Params& p, int role, int& slot, int 
     }
 }
 
+template <bool DEBUG>
 __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params p) {
+    const int dmode = DEBUG ? p.debug_mode : 0;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* sW = smem_raw;                                                     // weight ring
     float* sX = reinterpret_cast<float*>(sW + (size_t)STAGES * STAGE_BYTES);    // x / y tile, row-major [128][D]
@@ -360,7 +367,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
             const int rows = min(TILE_M, p.batch - tile * TILE_M);
             mbar_wait(&sm->x_empty, (tcount & 1) ^ 1, p.error, 1);
-            trace(p, 0, ts, 1001);
+            trace<DEBUG>(p, 0, ts, 1001);
             if (elect_one()) {
                 if (rows == TILE_M) {
                     mbar_expect_tx(&sm->x_full, (uint32_t)x_tile_bytes);
@@ -374,9 +381,9 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
                 const uint32_t bytes = (uint32_t)p.ops[i].w_bytes16 * 16u;
                 const uint32_t w_off = p.ops[i].w_off;
                 mbar_wait(&sm->w_empty[stage], wphase ^ 1, p.error, 2);
-                trace(p, 0, ts, i);
+                trace<DEBUG>(p, 0, ts, i);
                 if (elect_one()) {
-                    if (p.debug_mode & 1) {
+                    if (dmode & 1) {
                         mbar_arrive(&sm->w_full[stage]);
                     } else {
                         mbar_expect_tx(&sm->w_full[stage], bytes);
@@ -405,15 +412,15 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
                     if (acc) { mbar_wait(&sm->acc_empty[1], (empty_cnt1 & 1) ^ 1, p.error, 4); ++empty_cnt1; }
                     else { mbar_wait(&sm->acc_empty[0], (empty_cnt0 & 1) ^ 1, p.error, 4); ++empty_cnt0; }
                 }
-                trace(p, 1, ts, 2000 + i);
+                trace<DEBUG>(p, 1, ts, 2000 + i);
                 mbar_wait(&sm->w_full[stage], wphase, p.error, 5);
                 tc_fence_after();
-                trace(p, 1, ts, i);
+                trace<DEBUG>(p, 1, ts, i);
                 // B descriptor: high word constant (SBO = 128 B, version 1); low word = address >> 4 | LBO >> 4 << 16,
                 // advanced per k-step by two 8-k slabs of n rows x 16 B.  A: 8 TMEM columns per k-step.
                 const uint32_t b_lo = w_base16 + stage * (STAGE_BYTES >> 4) + (n << 16);
                 const uint32_t a_tmem = tmem + A_COL + p.ops[i].a_col;
-                const uint32_t ksteps = (p.debug_mode & 8) ? 1u : (uint32_t)p.ops[i].ksteps;
+                const uint32_t ksteps = (dmode & 8) ? 1u : (uint32_t)p.ops[i].ksteps;
                 const uint32_t d_tmem = tmem + p.ops[i].tmem_col;
                 const uint32_t idesc = make_idesc(n);
                 if (elect_one()) {
@@ -444,7 +451,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
             const int rows = min(TILE_M, p.batch - tile * TILE_M);
             // ---- x tile -> A0 in tensor memory (bf16 pairs; columns D, D+1 are the constant ones) ----
             mbar_wait(&sm->x_full, tcount & 1, p.error, 6);
-            trace(p, 2, ts, 3001);
+            trace<DEBUG>(p, 2, ts, 3001);
             if (rows < TILE_M) {
                 const float* src = p.x + (size_t)tile * TILE_M * p.D;
                 for (int i = et; i < TILE_M * p.D; i += EPI_THREADS) sX[i] = i < rows * p.D ? src[i] : 0.f;
@@ -464,13 +471,13 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&sm->a_ready);
-            trace(p, 2, ts, 3002);
+            trace<DEBUG>(p, 2, ts, 3002);
             // ---- two hidden layers: ELU, bf16 -> A operand of the next GEMM (tensor memory) ----
             for (int layer = 0; layer < 2; ++layer) {
                 mbar_wait(&sm->acc_full[0], full_cnt[0] & 1, p.error, 7);
                 ++full_cnt[0];
                 tc_fence_after();
-                trace(p, 2, ts, 3010 + layer);
+                trace<DEBUG>(p, 2, ts, 3010 + layer);
                 // 16 accumulator columns per step; the load of the next step is in flight while this one is processed
                 uint32_t r[16], rn[16];
                 int c0 = wg * 16;
@@ -490,7 +497,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&sm->a_ready);
-                trace(p, 2, ts, 3020 + layer);
+                trace<DEBUG>(p, 2, ts, 3020 + layer);
             }
             // ---- output layer chunks: spline transformer straight out of TMEM ----
             float ld = 0.f;
@@ -499,11 +506,11 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
                 mbar_wait(&sm->acc_full[b], full_cnt[b] & 1, p.error, 8);
                 ++full_cnt[b];
                 tc_fence_after();
-                trace(p, 2, ts, 3100 + c);
+                trace<DEBUG>(p, 2, ts, 3100 + c);
                 {
                     const int slot = wg;                                   // one feature slot per warpgroup
                     uint32_t r[32];
-                    if (p.debug_mode & 4) {
+                    if (dmode & 4) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) r[i] = 0x3c000000u + i * 1234567u + row;
                     } else {
@@ -514,13 +521,13 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
                         tmem_wait8(r); tmem_wait8(r + 8); tmem_wait8(r + 16); tmem_wait1(r + 24);
                     }
                     const FeatConst fc = sFeat[c * FEATS_PER_CHUNK + slot];
-                    if (p.debug_mode & 2) {
+                    if (dmode & 2) {
                         float acc = 0.f;
 #pragma unroll
                         for (int i = 0; i < NPAR; ++i) acc += __uint_as_float(r[i]);
                         ld += acc;
                     } else if (fc.col >= 0) {
-                        if (p.debug_params != nullptr && !(p.debug_mode & 16) && row < rows) {
+                        if (DEBUG && p.debug_params != nullptr && !(dmode & 16) && row < rows) {
                             float* dbg = p.debug_params + ((size_t)tile * TILE_M + row) * p.n_chunks * CHUNK_N + c * CHUNK_N +
                                          slot * PSTRIDE;
 #pragma unroll
@@ -533,7 +540,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
                 }
                 tc_fence_before();
                 mbar_arrive(&sm->acc_empty[b]);
-                trace(p, 2, ts, 3200 + c);
+                trace<DEBUG>(p, 2, ts, 3200 + c);
             }
             // ---- log-det: combine the warpgroups, store; y tile leaves with one bulk store ----
             if (wg > 0) sLd[(wg - 1) * TILE_M + row] = ld;
@@ -549,7 +556,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
                     bulk_s2g(p.y + (size_t)tile * TILE_M * p.D, sX, (uint32_t)x_tile_bytes);
                     bulk_wait_read();
                     mbar_arrive(&sm->x_empty);
-                    trace(p, 2, ts, 3300);
+                    trace<DEBUG>(p, 2, ts, 3300);
                 }
             }
             if (rows < TILE_M) {
@@ -610,13 +617,15 @@ extern "C" int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_st
     p.debug_mode = a->reserved;
     const size_t smem = fused::smem_bytes(p);
     TFEPB_CHECK_ARG(smem <= 227 * 1024, "shared memory plan of %zu bytes exceeds 227 KB", smem);
-    static thread_local size_t configured = 0;
-    if (configured < smem) {
-        TFEPB_CUDA(cudaFuncSetAttribute(fused::maf_spline_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    const bool debug = p.debug_mode != 0 || p.debug_params != nullptr;
+    auto kernel = debug ? fused::maf_spline_fwd_kernel<true> : fused::maf_spline_fwd_kernel<false>;
+    static thread_local size_t configured[2] = {0, 0};
+    if (configured[debug] < smem) {
+        TFEPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[debug] = smem;
     }
     const int n_tiles = (a->batch + fused::TILE_M - 1) / fused::TILE_M;
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-    fused::maf_spline_fwd_kernel<<<grid, fused::THREADS, smem, as_stream(stream)>>>(p);
+    kernel<<<grid, fused::THREADS, smem, as_stream(stream)>>>(p);
     return check_launch("maf_spline_fwd_kernel");
 }
