@@ -254,7 +254,7 @@ __device__ __forceinline__ float softplus_l2(float z) { return z > 28.85f ? z * 
 // ------------------------------------------------------------------------------------------------
 struct Smem {
     uint64_t w_full[STAGES], w_empty[STAGES];
-    uint64_t x_full, x_empty, a_ready;
+    uint64_t x_full[2], x_empty[2], a_ready;
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
     uint32_t pad[3];
@@ -333,9 +333,10 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
     const int dmode = DEBUG ? p.debug_mode : 0;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* sW = smem_raw;                                                     // weight ring
-    float* sX = reinterpret_cast<float*>(sW + (size_t)STAGES * STAGE_BYTES);    // x / y tile, row-major [128][D]
+    float* sX0 = reinterpret_cast<float*>(sW + (size_t)STAGES * STAGE_BYTES);   // two x / y tiles, row-major [128][D]
     const int x_tile_bytes = TILE_M * p.D * 4;
-    FeatConst* sFeat = reinterpret_cast<FeatConst*>(reinterpret_cast<uint8_t*>(sX) + ((x_tile_bytes + 127) & ~127));
+    const int x_tile_stride = (x_tile_bytes + 127) & ~127;
+    FeatConst* sFeat = reinterpret_cast<FeatConst*>(reinterpret_cast<uint8_t*>(sX0) + 2 * x_tile_stride);
     const int n_feat = p.n_chunks * FEATS_PER_CHUNK;
     float* sLd = reinterpret_cast<float*>(sFeat + n_feat);          // [EPI_WGS - 1][128] log-det partials
     Smem* sm = reinterpret_cast<Smem*>(sLd + (EPI_WGS - 1) * TILE_M);
@@ -347,8 +348,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
     for (int i = tid; i < n_feat; i += THREADS) sFeat[i] = p.feats[i];
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&sm->w_full[s], 1); mbar_init(&sm->w_empty[s], 1); }
-        mbar_init(&sm->x_full, 1);
-        mbar_init(&sm->x_empty, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&sm->x_full[b], 1); mbar_init(&sm->x_empty[b], 1); }
         mbar_init(&sm->a_ready, EPI_THREADS);
         for (int b = 0; b < 2; ++b) { mbar_init(&sm->acc_full[b], 1); mbar_init(&sm->acc_empty[b], EPI_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -364,19 +364,27 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
         // The whole warp walks the schedule (warp-uniform control flow); one elected lane issues the copies.
         uint32_t stage = 0, wphase = 0, tcount = 0;
         int ts = lane == 0 ? 0 : 1000000;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+        // x tile of local tile number t lives in buffer t & 1; it is requested one tile ahead, so its latency
+        // (and the drain of the y store that previously used the buffer) is off the critical path
+        auto request_x = [&](int tile, uint32_t t) {
             const int rows = min(TILE_M, p.batch - tile * TILE_M);
-            mbar_wait(&sm->x_empty, (tcount & 1) ^ 1, p.error, 1);
-            trace<DEBUG>(p, 0, ts, 1001);
+            const uint32_t b = t & 1;
+            mbar_wait(&sm->x_empty[b], ((t >> 1) & 1) ^ 1, p.error, 1);
             if (elect_one()) {
+                float* dst = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sX0) + b * x_tile_stride);
                 if (rows == TILE_M) {
-                    mbar_expect_tx(&sm->x_full, (uint32_t)x_tile_bytes);
-                    bulk_g2s(sX, p.x + (size_t)tile * TILE_M * p.D, (uint32_t)x_tile_bytes, &sm->x_full);
+                    mbar_expect_tx(&sm->x_full[b], (uint32_t)x_tile_bytes);
+                    bulk_g2s(dst, p.x + (size_t)tile * TILE_M * p.D, (uint32_t)x_tile_bytes, &sm->x_full[b]);
                 } else {
-                    mbar_arrive(&sm->x_full);       // ragged last tile: the epilogue warps copy it themselves
+                    mbar_arrive(&sm->x_full[b]);    // ragged last tile: the epilogue warps copy it themselves
                 }
             }
             __syncwarp();
+        };
+        if ((int)blockIdx.x < n_tiles) request_x(blockIdx.x, 0);
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+            trace<DEBUG>(p, 0, ts, 1001);
+            const int prefetch_at = p.n_ops > 8 ? 8 : p.n_ops - 1;   // after the first weight blocks of this tile are in flight
             for (int i = 0; i < p.n_ops; ++i) {
                 const uint32_t bytes = (uint32_t)p.ops[i].w_bytes16 * 16u;
                 const uint32_t w_off = p.ops[i].w_off;
@@ -392,6 +400,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; wphase ^= 1; }
+                if (i == prefetch_at && tile + (int)gridDim.x < n_tiles) request_x(tile + gridDim.x, tcount + 1);
             }
         }
     } else if (warp == 1) {
@@ -444,13 +453,15 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
         const int row = (warp & 3) * 32 + lane;   // sample row of the tile = TMEM lane
         const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t full_cnt[2] = {0, 0}, tcount = 0;
-        float* xrow = sX + row * p.D;
         int ts = (et == 0) ? 0 : 1000000;
 
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
             const int rows = min(TILE_M, p.batch - tile * TILE_M);
             // ---- x tile -> A0 in tensor memory (bf16 pairs; columns D, D+1 are the constant ones) ----
-            mbar_wait(&sm->x_full, tcount & 1, p.error, 6);
+            const uint32_t xb = tcount & 1;
+            float* sX = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sX0) + xb * x_tile_stride);
+            float* xrow = sX + row * p.D;
+            mbar_wait(&sm->x_full[xb], (tcount >> 1) & 1, p.error, 6);
             trace<DEBUG>(p, 2, ts, 3001);
             if (rows < TILE_M) {
                 const float* src = p.x + (size_t)tile * TILE_M * p.D;
@@ -554,8 +565,8 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
                 }
                 if (rows == TILE_M && et == 0) {
                     bulk_s2g(p.y + (size_t)tile * TILE_M * p.D, sX, (uint32_t)x_tile_bytes);
-                    bulk_wait_read();
-                    mbar_arrive(&sm->x_empty);
+                    bulk_wait_read();               // the other buffer is already being refilled: this wait is off the critical path
+                    mbar_arrive(&sm->x_empty[xb]);
                     trace<DEBUG>(p, 2, ts, 3300);
                 }
             }
@@ -563,7 +574,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
                 float* dst = p.y + (size_t)tile * TILE_M * p.D;
                 for (int i = et; i < rows * p.D; i += EPI_THREADS) dst[i] = sX[i];
                 asm volatile("bar.sync 1, 512;" ::: "memory");
-                if (et == 0) mbar_arrive(&sm->x_empty);
+                if (et == 0) mbar_arrive(&sm->x_empty[xb]);
             }
         }
     }
@@ -576,7 +587,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
 
 size_t smem_bytes(const Params& p) {
     size_t s = (size_t)STAGES * STAGE_BYTES;
-    s += ((size_t)TILE_M * p.D * 4 + 127) & ~(size_t)127;
+    s += 2 * (((size_t)TILE_M * p.D * 4 + 127) & ~(size_t)127);
     s += (size_t)p.n_chunks * FEATS_PER_CHUNK * sizeof(FeatConst);
     s += (EPI_WGS - 1) * TILE_M * 4 + sizeof(Smem);
     return s + 256;
