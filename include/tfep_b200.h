@@ -227,10 +227,12 @@ int tfepb_mt19937_indices(uint32_t* state625_dev, int64_t count, uint32_t max_id
 
 /* Fused resample + exponential average: for resample r (row r of idx, or a counter-based Philox
  * stream when idx == NULL) out_sums[r] = sum_j e[idx[r, j]] in double, where e_i = exp(v_i - max)
- * was produced by tfepb_exp_table.  analysis/bootstrap.py:185-233 with statistic = fep_estimator. */
+ * was produced by tfepb_exp_table.  analysis/bootstrap.py:185-233 with statistic = fep_estimator.
+ * `e` holds the n entries [shard_lo, shard_lo + n) of the global table (shard_lo = 0, n = everything on
+ * one GPU); draws outside the shard contribute zero, so the sums of batch-sharded ranks add up. */
 int tfepb_exp_table(int32_t dtype, const void* w, int64_t n, double scale, const double* max_dev,
                     float* e, tfepb_stream_t stream);
-int tfepb_bootstrap_sums(const float* e, int64_t n, uint32_t max_idx, const int32_t* idx, int64_t ldidx,
+int tfepb_bootstrap_sums(const float* e, int64_t n, int64_t shard_lo, uint32_t max_idx, const int32_t* idx, int64_t ldidx,
                          int32_t n_resamples, int64_t sample_size, uint64_t philox_seed,
                          uint64_t philox_offset, double* out_sums, tfepb_stream_t stream);
 

@@ -110,3 +110,26 @@ def test_philox_bootstrap_is_statistically_equivalent():
     # two independent bootstrap means differ by ~ sqrt(2) sigma / sqrt(R); allow 5 of those
     assert abs(float(a['mean']) - float(b['mean'])) < 5 * 2 ** 0.5 * float(a['standard_deviation']) / R ** 0.5
     assert 0.85 < float(b['standard_deviation']) / float(a['standard_deviation']) < 1.18
+
+
+def test_sharded_partials_add_up_on_one_gpu():
+    """Emulate two batch shards on one GPU: per-shard kernels + the host combine == the unsharded result."""
+    from tfep_b200 import _ops
+    from tfep_b200.analysis.estimator import _log_n, combine_partials
+    n, R = 30001, 9
+    w = (cases.normal((n,), 5) * 1.5).to(DEV)
+    cut = 11111
+    parts = torch.stack([_ops.lse(w[:cut], -1.0), _ops.lse(w[cut:], -1.0)])
+    m, s = combine_partials(parts)
+    df = -(m + torch.log(s) - _log_n(n))
+    assert rel_err(df, ao.fep_estimator(w.cpu().double())) < 1e-6
+    idx = torch.from_numpy(ao.resample_indices(3, R, n, n)).to(torch.int32).to(DEV)
+    total = torch.zeros(R, dtype=torch.float64, device=DEV)
+    gmax = parts[:, 0].max()
+    for lo, hi in ((0, cut), (cut, n)):
+        o = _ops.lse(w[lo:hi], -1.0)
+        e = _ops.exp_table(w[lo:hi], -1.0, o[:1])
+        total += _ops.bootstrap_sums(e, n, R, n, idx, shard_lo=lo) * torch.exp(o[0] - gmax)
+    stats = -(gmax + torch.log(total) - _log_n(n))
+    ref = ao.bootstrap_statistics(w.cpu(), ao.fep_estimator, R, generator=torch.Generator().manual_seed(3))
+    assert rel_err(stats, ref) < 2e-6

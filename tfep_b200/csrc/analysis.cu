@@ -133,9 +133,17 @@ constexpr int BS_DRAWS_PER_THREAD = 32;     // multiple of 4
 constexpr int BS_CHUNK = BS_THREADS * BS_DRAWS_PER_THREAD;
 
 // grid = (chunks of BS_CHUNK draws, resamples).  Explicit indices (exact MT19937 stream) or Philox.
+// A rank that holds only the shard [shard_lo, shard_lo + shard_len) of the data walks the SAME global index
+// stream and adds the draws that fall into its shard; the per-resample sums of all ranks add up.
+__device__ __forceinline__ float shard_fetch(const float* __restrict__ e, uint32_t i, uint32_t shard_lo, uint32_t shard_len) {
+    const uint32_t j = i - shard_lo;                 // wraps for i < shard_lo -> fails the range test
+    return j < shard_len ? __ldg(e + j) : 0.f;
+}
+
 __global__ void __launch_bounds__(BS_THREADS) bootstrap_sums_kernel(const float* __restrict__ e, uint32_t max_idx,
                                                                     const int32_t* __restrict__ idx, int64_t ldidx,
                                                                     int64_t sample_size, uint64_t seed, uint64_t offset,
+                                                                    uint32_t shard_lo, uint32_t shard_len,
                                                                     double* __restrict__ out) {
     const int r = blockIdx.y;
     const int64_t j0 = (int64_t)blockIdx.x * BS_CHUNK;
@@ -146,7 +154,7 @@ __global__ void __launch_bounds__(BS_THREADS) bootstrap_sums_kernel(const float*
         for (int k = 0; k < BS_DRAWS_PER_THREAD; ++k) {
             const int64_t j = j0 + (int64_t)k * BS_THREADS + threadIdx.x;
             if (j < sample_size) {
-                const float v = __ldg(e + row[j]);
+                const float v = shard_fetch(e, (uint32_t)row[j], shard_lo, shard_len);
                 if ((k & 3) == 0) acc0 += v; else if ((k & 3) == 1) acc1 += v; else if ((k & 3) == 2) acc2 += v; else acc3 += v;
             }
         }
@@ -159,10 +167,10 @@ __global__ void __launch_bounds__(BS_THREADS) bootstrap_sums_kernel(const float*
             if (j < sample_size) {
                 const uint64_t c = offset + ((uint64_t)r * (uint64_t)((sample_size + 3) / 4)) + (uint64_t)(j >> 2);
                 const uint4 u = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), key);
-                acc0 += __ldg(e + __umulhi(u.x, max_idx));
-                if (j + 1 < sample_size) acc1 += __ldg(e + __umulhi(u.y, max_idx));
-                if (j + 2 < sample_size) acc2 += __ldg(e + __umulhi(u.z, max_idx));
-                if (j + 3 < sample_size) acc3 += __ldg(e + __umulhi(u.w, max_idx));
+                acc0 += shard_fetch(e, __umulhi(u.x, max_idx), shard_lo, shard_len);
+                if (j + 1 < sample_size) acc1 += shard_fetch(e, __umulhi(u.y, max_idx), shard_lo, shard_len);
+                if (j + 2 < sample_size) acc2 += shard_fetch(e, __umulhi(u.z, max_idx), shard_lo, shard_len);
+                if (j + 3 < sample_size) acc3 += shard_fetch(e, __umulhi(u.w, max_idx), shard_lo, shard_len);
             }
         }
     }
@@ -285,19 +293,19 @@ extern "C" int tfepb_exp_table(int32_t dtype, const void* w, int64_t n, double s
     return check_launch("exp_table");
 }
 
-extern "C" int tfepb_bootstrap_sums(const float* e, int64_t n, uint32_t max_idx, const int32_t* idx, int64_t ldidx,
-                                    int32_t n_resamples, int64_t sample_size, uint64_t philox_seed,
+extern "C" int tfepb_bootstrap_sums(const float* e, int64_t n, int64_t shard_lo, uint32_t max_idx, const int32_t* idx,
+                                    int64_t ldidx, int32_t n_resamples, int64_t sample_size, uint64_t philox_seed,
                                     uint64_t philox_offset, double* out_sums, tfepb_stream_t stream) {
     TFEPB_CHECK_ARG(e && out_sums, "null buffer");
     TFEPB_CHECK_ARG(n_resamples > 0 && sample_size > 0, "bad sizes");
-    TFEPB_CHECK_ARG(max_idx > 0 && (int64_t)max_idx <= n, "max_idx out of range");
+    TFEPB_CHECK_ARG(max_idx > 0 && shard_lo >= 0 && n > 0 && n <= 0x7fffffff, "index range out of bounds");
     TFEPB_CHECK_ARG(n_resamples <= 65535, "at most 65535 resamples per call");
     if (int rc = require_sm100()) return rc;
     cudaStream_t s = as_stream(stream);
     TFEPB_CUDA(cudaMemsetAsync(out_sums, 0, sizeof(double) * n_resamples, s));
     dim3 grid((unsigned)((sample_size + BS_CHUNK - 1) / BS_CHUNK), (unsigned)n_resamples);
     bootstrap_sums_kernel<<<grid, BS_THREADS, 0, s>>>(e, max_idx, idx, ldidx, sample_size, philox_seed, philox_offset,
-                                                      out_sums);
+                                                      (uint32_t)shard_lo, (uint32_t)n, out_sums);
     return check_launch("bootstrap_sums");
 }
 
