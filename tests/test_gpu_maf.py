@@ -179,3 +179,17 @@ def test_headline_config_full_size_properties():
         d = (xi - x[sub]).abs()
         assert float(torch.minimum(d, (2 * math.pi - d).abs()).max()) < 2e-3
         assert float((ld[sub] + ldi).abs().max()) < 5e-3
+
+
+def test_host_pipeline_matches_direct_call():
+    """Chunked, stream-overlapped evaluation from / to pinned host memory == one direct call."""
+    from tfep_b200.utils.host_pipeline import HostPipeline
+    seq, _ = cfg_flow_modules('cfg2', DEV, n_layers=2)
+    x = cases.cfg_input('cfg2', 5000).pin_memory()
+    with torch.no_grad():
+        y, ld = seq(x.to(DEV))
+    pipe = HostPipeline(seq, 5000, 66, DEV, n_chunks=3)
+    for _ in range(2):
+        yh, ldh = pipe(x)
+        torch.cuda.synchronize()
+        assert torch.equal(yh, y.cpu()) and torch.equal(ldh, ld.cpu())
