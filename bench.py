@@ -276,7 +276,9 @@ def run_ours(args, rank, world, local_rank):
         launches_per_step = 16
     achieved = flops_per_launch / (k_ms * 1e-3) / 1e12
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': pk_peaks['bf16_tflops'], 'unit': 'TFLOP/s',
-                'frac': achieved / pk_peaks['bf16_tflops'], 'traffic': None, 'kernel': kernel,
+                'frac': achieved / pk_peaks['bf16_tflops'],
+                'traffic': 18.38e6 if args.precision == 'bf16' else None,   # dram read+write bytes per launch, ncu capture profiles/r01_ncu_fused_v3_details.md
+                'kernel': kernel,
                 'kernel_ms': k_ms, 'peak_source': pk_peaks['source'] + ', bf16 burst',
                 'whole_step_frac': (2.0 * plan.masked_macs * 4 * BATCH * args.steps / (total_ms * 1e-3) / 1e12)
                 / pk_peaks['bf16_tflops_sustained']}
