@@ -133,3 +133,17 @@ def test_sharded_partials_add_up_on_one_gpu():
     stats = -(gmax + torch.log(total) - _log_n(n))
     ref = ao.bootstrap_statistics(w.cpu(), ao.fep_estimator, R, generator=torch.Generator().manual_seed(3))
     assert rel_err(stats, ref) < 2e-6
+
+
+def test_estimator_unaligned_views_and_sizes():
+    """Vector loads with scalar head / tail: any offset and length gives the oracle's value."""
+    from tfep_b200.analysis import fep_estimator
+    base = cases.normal((5000,), 21) * 2
+    d = base.to(DEV)
+    for off in (0, 1, 2, 3, 5):
+        for n in (1, 3, 4, 17, 1023, 4096, 4990):
+            v = d[off:off + n]
+            assert rel_err(fep_estimator(v), ao.fep_estimator(base[off:off + n].double()).float()) < 2e-6, (off, n)
+    d64 = base.double().to(DEV)
+    for off in (0, 1):
+        assert rel_err(fep_estimator(d64[off:off + 999]), ao.fep_estimator(base[off:off + 999].double())) < 1e-12

@@ -47,43 +47,75 @@ __device__ __forceinline__ MS ms_block_reduce(MS v) {
     return v;   // valid in thread 0
 }
 
-// Each thread keeps a running (max, sum) over groups of UNROLL values: one exp per value plus one
-// rescale per group, the sum carried in double.
+// Each thread keeps a running (max, sum) over groups of values: one exp per value plus one rescale per
+// group, the sum carried in double.  The bulk is read with 16-byte vector loads, four of them in flight per
+// thread (the kernel is HBM bound: 4 or 8 bytes per sample, read once); the unaligned head / tail is scalar.
+template <typename T, int N>
+__device__ __forceinline__ void lse_absorb(const T (&v)[N], int count, T& m, double& s, bool& have) {
+    if (count <= 0) return;
+    T gm = v[0];
+#pragma unroll
+    for (int u = 1; u < N; ++u)
+        if (u < count) gm = v[u] > gm ? v[u] : gm;
+    if (!have || gm > m) {
+        if (have) s *= (double)Math<T>::exp(m - gm);
+        m = gm;
+        have = true;
+    }
+    T part = T(0);
+#pragma unroll
+    for (int u = 0; u < N; ++u)
+        if (u < count) part += Math<T>::exp(v[u] - m);
+    s += (double)part;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(LSE_THREADS) lse_partial_kernel(const T* __restrict__ w, const T* __restrict__ logw,
                                                                   int64_t n, T scale, double* __restrict__ partials) {
-    constexpr int UNROLL = 8;
+    constexpr int VEC = 16 / sizeof(T);          // elements per 16-byte load
+    constexpr int LOADS = 4;                      // vector loads in flight per thread
+    struct alignas(16) Pack { T v[VEC]; };
     T m = T(0);
     double s = 0.0;
     bool have = false;
-    const int64_t stride = (int64_t)gridDim.x * LSE_THREADS;
+    const int64_t nthreads = (int64_t)gridDim.x * LSE_THREADS;
     const int64_t t0 = (int64_t)blockIdx.x * LSE_THREADS + threadIdx.x;
-    for (int64_t base = t0; base < n; base += stride * UNROLL) {
-        T v[UNROLL];
-        T gm = T(0);
-        bool any = false;
+    // elements before the first 16-byte boundary of w (logw, if present, is only vector-loaded when co-aligned)
+    int64_t head = ((16 - (reinterpret_cast<uintptr_t>(w) & 15)) & 15) / sizeof(T);
+    if (head > n) head = n;
+    const bool vec_ok = logw == nullptr || ((reinterpret_cast<uintptr_t>(logw + head) & 15) == 0);
+    const int64_t nvec = vec_ok ? (n - head) / VEC : 0;
+    const Pack* wv = reinterpret_cast<const Pack*>(w + head);
+    const Pack* lv = reinterpret_cast<const Pack*>(logw ? logw + head : nullptr);
+    for (int64_t base = t0; base < nvec; base += nthreads * LOADS) {
+        Pack a[LOADS], b[LOADS];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int64_t i = base + (int64_t)u * stride;
-            if (i < n) {
-                v[u] = scale * w[i] + (logw ? logw[i] : T(0));
-                gm = any ? (v[u] > gm ? v[u] : gm) : v[u];
-                any = true;
+        for (int k = 0; k < LOADS; ++k) {
+            const int64_t i = base + (int64_t)k * nthreads;
+            if (i < nvec) {
+                a[k] = wv[i];
+                if (logw) b[k] = lv[i];
             }
         }
-        if (!any) break;
-        if (!have || gm > m) {
-            if (have) s *= (double)Math<T>::exp(m - gm);
-            m = gm;
-            have = true;
-        }
-        T part = T(0);
+        T v[LOADS * VEC];
+        int count = 0;
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int64_t i = base + (int64_t)u * stride;
-            if (i < n) part += Math<T>::exp(v[u] - m);
+        for (int k = 0; k < LOADS; ++k) {
+            const int64_t i = base + (int64_t)k * nthreads;
+            if (i < nvec) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) v[k * VEC + e] = scale * a[k].v[e] + (logw ? b[k].v[e] : T(0));
+                count = (k + 1) * VEC;
+            }
         }
-        s += (double)part;
+        lse_absorb<T, LOADS * VEC>(v, count, m, s, have);
+    }
+    // scalar head and tail
+    const int64_t done = head + nvec * VEC;
+    for (int64_t i = t0; i < head + (n - done); i += nthreads) {
+        const int64_t j = i < head ? i : done + (i - head);
+        T v1[1] = {scale * w[j] + (logw ? logw[j] : T(0))};
+        lse_absorb<T, 1>(v1, 1, m, s, have);
     }
     MS r = ms_block_reduce(MS{(double)m, have ? s : 0.0});
     if (threadIdx.x == 0) {
@@ -259,7 +291,7 @@ extern "C" int tfepb_lse(int32_t dtype, const void* w, const void* logw, int64_t
     TFEPB_CHECK_ARG(n > 0, "empty data");
     TFEPB_CHECK_ARG(w && partials && out2, "null buffer");
     if (int rc = require_sm100()) return rc;
-    int64_t blocks = (n + (int64_t)LSE_THREADS * 8 - 1) / ((int64_t)LSE_THREADS * 8);
+    int64_t blocks = (n + (int64_t)LSE_THREADS * 16 - 1) / ((int64_t)LSE_THREADS * 16);
     const int64_t cap = (int64_t)sm_count() * 8 < LSE_MAX_BLOCKS ? (int64_t)sm_count() * 8 : LSE_MAX_BLOCKS;
     if (blocks > cap) blocks = cap;
     cudaStream_t s = as_stream(stream);

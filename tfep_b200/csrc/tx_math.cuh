@@ -67,12 +67,19 @@ template <typename T>
 TFEPB_HD void sos_eval(const ParIn<T>& par, int n_poly, T x, T& y, T& ld) {
     T c1, c2, c3;
     sos_coefficients(par, n_poly, c1, c2, c3);
-    // same association as the reference loop (sos.py:216-226)
+    // y with the same association as the reference loop (sos.py:216-226)
     const T x2 = x * x;
     const T t2 = c2 * x, t3 = c3 * x2;
     const T poly = (c1 + t2) + t3;
-    const T dydx = (c1 + T(2) * t2) + T(3) * t3;
     y = poly * x + par[0];
+    // dy/dx = c1 + 2 c2 x + 3 c3 x^2 is evaluated in its sum-of-squares form sum_k (a_k0 + a_k1 x)^2:
+    // identical in exact arithmetic, but never negative (the expanded form can cancel to <= 0 in fp32
+    // when the polynomials nearly vanish, which turns the log-det into NaN).
+    T dydx = T(0);
+    for (int k = 0; k < n_poly; ++k) {
+        const T q = par[1 + 2 * k] + par[2 + 2 * k] * x;
+        dydx += q * q;
+    }
     ld = Math<T>::log(dydx);
 }
 
@@ -82,7 +89,12 @@ TFEPB_HD void sos_vjp(const ParIn<T>& par, int n_poly, T x, T gy, T& gx, const P
     T c1, c2, c3;
     sos_coefficients(par, n_poly, c1, c2, c3);
     const T x2 = x * x, x3 = x2 * x;
-    gx = ((c1 + T(2) * c2 * x) + T(3) * c3 * x2) * gy;
+    T dydx = T(0);
+    for (int k = 0; k < n_poly; ++k) {
+        const T q = par[1 + 2 * k] + par[2 + 2 * k] * x;
+        dydx += q * q;
+    }
+    gx = dydx * gy;
     gpar.set(0, gy);
     for (int k = 0; k < n_poly; ++k) {
         const T k0 = par[1 + 2 * k], k1 = par[2 + 2 * k];
