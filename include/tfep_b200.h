@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TFEPB_ABI_VERSION 1
+#define TFEPB_ABI_VERSION 2
 
 enum { TFEPB_F32 = 0, TFEPB_F64 = 1 };
 enum { TFEPB_ACT_NONE = 0, TFEPB_ACT_ELU = 1 };
@@ -167,23 +167,31 @@ int tfepb_moebius_backward(const tfepb_tx_io* io, int32_t dimension, double max_
                            const tfepb_tx_grads* g, tfepb_stream_t stream);
 
 /* ----------------------------------------------------------------------------------------------
- * Fused MAF layer forward on the tensor cores (tcgen05 / TMEM / bulk-copy engine), bf16 operands with
- * fp32 accumulation: y, logdet = T(x ; MADE(x)) for a MADE with two hidden layers and a circular
- * neural-spline transformer with 8 bins.  Replaces, in one launch per MAF layer,
- * AutoregressiveFlow.forward (nn/flows/autoregressive.py:144-177): the three masked linear layers
- * (nn/masked.py:266-277), the two ELUs (nn/conditioners/made.py:320) and NeuralSplineTransformer.forward
- * (nn/transformers/spline.py:184-241).  The caller packs the degree-sorted effective weights into
- * shared-memory-image blocks and lists the non-zero blocks in `ops` (tfep_b200/_fused.py documents the
- * format); masked blocks are simply absent from the schedule.  Biases travel inside the weight blocks
- * (two constant-one columns in every A operand), softmax / softplus rows are pre-scaled by log2(e).
+ * Fused MAF forward on the tensor cores (tcgen05 / TMEM / bulk-copy engine), bf16 operands with fp32
+ * accumulation: y, logdet = T(x ; MADE(x)) for MADEs with two hidden layers and a circular neural-spline
+ * transformer with 8 bins, for a CHAIN of n_layers >= 1 MAF layers in ONE launch.  Replaces
+ * SequentialFlow._pass (nn/flows/sequential.py:50-68) over AutoregressiveFlow.forward
+ * (nn/flows/autoregressive.py:144-177): per layer the three masked linear layers (nn/masked.py:266-277),
+ * the two ELUs (nn/conditioners/made.py:320) and NeuralSplineTransformer.forward
+ * (nn/transformers/spline.py:184-241); logdet is the sum over the layers.  The caller packs the
+ * degree-sorted effective weights into shared-memory-image blocks and lists the non-zero blocks in `ops`
+ * (tfep_b200/_fused.py documents the format); masked blocks are simply absent from the schedule.  Biases
+ * travel inside the weight blocks (two constant-one columns in every A operand); hidden-layer rows and
+ * softmax / softplus rows are pre-scaled by log2(e).
+ * The persistent grid walks (layer, tile-of-128-samples) work items layer-major; a tile of layer l+1 is
+ * released by a per-tile flag in `tile_flags` once layer l published it to `y` (which doubles as the
+ * inter-layer buffer; x == y is allowed).
  * -------------------------------------------------------------------------------------------- */
+#define TFEPB_FUSED_MAX_LAYERS 8
+#define TFEPB_FUSED_MAX_OPS 512          /* over all layers of one launch */
+
 typedef struct {
-    uint32_t w_off;                      /* block position in `weights` (bytes, multiple of 16) */
+    uint32_t w_off;                      /* block position in the layer's `weights` (bytes, multiple of 16) */
     uint16_t w_bytes16;                  /* block size in units of 16 bytes */
     uint16_t n, tmem_col, a_col;         /* MMA N, accumulator column, first A column (2 k-values per column) */
     uint8_t ksteps;                      /* K = 16 steps in the block */
-    uint8_t flags;                       /* 1 first block of accumulator, 2 commit, 4 accumulator 1,
-                                            16 wait for A operand, 32 wait for drained accumulator */
+    uint8_t flags;                       /* 1 first block of accumulator, 2 commit, bits 2-3 accumulator buffer
+                                            (0..2), 16 wait for A operand, 32 wait for drained accumulator */
     uint16_t reserved;
 } tfepb_fused_op;
 
@@ -193,17 +201,28 @@ typedef struct {
 } tfepb_fused_feature;
 
 typedef struct {
-    const void* x; void* y; void* logdet;          /* fp32 (batch, n_features), (batch, n_features), (batch,) */
-    int32_t batch, n_features;
-    int32_t k1, hidden_padded, n_chunks, n_ops;
-    const tfepb_fused_op* ops;                     /* HOST array of n_ops <= 112 entries (copied into the launch) */
-    const void* weights;                           /* device, packed bf16 blocks */
-    const tfepb_fused_feature* feats;              /* device: n_chunks * 8 */
+    const tfepb_fused_op* ops;           /* HOST array of n_ops entries (copied into the launch) */
+    int32_t n_ops, n_chunks;             /* n_chunks: output-layer chunks of 4 feature slots x 28 columns */
+    const void* weights;                 /* device, packed bf16 blocks */
+    const tfepb_fused_feature* feats;    /* device: n_chunks * 4 */
     float min_bin_size, min_slope, slope_offset;   /* slope_offset = log(exp(1 - min_slope) - 1) */
     int32_t reserved;
+} tfepb_fused_layer;
+
+typedef struct {
+    const void* x; void* y; void* logdet;          /* fp32 (batch, n_features), (batch, n_features), (batch,) */
+    int32_t batch, n_features;
+    int32_t k1, hidden_padded;                     /* padded widths shared by all layers of the chain */
+    int32_t n_layers, reserved;
+    const tfepb_fused_layer* layers;               /* HOST array of n_layers entries */
+    uint32_t* tile_flags;                          /* device, (n_layers - 1) * ceil(batch / 128) words owned by the
+                                                      caller and private to launches in flight; a word equal to
+                                                      `epoch` marks a published tile.  May be NULL if n_layers == 1 */
+    uint32_t epoch;                                /* any value the words do not hold yet (e.g. a call counter) */
+    int32_t debug_mode;                            /* development only, 0 */
     int32_t* error_flag;                           /* device int, set if an internal wait times out; may be NULL */
-    float* debug_params;                           /* NULL, or (batch, n_chunks * 128): conditioner outputs (+bias)
-                                                      in packed order, for parity tests of the GEMM chain */
+    float* debug_params;                           /* NULL, or (batch, n_chunks * 112): conditioner outputs (+bias)
+                                                      of layer 0 in packed order, for parity tests of the GEMM chain */
 } tfepb_fused_args;
 int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_stream_t stream);
 

@@ -21,11 +21,15 @@ def bf(t):
 
 
 def emulate(maf_oracle, x):
+    L2E = 1.4426950408889634
     (w1, b1), (w2, b2), (w3, b3) = [(w.double(), b.double()) for w, b in maf_oracle.layers]
-    h = torch.nn.functional.elu(bf(x) @ bf(w1).T + b1)
-    h = torch.nn.functional.elu(bf(h.float()) @ bf(w2).T + b2)
-    par = bf(h.float()) @ bf(w3).T + b3
-    return par
+    act = lambda t: torch.where(t > 0, t, L2E * (torch.exp2(t) - 1))
+    a1 = act(bf(x) @ bf((w1 * L2E).float()).T + b1 * L2E)
+    a2 = act(bf(a1.float()) @ bf(w2.float()).T + b2 * L2E)
+    n_feat = w3.shape[0] // 25
+    scale = torch.ones(w3.shape[0], dtype=torch.double)
+    scale[:24 * n_feat] = L2E
+    return (bf(a2.float()) @ bf((w3 * (scale / L2E)[:, None]).float()).T) / scale + b3
 
 
 with torch.no_grad():
@@ -33,7 +37,7 @@ with torch.no_grad():
     for li, maf in enumerate(seq):
         plan = _fused.FusedSplinePlan(maf)
         maf._fused = plan
-        dbg = torch.zeros(B, plan.n_chunks * 128, device=dev)
+        dbg = torch.zeros(B, plan.n_chunks * _fused.CHUNK_N, device=dev)
         y, ld = plan.forward(maf, cur, debug_params=dbg)
         torch.cuda.synchronize()
         err = int(plan._tables(torch.device(dev))['err'].item())

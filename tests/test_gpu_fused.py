@@ -25,15 +25,21 @@ def _bf(t):
 
 
 def _emulated_layer(oracle, x):
-    """One MAF layer in double with the kernel's bf16 operand roundings."""
+    """One MAF layer in double with the kernel's bf16 operand roundings and log2(e) pre-scalings
+    (tfep_b200/_fused.py: hidden accumulators hold log2(e) (W a + b), activations travel as log2(e) ELU)."""
+    L2E = 1.4426950408889634
     (w1, b1), (w2, b2), (w3, b3) = [(w.double(), b.double()) for w, b in oracle.layers]
-    h = torch.nn.functional.elu(_bf(x) @ _bf(w1).T + b1)
-    h = torch.nn.functional.elu(_bf(h.float()) @ _bf(w2).T + b2)
+
+    def act(t):                          # log2(e) ELU(t / log2(e))
+        return torch.where(t > 0, t, L2E * (torch.exp2(t) - 1))
+
+    a1 = act(_bf(x) @ _bf((w1 * L2E).float()).T + b1 * L2E)
+    a2 = act(_bf(a1.float()) @ _bf(w2.float()).T + b2 * L2E)
     # rows feeding softmax / softplus (parameters 0..23 of every feature) are stored pre-multiplied by log2(e)
     n_feat = w3.shape[0] // 25
     scale = torch.ones(w3.shape[0], dtype=torch.double)
-    scale[:24 * n_feat] = 1.4426950408889634
-    par = (_bf(h.float()) @ _bf((w3 * scale[:, None]).float()).T) / scale + b3
+    scale[:24 * n_feat] = L2E
+    par = (_bf(a2.float()) @ _bf((w3 * (scale / L2E)[:, None]).float()).T) / scale + b3
     old = torch.get_default_dtype()
     torch.set_default_dtype(torch.float64)
     try:
@@ -83,6 +89,27 @@ def test_full_batch_properties_and_agreement_with_fp32_path():
     assert float(d.median()) < 5e-3
     assert float((d < 5e-2).float().mean()) > 0.97
     assert float((ld - ld32).abs().median()) < 2e-2
+
+
+@pytest.mark.parametrize('batch', [1, 300, 128 * 148 + 77])
+def test_chain_launch_equals_layer_by_layer(batch):
+    """SequentialFlow runs the four bf16 layers as ONE launch (work items layer-major, per-tile flags):
+    bit-identical to one launch per layer, including the ragged last tile."""
+    seq, _ = cfg_flow_modules('cfg2', DEV)
+    x = cases.cfg_input('cfg2', batch).to(DEV)
+    for maf in seq:
+        maf.precision = 'bf16'
+    with torch.no_grad():
+        y, ld = seq(x)
+        y2, ld2 = seq(x)
+        cur, tot = x, None
+        for maf in seq:
+            cur, l = maf(cur)
+            tot = l if tot is None else tot + l
+    assert torch.equal(y, y2) and torch.equal(ld, ld2)
+    assert torch.equal(y, cur)
+    assert float((ld - tot).abs().max()) < 1e-5          # same per-layer values, summed in the same order
+    assert int(seq[0]._fused._tables(torch.device(DEV))['err'].item()) == 0
 
 
 def test_inference_only_and_eligibility():

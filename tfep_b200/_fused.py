@@ -11,9 +11,9 @@ the packed bf16 weight stream:
 * biases travel inside the GEMMs: packed unit 0 and 1 of every layer input are constant ones (columns D,
   D+1 of the x operand; two extra hidden units whose own weights reproduce the one) and the weight blocks
   hold bf16(b) and bf16(b - bf16(b)) in those columns;
-* each feature owns 32 consecutive output rows (25 spline parameters + 7 zero rows) so that the epilogue
-  reads them with one aligned tensor-memory load; rows feeding softmax / softplus are pre-multiplied by
-  log2(e);
+* each feature owns 28 consecutive output rows (25 spline parameters + 3 zero rows; 4 features = one MMA of
+  N = 112); hidden-layer rows and the rows feeding softmax / softplus are pre-multiplied by log2(e), the
+  hidden activations travel as log2(e) ELU(h) and the consuming layer's weights absorb the factor;
 * the schedule lists only blocks that intersect the staircase of the autoregressive mask
   (``deg_out >= deg_in`` for hidden layers, ``>`` for the output layer; reference nn/masked.py:90-99):
   for a tile of output rows the reduction stops at the last input unit they may see.
@@ -33,13 +33,14 @@ TILE_M = 128
 STAGE_BYTES = 32768
 FEATS_PER_CHUNK = 4
 NPAR = 25
-PSTRIDE = 32
+PSTRIDE = 28
 CHUNK_N = FEATS_PER_CHUNK * PSTRIDE
-ACC1_COL = CHUNK_N
+ACC_BUFS = 3
+MAX_LAYERS, MAX_OPS = 8, 512
 KB_OUT = 128
 KB_HID = 80
 LOG2E = 1.4426950408889634
-OP_FIRST, OP_COMMIT, OP_ACC1, OP_WAIT_A, OP_WAIT_EMPTY = 1, 2, 4, 16, 32
+OP_FIRST, OP_COMMIT, OP_ACC_SHIFT, OP_WAIT_A, OP_WAIT_EMPTY = 1, 2, 2, 16, 32
 
 OP_DTYPE = np.dtype([('w_off', '<u4'), ('w_bytes16', '<u2'), ('n', '<u2'), ('tmem_col', '<u2'), ('a_col', '<u2'),
                      ('ksteps', 'u1'), ('flags', 'u1'), ('reserved', '<u2')])
@@ -128,6 +129,7 @@ class FusedSplinePlan:
         for i in range(24):                                # widths, heights, slopes: log2 domain; shift: not
             scale[i::PSTRIDE] = LOG2E
         self.w3_scale = scale
+        assert self.n_chunks * CHUNK_N == len(w3_rows)
 
         # ---- schedule ----
         ops, gather = [], []           # gather: per op, index tensor into the concatenated padded matrices
@@ -166,14 +168,14 @@ class FusedSplinePlan:
         for c in range(self.n_chunks):
             kmax = _ceil16(2 + int((deg_h2 < chunk_maxdeg[c]).sum()))
             blocks = list(range(0, kmax, KB_OUT))
-            acc = c & 1
+            acc = c % ACC_BUFS
             for bi, kb in enumerate(blocks):
-                fl = (OP_ACC1 if acc else 0)
+                fl = acc << OP_ACC_SHIFT
                 if bi == 0:
                     fl |= OP_FIRST | OP_WAIT_EMPTY | (OP_WAIT_A if c == 0 else 0)
                 if bi == len(blocks) - 1:
                     fl |= OP_COMMIT
-                add(CHUNK_N, ACC1_COL if acc else 0, kb, min(KB_OUT, kmax - kb), kb // 8, fl, off2, self.HP, c * CHUNK_N)
+                add(CHUNK_N, acc * CHUNK_N, kb, min(KB_OUT, kmax - kb), kb // 8, fl, off2, self.HP, c * CHUNK_N)
         self.ops_host = np.array(ops, dtype=OP_DTYPE)
         self.gather_host = torch.cat(gather)
         self.weight_bytes = w_off
@@ -210,20 +212,24 @@ class FusedSplinePlan:
                 hi = b.to(torch.bfloat16).float()
                 return hi, b - hi
 
+            # The accumulators of the hidden layers hold t = log2(e) (W a + b) and the epilogue stores
+            # a' = log2(e) ELU(t / log2(e)) (one ex2 + one fma per unit), so: layer 1 is scaled by log2(e);
+            # layer 2 sees a' and is scaled by log2(e) itself -> weights unchanged, bias scaled; the output rows
+            # see a' -> divide by log2(e), then the log2-domain rows are multiplied by it again.
             W1p = torch.zeros(HP, K1, device=dev)
-            W1p[2:2 + H, :D] = w1.index_select(0, tb['perm1'])
-            W1p[2:2 + H, D], W1p[2:2 + H, D + 1] = hi_lo(b1.index_select(0, tb['perm1']))
-            W1p[0, D] = W1p[1, D] = 1.0                   # hidden units 0, 1 = ELU(1 * 1) = 1
+            W1p[2:2 + H, :D] = w1.index_select(0, tb['perm1']) * LOG2E
+            W1p[2:2 + H, D], W1p[2:2 + H, D + 1] = hi_lo(b1.index_select(0, tb['perm1']) * LOG2E)
+            W1p[0, D] = W1p[1, D] = 1.0                   # hidden units 0, 1: t = 1 > 0 -> a' = 1 (constant ones)
             W2p = torch.zeros(HP, HP, device=dev)
             W2p[2:2 + H, 2:2 + H] = w2.index_select(0, tb['perm2']).index_select(1, tb['perm1'])
-            W2p[2:2 + H, 0], W2p[2:2 + H, 1] = hi_lo(b2.index_select(0, tb['perm2']))
+            W2p[2:2 + H, 0], W2p[2:2 + H, 1] = hi_lo(b2.index_select(0, tb['perm2']) * LOG2E)
             W2p[0, 0] = W2p[1, 0] = 1.0
             rows, scale = tb['w3_rows'], tb['w3_scale']
             safe = torch.where(rows < 0, torch.full_like(rows, w3.shape[0]), rows)
             w3e = torch.cat([w3, torch.zeros(1, H, device=dev)], dim=0)
             b3e = torch.cat([b3, torch.zeros(1, device=dev)])
             W3p = torch.zeros(len(rows), HP, device=dev)
-            W3p[:, 2:2 + H] = w3e.index_select(0, safe).index_select(1, tb['perm2']) * scale[:, None]
+            W3p[:, 2:2 + H] = w3e.index_select(0, safe).index_select(1, tb['perm2']) * (scale / LOG2E)[:, None]
             W3p[:, 0], W3p[:, 1] = hi_lo(b3e.index_select(0, safe) * scale)
             src = torch.cat([W1p.flatten(), W2p.flatten(), W3p.flatten()]).to(torch.bfloat16)
             packed = src.index_select(0, tb['gather']).contiguous()
@@ -232,20 +238,53 @@ class FusedSplinePlan:
 
     def forward(self, maf, x, debug_params=None):
         """y, log_det_J = fused layer on a contiguous fp32 CUDA tensor (no autograd)."""
-        _lib.require_cuda(x)
-        if x.dtype != torch.float32:
-            raise _lib.TfepB200Error('the fused bf16 path takes float32 inputs')
-        x = x.contiguous()
-        packed = self.pack(maf)
-        tb = self._tables(x.device)
-        y = torch.empty_like(x)
-        ld = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
-        args = _lib.FusedArgs(x=x.data_ptr(), y=y.data_ptr(), logdet=ld.data_ptr(), batch=x.shape[0], n_features=self.D,
-                              k1=self.K1, hidden_padded=self.HP, n_chunks=self.n_chunks, n_ops=len(self.ops_host),
-                              ops=self.ops_host.ctypes.data, weights=packed.data_ptr(),
-                              feats=tb['feats'].data_ptr(), min_bin_size=self.min_bin, min_slope=self.min_slope,
-                              slope_offset=self.slope_offset, reserved=int(os.environ.get('TFEPB_FUSED_DEBUG_MODE', '0')), error_flag=tb['err'].data_ptr(),
-                              debug_params=None if debug_params is None else debug_params.data_ptr())
-        with torch.cuda.device(x.device):
-            check(_lib.load().tfepb_maf_spline_forward_bf16(ctypes.byref(args), stream_ptr(x)))
-        return y, ld
+        return run_chain([(self, maf)], x, debug_params=debug_params)
+
+
+_EPOCH = [0]
+
+
+def run_chain(plans_mafs, x, debug_params=None):
+    """One launch for a chain of fused MAF layers: y, sum of log_det_J (reference sequential.py:50-68)."""
+    _lib.require_cuda(x)
+    if x.dtype != torch.float32:
+        raise _lib.TfepB200Error('the fused bf16 path takes float32 inputs')
+    n_layers = len(plans_mafs)
+    first = plans_mafs[0][0]
+    if n_layers > MAX_LAYERS or sum(len(pl.ops_host) for pl, _ in plans_mafs) > MAX_OPS:
+        raise _lib.TfepB200Error('chain too long for one fused launch')
+    if any((pl.D, pl.K1, pl.HP) != (first.D, first.K1, first.HP) for pl, _ in plans_mafs):
+        raise _lib.TfepB200Error('fused chain needs layers of identical widths')
+    x = x.contiguous()
+    B = x.shape[0]
+    y = torch.empty_like(x)
+    ld = torch.empty(B, dtype=torch.float32, device=x.device)
+    layers = (_lib.FusedLayer * n_layers)()
+    keep = []
+    for i, (pl, maf) in enumerate(plans_mafs):
+        packed = pl.pack(maf)
+        tb = pl._tables(x.device)
+        keep.append(packed)
+        layers[i] = _lib.FusedLayer(ops=pl.ops_host.ctypes.data, n_ops=len(pl.ops_host), n_chunks=pl.n_chunks,
+                                    weights=packed.data_ptr(), feats=tb['feats'].data_ptr(), min_bin_size=pl.min_bin,
+                                    min_slope=pl.min_slope, slope_offset=pl.slope_offset, reserved=0)
+    tb = first._tables(x.device)
+    flags = None
+    if n_layers > 1:
+        # per-tile publication flags; a fresh epoch per launch instead of a memset (launches using the same
+        # workspace are serialised on the stream)
+        need = (n_layers - 1) * ((B + TILE_M - 1) // TILE_M)
+        key = ('flags', torch.cuda.current_stream(x.device).cuda_stream)
+        flags = tb.get(key)
+        if flags is None or flags.numel() < need:
+            flags = tb[key] = torch.zeros(max(need, 4096), dtype=torch.int32, device=x.device)
+    _EPOCH[0] = (_EPOCH[0] % 0x7fffffff) + 1
+    args = _lib.FusedArgs(x=x.data_ptr(), y=y.data_ptr(), logdet=ld.data_ptr(), batch=B, n_features=first.D,
+                          k1=first.K1, hidden_padded=first.HP, n_layers=n_layers, reserved=0, layers=layers,
+                          tile_flags=None if flags is None else flags.data_ptr(), epoch=_EPOCH[0],
+                          debug_mode=int(os.environ.get('TFEPB_FUSED_DEBUG_MODE', '0')),
+                          error_flag=tb['err'].data_ptr(),
+                          debug_params=None if debug_params is None else debug_params.data_ptr())
+    with torch.cuda.device(x.device):
+        check(_lib.load().tfepb_maf_spline_forward_bf16(ctypes.byref(args), stream_ptr(x)))
+    return y, ld

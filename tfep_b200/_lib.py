@@ -15,7 +15,7 @@ from . import _build
 F32, F64 = 0, 1
 ACT_NONE, ACT_ELU = 0, 1
 GEMM_TILE_N = 64
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class TfepB200Error(RuntimeError):
@@ -64,11 +64,15 @@ class TxGrads(Structure):
                 ('grad_x', c_void_p), ('ldgx', c_int64), ('grad_par', c_void_p)]
 
 
+class FusedLayer(Structure):
+    _fields_ = [('ops', c_void_p), ('n_ops', c_int32), ('n_chunks', c_int32), ('weights', c_void_p), ('feats', c_void_p),
+                ('min_bin_size', c_float), ('min_slope', c_float), ('slope_offset', c_float), ('reserved', c_int32)]
+
+
 class FusedArgs(Structure):
     _fields_ = [('x', c_void_p), ('y', c_void_p), ('logdet', c_void_p), ('batch', c_int32), ('n_features', c_int32),
-                ('k1', c_int32), ('hidden_padded', c_int32), ('n_chunks', c_int32), ('n_ops', c_int32),
-                ('ops', c_void_p), ('weights', c_void_p), ('feats', c_void_p),
-                ('min_bin_size', c_float), ('min_slope', c_float), ('slope_offset', c_float), ('reserved', c_int32),
+                ('k1', c_int32), ('hidden_padded', c_int32), ('n_layers', c_int32), ('reserved', c_int32),
+                ('layers', POINTER(FusedLayer)), ('tile_flags', c_void_p), ('epoch', c_uint32), ('debug_mode', c_int32),
                 ('error_flag', c_void_p), ('debug_params', c_void_p)]
 
 

@@ -1,17 +1,25 @@
-// Fused MAF layer forward for sm_100a: MADE conditioner on tcgen05 tensor cores + neural-spline transformer
-// and per-sample log|det J| in the GEMM epilogue.
+// Fused MAF forward for sm_100a: MADE conditioner on tcgen05 tensor cores + neural-spline transformer and
+// per-sample log|det J| in the GEMM epilogue, for a chain of MAF layers in one persistent launch.
 //
-//   y, logdet = T_spline(x ; MADE(x))            (reference: nn/flows/autoregressive.py:144-177,
-//                                                  nn/conditioners/made.py:294-329, nn/transformers/spline.py)
+//   y, logdet = T_spline(x ; MADE(x))  per layer    (reference: nn/flows/autoregressive.py:144-177,
+//                                                     nn/conditioners/made.py:294-329, nn/transformers/spline.py,
+//                                                     chained as nn/flows/sequential.py:50-68)
 //
-// One persistent CTA per SM walks over tiles of 128 samples.  For one tile:
+// One persistent CTA per SM walks over WORK ITEMS (layer, tile of 128 samples), layer-major: item j belongs
+// to CTA j % grid.  With L layers there are L x n_tiles items, so the last wave of the grid is nearly full
+// (2048 items on 148 SMs instead of 512 per launch), and the whole chain is one launch.  A tile of layer
+// l + 1 is read back from y (L2-resident) once the CTA that produced it published a per-tile flag; items
+// are taken in increasing order by co-resident CTAs, so the wait always ends.
+//
+// For one item:
 //   x tile (fp32)  --bulk copy-->  smem  --bf16, tcgen05.st-->  A0 in TENSOR MEMORY
 //   GEMM1  D1 = A0 W1^T   (tcgen05.mma, A from TMEM, B from smem, D in TMEM)  -> epilogue: ELU, bf16 -> A1 (TMEM)
 //   GEMM2  D2 = A1 W2^T                                                         -> epilogue: ELU, bf16 -> A2 (TMEM)
-//   GEMM3  chunk c: 4 features x 32 columns (25 spline parameters each), double-buffered accumulators;
+//   GEMM3  chunk c: 4 features x 28 columns (25 spline parameters each), THREE accumulator buffers in flight;
 //          epilogue: softmax / softplus / bin search / rational-quadratic map + log-det straight out of TMEM,
 //          so neither the hidden activations nor the (batch, 1650) parameter tensor ever exist in memory.
-//   y tile is written in place over the x tile in smem and leaves with one bulk store.
+//   y tile is written in place over the x tile in smem; a dedicated warp stores it with one bulk copy, adds
+//   the log-det of the layer to the running sum and publishes the tile flag.
 // Keeping the A operand in tensor memory matters: with both operands in shared memory the MMAs ran at half
 // rate (measured, profiles/r01_*), because A and B compete for the shared-memory operand port.
 //
@@ -22,13 +30,15 @@
 // through an mbarrier ring.
 //
 // Biases ride in the GEMMs: every A operand carries two constant-one columns and the weight blocks hold
-// bf16(b) and bf16(b - bf16(b)) in the matching columns, so the epilogues never load a bias.  The rows of
-// the output layer that feed softmax / softplus are pre-multiplied by log2(e), so the epilogue uses the
-// hardware ex2 / lg2 directly.
+// bf16(b) and bf16(b - bf16(b)) in the matching columns, so the epilogues never load a bias.  Hidden-layer
+// rows and the output rows that feed softmax / softplus are pre-multiplied by log2(e), so ELU, softmax and
+// softplus use the hardware ex2 / lg2 directly (the hidden activations travel as log2(e) ELU(h); the next
+// layer's weights absorb the factor).
 //
-// Warp roles: warp 0 = TMEM allocator + bulk-copy producer, warp 1 = MMA issuer, warps 2..17 = epilogue
-// (four warpgroups of 128 threads: thread <-> sample row, TMEM lane quadrant = warp % 4; the warpgroups
-// split the columns of a hidden layer / the feature slots of a chunk).
+// Warp roles: warp 0 = TMEM allocator + bulk-copy producer, warp 1 = MMA issuer, warp 2 = y store / log-det /
+// publish, warp 3 idle, warps 4..19 = epilogue (four warpgroups of 128 threads: thread <-> sample row,
+// TMEM lane quadrant = warp % 4; the warpgroups split the columns of a hidden layer / the feature slots of
+// a chunk).
 #include "common.cuh"
 
 #include <cuda_bf16.h>
@@ -40,23 +50,26 @@ namespace fused {
 constexpr int TILE_M = 128;
 constexpr int EPI_WGS = 4;                      // epilogue warpgroups
 constexpr int EPI_THREADS = EPI_WGS * 128;
-constexpr int THREADS = 64 + EPI_THREADS;
+constexpr int AUX_THREADS = 128;                // producer, MMA issuer, store warp, one idle warp
+constexpr int THREADS = AUX_THREADS + EPI_THREADS;
 constexpr int STAGES = 4;
 constexpr int STAGE_BYTES = 32768;              // one weight block (<= 256 rows, bf16)
 constexpr int FEATS_PER_CHUNK = 4;
 constexpr int NPAR = 25;                        // circular spline, K = 8: 8 widths, 8 heights, 8 slopes, shift
-constexpr int PSTRIDE = 32;                     // accumulator columns per feature slot (25 used)
-constexpr int CHUNK_N = FEATS_PER_CHUNK * PSTRIDE;   // 128
+constexpr int PSTRIDE = 28;                     // accumulator columns per feature slot (25 used)
+constexpr int CHUNK_N = FEATS_PER_CHUNK * PSTRIDE;   // 112
+constexpr int ACC_BUFS = 3;                     // chunk accumulators in flight (3 x 112 = 336 columns)
 constexpr int ACC_COLS = 336;                   // TMEM columns [0, 336): accumulators
 constexpr int A_COL = 336;                      // TMEM columns [336, 512): bf16 A operand (2 k-values per column)
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
 constexpr uint64_t WATCHDOG_CYCLES = 4000000000ull;
 
-constexpr int MAX_OPS = 112;
+constexpr int MAX_LAYERS = TFEPB_FUSED_MAX_LAYERS;
+constexpr int MAX_OPS = TFEPB_FUSED_MAX_OPS;
 struct Op {                 // one weight block = one ring stage (16 bytes; the table travels in the kernel parameters,
                             // so that the issuing warps read it through the constant bank into uniform registers)
-    uint32_t w_off;         // byte offset into the packed weights (multiple of 16)
+    uint32_t w_off;         // byte offset into the packed weights of the layer (multiple of 16)
     uint16_t w_bytes16;     // block size / 16
     uint16_t n;             // MMA N of this block (rows of the weight block)
     uint16_t tmem_col;      // destination accumulator column
@@ -68,7 +81,7 @@ struct Op {                 // one weight block = one ring stage (16 bytes; the 
 enum : uint32_t {
     OP_FIRST = 1u,          // first block of its accumulator: overwrite instead of accumulate
     OP_COMMIT = 2u,         // last block of its accumulator group: commit to acc_full[acc]
-    OP_ACC1 = 4u,           // accumulator id 1 (else 0)
+    OP_ACC_SHIFT = 2u,      // bits 2-3: accumulator buffer 0..2
     OP_WAIT_A = 16u,        // wait for the A operand (start of a GEMM phase)
     OP_WAIT_EMPTY = 32u,    // wait until the epilogue drained accumulator `acc` (GEMM3 chunks)
 };
@@ -78,19 +91,25 @@ struct __align__(16) FeatConst {   // per sorted feature
     float x0, L, invL, Rw, Rh, y0, pad;
 };
 
+struct LayerP {
+    const uint8_t* weights;     // packed bf16 weight blocks
+    const FeatConst* feats;     // n_chunks * FEATS_PER_CHUNK
+    int op_base, n_ops, n_chunks;
+    float min_bin, min_slope, slope_offset2;   // slope_offset2 = log2(e) * log(exp(1 - min_slope) - 1)
+};
+
 struct Params {
     const float* x; float* y; float* logdet;
     int batch, D;               // D = row length of x / y
     int K1;                     // D + 2 padded to a multiple of 16
     int HP;                     // hidden width (+2) padded to a multiple of 16
-    int n_chunks;               // GEMM3 chunks
-    int n_ops;
-    const uint8_t* weights;     // packed bf16 weight blocks
-    const FeatConst* feats;     // n_chunks * FEATS_PER_CHUNK
-    float min_bin, min_slope, slope_offset2;   // slope_offset2 = log2(e) * log(exp(1 - min_slope) - 1)
+    int n_layers, n_tiles, feat_stride;   // feat_stride: feature slots reserved per layer in shared memory
+    uint32_t* flags;            // (n_layers - 1) x n_tiles: == epoch once the tile of that layer is in y
+    uint32_t epoch;
     int* error;                 // device int: set on watchdog timeout
     float* debug_params;        // optional (batch, n_chunks * CHUNK_N): conditioner outputs as seen by the epilogue
     int debug_mode;             // development only (timing experiments)
+    LayerP layers[MAX_LAYERS];
     Op ops[MAX_OPS];
 };
 
@@ -142,6 +161,16 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -245,7 +274,8 @@ __device__ __forceinline__ float rcp(float v) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
 }
-__device__ __forceinline__ float fast_elu(float v) { return v > 0.f ? v : ex2(v * LOG2E) - 1.f; }
+// ELU in the log2 domain: t = log2(e) h  ->  log2(e) ELU(h) = t > 0 ? t : log2(e) (2^t - 1)
+__device__ __forceinline__ float elu_l2(float t) { return t > 0.f ? t : fmaf(ex2(t), LOG2E, -LOG2E); }
 // softplus of a log2-domain argument z = log2(e) * v: log(1 + e^v) = ln2 * lg2(1 + 2^z)
 __device__ __forceinline__ float softplus_l2(float z) { return z > 28.85f ? z * LN2 : LN2 * lg2(1.f + ex2(z)); }
 
@@ -254,8 +284,8 @@ __device__ __forceinline__ float softplus_l2(float z) { return z > 28.85f ? z * 
 // ------------------------------------------------------------------------------------------------
 struct Smem {
     uint64_t w_full[STAGES], w_empty[STAGES];
-    uint64_t x_full[2], x_empty[2], a_ready;
-    uint64_t acc_full[2], acc_empty[2];
+    uint64_t x_full[2], x_empty[2], y_ready[2], a_ready;
+    uint64_t acc_full[ACC_BUFS], acc_empty[ACC_BUFS];
     uint32_t tmem_base;
     uint32_t pad[3];
 };
@@ -329,7 +359,7 @@ __device__ __forceinline__ void trace(const Params& p, int role, int& slot, int 
 }
 
 template <bool DEBUG>
-__global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params p) {
+__global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid_constant__ Params p) {
     const int dmode = DEBUG ? p.debug_mode : 0;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* sW = smem_raw;                                                     // weight ring
@@ -337,20 +367,25 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
     const int x_tile_bytes = TILE_M * p.D * 4;
     const int x_tile_stride = (x_tile_bytes + 127) & ~127;
     FeatConst* sFeat = reinterpret_cast<FeatConst*>(reinterpret_cast<uint8_t*>(sX0) + 2 * x_tile_stride);
-    const int n_feat = p.n_chunks * FEATS_PER_CHUNK;
-    float* sLd = reinterpret_cast<float*>(sFeat + n_feat);          // [EPI_WGS - 1][128] log-det partials
-    Smem* sm = reinterpret_cast<Smem*>(sLd + (EPI_WGS - 1) * TILE_M);
+    float* sLd = reinterpret_cast<float*>(sFeat + p.n_layers * p.feat_stride);   // [2][EPI_WGS][128] log-det partials
+    Smem* sm = reinterpret_cast<Smem*>(sLd + 2 * EPI_WGS * TILE_M);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_tiles = (p.batch + TILE_M - 1) / TILE_M;
+    const int n_tiles = p.n_tiles;
+    const int n_items = p.n_layers * n_tiles;
 
     // ---- one-time setup ----
-    for (int i = tid; i < n_feat; i += THREADS) sFeat[i] = p.feats[i];
+    for (int l = 0; l < p.n_layers; ++l) {
+        const int nf = p.layers[l].n_chunks * FEATS_PER_CHUNK;
+        for (int i = tid; i < nf; i += THREADS) sFeat[l * p.feat_stride + i] = p.layers[l].feats[i];
+    }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&sm->w_full[s], 1); mbar_init(&sm->w_empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&sm->x_full[b], 1); mbar_init(&sm->x_empty[b], 1); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&sm->x_full[b], 1); mbar_init(&sm->x_empty[b], 1); mbar_init(&sm->y_ready[b], EPI_THREADS);
+        }
         mbar_init(&sm->a_ready, EPI_THREADS);
-        for (int b = 0; b < 2; ++b) { mbar_init(&sm->acc_full[b], 1); mbar_init(&sm->acc_empty[b], EPI_THREADS); }
+        for (int b = 0; b < ACC_BUFS; ++b) { mbar_init(&sm->acc_full[b], 1); mbar_init(&sm->acc_empty[b], EPI_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(&sm->tmem_base, 512);
@@ -364,30 +399,69 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
         // The whole warp walks the schedule (warp-uniform control flow); one elected lane issues the copies.
         uint32_t stage = 0, wphase = 0, tcount = 0;
         int ts = lane == 0 ? 0 : 1000000;
-        // x tile of local tile number t lives in buffer t & 1; it is requested one tile ahead, so its latency
+        // x tile of local item number t lives in buffer t & 1; it is requested one item ahead, so its latency
         // (and the drain of the y store that previously used the buffer) is off the critical path
-        auto request_x = [&](int tile, uint32_t t) {
+        auto flag_of = [&](int item) -> const uint32_t* {
+            const int layer = item / n_tiles, tile = item - layer * n_tiles;
+            return layer == 0 ? nullptr : p.flags + (size_t)(layer - 1) * n_tiles + tile;
+        };
+        auto request_x = [&](int item, uint32_t t) {
+            const int layer = item / n_tiles, tile = item - layer * n_tiles;
             const int rows = min(TILE_M, p.batch - tile * TILE_M);
             const uint32_t b = t & 1;
+            const float* src = layer == 0 ? p.x : p.y;
+            if (layer > 0) {
+                // the tile must have been published by the CTA that ran the previous layer on it
+                const uint32_t* flag = flag_of(item);
+                uint32_t polls = 0;
+                long long t0 = 0;
+                while (ld_acquire_gpu(flag) != p.epoch) {
+                    if ((++polls & 0xffu) != 0) continue;
+                    if (t0 == 0) t0 = clock64();
+                    if ((uint64_t)(clock64() - t0) > WATCHDOG_CYCLES) {
+                        if (p.error) atomicExch(p.error, 9);
+                        __threadfence_system();
+                        __trap();
+                    }
+                }
+                fence_proxy_async();        // the copy below reads through the async proxy
+            }
             mbar_wait(&sm->x_empty[b], ((t >> 1) & 1) ^ 1, p.error, 1);
             if (elect_one()) {
                 float* dst = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sX0) + b * x_tile_stride);
                 if (rows == TILE_M) {
                     mbar_expect_tx(&sm->x_full[b], (uint32_t)x_tile_bytes);
-                    bulk_g2s(dst, p.x + (size_t)tile * TILE_M * p.D, (uint32_t)x_tile_bytes, &sm->x_full[b]);
+                    bulk_g2s(dst, src + (size_t)tile * TILE_M * p.D, (uint32_t)x_tile_bytes, &sm->x_full[b]);
                 } else {
                     mbar_arrive(&sm->x_full[b]);    // ragged last tile: the epilogue warps copy it themselves
                 }
             }
             __syncwarp();
         };
-        if ((int)blockIdx.x < n_tiles) request_x(blockIdx.x, 0);
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+        // When every layer has at least two rounds of tiles, the tile an item needs was published a full round
+        // ago: its x tile is requested early, during the previous item.  Otherwise the producer of the needed tile
+        // may be this very CTA (or a neighbour) still working on it: the request is deferred into the item's own
+        // schedule and polled without blocking while the first weight blocks stream in.
+        const bool far = n_tiles >= 2 * (int)gridDim.x;
+        bool need_x = true;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
+            const LayerP& L = p.layers[item / n_tiles];
+            const int n_ops = L.n_ops, op_base = L.op_base;
+            const uint8_t* weights = L.weights;
             trace<DEBUG>(p, 0, ts, 1001);
-            const int prefetch_at = p.n_ops > 8 ? 8 : p.n_ops - 1;   // after the first weight blocks of this tile are in flight
-            for (int i = 0; i < p.n_ops; ++i) {
-                const uint32_t bytes = (uint32_t)p.ops[i].w_bytes16 * 16u;
-                const uint32_t w_off = p.ops[i].w_off;
+            const int prefetch_at = n_ops > 8 ? 8 : n_ops - 1;   // after the first weight blocks of this item are in flight
+            const int must_at = n_ops > STAGES - 1 ? STAGES - 1 : n_ops - 1;   // the ring is full: the MMAs need x to go on
+            for (int i = 0; i < n_ops; ++i) {
+                if (need_x) {
+                    const uint32_t* flag = flag_of(item);
+                    if (i == must_at || flag == nullptr || ld_acquire_gpu(flag) == p.epoch) {
+                        request_x(item, tcount);
+                        need_x = false;
+                    }
+                }
+                const Op& op = p.ops[op_base + i];
+                const uint32_t bytes = (uint32_t)op.w_bytes16 * 16u;
+                const uint32_t w_off = op.w_off;
                 mbar_wait(&sm->w_empty[stage], wphase ^ 1, p.error, 2);
                 trace<DEBUG>(p, 0, ts, i);
                 if (elect_one()) {
@@ -395,31 +469,35 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
                         mbar_arrive(&sm->w_full[stage]);
                     } else {
                         mbar_expect_tx(&sm->w_full[stage], bytes);
-                        bulk_g2s(sW + (size_t)stage * STAGE_BYTES, p.weights + w_off, bytes, &sm->w_full[stage]);
+                        bulk_g2s(sW + (size_t)stage * STAGE_BYTES, weights + w_off, bytes, &sm->w_full[stage]);
                     }
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; wphase ^= 1; }
-                if (i == prefetch_at && tile + (int)gridDim.x < n_tiles) request_x(tile + gridDim.x, tcount + 1);
+                if (far && i == prefetch_at && item + (int)gridDim.x < n_items) request_x(item + gridDim.x, tcount + 1);
             }
+            need_x = !far;
         }
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
         // Warp-uniform walk over the schedule; one elected lane issues the tcgen05.mma / commit instructions.
-        uint32_t stage = 0, wphase = 0, a_cnt = 0, empty_cnt0 = 0, empty_cnt1 = 0;
+        uint32_t stage = 0, wphase = 0, a_cnt = 0, empty_bits = 0;   // empty_bits: next phase parity per accumulator
         int ts = lane == 0 ? 0 : 1000000;
         const uint32_t w_base16 = smem_u32(sW) >> 4;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            for (int i = 0; i < p.n_ops; ++i) {
-                const uint32_t flags = p.ops[i].flags, n = p.ops[i].n;
-                const uint32_t acc = (flags & OP_ACC1) ? 1u : 0u;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const LayerP& L = p.layers[item / n_tiles];
+            const int n_ops = L.n_ops, op_base = L.op_base;
+            for (int i = 0; i < n_ops; ++i) {
+                const Op& op = p.ops[op_base + i];
+                const uint32_t flags = op.flags, n = op.n;
+                const uint32_t acc = (flags >> OP_ACC_SHIFT) & 3u;
                 if (flags & OP_WAIT_A) {
                     mbar_wait(&sm->a_ready, a_cnt & 1, p.error, 3);
                     ++a_cnt;
                 }
                 if (flags & OP_WAIT_EMPTY) {
-                    if (acc) { mbar_wait(&sm->acc_empty[1], (empty_cnt1 & 1) ^ 1, p.error, 4); ++empty_cnt1; }
-                    else { mbar_wait(&sm->acc_empty[0], (empty_cnt0 & 1) ^ 1, p.error, 4); ++empty_cnt0; }
+                    mbar_wait(&sm->acc_empty[acc], ((empty_bits >> acc) & 1u) ^ 1u, p.error, 4);
+                    empty_bits ^= 1u << acc;
                 }
                 trace<DEBUG>(p, 1, ts, 2000 + i);
                 mbar_wait(&sm->w_full[stage], wphase, p.error, 5);
@@ -428,9 +506,9 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
                 // B descriptor: high word constant (SBO = 128 B, version 1); low word = address >> 4 | LBO >> 4 << 16,
                 // advanced per k-step by two 8-k slabs of n rows x 16 B.  A: 8 TMEM columns per k-step.
                 const uint32_t b_lo = w_base16 + stage * (STAGE_BYTES >> 4) + (n << 16);
-                const uint32_t a_tmem = tmem + A_COL + p.ops[i].a_col;
-                const uint32_t ksteps = (dmode & 8) ? 1u : (uint32_t)p.ops[i].ksteps;
-                const uint32_t d_tmem = tmem + p.ops[i].tmem_col;
+                const uint32_t a_tmem = tmem + A_COL + op.a_col;
+                const uint32_t ksteps = (dmode & 8) ? 1u : (uint32_t)op.ksteps;
+                const uint32_t d_tmem = tmem + op.tmem_col;
                 const uint32_t idesc = make_idesc(n);
                 if (elect_one()) {
                     uint32_t accumulate = (flags & OP_FIRST) ? 0u : 1u;
@@ -446,16 +524,67 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
                 if (++stage == STAGES) { stage = 0; wphase ^= 1; }
             }
         }
-    } else {
+    } else if (warp == 2) {
+        // =========================== y store, log-det, publish ===========================
+        uint32_t tcount = 0;
+        int ts = lane == 0 ? 0 : 1000000;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
+            const int layer = item / n_tiles, tile = item - layer * n_tiles;
+            const int rows = min(TILE_M, p.batch - tile * TILE_M);
+            const uint32_t xb = tcount & 1;
+            const float* sY = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(sX0) + xb * x_tile_stride);
+            mbar_wait(&sm->y_ready[xb], (tcount >> 1) & 1, p.error, 10);
+            trace<DEBUG>(p, 3, ts, 4000);
+            float* dst = p.y + (size_t)tile * TILE_M * p.D;
+            if (rows == TILE_M) {
+                if (elect_one()) bulk_s2g(dst, sY, (uint32_t)x_tile_bytes);
+                __syncwarp();
+            }
+            // log-det of this layer: fixed summation order over the warpgroups, added to the running sum
+            const float* ldp = sLd + xb * (EPI_WGS * TILE_M);
+#pragma unroll
+            for (int r = 0; r < TILE_M / 32; ++r) {
+                const int row = r * 32 + lane;
+                if (row < rows) {
+                    float v = ldp[row];
+#pragma unroll
+                    for (int g = 1; g < EPI_WGS; ++g) v += ldp[g * TILE_M + row];
+                    float* out = p.logdet + (size_t)tile * TILE_M + row;
+                    if (layer > 0) v += __ldcg(out);
+                    *out = v;
+                }
+            }
+            if (rows < TILE_M) {
+                for (int i = lane; i < rows * p.D; i += 32) dst[i] = sY[i];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm->x_empty[xb]);
+            } else {
+                if (lane == 0) {                 // the lane that issued the bulk store owns its group
+                    bulk_wait_read();
+                    mbar_arrive(&sm->x_empty[xb]);
+                    if (layer + 1 < p.n_layers) bulk_wait_all();
+                }
+            }
+            __syncwarp();
+            if (layer + 1 < p.n_layers && lane == 0) {
+                fence_proxy_async();
+                __threadfence();
+                st_release_gpu(p.flags + (size_t)layer * n_tiles + tile, p.epoch);
+            }
+            trace<DEBUG>(p, 3, ts, 4001);
+        }
+    } else if (warp >= AUX_THREADS / 32) {
         // =========================== epilogue warps ===========================
-        const int et = tid - 64;                  // 0..511
+        const int et = tid - AUX_THREADS;         // 0..511
         const int wg = et >> 7;                   // warpgroup 0..3
         const int row = (warp & 3) * 32 + lane;   // sample row of the tile = TMEM lane
         const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        uint32_t full_cnt[2] = {0, 0}, tcount = 0;
+        uint32_t full_bits = 0, tcount = 0;       // full_bits: phase parity to wait for, per accumulator
         int ts = (et == 0) ? 0 : 1000000;
 
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
+            const int layer = item / n_tiles, tile = item - layer * n_tiles;
+            const LayerP& L = p.layers[layer];
             const int rows = min(TILE_M, p.batch - tile * TILE_M);
             // ---- x tile -> A0 in tensor memory (bf16 pairs; columns D, D+1 are the constant ones) ----
             const uint32_t xb = tcount & 1;
@@ -464,8 +593,8 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
             mbar_wait(&sm->x_full[xb], (tcount >> 1) & 1, p.error, 6);
             trace<DEBUG>(p, 2, ts, 3001);
             if (rows < TILE_M) {
-                const float* src = p.x + (size_t)tile * TILE_M * p.D;
-                for (int i = et; i < TILE_M * p.D; i += EPI_THREADS) sX[i] = i < rows * p.D ? src[i] : 0.f;
+                const float* src = (layer == 0 ? p.x : p.y) + (size_t)tile * TILE_M * p.D;
+                for (int i = et; i < TILE_M * p.D; i += EPI_THREADS) sX[i] = i < rows * p.D ? __ldcg(src + i) : 0.f;
                 asm volatile("bar.sync 1, 512;" ::: "memory");
             }
             for (int c0 = wg * 8; c0 < p.K1 / 2; c0 += EPI_WGS * 8) {      // 8 TMEM columns = 16 inputs per step
@@ -484,11 +613,11 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
             mbar_arrive(&sm->a_ready);
             trace<DEBUG>(p, 2, ts, 3002);
             // ---- two hidden layers: ELU, bf16 -> A operand of the next GEMM (tensor memory) ----
-            for (int layer = 0; layer < 2; ++layer) {
-                mbar_wait(&sm->acc_full[0], full_cnt[0] & 1, p.error, 7);
-                ++full_cnt[0];
+            for (int hl = 0; hl < 2; ++hl) {
+                mbar_wait(&sm->acc_full[0], full_bits & 1u, p.error, 7);
+                full_bits ^= 1u;
                 tc_fence_after();
-                trace<DEBUG>(p, 2, ts, 3010 + layer);
+                trace<DEBUG>(p, 2, ts, 3010 + hl);
                 // 16 accumulator columns per step; the load of the next step is in flight while this one is processed
                 uint32_t r[16], rn[16];
                 int c0 = wg * 16;
@@ -500,7 +629,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
                     uint32_t q[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
-                        q[i] = pack_bf16(fast_elu(__uint_as_float(r[2 * i])), fast_elu(__uint_as_float(r[2 * i + 1])));
+                        q[i] = pack_bf16(elu_l2(__uint_as_float(r[2 * i])), elu_l2(__uint_as_float(r[2 * i + 1])));
                     tmem_st8(lane_addr + A_COL + c0 / 2, q);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) r[i] = rn[i];
@@ -508,74 +637,59 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&sm->a_ready);
-                trace<DEBUG>(p, 2, ts, 3020 + layer);
+                trace<DEBUG>(p, 2, ts, 3020 + hl);
             }
             // ---- output layer chunks: spline transformer straight out of TMEM ----
             float ld = 0.f;
-            for (int c = 0; c < p.n_chunks; ++c) {
-                const int b = c & 1;
-                mbar_wait(&sm->acc_full[b], full_cnt[b] & 1, p.error, 8);
-                ++full_cnt[b];
+            const FeatConst* feat = sFeat + layer * p.feat_stride + wg;    // one feature slot per warpgroup
+            const float min_bin = L.min_bin, min_slope = L.min_slope, slope_offset2 = L.slope_offset2;
+            const int n_chunks = L.n_chunks;
+            uint32_t b = 0;
+            for (int c = 0; c < n_chunks; ++c) {
+                mbar_wait(&sm->acc_full[b], (full_bits >> b) & 1u, p.error, 8);
+                full_bits ^= 1u << b;
                 tc_fence_after();
                 trace<DEBUG>(p, 2, ts, 3100 + c);
                 {
-                    const int slot = wg;                                   // one feature slot per warpgroup
                     uint32_t r[32];
                     if (dmode & 4) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) r[i] = 0x3c000000u + i * 1234567u + row;
                     } else {
-                        const uint32_t a0 = lane_addr + b * CHUNK_N + slot * PSTRIDE;
+                        const uint32_t a0 = lane_addr + b * CHUNK_N + wg * PSTRIDE;
                         tmem_ld16(a0, r);                  // 25 parameters: 16 + 8 + 1 columns
                         tmem_ld8(a0 + 16, r + 16);
                         tmem_ld1(a0 + 24, r + 24);
                         tmem_wait8(r); tmem_wait8(r + 8); tmem_wait8(r + 16); tmem_wait1(r + 24);
                     }
-                    const FeatConst fc = sFeat[c * FEATS_PER_CHUNK + slot];
+                    const FeatConst fc = feat[c * FEATS_PER_CHUNK];
                     if (dmode & 2) {
                         float acc = 0.f;
 #pragma unroll
                         for (int i = 0; i < NPAR; ++i) acc += __uint_as_float(r[i]);
                         ld += acc;
                     } else if (fc.col >= 0) {
-                        if (DEBUG && p.debug_params != nullptr && !(dmode & 16) && row < rows) {
-                            float* dbg = p.debug_params + ((size_t)tile * TILE_M + row) * p.n_chunks * CHUNK_N + c * CHUNK_N +
-                                         slot * PSTRIDE;
+                        if (DEBUG && p.debug_params != nullptr && !(dmode & 16) && row < rows && layer == 0) {
+                            float* dbg = p.debug_params + ((size_t)tile * TILE_M + row) * n_chunks * CHUNK_N + c * CHUNK_N +
+                                         wg * PSTRIDE;
 #pragma unroll
                             for (int i = 0; i < NPAR; ++i) dbg[i] = __uint_as_float(r[i]);
                         }
                         float yv;
-                        ld += spline8_circular(r, xrow[fc.col], fc, p.min_bin, p.min_slope, p.slope_offset2, yv);
+                        ld += spline8_circular(r, xrow[fc.col], fc, min_bin, min_slope, slope_offset2, yv);
                         xrow[fc.col] = yv;
                     }
                 }
                 tc_fence_before();
                 mbar_arrive(&sm->acc_empty[b]);
                 trace<DEBUG>(p, 2, ts, 3200 + c);
+                b = (b == ACC_BUFS - 1) ? 0u : b + 1u;
             }
-            // ---- log-det: combine the warpgroups, store; y tile leaves with one bulk store ----
-            if (wg > 0) sLd[(wg - 1) * TILE_M + row] = ld;
+            // ---- hand the y tile and the log-det partials to the store warp ----
+            sLd[xb * (EPI_WGS * TILE_M) + wg * TILE_M + row] = ld;
             fence_async_smem();                      // y tile writes -> visible to the bulk-copy engine
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            if (wg == 0) {
-                if (row < rows) {
-#pragma unroll
-                    for (int g = 0; g < EPI_WGS - 1; ++g) ld += sLd[g * TILE_M + row];
-                    p.logdet[(size_t)tile * TILE_M + row] = ld;
-                }
-                if (rows == TILE_M && et == 0) {
-                    bulk_s2g(p.y + (size_t)tile * TILE_M * p.D, sX, (uint32_t)x_tile_bytes);
-                    bulk_wait_read();               // the other buffer is already being refilled: this wait is off the critical path
-                    mbar_arrive(&sm->x_empty[xb]);
-                    trace<DEBUG>(p, 2, ts, 3300);
-                }
-            }
-            if (rows < TILE_M) {
-                float* dst = p.y + (size_t)tile * TILE_M * p.D;
-                for (int i = et; i < rows * p.D; i += EPI_THREADS) dst[i] = sX[i];
-                asm volatile("bar.sync 1, 512;" ::: "memory");
-                if (et == 0) mbar_arrive(&sm->x_empty[xb]);
-            }
+            mbar_arrive(&sm->y_ready[xb]);
+            trace<DEBUG>(p, 2, ts, 3300);
         }
     }
 
@@ -588,8 +702,8 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const Params
 size_t smem_bytes(const Params& p) {
     size_t s = (size_t)STAGES * STAGE_BYTES;
     s += 2 * (((size_t)TILE_M * p.D * 4 + 127) & ~(size_t)127);
-    s += (size_t)p.n_chunks * FEATS_PER_CHUNK * sizeof(FeatConst);
-    s += (EPI_WGS - 1) * TILE_M * 4 + sizeof(Smem);
+    s += (size_t)p.n_layers * p.feat_stride * sizeof(FeatConst);
+    s += 2 * EPI_WGS * TILE_M * 4 + sizeof(Smem);
     return s + 256;
 }
 
@@ -600,32 +714,47 @@ using namespace tfepb;
 
 static_assert(sizeof(fused::Op) == sizeof(tfepb_fused_op), "schedule entry layout mismatch");
 static_assert(sizeof(fused::FeatConst) == sizeof(tfepb_fused_feature), "feature table layout mismatch");
+static_assert(sizeof(fused::Params) < 32000, "kernel parameter space");
 
 extern "C" int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_stream_t stream) {
     TFEPB_CHECK_ARG(a != nullptr, "null argument struct");
-    TFEPB_CHECK_ARG(a->x && a->y && a->logdet && a->ops && a->weights && a->feats, "null buffer");
+    TFEPB_CHECK_ARG(a->x && a->y && a->logdet && a->layers, "null buffer");
     TFEPB_CHECK_ARG(a->batch >= 0 && a->n_features > 0, "bad sizes");
+    TFEPB_CHECK_ARG(a->n_layers >= 1 && a->n_layers <= fused::MAX_LAYERS, "n_layers must be in [1, %d]", fused::MAX_LAYERS);
+    TFEPB_CHECK_ARG(a->n_layers == 1 || a->tile_flags != nullptr, "a chain of layers needs the tile_flags workspace");
     TFEPB_CHECK_ARG(a->k1 % 16 == 0 && a->k1 >= a->n_features + 2, "k1 must hold n_features + 2 bias columns, rounded up to 16");
     TFEPB_CHECK_ARG(a->hidden_padded % 16 == 0 && a->hidden_padded > 0 && a->hidden_padded <= fused::ACC_COLS,
                     "hidden width (padded) must be a multiple of 16 and at most 336 (tensor-memory plan)");
     TFEPB_CHECK_ARG(a->k1 <= 2 * (512 - fused::A_COL), "too many input features for the tensor-memory plan");
-    TFEPB_CHECK_ARG(a->n_chunks > 0 && a->n_ops > 0 && a->n_ops <= fused::MAX_OPS, "bad schedule length");
     TFEPB_CHECK_ARG((a->n_features * 4 * fused::TILE_M) % 16 == 0, "tile of x must be a multiple of 16 bytes");
-    TFEPB_CHECK_ARG(((uintptr_t)a->x % 16 == 0) && ((uintptr_t)a->y % 16 == 0) && ((uintptr_t)a->weights % 16 == 0),
-                    "x, y and the packed weights must be 16-byte aligned");
+    TFEPB_CHECK_ARG(((uintptr_t)a->x % 16 == 0) && ((uintptr_t)a->y % 16 == 0), "x and y must be 16-byte aligned");
     if (int rc = require_sm100()) return rc;
     if (a->batch == 0) return 0;
     fused::Params p{};
     p.x = (const float*)a->x; p.y = (float*)a->y; p.logdet = (float*)a->logdet;
     p.batch = a->batch; p.D = a->n_features; p.K1 = a->k1; p.HP = a->hidden_padded;
-    p.n_chunks = a->n_chunks; p.n_ops = a->n_ops;
-    memcpy(p.ops, a->ops, sizeof(fused::Op) * (size_t)a->n_ops);
-    p.weights = (const uint8_t*)a->weights;
-    p.feats = (const fused::FeatConst*)a->feats;
-    p.min_bin = a->min_bin_size; p.min_slope = a->min_slope; p.slope_offset2 = a->slope_offset * fused::LOG2E;
+    p.n_layers = a->n_layers;
+    p.n_tiles = (a->batch + fused::TILE_M - 1) / fused::TILE_M;
+    p.flags = a->tile_flags; p.epoch = a->epoch;
+    int op_base = 0, feat_stride = 0;
+    for (int l = 0; l < a->n_layers; ++l) {
+        const tfepb_fused_layer& s = a->layers[l];
+        TFEPB_CHECK_ARG(s.ops && s.weights && s.feats, "layer %d: null buffer", l);
+        TFEPB_CHECK_ARG(s.n_chunks > 0 && s.n_ops > 0 && op_base + s.n_ops <= fused::MAX_OPS, "layer %d: bad schedule length", l);
+        TFEPB_CHECK_ARG((uintptr_t)s.weights % 16 == 0, "layer %d: packed weights must be 16-byte aligned", l);
+        fused::LayerP& d = p.layers[l];
+        d.weights = (const uint8_t*)s.weights;
+        d.feats = (const fused::FeatConst*)s.feats;
+        d.op_base = op_base; d.n_ops = s.n_ops; d.n_chunks = s.n_chunks;
+        d.min_bin = s.min_bin_size; d.min_slope = s.min_slope; d.slope_offset2 = s.slope_offset * fused::LOG2E;
+        memcpy(p.ops + op_base, s.ops, sizeof(fused::Op) * (size_t)s.n_ops);
+        op_base += s.n_ops;
+        if (s.n_chunks * fused::FEATS_PER_CHUNK > feat_stride) feat_stride = s.n_chunks * fused::FEATS_PER_CHUNK;
+    }
+    p.feat_stride = feat_stride;
     p.error = a->error_flag;
     p.debug_params = a->debug_params;
-    p.debug_mode = a->reserved;
+    p.debug_mode = a->debug_mode;
     const size_t smem = fused::smem_bytes(p);
     TFEPB_CHECK_ARG(smem <= 227 * 1024, "shared memory plan of %zu bytes exceeds 227 KB", smem);
     const bool debug = p.debug_mode != 0 || p.debug_params != nullptr;
@@ -635,8 +764,8 @@ extern "C" int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_st
         TFEPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[debug] = smem;
     }
-    const int n_tiles = (a->batch + fused::TILE_M - 1) / fused::TILE_M;
-    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+    // one CTA per SM; never more CTAs than tiles, so that the items a CTA waits for belong to CTAs that run
+    const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
     kernel<<<grid, fused::THREADS, smem, as_stream(stream)>>>(p);
     return check_launch("maf_spline_fwd_kernel");
 }

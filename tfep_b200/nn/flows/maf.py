@@ -151,12 +151,15 @@ class MAF(AutoregressiveFlow):
     def _forward_fused(self, x):
         """Tensor-core path: the whole layer in one kernel launch (no autograd, no silent fallback)."""
         from ... import _fused
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError("tfep_b200: precision='bf16' is an inference path; use torch.no_grad() "
-                                      "or precision='fp32' for training")
+        self._check_fused_inference(x)
         if self._fused is None:
             self._fused = _fused.FusedSplinePlan(self)
         return self._fused.forward(self, x)
+
+    def _check_fused_inference(self, x):
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("tfep_b200: precision='bf16' is an inference path; use torch.no_grad() "
+                                      "or precision='fp32' for training")
 
     def inverse(self, y: torch.Tensor):
         """Returns ``(x, log_det_J)``: degree-ordered sweep (see the module docstring)."""

@@ -17,6 +17,8 @@ class SequentialFlow(torch.nn.Sequential):
         return self._pass(y, inverse=True)
 
     def _pass(self, x, inverse):
+        if not inverse and len(self) > 1 and self._fused_chain_ok(x):
+            return self._forward_fused_chain(x)
         cumulative_log_det_J = None
         for flow in (reversed(self) if inverse else self):
             x, log_det_J = flow.inverse(x) if inverse else flow(x)
@@ -24,3 +26,31 @@ class SequentialFlow(torch.nn.Sequential):
         if cumulative_log_det_J is None:
             cumulative_log_det_J = torch.zeros(x.size(0), dtype=x.dtype, device=x.device)
         return x, cumulative_log_det_J
+
+    # -- tensor-core fast path: the whole chain of precision='bf16' MAF layers in ONE kernel launch --------
+    def _fused_chain_ok(self, x):
+        from .maf import MAF
+        from ... import _fused
+        if not all(isinstance(f, MAF) and f.precision == 'bf16' for f in self):
+            return False
+        if len(self) > _fused.MAX_LAYERS or any(_fused.eligibility(f) is not None for f in self):
+            return False
+        return True
+
+    def _forward_fused_chain(self, x):
+        from ... import _fused
+        pairs = []
+        for f in self:
+            f._check_fused_inference(x)
+            if f._fused is None:
+                f._fused = _fused.FusedSplinePlan(f)
+            pairs.append((f._fused, f))
+        first = pairs[0][0]
+        if any((pl.D, pl.K1, pl.HP) != (first.D, first.K1, first.HP) for pl, _ in pairs) or \
+                sum(len(pl.ops_host) for pl, _ in pairs) > _fused.MAX_OPS:
+            y, ld = x, None
+            for pl, f in pairs:
+                y, l = pl.forward(f, y)
+                ld = l if ld is None else ld + l
+            return y, ld
+        return _fused.run_chain(pairs, x)
