@@ -186,13 +186,14 @@ int tfepb_moebius_backward(const tfepb_tx_io* io, int32_t dimension, double max_
 #define TFEPB_FUSED_MAX_OPS 512          /* over all layers of one launch */
 
 typedef struct {
-    uint32_t w_off;                      /* block position in the layer's `weights` (bytes, multiple of 16) */
-    uint16_t w_bytes16;                  /* block size in units of 16 bytes */
+    uint32_t w_off;                      /* block position in the layer's `weights` (bytes, multiple of 16);
+                                            the block holds n x (16 ksteps) bf16 = n * ksteps * 32 bytes */
+    uint32_t idesc;                      /* tcgen05 instruction descriptor: kind::f16, bf16 x bf16 -> fp32, M = 128, N = n */
     uint16_t n, tmem_col, a_col;         /* MMA N, accumulator column, first A column (2 k-values per column) */
     uint8_t ksteps;                      /* K = 16 steps in the block */
     uint8_t flags;                       /* 1 first block of accumulator, 2 commit, bits 2-3 accumulator buffer
-                                            (0..2), 16 wait for A operand, 32 wait for drained accumulator */
-    uint16_t reserved;
+                                            (0..2), 16 wait for A operand, 32 wait for drained accumulator,
+                                            64 issued by the second MMA warp, 128 hidden-layer block */
 } tfepb_fused_op;
 
 typedef struct {
@@ -213,7 +214,8 @@ typedef struct {
     const void* x; void* y; void* logdet;          /* fp32 (batch, n_features), (batch, n_features), (batch,) */
     int32_t batch, n_features;
     int32_t k1, hidden_padded;                     /* padded widths shared by all layers of the chain */
-    int32_t n_layers, reserved;
+    int32_t n_layers;
+    int32_t hidden_groups;                         /* accumulator groups (flag-2 commits) per hidden GEMM in `ops` */
     const tfepb_fused_layer* layers;               /* HOST array of n_layers entries */
     uint32_t* tile_flags;                          /* device, (n_layers - 1) * ceil(batch / 128) words owned by the
                                                       caller and private to launches in flight; a word equal to

@@ -26,7 +26,7 @@ NVCC_FLAGS = [
     '-Xcompiler', '-fPIC',
     '-Xptxas', '-v',
     '-I', INCLUDE,
-]
+] + os.environ.get('TFEPB_EXTRA_NVCC_FLAGS', '').split()
 
 
 def _nvcc():

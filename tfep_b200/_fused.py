@@ -40,10 +40,10 @@ MAX_LAYERS, MAX_OPS = 8, 512
 KB_OUT = 128
 KB_HID = 80
 LOG2E = 1.4426950408889634
-OP_FIRST, OP_COMMIT, OP_ACC_SHIFT, OP_WAIT_A, OP_WAIT_EMPTY = 1, 2, 2, 16, 32
+OP_FIRST, OP_COMMIT, OP_ACC_SHIFT, OP_WAIT_A, OP_WAIT_EMPTY, OP_OWNER1, OP_HIDDEN = 1, 2, 2, 16, 32, 64, 128
 
-OP_DTYPE = np.dtype([('w_off', '<u4'), ('w_bytes16', '<u2'), ('n', '<u2'), ('tmem_col', '<u2'), ('a_col', '<u2'),
-                     ('ksteps', 'u1'), ('flags', 'u1'), ('reserved', '<u2')])
+OP_DTYPE = np.dtype([('w_off', '<u4'), ('idesc', '<u4'), ('n', '<u2'), ('tmem_col', '<u2'), ('a_col', '<u2'),
+                     ('ksteps', 'u1'), ('flags', 'u1')])
 
 
 def _idesc(n):
@@ -145,12 +145,14 @@ class FusedSplinePlan:
             gather.append(idx)
             nbytes = n * kmax_block * 2
             assert nbytes <= STAGE_BYTES and nbytes % 16 == 0
-            ops.append((w_off, nbytes // 16, n, tmem_col, a_slab0 * 4, ksteps, flags, 0))
+            ops.append((w_off, _idesc(n), n, tmem_col, a_slab0 * 4, ksteps, flags))
             w_off += nbytes
 
+        # Accumulator groups alternate between the two MMA issuer warps (OP_OWNER1); every group ends with a
+        # commit (hidden layers: one per row chunk, counted by the epilogue through `hidden_groups`).
         # GEMM1: full K1 per row chunk (the first layer is tiny; no staircase)
         for i, (a, b) in enumerate(self.hidden_chunks):
-            fl = OP_FIRST | (OP_WAIT_A if i == 0 else 0) | (OP_COMMIT if i == len(self.hidden_chunks) - 1 else 0)
+            fl = OP_FIRST | OP_COMMIT | OP_HIDDEN | (OP_WAIT_A if i == 0 else 0) | (OP_OWNER1 if i & 1 else 0)
             add(b - a, a, 0, self.K1, 0, fl, 0, self.K1, a)
         # GEMM2: rows see layer-1 units of degree <= their own
         first = True
@@ -159,8 +161,8 @@ class FusedSplinePlan:
             kmax = _ceil16(2 + int((deg_h1 <= int(real.max())).sum())) if len(real) else 16
             blocks = list(range(0, kmax, KB_HID))
             for bi, kb in enumerate(blocks):
-                fl = (OP_FIRST if bi == 0 else 0) | (OP_WAIT_A if first else 0)
-                if i == len(self.hidden_chunks) - 1 and bi == len(blocks) - 1:
+                fl = OP_HIDDEN | (OP_FIRST if bi == 0 else 0) | (OP_WAIT_A if first else 0) | (OP_OWNER1 if i & 1 else 0)
+                if bi == len(blocks) - 1:
                     fl |= OP_COMMIT
                 first = False
                 add(b - a, a, kb, min(KB_HID, kmax - kb), kb // 8, fl, off1, self.HP, a)
@@ -170,7 +172,7 @@ class FusedSplinePlan:
             blocks = list(range(0, kmax, KB_OUT))
             acc = c % ACC_BUFS
             for bi, kb in enumerate(blocks):
-                fl = acc << OP_ACC_SHIFT
+                fl = (acc << OP_ACC_SHIFT) | (OP_OWNER1 if c & 1 else 0)
                 if bi == 0:
                     fl |= OP_FIRST | OP_WAIT_EMPTY | (OP_WAIT_A if c == 0 else 0)
                 if bi == len(blocks) - 1:
@@ -253,7 +255,7 @@ def run_chain(plans_mafs, x, debug_params=None):
     first = plans_mafs[0][0]
     if n_layers > MAX_LAYERS or sum(len(pl.ops_host) for pl, _ in plans_mafs) > MAX_OPS:
         raise _lib.TfepB200Error('chain too long for one fused launch')
-    if any((pl.D, pl.K1, pl.HP) != (first.D, first.K1, first.HP) for pl, _ in plans_mafs):
+    if any((pl.D, pl.K1, pl.HP, len(pl.hidden_chunks)) != (first.D, first.K1, first.HP, len(first.hidden_chunks)) for pl, _ in plans_mafs):
         raise _lib.TfepB200Error('fused chain needs layers of identical widths')
     x = x.contiguous()
     B = x.shape[0]
@@ -280,7 +282,7 @@ def run_chain(plans_mafs, x, debug_params=None):
             flags = tb[key] = torch.zeros(max(need, 4096), dtype=torch.int32, device=x.device)
     _EPOCH[0] = (_EPOCH[0] % 0x7fffffff) + 1
     args = _lib.FusedArgs(x=x.data_ptr(), y=y.data_ptr(), logdet=ld.data_ptr(), batch=B, n_features=first.D,
-                          k1=first.K1, hidden_padded=first.HP, n_layers=n_layers, reserved=0, layers=layers,
+                          k1=first.K1, hidden_padded=first.HP, n_layers=n_layers, hidden_groups=len(first.hidden_chunks), layers=layers,
                           tile_flags=None if flags is None else flags.data_ptr(), epoch=_EPOCH[0],
                           debug_mode=int(os.environ.get('TFEPB_FUSED_DEBUG_MODE', '0')),
                           error_flag=tb['err'].data_ptr(),

@@ -35,8 +35,8 @@
 // softplus use the hardware ex2 / lg2 directly (the hidden activations travel as log2(e) ELU(h); the next
 // layer's weights absorb the factor).
 //
-// Warp roles: warp 0 = TMEM allocator + bulk-copy producer, warp 1 = MMA issuer, warp 2 = y store / log-det /
-// publish, warp 3 idle, warps 4..19 = epilogue (four warpgroups of 128 threads: thread <-> sample row,
+// Warp roles: warp 0 = TMEM allocator + bulk-copy producer, warps 1 and 3 = MMA issuers, warp 2 = y store /
+// log-det / publish, warps 4..19 = epilogue (four warpgroups of 128 threads: thread <-> sample row,
 // TMEM lane quadrant = warp % 4; the warpgroups split the columns of a hidden layer / the feature slots of
 // a chunk).
 #include "common.cuh"
@@ -67,16 +67,15 @@ constexpr uint64_t WATCHDOG_CYCLES = 4000000000ull;
 
 constexpr int MAX_LAYERS = TFEPB_FUSED_MAX_LAYERS;
 constexpr int MAX_OPS = TFEPB_FUSED_MAX_OPS;
-struct Op {                 // one weight block = one ring stage (16 bytes; the table travels in the kernel parameters,
+struct __align__(16) Op {   // one weight block = one ring stage (16 bytes; the table travels in the kernel parameters,
                             // so that the issuing warps read it through the constant bank into uniform registers)
     uint32_t w_off;         // byte offset into the packed weights of the layer (multiple of 16)
-    uint16_t w_bytes16;     // block size / 16
-    uint16_t n;             // MMA N of this block (rows of the weight block)
+    uint32_t idesc;         // tcgen05 instruction descriptor (kind::f16, bf16 x bf16 -> fp32, M = 128, N = n)
+    uint16_t n;             // MMA N of this block (rows of the weight block); the block holds n * ksteps * 32 bytes
     uint16_t tmem_col;      // destination accumulator column
     uint16_t a_col;         // first A column (two k-values each) this block multiplies
     uint8_t ksteps;         // K = 16 steps in this block
     uint8_t flags;
-    uint16_t reserved;
 };
 enum : uint32_t {
     OP_FIRST = 1u,          // first block of its accumulator: overwrite instead of accumulate
@@ -84,6 +83,8 @@ enum : uint32_t {
     OP_ACC_SHIFT = 2u,      // bits 2-3: accumulator buffer 0..2
     OP_WAIT_A = 16u,        // wait for the A operand (start of a GEMM phase)
     OP_WAIT_EMPTY = 32u,    // wait until the epilogue drained accumulator `acc` (GEMM3 chunks)
+    OP_OWNER1 = 64u,        // issued by the second MMA warp (accumulator groups alternate between the two issuers)
+    OP_HIDDEN = 128u,       // hidden-layer block: its group commits to hid_full instead of acc_full[acc]
 };
 
 struct __align__(16) FeatConst {   // per sorted feature
@@ -104,6 +105,7 @@ struct Params {
     int K1;                     // D + 2 padded to a multiple of 16
     int HP;                     // hidden width (+2) padded to a multiple of 16
     int n_layers, n_tiles, feat_stride;   // feat_stride: feature slots reserved per layer in shared memory
+    int hidden_groups;          // accumulator groups (row chunks) per hidden GEMM = commits the epilogue waits for
     uint32_t* flags;            // (n_layers - 1) x n_tiles: == epoch once the tile of that layer is in y
     uint32_t epoch;
     int* error;                 // device int: set on watchdog timeout
@@ -137,8 +139,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug must end in a trap (error return), never in a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* error, int tag) {
-    if (mbar_try_wait(bar, parity)) return;
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int* error, int tag) {
     uint32_t polls = 0;
     long long t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
@@ -150,6 +151,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
             __trap();
         }
     }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* error, int tag) {
+    if (mbar_try_wait(bar, parity)) return;
+    mbar_wait_slow(bar, parity, error, tag);
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -285,7 +290,7 @@ __device__ __forceinline__ float softplus_l2(float z) { return z > 28.85f ? z * 
 struct Smem {
     uint64_t w_full[STAGES], w_empty[STAGES];
     uint64_t x_full[2], x_empty[2], y_ready[2], a_ready;
-    uint64_t acc_full[ACC_BUFS], acc_empty[ACC_BUFS];
+    uint64_t acc_full[ACC_BUFS], acc_empty[ACC_BUFS], hid_full;
     uint32_t tmem_base;
     uint32_t pad[3];
 };
@@ -349,6 +354,9 @@ __device__ __forceinline__ float spline8_circular(const uint32_t (&r)[32], float
 // development aid: CTA 0 stamps clock64() of key events into debug_params (as long long) when debug_mode & 16
 template <bool DEBUG>
 __device__ __forceinline__ void trace(const Params& p, int role, int& slot, int tag) {
+#ifndef TFEPB_TRACE
+    return;                 // compiled in only with -DTFEPB_TRACE (TFEPB_EXTRA_NVCC_FLAGS, scripts/dev_trace.py)
+#endif
     if (!DEBUG) return;
     if ((p.debug_mode & 16) && blockIdx.x == 0 && slot < 400) {
         long long* t = reinterpret_cast<long long*>(p.debug_params) + role * 800 + 2 * slot;
@@ -386,6 +394,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
         }
         mbar_init(&sm->a_ready, EPI_THREADS);
         for (int b = 0; b < ACC_BUFS; ++b) { mbar_init(&sm->acc_full[b], 1); mbar_init(&sm->acc_empty[b], EPI_THREADS); }
+        mbar_init(&sm->hid_full, (uint32_t)p.hidden_groups);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(&sm->tmem_base, 512);
@@ -444,10 +453,11 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
         // schedule and polled without blocking while the first weight blocks stream in.
         const bool far = n_tiles >= 2 * (int)gridDim.x;
         bool need_x = true;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
-            const LayerP& L = p.layers[item / n_tiles];
-            const int n_ops = L.n_ops, op_base = L.op_base;
-            const uint8_t* weights = L.weights;
+        int layer = 0, tile = blockIdx.x;            // grid <= n_tiles: the first item of every CTA is in layer 0
+        while (layer < p.n_layers) {
+            const int item = layer * n_tiles + tile;
+            const int n_ops = p.layers[layer].n_ops, op_base = p.layers[layer].op_base;
+            const uint8_t* weights = p.layers[layer].weights;
             trace<DEBUG>(p, 0, ts, 1001);
             const int prefetch_at = n_ops > 8 ? 8 : n_ops - 1;   // after the first weight blocks of this item are in flight
             const int must_at = n_ops > STAGES - 1 ? STAGES - 1 : n_ops - 1;   // the ring is full: the MMAs need x to go on
@@ -459,9 +469,8 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
                         need_x = false;
                     }
                 }
-                const Op& op = p.ops[op_base + i];
-                const uint32_t bytes = (uint32_t)op.w_bytes16 * 16u;
-                const uint32_t w_off = op.w_off;
+                const Op op = p.ops[op_base + i];
+                const uint32_t bytes = (uint32_t)op.n * op.ksteps * 32u;
                 mbar_wait(&sm->w_empty[stage], wphase ^ 1, p.error, 2);
                 trace<DEBUG>(p, 0, ts, i);
                 if (elect_one()) {
@@ -469,7 +478,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
                         mbar_arrive(&sm->w_full[stage]);
                     } else {
                         mbar_expect_tx(&sm->w_full[stage], bytes);
-                        bulk_g2s(sW + (size_t)stage * STAGE_BYTES, weights + w_off, bytes, &sm->w_full[stage]);
+                        bulk_g2s(sW + (size_t)stage * STAGE_BYTES, weights + op.w_off, bytes, &sm->w_full[stage]);
                     }
                 }
                 __syncwarp();
@@ -477,28 +486,39 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
                 if (far && i == prefetch_at && item + (int)gridDim.x < n_items) request_x(item + gridDim.x, tcount + 1);
             }
             need_x = !far;
+            ++tcount;
+            tile += gridDim.x;
+            while (tile >= n_tiles) { tile -= n_tiles; ++layer; }
         }
-    } else if (warp == 1) {
-        // =========================== MMA issuer ===========================
+    } else if (warp == 1 || warp == 3) {
+        // =========================== MMA issuers ===========================
         // Warp-uniform walk over the schedule; one elected lane issues the tcgen05.mma / commit instructions.
-        uint32_t stage = 0, wphase = 0, a_cnt = 0, empty_bits = 0;   // empty_bits: next phase parity per accumulator
-        int ts = lane == 0 ? 0 : 1000000;
+        // A single warp needs ~100 dependent instructions (~450 cycles) per weight block, more than the MMAs of
+        // the block take, so the accumulator groups alternate between TWO issuer warps (OP_OWNER1): each walks
+        // the whole schedule to keep the ring position, and issues only its own groups.  Accumulation order
+        // inside a group is kept (one warp per group); groups are independent of each other.
+        const uint32_t me = warp == 3 ? OP_OWNER1 : 0u;
+        uint32_t stage = 0, wphase = 0, a_par = 0, empty_bits = 0;   // empty_bits: next phase parity per accumulator
+        int ts = (lane == 0 && warp == 1) ? 0 : 1000000;
         const uint32_t w_base16 = smem_u32(sW) >> 4;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const LayerP& L = p.layers[item / n_tiles];
-            const int n_ops = L.n_ops, op_base = L.op_base;
+        int layer = 0, tile = blockIdx.x;
+        while (layer < p.n_layers) {
+            const int n_ops = p.layers[layer].n_ops, op_base = p.layers[layer].op_base;
             for (int i = 0; i < n_ops; ++i) {
-                const Op& op = p.ops[op_base + i];
+                const Op op = p.ops[op_base + i];
                 const uint32_t flags = op.flags, n = op.n;
                 const uint32_t acc = (flags >> OP_ACC_SHIFT) & 3u;
-                if (flags & OP_WAIT_A) {
-                    mbar_wait(&sm->a_ready, a_cnt & 1, p.error, 3);
-                    ++a_cnt;
+                if (flags & OP_WAIT_A) {            // both issuers pass every A hand-over (keeps their parity in step)
+                    mbar_wait(&sm->a_ready, a_par, p.error, 3);
+                    a_par ^= 1u;
                 }
-                if (flags & OP_WAIT_EMPTY) {
-                    mbar_wait(&sm->acc_empty[acc], ((empty_bits >> acc) & 1u) ^ 1u, p.error, 4);
-                    empty_bits ^= 1u << acc;
+                const uint32_t empty_par = ((empty_bits >> acc) & 1u) ^ 1u;
+                if (flags & OP_WAIT_EMPTY) empty_bits ^= 1u << acc;      // every use of the buffer, whoever issues it
+                if ((flags & OP_OWNER1) != me) {
+                    if (++stage == STAGES) { stage = 0; wphase ^= 1; }
+                    continue;
                 }
+                if (flags & OP_WAIT_EMPTY) mbar_wait(&sm->acc_empty[acc], empty_par, p.error, 4);
                 trace<DEBUG>(p, 1, ts, 2000 + i);
                 mbar_wait(&sm->w_full[stage], wphase, p.error, 5);
                 tc_fence_after();
@@ -509,20 +529,21 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
                 const uint32_t a_tmem = tmem + A_COL + op.a_col;
                 const uint32_t ksteps = (dmode & 8) ? 1u : (uint32_t)op.ksteps;
                 const uint32_t d_tmem = tmem + op.tmem_col;
-                const uint32_t idesc = make_idesc(n);
                 if (elect_one()) {
                     uint32_t accumulate = (flags & OP_FIRST) ? 0u : 1u;
                     for (uint32_t ks = 0; ks < ksteps; ++ks) {
                         const uint64_t db = ((uint64_t)DESC_HI << 32) | (b_lo + ks * 2u * n);
-                        umma_ts(d_tmem, a_tmem + ks * 8u, db, idesc, accumulate);
+                        umma_ts(d_tmem, a_tmem + ks * 8u, db, op.idesc, accumulate);
                         accumulate = 1u;
                     }
                     umma_commit(&sm->w_empty[stage]);                   // frees the ring stage when the MMAs retire
-                    if (flags & OP_COMMIT) umma_commit(&sm->acc_full[acc]);
+                    if (flags & OP_COMMIT) umma_commit((flags & OP_HIDDEN) ? &sm->hid_full : &sm->acc_full[acc]);
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; wphase ^= 1; }
             }
+            tile += gridDim.x;
+            while (tile >= n_tiles) { tile -= n_tiles; ++layer; }
         }
     } else if (warp == 2) {
         // =========================== y store, log-det, publish ===========================
@@ -579,7 +600,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
         const int wg = et >> 7;                   // warpgroup 0..3
         const int row = (warp & 3) * 32 + lane;   // sample row of the tile = TMEM lane
         const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        uint32_t full_bits = 0, tcount = 0;       // full_bits: phase parity to wait for, per accumulator
+        uint32_t full_bits = 0, hid_par = 0, tcount = 0;   // full_bits: phase parity to wait for, per accumulator
         int ts = (et == 0) ? 0 : 1000000;
 
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
@@ -614,8 +635,8 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
             trace<DEBUG>(p, 2, ts, 3002);
             // ---- two hidden layers: ELU, bf16 -> A operand of the next GEMM (tensor memory) ----
             for (int hl = 0; hl < 2; ++hl) {
-                mbar_wait(&sm->acc_full[0], full_bits & 1u, p.error, 7);
-                full_bits ^= 1u;
+                mbar_wait(&sm->hid_full, hid_par, p.error, 7);
+                hid_par ^= 1u;
                 tc_fence_after();
                 trace<DEBUG>(p, 2, ts, 3010 + hl);
                 // 16 accumulator columns per step; the load of the next step is in flight while this one is processed
@@ -726,6 +747,7 @@ extern "C" int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_st
     TFEPB_CHECK_ARG(a->hidden_padded % 16 == 0 && a->hidden_padded > 0 && a->hidden_padded <= fused::ACC_COLS,
                     "hidden width (padded) must be a multiple of 16 and at most 336 (tensor-memory plan)");
     TFEPB_CHECK_ARG(a->k1 <= 2 * (512 - fused::A_COL), "too many input features for the tensor-memory plan");
+    TFEPB_CHECK_ARG(a->hidden_groups >= 1 && a->hidden_groups <= 8, "hidden_groups must be in [1, 8]");
     TFEPB_CHECK_ARG((a->n_features * 4 * fused::TILE_M) % 16 == 0, "tile of x must be a multiple of 16 bytes");
     TFEPB_CHECK_ARG(((uintptr_t)a->x % 16 == 0) && ((uintptr_t)a->y % 16 == 0), "x and y must be 16-byte aligned");
     if (int rc = require_sm100()) return rc;
@@ -752,6 +774,7 @@ extern "C" int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_st
         if (s.n_chunks * fused::FEATS_PER_CHUNK > feat_stride) feat_stride = s.n_chunks * fused::FEATS_PER_CHUNK;
     }
     p.feat_stride = feat_stride;
+    p.hidden_groups = a->hidden_groups;
     p.error = a->error_flag;
     p.debug_params = a->debug_params;
     p.debug_mode = a->debug_mode;
