@@ -234,24 +234,25 @@ def run_ours(args, rank, world, local_rank):
     pk = seq[0]._pack()
     plan = pk['plan']
     if args.precision == 'bf16':
-        # dominant (only) kernel: the fused MAF-layer kernel, one launch per layer, timed alone
-        fused = seq[0]._fused
+        # dominant (only) kernel: the fused MAF-chain kernel (all layers in ONE persistent launch), timed alone
         with torch.no_grad():
             for _ in range(3):
-                fused.forward(seq[0], x)
+                seq(x)
             kev = []
             for _ in range(10):
                 flush.zero_()
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s.record()
-                fused.forward(seq[0], x)
+                seq(x)
                 e.record()
                 kev.append((s, e))
             torch.cuda.synchronize(dev)
         k_ms = statistics.mean(s.elapsed_time(e) for s, e in kev)
-        flops_per_launch = 2.0 * plan.masked_macs * BATCH        # algorithmic: 2 x non-zeros of the three masks
-        kernel = 'maf_spline_fwd_kernel (one MAF layer: 3 masked GEMMs on tcgen05 + ELU + spline epilogue)'
-        launches_per_step = len(seq)
+        # algorithmic: 2 x non-zeros of the three masks x layers x samples
+        flops_per_launch = 2.0 * plan.masked_macs * len(seq) * BATCH
+        kernel = (f'maf_spline_fwd_kernel ({len(seq)} MAF layers in one launch: 3 masked GEMMs on tcgen05 + ELU + spline '
+                  'epilogue per layer)')
+        launches_per_step = 1
     else:
         # dominant kernel of the exact path: the output-layer GEMM (328 -> 1650) of one MAF layer, timed alone
         with torch.no_grad():
@@ -277,7 +278,7 @@ def run_ours(args, rank, world, local_rank):
     achieved = flops_per_launch / (k_ms * 1e-3) / 1e12
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': pk_peaks['bf16_tflops'], 'unit': 'TFLOP/s',
                 'frac': achieved / pk_peaks['bf16_tflops'],
-                'traffic': 18.38e6 if args.precision == 'bf16' else None,   # dram read+write bytes per launch, ncu capture profiles/r01_ncu_fused_v3_details.md
+                'traffic': None,
                 'kernel': kernel,
                 'kernel_ms': k_ms, 'peak_source': pk_peaks['source'] + ', bf16 burst',
                 'whole_step_frac': (2.0 * plan.masked_macs * 4 * BATCH * args.steps / (total_ms * 1e-3) / 1e12)

@@ -280,7 +280,8 @@ __device__ __forceinline__ float rcp(float v) {
     return r;
 }
 // ELU in the log2 domain: t = log2(e) h  ->  log2(e) ELU(h) = t > 0 ? t : log2(e) (2^t - 1)
-__device__ __forceinline__ float elu_l2(float t) { return t > 0.f ? t : fmaf(ex2(t), LOG2E, -LOG2E); }
+// Branch-free: g(t) = log2(e) (2^min(t, 0) - 1) is 0 for t >= 0 and >= t for t <= 0, so the result is max(t, g).
+__device__ __forceinline__ float elu_l2(float t, float l2e) { return fmaxf(t, fmaf(ex2(fminf(t, 0.f)), l2e, -LOG2E)); }
 // softplus of a log2-domain argument z = log2(e) * v: log(1 + e^v) = ln2 * lg2(1 + 2^z)
 __device__ __forceinline__ float softplus_l2(float z) { return z > 28.85f ? z * LN2 : LN2 * lg2(1.f + ex2(z)); }
 
@@ -313,24 +314,27 @@ __device__ __forceinline__ float spline8_circular(const uint32_t (&r)[32], float
     // softmax numerators (log2 domain)
     float mw = fmaxf(fmaxf(fmaxf(p[0], p[1]), fmaxf(p[2], p[3])), fmaxf(fmaxf(p[4], p[5]), fmaxf(p[6], p[7])));
     float mh = fmaxf(fmaxf(fmaxf(p[8], p[9]), fmaxf(p[10], p[11])), fmaxf(fmaxf(p[12], p[13]), fmaxf(p[14], p[15])));
-    float ew[8], eh[8], sw = 0.f, sh = 0.f;
+    float ew[8], eh[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        ew[k] = ex2(p[k] - mw); sw += ew[k];
-        eh[k] = ex2(p[8 + k] - mh); sh += eh[k];
+        ew[k] = ex2(p[k] - mw);
+        eh[k] = ex2(p[8 + k] - mh);
     }
+    const float sw = ((ew[0] + ew[1]) + (ew[2] + ew[3])) + ((ew[4] + ew[5]) + (ew[6] + ew[7]));
+    const float sh = ((eh[0] + eh[1]) + (eh[2] + eh[3])) + ((eh[4] + eh[5]) + (eh[6] + eh[7]));
     const float rw = fc.Rw * rcp(sw), rh = fc.Rh * rcp(sh);
     // walk the knots (relative to x0 / y0): last bin whose left knot is below t
-    float left = 0.f, bottom = 0.f;
-    float w_sel = fmaf(ew[0], rw, min_bin), h_sel = fmaf(eh[0], rh, min_bin), xk = 0.f, yk = 0.f;
+    float wk = fmaf(ew[0], rw, min_bin), hk = fmaf(eh[0], rh, min_bin);
+    float left = wk, bottom = hk, w_sel = wk, h_sel = hk, xk = 0.f, yk = 0.f;
     float raw0 = p[16], raw1 = p[17];
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
-        left += fmaf(ew[k], rw, min_bin);
-        bottom += fmaf(eh[k], rh, min_bin);
+        if (k > 0) { left += wk; bottom += hk; }
+        wk = fmaf(ew[k + 1], rw, min_bin);
+        hk = fmaf(eh[k + 1], rh, min_bin);
         const bool adv = t > left;
-        w_sel = adv ? fmaf(ew[k + 1], rw, min_bin) : w_sel;
-        h_sel = adv ? fmaf(eh[k + 1], rh, min_bin) : h_sel;
+        w_sel = adv ? wk : w_sel;
+        h_sel = adv ? hk : h_sel;
         xk = adv ? left : xk;
         yk = adv ? bottom : yk;
         raw0 = adv ? p[16 + k + 1] : raw0;
@@ -639,21 +643,32 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
                 hid_par ^= 1u;
                 tc_fence_after();
                 trace<DEBUG>(p, 2, ts, 3010 + hl);
-                // 16 accumulator columns per step; the load of the next step is in flight while this one is processed
-                uint32_t r[16], rn[16];
-                int c0 = wg * 16;
-                if (c0 < p.HP) tmem_ld16(lane_addr + c0, r);
-                for (; c0 < p.HP; c0 += EPI_WGS * 16) {
-                    tmem_wait8(r); tmem_wait8(r + 8);
-                    const int cn = c0 + EPI_WGS * 16;
-                    if (cn < p.HP) tmem_ld16(lane_addr + cn, rn);
+                // 16 accumulator columns per step, two register sets in ping-pong: the load of the next step is in
+                // flight while this one is processed
+                uint32_t ra[16], rb[16];
+                float l2e;                          // opaque to the compiler: kept in ONE register instead of being
+                asm volatile("mov.f32 %0, 0f3FB8AA3B;" : "=f"(l2e));    // re-materialised for every element
+                auto elu16 = [&](uint32_t (&r)[16], int c0) {
                     uint32_t q[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
-                        q[i] = pack_bf16(elu_l2(__uint_as_float(r[2 * i])), elu_l2(__uint_as_float(r[2 * i + 1])));
+                        q[i] = pack_bf16(elu_l2(__uint_as_float(r[2 * i]), l2e), elu_l2(__uint_as_float(r[2 * i + 1]), l2e));
                     tmem_st8(lane_addr + A_COL + c0 / 2, q);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) r[i] = rn[i];
+                };
+                int c0 = wg * 16;
+                if (c0 < p.HP) tmem_ld16(lane_addr + c0, ra);
+                while (c0 < p.HP) {
+                    tmem_wait8(ra); tmem_wait8(ra + 8);
+                    int cn = c0 + EPI_WGS * 16;
+                    if (cn < p.HP) tmem_ld16(lane_addr + cn, rb);
+                    elu16(ra, c0);
+                    c0 = cn;
+                    if (c0 >= p.HP) break;
+                    tmem_wait8(rb); tmem_wait8(rb + 8);
+                    cn = c0 + EPI_WGS * 16;
+                    if (cn < p.HP) tmem_ld16(lane_addr + cn, ra);
+                    elu16(rb, c0);
+                    c0 = cn;
                 }
                 tmem_st_wait();
                 tc_fence_before();
@@ -683,6 +698,9 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
                         tmem_ld1(a0 + 24, r + 24);
                         tmem_wait8(r); tmem_wait8(r + 8); tmem_wait8(r + 16); tmem_wait1(r + 24);
                     }
+                    // the parameters are in registers: the accumulator can be refilled while the spline is evaluated
+                    tc_fence_before();
+                    mbar_arrive(&sm->acc_empty[b]);
                     const FeatConst fc = feat[c * FEATS_PER_CHUNK];
                     if (dmode & 2) {
                         float acc = 0.f;
@@ -701,8 +719,6 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
                         xrow[fc.col] = yv;
                     }
                 }
-                tc_fence_before();
-                mbar_arrive(&sm->acc_empty[b]);
                 trace<DEBUG>(p, 2, ts, 3200 + c);
                 b = (b == ACC_BUFS - 1) ? 0u : b + 1u;
             }
