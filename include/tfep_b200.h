@@ -229,6 +229,58 @@ typedef struct {
 int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_stream_t stream);
 
 /* ----------------------------------------------------------------------------------------------
+ * Persistent inverse sweep of one MAF layer, exact fp32 / fp64 arithmetic: x, logdet = MAF.inverse(y).
+ * Replaces AutoregressiveFlow.inverse (nn/flows/autoregressive.py:179-229), which runs n_degrees full
+ * conditioner passes: with degree-sorted packed weights every unit is evaluated once, degree by degree,
+ * by one persistent kernel that keeps x and all hidden activations of a sample tile in shared memory.
+ * `w[l]` (n_out[l] rows, leading dimension ldw[l] = a multiple of 16 bytes, zero padded) and `b[l]` are the
+ * packed effective weights of linear layer l (l = n_linear - 1 is the output layer, rows grouped by degree);
+ * `groups` lists, in ascending degree, the output rows and the hidden units that become computable.
+ * -------------------------------------------------------------------------------------------- */
+#define TFEPB_SWEEP_MAX_LINEAR 5
+enum { TFEPB_SWEEP_AFFINE = 0, TFEPB_SWEEP_SPLINE = 1, TFEPB_SWEEP_MOEBIUS = 2 };
+
+typedef struct {
+    int32_t out_r0, out_r1, out_k;       /* output-layer rows of the group and the reduction length they need */
+    int32_t h_a[TFEPB_SWEEP_MAX_LINEAR - 1], h_b[TFEPB_SWEEP_MAX_LINEAR - 1], h_k[TFEPB_SWEEP_MAX_LINEAR - 1];
+                                         /* per hidden layer l (index l - 1): units [h_a, h_b) computable after
+                                            the group, and their reduction length */
+    int32_t part_first, part_count;      /* entries of `group_parts` */
+} tfepb_sweep_group;
+
+typedef struct {
+    int32_t kind;                        /* TFEPB_SWEEP_* */
+    int32_t n_bins, circular, identity_boundary_slopes, learn_lower_bound, learn_upper_bound;   /* spline */
+    int32_t dimension, unit_sphere;      /* moebius */
+    const void *x0, *xf, *y0, *yf;       /* spline domain per feature of the part (dtype of the call) */
+    double min_bin_size, min_slope, max_radius;
+    const int32_t* cols;                 /* feature -> column of x / y, or NULL */
+    const int32_t* par_base;             /* feature -> first packed output row of its parameters */
+} tfepb_sweep_part;
+
+typedef struct {
+    int32_t part, ids_offset, n_ids;     /* features `ids[ids_offset .. + n_ids)` of `part` belong to the group */
+} tfepb_sweep_group_part;
+
+typedef struct {
+    int32_t dtype, batch, n_features, n_linear;
+    const void* y; int64_t ldy;
+    void* x; int64_t ldx;
+    void* logdet;
+    const void* w[TFEPB_SWEEP_MAX_LINEAR];
+    const void* b[TFEPB_SWEEP_MAX_LINEAR];
+    int32_t n_out[TFEPB_SWEEP_MAX_LINEAR], ldw[TFEPB_SWEEP_MAX_LINEAR];
+    const tfepb_sweep_group* groups;             /* device */
+    int32_t n_groups, max_params;                /* max_params = max (out_r1 - out_r0) */
+    const tfepb_sweep_part* parts;               /* device */
+    const tfepb_sweep_group_part* group_parts;   /* device */
+    const int32_t* ids;                          /* device */
+    const int32_t* fixed_cols;                   /* device: conditioning features copied from y (may be NULL) */
+    int32_t n_fixed, reserved;
+} tfepb_sweep_args;
+int tfepb_maf_inverse_sweep(const tfepb_sweep_args* a, tfepb_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------------
  * (T)FEP estimator and bootstrap
  * -------------------------------------------------------------------------------------------- */
 /* One pass over v_i = scale * w_i (+ logw_i): writes out[0] = max_i v_i, out[1] = sum_i exp(v_i - max)

@@ -61,6 +61,29 @@ def test_generic_autoregressive_flow_matches_packed_path():
                 assert rel_err(xi2, xi) < 1e-10 and rel_err(ldi2, ldi) < 1e-10, name
 
 
+def test_persistent_sweep_matches_host_driven_sweep(prec):
+    """tfepb_maf_inverse_sweep (one persistent kernel, tile state in shared memory) against the same
+    degree-ordered sweep driven from the host with the stand-alone GEMM / transformer kernels, on every
+    invertible MAF configuration, for batches that are not multiples of the 64 / 32-sample tile."""
+    tol = 20 * TOL[prec]
+    for name, case in cases.maf_cases(DT[prec]).items():
+        if not case['invertible']:
+            continue
+        _, sd = cases.build_oracle(case, DT[prec])
+        maf = to_maf(case, sd, DEV, DT[prec])
+        x = case['x'].to(DEV)
+        reps = -(-150 // x.shape[0])
+        xx = torch.cat([x] * reps)[:150] if x.shape[0] < 150 else x
+        with torch.no_grad():
+            y, _ = maf(xx)
+            for b in (1, 33, 150):
+                xi, ldi = maf.inverse(y[:b])
+                xh, ldh = maf._inverse_host_sweep(y[:b])
+                assert rel_err(xi, xh) < tol and rel_err(ldi, ldh) < tol, (name, b)
+                xi2, ldi2 = maf.inverse(y[:b])
+                assert torch.equal(xi, xi2) and torch.equal(ldi, ldi2), name       # deterministic
+
+
 def test_round_trip_and_conditioning_untouched(prec):
     """inverse(forward(x)) == x, log-dets cancel, conditioning features pass through
     (reference tests/nn/flows/test_maf.py:226-295)."""

@@ -76,6 +76,15 @@ class FusedArgs(Structure):
                 ('error_flag', c_void_p), ('debug_params', c_void_p)]
 
 
+class SweepArgs(Structure):
+    _fields_ = [('dtype', c_int32), ('batch', c_int32), ('n_features', c_int32), ('n_linear', c_int32),
+                ('y', c_void_p), ('ldy', c_int64), ('x', c_void_p), ('ldx', c_int64), ('logdet', c_void_p),
+                ('w', c_void_p * 5), ('b', c_void_p * 5), ('n_out', c_int32 * 5), ('ldw', c_int32 * 5),
+                ('groups', c_void_p), ('n_groups', c_int32), ('max_params', c_int32),
+                ('parts', c_void_p), ('group_parts', c_void_p), ('ids', c_void_p), ('fixed_cols', c_void_p),
+                ('n_fixed', c_int32), ('reserved', c_int32)]
+
+
 # every symbol include/tfep_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     'tfepb_abi_version': (c_int32, []),
@@ -93,6 +102,7 @@ SYMBOLS = {
     'tfepb_sos_backward': (c_int32, [POINTER(TxIo), c_int32, POINTER(TxGrads), c_void_p]),
     'tfepb_moebius_backward': (c_int32, [POINTER(TxIo), c_int32, c_double, c_int32, POINTER(TxGrads), c_void_p]),
     'tfepb_maf_spline_forward_bf16': (c_int32, [POINTER(FusedArgs), c_void_p]),
+    'tfepb_maf_inverse_sweep': (c_int32, [POINTER(SweepArgs), c_void_p]),
     'tfepb_lse_workspace_bytes': (c_int64, []),
     'tfepb_lse': (c_int32, [c_int32, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p]),
     'tfepb_mt19937_seed': (c_int32, [c_uint32, c_void_p]),

@@ -1,0 +1,300 @@
+// Persistent inverse sweep of one MAF layer (exact fp32 / fp64 arithmetic).
+//
+//   x, logdet = MAF.inverse(y)                      (reference: nn/flows/autoregressive.py:179-229)
+//
+// The reference inverts an autoregressive flow with n_degrees FULL passes of the conditioner (pass i fixes
+// the features of degree i, autoregressive.py:216-227).  With hidden units sorted by degree
+// (tfep_b200/_pack.py) every unit can be evaluated exactly once, as soon as its inputs exist:
+//
+//   for each degree d (ascending):
+//       par_d  = W_out[rows of the features of degree d] . h_last[units of degree < d] + b    (A)
+//       x_d    = T^-1(y_d ; par_d),  logdet += ...                                            (T)
+//       h_l[units of degree d] = ELU(W_l[those rows] . h_{l-1}[units of degree <= d] + b)     (H, l = 1..)
+//
+// i.e. nnz(masks) multiply-accumulates per sample -- the cost of ONE forward pass -- instead of n_degrees
+// passes.  The whole sweep runs in one persistent kernel: a CTA owns a tile of TS samples and keeps x and
+// every hidden activation of the tile in shared memory across all degrees (nothing but y, x and logdet
+// touches HBM; the weights stream from L2 through L1, each row being read once per tile).  The stages
+// of a degree are separated by CTA barriers; inside a stage a warp owns 32 samples (lane = sample, so the
+// 16-byte activation loads are conflict-free with the padded leading dimensions chosen by the host) and a
+// block of up to 8 output rows, whose weights arrive as warp-uniform 16-byte loads; short stages are split
+// along the reduction and combined in a fixed order (deterministic results).
+//
+// Transformers run through the same device operators as the stand-alone kernels (tx_ops.cuh), reading
+// the parameters of the degree group from shared memory.
+#include "common.cuh"
+#include "tx_math.cuh"
+#include "tx_ops.cuh"
+
+namespace tfepb {
+namespace sweep {
+
+constexpr int MAXL = TFEPB_SWEEP_MAX_LINEAR;
+constexpr int RB = 8;                       // output rows per register block
+
+template <typename T> struct Vec;
+template <> struct Vec<float> { using type = float4; static constexpr int N = 4; };
+template <> struct Vec<double> { using type = double2; static constexpr int N = 2; };
+
+__device__ __forceinline__ float dot_acc(float4 w, float4 h, float a) {
+    a = fmaf(w.x, h.x, a); a = fmaf(w.y, h.y, a); a = fmaf(w.z, h.z, a); return fmaf(w.w, h.w, a);
+}
+__device__ __forceinline__ double dot_acc(double2 w, double2 h, double a) { return fma(w.y, h.y, fma(w.x, h.x, a)); }
+
+template <typename T>
+struct Params {
+    const T* y; int64_t ldy;
+    T* x; int64_t ldx;
+    T* logdet;
+    int batch, D, n_linear;
+    const T* w[MAXL]; const T* b[MAXL];
+    int ldw[MAXL];
+    int act_ld[MAXL];                 // shared-memory leading dimensions: [0] x tile, [l] hidden layer l
+    int par_ld;
+    const tfepb_sweep_group* groups; int n_groups;
+    const tfepb_sweep_part* parts;
+    const tfepb_sweep_group_part* gparts;
+    const int* ids;
+    const int* fixed_cols; int n_fixed;
+};
+
+// out[s][ocol0 + (r - r0)] = act(bias[r] + sum_k W[r][k] in[s][k]) for r in [r0, r1), all TS samples of the tile.
+// Ends with a CTA barrier.  K is rounded up to the vector width: the host pads the weight rows with zeros and
+// activations that do not exist yet are zero.
+template <typename T, int TS, int THREADS>
+__device__ void gemv_stage(const T* __restrict__ W, int ldw, const T* __restrict__ bias, int r0, int r1, int K,
+                           const T* in, int ldin, T* out, int ldout, int ocol0, bool act, T* scratch) {
+    using V = typename Vec<T>::type;
+    constexpr int NV = Vec<T>::N;
+    constexpr int SG = TS / 32;                  // warps side by side over the samples
+    constexpr int NWG = THREADS / 32 / SG;       // warp groups sharing the rows / the reduction
+    const int R = r1 - r0;
+    if (R <= 0) return;                          // uniform over the CTA
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sg = warp % SG, wg = warp / SG;
+    const int s = sg * 32 + lane;
+    const int nrb = (R + RB - 1) / RB;
+    const int rbs = (R + nrb - 1) / nrb;         // balanced block size <= RB
+    const int Kv = (K + NV - 1) / NV;
+    int nks = NWG / nrb;
+    if (nks > Kv / 8) nks = Kv / 8;              // at least 8 vector steps per slice
+    if (nks < 1) nks = 1;
+    const int items = nrb * nks;
+    const V* inv = reinterpret_cast<const V*>(in + (size_t)s * ldin);
+    for (int it = wg; it < items; it += NWG) {
+        const int rb = it / nks, ks = it - rb * nks;
+        const int ra = r0 + rb * rbs;
+        const int nr = min(rbs, r1 - ra);
+        const int kv0 = (Kv * ks) / nks, kv1 = (Kv * (ks + 1)) / nks;
+        T acc[RB];
+#pragma unroll
+        for (int j = 0; j < RB; ++j) acc[j] = T(0);
+        const T* wrow = W + (size_t)ra * ldw;
+#pragma unroll 2
+        for (int kv = kv0; kv < kv1; ++kv) {
+            const V h = inv[kv];
+#pragma unroll
+            for (int j = 0; j < RB; ++j) {
+                if (j < nr) {
+                    const V wv = __ldg(reinterpret_cast<const V*>(wrow + (size_t)j * ldw) + kv);
+                    acc[j] = dot_acc(wv, h, acc[j]);
+                }
+            }
+        }
+        if (nks == 1) {
+#pragma unroll
+            for (int j = 0; j < RB; ++j) {
+                if (j < nr) {
+                    const T v = acc[j] + bias[ra + j];
+                    out[(size_t)s * ldout + ocol0 + (ra - r0) + j] = act ? tfepb::elu(v) : v;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < RB; ++j)
+                if (j < nr) scratch[((size_t)it * RB + j) * TS + s] = acc[j];
+        }
+    }
+    if (nks > 1) {
+        __syncthreads();
+        for (int o = threadIdx.x; o < R * TS; o += THREADS) {
+            const int r = o / TS, ss = o - r * TS;
+            const int rb = r / rbs, j = r - rb * rbs;
+            T v = bias[r0 + r];
+            for (int ks = 0; ks < nks; ++ks) v += scratch[((size_t)(rb * nks + ks) * RB + j) * TS + ss];
+            out[(size_t)ss * ldout + ocol0 + r] = act ? tfepb::elu(v) : v;
+        }
+    }
+    __syncthreads();
+}
+
+template <typename T, int MAXK>
+__device__ __forceinline__ SplineOp<T, MAXK> make_spline(const tfepb_sweep_part& d) {
+    SplineOp<T, MAXK> op;
+    op.K = d.n_bins; op.circular = d.circular; op.idslopes = d.identity_boundary_slopes;
+    op.learn_lo = d.learn_lower_bound; op.learn_hi = d.learn_upper_bound;
+    op.x0 = (const T*)d.x0; op.xf = (const T*)d.xf; op.y0 = (const T*)d.y0; op.yf = (const T*)d.yf;
+    op.min_bin = (T)d.min_bin_size; op.min_slope = (T)d.min_slope;
+    op.bins = nullptr; op.ldbins = 0;
+    return op;
+}
+
+// Inverse transformer of the features of one degree group: thread s handles sample s of the tile.
+template <typename T, int TS, int THREADS>
+__device__ void transform_stage(const Params<T>& p, const tfepb_sweep_group& g, int64_t tile0, int rows, T* xs, const T* par,
+                                T* ldacc) {
+    const int s = threadIdx.x;
+    if (s < TS && s < rows && g.part_count > 0) {
+        TxView<T> v{};
+        v.x = p.y + tile0 * p.ldy; v.ldx = p.ldy;          // source: y (global), local row index
+        v.y = xs; v.ldy = p.act_ld[0];                     // destination: the x tile in shared memory
+        v.par = par; v.ldp = p.par_ld; v.poff = -(int64_t)g.out_r0; v.sp = 1; v.sf = 0;
+        v.logdet = nullptr; v.accumulate = 0; v.B = rows; v.inverse = 1;
+        T ld = T(0);
+        for (int q = 0; q < g.part_count; ++q) {
+            const tfepb_sweep_group_part gp = p.gparts[g.part_first + q];
+            const tfepb_sweep_part& d = p.parts[gp.part];
+            v.pbase = d.par_base; v.cols = d.cols; v.ids = p.ids + gp.ids_offset; v.F = gp.n_ids;
+            if (d.kind == TFEPB_SWEEP_AFFINE) {
+                AffineOp<T> op;
+                for (int u = 0; u < gp.n_ids; ++u) ld += op.apply(v, s, u);
+            } else if (d.kind == TFEPB_SWEEP_SPLINE) {
+                if (d.n_bins <= 8) {
+                    const SplineOp<T, 8> op = make_spline<T, 8>(d);
+                    for (int u = 0; u < gp.n_ids; ++u) ld += op.apply(v, s, u);
+                } else {
+                    const SplineOp<T, 32> op = make_spline<T, 32>(d);
+                    for (int u = 0; u < gp.n_ids; ++u) ld += op.apply(v, s, u);
+                }
+            } else {
+                const MoebiusOp<T> op{d.dimension, (T)d.max_radius, d.unit_sphere};
+                for (int u = 0; u < gp.n_ids / d.dimension; ++u) ld += op.apply(v, s, u);
+            }
+        }
+        ldacc[s] += ld;
+    }
+    __syncthreads();
+}
+
+template <typename T, int TS, int THREADS>
+__global__ void __launch_bounds__(THREADS) maf_inverse_sweep_kernel(const Params<T> p) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    T* act[MAXL];
+    T* cur = reinterpret_cast<T*>(smem_raw);
+    for (int l = 0; l < p.n_linear; ++l) { act[l] = cur; cur += (size_t)TS * p.act_ld[l]; }
+    T* par = cur; cur += (size_t)TS * p.par_ld;
+    T* scratch = cur; cur += (size_t)(THREADS / 32 / (TS / 32)) * RB * TS;
+    T* ldacc = cur;
+    const int L = p.n_linear;
+    const int n_tiles = (p.batch + TS - 1) / TS;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t tile0 = (int64_t)tile * TS;
+        const int rows = min(TS, p.batch - (int)tile0);
+        // ---- reset the tile state: x = 0 (+ conditioning features copied from y), activations = 0 ----
+        for (int l = 0; l < L; ++l)
+            for (int i = threadIdx.x; i < TS * p.act_ld[l]; i += THREADS) act[l][i] = T(0);
+        if (threadIdx.x < TS) ldacc[threadIdx.x] = T(0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < rows * p.n_fixed; i += THREADS) {
+            const int s = i / p.n_fixed, c = p.fixed_cols[i - s * p.n_fixed];
+            act[0][(size_t)s * p.act_ld[0] + c] = p.y[(tile0 + s) * p.ldy + c];
+        }
+        __syncthreads();
+        // ---- degree sweep ----
+        for (int gi = 0; gi < p.n_groups; ++gi) {
+            const tfepb_sweep_group g = p.groups[gi];
+            if (g.out_r1 > g.out_r0) {
+                gemv_stage<T, TS, THREADS>(p.w[L - 1], p.ldw[L - 1], p.b[L - 1], g.out_r0, g.out_r1, g.out_k, act[L - 1], p.act_ld[L - 1],
+                                  par, p.par_ld, 0, false, scratch);
+                transform_stage<T, TS, THREADS>(p, g, tile0, rows, act[0], par, ldacc);
+            }
+            for (int l = 1; l < L; ++l)
+                gemv_stage<T, TS, THREADS>(p.w[l - 1], p.ldw[l - 1], p.b[l - 1], g.h_a[l - 1], g.h_b[l - 1], g.h_k[l - 1], act[l - 1],
+                                  p.act_ld[l - 1], act[l], p.act_ld[l], g.h_a[l - 1], true, scratch);
+        }
+        // ---- write the tile ----
+        for (int i = threadIdx.x; i < rows * p.D; i += THREADS) {
+            const int s = i / p.D, c = i - s * p.D;
+            p.x[(tile0 + s) * p.ldx + c] = act[0][(size_t)s * p.act_ld[0] + c];
+        }
+        if (threadIdx.x < rows) p.logdet[tile0 + threadIdx.x] = ldacc[threadIdx.x];
+        __syncthreads();
+    }
+}
+
+template <typename T>
+size_t smem_bytes(const Params<T>& p, int TS, int THREADS) {
+    size_t n = 0;
+    for (int l = 0; l < p.n_linear; ++l) n += (size_t)TS * p.act_ld[l];
+    n += (size_t)TS * p.par_ld;
+    n += (size_t)(THREADS / 32 / (TS / 32)) * RB * TS;
+    n += TS;
+    return n * sizeof(T) + 16;
+}
+
+// leading dimension >= n whose 16-byte loads by 8 consecutive lanes (lane = row) hit 8 different bank groups
+template <typename T>
+int padded_ld(int n) {
+    const int nv = Vec<T>::N;                    // elements per 16 bytes
+    int ld = (n + nv - 1) / nv * nv;
+    while (((ld / nv) & 1) == 0) ld += nv;       // odd number of 16-byte chunks per row
+    return ld;
+}
+
+template <typename T>
+int launch(const tfepb_sweep_args* a, cudaStream_t stream) {
+    Params<T> p{};
+    p.y = (const T*)a->y; p.ldy = a->ldy; p.x = (T*)a->x; p.ldx = a->ldx; p.logdet = (T*)a->logdet;
+    p.batch = a->batch; p.D = a->n_features; p.n_linear = a->n_linear;
+    const int nv = Vec<T>::N;
+    for (int l = 0; l < a->n_linear; ++l) {
+        p.w[l] = (const T*)a->w[l]; p.b[l] = (const T*)a->b[l]; p.ldw[l] = a->ldw[l];
+        TFEPB_CHECK_ARG(p.w[l] && p.b[l], "layer %d: null weights", l);
+        TFEPB_CHECK_ARG(a->ldw[l] % nv == 0 && ((uintptr_t)a->w[l] % 16) == 0,
+                        "layer %d: weight rows must be 16-byte aligned (pad the leading dimension)", l);
+        const int width = l == 0 ? a->n_features : a->n_out[l - 1];
+        TFEPB_CHECK_ARG(a->ldw[l] >= width, "layer %d: leading dimension smaller than the input width", l);
+        p.act_ld[l] = padded_ld<T>(a->ldw[l] > width ? a->ldw[l] : width);
+    }
+    p.par_ld = a->max_params < 1 ? 1 : a->max_params;
+    p.groups = a->groups; p.n_groups = a->n_groups; p.parts = a->parts; p.gparts = a->group_parts; p.ids = a->ids;
+    p.fixed_cols = a->fixed_cols; p.n_fixed = a->n_fixed;
+    // Tile shapes, in order of preference: two independent CTAs of 128 threads x 32 samples per SM (while one
+    // is in the single-warp transformer stage or at a barrier the other one multiplies), else one CTA of
+    // 256 threads with 64 or 32 samples.
+    const size_t limit = 227 * 1024, half = 113 * 1024;
+    const size_t s32x128 = smem_bytes(p, 32, 128), s64 = smem_bytes(p, 64, 256), s32 = smem_bytes(p, 32, 256);
+    TFEPB_CHECK_ARG(s32 <= limit, "the activations of 32 samples (%zu bytes) exceed the shared memory of an SM", s32);
+    int TS, per_sm;
+    size_t smem;
+    void (*kernel)(const Params<T>);
+    if (s32x128 <= half) { kernel = maf_inverse_sweep_kernel<T, 32, 128>; TS = 32; smem = s32x128; per_sm = 2; }
+    else if (s64 <= limit) { kernel = maf_inverse_sweep_kernel<T, 64, 256>; TS = 64; smem = s64; per_sm = 1; }
+    else { kernel = maf_inverse_sweep_kernel<T, 32, 256>; TS = 32; smem = s32; per_sm = 1; }
+    TFEPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int n_tiles = (a->batch + TS - 1) / TS;
+    const int cap = sm_count() * per_sm;
+    const int grid = n_tiles < cap ? n_tiles : cap;
+    kernel<<<grid, per_sm == 2 ? 128 : 256, smem, stream>>>(p);
+    return check_launch("maf_inverse_sweep_kernel");
+}
+
+}  // namespace sweep
+}  // namespace tfepb
+
+using namespace tfepb;
+
+extern "C" int tfepb_maf_inverse_sweep(const tfepb_sweep_args* a, tfepb_stream_t stream) {
+    TFEPB_CHECK_ARG(a != nullptr, "null argument struct");
+    TFEPB_CHECK_ARG(a->dtype == TFEPB_F32 || a->dtype == TFEPB_F64, "unknown dtype %d", a->dtype);
+    TFEPB_CHECK_ARG(a->batch >= 0 && a->n_features > 0, "bad sizes");
+    TFEPB_CHECK_ARG(a->n_linear >= 1 && a->n_linear <= sweep::MAXL, "n_linear must be in [1, %d]", sweep::MAXL);
+    TFEPB_CHECK_ARG(a->y && a->x && a->logdet, "null buffer");
+    TFEPB_CHECK_ARG(a->n_groups >= 0 && (a->n_groups == 0 || (a->groups && a->parts && a->group_parts && a->ids)),
+                    "null schedule table");
+    TFEPB_CHECK_ARG(a->n_fixed == 0 || a->fixed_cols != nullptr, "null fixed_cols");
+    if (int rc = require_sm100()) return rc;
+    if (a->batch == 0) return 0;
+    if (a->dtype == TFEPB_F32) return sweep::launch<float>(a, as_stream(stream));
+    return sweep::launch<double>(a, as_stream(stream));
+}

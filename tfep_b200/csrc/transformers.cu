@@ -7,34 +7,10 @@
 // with warp shuffles and written once.  These kernels are HBM-bound (parameters are read once).
 #include "common.cuh"
 #include "tx_math.cuh"
+#include "tx_ops.cuh"
 
 namespace tfepb {
 namespace {
-
-template <typename T>
-struct TxView {
-    const T* x; int64_t ldx;
-    T* y; int64_t ldy;
-    const T* par; int64_t ldp, poff, sp, sf;
-    const int* pbase;
-    const int* cols;
-    const int* ids;
-    T* logdet;
-    int accumulate, B, F, inverse;
-    // gradients (backward kernels only)
-    const T* gy; int64_t ldgy;
-    const T* gld;
-    T* gx; int64_t ldgx;
-    T* gpar;
-
-    __device__ __forceinline__ int col(int f) const { return cols ? cols[f] : f; }
-    __device__ __forceinline__ int fid(int u) const { return ids ? ids[u] : u; }
-    __device__ __forceinline__ int64_t poffset(int b, int f) const {
-        return (int64_t)b * ldp + poff + (pbase ? (int64_t)pbase[f] : (int64_t)f * sf);
-    }
-    __device__ __forceinline__ ParIn<T> pin(int b, int f) const { return ParIn<T>{par + poffset(b, f), sp}; }
-    __device__ __forceinline__ ParOut<T> pout(int b, int f) const { return ParOut<T>{gpar + poffset(b, f), sp}; }
-};
 
 template <typename T>
 TxView<T> make_view(const tfepb_tx_io* io, const tfepb_tx_grads* g = nullptr) {
@@ -95,121 +71,6 @@ __global__ void __launch_bounds__(TX_THREADS) tx_backward_kernel(TxView<T> v, Op
         for (int u = lane; u < units; u += 32) op.backward(v, b, u, gl);
     }
 }
-
-// ------------------------------------------------------------------------------------------
-template <typename T>
-struct AffineOp {
-    __device__ int units(int F) const { return F; }
-    __device__ T apply(const TxView<T>& v, int b, int u) const {
-        const int f = v.fid(u), c = v.col(f);
-        T out, ld;
-        if (v.inverse) affine_eval<T, true>(v.pin(b, f), v.x[(int64_t)b * v.ldx + c], out, ld);
-        else affine_eval<T, false>(v.pin(b, f), v.x[(int64_t)b * v.ldx + c], out, ld);
-        v.y[(int64_t)b * v.ldy + c] = out;
-        return ld;
-    }
-    __device__ void backward(const TxView<T>& v, int b, int u, T gl) const {
-        const int f = v.fid(u), c = v.col(f);
-        T gx;
-        affine_vjp<T>(v.pin(b, f), v.x[(int64_t)b * v.ldx + c], v.gy[(int64_t)b * v.ldgy + c], gl, gx, v.pout(b, f));
-        v.gx[(int64_t)b * v.ldgx + c] = gx;
-    }
-};
-
-template <typename T>
-struct SosOp {
-    int n_poly;
-    __device__ int units(int F) const { return F; }
-    __device__ T apply(const TxView<T>& v, int b, int u) const {
-        const int f = v.fid(u), c = v.col(f);
-        T out, ld;
-        sos_eval<T>(v.pin(b, f), n_poly, v.x[(int64_t)b * v.ldx + c], out, ld);
-        v.y[(int64_t)b * v.ldy + c] = out;
-        return ld;
-    }
-    __device__ void backward(const TxView<T>& v, int b, int u, T) const {
-        const int f = v.fid(u), c = v.col(f);
-        T gx;
-        sos_vjp<T>(v.pin(b, f), n_poly, v.x[(int64_t)b * v.ldx + c], v.gy[(int64_t)b * v.ldgy + c], gx, v.pout(b, f));
-        v.gx[(int64_t)b * v.ldgx + c] = gx;
-    }
-};
-
-template <typename T>
-struct MoebiusOp {
-    int d;
-    T max_radius;
-    int unit_sphere;
-    __device__ int units(int F) const { return F / d; }
-    // Vector blocks are `d` consecutive TRANSFORMER features; their columns go through `cols`.
-    // With cols == nullptr the block is contiguous in x / y (stride 1).
-    __device__ T apply(const TxView<T>& v, int b, int u) const {
-        const int f0 = v.fid(u * d);
-        if (v.cols == nullptr && v.pbase == nullptr) {
-            return moebius_eval<T>(v.x + (int64_t)b * v.ldx + f0, 1, v.par + v.poffset(b, f0), v.sf,
-                                   v.inverse ? T(-1) : T(1), d, max_radius, unit_sphere != 0,
-                                   v.y + (int64_t)b * v.ldy + f0, 1);
-        }
-        // gather through the column map (d <= 16)
-        T xs[16], vs[16], ys[16];
-        for (int i = 0; i < d; ++i) {
-            xs[i] = v.x[(int64_t)b * v.ldx + v.col(f0 + i)];
-            vs[i] = v.par[v.poffset(b, f0 + i)];
-        }
-        const T ld = moebius_eval<T>(xs, 1, vs, 1, v.inverse ? T(-1) : T(1), d, max_radius, unit_sphere != 0, ys, 1);
-        for (int i = 0; i < d; ++i) v.y[(int64_t)b * v.ldy + v.col(f0 + i)] = ys[i];
-        return ld;
-    }
-    __device__ void backward(const TxView<T>& v, int b, int u, T gl) const {
-        const int f0 = v.fid(u * d);
-        T xs[16], vs[16], gys[16], gxs[16], gvs[16];
-        for (int i = 0; i < d; ++i) {
-            const int c = v.col(f0 + i);
-            xs[i] = v.x[(int64_t)b * v.ldx + c];
-            gys[i] = v.gy[(int64_t)b * v.ldgy + c];
-            vs[i] = v.par[v.poffset(b, f0 + i)];
-        }
-        moebius_vjp<T>(xs, 1, vs, 1, d, max_radius, unit_sphere != 0, gys, 1, gl, gxs, 1, gvs, 1);
-        for (int i = 0; i < d; ++i) {
-            v.gx[(int64_t)b * v.ldgx + v.col(f0 + i)] = gxs[i];
-            v.gpar[v.poffset(b, f0 + i)] = gvs[i];
-        }
-    }
-};
-
-template <typename T, int MAXK>
-struct SplineOp {
-    int K, circular, idslopes, learn_lo, learn_hi;
-    const T *x0, *xf, *y0, *yf;
-    T min_bin, min_slope;
-    int* bins; int64_t ldbins;
-
-    __device__ int units(int F) const { return F; }
-    __device__ SplineFeat<T> feat(int f) const {
-        SplineFeat<T> c;
-        c.K = K; c.circular = circular; c.idslopes = idslopes; c.learn_lo = learn_lo; c.learn_hi = learn_hi;
-        c.x0 = x0[f]; c.xf = xf[f]; c.y0 = y0[f]; c.yf = yf[f];
-        c.min_bin = min_bin; c.min_slope = min_slope;
-        return c;
-    }
-    __device__ T apply(const TxView<T>& v, int b, int u) const {
-        const int f = v.fid(u), col = v.col(f);
-        T out, ld;
-        int bin;
-        if (v.inverse) spline_eval<T, MAXK, true>(feat(f), v.pin(b, f), v.x[(int64_t)b * v.ldx + col], out, ld, bin);
-        else spline_eval<T, MAXK, false>(feat(f), v.pin(b, f), v.x[(int64_t)b * v.ldx + col], out, ld, bin);
-        v.y[(int64_t)b * v.ldy + col] = out;
-        if (bins != nullptr) bins[(int64_t)b * ldbins + f] = bin;
-        return ld;
-    }
-    __device__ void backward(const TxView<T>& v, int b, int u, T gl) const {
-        const int f = v.fid(u), col = v.col(f);
-        T gx;
-        spline_vjp<T, MAXK>(feat(f), v.pin(b, f), v.x[(int64_t)b * v.ldx + col], v.gy[(int64_t)b * v.ldgy + col], gl, gx,
-                            v.pout(b, f));
-        v.gx[(int64_t)b * v.ldgx + col] = gx;
-    }
-};
 
 template <typename T, typename Op>
 int run(const tfepb_tx_io* io, const tfepb_tx_grads* g, Op op, cudaStream_t s, const char* what) {

@@ -80,6 +80,7 @@ class MAF(AutoregressiveFlow):
         self._degrees_in_host = degrees_in.long().cpu().clone()
         self._packing = None
         self._fused = None
+        self._sweep = None
         #: 'fp32' (exact FFMA path, parity <= 1e-5 with the reference) or 'bf16' (fused tcgen05 tensor-core
         #: kernel: bf16 operands, fp32 accumulation and epilogue; inference only, see tfep_b200/_fused.py)
         self.precision = 'fp32'
@@ -170,6 +171,19 @@ class MAF(AutoregressiveFlow):
             raise NotImplementedError('Inversion of SOS polynomial transformer has not been implemented yet.')
         if torch.is_grad_enabled() and (y.requires_grad or any(p.requires_grad for p in self.parameters())):
             raise NotImplementedError('tfep_b200: MAF.inverse is not differentiable yet; call it under torch.no_grad()')
+        from ... import _sweep
+        if _sweep.eligibility(self, pk) is not None:
+            return self._inverse_host_sweep(y)
+        if self._sweep is None:
+            self._sweep = _sweep.SweepPlan(self, pk)
+        layouts, _ = self._packed_tables(y.device)
+        with torch.no_grad():
+            return self._sweep.inverse(self, y, layouts)
+
+    def _inverse_host_sweep(self, y: torch.Tensor):
+        """The same degree-ordered sweep driven from the host (four launches per degree); kept as the
+        cross-check of the persistent kernel (tests/test_gpu_maf.py)."""
+        pk = self._pack()
         y = y.contiguous()
         plan, parts, groups = pk['plan'], pk['parts'], pk['groups']
         layouts, gids = self._packed_tables(y.device)
