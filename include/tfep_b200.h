@@ -229,6 +229,45 @@ typedef struct {
 int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_stream_t stream);
 
 /* ----------------------------------------------------------------------------------------------
+ * Fused MAF INVERSE on the tensor cores, bf16 operands with fp32 accumulation, for a chain of n_layers >= 1
+ * MAF layers (given in the order they are inverted) in ONE launch: x, logdet = MAF.inverse(y) with a MADE of
+ * two hidden layers and a circular 8-bin neural spline, one feature per degree.  Replaces
+ * AutoregressiveFlow.inverse (nn/flows/autoregressive.py:179-229; n_degrees conditioner passes) by the
+ * degree-ordered sweep: per degree three small tcgen05 products whose A operands (x, h1, h2 of a 128-sample
+ * tile) stay resident in tensor memory; `ops` lists one weight block per product (same entry layout and
+ * block image as the forward kernel; a_col is the tensor-memory column of the operand: 64 x, 128 h1, 320 h2;
+ * tmem_col the accumulator: 0 output rows, 32 hidden units), `steps` one entry per degree.
+ * -------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t col;                         /* column of the feature of this degree in y / x */
+    float x0, period, inv_period, rescaled_width, rescaled_height, y0;
+    int32_t partner;                     /* other half of the bf16 pair column of x: 0 not known yet, 1 known, 2 constant one */
+    int32_t h1_first, h1_count, h2_first, h2_count;   /* packed hidden units computable after the feature (<= 15) */
+} tfepb_fused_inv_step;
+
+typedef struct {
+    const tfepb_fused_op* ops;           /* DEVICE array, 16-byte aligned */
+    const tfepb_fused_inv_step* steps;   /* DEVICE array, 16-byte aligned */
+    int32_t n_ops, n_steps;
+    const void* weights;                 /* device, packed bf16 blocks */
+    float min_bin_size, min_slope, slope_offset;
+    int32_t reserved;
+} tfepb_fused_inv_layer;
+
+typedef struct {
+    const void* y; void* x; void* logdet;          /* fp32 (batch, n_features), (batch, n_features), (batch,) */
+    int32_t batch, n_features;
+    int32_t k1, hidden_padded;
+    int32_t n_layers, reserved;
+    const tfepb_fused_inv_layer* layers;           /* HOST array of n_layers entries */
+    uint32_t* tile_flags;                          /* as for the forward kernel */
+    uint32_t epoch;
+    int32_t reserved2;
+    int32_t* error_flag;
+} tfepb_fused_inv_args;
+int tfepb_maf_spline_inverse_bf16(const tfepb_fused_inv_args* a, tfepb_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------------
  * Persistent inverse sweep of one MAF layer, exact fp32 / fp64 arithmetic: x, logdet = MAF.inverse(y).
  * Replaces AutoregressiveFlow.inverse (nn/flows/autoregressive.py:179-229), which runs n_degrees full
  * conditioner passes: with degree-sorted packed weights every unit is evaluated once, degree by degree,

@@ -112,6 +112,56 @@ def test_chain_launch_equals_layer_by_layer(batch):
     assert int(seq[0]._fused._tables(torch.device(DEV))['err'].item()) == 0
 
 
+@pytest.mark.parametrize('batch', [1, 129, 1000])
+def test_fused_inverse_layers(batch):
+    """tfepb_maf_spline_inverse_bf16, one layer (ascending and descending degrees): against the EXACT inverse
+    sweep of the same y (differences = bf16 operand rounding: same stated tolerance as the forward kernel)
+    and as the inverse of the fused forward (same roundings in both directions: tight, except for the few
+    samples whose x sits on a bf16 rounding boundary and flips the conditioner input)."""
+    seq, _ = cfg_flow_modules('cfg2', DEV, n_layers=2)
+    x = cases.cfg_input('cfg2', batch).to(DEV)
+    for maf in seq:
+        with torch.no_grad():
+            maf.precision = 'bf16'
+            y, ld = maf(x)
+            xi, ldi = maf.inverse(y)
+            xi2, ldi2 = maf.inverse(y)
+            maf.precision = 'fp32'
+            xe, lde = maf.inverse(y)
+        assert torch.equal(xi, xi2) and torch.equal(ldi, ldi2)
+        assert xi.shape == (batch, 66) and ldi.shape == (batch,)
+        assert float(_circ(xi, xe).max()) < 5e-2 and float(_circ(xi, xe).mean()) < 2e-3
+        assert float((ldi - lde).abs().max()) < 1e-1 and float((ldi - lde).abs().mean()) < 8e-3
+        d = _circ(xi, x).max(dim=1).values
+        assert float(d.median()) < 2e-5
+        assert float((d < 2e-2).float().mean()) > 0.97
+        assert float((ld + ldi).abs().median()) < 5e-5
+
+
+def test_fused_inverse_chain_round_trip():
+    """SequentialFlow.inverse with four bf16 layers = ONE launch of the inverse kernel (layers in reverse
+    order, per-tile flags), bit-identical to one launch per layer; round trip through the fused forward."""
+    seq, _ = cfg_flow_modules('cfg2', DEV)
+    x = cases.cfg_input('cfg2', 128 * 148 + 77).to(DEV)
+    for maf in seq:
+        maf.precision = 'bf16'
+    with torch.no_grad():
+        y, ld = seq(x)
+        xi, ldi = seq.inverse(y)
+        cur, tot = y, None
+        for maf in reversed(seq):
+            cur, l = maf.inverse(cur)
+            tot = l if tot is None else tot + l
+    assert torch.equal(xi, cur)
+    assert float((ldi - tot).abs().max()) < 1e-5
+    d = _circ(xi, x).max(dim=1).values
+    assert float(d.median()) < 1e-4
+    assert float((d < 5e-2).float().mean()) > 0.9
+    assert float((ld + ldi).abs().median()) < 2e-4
+    assert bool(torch.isfinite(xi).all()) and bool(torch.isfinite(ldi).all())
+    assert int(seq[0]._fused._tables(torch.device(DEV))['err'].item()) == 0
+
+
 def test_inference_only_and_eligibility():
     from tfep_b200._lib import TfepB200Error
     from tfep_b200.nn.conditioners import generate_degrees

@@ -37,6 +37,8 @@ PSTRIDE = 28
 CHUNK_N = FEATS_PER_CHUNK * PSTRIDE
 ACC_BUFS = 3
 MAX_LAYERS, MAX_OPS = 8, 512
+INV_STAGE_BYTES = 24576
+INV_ACC_OUT, INV_ACC_HID, INV_A0_COL, INV_A1_COL, INV_A2_COL = 0, 32, 64, 128, 320
 KB_OUT = 128
 KB_HID = 80
 LOG2E = 1.4426950408889634
@@ -49,6 +51,9 @@ OP_DTYPE = np.dtype([('w_off', '<u4'), ('idesc', '<u4'), ('n', '<u2'), ('tmem_co
 def _idesc(n):
     """kind::f16 instruction descriptor: D = fp32 (bit 4), A = B = bf16 (bits 7, 10), K-major, N >> 3 at 17, M >> 4 at 24."""
     return (1 << 4) | (1 << 7) | (1 << 10) | ((n >> 3) << 17) | ((TILE_M >> 4) << 24)
+STEP_DTYPE = np.dtype([('col', '<i4'), ('x0', '<f4'), ('period', '<f4'), ('inv_period', '<f4'), ('rw', '<f4'), ('rh', '<f4'),
+                       ('y0', '<f4'), ('partner', '<i4'), ('h1_first', '<i4'), ('h1_count', '<i4'), ('h2_first', '<i4'),
+                       ('h2_count', '<i4')])
 FEAT_DTYPE = np.dtype([('col', '<i4'), ('x0', '<f4'), ('period', '<f4'), ('inv_period', '<f4'), ('rw', '<f4'),
                        ('rh', '<f4'), ('y0', '<f4'), ('reserved', '<f4')])
 
@@ -106,6 +111,8 @@ class FusedSplinePlan:
         cols = part.x_columns().tolist()
         deg_in = maf._degrees_in_host
         order = sorted(range(part.n_features), key=lambda f: (int(deg_in[cols[f]]), cols[f]))
+        self._order = order
+        self._inv, self._inv_why = None, None
         self.n_chunks = math.ceil(len(order) / FEATS_PER_CHUNK)
         ref_cols = part.ref_columns()                       # (F, 25) rows of the reference output layer
         x0, xf, y0, yf = (b.detach().float().cpu() for b in (t.x0, t.xf, t._y0, t._yf))
@@ -233,10 +240,108 @@ class FusedSplinePlan:
             W3p = torch.zeros(len(rows), HP, device=dev)
             W3p[:, 2:2 + H] = w3e.index_select(0, safe).index_select(1, tb['perm2']) * (scale / LOG2E)[:, None]
             W3p[:, 0], W3p[:, 1] = hi_lo(b3e.index_select(0, safe) * scale)
-            src = torch.cat([W1p.flatten(), W2p.flatten(), W3p.flatten()]).to(torch.bfloat16)
+            # the trailing zero is what padding rows of the inverse blocks point at
+            src = torch.cat([W1p.flatten(), W2p.flatten(), W3p.flatten(), torch.zeros(1, device=dev)]).to(torch.bfloat16)
             packed = src.index_select(0, tb['gather']).contiguous()
-        self._cache = (key, packed)
+        self._cache = (key, packed, src)
         return self._cache[1]
+
+    # ---------------------------------------------------------------------------------------------
+    # inverse direction (tfepb_maf_spline_inverse_bf16): one block per product of the degree sweep
+    # ---------------------------------------------------------------------------------------------
+    def inverse_eligibility(self):
+        if self._inv is False:
+            return self._inv_why
+        return None
+
+    def _build_inverse(self, maf):
+        """Schedule, step table and gather indices of the degree-ordered sweep (host integer work, once)."""
+        pk = maf._pack()
+        plan = pk['plan']
+        deg_in = maf._degrees_in_host
+        deg_h1, deg_h2 = plan.packed_degrees[1], plan.packed_degrees[2]
+        part = pk['parts'][0]
+        cols = part.x_columns().tolist()
+        order = self._order
+        why = None
+        if int(deg_in.min()) < 0:
+            why = 'conditioning features (degree -1)'
+        degs = [int(deg_in[cols[f]]) for f in order]
+        if why is None and any(b <= a for a, b in zip(degs, degs[1:])):
+            why = 'more than one feature per degree'
+        if self.K1 > 128 or self.HP > 352:
+            why = 'layer widths exceed the tensor-memory plan of the inverse kernel'
+        ops, steps, gather = [], [], []
+        off1, off2 = self.HP * self.K1, self.HP * self.K1 + self.HP * self.HP
+        zero_idx = off2 + len(self.w3_rows) * self.HP
+        w_off = 0
+
+        def add(rows, n, kmax, a_col, tmem_col, base, ld):
+            nonlocal w_off
+            ksteps = kmax // 16
+            r = torch.full((n,), -1, dtype=torch.long)
+            r[:len(rows)] = torch.as_tensor(rows, dtype=torch.long)
+            ks = torch.arange(kmax)
+            idx = base + r[:, None] * ld + ks[None, :]
+            idx = torch.where(r[:, None] < 0, torch.full_like(idx, zero_idx), idx)
+            gather.append(idx.reshape(n, 2 * ksteps, 8).permute(1, 0, 2).reshape(-1))
+            nbytes = n * kmax * 2
+            assert nbytes <= INV_STAGE_BYTES and nbytes % 16 == 0
+            ops.append((w_off, _idesc(n), n, tmem_col, a_col, ksteps, 0))
+            w_off += nbytes
+
+        D = self.D
+        for si, f in enumerate(order if why is None else []):
+            d = degs[si]
+            c, j = divmod(si, FEATS_PER_CHUNK)
+            r0 = c * CHUNK_N + j * PSTRIDE
+            kmax = _ceil16(2 + int((deg_h2 < d).sum()))
+            add(list(range(r0, r0 + NPAR)), 32, kmax, INV_A2_COL, INV_ACC_OUT, off2, self.HP)
+            u1 = (deg_h1 == d).nonzero().flatten()
+            u2 = (deg_h2 == d).nonzero().flatten()
+            last = si == len(order) - 1
+            h1 = (0, 0) if (last or len(u1) == 0) else (2 + int(u1[0]), len(u1))
+            h2 = (0, 0) if (last or len(u2) == 0) else (2 + int(u2[0]), len(u2))
+            if h1[1] > 15 or h2[1] > 15:
+                why = 'more than 15 hidden units of one degree'
+                break
+            if h1[1]:
+                assert torch.equal(u1, torch.arange(int(u1[0]), int(u1[0]) + len(u1)))
+                add(list(range(h1[0], h1[0] + h1[1])), 16, self.K1, INV_A0_COL, INV_ACC_HID, 0, self.K1)
+            if h2[1]:
+                assert torch.equal(u2, torch.arange(int(u2[0]), int(u2[0]) + len(u2)))
+                kmax2 = _ceil16(2 + int((deg_h1 <= d).sum()))
+                add(list(range(h2[0], h2[0] + h2[1])), 16, kmax2, INV_A1_COL, INV_ACC_HID, off1, self.HP)
+            col = cols[f]
+            pc = col ^ 1
+            partner = 2 if pc == D else (0 if pc > D else (1 if int(deg_in[pc]) < d else 0))
+            ft = self.feats_host[si]
+            steps.append((col, ft['x0'], ft['period'], ft['inv_period'], ft['rw'], ft['rh'], ft['y0'], partner,
+                          h1[0], h1[1], h2[0], h2[1]))
+        if why is not None:
+            self._inv, self._inv_why = False, why
+            return
+        self._inv = dict(ops=np.array(ops, dtype=OP_DTYPE), steps=np.array(steps, dtype=STEP_DTYPE),
+                         gather=torch.cat(gather), dev={}, cache=None)
+
+    def inverse_tables(self, maf, device):
+        """(ops, steps, packed weights) on the device for the current parameters."""
+        if self._inv is None:
+            self._build_inverse(maf)
+        if self._inv is False:
+            raise _lib.TfepB200Error(f'fused bf16 inverse unavailable: {self._inv_why}')
+        inv = self._inv
+        key = str(device)
+        if key not in inv['dev']:
+            inv['dev'][key] = dict(ops=torch.from_numpy(inv['ops'].view(np.uint8).reshape(-1).copy()).to(device),
+                                   steps=torch.from_numpy(inv['steps'].view(np.uint8).reshape(-1).copy()).to(device),
+                                   gather=inv['gather'].to(device))
+        tb = inv['dev'][key]
+        self.pack(maf)                                   # refreshes the padded source matrices if parameters changed
+        ver, _, src = self._cache
+        if inv['cache'] is None or inv['cache'][0] != (ver, key):
+            inv['cache'] = ((ver, key), src.index_select(0, tb['gather']).contiguous())
+        return tb['ops'], tb['steps'], inv['cache'][1]
 
     def forward(self, maf, x, debug_params=None):
         """y, log_det_J = fused layer on a contiguous fp32 CUDA tensor (no autograd)."""
@@ -290,3 +395,45 @@ def run_chain(plans_mafs, x, debug_params=None):
     with torch.cuda.device(x.device):
         check(_lib.load().tfepb_maf_spline_forward_bf16(ctypes.byref(args), stream_ptr(x)))
     return y, ld
+
+
+def run_inverse_chain(plans_mafs, y):
+    """One launch for the inverse of a chain of fused MAF layers, given in the order they are inverted:
+    x, sum of log_det_J (reference sequential.py:50-68 with inverse=True)."""
+    _lib.require_cuda(y)
+    if y.dtype != torch.float32:
+        raise _lib.TfepB200Error('the fused bf16 path takes float32 inputs')
+    n_layers = len(plans_mafs)
+    first = plans_mafs[0][0]
+    if n_layers > MAX_LAYERS:
+        raise _lib.TfepB200Error('chain too long for one fused launch')
+    if any((pl.D, pl.K1, pl.HP) != (first.D, first.K1, first.HP) for pl, _ in plans_mafs):
+        raise _lib.TfepB200Error('fused chain needs layers of identical widths')
+    y = y.contiguous()
+    B = y.shape[0]
+    x = torch.empty_like(y)
+    ld = torch.empty(B, dtype=torch.float32, device=y.device)
+    layers = (_lib.FusedInvLayer * n_layers)()
+    keep = []
+    for i, (pl, maf) in enumerate(plans_mafs):
+        ops, steps, packed = pl.inverse_tables(maf, y.device)
+        keep.append((ops, steps, packed))
+        layers[i] = _lib.FusedInvLayer(ops=ops.data_ptr(), steps=steps.data_ptr(), n_ops=len(pl._inv['ops']),
+                                       n_steps=len(pl._inv['steps']), weights=packed.data_ptr(), min_bin_size=pl.min_bin,
+                                       min_slope=pl.min_slope, slope_offset=pl.slope_offset, reserved=0)
+    tb = first._tables(y.device)
+    flags = None
+    if n_layers > 1:
+        need = (n_layers - 1) * ((B + TILE_M - 1) // TILE_M)
+        key = ('flags', torch.cuda.current_stream(y.device).cuda_stream)
+        flags = tb.get(key)
+        if flags is None or flags.numel() < need:
+            flags = tb[key] = torch.zeros(max(need, 4096), dtype=torch.int32, device=y.device)
+    _EPOCH[0] = (_EPOCH[0] % 0x7fffffff) + 1
+    args = _lib.FusedInvArgs(y=y.data_ptr(), x=x.data_ptr(), logdet=ld.data_ptr(), batch=B, n_features=first.D,
+                             k1=first.K1, hidden_padded=first.HP, n_layers=n_layers, reserved=0, layers=layers,
+                             tile_flags=None if flags is None else flags.data_ptr(), epoch=_EPOCH[0], reserved2=0,
+                             error_flag=tb['err'].data_ptr())
+    with torch.cuda.device(y.device):
+        check(_lib.load().tfepb_maf_spline_inverse_bf16(ctypes.byref(args), stream_ptr(y)))
+    return x, ld

@@ -76,6 +76,18 @@ class FusedArgs(Structure):
                 ('error_flag', c_void_p), ('debug_params', c_void_p)]
 
 
+class FusedInvLayer(Structure):
+    _fields_ = [('ops', c_void_p), ('steps', c_void_p), ('n_ops', c_int32), ('n_steps', c_int32), ('weights', c_void_p),
+                ('min_bin_size', c_float), ('min_slope', c_float), ('slope_offset', c_float), ('reserved', c_int32)]
+
+
+class FusedInvArgs(Structure):
+    _fields_ = [('y', c_void_p), ('x', c_void_p), ('logdet', c_void_p), ('batch', c_int32), ('n_features', c_int32),
+                ('k1', c_int32), ('hidden_padded', c_int32), ('n_layers', c_int32), ('reserved', c_int32),
+                ('layers', POINTER(FusedInvLayer)), ('tile_flags', c_void_p), ('epoch', c_uint32), ('reserved2', c_int32),
+                ('error_flag', c_void_p)]
+
+
 class SweepArgs(Structure):
     _fields_ = [('dtype', c_int32), ('batch', c_int32), ('n_features', c_int32), ('n_linear', c_int32),
                 ('y', c_void_p), ('ldy', c_int64), ('x', c_void_p), ('ldx', c_int64), ('logdet', c_void_p),
@@ -102,6 +114,7 @@ SYMBOLS = {
     'tfepb_sos_backward': (c_int32, [POINTER(TxIo), c_int32, POINTER(TxGrads), c_void_p]),
     'tfepb_moebius_backward': (c_int32, [POINTER(TxIo), c_int32, c_double, c_int32, POINTER(TxGrads), c_void_p]),
     'tfepb_maf_spline_forward_bf16': (c_int32, [POINTER(FusedArgs), c_void_p]),
+    'tfepb_maf_spline_inverse_bf16': (c_int32, [POINTER(FusedInvArgs), c_void_p]),
     'tfepb_maf_inverse_sweep': (c_int32, [POINTER(SweepArgs), c_void_p]),
     'tfepb_lse_workspace_bytes': (c_int64, []),
     'tfepb_lse': (c_int32, [c_int32, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p]),

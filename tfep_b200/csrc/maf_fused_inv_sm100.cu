@@ -1,0 +1,508 @@
+// Fused MAF INVERSE for sm_100a: the degree-ordered sweep of MAF.inverse on tcgen05 tensor cores, for a chain
+// of MAF layers in one persistent launch (bf16 operands, fp32 accumulation and epilogue).
+//
+//   x, logdet = MAF.inverse(y)          (reference: nn/flows/autoregressive.py:179-229 -- n_degrees full
+//                                         conditioner passes; chained in reverse as nn/flows/sequential.py:50-68)
+//
+// Inverting an autoregressive flow is sequential over the degrees: the spline parameters of the feature of
+// degree d need the hidden units of degree < d, which need x of degree < d.  With degree-sorted hidden units
+// every unit is computed once (tfep_b200/_pack.py), so per degree there are three small dependent products
+//
+//   OUT_d : par_d (25 rows, padded to 32) = W3[feature d] . h2[units of degree < d]     -> spline inverse -> x_d
+//   H1_d  : h1[units of degree d] (<= 15, padded to 16) = ELU(W1[those rows] . x)        -> A1 operand
+//   H2_d  : h2[units of degree d]                       = ELU(W2[those rows] . h1[<= d]) -> A2 operand
+//
+// each a handful of tcgen05.mma instructions (M = 128 samples, N = 32 / 16, K up to 336) whose A operands
+// -- x, h1 and h2 of the 128-sample tile -- stay RESIDENT IN TENSOR MEMORY for the whole sweep and grow
+// in place, column by column, as the epilogue warpgroup produces them.  The weight blocks (bias folded in,
+// log2(e) pre-scalings as in the forward kernel, maf_fused_sm100.cu) stream from L2 through the bulk-copy
+// ring in the order they are needed; the 3 x D steps of a layer form one dependent chain, so the kernel is
+// latency bound and one CTA per SM runs one tile.  Work items are (layer, tile) pairs, layer-major, with
+// per-tile flags between the layers exactly as in the forward kernel.
+//
+// Warp roles: warp 0 = TMEM allocator + bulk-copy producer, warp 1 = MMA issuer, warp 2 = x store / log-det /
+// publish, warp 3 idle, warps 4..7 = epilogue (thread <-> sample row <-> TMEM lane).
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+#include <string.h>
+
+namespace tfepb {
+namespace finv {
+
+using namespace tc;
+
+constexpr int THREADS = 256;
+constexpr int EPI_THREADS = 128;
+constexpr int STAGES = 4;
+constexpr int STAGE_BYTES = 24576;              // largest block: 32 rows x 336 k x 2 B = 21 KB
+constexpr int NPAR = 25;
+constexpr int ACC_OUT = 0, ACC_HID = 32;        // accumulator columns
+constexpr int A0_COL = 64, A1_COL = 128, A2_COL = 320;   // bf16 A operands: x (<= 64 cols), h1, h2 (<= 184 cols)
+constexpr int MAX_LAYERS = TFEPB_FUSED_MAX_LAYERS;
+
+struct __align__(16) Op {   // same layout as tfepb_fused_op; a_col = absolute TMEM column of the A operand
+    uint32_t w_off, idesc;
+    uint16_t n, tmem_col, a_col;
+    uint8_t ksteps, flags;
+};
+
+struct __align__(16) Step {  // one degree of the sweep (tfepb_fused_inv_step)
+    int col;                 // column of the feature in y / x
+    float x0, L, invL, Rw, Rh, y0;
+    int partner;             // the other half of the bf16 pair column (col ^ 1): 0 unknown yet (zero), 1 already
+                             // inverted (read it back), 2 the constant-one bias column
+    int h1_a, h1_n, h2_a, h2_n;   // packed positions of the hidden units that become computable (n = 0: none)
+};
+
+struct LayerP {
+    const uint8_t* weights;
+    const Op* ops;           // device
+    const Step* steps;       // device
+    int n_ops, n_steps;
+    float min_bin, min_slope, slope_offset2;
+};
+
+struct Params {
+    const float* y; float* x; float* logdet;
+    int batch, D, K1, HP, n_layers, n_tiles;
+    uint32_t* flags; uint32_t epoch;
+    int* error;
+    LayerP layers[MAX_LAYERS];
+};
+
+struct Smem {
+    uint64_t w_full[STAGES], w_empty[STAGES];
+    uint64_t x_full[2], x_empty[2], y_ready[2], a_ready, acc_full;
+    uint32_t tmem_base;
+    uint32_t pad[3];
+};
+
+// Inverse of the circular 8-bin spline for one feature of one sample (reference nn/transformers/spline.py:
+// 504-543, 257-259).  r[0..24] as in the forward epilogue (log2-domain widths / heights / slopes, shift).
+// Returns log|dx/dy|.
+__device__ __forceinline__ float spline8_circular_inverse(const uint32_t (&r)[32], float yv, const Step& fc, float min_bin,
+                                                          float min_slope, float slope_offset2, float& x) {
+    float p[NPAR];
+#pragma unroll
+    for (int i = 0; i < NPAR; ++i) p[i] = __uint_as_float(r[i]);
+    float t = yv - fc.y0;
+    t = fminf(fmaxf(t, 0.f), fc.L);
+    float mw = fmaxf(fmaxf(fmaxf(p[0], p[1]), fmaxf(p[2], p[3])), fmaxf(fmaxf(p[4], p[5]), fmaxf(p[6], p[7])));
+    float mh = fmaxf(fmaxf(fmaxf(p[8], p[9]), fmaxf(p[10], p[11])), fmaxf(fmaxf(p[12], p[13]), fmaxf(p[14], p[15])));
+    float ew[8], eh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        ew[k] = ex2(p[k] - mw);
+        eh[k] = ex2(p[8 + k] - mh);
+    }
+    const float sw = ((ew[0] + ew[1]) + (ew[2] + ew[3])) + ((ew[4] + ew[5]) + (ew[6] + ew[7]));
+    const float sh = ((eh[0] + eh[1]) + (eh[2] + eh[3])) + ((eh[4] + eh[5]) + (eh[6] + eh[7]));
+    const float rw = fc.Rw * rcp(sw), rh = fc.Rh * rcp(sh);
+    // walk the knots along y: last bin whose bottom knot is below t (same knot arithmetic as the forward kernel)
+    float wk = fmaf(ew[0], rw, min_bin), hk = fmaf(eh[0], rh, min_bin);
+    float left = wk, bottom = hk, w_sel = wk, h_sel = hk, xk = 0.f, yk = 0.f;
+    float raw0 = p[16], raw1 = p[17];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        if (k > 0) { left += wk; bottom += hk; }
+        wk = fmaf(ew[k + 1], rw, min_bin);
+        hk = fmaf(eh[k + 1], rh, min_bin);
+        const bool adv = t > bottom;
+        w_sel = adv ? wk : w_sel;
+        h_sel = adv ? hk : h_sel;
+        xk = adv ? left : xk;
+        yk = adv ? bottom : yk;
+        raw0 = adv ? p[16 + k + 1] : raw0;
+        raw1 = adv ? p[16 + ((k + 2) & 7)] : raw1;
+    }
+    const float dk = softplus_l2(raw0 + slope_offset2) + min_slope;
+    const float dk1 = softplus_l2(raw1 + slope_offset2) + min_slope;
+    const float s = h_sel * rcp(w_sel);
+    const float yr = t - yk;
+    const float q = dk1 + dk - 2.f * s;
+    const float a = fmaf(h_sel, s - dk, yr * q);
+    const float b = fmaf(h_sel, dk, -yr * q);
+    const float c = -s * yr;
+    const float disc = fmaxf(fmaf(b, b, -4.f * a * c), 0.f);
+    const float e = 2.f * c * rcp(-b - sqrt_approx(disc));
+    const float ome = 1.f - e, u = e * ome, e2 = e * e;
+    const float den = fmaf(q, u, s);
+    const float iden = rcp(den);
+    const float nn = fmaf(dk1, e2, fmaf(2.f * s, u, dk * ome * ome));
+    const float rr = s * iden;
+    // un-shift and wrap into [x0, x0 + L)
+    float xr = fmaf(e, w_sel, xk) - p[24];
+    xr = xr - fc.L * floorf(xr * fc.invL);
+    xr = (xr < 0.f) ? xr + fc.L : xr;
+    xr = (xr >= fc.L) ? xr - fc.L : xr;
+    x = fc.x0 + xr;
+    return -LN2 * lg2(nn * rr * rr);
+}
+
+__device__ __forceinline__ float elu_l2(float t, float l2e) { return fmaxf(t, fmaf(ex2(fminf(t, 0.f)), l2e, -LOG2E)); }
+
+__global__ void __launch_bounds__(THREADS, 1) maf_spline_inv_kernel(const __grid_constant__ Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* sW = smem_raw;
+    float* sX0 = reinterpret_cast<float*>(sW + (size_t)STAGES * STAGE_BYTES);   // two y / x tiles, row-major [128][D]
+    const int x_tile_bytes = TILE_M * p.D * 4;
+    const int x_tile_stride = (x_tile_bytes + 127) & ~127;
+    float* sLd = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sX0) + 2 * x_tile_stride);   // [2][128]
+    Smem* sm = reinterpret_cast<Smem*>(sLd + 2 * TILE_M);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_tiles = p.n_tiles;
+    const int n_items = p.n_layers * n_tiles;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&sm->w_full[s], 1); mbar_init(&sm->w_empty[s], 1); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&sm->x_full[b], 1); mbar_init(&sm->x_empty[b], 1); mbar_init(&sm->y_ready[b], EPI_THREADS);
+        }
+        mbar_init(&sm->a_ready, EPI_THREADS);
+        mbar_init(&sm->acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(&sm->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm->tmem_base;
+
+    if (warp == 0) {
+        // =========================== producer: input tiles + weight blocks ===========================
+        uint32_t stage = 0, wphase = 0, tcount = 0;
+        auto flag_of = [&](int item) -> const uint32_t* {
+            const int layer = item / n_tiles, tile = item - layer * n_tiles;
+            return layer == 0 ? nullptr : p.flags + (size_t)(layer - 1) * n_tiles + tile;
+        };
+        auto request_x = [&](int item, uint32_t t) {
+            const int layer = item / n_tiles, tile = item - layer * n_tiles;
+            const int rows = min(TILE_M, p.batch - tile * TILE_M);
+            const uint32_t b = t & 1;
+            const float* src = layer == 0 ? p.y : p.x;
+            if (layer > 0) {
+                const uint32_t* flag = flag_of(item);
+                uint32_t polls = 0;
+                long long t0 = 0;
+                while (ld_acquire_gpu(flag) != p.epoch) {
+                    if ((++polls & 0xffu) != 0) continue;
+                    if (t0 == 0) t0 = clock64();
+                    if ((uint64_t)(clock64() - t0) > WATCHDOG_CYCLES) {
+                        if (p.error) atomicExch(p.error, 9);
+                        __threadfence_system();
+                        __trap();
+                    }
+                }
+                fence_proxy_async();
+            }
+            mbar_wait(&sm->x_empty[b], ((t >> 1) & 1) ^ 1, p.error, 1);
+            if (elect_one()) {
+                float* dst = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sX0) + b * x_tile_stride);
+                if (rows == TILE_M) {
+                    mbar_expect_tx(&sm->x_full[b], (uint32_t)x_tile_bytes);
+                    bulk_g2s(dst, src + (size_t)tile * TILE_M * p.D, (uint32_t)x_tile_bytes, &sm->x_full[b]);
+                } else {
+                    mbar_arrive(&sm->x_full[b]);    // ragged last tile: the epilogue warps copy it themselves
+                }
+            }
+            __syncwarp();
+        };
+        const bool far = n_tiles >= 2 * (int)gridDim.x;
+        bool need_x = true;
+        int layer = 0, tile = blockIdx.x;
+        while (layer < p.n_layers) {
+            const int item = layer * n_tiles + tile;
+            const int n_ops = p.layers[layer].n_ops;
+            const Op* ops = p.layers[layer].ops;
+            const uint8_t* weights = p.layers[layer].weights;
+            const int prefetch_at = n_ops > 8 ? 8 : n_ops - 1;
+            const int must_at = n_ops > STAGES - 1 ? STAGES - 1 : n_ops - 1;
+            for (int i = 0; i < n_ops; ++i) {
+                if (need_x) {
+                    const uint32_t* flag = flag_of(item);
+                    if (i == must_at || flag == nullptr || ld_acquire_gpu(flag) == p.epoch) {
+                        request_x(item, tcount);
+                        need_x = false;
+                    }
+                }
+                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(ops + i));
+                const uint32_t n = raw.z & 0xffffu, ksteps = (raw.w >> 16) & 0xffu;
+                const uint32_t bytes = n * ksteps * 32u;
+                mbar_wait(&sm->w_empty[stage], wphase ^ 1, p.error, 2);
+                if (elect_one()) {
+                    mbar_expect_tx(&sm->w_full[stage], bytes);
+                    bulk_g2s(sW + (size_t)stage * STAGE_BYTES, weights + raw.x, bytes, &sm->w_full[stage]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; wphase ^= 1; }
+                if (far && i == prefetch_at && item + (int)gridDim.x < n_items) request_x(item + gridDim.x, tcount + 1);
+            }
+            need_x = !far;
+            ++tcount;
+            tile += gridDim.x;
+            while (tile >= n_tiles) { tile -= n_tiles; ++layer; }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer: one dependent chain of small products ===========================
+        uint32_t stage = 0, wphase = 0, a_par = 0;
+        const uint32_t w_base16 = smem_u32(sW) >> 4;
+        int layer = 0, tile = blockIdx.x;
+        while (layer < p.n_layers) {
+            const int n_ops = p.layers[layer].n_ops;
+            const Op* ops = p.layers[layer].ops;
+            uint4 nxt = __ldg(reinterpret_cast<const uint4*>(ops));
+            for (int i = 0; i < n_ops; ++i) {
+                const uint4 raw = nxt;
+                if (i + 1 < n_ops) nxt = __ldg(reinterpret_cast<const uint4*>(ops + i + 1));
+                const uint32_t idesc = raw.y, n = raw.z & 0xffffu, d_col = raw.z >> 16, a_col = raw.w & 0xffffu;
+                const uint32_t ksteps = (raw.w >> 16) & 0xffu;
+                mbar_wait(&sm->a_ready, a_par, p.error, 3);          // every product needs what the previous one produced
+                a_par ^= 1u;
+                mbar_wait(&sm->w_full[stage], wphase, p.error, 5);
+                tc_fence_after();
+                const uint32_t b_lo = w_base16 + stage * (STAGE_BYTES >> 4) + (n << 16);
+                const uint32_t a_tmem = tmem + a_col, d_tmem = tmem + d_col;
+                if (elect_one()) {
+                    uint32_t accumulate = 0u;
+                    for (uint32_t ks = 0; ks < ksteps; ++ks) {
+                        const uint64_t db = ((uint64_t)DESC_HI << 32) | (b_lo + ks * 2u * n);
+                        umma_ts(d_tmem, a_tmem + ks * 8u, db, idesc, accumulate);
+                        accumulate = 1u;
+                    }
+                    umma_commit(&sm->w_empty[stage]);
+                    umma_commit(&sm->acc_full);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; wphase ^= 1; }
+            }
+            tile += gridDim.x;
+            while (tile >= n_tiles) { tile -= n_tiles; ++layer; }
+        }
+    } else if (warp == 2) {
+        // =========================== x store, log-det, publish ===========================
+        uint32_t tcount = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
+            const int layer = item / n_tiles, tile = item - layer * n_tiles;
+            const int rows = min(TILE_M, p.batch - tile * TILE_M);
+            const uint32_t xb = tcount & 1;
+            const float* sY = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(sX0) + xb * x_tile_stride);
+            mbar_wait(&sm->y_ready[xb], (tcount >> 1) & 1, p.error, 10);
+            float* dst = p.x + (size_t)tile * TILE_M * p.D;
+            if (rows == TILE_M) {
+                if (elect_one()) bulk_s2g(dst, sY, (uint32_t)x_tile_bytes);
+                __syncwarp();
+            }
+            const float* ldp = sLd + xb * TILE_M;
+#pragma unroll
+            for (int r = 0; r < TILE_M / 32; ++r) {
+                const int row = r * 32 + lane;
+                if (row < rows) {
+                    float v = ldp[row];
+                    float* out = p.logdet + (size_t)tile * TILE_M + row;
+                    if (layer > 0) v += __ldcg(out);
+                    *out = v;
+                }
+            }
+            if (rows < TILE_M) {
+                for (int i = lane; i < rows * p.D; i += 32) dst[i] = sY[i];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm->x_empty[xb]);
+            } else {
+                if (lane == 0) {
+                    bulk_wait_read();
+                    mbar_arrive(&sm->x_empty[xb]);
+                    if (layer + 1 < p.n_layers) bulk_wait_all();
+                }
+            }
+            __syncwarp();
+            if (layer + 1 < p.n_layers && lane == 0) {
+                fence_proxy_async();
+                __threadfence();
+                st_release_gpu(p.flags + (size_t)layer * n_tiles + tile, p.epoch);
+            }
+        }
+    } else if (warp >= 4) {
+        // =========================== epilogue warpgroup ===========================
+        const int et = tid - 128;                 // 0..127 = sample row = TMEM lane
+        const int row = et;
+        const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t acc_par = 0, tcount = 0;
+        float l2e;
+        asm volatile("mov.f32 %0, 0f3FB8AA3B;" : "=f"(l2e));
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tcount) {
+            const int layer = item / n_tiles, tile = item - layer * n_tiles;
+            const LayerP& L = p.layers[layer];
+            const int rows = min(TILE_M, p.batch - tile * TILE_M);
+            const uint32_t xb = tcount & 1;
+            float* sX = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sX0) + xb * x_tile_stride);
+            float* xrow = sX + row * p.D;
+            // ---- reset the A operands: zeros, the constant-one columns of x, h1 and h2 ----
+            {
+                uint32_t z[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) z[i] = 0u;
+                for (int c = 0; c < p.K1 / 2; c += 8) tmem_st8(lane_addr + A0_COL + c, z);
+                for (int c = 0; c < p.HP / 2; c += 8) {
+                    tmem_st8(lane_addr + A1_COL + c, z);
+                    tmem_st8(lane_addr + A2_COL + c, z);
+                }
+                tmem_st_wait();
+                const uint32_t one2 = pack_bf16(1.f, 1.f);
+                if (p.D & 1) {
+                    tmem_st1(lane_addr + A0_COL + p.D / 2, pack_bf16(0.f, 1.f));     // columns D (high half), D + 1
+                    tmem_st1(lane_addr + A0_COL + p.D / 2 + 1, pack_bf16(1.f, 0.f));
+                } else {
+                    tmem_st1(lane_addr + A0_COL + p.D / 2, one2);
+                }
+                tmem_st1(lane_addr + A1_COL, one2);
+                tmem_st1(lane_addr + A2_COL, one2);
+                tmem_st_wait();
+            }
+            mbar_wait(&sm->x_full[xb], (tcount >> 1) & 1, p.error, 6);
+            if (rows < TILE_M) {
+                const float* src = (layer == 0 ? p.y : p.x) + (size_t)tile * TILE_M * p.D;
+                for (int i = et; i < TILE_M * p.D; i += EPI_THREADS) sX[i] = i < rows * p.D ? __ldcg(src + i) : 0.f;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            tc_fence_before();
+            mbar_arrive(&sm->a_ready);
+            // ---- degree sweep ----
+            float ld = 0.f;
+            float open1 = 0.f, open2 = 0.f;          // last unit written to an odd-length prefix of h1 / h2 (low half of a pair)
+            const int n_steps = L.n_steps;
+            const float min_bin = L.min_bin, min_slope = L.min_slope, slope_offset2 = L.slope_offset2;
+            for (int d = 0; d < n_steps; ++d) {
+                const Step st = L.steps[d];
+                // OUT_d: parameters of the feature -> x_d
+                mbar_wait(&sm->acc_full, acc_par, p.error, 8);
+                acc_par ^= 1u;
+                tc_fence_after();
+                {
+                    uint32_t r[32];
+                    tmem_ld16(lane_addr + ACC_OUT, r);
+                    tmem_ld8(lane_addr + ACC_OUT + 16, r + 16);
+                    tmem_ld1(lane_addr + ACC_OUT + 24, r + 24);
+                    tmem_wait8(r); tmem_wait8(r + 8); tmem_wait8(r + 16); tmem_wait1(r + 24);
+                    float xv;
+                    ld += spline8_circular_inverse(r, xrow[st.col], st, min_bin, min_slope, slope_offset2, xv);
+                    xrow[st.col] = xv;
+                    // bf16 pair column of the x operand: the partner is known (already x) or still zero
+                    const float other = st.partner == 1 ? xrow[st.col ^ 1] : (st.partner == 2 ? 1.f : 0.f);
+                    const uint32_t q = (st.col & 1) ? pack_bf16(other, xv) : pack_bf16(xv, other);
+                    tmem_st1(lane_addr + A0_COL + (st.col >> 1), q);
+                    tmem_st_wait();
+                }
+                // one hand-over per product that follows in this item (the last x of a tile has no consumer)
+                const bool last = d + 1 == n_steps;
+                tc_fence_before();
+                if (st.h1_n != 0 || st.h2_n != 0 || !last) mbar_arrive(&sm->a_ready);
+                // H1_d, H2_d: the hidden units of this degree -> A operands (up to 15 units, 8 pair columns; the
+                // padding rows of the block give exact zeros, which is what the not-yet-known units must hold)
+#pragma unroll
+                for (int hl = 0; hl < 2; ++hl) {
+                    const int ha = hl == 0 ? st.h1_a : st.h2_a, hn = hl == 0 ? st.h1_n : st.h2_n;
+                    if (hn == 0) continue;
+                    mbar_wait(&sm->acc_full, acc_par, p.error, 7);
+                    acc_par ^= 1u;
+                    tc_fence_after();
+                    uint32_t r[16];
+                    tmem_ld16(lane_addr + ACC_HID, r);
+                    tmem_wait8(r); tmem_wait8(r + 8);
+                    float v[17];
+                    float& open = hl == 0 ? open1 : open2;
+                    const int odd = ha & 1;
+                    v[0] = open;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i + 1] = elu_l2(__uint_as_float(r[i]), l2e);
+                    // units ha .. ha + hn - 1 = v[1 .. hn]; pair columns start at ha / 2
+                    uint32_t q[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float lo = odd ? v[2 * i] : v[2 * i + 1];
+                        const float hi = odd ? v[2 * i + 1] : (2 * i + 2 <= 16 ? v[2 * i + 2] : 0.f);
+                        q[i] = pack_bf16(lo, hi);
+                    }
+                    // remember the last unit if it opens a new pair column (its partner arrives with the next degree)
+                    {
+                        float last = 0.f;
+#pragma unroll
+                        for (int i = 1; i <= 16; ++i) last = (i == hn) ? v[i] : last;
+                        open = ((ha + hn) & 1) ? last : 0.f;
+                    }
+                    tmem_st8(lane_addr + (hl == 0 ? A1_COL : A2_COL) + (ha >> 1), q);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    if ((hl == 0 && st.h2_n != 0) || !last) mbar_arrive(&sm->a_ready);
+                }
+            }
+            sLd[xb * TILE_M + row] = ld;
+            fence_async_smem();
+            mbar_arrive(&sm->y_ready[xb]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+size_t smem_bytes(const Params& p) {
+    size_t s = (size_t)STAGES * STAGE_BYTES;
+    s += 2 * (((size_t)TILE_M * p.D * 4 + 127) & ~(size_t)127);
+    s += 2 * TILE_M * 4 + sizeof(Smem);
+    return s + 256;
+}
+
+}  // namespace finv
+}  // namespace tfepb
+
+using namespace tfepb;
+
+static_assert(sizeof(finv::Op) == sizeof(tfepb_fused_op), "schedule entry layout mismatch");
+static_assert(sizeof(finv::Step) == sizeof(tfepb_fused_inv_step), "step table layout mismatch");
+
+extern "C" int tfepb_maf_spline_inverse_bf16(const tfepb_fused_inv_args* a, tfepb_stream_t stream) {
+    TFEPB_CHECK_ARG(a != nullptr, "null argument struct");
+    TFEPB_CHECK_ARG(a->y && a->x && a->logdet && a->layers, "null buffer");
+    TFEPB_CHECK_ARG(a->batch >= 0 && a->n_features > 0, "bad sizes");
+    TFEPB_CHECK_ARG(a->n_layers >= 1 && a->n_layers <= finv::MAX_LAYERS, "n_layers must be in [1, %d]", finv::MAX_LAYERS);
+    TFEPB_CHECK_ARG(a->n_layers == 1 || a->tile_flags != nullptr, "a chain of layers needs the tile_flags workspace");
+    TFEPB_CHECK_ARG(a->k1 % 16 == 0 && a->k1 >= a->n_features + 2 && a->k1 <= 2 * (finv::A1_COL - finv::A0_COL),
+                    "k1 must hold n_features + 2 bias columns, rounded up to 16, and fit the tensor-memory plan");
+    TFEPB_CHECK_ARG(a->hidden_padded % 16 == 0 && a->hidden_padded > 0 && a->hidden_padded <= 352,
+                    "hidden width (padded) must be a multiple of 16 and at most 352 (tensor-memory plan)");
+    TFEPB_CHECK_ARG((a->n_features * 4 * tc::TILE_M) % 16 == 0, "tile of y must be a multiple of 16 bytes");
+    TFEPB_CHECK_ARG(((uintptr_t)a->y % 16 == 0) && ((uintptr_t)a->x % 16 == 0), "y and x must be 16-byte aligned");
+    if (int rc = require_sm100()) return rc;
+    if (a->batch == 0) return 0;
+    finv::Params p{};
+    p.y = (const float*)a->y; p.x = (float*)a->x; p.logdet = (float*)a->logdet;
+    p.batch = a->batch; p.D = a->n_features; p.K1 = a->k1; p.HP = a->hidden_padded;
+    p.n_layers = a->n_layers;
+    p.n_tiles = (a->batch + tc::TILE_M - 1) / tc::TILE_M;
+    p.flags = a->tile_flags; p.epoch = a->epoch; p.error = a->error_flag;
+    for (int l = 0; l < a->n_layers; ++l) {
+        const tfepb_fused_inv_layer& s = a->layers[l];
+        TFEPB_CHECK_ARG(s.ops && s.steps && s.weights, "layer %d: null buffer", l);
+        TFEPB_CHECK_ARG(s.n_ops > 0 && s.n_steps > 0, "layer %d: empty schedule", l);
+        TFEPB_CHECK_ARG((uintptr_t)s.weights % 16 == 0 && (uintptr_t)s.ops % 16 == 0 && (uintptr_t)s.steps % 16 == 0,
+                        "layer %d: tables and packed weights must be 16-byte aligned", l);
+        finv::LayerP& d = p.layers[l];
+        d.weights = (const uint8_t*)s.weights;
+        d.ops = (const finv::Op*)s.ops; d.steps = (const finv::Step*)s.steps;
+        d.n_ops = s.n_ops; d.n_steps = s.n_steps;
+        d.min_bin = s.min_bin_size; d.min_slope = s.min_slope; d.slope_offset2 = s.slope_offset * tc::LOG2E;
+    }
+    const size_t smem = finv::smem_bytes(p);
+    TFEPB_CHECK_ARG(smem <= 227 * 1024, "shared memory plan of %zu bytes exceeds 227 KB", smem);
+    static thread_local size_t configured = 0;
+    if (configured < smem) {
+        TFEPB_CUDA(cudaFuncSetAttribute(finv::maf_spline_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+    finv::maf_spline_inv_kernel<<<grid, finv::THREADS, smem, as_stream(stream)>>>(p);
+    return check_launch("maf_spline_inv_kernel");
+}

@@ -171,6 +171,11 @@ class MAF(AutoregressiveFlow):
             raise NotImplementedError('Inversion of SOS polynomial transformer has not been implemented yet.')
         if torch.is_grad_enabled() and (y.requires_grad or any(p.requires_grad for p in self.parameters())):
             raise NotImplementedError('tfep_b200: MAF.inverse is not differentiable yet; call it under torch.no_grad()')
+        if self.precision == 'bf16':
+            from ... import _fused
+            if self._fused is None:
+                self._fused = _fused.FusedSplinePlan(self)
+            return _fused.run_inverse_chain([(self._fused, self)], y)
         from ... import _sweep
         if _sweep.eligibility(self, pk) is not None:
             return self._inverse_host_sweep(y)

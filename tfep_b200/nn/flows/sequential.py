@@ -17,8 +17,8 @@ class SequentialFlow(torch.nn.Sequential):
         return self._pass(y, inverse=True)
 
     def _pass(self, x, inverse):
-        if not inverse and len(self) > 1 and self._fused_chain_ok(x):
-            return self._forward_fused_chain(x)
+        if len(self) > 1 and self._fused_chain_ok(x):
+            return self._inverse_fused_chain(x) if inverse else self._forward_fused_chain(x)
         cumulative_log_det_J = None
         for flow in (reversed(self) if inverse else self):
             x, log_det_J = flow.inverse(x) if inverse else flow(x)
@@ -54,3 +54,20 @@ class SequentialFlow(torch.nn.Sequential):
                 ld = l if ld is None else ld + l
             return y, ld
         return _fused.run_chain(pairs, x)
+
+    def _inverse_fused_chain(self, y):
+        from ... import _fused
+        pairs = []
+        for f in reversed(self):
+            f._check_fused_inference(y)
+            if f._fused is None:
+                f._fused = _fused.FusedSplinePlan(f)
+            pairs.append((f._fused, f))
+        first = pairs[0][0]
+        if any((pl.D, pl.K1, pl.HP) != (first.D, first.K1, first.HP) for pl, _ in pairs):
+            x, ld = y, None
+            for pl, f in pairs:
+                x, l = _fused.run_inverse_chain([(pl, f)], x)
+                ld = l if ld is None else ld + l
+            return x, ld
+        return _fused.run_inverse_chain(pairs, y)
