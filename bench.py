@@ -206,26 +206,53 @@ def run_ours(args, rank, world, local_rank):
     # end to end through the public API with host buffers (pinned), copies inside the timed region:
     # tfep_b200.utils.host_pipeline.HostPipeline = chunked H2D copy -> flow -> D2H copy of (y, log_det_J) on three streams
     from tfep_b200.utils.host_pipeline import HostPipeline
-    pipe = HostPipeline(seq, BATCH, 66, dev, n_chunks=4)
-    y_host, ld_host = pipe.y_host, pipe.ld_host
+    pipe = HostPipeline(seq, BATCH, 66, dev, n_chunks=2)
 
     def e2e_step():
-        pipe(x_host)
+        # wait=False: consecutive steps overlap (upload of step g + 1 / download of step g - 1 while step g computes);
+        # every step still uploads its own x from pinned host memory and downloads its own (y, log_det_J)
+        pipe(x_host, wait=False)
 
     for _ in range(max(1, args.warmup)):
         e2e_step()
+    pipe.join()
     barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(args.steps):
         e2e_step()
+    pipe.join()
     b.record()
     torch.cuda.synchronize(dev)
+    y_host, ld_host = pipe.y_host, pipe.ld_host
     e2e_ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
     barrier()
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms)
+
+    # secondary: MAF.inverse of the same configuration (cfg2 is "forward + inverse + log-det"), device resident
+    inv = None
+    if args.precision == 'bf16':
+        with torch.no_grad():
+            y_dev, _ = seq(x)
+            for _ in range(2):
+                seq.inverse(y_dev)
+            torch.cuda.synchronize(dev)
+            iev = []
+            for _ in range(5):
+                flush.zero_()
+                s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s_.record()
+                x_back, ld_back = seq.inverse(y_dev)
+                e_.record()
+                iev.append((s_, e_))
+            torch.cuda.synchronize(dev)
+            inv_ms = statistics.median(s_.elapsed_time(e_) for s_, e_ in iev)
+            d = (x_back - x).abs()
+            d = torch.minimum(d, (2 * 3.141592653589793 - d).abs()).max(dim=1).values
+            inv = {'samples_per_s': BATCH / (inv_ms * 1e-3), 'ms': inv_ms, 'kernel': 'maf_spline_inv_kernel (one launch per step)',
+                   'round_trip_median_abs_err': float(d.median()), 'round_trip_frac_below_1e-3': float((d < 1e-3).float().mean())}
 
     if rank != 0:
         return
@@ -299,6 +326,7 @@ def run_ours(args, rank, world, local_rank):
         'e2e': {'value': BATCH * world * args.steps / (e2e_ms * 1e-3), 'unit': UNIT,
                 'h2d_bytes_per_step': x_host.numel() * 4, 'd2h_bytes_per_step': (y_host.numel() + ld_host.numel()) * 4},
         'gpu_launches': launches_per_step * args.steps,
+        'inverse': inv,
         'roofline': roofline,
         'cpu_baseline': {'value': cpu_value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': f'{sample} samples x {len(times)} passes of the same cfg2 forward, fp32, no_grad'},

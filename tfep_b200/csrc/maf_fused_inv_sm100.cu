@@ -258,12 +258,14 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_inv_kernel(const __grid
                 if (i + 1 < n_ops) nxt = __ldg(reinterpret_cast<const uint4*>(ops + i + 1));
                 const uint32_t idesc = raw.y, n = raw.z & 0xffffu, d_col = raw.z >> 16, a_col = raw.w & 0xffffu;
                 const uint32_t ksteps = (raw.w >> 16) & 0xffu;
-                mbar_wait(&sm->a_ready, a_par, p.error, 3);          // every product needs what the previous one produced
-                a_par ^= 1u;
+                // everything that does not depend on the previous product first: the weights and the descriptors ...
                 mbar_wait(&sm->w_full[stage], wphase, p.error, 5);
-                tc_fence_after();
                 const uint32_t b_lo = w_base16 + stage * (STAGE_BYTES >> 4) + (n << 16);
                 const uint32_t a_tmem = tmem + a_col, d_tmem = tmem + d_col;
+                // ... then the hand-over: every product needs what the previous one produced
+                mbar_wait(&sm->a_ready, a_par, p.error, 3);
+                a_par ^= 1u;
+                tc_fence_after();
                 if (elect_one()) {
                     uint32_t accumulate = 0u;
                     for (uint32_t ks = 0; ks < ksteps; ++ks) {

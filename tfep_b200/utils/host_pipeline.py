@@ -3,7 +3,9 @@
 The reference keeps trajectories on the host and feeds the mapped coordinates to an external potential
 (tfep/app/base.py:790-797), so in practice x arrives from, and y / log_det_J return to, host memory.  The
 batch is cut into chunks that travel through three CUDA streams -- host->device copy, flow kernels,
-device->host copy -- so that PCIe transfers in both directions hide behind the compute of neighbouring chunks.
+device->host copy -- so that PCIe transfers in both directions hide behind the compute of neighbouring chunks;
+with ``wait=False`` consecutive batches overlap as well (double-buffered staging on both sides): the upload
+of batch g + 1 and the download of batch g - 1 run while batch g is in the kernels.
 """
 
 import torch
@@ -16,32 +18,60 @@ class HostPipeline:
         self.flow, self.device = flow, torch.device(device)
         self.bounds = [(i * batch // n_chunks, (i + 1) * batch // n_chunks) for i in range(n_chunks)]
         self.bounds = [(a, b) for a, b in self.bounds if b > a]
-        self.x_dev = torch.empty(batch, n_features, dtype=dtype, device=self.device)
-        self.y_host = torch.empty(batch, n_features, dtype=dtype).pin_memory()
-        self.ld_host = torch.empty(batch, dtype=dtype).pin_memory()
+        self.x_dev = [torch.empty(batch, n_features, dtype=dtype, device=self.device) for _ in range(2)]
+        self.y_hosts = [torch.empty(batch, n_features, dtype=dtype).pin_memory() for _ in range(2)]
+        self.ld_hosts = [torch.empty(batch, dtype=dtype).pin_memory() for _ in range(2)]
         self.s_in = torch.cuda.Stream(self.device)
         self.s_out = torch.cuda.Stream(self.device)
+        self.generation = 0
+        self._computed = [None, None]        # event: kernels that read x_dev[i] have finished
+        self._downloaded = [None, None]      # event: y_hosts[i] / ld_hosts[i] are complete
 
-    def __call__(self, x_host, inverse=False):
-        """x_host: pinned (batch, n_features) tensor.  Returns pinned ``(y_host, ld_host)``; the copies are
-        complete when the call returns (the current stream has been joined with the output stream)."""
+    @property
+    def y_host(self):
+        """Output buffers of the most recent call."""
+        return self.y_hosts[(self.generation - 1) % 2]
+
+    @property
+    def ld_host(self):
+        return self.ld_hosts[(self.generation - 1) % 2]
+
+    def __call__(self, x_host, inverse=False, wait=True):
+        """x_host: pinned (batch, n_features) tensor.  Returns pinned ``(y_host, ld_host)``.
+
+        ``wait=True``: the current stream has been joined with the output stream when the call returns (results
+        valid after a synchronize of the current stream).  ``wait=False``: nothing is joined, so the next call
+        may start uploading while this batch computes and downloads; results of this call are valid after
+        :meth:`join` (or once two more calls have been issued, the buffers are reused)."""
         main = torch.cuda.current_stream(self.device)
-        self.s_in.wait_stream(main)
-        self.s_out.wait_stream(main)
+        g = self.generation % 2
+        self.generation += 1
+        x_dev, y_host, ld_host = self.x_dev[g], self.y_hosts[g], self.ld_hosts[g]
+        if self._computed[g] is not None:
+            self.s_in.wait_event(self._computed[g])          # staging buffer free again
+        if self._downloaded[g] is not None:
+            self.s_out.wait_event(self._downloaded[g])
         fn = self.flow.inverse if inverse else self.flow
         with torch.no_grad():
             for a, b in self.bounds:
                 with torch.cuda.stream(self.s_in):
-                    self.x_dev[a:b].copy_(x_host[a:b], non_blocking=True)
+                    x_dev[a:b].copy_(x_host[a:b], non_blocking=True)
                     ready = self.s_in.record_event()
                 main.wait_event(ready)
-                y, ld = fn(self.x_dev[a:b])
+                y, ld = fn(x_dev[a:b])
                 done = main.record_event()
                 with torch.cuda.stream(self.s_out):
                     self.s_out.wait_event(done)
-                    self.y_host[a:b].copy_(y, non_blocking=True)
-                    self.ld_host[a:b].copy_(ld, non_blocking=True)
+                    y_host[a:b].copy_(y, non_blocking=True)
+                    ld_host[a:b].copy_(ld, non_blocking=True)
                     y.record_stream(self.s_out)
                     ld.record_stream(self.s_out)
-        main.wait_stream(self.s_out)
-        return self.y_host, self.ld_host
+        self._computed[g] = done
+        self._downloaded[g] = self.s_out.record_event()
+        if wait:
+            main.wait_stream(self.s_out)
+        return y_host, ld_host
+
+    def join(self):
+        """Make the current stream wait for every download issued so far."""
+        torch.cuda.current_stream(self.device).wait_stream(self.s_out)
