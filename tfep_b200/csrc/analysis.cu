@@ -50,6 +50,24 @@ __device__ __forceinline__ MS ms_block_reduce(MS v) {
 // Each thread keeps a running (max, sum) over groups of values: one exp per value plus one rescale per
 // group, the sum carried in double.  The bulk is read with 16-byte vector loads, four of them in flight per
 // thread (the kernel is HBM bound: 4 or 8 bytes per sample, read once); the unaligned head / tail is scalar.
+// fp32 data is reduced in the log2 domain (values pre-multiplied by log2(e), hardware ex2: one FFMA + one MUFU
+// + one FADD per sample, so that the instruction stream stays below the memory time); fp64 data uses exp.
+template <typename T> struct LseDom;
+template <> struct LseDom<float> {
+    static __device__ __forceinline__ float factor() { return 1.4426950408889634f; }
+    static __device__ __forceinline__ float exp(float d) {
+        float r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+        return r;
+    }
+    static __device__ __forceinline__ double to_natural(float m) { return (double)m * 0.6931471805599453094; }
+};
+template <> struct LseDom<double> {
+    static __device__ __forceinline__ double factor() { return 1.0; }
+    static __device__ __forceinline__ double exp(double d) { return ::exp(d); }
+    static __device__ __forceinline__ double to_natural(double m) { return m; }
+};
+
 template <typename T, int N>
 __device__ __forceinline__ void lse_absorb(const T (&v)[N], int count, T& m, double& s, bool& have) {
     if (count <= 0) return;
@@ -58,23 +76,25 @@ __device__ __forceinline__ void lse_absorb(const T (&v)[N], int count, T& m, dou
     for (int u = 1; u < N; ++u)
         if (u < count) gm = v[u] > gm ? v[u] : gm;
     if (!have || gm > m) {
-        if (have) s *= (double)Math<T>::exp(m - gm);
+        if (have) s *= (double)LseDom<T>::exp(m - gm);
         m = gm;
         have = true;
     }
     T part = T(0);
 #pragma unroll
     for (int u = 0; u < N; ++u)
-        if (u < count) part += Math<T>::exp(v[u] - m);
+        if (u < count) part += LseDom<T>::exp(v[u] - m);
     s += (double)part;
 }
 
 template <typename T>
-__global__ void __launch_bounds__(LSE_THREADS) lse_partial_kernel(const T* __restrict__ w, const T* __restrict__ logw,
-                                                                  int64_t n, T scale, double* __restrict__ partials) {
+__global__ void __launch_bounds__(LSE_THREADS, 4) lse_partial_kernel(const T* __restrict__ w, const T* __restrict__ logw,
+                                                                  int64_t n, T scale_nat, double* __restrict__ partials) {
     constexpr int VEC = 16 / sizeof(T);          // elements per 16-byte load
     constexpr int LOADS = 4;                      // vector loads in flight per thread
     struct alignas(16) Pack { T v[VEC]; };
+    const T dom = LseDom<T>::factor();            // v = dom * (scale w + logw): log2 domain for fp32
+    const T scale = scale_nat * dom;
     T m = T(0);
     double s = 0.0;
     bool have = false;
@@ -87,7 +107,38 @@ __global__ void __launch_bounds__(LSE_THREADS) lse_partial_kernel(const T* __res
     const int64_t nvec = vec_ok ? (n - head) / VEC : 0;
     const Pack* wv = reinterpret_cast<const Pack*>(w + head);
     const Pack* lv = reinterpret_cast<const Pack*>(logw ? logw + head : nullptr);
-    for (int64_t base = t0; base < nvec; base += nthreads * LOADS) {
+    // full groups: every load of the group is in range, no per-value bookkeeping
+    int64_t base = t0;
+    for (; base + (int64_t)(LOADS - 1) * nthreads < nvec; base += nthreads * LOADS) {
+        Pack a[LOADS], b[LOADS];
+#pragma unroll
+        for (int k = 0; k < LOADS; ++k) {
+            a[k] = wv[base + (int64_t)k * nthreads];
+            if (logw) b[k] = lv[base + (int64_t)k * nthreads];
+        }
+        T v[LOADS * VEC];
+#pragma unroll
+        for (int k = 0; k < LOADS; ++k)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) v[k * VEC + e] = logw ? scale * a[k].v[e] + dom * b[k].v[e] : scale * a[k].v[e];
+        T gm = v[0];
+#pragma unroll
+        for (int u = 1; u < LOADS * VEC; ++u) gm = fmax(gm, v[u]);
+        if (!have || gm > m) {
+            if (have) s *= (double)LseDom<T>::exp(m - gm);
+            m = gm;
+            have = true;
+        }
+        T p0 = T(0), p1 = T(0);
+#pragma unroll
+        for (int u = 0; u < LOADS * VEC; u += 2) {
+            p0 += LseDom<T>::exp(v[u] - m);
+            p1 += LseDom<T>::exp(v[u + 1] - m);
+        }
+        s += (double)(p0 + p1);
+    }
+    // ragged last group
+    for (; base < nvec; base += nthreads * LOADS) {
         Pack a[LOADS], b[LOADS];
 #pragma unroll
         for (int k = 0; k < LOADS; ++k) {
@@ -104,7 +155,7 @@ __global__ void __launch_bounds__(LSE_THREADS) lse_partial_kernel(const T* __res
             const int64_t i = base + (int64_t)k * nthreads;
             if (i < nvec) {
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) v[k * VEC + e] = scale * a[k].v[e] + (logw ? b[k].v[e] : T(0));
+                for (int e = 0; e < VEC; ++e) v[k * VEC + e] = scale * a[k].v[e] + (logw ? dom * b[k].v[e] : T(0));
                 count = (k + 1) * VEC;
             }
         }
@@ -114,10 +165,10 @@ __global__ void __launch_bounds__(LSE_THREADS) lse_partial_kernel(const T* __res
     const int64_t done = head + nvec * VEC;
     for (int64_t i = t0; i < head + (n - done); i += nthreads) {
         const int64_t j = i < head ? i : done + (i - head);
-        T v1[1] = {scale * w[j] + (logw ? logw[j] : T(0))};
+        T v1[1] = {scale * w[j] + (logw ? dom * logw[j] : T(0))};
         lse_absorb<T, 1>(v1, 1, m, s, have);
     }
-    MS r = ms_block_reduce(MS{(double)m, have ? s : 0.0});
+    MS r = ms_block_reduce(MS{LseDom<T>::to_natural(m), have ? s : 0.0});
     if (threadIdx.x == 0) {
         partials[2 * blockIdx.x] = r.m;
         partials[2 * blockIdx.x + 1] = r.s;
@@ -292,7 +343,8 @@ extern "C" int tfepb_lse(int32_t dtype, const void* w, const void* logw, int64_t
     TFEPB_CHECK_ARG(w && partials && out2, "null buffer");
     if (int rc = require_sm100()) return rc;
     int64_t blocks = (n + (int64_t)LSE_THREADS * 16 - 1) / ((int64_t)LSE_THREADS * 16);
-    const int64_t cap = (int64_t)sm_count() * 8 < LSE_MAX_BLOCKS ? (int64_t)sm_count() * 8 : LSE_MAX_BLOCKS;
+    // one wave of co-resident blocks (4 per SM by the launch bounds): no tail wave
+    const int64_t cap = (int64_t)sm_count() * 4 < LSE_MAX_BLOCKS ? (int64_t)sm_count() * 4 : LSE_MAX_BLOCKS;
     if (blocks > cap) blocks = cap;
     cudaStream_t s = as_stream(stream);
     if (dtype == TFEPB_F32)
