@@ -215,7 +215,12 @@ typedef struct {
     int32_t batch, n_features;
     int32_t k1, hidden_padded;                     /* padded widths shared by all layers of the chain */
     int32_t n_layers;
-    int32_t hidden_groups;                         /* accumulator groups (flag-2 commits) per hidden GEMM in `ops` */
+    int32_t hidden_halves;                         /* 1 or 2: column halves a hidden layer is computed and handed over in */
+    int32_t hidden_split[2];                       /* per hidden layer: first column of the second half (multiple of 16);
+                                                      the ops of a half carry its index (0 / 1) in flag bits 2-3 and each
+                                                      half ends with a commit (flag 2); every flag-16 op consumes the next
+                                                      hand-over, in the order x, h1 first half, h1 second half, h2 first
+                                                      half, h2 second half */
     const tfepb_fused_layer* layers;               /* HOST array of n_layers entries */
     uint32_t* tile_flags;                          /* device, (n_layers - 1) * ceil(batch / 128) words owned by the
                                                       caller and private to launches in flight; a word equal to

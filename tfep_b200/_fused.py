@@ -100,11 +100,25 @@ class FusedSplinePlan:
             raise _lib.TfepB200Error('layer widths exceed the tensor-memory plan of the fused kernel')
         self.perm1, self.perm2 = plan.perms[1], plan.perms[2]
 
-        # hidden-layer row chunks (<= 160 rows so that a GEMM1 block fits a ring stage)
-        n_hc = max(1, math.ceil(self.HP / 192))
-        hc = _ceil16(math.ceil(self.HP / n_hc))
-        self.hidden_chunks = [(r, min(r + hc, self.HP)) for r in range(0, self.HP, hc)]
-        assert all((b - a) * self.K1 * 2 <= STAGE_BYTES for a, b in self.hidden_chunks)
+        # Hidden layers are computed and handed over in two column halves (rows of the GEMM = columns of the
+        # accumulator).  Layer 1 splits at s1; layer 2 splits at the largest s2 whose rows only see layer-1 units
+        # below s1, so that GEMM2 of the first half can run while the ELU of the second half of h1 is in progress.
+        def kmax2(rows_end):
+            real = deg_h2[:max(min(rows_end - 2, self.H), 0)]
+            return _ceil16(2 + int((deg_h1 <= int(real.max())).sum())) if len(real) else 16
+
+        s1 = 16 * math.ceil(self.HP / 32)
+        s2 = s1
+        while s2 > 16 and kmax2(s2) > s1:
+            s2 -= 16
+        self.halves = 2 if (self.HP >= 64 and kmax2(s2) <= s1 and (self.HP - s2) * KB_HID * 2 <= STAGE_BYTES) else 1
+        if self.halves == 2:
+            self.hidden_chunks1 = [(0, s1), (s1, self.HP)]
+            self.hidden_chunks2 = [(0, s2), (s2, self.HP)]
+        else:
+            self.hidden_chunks1 = self.hidden_chunks2 = [(0, self.HP)]
+        self.hidden_split = (self.hidden_chunks1[0][1], self.hidden_chunks2[0][1])
+        assert all((b - a) * self.K1 * 2 <= STAGE_BYTES for a, b in self.hidden_chunks1)
 
         # sorted features -> chunks of 8 slots
         part = pk['parts'][0]
@@ -156,32 +170,38 @@ class FusedSplinePlan:
             w_off += nbytes
 
         # Accumulator groups alternate between the two MMA issuer warps (OP_OWNER1); every group ends with a
-        # commit (hidden layers: one per row chunk, counted by the epilogue through `hidden_groups`).
-        # GEMM1: full K1 per row chunk (the first layer is tiny; no staircase)
-        for i, (a, b) in enumerate(self.hidden_chunks):
-            fl = OP_FIRST | OP_COMMIT | OP_HIDDEN | (OP_WAIT_A if i == 0 else 0) | (OP_OWNER1 if i & 1 else 0)
+        # commit.  Hidden layers: one group per column half (its index travels in the accumulator bits); every
+        # OP_WAIT_A consumes the next hand-over of the epilogue, in the order x, h1 half 0, h1 half 1, h2 half 0,
+        # h2 half 1.
+        # GEMM1: full K1 per half (the first layer is tiny; no staircase); both halves need only x
+        for i, (a, b) in enumerate(self.hidden_chunks1):
+            fl = OP_FIRST | OP_COMMIT | OP_HIDDEN | (i << OP_ACC_SHIFT) | (OP_WAIT_A if i == 0 else 0) | (OP_OWNER1 if i & 1 else 0)
             add(b - a, a, 0, self.K1, 0, fl, 0, self.K1, a)
-        # GEMM2: rows see layer-1 units of degree <= their own
-        first = True
-        for i, (a, b) in enumerate(self.hidden_chunks):
-            real = deg_h2[max(a - 2, 0):max(min(b - 2, self.H), 0)]      # packed position = 2 + sorted index
-            kmax = _ceil16(2 + int((deg_h1 <= int(real.max())).sum())) if len(real) else 16
+        # GEMM2: rows see layer-1 units of degree <= their own; half i waits for half i of h1
+        for i, (a, b) in enumerate(self.hidden_chunks2):
+            kmax = kmax2(b)
+            if self.halves == 2 and i == 0:
+                assert kmax <= self.hidden_split[0]
             blocks = list(range(0, kmax, KB_HID))
             for bi, kb in enumerate(blocks):
-                fl = OP_HIDDEN | (OP_FIRST if bi == 0 else 0) | (OP_WAIT_A if first else 0) | (OP_OWNER1 if i & 1 else 0)
+                fl = OP_HIDDEN | (i << OP_ACC_SHIFT) | (OP_FIRST | OP_WAIT_A if bi == 0 else 0) | (OP_OWNER1 if i & 1 else 0)
                 if bi == len(blocks) - 1:
                     fl |= OP_COMMIT
-                first = False
                 add(b - a, a, kb, min(KB_HID, kmax - kb), kb // 8, fl, off1, self.HP, a)
-        # GEMM3: a chunk of features sees layer-2 units of degree < its largest degree
+        # GEMM3: a chunk of features sees layer-2 units of degree < its largest degree.  The first chunk only needs
+        # the first half of h2 (its accumulator lies inside the columns that half has released); the second chunk
+        # consumes the hand-over of the second half, after which everything is available.
         for c in range(self.n_chunks):
             kmax = _ceil16(2 + int((deg_h2 < chunk_maxdeg[c]).sum()))
             blocks = list(range(0, kmax, KB_OUT))
             acc = c % ACC_BUFS
+            wait_a = c == 0 or (c == 1 and self.halves == 2)
+            if self.halves == 2 and c == 0 and (kmax > self.hidden_split[1] or CHUNK_N > self.hidden_split[1] or self.n_chunks < 2):
+                raise _lib.TfepB200Error('fused bf16 path: first output chunk does not fit the first half of h2')
             for bi, kb in enumerate(blocks):
                 fl = (acc << OP_ACC_SHIFT) | (OP_OWNER1 if c & 1 else 0)
                 if bi == 0:
-                    fl |= OP_FIRST | OP_WAIT_EMPTY | (OP_WAIT_A if c == 0 else 0)
+                    fl |= OP_FIRST | OP_WAIT_EMPTY | (OP_WAIT_A if wait_a else 0)
                 if bi == len(blocks) - 1:
                     fl |= OP_COMMIT
                 add(CHUNK_N, acc * CHUNK_N, kb, min(KB_OUT, kmax - kb), kb // 8, fl, off2, self.HP, c * CHUNK_N)
@@ -360,7 +380,7 @@ def run_chain(plans_mafs, x, debug_params=None):
     first = plans_mafs[0][0]
     if n_layers > MAX_LAYERS or sum(len(pl.ops_host) for pl, _ in plans_mafs) > MAX_OPS:
         raise _lib.TfepB200Error('chain too long for one fused launch')
-    if any((pl.D, pl.K1, pl.HP, len(pl.hidden_chunks)) != (first.D, first.K1, first.HP, len(first.hidden_chunks)) for pl, _ in plans_mafs):
+    if any((pl.D, pl.K1, pl.HP, pl.halves, pl.hidden_split) != (first.D, first.K1, first.HP, first.halves, first.hidden_split) for pl, _ in plans_mafs):
         raise _lib.TfepB200Error('fused chain needs layers of identical widths')
     x = x.contiguous()
     B = x.shape[0]
@@ -387,7 +407,8 @@ def run_chain(plans_mafs, x, debug_params=None):
             flags = tb[key] = torch.zeros(max(need, 4096), dtype=torch.int32, device=x.device)
     _EPOCH[0] = (_EPOCH[0] % 0x7fffffff) + 1
     args = _lib.FusedArgs(x=x.data_ptr(), y=y.data_ptr(), logdet=ld.data_ptr(), batch=B, n_features=first.D,
-                          k1=first.K1, hidden_padded=first.HP, n_layers=n_layers, hidden_groups=len(first.hidden_chunks), layers=layers,
+                          k1=first.K1, hidden_padded=first.HP, n_layers=n_layers, hidden_halves=first.halves,
+                          hidden_split=(ctypes.c_int32 * 2)(*first.hidden_split), layers=layers,
                           tile_flags=None if flags is None else flags.data_ptr(), epoch=_EPOCH[0],
                           debug_mode=int(os.environ.get('TFEPB_FUSED_DEBUG_MODE', '0')),
                           error_flag=tb['err'].data_ptr(),

@@ -82,7 +82,7 @@ enum : uint32_t {
     OP_WAIT_A = 16u,        // wait for the A operand (start of a GEMM phase)
     OP_WAIT_EMPTY = 32u,    // wait until the epilogue drained accumulator `acc` (GEMM3 chunks)
     OP_OWNER1 = 64u,        // issued by the second MMA warp (accumulator groups alternate between the two issuers)
-    OP_HIDDEN = 128u,       // hidden-layer block: its group commits to hid_full instead of acc_full[acc]
+    OP_HIDDEN = 128u,       // hidden-layer block: its group commits to hid_full[acc] (acc = column half) instead of acc_full[acc]
 };
 
 struct __align__(16) FeatConst {   // per sorted feature
@@ -103,7 +103,8 @@ struct Params {
     int K1;                     // D + 2 padded to a multiple of 16
     int HP;                     // hidden width (+2) padded to a multiple of 16
     int n_layers, n_tiles, feat_stride;   // feat_stride: feature slots reserved per layer in shared memory
-    int hidden_groups;          // accumulator groups (row chunks) per hidden GEMM = commits the epilogue waits for
+    int n_halves;               // column halves of a hidden layer (1 or 2), each its own accumulator group and hand-over
+    int hsplit[2];              // first column of the second half, per hidden layer (multiple of 16)
     uint32_t* flags;            // (n_layers - 1) x n_tiles: == epoch once the tile of that layer is in y
     uint32_t epoch;
     int* error;                 // device int: set on watchdog timeout
@@ -119,7 +120,7 @@ struct Params {
 struct Smem {
     uint64_t w_full[STAGES], w_empty[STAGES];
     uint64_t x_full[2], x_empty[2], y_ready[2], a_ready;
-    uint64_t acc_full[ACC_BUFS], acc_empty[ACC_BUFS], hid_full;
+    uint64_t acc_full[ACC_BUFS], acc_empty[ACC_BUFS], hid_full[2];
     uint32_t tmem_base;
     uint32_t pad[3];
 };
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
         }
         mbar_init(&sm->a_ready, EPI_THREADS);
         for (int b = 0; b < ACC_BUFS; ++b) { mbar_init(&sm->acc_full[b], 1); mbar_init(&sm->acc_empty[b], EPI_THREADS); }
-        mbar_init(&sm->hid_full, (uint32_t)p.hidden_groups);
+        mbar_init(&sm->hid_full[0], 1); mbar_init(&sm->hid_full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(&sm->tmem_base, 512);
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
                         accumulate = 1u;
                     }
                     umma_commit(&sm->w_empty[stage]);                   // frees the ring stage when the MMAs retire
-                    if (flags & OP_COMMIT) umma_commit((flags & OP_HIDDEN) ? &sm->hid_full : &sm->acc_full[acc]);
+                    if (flags & OP_COMMIT) umma_commit((flags & OP_HIDDEN) ? &sm->hid_full[acc] : &sm->acc_full[acc]);
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; wphase ^= 1; }
@@ -466,42 +467,57 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
             mbar_arrive(&sm->a_ready);
             trace<DEBUG>(p, 2, ts, 3002);
             // ---- two hidden layers: ELU, bf16 -> A operand of the next GEMM (tensor memory) ----
+            // Each layer is handed over in two column halves: GEMM2 of the first half (its rows only see the
+            // first half of h1) runs while the second half of h1 is still in the ELU, and the first output chunk
+            // starts on the first half of h2.
             for (int hl = 0; hl < 2; ++hl) {
-                mbar_wait(&sm->hid_full, hid_par, p.error, 7);
-                hid_par ^= 1u;
-                tc_fence_after();
-                trace<DEBUG>(p, 2, ts, 3010 + hl);
-                // 16 accumulator columns per step, two register sets in ping-pong: the load of the next step is in
-                // flight while this one is processed
-                uint32_t ra[16], rb[16];
-                float l2e;                          // opaque to the compiler: kept in ONE register instead of being
-                asm volatile("mov.f32 %0, 0f3FB8AA3B;" : "=f"(l2e));    // re-materialised for every element
-                auto elu16 = [&](uint32_t (&r)[16], int c0) {
-                    uint32_t q[8];
+                for (int half = 0; half < p.n_halves; ++half) {
+                    // h2 overwrites h1 in place (same A-operand columns), so the second layer may only be written
+                    // once BOTH halves of GEMM2 have read h1; the first layer starts on its first half right away
+                    if (hl == 0 || half == 0) {
+                        mbar_wait(&sm->hid_full[half], (hid_par >> half) & 1u, p.error, 7);
+                        hid_par ^= 1u << half;
+                        if (hl == 1 && p.n_halves == 2) {
+                            mbar_wait(&sm->hid_full[1], (hid_par >> 1) & 1u, p.error, 7);
+                            hid_par ^= 2u;
+                        }
+                    }
+                    tc_fence_after();
+                    trace<DEBUG>(p, 2, ts, 3010 + 2 * hl + half);
+                    const int cbeg = half == 0 ? 0 : p.hsplit[hl];
+                    const int cend = (half == 0 && p.n_halves == 2) ? p.hsplit[hl] : p.HP;
+                    // 16 accumulator columns per step, two register sets in ping-pong: the load of the next step is
+                    // in flight while this one is processed
+                    uint32_t ra[16], rb[16];
+                    float l2e;                          // opaque to the compiler: kept in ONE register instead of being
+                    asm volatile("mov.f32 %0, 0f3FB8AA3B;" : "=f"(l2e));    // re-materialised for every element
+                    auto elu16 = [&](uint32_t (&r)[16], int c0) {
+                        uint32_t q[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        q[i] = pack_bf16(elu_l2(__uint_as_float(r[2 * i]), l2e), elu_l2(__uint_as_float(r[2 * i + 1]), l2e));
-                    tmem_st8(lane_addr + A_COL + c0 / 2, q);
-                };
-                int c0 = wg * 16;
-                if (c0 < p.HP) tmem_ld16(lane_addr + c0, ra);
-                while (c0 < p.HP) {
-                    tmem_wait8(ra); tmem_wait8(ra + 8);
-                    int cn = c0 + EPI_WGS * 16;
-                    if (cn < p.HP) tmem_ld16(lane_addr + cn, rb);
-                    elu16(ra, c0);
-                    c0 = cn;
-                    if (c0 >= p.HP) break;
-                    tmem_wait8(rb); tmem_wait8(rb + 8);
-                    cn = c0 + EPI_WGS * 16;
-                    if (cn < p.HP) tmem_ld16(lane_addr + cn, ra);
-                    elu16(rb, c0);
-                    c0 = cn;
+                        for (int i = 0; i < 8; ++i)
+                            q[i] = pack_bf16(elu_l2(__uint_as_float(r[2 * i]), l2e), elu_l2(__uint_as_float(r[2 * i + 1]), l2e));
+                        tmem_st8(lane_addr + A_COL + c0 / 2, q);
+                    };
+                    int c0 = cbeg + wg * 16;
+                    if (c0 < cend) tmem_ld16(lane_addr + c0, ra);
+                    while (c0 < cend) {
+                        tmem_wait8(ra); tmem_wait8(ra + 8);
+                        int cn = c0 + EPI_WGS * 16;
+                        if (cn < cend) tmem_ld16(lane_addr + cn, rb);
+                        elu16(ra, c0);
+                        c0 = cn;
+                        if (c0 >= cend) break;
+                        tmem_wait8(rb); tmem_wait8(rb + 8);
+                        cn = c0 + EPI_WGS * 16;
+                        if (cn < cend) tmem_ld16(lane_addr + cn, ra);
+                        elu16(rb, c0);
+                        c0 = cn;
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&sm->a_ready);
+                    trace<DEBUG>(p, 2, ts, 3020 + 2 * hl + half);
                 }
-                tmem_st_wait();
-                tc_fence_before();
-                mbar_arrive(&sm->a_ready);
-                trace<DEBUG>(p, 2, ts, 3020 + hl);
             }
             // ---- output layer chunks: spline transformer straight out of TMEM ----
             float ld = 0.f;
@@ -591,7 +607,11 @@ extern "C" int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_st
     TFEPB_CHECK_ARG(a->hidden_padded % 16 == 0 && a->hidden_padded > 0 && a->hidden_padded <= fused::ACC_COLS,
                     "hidden width (padded) must be a multiple of 16 and at most 336 (tensor-memory plan)");
     TFEPB_CHECK_ARG(a->k1 <= 2 * (512 - fused::A_COL), "too many input features for the tensor-memory plan");
-    TFEPB_CHECK_ARG(a->hidden_groups >= 1 && a->hidden_groups <= 8, "hidden_groups must be in [1, 8]");
+    TFEPB_CHECK_ARG(a->hidden_halves == 1 || a->hidden_halves == 2, "hidden_halves must be 1 or 2");
+    for (int i = 0; i < 2; ++i)
+        TFEPB_CHECK_ARG(a->hidden_halves == 1 || (a->hidden_split[i] % 16 == 0 && a->hidden_split[i] > 0 &&
+                                                   a->hidden_split[i] < a->hidden_padded),
+                        "hidden_split must be a multiple of 16 inside the hidden width");
     TFEPB_CHECK_ARG((a->n_features * 4 * fused::TILE_M) % 16 == 0, "tile of x must be a multiple of 16 bytes");
     TFEPB_CHECK_ARG(((uintptr_t)a->x % 16 == 0) && ((uintptr_t)a->y % 16 == 0), "x and y must be 16-byte aligned");
     if (int rc = require_sm100()) return rc;
@@ -618,7 +638,7 @@ extern "C" int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_st
         if (s.n_chunks * fused::FEATS_PER_CHUNK > feat_stride) feat_stride = s.n_chunks * fused::FEATS_PER_CHUNK;
     }
     p.feat_stride = feat_stride;
-    p.hidden_groups = a->hidden_groups;
+    p.n_halves = a->hidden_halves; p.hsplit[0] = a->hidden_split[0]; p.hsplit[1] = a->hidden_split[1];
     p.error = a->error_flag;
     p.debug_params = a->debug_params;
     p.debug_mode = a->debug_mode;
