@@ -162,6 +162,25 @@ def test_fused_inverse_chain_round_trip():
     assert int(seq[0]._fused._tables(torch.device(DEV))['err'].item()) == 0
 
 
+def test_long_chain_is_split_into_launches():
+    """Six layers: forward runs as 4 + 2 layers per launch (shared-memory budget of the feature tables), inverse
+    as one launch; both equal the layer-by-layer results."""
+    seq, _ = cfg_flow_modules('cfg2', DEV, n_layers=6)
+    x = cases.cfg_input('cfg2', 700).to(DEV)
+    for maf in seq:
+        maf.precision = 'bf16'
+    with torch.no_grad():
+        y, ld = seq(x)
+        cur, tot = x, None
+        for maf in seq:
+            cur, l = maf(cur)
+            tot = l if tot is None else tot + l
+        xi, ldi = seq.inverse(y)
+    assert torch.equal(y, cur) and float((ld - tot).abs().max()) < 1e-5
+    d = _circ(xi, x).max(dim=1).values
+    assert float(d.median()) < 1e-4 and float((ld + ldi).abs().median()) < 5e-4
+
+
 def test_inference_only_and_eligibility():
     from tfep_b200._lib import TfepB200Error
     from tfep_b200.nn.conditioners import generate_degrees

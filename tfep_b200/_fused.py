@@ -30,7 +30,7 @@ from . import _lib
 from ._lib import check, ptr, stream_ptr
 
 TILE_M = 128
-STAGE_BYTES = 32768
+STAGE_BYTES = 49152
 FEATS_PER_CHUNK = 4
 NPAR = 25
 PSTRIDE = 28
@@ -39,8 +39,8 @@ ACC_BUFS = 3
 MAX_LAYERS, MAX_OPS = 8, 512
 INV_STAGE_BYTES = 24576
 INV_ACC_OUT, INV_ACC_HID, INV_A0_COL, INV_A1_COL, INV_A2_COL = 0, 32, 64, 128, 320
-KB_OUT = 128
-KB_HID = 80
+KB_OUT = 192
+KB_HID = 112
 LOG2E = 1.4426950408889634
 OP_FIRST, OP_COMMIT, OP_ACC_SHIFT, OP_WAIT_A, OP_WAIT_EMPTY, OP_OWNER1, OP_HIDDEN = 1, 2, 2, 16, 32, 64, 128
 
@@ -371,8 +371,17 @@ class FusedSplinePlan:
 _EPOCH = [0]
 
 
+LAYERS_PER_LAUNCH = 4          # the feature tables of all layers of a launch share the 227 KB of shared memory
+
+
 def run_chain(plans_mafs, x, debug_params=None):
-    """One launch for a chain of fused MAF layers: y, sum of log_det_J (reference sequential.py:50-68)."""
+    """A chain of fused MAF layers, LAYERS_PER_LAUNCH per launch: y, sum of log_det_J (reference sequential.py:50-68)."""
+    if len(plans_mafs) > LAYERS_PER_LAUNCH:
+        y, ld = x, None
+        for i in range(0, len(plans_mafs), LAYERS_PER_LAUNCH):
+            y, l = run_chain(plans_mafs[i:i + LAYERS_PER_LAUNCH], y)
+            ld = l if ld is None else ld + l
+        return y, ld
     _lib.require_cuda(x)
     if x.dtype != torch.float32:
         raise _lib.TfepB200Error('the fused bf16 path takes float32 inputs')
@@ -421,13 +430,17 @@ def run_chain(plans_mafs, x, debug_params=None):
 def run_inverse_chain(plans_mafs, y):
     """One launch for the inverse of a chain of fused MAF layers, given in the order they are inverted:
     x, sum of log_det_J (reference sequential.py:50-68 with inverse=True)."""
+    if len(plans_mafs) > MAX_LAYERS:
+        x, ld = y, None
+        for i in range(0, len(plans_mafs), MAX_LAYERS):
+            x, l = run_inverse_chain(plans_mafs[i:i + MAX_LAYERS], x)
+            ld = l if ld is None else ld + l
+        return x, ld
     _lib.require_cuda(y)
     if y.dtype != torch.float32:
         raise _lib.TfepB200Error('the fused bf16 path takes float32 inputs')
     n_layers = len(plans_mafs)
     first = plans_mafs[0][0]
-    if n_layers > MAX_LAYERS:
-        raise _lib.TfepB200Error('chain too long for one fused launch')
     if any((pl.D, pl.K1, pl.HP) != (first.D, first.K1, first.HP) for pl, _ in plans_mafs):
         raise _lib.TfepB200Error('fused chain needs layers of identical widths')
     y = y.contiguous()

@@ -53,8 +53,8 @@ constexpr int EPI_WGS = 4;                      // epilogue warpgroups
 constexpr int EPI_THREADS = EPI_WGS * 128;
 constexpr int AUX_THREADS = 128;                // producer, MMA issuer, store warp, one idle warp
 constexpr int THREADS = AUX_THREADS + EPI_THREADS;
-constexpr int STAGES = 4;
-constexpr int STAGE_BYTES = 32768;              // one weight block (<= 256 rows, bf16)
+constexpr int STAGES = 3;
+constexpr int STAGE_BYTES = 49152;              // one weight block (<= 256 rows, bf16)
 constexpr int FEATS_PER_CHUNK = 4;
 constexpr int NPAR = 25;                        // circular spline, K = 8: 8 widths, 8 heights, 8 slopes, shift
 constexpr int PSTRIDE = 28;                     // accumulator columns per feature slot (25 used)

@@ -33,7 +33,7 @@ class SequentialFlow(torch.nn.Sequential):
         from ... import _fused
         if not all(isinstance(f, MAF) and f.precision == 'bf16' for f in self):
             return False
-        if len(self) > _fused.MAX_LAYERS or any(_fused.eligibility(f) is not None for f in self):
+        if any(_fused.eligibility(f) is not None for f in self):
             return False
         return True
 
