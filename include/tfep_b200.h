@@ -352,6 +352,13 @@ int tfepb_exp_table(int32_t dtype, const void* w, int64_t n, double scale, const
 int tfepb_bootstrap_sums(const float* e, int64_t n, int64_t shard_lo, uint32_t max_idx, const int32_t* idx, int64_t ldidx,
                          int32_t n_resamples, int64_t sample_size, uint64_t philox_seed,
                          uint64_t philox_offset, double* out_sums, tfepb_stream_t stream);
+/* Bayesian bootstrap of the FEP estimator (analysis/bootstrap.py:236-262, estimator.py:78-79): per resample r
+ * out_sums[r] = sum_i e[i] g_ri and out_weight_sums[r] = sum_i g_ri with g_ri ~ Exp(1) from Philox4x32-10
+ * (counter = philox_offset + r * ceil(n / 4) + i / 4), i.e. Dirichlet(1, ..., 1) weights g_ri / sum_i g_ri.
+ * One coalesced pass over the exp table `e` (tfepb_exp_table) per resample; n_resamples <= 65535 per call. */
+int tfepb_bayesian_bootstrap_sums(const float* e, int64_t n, int32_t n_resamples, uint64_t philox_seed,
+                                  uint64_t philox_offset, double* out_sums, double* out_weight_sums,
+                                  tfepb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -131,14 +131,36 @@ def summarize(stats, confidence_level=0.95, method='percentile', full_statistic=
                 mean=torch.mean(stats), median=torch.median(stats))
 
 
+def bayesian_bootstrap_statistics(data, statistic, n_resamples, sample_size=None, batch=None):
+    """Statistics under Dirichlet(1, ..., 1) sample weights.  analysis/bootstrap.py:236-262 (the weights come
+    from the GLOBAL torch generator: seed with torch.manual_seed for reproducibility)."""
+    n = len(data) if sample_size is None else sample_size
+    batch = n_resamples if batch is None else batch
+    out = torch.empty(n_resamples, dtype=data.dtype)
+    dirichlet = torch.distributions.Dirichlet(torch.ones(n))
+    for k in range(0, n_resamples, batch):
+        nb = min(batch, n_resamples - k)
+        weights = dirichlet.sample((nb,))
+        out[k:k + nb] = statistic(data.expand((nb, *data.shape))[:, :n], weights=weights, vectorized=True)
+    return out
+
+
 def bootstrap(data, statistic, *, confidence_level=0.95, n_resamples=9999, bootstrap_sample_size=None,
-              take_first_only=False, batch=None, method='percentile', generator=None):
-    """analysis/bootstrap.py:24-182 (standard, non-Bayesian path)."""
+              take_first_only=False, batch=None, method='percentile', bayesian=False, generator=None):
+    """analysis/bootstrap.py:24-182."""
+    if bayesian and generator is not None:
+        raise ValueError('Bayesian bootstrapping does not support random number generators.')
+    if bayesian and bootstrap_sample_size is not None and not take_first_only:
+        raise ValueError('With Bayesian bootstrapping, specifying a bootstrap_sample_size '
+                         'is supported only when take_first_only is True.')
     sizes = [len(data)] if bootstrap_sample_size is None else list(bootstrap_sample_size)
     res = []
     with torch.no_grad():
         for s in sizes:
-            st = bootstrap_statistics(data, statistic, n_resamples, s, take_first_only, batch, generator)
+            if bayesian:
+                st = bayesian_bootstrap_statistics(data, statistic, n_resamples, s, batch)
+            else:
+                st = bootstrap_statistics(data, statistic, n_resamples, s, take_first_only, batch, generator)
             full = statistic(data.unsqueeze(0)) if method == 'basic' else None
             res.append(summarize(st, confidence_level, method, full))
     return res[0] if len(sizes) == 1 else res

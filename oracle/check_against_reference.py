@@ -148,6 +148,16 @@ def check_analysis(ref, fails):
                 _same(ra[k], rb[k], f'bootstrap {kw} [{i}] {k}', fails)
             for k in ('low', 'high'):
                 _same(ra['confidence_interval'][k], rb['confidence_interval'][k], f'bootstrap {kw} [{i}] ci {k}', fails)
+    # Bayesian bootstrap: Dirichlet weights from the global generator
+    for kw in [dict(n_resamples=15, batch=4), dict(n_resamples=9, bootstrap_sample_size=[300], take_first_only=True)]:
+        torch.manual_seed(5)
+        a = ao.bootstrap(w, ao.fep_estimator, bayesian=True, **kw)
+        torch.manual_seed(5)
+        b = ref.bootstrap(w, ref.fep_estimator, bayesian=True, **kw)
+        for k in ('standard_deviation', 'mean', 'median'):
+            _same(a[k], b[k], f'bayesian bootstrap {kw} {k}', fails)
+        for k in ('low', 'high'):
+            _same(a['confidence_interval'][k], b['confidence_interval'][k], f'bayesian bootstrap {kw} ci {k}', fails)
     a = ao.bootstrap(wb, ao.fep_estimator, n_resamples=12, batch=5, generator=torch.Generator().manual_seed(2))
     b = ref.bootstrap(wb, ref.fep_estimator, n_resamples=12, batch=5, generator=torch.Generator().manual_seed(2))
     _same(a['mean'], b['mean'], 'bootstrap biased mean', fails)

@@ -112,6 +112,34 @@ def test_philox_bootstrap_is_statistically_equivalent():
     assert 0.85 < float(b['standard_deviation']) / float(a['standard_deviation']) < 1.18
 
 
+def test_bayesian_bootstrap_statistical_parity():
+    """Bayesian bootstrap (Dirichlet(1..1) weights; reference bootstrap.py:236-262).  The reference draws the
+    weights from the global generator, so parity is statistical: the fused streaming kernel, the generic
+    weight-matrix path of this package and the oracle (= reference, pinned in oracle/check_against_reference.py)
+    must give the same bootstrap distribution."""
+    from tfep_b200.analysis import bootstrap, fep_estimator
+    n, R = 4000, 3000
+    w = cases.normal((n,), 6)
+    torch.manual_seed(11)
+    ref = ao.bootstrap(w, ao.fep_estimator, n_resamples=R, bayesian=True)
+    torch.manual_seed(12)
+    fused = bootstrap(w.to(DEV), fep_estimator, n_resamples=R, bayesian=True)
+    generic = bootstrap(w.to(DEV), lambda d, weights=None, vectorized=False: fep_estimator(d, weights=weights, vectorized=vectorized),
+                        n_resamples=400, batch=100, bayesian=True)
+    sd = float(ref['standard_deviation'])
+    for got, r in ((fused, R), (generic, 400)):
+        assert abs(float(got['mean']) - float(ref['mean'])) < 5 * 2 ** 0.5 * sd / min(r, R) ** 0.5
+        assert 0.8 < float(got['standard_deviation']) / sd < 1.25
+    assert abs(float(fused['confidence_interval']['low']) - float(ref['confidence_interval']['low'])) < 0.5 * sd
+    assert abs(float(fused['confidence_interval']['high']) - float(ref['confidence_interval']['high'])) < 0.5 * sd
+    # sample-size sweep with take_first_only and the argument checks of the reference
+    sizes = bootstrap(w.to(DEV), fep_estimator, n_resamples=200, bayesian=True, bootstrap_sample_size=[500, 2000],
+                      take_first_only=True)
+    assert len(sizes) == 2 and float(sizes[0]['standard_deviation']) > float(sizes[1]['standard_deviation'])
+    with pytest.raises(ValueError, match='only when take_first_only'):
+        bootstrap(w.to(DEV), fep_estimator, bayesian=True, bootstrap_sample_size=[100])
+
+
 def test_sharded_partials_add_up_on_one_gpu():
     """Emulate two batch shards on one GPU: per-shard kernels + the host combine == the unsharded result."""
     from tfep_b200 import _ops

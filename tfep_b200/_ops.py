@@ -284,6 +284,17 @@ def bootstrap_sums(e, max_idx, n_resamples, sample_size, idx=None, philox_seed=0
     return out
 
 
+def bayesian_bootstrap_sums(e, n_resamples, philox_seed=0, philox_offset=0):
+    """Per-resample ``(sum_i e_i g_ri, sum_i g_ri)`` with Exp(1) variates g (Dirichlet(1..1) weights, unnormalised)."""
+    require_cuda(e)
+    s = torch.empty(n_resamples, dtype=torch.float64, device=e.device)
+    g = torch.empty(n_resamples, dtype=torch.float64, device=e.device)
+    with torch.cuda.device(e.device):
+        check(_lib.load().tfepb_bayesian_bootstrap_sums(ptr(e), e.numel(), int(n_resamples), int(philox_seed),
+                                                        int(philox_offset), ptr(s), ptr(g), stream_ptr(e)))
+    return s, g
+
+
 def mt19937_seed(seed):
     st = torch.empty(625, dtype=torch.int32)
     check(_lib.load().tfepb_mt19937_seed(ctypes.c_uint32(seed & 0xffffffff), ptr(st)))

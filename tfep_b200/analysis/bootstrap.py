@@ -83,8 +83,6 @@ def bootstrap(
     elif bayesian and not take_first_only:
         raise ValueError('With Bayesian bootstrapping, specifying a bootstrap_sample_size '
                          'is supported only when take_first_only is True.')
-    if bayesian:
-        raise NotImplementedError('tfep_b200: Bayesian bootstrapping is not implemented yet')
     if rng not in ('mt19937', 'philox'):
         raise ValueError("rng must be 'mt19937' or 'philox'")
     if batch is None:
@@ -93,8 +91,11 @@ def bootstrap(
     with torch.no_grad():
         results = []
         for sample_size in bootstrap_sample_size:
-            stats = _bootstrap_statistics(data, statistic, n_resamples, sample_size, take_first_only, batch,
-                                          generator, rng)
+            if bayesian:
+                stats = _bayesian_bootstrap_statistics(data[:sample_size], statistic, n_resamples, batch)
+            else:
+                stats = _bootstrap_statistics(data, statistic, n_resamples, sample_size, take_first_only, batch,
+                                              generator, rng)
             alpha = (1 - confidence_level) / 2
             quantiles = torch.tensor([alpha, 1 - alpha], dtype=stats.dtype, device=stats.device)
             ci_l, ci_u = torch.quantile(stats, q=quantiles)
@@ -170,4 +171,34 @@ def _bootstrap_statistics(data, statistic, n_resamples, sample_size, take_first_
         stats[k:k + nb] = statistic(torch.gather(expanded, dim=1, index=idx), vectorized=True)
     if state is not None:
         _state_to_generator(gen, state)
+    return stats
+
+
+def _bayesian_bootstrap_statistics(data, statistic, n_resamples, batch):
+    """Statistics under Dirichlet(1, ..., 1) sample weights (reference bootstrap.py:236-262).
+
+    The reference draws the weights from the global generator (``Dirichlet.sample``; no generator argument), so
+    only statistical parity is defined.  With this package's ``fep_estimator`` on 1-D work values the weights are
+    never materialised: Dirichlet(1..1) = normalised Exp(1) variates g, and
+    ``-kT logsumexp(v + log(g / sum g)) = -kT (log sum_i e^{v_i} g_i - log sum_i g_i)`` is one streaming pass per
+    resample (tfepb_bayesian_bootstrap_sums).  Any other statistic receives a ``(batch, n)`` weight matrix."""
+    n = len(data)
+    kT = _fused_kT(statistic)
+    if kT is not None and data.dim() == 1:
+        scale = -1.0 / kT
+        o = _ops.lse(data, scale)
+        e = _ops.exp_table(data, scale, o[:1])
+        seed = int(torch.randint(0, 2**62, (1,)).item())
+        stats = torch.empty(n_resamples, dtype=torch.float64, device=data.device)
+        for k in range(0, n_resamples, 65535):
+            nb = min(65535, n_resamples - k)
+            s, g = _ops.bayesian_bootstrap_sums(e, nb, seed, k * ((n + 3) // 4))
+            stats[k:k + nb] = -kT * (o[0] + torch.log(s) - torch.log(g))
+        return stats.to(data.dtype)
+    stats = torch.empty(n_resamples, dtype=data.dtype, device=data.device)
+    dirichlet = torch.distributions.Dirichlet(torch.ones(n, dtype=data.dtype, device=data.device))
+    for k in range(0, n_resamples, batch):
+        nb = min(batch, n_resamples - k)
+        weights = dirichlet.sample((nb,))
+        stats[k:k + nb] = statistic(data.expand((nb, *data.shape)), weights=weights, vectorized=True)
     return stats

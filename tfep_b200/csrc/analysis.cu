@@ -270,6 +270,61 @@ __global__ void __launch_bounds__(BS_THREADS) bootstrap_sums_kernel(const float*
 }
 
 // ---------------------------------------------------------------------------------------------
+// Bayesian bootstrap (analysis/bootstrap.py:236-262 with statistic = fep_estimator, estimator.py:78-79):
+// sample weights ~ Dirichlet(1, ..., 1) = normalised Exp(1) variables g_ri = -log(u_ri), so that
+//     -kT logsumexp(v_i + log weight_ri) = -kT [ log sum_i e^{v_i} g_ri - log sum_i g_ri ].
+// One streaming pass per resample over the exp table (coalesced, no batch x n weight matrix): the uniforms
+// come from Philox4x32-10 in registers, counter = (resample, sample / 4).
+// grid = (chunks of BS_CHUNK samples, resamples); out_s[r] += sum e_i g_ri, out_g[r] += sum g_ri.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float exp1_variate(uint32_t u) {
+    // u uniform on {0, .., 2^32 - 1} -> (u + 0.5) 2^-32 in (0, 1); -log of it
+    return -0.6931471805599453f * __log2f(((float)(u >> 8) + 0.5f) * (1.0f / 16777216.0f));
+}
+
+__global__ void __launch_bounds__(BS_THREADS) bayesian_sums_kernel(const float* __restrict__ e, int64_t n, uint64_t seed,
+                                                                   uint64_t offset, double* __restrict__ out_s,
+                                                                   double* __restrict__ out_g) {
+    const int r = blockIdx.y;
+    const int64_t j0 = (int64_t)blockIdx.x * BS_CHUNK;
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    float s0 = 0.f, s1 = 0.f, g0 = 0.f, g1 = 0.f;
+    const bool vec = (reinterpret_cast<uintptr_t>(e) & 15) == 0;
+#pragma unroll 2
+    for (int k = 0; k < BS_DRAWS_PER_THREAD / 4; ++k) {
+        const int64_t j = j0 + ((int64_t)k * BS_THREADS + threadIdx.x) * 4;      // 4 consecutive samples per Philox call
+        if (j < n) {
+            const uint64_t c = offset + ((uint64_t)r * (uint64_t)((n + 3) / 4)) + (uint64_t)(j >> 2);
+            const uint4 u = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), key);
+            const float a = exp1_variate(u.x), b = exp1_variate(u.y), cc = exp1_variate(u.z), d = exp1_variate(u.w);
+            if (vec && j + 3 < n) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(e + j));
+                s0 = fmaf(v.x, a, s0); s1 = fmaf(v.y, b, s1); s0 = fmaf(v.z, cc, s0); s1 = fmaf(v.w, d, s1);
+                g0 += a + cc; g1 += b + d;
+            } else {
+                s0 = fmaf(__ldg(e + j), a, s0); g0 += a;
+                if (j + 1 < n) { s1 = fmaf(__ldg(e + j + 1), b, s1); g1 += b; }
+                if (j + 2 < n) { s0 = fmaf(__ldg(e + j + 2), cc, s0); g0 += cc; }
+                if (j + 3 < n) { s1 = fmaf(__ldg(e + j + 3), d, s1); g1 += d; }
+            }
+        }
+    }
+    double s = (double)s0 + (double)s1, g = (double)g0 + (double)g1;
+    s = warp_sum(s);
+    g = warp_sum(g);
+    __shared__ double ws[BS_THREADS / 32], wg[BS_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) { ws[threadIdx.x >> 5] = s; wg[threadIdx.x >> 5] = g; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < BS_THREADS / 32 ? ws[threadIdx.x] : 0.0;
+        g = threadIdx.x < BS_THREADS / 32 ? wg[threadIdx.x] : 0.0;
+        s = warp_sum(s);
+        g = warp_sum(g);
+        if (threadIdx.x == 0) { atomicAdd(out_s + r, s); atomicAdd(out_g + r, g); }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // MT19937: one CTA advances the 624-word state by whole twists (three dependency-free spans of
 // 227 words, see oracle/analysis_oracle.py) and tempers / reduces the outputs modulo max_idx.
 // The stream is inherently sequential, so a single CTA is used; jump-ahead is future work.
@@ -391,6 +446,21 @@ extern "C" int tfepb_bootstrap_sums(const float* e, int64_t n, int64_t shard_lo,
     bootstrap_sums_kernel<<<grid, BS_THREADS, 0, s>>>(e, max_idx, idx, ldidx, sample_size, philox_seed, philox_offset,
                                                       (uint32_t)shard_lo, (uint32_t)n, out_sums);
     return check_launch("bootstrap_sums");
+}
+
+extern "C" int tfepb_bayesian_bootstrap_sums(const float* e, int64_t n, int32_t n_resamples, uint64_t philox_seed,
+                                             uint64_t philox_offset, double* out_sums, double* out_weight_sums,
+                                             tfepb_stream_t stream) {
+    TFEPB_CHECK_ARG(e && out_sums && out_weight_sums, "null buffer");
+    TFEPB_CHECK_ARG(n > 0 && n_resamples > 0, "bad sizes");
+    TFEPB_CHECK_ARG(n_resamples <= 65535, "at most 65535 resamples per call");
+    if (int rc = require_sm100()) return rc;
+    cudaStream_t s = as_stream(stream);
+    TFEPB_CUDA(cudaMemsetAsync(out_sums, 0, sizeof(double) * n_resamples, s));
+    TFEPB_CUDA(cudaMemsetAsync(out_weight_sums, 0, sizeof(double) * n_resamples, s));
+    dim3 grid((unsigned)((n + BS_CHUNK - 1) / BS_CHUNK), (unsigned)n_resamples);
+    bayesian_sums_kernel<<<grid, BS_THREADS, 0, s>>>(e, n, philox_seed, philox_offset, out_sums, out_weight_sums);
+    return check_launch("bayesian_bootstrap_sums");
 }
 
 extern "C" int tfepb_mt19937_seed(uint32_t seed, uint32_t* state625_host) {
