@@ -77,3 +77,47 @@ def test_combine_partials_is_order_and_split_invariant():
         parts = torch.stack([_partial(c) for c in torch.tensor_split(v, cuts)])
         m, s = combine_partials(parts)
         assert abs(float(m + torch.log(s)) - float(whole[0] + torch.log(whole[1]))) < 1e-12
+
+
+def _grad_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from tfep_b200.utils.data_parallel import allreduce_gradients, broadcast_parameters, shard_bounds
+        torch.manual_seed(100 + rank)                      # different initial weights per rank on purpose
+        net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ELU(), torch.nn.Linear(7, 3))
+        broadcast_parameters(net)
+        torch.manual_seed(1)
+        x = torch.randn(40, 5)
+        lo, hi = shard_bounds(40)
+        # mean loss over the GLOBAL batch = sum over ranks of (local sum / n_global)
+        loss = (net(x[lo:hi]) ** 2).sum() / 40
+        loss.backward()
+        n = allreduce_gradients(net, average=False)
+        ref = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ELU(), torch.nn.Linear(7, 3))
+        ref.load_state_dict(net.state_dict())
+        ((ref(x) ** 2).sum() / 40).backward()
+        err = max(float((a.grad - b.grad).abs().max()) for a, b in zip(net.parameters(), ref.parameters()))
+        out.put((rank, err, n, (lo, hi)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_matches_full_batch():
+    """Data-parallel training step: gradients of the batch-sharded loss, added with one flat all-reduce,
+    equal the single-process gradients of the full batch (weights broadcast from rank 0 first)."""
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(r[3] for r in res) == [(0, 20), (20, 40)]
+    for rank, err, n, _ in res:
+        assert err < 1e-6 and n == 5 * 7 + 7 + 7 * 3 + 3, (rank, err, n)
