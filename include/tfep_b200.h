@@ -320,7 +320,10 @@ typedef struct {
     const tfepb_sweep_group_part* group_parts;   /* device */
     const int32_t* ids;                          /* device */
     const int32_t* fixed_cols;                   /* device: conditioning features copied from y (may be NULL) */
-    int32_t n_fixed, reserved;
+    int32_t n_fixed;
+    int32_t max_group_weight_elems;              /* max over groups of the elements of all weight rows the group uses
+                                                    (rows x leading dimension, output + hidden layers); 0 = unknown:
+                                                    the kernel then reads weights through L1 instead of staging them */
 } tfepb_sweep_args;
 int tfepb_maf_inverse_sweep(const tfepb_sweep_args* a, tfepb_stream_t stream);
 

@@ -94,7 +94,7 @@ class SweepArgs(Structure):
                 ('w', c_void_p * 5), ('b', c_void_p * 5), ('n_out', c_int32 * 5), ('ldw', c_int32 * 5),
                 ('groups', c_void_p), ('n_groups', c_int32), ('max_params', c_int32),
                 ('parts', c_void_p), ('group_parts', c_void_p), ('ids', c_void_p), ('fixed_cols', c_void_p),
-                ('n_fixed', c_int32), ('reserved', c_int32)]
+                ('n_fixed', c_int32), ('max_group_weight_elems', c_int32)]
 
 
 # every symbol include/tfep_b200.h declares: name -> (restype, argtypes)

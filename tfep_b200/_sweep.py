@@ -160,6 +160,10 @@ class SweepPlan:
         a.parts, a.group_parts, a.ids = tb['parts'].data_ptr(), tb['gparts'].data_ptr(), tb['ids'].data_ptr()
         a.fixed_cols = None if tb['fixed'] is None else tb['fixed'].data_ptr()
         a.n_fixed = 0 if tb['fixed'] is None else len(self.fixed_host)
+        ldw = [w.shape[1] for w in ws]
+        a.max_group_weight_elems = max(
+            [int(r['out_r1'] - r['out_r0']) * ldw[self.L - 1] +
+             sum(int(r['h_b'][l - 1] - r['h_a'][l - 1]) * ldw[l - 1] for l in range(1, self.L)) for r in self.groups_host] + [0])
         with torch.cuda.device(y.device):
             check(_lib.load().tfepb_maf_inverse_sweep(ctypes.byref(a), stream_ptr(y)))
         return x, ld

@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "tx_math.cuh"
 #include "tx_ops.cuh"
+#include "tc_ptx.cuh"
 
 namespace tfepb {
 namespace sweep {
@@ -56,12 +57,13 @@ struct Params {
     const tfepb_sweep_group_part* gparts;
     const int* ids;
     const int* fixed_cols; int n_fixed;
+    int stage_elems;                  // weights of one degree group (elements), staged kernel only
 };
 
 // out[s][ocol0 + (r - r0)] = act(bias[r] + sum_k W[r][k] in[s][k]) for r in [r0, r1), all TS samples of the tile.
 // Ends with a CTA barrier.  K is rounded up to the vector width: the host pads the weight rows with zeros and
 // activations that do not exist yet are zero.
-template <typename T, int TS, int THREADS>
+template <typename T, int TS, int THREADS, bool WSMEM = false>
 __device__ void gemv_stage(const T* __restrict__ W, int ldw, const T* __restrict__ bias, int r0, int r1, int K,
                            const T* in, int ldin, T* out, int ldout, int ocol0, bool act, T* scratch) {
     using V = typename Vec<T>::type;
@@ -96,7 +98,8 @@ __device__ void gemv_stage(const T* __restrict__ W, int ldw, const T* __restrict
 #pragma unroll
             for (int j = 0; j < RB; ++j) {
                 if (j < nr) {
-                    const V wv = __ldg(reinterpret_cast<const V*>(wrow + (size_t)j * ldw) + kv);
+                    const V* wp = reinterpret_cast<const V*>(wrow + (size_t)j * ldw) + kv;
+                    const V wv = WSMEM ? *wp : __ldg(wp);
                     acc[j] = dot_acc(wv, h, acc[j]);
                 }
             }
@@ -222,6 +225,95 @@ __global__ void __launch_bounds__(THREADS) maf_inverse_sweep_kernel(const Params
     }
 }
 
+// Same sweep with the weights of every degree group STAGED in shared memory: one elected thread bulk-copies the
+// rows of degree d + 1 (output rows + hidden rows, full width, contiguous in the packed matrices) into the other
+// half of a double buffer while the CTA works on degree d, so the dot products read their weights as
+// conflict-free shared-memory broadcasts instead of waiting on L1 / L2 (the unstaged kernel is latency bound on
+// exactly those loads).  Used when the tile state of 32 samples plus two groups of weights fit (fp32, cfg1 / cfg2).
+template <typename T, int TS, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) maf_inverse_sweep_staged_kernel(const Params<T> p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    T* act[MAXL];
+    T* cur = reinterpret_cast<T*>(smem_raw);
+    for (int l = 0; l < p.n_linear; ++l) { act[l] = cur; cur += (size_t)TS * p.act_ld[l]; }
+    T* par = cur; cur += (size_t)TS * p.par_ld;
+    T* scratch = cur; cur += (size_t)(THREADS / 32 / (TS / 32)) * RB * TS;
+    T* ldacc = cur; cur += TS;
+    cur = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(cur) + 127) & ~(uintptr_t)127);
+    T* wbuf[2] = {cur, cur + p.stage_elems};
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cur + 2 * (size_t)p.stage_elems);
+    const int L = p.n_linear;
+    const int n_tiles = (p.batch + TS - 1) / TS;
+    if (threadIdx.x == 0) {
+        tc::mbar_init(&bars[0], 1);
+        tc::mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t issued = 0, waited = 0;          // groups issued / consumed so far (buffer = count & 1, phase = count >> 1)
+    // issue the copies of group gi into its buffer; offsets: output rows first, then the hidden layers in order
+    auto prefetch = [&](int gi) {
+        const tfepb_sweep_group g = p.groups[gi];
+        T* dst = wbuf[issued & 1];
+        uint64_t* bar = &bars[issued & 1];
+        uint32_t bytes = 0;
+        const uint32_t ob = (uint32_t)(g.out_r1 - g.out_r0) * p.ldw[L - 1] * sizeof(T);
+        bytes += ob;
+        for (int l = 1; l < L; ++l) bytes += (uint32_t)(g.h_b[l - 1] - g.h_a[l - 1]) * p.ldw[l - 1] * sizeof(T);
+        if (bytes == 0) { tc::mbar_arrive(bar); ++issued; return; }
+        tc::mbar_expect_tx(bar, bytes);
+        if (ob) tc::bulk_g2s(dst, p.w[L - 1] + (size_t)g.out_r0 * p.ldw[L - 1], ob, bar);
+        T* d = dst + (size_t)(g.out_r1 - g.out_r0) * p.ldw[L - 1];
+        for (int l = 1; l < L; ++l) {
+            const uint32_t hb = (uint32_t)(g.h_b[l - 1] - g.h_a[l - 1]) * p.ldw[l - 1] * sizeof(T);
+            if (hb) tc::bulk_g2s(d, p.w[l - 1] + (size_t)g.h_a[l - 1] * p.ldw[l - 1], hb, bar);
+            d += (size_t)(g.h_b[l - 1] - g.h_a[l - 1]) * p.ldw[l - 1];
+        }
+        ++issued;
+    };
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t tile0 = (int64_t)tile * TS;
+        const int rows = min(TS, p.batch - (int)tile0);
+        if (threadIdx.x == 0 && p.n_groups > 0) prefetch(0);
+        for (int l = 0; l < L; ++l)
+            for (int i = threadIdx.x; i < TS * p.act_ld[l]; i += THREADS) act[l][i] = T(0);
+        if (threadIdx.x < TS) ldacc[threadIdx.x] = T(0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < rows * p.n_fixed; i += THREADS) {
+            const int s = i / p.n_fixed, c = p.fixed_cols[i - s * p.n_fixed];
+            act[0][(size_t)s * p.act_ld[0] + c] = p.y[(tile0 + s) * p.ldy + c];
+        }
+        __syncthreads();
+        for (int gi = 0; gi < p.n_groups; ++gi) {
+            const tfepb_sweep_group g = p.groups[gi];
+            // every thread is past the stages of group gi - 1 (CTA barrier): its buffer may be refilled
+            if (threadIdx.x == 0 && gi + 1 < p.n_groups) prefetch(gi + 1);
+            tc::mbar_wait(&bars[waited & 1], (waited >> 1) & 1, nullptr, 0);
+            const T* wsm = wbuf[waited & 1];
+            ++waited;
+            if (g.out_r1 > g.out_r0) {
+                gemv_stage<T, TS, THREADS, true>(wsm - (size_t)g.out_r0 * p.ldw[L - 1], p.ldw[L - 1], p.b[L - 1], g.out_r0, g.out_r1,
+                                                 g.out_k, act[L - 1], p.act_ld[L - 1], par, p.par_ld, 0, false, scratch);
+                transform_stage<T, TS, THREADS>(p, g, tile0, rows, act[0], par, ldacc);
+            }
+            const T* wh = wsm + (size_t)(g.out_r1 - g.out_r0) * p.ldw[L - 1];
+            for (int l = 1; l < L; ++l) {
+                gemv_stage<T, TS, THREADS, true>(wh - (size_t)g.h_a[l - 1] * p.ldw[l - 1], p.ldw[l - 1], p.b[l - 1], g.h_a[l - 1],
+                                                 g.h_b[l - 1], g.h_k[l - 1], act[l - 1], p.act_ld[l - 1], act[l], p.act_ld[l],
+                                                 g.h_a[l - 1], true, scratch);
+                wh += (size_t)(g.h_b[l - 1] - g.h_a[l - 1]) * p.ldw[l - 1];
+            }
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < rows * p.D; i += THREADS) {
+            const int s = i / p.D, c = i - s * p.D;
+            p.x[(tile0 + s) * p.ldx + c] = act[0][(size_t)s * p.act_ld[0] + c];
+        }
+        if (threadIdx.x < rows) p.logdet[tile0 + threadIdx.x] = ldacc[threadIdx.x];
+        __syncthreads();
+    }
+}
+
 template <typename T>
 size_t smem_bytes(const Params<T>& p, int TS, int THREADS) {
     size_t n = 0;
@@ -259,23 +351,27 @@ int launch(const tfepb_sweep_args* a, cudaStream_t stream) {
     p.par_ld = a->max_params < 1 ? 1 : a->max_params;
     p.groups = a->groups; p.n_groups = a->n_groups; p.parts = a->parts; p.gparts = a->group_parts; p.ids = a->ids;
     p.fixed_cols = a->fixed_cols; p.n_fixed = a->n_fixed;
-    // Tile shapes, in order of preference: two independent CTAs of 128 threads x 32 samples per SM (while one
-    // is in the single-warp transformer stage or at a barrier the other one multiplies), else one CTA of
-    // 256 threads with 64 or 32 samples.
+    // Tile shapes, in order of preference: (a) 32 samples with the weights of two degree groups staged in shared
+    // memory; (b) two independent CTAs of 128 threads x 32 samples per SM (while one is in the single-warp
+    // transformer stage or at a barrier the other one multiplies); (c) one CTA of 256 threads with 64 or 32 samples.
     const size_t limit = 227 * 1024, half = 113 * 1024;
     const size_t s32x128 = smem_bytes(p, 32, 128), s64 = smem_bytes(p, 64, 256), s32 = smem_bytes(p, 32, 256);
     TFEPB_CHECK_ARG(s32 <= limit, "the activations of 32 samples (%zu bytes) exceed the shared memory of an SM", s32);
-    int TS, per_sm;
+    int TS, per_sm, threads = 256;
     size_t smem;
     void (*kernel)(const Params<T>);
-    if (s32x128 <= half) { kernel = maf_inverse_sweep_kernel<T, 32, 128>; TS = 32; smem = s32x128; per_sm = 2; }
+    p.stage_elems = (a->max_group_weight_elems + 31) / 32 * 32;
+    const size_t staged = s32 + 256 + 2 * (size_t)p.stage_elems * sizeof(T) + 16;
+    if (a->max_group_weight_elems > 0 && staged <= limit) {
+        kernel = maf_inverse_sweep_staged_kernel<T, 32, 256>; TS = 32; smem = staged; per_sm = 1;
+    } else if (s32x128 <= half) { kernel = maf_inverse_sweep_kernel<T, 32, 128>; TS = 32; smem = s32x128; per_sm = 2; threads = 128; }
     else if (s64 <= limit) { kernel = maf_inverse_sweep_kernel<T, 64, 256>; TS = 64; smem = s64; per_sm = 1; }
     else { kernel = maf_inverse_sweep_kernel<T, 32, 256>; TS = 32; smem = s32; per_sm = 1; }
     TFEPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int n_tiles = (a->batch + TS - 1) / TS;
     const int cap = sm_count() * per_sm;
     const int grid = n_tiles < cap ? n_tiles : cap;
-    kernel<<<grid, per_sm == 2 ? 128 : 256, smem, stream>>>(p);
+    kernel<<<grid, threads, smem, stream>>>(p);
     return check_launch("maf_inverse_sweep_kernel");
 }
 
