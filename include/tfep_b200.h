@@ -159,6 +159,13 @@ typedef struct {
     void* grad_par;                           /* same addressing as io->par */
 } tfepb_tx_grads;
 int tfepb_affine_backward(const tfepb_tx_io* io, const tfepb_tx_grads* g, tfepb_stream_t stream);
+/* Volume-preserving shift y = x + b (VolumePreservingShiftTransformer, nn/transformers/affine.py:148-275, 366-456);
+ * `period[f]` > 0 wraps feature f as (x + b) % period + lower[f] (tables of n_features values, dtype of the call);
+ * one parameter per feature, log-det = 0. */
+int tfepb_shift(const tfepb_tx_io* io, const void* period, const void* lower, tfepb_stream_t stream);
+int tfepb_shift_backward(const tfepb_tx_io* io, const void* period, const void* lower, const tfepb_tx_grads* g,
+                         tfepb_stream_t stream);
+
 int tfepb_spline_backward(const tfepb_tx_io* io, const tfepb_spline_cfg* cfg, const tfepb_tx_grads* g,
                           tfepb_stream_t stream);
 int tfepb_sos_backward(const tfepb_tx_io* io, int32_t n_polynomials, const tfepb_tx_grads* g,
@@ -282,7 +289,7 @@ int tfepb_maf_spline_inverse_bf16(const tfepb_fused_inv_args* a, tfepb_stream_t 
  * `groups` lists, in ascending degree, the output rows and the hidden units that become computable.
  * -------------------------------------------------------------------------------------------- */
 #define TFEPB_SWEEP_MAX_LINEAR 5
-enum { TFEPB_SWEEP_AFFINE = 0, TFEPB_SWEEP_SPLINE = 1, TFEPB_SWEEP_MOEBIUS = 2 };
+enum { TFEPB_SWEEP_AFFINE = 0, TFEPB_SWEEP_SPLINE = 1, TFEPB_SWEEP_MOEBIUS = 2, TFEPB_SWEEP_SHIFT = 3 };
 
 typedef struct {
     int32_t out_r0, out_r1, out_k;       /* output-layer rows of the group and the reduction length they need */
@@ -296,7 +303,8 @@ typedef struct {
     int32_t kind;                        /* TFEPB_SWEEP_* */
     int32_t n_bins, circular, identity_boundary_slopes, learn_lower_bound, learn_upper_bound;   /* spline */
     int32_t dimension, unit_sphere;      /* moebius */
-    const void *x0, *xf, *y0, *yf;       /* spline domain per feature of the part (dtype of the call) */
+    const void *x0, *xf, *y0, *yf;       /* spline domain per feature of the part (dtype of the call);
+                                            shift: x0 = period table (0 = not periodic), xf = lower-limit table */
     double min_bin_size, min_slope, max_radius;
     const int32_t* cols;                 /* feature -> column of x / y, or NULL */
     const int32_t* par_base;             /* feature -> first packed output row of its parameters */

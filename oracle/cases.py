@@ -72,6 +72,8 @@ def as_double(spec):
                          min_bin_size=spec.min_bin_size, min_slope=spec.min_slope)
     if isinstance(spec, fo.Mixed):
         return fo.Mixed([as_double(t) for t in spec.transformers], [i.tolist() for i in spec.indices])
+    if isinstance(spec, fo.Shift) and spec.periodic_limits is not None:
+        return fo.Shift(spec.periodic_indices, spec.periodic_limits.double())
     return spec
 
 
@@ -96,6 +98,10 @@ def transformer_cases(dtype=torch.float32):
         cases[name] = (spec, n, x, par)
 
     add('affine', fo.Affine(), 7, normal((B, 7), 1, dtype))
+    add('shift', fo.Shift(), 5, normal((B, 5), 17, dtype))
+    add('shift_periodic', fo.Shift(periodic_indices=torch.tensor([0, 3]),
+                                   periodic_limits=torch.tensor([-math.pi, math.pi], dtype=dtype)), 5,
+        normal((B, 5), 18, dtype) * 2.0, pscale=2.0)
     add('spline_k8', _spline(6, dtype, n_bins=8), 6, normal((B, 6), 2, dtype) * 1.5)      # some in the tails
     add('spline_k5_circular', _spline(5, dtype, n_bins=5, circular=True, x0=-math.pi, xf=math.pi), 5,
         uniform((B, 5), 3, -math.pi, math.pi, dtype) * 0.999, pscale=1.5)
@@ -156,6 +162,9 @@ def maf_cases(dtype=torch.float32):
     xm[:, [2, 5]] = uniform((B, 2), 31, -math.pi, math.pi, dtype) * 0.999
     add('mixed_splines', fo.gen_degrees(6), mixed, xm)
     add('repeated_degrees', torch.tensor([0, 0, 1, 2, 2, 2, 1]), fo.Affine(), normal((B, 7), 32, dtype))
+    add('shift_periodic_cond', fo.gen_degrees(7, conditioning_indices=[3]),
+        fo.Shift(periodic_indices=torch.tensor([1, 4]), periodic_limits=torch.tensor([0.0, 2.0], dtype=dtype)),
+        normal((B, 7), 33, dtype))
     return c
 
 

@@ -19,6 +19,8 @@ from .ref_import import import_reference, reference_available
 def to_reference_transformer(ref, spec):
     if isinstance(spec, fo.Affine):
         return ref.AffineTransformer()
+    if isinstance(spec, fo.Shift):
+        return ref.VolumePreservingShiftTransformer(spec.periodic_indices, spec.periodic_limits)
     if isinstance(spec, fo.Spline):
         return ref.NeuralSplineTransformer(
             x0=spec.x0, xf=spec.xf, n_bins=spec.n_bins, y0=spec.y0, yf=spec.yf, circular=spec.circular,

@@ -159,6 +159,31 @@ class Affine(_Spec):
 
 
 @dataclass
+class Shift(_Spec):
+    """VolumePreservingShiftTransformer: nn/transformers/affine.py:148-275, 366-456."""
+    periodic_indices: Optional[torch.Tensor] = None
+    periodic_limits: Optional[torch.Tensor] = None
+    n_params_per_feature: int = 1
+
+    def identity_params(self, n):
+        return torch.zeros(n)
+
+    def _wrap(self, v):
+        if self.periodic_indices is not None:
+            lim = self.periodic_limits
+            v[:, self.periodic_indices] = v[:, self.periodic_indices] % (lim[1] - lim[0]) + lim[0]
+        return v
+
+    def forward(self, x, par):
+        y = self._wrap(x + par)
+        return y, torch.zeros(x.shape[0], dtype=x.dtype, device=x.device)
+
+    def inverse(self, y, par):
+        x = self._wrap(y - par)
+        return x, torch.zeros(y.shape[0], dtype=y.dtype, device=y.device)
+
+
+@dataclass
 class Spline(_Spec):
     """nn/transformers/spline.py:29-417 (module) and :424-650 (functional)."""
     x0: torch.Tensor = None

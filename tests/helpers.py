@@ -20,6 +20,8 @@ def to_module(spec):
     from tfep_b200.nn import transformers as T
     if isinstance(spec, fo.Affine):
         return T.AffineTransformer()
+    if isinstance(spec, fo.Shift):
+        return T.VolumePreservingShiftTransformer(spec.periodic_indices, spec.periodic_limits)
     if isinstance(spec, fo.Spline):
         return T.NeuralSplineTransformer(
             x0=spec.x0.clone(), xf=spec.xf.clone(), n_bins=spec.n_bins, y0=spec.y0.clone(), yf=spec.yf.clone(),

@@ -56,6 +56,19 @@ def affine(x, par, inverse=False, gy=None, gl=None):
     return (k[6], k[7]) if gy is not None else (k[2], k[3])
 
 
+def shift(x, par, spec, inverse=False, gy=None, gl=None):
+    """``spec``: oracle.flow_oracle.Shift."""
+    args, k = _io(x, par, gy, gl)
+    F = x.shape[1]
+    period, lower = torch.zeros(F, dtype=x.dtype), torch.zeros(F, dtype=x.dtype)
+    if spec.periodic_indices is not None:
+        lim = spec.periodic_limits.to(x.dtype)
+        period[spec.periodic_indices] = lim[1] - lim[0]
+        lower[spec.periodic_indices] = lim[0]
+    lib().hc_shift(*args, _p(period), _p(lower), ctypes.c_int(int(inverse)), ctypes.c_int(int(gy is not None)))
+    return (k[6], k[7]) if gy is not None else (k[2], k[3])
+
+
 def sos(x, par, n_poly, gy=None):
     args, k = _io(x, par, gy, None)
     lib().hc_sos(*args, ctypes.c_int(n_poly), ctypes.c_int(int(gy is not None)))

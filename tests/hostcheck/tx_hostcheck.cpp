@@ -39,6 +39,25 @@ void affine(const Io<T>& io, int inverse, int backward) {
 }
 
 template <typename T>
+void shift(const Io<T>& io, const T* period, const T* lower, int inverse, int backward) {
+    for (int b = 0; b < io.B; ++b) {
+        for (int f = 0; f < io.F; ++f) {
+            const int64_t i = (int64_t)b * io.F + f;
+            if (backward) {
+                io.gx[i] = io.gy[i];
+                io.pout(b, f).set(0, io.gy[i]);
+            } else {
+                T out;
+                if (inverse) shift_eval<T, true>(io.pin(b, f), io.x[i], period[f], lower[f], out);
+                else shift_eval<T, false>(io.pin(b, f), io.x[i], period[f], lower[f], out);
+                io.y[i] = out;
+            }
+        }
+        if (!backward) io.ld[b] = 0;
+    }
+}
+
+template <typename T>
 void sos(const Io<T>& io, int n_poly, int backward) {
     for (int b = 0; b < io.B; ++b) {
         T acc = 0;
@@ -115,6 +134,11 @@ Io<T> mk(int B, int F, int P, const void* x, const void* par, void* y, void* ld,
 
 extern "C" void hc_affine(IO_ARGS, int inverse, int backward) {
     if (f64) affine<double>(IO(double), inverse, backward); else affine<float>(IO(float), inverse, backward);
+}
+
+extern "C" void hc_shift(IO_ARGS, const void* period, const void* lower, int inverse, int backward) {
+    if (f64) shift<double>(IO(double), (const double*)period, (const double*)lower, inverse, backward);
+    else shift<float>(IO(float), (const float*)period, (const float*)lower, inverse, backward);
 }
 
 extern "C" void hc_sos(IO_ARGS, int n_poly, int backward) {

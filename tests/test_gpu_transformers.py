@@ -66,6 +66,12 @@ def test_round_trip(prec):
             d = (xi.cpu() - x).abs()
             # x = T^-1(y) amplifies the rounding of y by 1 / (dy/dx), and slopes go down to min_slope = 1e-4
             assert float(torch.minimum(d, (period - d).abs()).max()) < (5e-3 if prec == 'f32' else 1e-8), name
+        elif isinstance(spec, fo.Shift) and spec.periodic_indices is not None:
+            # the reference wraps as `v % P + lower` in both directions, which is not its own inverse: the
+            # non-periodic features must come back, the periodic ones must equal the oracle's inverse
+            keep = [i for i in range(n) if i not in spec.periodic_indices.tolist()]
+            assert rel_err(xi[:, keep], xx[:, keep]) < 50 * TOL[prec], name
+            assert rel_err(xi, spec.inverse(y.cpu(), par)[0]) < 50 * TOL[prec], name
         elif not isinstance(spec, fo.Mixed):
             assert rel_err(xi, xx) < 50 * TOL[prec], name
         # log-dets of +-16 from slopes near min_slope: the fp32 round trip cancels to ~1e-3 absolute
@@ -104,7 +110,8 @@ def test_vjp_against_oracle_autograd(prec):
         if ld.requires_grad:
             loss = loss + (ld * gl.to(DEV)).sum()
         else:
-            assert isinstance(spec, fo.SOS)          # the reference's SOS log-det carries no gradient
+            assert isinstance(spec, (fo.SOS, fo.Shift))   # the reference's SOS log-det carries no gradient; the
+                                                          # volume-preserving shift returns constant zeros
         loss.backward()
         scale = float(1 + gp_o.abs().max())
         assert rel_err(xd.grad, gx_o) < 20 * TOL[prec], name
@@ -134,12 +141,17 @@ def test_ragged_and_empty_batches():
 
 
 def test_functional_api():
-    from tfep_b200.nn.transformers import affine_transformer, affine_transformer_inverse, moebius_transformer
+    from tfep_b200.nn.transformers import (affine_transformer, affine_transformer_inverse, moebius_transformer,
+                                           volume_preserving_shift_transformer,
+                                           volume_preserving_shift_transformer_inverse)
     x, s, a = (cases.normal((9, 5), k).to(DEV) for k in (1, 2, 3))
     y, ld = affine_transformer(x, s, a)
     assert rel_err(y, x.cpu() * torch.exp(a.cpu()) + s.cpu()) < 1e-6 and rel_err(ld, a.cpu().sum(1)) < 1e-6
     xi, _ = affine_transformer_inverse(y, s, a)
     assert rel_err(xi, x) < 1e-5
+    ys, lds = volume_preserving_shift_transformer(x, s)
+    xs, _ = volume_preserving_shift_transformer_inverse(ys, s)
+    assert rel_err(ys, x.cpu() + s.cpu()) < 1e-6 and float(lds.abs().max()) == 0.0 and rel_err(xs, x) < 1e-6
     xv, wv = cases.normal((4, 3, 3), 5), cases.normal((4, 3, 3), 6)
     y, ld = moebius_transformer(xv.to(DEV), wv.to(DEV))
     y_o, ld_o = fo.Moebius(3).forward(xv.reshape(4, 9), wv.reshape(4, 9))

@@ -18,6 +18,8 @@ TOL = {torch.float32: 3e-5, torch.float64: 1e-11}
 def _run(spec, x, par, inverse=False, **kw):
     if isinstance(spec, fo.Affine):
         return hc.affine(x, par, inverse, **kw)
+    if isinstance(spec, fo.Shift):
+        return hc.shift(x, par, spec, inverse, **kw)
     if isinstance(spec, fo.SOS):
         return hc.sos(x, par, spec.n_polynomials, **{k: v for k, v in kw.items() if k == 'gy'})
     if isinstance(spec, fo.Moebius):

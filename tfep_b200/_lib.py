@@ -107,6 +107,8 @@ SYMBOLS = {
     'tfepb_masked_linear_backward_weight': (c_int32, [POINTER(LinearBwdWeightArgs), c_void_p]),
     'tfepb_affine': (c_int32, [POINTER(TxIo), c_void_p]),
     'tfepb_spline': (c_int32, [POINTER(TxIo), POINTER(SplineCfg), c_void_p]),
+    'tfepb_shift': (c_int32, [POINTER(TxIo), c_void_p, c_void_p, c_void_p]),
+    'tfepb_shift_backward': (c_int32, [POINTER(TxIo), c_void_p, c_void_p, POINTER(TxGrads), c_void_p]),
     'tfepb_sos': (c_int32, [POINTER(TxIo), c_int32, c_void_p]),
     'tfepb_moebius': (c_int32, [POINTER(TxIo), c_int32, c_double, c_int32, c_void_p]),
     'tfepb_affine_backward': (c_int32, [POINTER(TxIo), POINTER(TxGrads), c_void_p]),

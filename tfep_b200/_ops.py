@@ -178,7 +178,7 @@ def _spline_cfg(spec, dtype, device, bins=None):
 
 def transformer_apply(kind, spec, x, par, layout, n_features, *, inverse=False, cols=None, feat_ids=None,
                       y=None, logdet=None, accumulate=False, bins=None):
-    """Run one transformer kernel.  ``kind`` in {'affine','spline','sos','moebius'}; ``spec`` carries its
+    """Run one transformer kernel.  ``kind`` in {'affine','shift','spline','sos','moebius'}; ``spec`` carries its
     constants.  x / y are (batch, *) matrices addressed through ``cols``; returns (y, logdet)."""
     require_cuda(x, par)
     x, par = _rows(x), _rows(par)
@@ -197,6 +197,9 @@ def transformer_apply(kind, spec, x, par, layout, n_features, *, inverse=False, 
     with torch.cuda.device(x.device):
         if kind == 'affine':
             check(lib.tfepb_affine(ctypes.byref(io), s))
+        elif kind == 'shift':
+            period, lower = spec.tables(x.dtype, x.device)
+            check(lib.tfepb_shift(ctypes.byref(io), ptr(period), ptr(lower), s))
         elif kind == 'spline':
             cfg, keep = _spline_cfg(spec, x.dtype, x.device, bins)
             check(lib.tfepb_spline(ctypes.byref(io), ctypes.byref(cfg), s))
@@ -231,6 +234,9 @@ def transformer_vjp(kind, spec, x, par, layout, n_features, grad_y, grad_logdet,
     with torch.cuda.device(x.device):
         if kind == 'affine':
             check(lib.tfepb_affine_backward(ctypes.byref(io), ctypes.byref(g), s))
+        elif kind == 'shift':
+            period, lower = spec.tables(x.dtype, x.device)
+            check(lib.tfepb_shift_backward(ctypes.byref(io), ptr(period), ptr(lower), ctypes.byref(g), s))
         elif kind == 'spline':
             cfg, keep = _spline_cfg(spec, x.dtype, x.device)
             check(lib.tfepb_spline_backward(ctypes.byref(io), ctypes.byref(cfg), ctypes.byref(g), s))

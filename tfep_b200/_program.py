@@ -72,11 +72,12 @@ class ProgramFunction(torch.autograd.Function):
         for i, (part, layout) in enumerate(zip(parts, layouts)):
             _ops.transformer_apply(part.kind, part.spec, x, par, layout, part.n_features, inverse=inverse,
                                    cols=part.cols_on(dev), y=y, logdet=ld, accumulate=i > 0)
-            any_ld_grad = any_ld_grad or part.kind != 'sos'
+            any_ld_grad = any_ld_grad or part.kind not in ('sos', 'shift')
         ctx.save_for_backward(x, par)
         ctx.meta = (parts, layouts, inverse, passthrough)
         if not any_ld_grad:
-            ctx.mark_non_differentiable(ld)         # the reference's SOS log-det carries no gradient (sos.py:233)
+            ctx.mark_non_differentiable(ld)         # the reference's SOS log-det carries no gradient (sos.py:233);
+                                                    # the volume-preserving shift returns constant zeros
         return y, ld
 
     @staticmethod

@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import check, dtype_code, stream_ptr
 
 MAXL = 5
-KIND = {'affine': 0, 'spline': 1, 'moebius': 2}
+KIND = {'affine': 0, 'spline': 1, 'moebius': 2, 'shift': 3}
 
 GROUP_DTYPE = np.dtype([('out_r0', '<i4'), ('out_r1', '<i4'), ('out_k', '<i4'), ('h_a', '<i4', (MAXL - 1,)),
                         ('h_b', '<i4', (MAXL - 1,)), ('h_k', '<i4', (MAXL - 1,)), ('part_first', '<i4'),
@@ -106,6 +106,10 @@ class SweepPlan:
                     r['learn_lower_bound'], r['learn_upper_bound'] = int(spec.learn_lower), int(spec.learn_upper)
                     r['x0'], r['xf'], r['y0'], r['yf'] = (t.data_ptr() for t in dom)
                     r['min_bin_size'], r['min_slope'] = spec.min_bin_size, spec.min_slope
+                elif part.kind == 'shift':
+                    tabs = spec.tables(dtype, device)
+                    keep.append(tabs)
+                    r['x0'], r['xf'] = tabs[0].data_ptr(), tabs[1].data_ptr()
                 elif part.kind == 'moebius':
                     r['dimension'], r['unit_sphere'] = spec.dimension, int(spec.unit_sphere)
                     r['max_radius'] = float(spec.max_radius)

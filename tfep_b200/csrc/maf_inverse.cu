@@ -161,6 +161,9 @@ __device__ void transform_stage(const Params<T>& p, const tfepb_sweep_group& g, 
             if (d.kind == TFEPB_SWEEP_AFFINE) {
                 AffineOp<T> op;
                 for (int u = 0; u < gp.n_ids; ++u) ld += op.apply(v, s, u);
+            } else if (d.kind == TFEPB_SWEEP_SHIFT) {
+                const ShiftOp<T> op{(const T*)d.x0, (const T*)d.xf};      // period / lower tables travel in x0 / xf
+                for (int u = 0; u < gp.n_ids; ++u) ld += op.apply(v, s, u);
             } else if (d.kind == TFEPB_SWEEP_SPLINE) {
                 if (d.n_bins <= 8) {
                     const SplineOp<T, 8> op = make_spline<T, 8>(d);

@@ -138,6 +138,25 @@ extern "C" int tfepb_affine_backward(const tfepb_tx_io* io, const tfepb_tx_grads
     return run<double>(io, g, AffineOp<double>{}, as_stream(stream), "affine_backward");
 }
 
+extern "C" int tfepb_shift(const tfepb_tx_io* io, const void* period, const void* lower, tfepb_stream_t stream) {
+    if (int rc = check_io(io, nullptr)) return rc;
+    TFEPB_CHECK_ARG(period && lower, "null period / lower table");
+    if (io->dtype == TFEPB_F32)
+        return run<float>(io, nullptr, ShiftOp<float>{(const float*)period, (const float*)lower}, as_stream(stream), "shift");
+    return run<double>(io, nullptr, ShiftOp<double>{(const double*)period, (const double*)lower}, as_stream(stream), "shift");
+}
+
+extern "C" int tfepb_shift_backward(const tfepb_tx_io* io, const void* period, const void* lower, const tfepb_tx_grads* g,
+                                    tfepb_stream_t stream) {
+    TFEPB_CHECK_ARG(g != nullptr, "null gradient struct");
+    if (int rc = check_io(io, g)) return rc;
+    TFEPB_CHECK_ARG(period && lower, "null period / lower table");
+    if (io->dtype == TFEPB_F32)
+        return run<float>(io, g, ShiftOp<float>{(const float*)period, (const float*)lower}, as_stream(stream), "shift_backward");
+    return run<double>(io, g, ShiftOp<double>{(const double*)period, (const double*)lower}, as_stream(stream),
+                       "shift_backward");
+}
+
 extern "C" int tfepb_sos(const tfepb_tx_io* io, int32_t n_polynomials, tfepb_stream_t stream) {
     if (int rc = check_io(io, nullptr)) return rc;
     TFEPB_CHECK_ARG(n_polynomials >= 2, "n_polynomials must be strictly greater than 1.");

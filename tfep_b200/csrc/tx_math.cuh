@@ -4,7 +4,7 @@
 // tests/hostcheck against the oracle and used by the SIMT kernels in transformers.cu.
 //
 // Reference lines (relative to the reference's tfep/nn/transformers/):
-//   affine.py:281-363   spline.py:319-417, 424-650   sos.py:207-306   moebius.py:374-478
+//   affine.py:281-363, 366-456   spline.py:319-417, 424-650   sos.py:207-306   moebius.py:374-478
 #pragma once
 
 #include "hd_math.cuh"
@@ -46,6 +46,17 @@ TFEPB_HD void affine_vjp(const ParIn<T>& par, T x, T gy, T gl, T& gx, const ParO
     gx = gy * sc;
     gpar.set(0, gy);
     gpar.set(1, gy * x * sc + gl);
+}
+
+// ---------------------------------------------------------------------------------------------
+// volume-preserving shift: y = x + b, periodic features wrapped as (x + b) % period + lower
+// (affine.py:366-456; the reference does NOT subtract `lower` before the modulo -- reproduced)
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool INVERSE>
+TFEPB_HD void shift_eval(const ParIn<T>& par, T t, T period, T lower, T& out) {
+    T v = INVERSE ? t - par[0] : t + par[0];
+    if (period > T(0)) v = py_remainder(v, period) + lower;
+    out = v;
 }
 
 // ---------------------------------------------------------------------------------------------

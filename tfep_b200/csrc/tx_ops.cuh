@@ -54,6 +54,28 @@ struct AffineOp {
 };
 
 template <typename T>
+struct ShiftOp {
+    const T* period;     // per feature of the part: period, or 0 for a non-periodic feature
+    const T* lower;      // per feature: lower limit of the periodic range
+    __device__ int units(int F) const { return F; }
+    __device__ T apply(const TxView<T>& v, int b, int u) const {
+        const int f = v.fid(u), c = v.col(f);
+        T out;
+        if (v.inverse) shift_eval<T, true>(v.pin(b, f), v.x[(int64_t)b * v.ldx + c], period[f], lower[f], out);
+        else shift_eval<T, false>(v.pin(b, f), v.x[(int64_t)b * v.ldx + c], period[f], lower[f], out);
+        v.y[(int64_t)b * v.ldy + c] = out;
+        return T(0);
+    }
+    // the wrap is piecewise constant: dy/dx = 1, dy/db = 1, log-det = 0
+    __device__ void backward(const TxView<T>& v, int b, int u, T) const {
+        const int f = v.fid(u), c = v.col(f);
+        const T gy = v.gy[(int64_t)b * v.ldgy + c];
+        v.gx[(int64_t)b * v.ldgx + c] = gy;
+        v.pout(b, f).set(0, gy);
+    }
+};
+
+template <typename T>
 struct SosOp {
     int n_poly;
     __device__ int units(int F) const { return F; }

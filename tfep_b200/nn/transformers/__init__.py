@@ -1,6 +1,7 @@
 """Transformers for autoregressive normalizing flows (reference tfep/nn/transformers/__init__.py)."""
 
-from .affine import AffineTransformer, affine_transformer, affine_transformer_inverse
+from .affine import (AffineTransformer, VolumePreservingShiftTransformer, affine_transformer, affine_transformer_inverse,
+                     volume_preserving_shift_transformer, volume_preserving_shift_transformer_inverse)
 from .mixed import MixedTransformer
 from .moebius import MoebiusTransformer, moebius_transformer
 from .sos import SOSPolynomialTransformer, sos_polynomial_transformer
