@@ -174,6 +174,19 @@ int tfepb_moebius_backward(const tfepb_tx_io* io, int32_t dimension, double max_
                            const tfepb_tx_grads* g, tfepb_stream_t stream);
 
 /* ----------------------------------------------------------------------------------------------
+ * PeriodicEmbedding of the MADE input (nn/embeddings/mafembed.py:112-142): input column c is copied to output
+ * column out_col[c], or, if periodic[c], lifted to out[out_col[c]], out[out_col[c] + 1] =
+ * cos, sin((x - lower) * scale) with scale = 2 pi / (upper - lower).  Backward: grad_x from grad_out.
+ * -------------------------------------------------------------------------------------------- */
+int tfepb_periodic_embedding(int32_t dtype, const void* x, int64_t ldx, int32_t batch, int32_t n_in,
+                             const int32_t* out_col, const int32_t* periodic, double lower, double scale,
+                             void* out, int64_t ldo, tfepb_stream_t stream);
+int tfepb_periodic_embedding_backward(int32_t dtype, const void* x, int64_t ldx, int32_t batch, int32_t n_in,
+                                      const int32_t* out_col, const int32_t* periodic, double lower, double scale,
+                                      const void* grad_out, int64_t ldgo, void* grad_x, int64_t ldgx,
+                                      tfepb_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------------
  * Fused MAF forward on the tensor cores (tcgen05 / TMEM / bulk-copy engine), bf16 operands with fp32
  * accumulation: y, logdet = T(x ; MADE(x)) for MADEs with two hidden layers and a circular neural-spline
  * transformer with 8 bins, for a CHAIN of n_layers >= 1 MAF layers in ONE launch.  Replaces
@@ -329,6 +342,12 @@ typedef struct {
     const int32_t* ids;                          /* device */
     const int32_t* fixed_cols;                   /* device: conditioning features copied from y (may be NULL) */
     int32_t n_fixed;
+    int32_t n_embedded;                          /* width of the conditioner input: n_features, or more with an embedding */
+    const int32_t* emb_out_col;                  /* device, per column of x: first conditioner-input column (NULL = no
+                                                    embedding: the conditioner reads x itself) */
+    const int32_t* emb_periodic;                 /* device, per column of x: 1 = lifted to (cos, sin) */
+    double emb_lower, emb_scale;                 /* (x - lower) * scale is the angle of a lifted feature */
+    int32_t reserved;
     int32_t max_group_weight_elems;              /* max over groups of the elements of all weight rows the group uses
                                                     (rows x leading dimension, output + hidden layers); 0 = unknown:
                                                     the kernel then reads weights through L1 instead of staging them */

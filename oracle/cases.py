@@ -138,9 +138,10 @@ def maf_cases(dtype=torch.float32):
     B = 16
     c = {}
 
-    def add(name, degrees_in, spec, x, hidden_layers=2, weight_norm=True, seed=100, invertible=True, gain=2.0):
+    def add(name, degrees_in, spec, x, hidden_layers=2, weight_norm=True, seed=100, invertible=True, gain=2.0,
+            embedding=None):
         c[name] = dict(degrees_in=torch.as_tensor(degrees_in), spec=spec, hidden_layers=hidden_layers,
-                       weight_norm=weight_norm, x=x, seed=seed, invertible=invertible, gain=gain)
+                       weight_norm=weight_norm, x=x, seed=seed, invertible=invertible, gain=gain, embedding=embedding)
 
     add('affine_asc', fo.gen_degrees(8), fo.Affine(), normal((B, 8), 21, dtype))
     add('affine_desc_nown', fo.gen_degrees(8, order='descending'), fo.Affine(), normal((B, 8), 22, dtype),
@@ -162,6 +163,15 @@ def maf_cases(dtype=torch.float32):
     xm[:, [2, 5]] = uniform((B, 2), 31, -math.pi, math.pi, dtype) * 0.999
     add('mixed_splines', fo.gen_degrees(6), mixed, xm)
     add('repeated_degrees', torch.tensor([0, 0, 1, 2, 2, 2, 1]), fo.Affine(), normal((B, 7), 32, dtype))
+    # PeriodicEmbedding of the conditioner input (what the reference's MixedMAFMap runs, app/mixedmaf.py:341-353)
+    xe = normal((B, 7), 34, dtype)
+    xe[:, [1, 4, 5]] = uniform((B, 3), 35, 0.0, 1.0, dtype)
+    add('spline_embed_periodic', fo.gen_degrees(7, conditioning_indices=[2]),
+        fo.Mixed([_spline(3, dtype, n_bins=4, circular=True, x0=0.0, xf=1.0), _spline(3, dtype, n_bins=4, x0=-4.0, xf=4.0)],
+                 [[0, 3, 4], [1, 2, 5]]),                 # indices among the 6 mapped features: columns 1, 4, 5 are circular
+        xe, embedding=fo.PeriodicEmbed(7, [0.0, 1.0], [1, 4, 5]))
+    add('affine_embed_all_desc', fo.gen_degrees(5, order='descending'), fo.Affine(), normal((B, 5), 36, dtype),
+        hidden_layers=1, embedding=fo.PeriodicEmbed(5, torch.tensor([-math.pi, math.pi], dtype=dtype)))
     add('shift_periodic_cond', fo.gen_degrees(7, conditioning_indices=[3]),
         fo.Shift(periodic_indices=torch.tensor([1, 4]), periodic_limits=torch.tensor([0.0, 2.0], dtype=dtype)),
         normal((B, 7), 33, dtype))
@@ -170,7 +180,7 @@ def maf_cases(dtype=torch.float32):
 
 def build_oracle(case, dtype=torch.float32):
     m = fo.MafOracle(case['degrees_in'], case['spec'], hidden_layers=case['hidden_layers'],
-                     weight_norm=case['weight_norm'])
+                     weight_norm=case['weight_norm'], embedding=case.get('embedding'))
     sd = seeded_state([k.to(dtype) for k in m.masks], case['seed'], dtype, case['weight_norm'], case['gain'])
     return m.load(sd), sd
 

@@ -37,8 +37,12 @@ def to_reference_transformer(ref, spec):
 
 
 def to_reference_maf(ref, case, state_dict):
+    emb = case.get('embedding')
+    if emb is not None:
+        emb = ref.PeriodicEmbedding(emb.n_features_in, emb.limits, emb.periodic_indices)
     maf = ref.MAF(degrees_in=case['degrees_in'], transformer=to_reference_transformer(ref, case['spec']),
-                  hidden_layers=case['hidden_layers'], weight_norm=case['weight_norm'], initialize_identity=False)
+                  hidden_layers=case['hidden_layers'], embedding=emb, weight_norm=case['weight_norm'],
+                  initialize_identity=False)
     missing, unexpected = maf.load_state_dict(state_dict, strict=False)
     assert not unexpected, unexpected
     assert not [k for k in missing if 'weight' in k or 'bias' in k], missing

@@ -499,6 +499,26 @@ class Mixed(_Spec):
 # autoregressive flow
 # ---------------------------------------------------------------------------
 
+class PeriodicEmbed:
+    """PeriodicEmbedding: nn/embeddings/mafembed.py:65-172 (non-periodic features first, then (cos, sin) pairs)."""
+
+    def __init__(self, n_features_in, limits, periodic_indices=None):
+        self.n_features_in = n_features_in
+        self.limits = torch.as_tensor(limits)
+        self.periodic_indices = torch.arange(n_features_in) if periodic_indices is None else torch.as_tensor(periodic_indices)
+        allidx = torch.arange(n_features_in)
+        self.nonperiodic_indices = allidx[~torch.isin(allidx, self.periodic_indices)]
+
+    def __call__(self, x):
+        scale = 2 * torch.pi / (self.limits[1] - self.limits[0])
+        xp = (x[:, self.periodic_indices] - self.limits[0]) * scale
+        return torch.cat([x[:, self.nonperiodic_indices],
+                          torch.stack([torch.cos(xp), torch.sin(xp)], dim=2).reshape(x.shape[0], -1)], dim=1)
+
+    def get_degrees_out(self, degrees_in):
+        return torch.cat([degrees_in[self.nonperiodic_indices], degrees_in[self.periodic_indices].repeat_interleave(2)])
+
+
 class MafOracle:
     """One MAF layer evaluated from a reference-compatible ``state_dict``.
 

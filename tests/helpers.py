@@ -39,9 +39,13 @@ def to_module(spec):
 
 def to_maf(case, state_dict, device=None, dtype=None):
     """oracle MAF case (+ its seeded state) -> tfep_b200.nn.flows.MAF with the same parameters."""
+    from tfep_b200.nn.embeddings import PeriodicEmbedding
     from tfep_b200.nn.flows import MAF
+    emb = case.get('embedding')
+    if emb is not None:
+        emb = PeriodicEmbedding(emb.n_features_in, emb.limits, emb.periodic_indices)
     maf = MAF(degrees_in=case['degrees_in'], transformer=to_module(case['spec']), hidden_layers=case['hidden_layers'],
-              weight_norm=case['weight_norm'], initialize_identity=False)
+              embedding=emb, weight_norm=case['weight_norm'], initialize_identity=False)
     if dtype is not None:
         maf = maf.to(dtype)
     missing, unexpected = maf.load_state_dict(state_dict, strict=False)

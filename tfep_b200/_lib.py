@@ -94,7 +94,8 @@ class SweepArgs(Structure):
                 ('w', c_void_p * 5), ('b', c_void_p * 5), ('n_out', c_int32 * 5), ('ldw', c_int32 * 5),
                 ('groups', c_void_p), ('n_groups', c_int32), ('max_params', c_int32),
                 ('parts', c_void_p), ('group_parts', c_void_p), ('ids', c_void_p), ('fixed_cols', c_void_p),
-                ('n_fixed', c_int32), ('max_group_weight_elems', c_int32)]
+                ('n_fixed', c_int32), ('n_embedded', c_int32), ('emb_out_col', c_void_p), ('emb_periodic', c_void_p),
+                ('emb_lower', c_double), ('emb_scale', c_double), ('reserved', c_int32), ('max_group_weight_elems', c_int32)]
 
 
 # every symbol include/tfep_b200.h declares: name -> (restype, argtypes)
@@ -115,6 +116,10 @@ SYMBOLS = {
     'tfepb_spline_backward': (c_int32, [POINTER(TxIo), POINTER(SplineCfg), POINTER(TxGrads), c_void_p]),
     'tfepb_sos_backward': (c_int32, [POINTER(TxIo), c_int32, POINTER(TxGrads), c_void_p]),
     'tfepb_moebius_backward': (c_int32, [POINTER(TxIo), c_int32, c_double, c_int32, POINTER(TxGrads), c_void_p]),
+    'tfepb_periodic_embedding': (c_int32, [c_int32, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_double, c_double,
+                                           c_void_p, c_int64, c_void_p]),
+    'tfepb_periodic_embedding_backward': (c_int32, [c_int32, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_double,
+                                                    c_double, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     'tfepb_maf_spline_forward_bf16': (c_int32, [POINTER(FusedArgs), c_void_p]),
     'tfepb_maf_spline_inverse_bf16': (c_int32, [POINTER(FusedInvArgs), c_void_p]),
     'tfepb_maf_inverse_sweep': (c_int32, [POINTER(SweepArgs), c_void_p]),

@@ -34,6 +34,10 @@ def eligibility(maf, pk):
         return 'transformer does not lower to native parts'
     if pk['plan'].n_layers > MAXL:
         return 'too many linear layers'
+    if maf._embedding is not None:
+        from .nn.embeddings import PeriodicEmbedding
+        if not isinstance(maf._embedding, PeriodicEmbedding):
+            return 'only PeriodicEmbedding is applied inside the sweep kernel'
     for part in pk['parts']:
         if part.kind not in KIND:
             return f'no inverse for transformer kind {part.kind!r}'
@@ -54,6 +58,8 @@ class SweepPlan:
         L = plan.n_layers
         self.L = L
         self.D = len(maf._degrees_in_host)
+        self.E = len(plan.packed_degrees[0])           # width of the conditioner input (> D with an embedding)
+        self.embedding = maf._embedding
         groups = np.zeros(0, dtype=GROUP_DTYPE)
         gparts, ids = [], []
         rows = []
@@ -62,7 +68,7 @@ class SweepPlan:
             for l in range(1, L):
                 a, b = plan.degree_rows(l, degree)
                 rec['h_a'][l - 1], rec['h_b'][l - 1] = a, b
-                rec['h_k'][l - 1] = self.D if l == 1 else plan.degree_prefix(l - 1, degree, strict=False)
+                rec['h_k'][l - 1] = self.E if l == 1 else plan.degree_prefix(l - 1, degree, strict=False)
 
         if int(maf._degrees_in_host.min()) == -1:          # conditioning features feed hidden units of degree -1
             rec = np.zeros((), dtype=GROUP_DTYPE)
@@ -72,7 +78,7 @@ class SweepPlan:
         for gi, grp in enumerate(pk['groups']):
             rec = np.zeros((), dtype=GROUP_DTYPE)
             rec['out_r0'], rec['out_r1'] = grp['rows']
-            rec['out_k'] = self.D if L == 1 else plan.degree_prefix(L - 1, grp['degree'], strict=True)
+            rec['out_k'] = self.E if L == 1 else plan.degree_prefix(L - 1, grp['degree'], strict=True)
             rec['part_first'] = len(gparts)
             for pi, fids in enumerate(grp['ids']):
                 if fids:
@@ -164,6 +170,11 @@ class SweepPlan:
         a.parts, a.group_parts, a.ids = tb['parts'].data_ptr(), tb['gparts'].data_ptr(), tb['ids'].data_ptr()
         a.fixed_cols = None if tb['fixed'] is None else tb['fixed'].data_ptr()
         a.n_fixed = 0 if tb['fixed'] is None else len(self.fixed_host)
+        a.n_embedded = self.E
+        if self.embedding is not None:
+            out_col, periodic = self.embedding._tables(y.device)
+            a.emb_out_col, a.emb_periodic = out_col.data_ptr(), periodic.data_ptr()
+            a.emb_lower, a.emb_scale = self.embedding._lower, self.embedding._scale
         ldw = [w.shape[1] for w in ws]
         a.max_group_weight_elems = max(
             [int(r['out_r1'] - r['out_r0']) * ldw[self.L - 1] +

@@ -58,6 +58,11 @@ struct Params {
     const int* ids;
     const int* fixed_cols; int n_fixed;
     int stage_elems;                  // weights of one degree group (elements), staged kernel only
+    // optional PeriodicEmbedding of the conditioner input (nn/embeddings/mafembed.py): act[0] then holds the
+    // embedded features (width E) and x lives in its own tile
+    const int* emb_out_col; const int* emb_periodic;
+    T emb_lower, emb_scale;
+    int E, xs_ld;
 };
 
 // out[s][ocol0 + (r - r0)] = act(bias[r] + sum_k W[r][k] in[s][k]) for r in [r0, r1), all TS samples of the tile.
@@ -131,6 +136,21 @@ __device__ void gemv_stage(const T* __restrict__ W, int ldw, const T* __restrict
     __syncthreads();
 }
 
+// conditioner-input columns of x column c of sample s (identity without an embedding: x IS the conditioner input)
+template <typename T>
+__device__ __forceinline__ void embed_column(const Params<T>& p, T* act0, const T* xs, int s, int c) {
+    if (p.emb_out_col == nullptr) return;
+    const T v = xs[(size_t)s * p.xs_ld + c];
+    T* o = act0 + (size_t)s * p.act_ld[0] + p.emb_out_col[c];
+    if (p.emb_periodic[c]) {
+        const T a = (v - p.emb_lower) * p.emb_scale;
+        o[0] = cos(a);
+        o[1] = sin(a);
+    } else {
+        o[0] = v;
+    }
+}
+
 template <typename T, int MAXK>
 __device__ __forceinline__ SplineOp<T, MAXK> make_spline(const tfepb_sweep_part& d) {
     SplineOp<T, MAXK> op;
@@ -144,13 +164,13 @@ __device__ __forceinline__ SplineOp<T, MAXK> make_spline(const tfepb_sweep_part&
 
 // Inverse transformer of the features of one degree group: thread s handles sample s of the tile.
 template <typename T, int TS, int THREADS>
-__device__ void transform_stage(const Params<T>& p, const tfepb_sweep_group& g, int64_t tile0, int rows, T* xs, const T* par,
-                                T* ldacc) {
+__device__ void transform_stage(const Params<T>& p, const tfepb_sweep_group& g, int64_t tile0, int rows, T* xs, T* act0,
+                                const T* par, T* ldacc) {
     const int s = threadIdx.x;
     if (s < TS && s < rows && g.part_count > 0) {
         TxView<T> v{};
         v.x = p.y + tile0 * p.ldy; v.ldx = p.ldy;          // source: y (global), local row index
-        v.y = xs; v.ldy = p.act_ld[0];                     // destination: the x tile in shared memory
+        v.y = xs; v.ldy = p.xs_ld;                         // destination: the x tile in shared memory
         v.par = par; v.ldp = p.par_ld; v.poff = -(int64_t)g.out_r0; v.sp = 1; v.sf = 0;
         v.logdet = nullptr; v.accumulate = 0; v.B = rows; v.inverse = 1;
         T ld = T(0);
@@ -178,6 +198,16 @@ __device__ void transform_stage(const Params<T>& p, const tfepb_sweep_group& g, 
             }
         }
         ldacc[s] += ld;
+        if (p.emb_out_col != nullptr) {            // lift the freshly inverted features into the conditioner input
+            for (int q = 0; q < g.part_count; ++q) {
+                const tfepb_sweep_group_part gp = p.gparts[g.part_first + q];
+                const tfepb_sweep_part& d = p.parts[gp.part];
+                for (int u = 0; u < gp.n_ids; ++u) {
+                    const int f = p.ids[gp.ids_offset + u];
+                    embed_column<T>(p, act0, xs, s, d.cols ? d.cols[f] : f);
+                }
+            }
+        }
     }
     __syncthreads();
 }
@@ -190,7 +220,8 @@ __global__ void __launch_bounds__(THREADS) maf_inverse_sweep_kernel(const Params
     for (int l = 0; l < p.n_linear; ++l) { act[l] = cur; cur += (size_t)TS * p.act_ld[l]; }
     T* par = cur; cur += (size_t)TS * p.par_ld;
     T* scratch = cur; cur += (size_t)(THREADS / 32 / (TS / 32)) * RB * TS;
-    T* ldacc = cur;
+    T* ldacc = cur; cur += TS;
+    T* xs = p.emb_out_col ? cur : act[0];
     const int L = p.n_linear;
     const int n_tiles = (p.batch + TS - 1) / TS;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -200,10 +231,13 @@ __global__ void __launch_bounds__(THREADS) maf_inverse_sweep_kernel(const Params
         for (int l = 0; l < L; ++l)
             for (int i = threadIdx.x; i < TS * p.act_ld[l]; i += THREADS) act[l][i] = T(0);
         if (threadIdx.x < TS) ldacc[threadIdx.x] = T(0);
+        if (p.emb_out_col)
+            for (int i = threadIdx.x; i < TS * p.xs_ld; i += THREADS) xs[i] = T(0);
         __syncthreads();
         for (int i = threadIdx.x; i < rows * p.n_fixed; i += THREADS) {
             const int s = i / p.n_fixed, c = p.fixed_cols[i - s * p.n_fixed];
-            act[0][(size_t)s * p.act_ld[0] + c] = p.y[(tile0 + s) * p.ldy + c];
+            xs[(size_t)s * p.xs_ld + c] = p.y[(tile0 + s) * p.ldy + c];
+            embed_column<T>(p, act[0], xs, s, c);
         }
         __syncthreads();
         // ---- degree sweep ----
@@ -212,7 +246,7 @@ __global__ void __launch_bounds__(THREADS) maf_inverse_sweep_kernel(const Params
             if (g.out_r1 > g.out_r0) {
                 gemv_stage<T, TS, THREADS>(p.w[L - 1], p.ldw[L - 1], p.b[L - 1], g.out_r0, g.out_r1, g.out_k, act[L - 1], p.act_ld[L - 1],
                                   par, p.par_ld, 0, false, scratch);
-                transform_stage<T, TS, THREADS>(p, g, tile0, rows, act[0], par, ldacc);
+                transform_stage<T, TS, THREADS>(p, g, tile0, rows, xs, act[0], par, ldacc);
             }
             for (int l = 1; l < L; ++l)
                 gemv_stage<T, TS, THREADS>(p.w[l - 1], p.ldw[l - 1], p.b[l - 1], g.h_a[l - 1], g.h_b[l - 1], g.h_k[l - 1], act[l - 1],
@@ -221,7 +255,7 @@ __global__ void __launch_bounds__(THREADS) maf_inverse_sweep_kernel(const Params
         // ---- write the tile ----
         for (int i = threadIdx.x; i < rows * p.D; i += THREADS) {
             const int s = i / p.D, c = i - s * p.D;
-            p.x[(tile0 + s) * p.ldx + c] = act[0][(size_t)s * p.act_ld[0] + c];
+            p.x[(tile0 + s) * p.ldx + c] = xs[(size_t)s * p.xs_ld + c];
         }
         if (threadIdx.x < rows) p.logdet[tile0 + threadIdx.x] = ldacc[threadIdx.x];
         __syncthreads();
@@ -242,6 +276,8 @@ __global__ void __launch_bounds__(THREADS, 1) maf_inverse_sweep_staged_kernel(co
     T* par = cur; cur += (size_t)TS * p.par_ld;
     T* scratch = cur; cur += (size_t)(THREADS / 32 / (TS / 32)) * RB * TS;
     T* ldacc = cur; cur += TS;
+    T* xs = p.emb_out_col ? cur : act[0];
+    if (p.emb_out_col) cur += (size_t)TS * p.xs_ld;
     cur = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(cur) + 127) & ~(uintptr_t)127);
     T* wbuf[2] = {cur, cur + p.stage_elems};
     uint64_t* bars = reinterpret_cast<uint64_t*>(cur + 2 * (size_t)p.stage_elems);
@@ -281,10 +317,13 @@ __global__ void __launch_bounds__(THREADS, 1) maf_inverse_sweep_staged_kernel(co
         for (int l = 0; l < L; ++l)
             for (int i = threadIdx.x; i < TS * p.act_ld[l]; i += THREADS) act[l][i] = T(0);
         if (threadIdx.x < TS) ldacc[threadIdx.x] = T(0);
+        if (p.emb_out_col)
+            for (int i = threadIdx.x; i < TS * p.xs_ld; i += THREADS) xs[i] = T(0);
         __syncthreads();
         for (int i = threadIdx.x; i < rows * p.n_fixed; i += THREADS) {
             const int s = i / p.n_fixed, c = p.fixed_cols[i - s * p.n_fixed];
-            act[0][(size_t)s * p.act_ld[0] + c] = p.y[(tile0 + s) * p.ldy + c];
+            xs[(size_t)s * p.xs_ld + c] = p.y[(tile0 + s) * p.ldy + c];
+            embed_column<T>(p, act[0], xs, s, c);
         }
         __syncthreads();
         for (int gi = 0; gi < p.n_groups; ++gi) {
@@ -297,7 +336,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_inverse_sweep_staged_kernel(co
             if (g.out_r1 > g.out_r0) {
                 gemv_stage<T, TS, THREADS, true>(wsm - (size_t)g.out_r0 * p.ldw[L - 1], p.ldw[L - 1], p.b[L - 1], g.out_r0, g.out_r1,
                                                  g.out_k, act[L - 1], p.act_ld[L - 1], par, p.par_ld, 0, false, scratch);
-                transform_stage<T, TS, THREADS>(p, g, tile0, rows, act[0], par, ldacc);
+                transform_stage<T, TS, THREADS>(p, g, tile0, rows, xs, act[0], par, ldacc);
             }
             const T* wh = wsm + (size_t)(g.out_r1 - g.out_r0) * p.ldw[L - 1];
             for (int l = 1; l < L; ++l) {
@@ -310,7 +349,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_inverse_sweep_staged_kernel(co
         }
         for (int i = threadIdx.x; i < rows * p.D; i += THREADS) {
             const int s = i / p.D, c = i - s * p.D;
-            p.x[(tile0 + s) * p.ldx + c] = act[0][(size_t)s * p.act_ld[0] + c];
+            p.x[(tile0 + s) * p.ldx + c] = xs[(size_t)s * p.xs_ld + c];
         }
         if (threadIdx.x < rows) p.logdet[tile0 + threadIdx.x] = ldacc[threadIdx.x];
         __syncthreads();
@@ -324,6 +363,7 @@ size_t smem_bytes(const Params<T>& p, int TS, int THREADS) {
     n += (size_t)TS * p.par_ld;
     n += (size_t)(THREADS / 32 / (TS / 32)) * RB * TS;
     n += TS;
+    if (p.emb_out_col) n += (size_t)TS * p.xs_ld;
     return n * sizeof(T) + 16;
 }
 
@@ -347,13 +387,17 @@ int launch(const tfepb_sweep_args* a, cudaStream_t stream) {
         TFEPB_CHECK_ARG(p.w[l] && p.b[l], "layer %d: null weights", l);
         TFEPB_CHECK_ARG(a->ldw[l] % nv == 0 && ((uintptr_t)a->w[l] % 16) == 0,
                         "layer %d: weight rows must be 16-byte aligned (pad the leading dimension)", l);
-        const int width = l == 0 ? a->n_features : a->n_out[l - 1];
+        const int width = l == 0 ? (a->emb_out_col ? a->n_embedded : a->n_features) : a->n_out[l - 1];
         TFEPB_CHECK_ARG(a->ldw[l] >= width, "layer %d: leading dimension smaller than the input width", l);
         p.act_ld[l] = padded_ld<T>(a->ldw[l] > width ? a->ldw[l] : width);
     }
     p.par_ld = a->max_params < 1 ? 1 : a->max_params;
     p.groups = a->groups; p.n_groups = a->n_groups; p.parts = a->parts; p.gparts = a->group_parts; p.ids = a->ids;
     p.fixed_cols = a->fixed_cols; p.n_fixed = a->n_fixed;
+    p.emb_out_col = a->emb_out_col; p.emb_periodic = a->emb_periodic;
+    p.emb_lower = (T)a->emb_lower; p.emb_scale = (T)a->emb_scale;
+    p.E = a->emb_out_col ? a->n_embedded : a->n_features;
+    p.xs_ld = a->emb_out_col ? a->n_features : p.act_ld[0];
     // Tile shapes, in order of preference: (a) 32 samples with the weights of two degree groups staged in shared
     // memory; (b) two independent CTAs of 128 threads x 32 samples per SM (while one is in the single-warp
     // transformer stage or at a barrier the other one multiplies); (c) one CTA of 256 threads with 64 or 32 samples.
@@ -392,6 +436,8 @@ extern "C" int tfepb_maf_inverse_sweep(const tfepb_sweep_args* a, tfepb_stream_t
     TFEPB_CHECK_ARG(a->n_groups >= 0 && (a->n_groups == 0 || (a->groups && a->parts && a->group_parts && a->ids)),
                     "null schedule table");
     TFEPB_CHECK_ARG(a->n_fixed == 0 || a->fixed_cols != nullptr, "null fixed_cols");
+    TFEPB_CHECK_ARG(a->emb_out_col == nullptr || (a->emb_periodic != nullptr && a->n_embedded >= a->n_features),
+                    "embedding tables: emb_periodic and n_embedded >= n_features are required with emb_out_col");
     if (int rc = require_sm100()) return rc;
     if (a->batch == 0) return 0;
     if (a->dtype == TFEPB_F32) return sweep::launch<float>(a, as_stream(stream));

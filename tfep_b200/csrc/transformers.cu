@@ -120,10 +120,96 @@ int check_spline(const tfepb_tx_io* io, const tfepb_spline_cfg* cfg) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// PeriodicEmbedding (nn/embeddings/mafembed.py:112-142): one thread per input element; column c goes to
+// out_col[c] (copy) or to the pair out_col[c], out_col[c] + 1 = cos, sin of (x - lower) * scale.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) periodic_embedding_kernel(const T* __restrict__ x, int64_t ldx, int batch, int n_in,
+                                                                 const int* __restrict__ out_col,
+                                                                 const int* __restrict__ periodic, T lower, T scale,
+                                                                 T* __restrict__ out, int64_t ldo) {
+    const int64_t total = (int64_t)batch * n_in;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / n_in), c = (int)(i - (int64_t)b * n_in);
+        const T v = x[(int64_t)b * ldx + c];
+        T* o = out + (int64_t)b * ldo + out_col[c];
+        if (periodic[c]) {
+            const T a = (v - lower) * scale;
+            o[0] = cos(a);
+            o[1] = sin(a);
+        } else {
+            o[0] = v;
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) periodic_embedding_backward_kernel(const T* __restrict__ x, int64_t ldx, int batch,
+                                                                          int n_in, const int* __restrict__ out_col,
+                                                                          const int* __restrict__ periodic, T lower,
+                                                                          T scale, const T* __restrict__ go, int64_t ldgo,
+                                                                          T* __restrict__ gx, int64_t ldgx) {
+    const int64_t total = (int64_t)batch * n_in;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / n_in), c = (int)(i - (int64_t)b * n_in);
+        const T* g = go + (int64_t)b * ldgo + out_col[c];
+        T r = g[0];
+        if (periodic[c]) {
+            const T a = (x[(int64_t)b * ldx + c] - lower) * scale;
+            r = scale * (g[1] * cos(a) - g[0] * sin(a));
+        }
+        gx[(int64_t)b * ldgx + c] = r;
+    }
+}
+
 }  // namespace
 }  // namespace tfepb
 
 using namespace tfepb;
+
+extern "C" int tfepb_periodic_embedding(int32_t dtype, const void* x, int64_t ldx, int32_t batch, int32_t n_in,
+                                        const int32_t* out_col, const int32_t* periodic, double lower, double scale,
+                                        void* out, int64_t ldo, tfepb_stream_t stream) {
+    TFEPB_CHECK_ARG(dtype == TFEPB_F32 || dtype == TFEPB_F64, "unknown dtype %d", dtype);
+    TFEPB_CHECK_ARG(batch >= 0 && n_in > 0, "bad sizes");
+    TFEPB_CHECK_ARG(x && out && out_col && periodic, "null buffer");
+    if (int rc = require_sm100()) return rc;
+    if (batch == 0) return 0;
+    int64_t blocks = ((int64_t)batch * n_in + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (dtype == TFEPB_F32)
+        periodic_embedding_kernel<float><<<(int)blocks, 256, 0, as_stream(stream)>>>(
+            (const float*)x, ldx, batch, n_in, out_col, periodic, (float)lower, (float)scale, (float*)out, ldo);
+    else
+        periodic_embedding_kernel<double><<<(int)blocks, 256, 0, as_stream(stream)>>>(
+            (const double*)x, ldx, batch, n_in, out_col, periodic, lower, scale, (double*)out, ldo);
+    return check_launch("periodic_embedding");
+}
+
+extern "C" int tfepb_periodic_embedding_backward(int32_t dtype, const void* x, int64_t ldx, int32_t batch, int32_t n_in,
+                                                 const int32_t* out_col, const int32_t* periodic, double lower, double scale,
+                                                 const void* grad_out, int64_t ldgo, void* grad_x, int64_t ldgx,
+                                                 tfepb_stream_t stream) {
+    TFEPB_CHECK_ARG(dtype == TFEPB_F32 || dtype == TFEPB_F64, "unknown dtype %d", dtype);
+    TFEPB_CHECK_ARG(batch >= 0 && n_in > 0, "bad sizes");
+    TFEPB_CHECK_ARG(x && grad_out && grad_x && out_col && periodic, "null buffer");
+    if (int rc = require_sm100()) return rc;
+    if (batch == 0) return 0;
+    int64_t blocks = ((int64_t)batch * n_in + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (dtype == TFEPB_F32)
+        periodic_embedding_backward_kernel<float><<<(int)blocks, 256, 0, as_stream(stream)>>>(
+            (const float*)x, ldx, batch, n_in, out_col, periodic, (float)lower, (float)scale, (const float*)grad_out, ldgo,
+            (float*)grad_x, ldgx);
+    else
+        periodic_embedding_backward_kernel<double><<<(int)blocks, 256, 0, as_stream(stream)>>>(
+            (const double*)x, ldx, batch, n_in, out_col, periodic, lower, scale, (const double*)grad_out, ldgo,
+            (double*)grad_x, ldgx);
+    return check_launch("periodic_embedding_backward");
+}
 
 extern "C" int tfepb_affine(const tfepb_tx_io* io, tfepb_stream_t stream) {
     if (int rc = check_io(io, nullptr)) return rc;

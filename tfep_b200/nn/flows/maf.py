@@ -165,7 +165,9 @@ class MAF(AutoregressiveFlow):
     def inverse(self, y: torch.Tensor):
         """Returns ``(x, log_det_J)``: degree-ordered sweep (see the module docstring)."""
         pk = self._pack()
-        if pk is False or self._n_conditioner_indices > 0 or self._embedding is not None:
+        from ... import _sweep
+        if pk is False or self._n_conditioner_indices > 0 or \
+                (self._embedding is not None and _sweep.eligibility(self, pk) is not None):
             return super().inverse(y)
         if any(p.kind == 'sos' for p in pk['parts']):
             raise NotImplementedError('Inversion of SOS polynomial transformer has not been implemented yet.')
