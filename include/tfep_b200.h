@@ -218,7 +218,10 @@ typedef struct {
 
 typedef struct {
     int32_t col;                         /* column of the feature in x / y; -1 = padding slot */
-    float x0, period, inv_period, rescaled_width, rescaled_height, y0, reserved;
+    float x0, period;                    /* lower limit and width xf - x0 of the spline domain */
+    float inv_period;                    /* 1 / period */
+    float rescaled_width, rescaled_height, y0;   /* period - 8 min_bin, (yf - y0) - 8 min_bin, lower limit of y */
+    int32_t kind;                        /* 0 circular (8 slopes + shift), 1 not circular (9 slopes, linear tails) */
 } tfepb_fused_feature;
 
 typedef struct {
@@ -247,6 +250,8 @@ typedef struct {
                                                       `epoch` marks a published tile.  May be NULL if n_layers == 1 */
     uint32_t epoch;                                /* any value the words do not hold yet (e.g. a call counter) */
     int32_t debug_mode;                            /* development only, 0 */
+    int32_t mixed_splines;                         /* 1 if any feature has kind != 0 (selects the generic spline epilogue) */
+    int32_t reserved2;
     int32_t* error_flag;                           /* device int, set if an internal wait times out; may be NULL */
     float* debug_params;                           /* NULL, or (batch, n_chunks * 112): conditioner outputs (+bias)
                                                       of layer 0 in packed order, for parity tests of the GEMM chain */
@@ -266,7 +271,8 @@ int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_stream_t stre
 typedef struct {
     int32_t col;                         /* column of the feature of this degree in y / x */
     float x0, period, inv_period, rescaled_width, rescaled_height, y0;
-    int32_t partner;                     /* other half of the bf16 pair column of x: 0 not known yet, 1 known, 2 constant one */
+    int32_t partner;                     /* bits 0-3: other half of the bf16 pair column of x: 0 not known yet, 1 known,
+                                            2 constant one; bit 4: spline kind (0 circular, 1 not circular) */
     int32_t h1_first, h1_count, h2_first, h2_count;   /* packed hidden units computable after the feature (<= 15) */
 } tfepb_fused_inv_step;
 
@@ -283,7 +289,8 @@ typedef struct {
     const void* y; void* x; void* logdet;          /* fp32 (batch, n_features), (batch, n_features), (batch,) */
     int32_t batch, n_features;
     int32_t k1, hidden_padded;
-    int32_t n_layers, reserved;
+    int32_t n_layers;
+    int32_t reserved;                              /* mixed_splines: 1 if any step has the not-circular kind bit */
     const tfepb_fused_inv_layer* layers;           /* HOST array of n_layers entries */
     uint32_t* tile_flags;                          /* as for the forward kernel */
     uint32_t epoch;

@@ -198,6 +198,14 @@ def cfg_flow(name, dtype=torch.float32, n_layers=None, D=None):
         D, L = D or 66, n_layers or 4
         mk = lambda: fo.Spline(x0=torch.full((D,), -math.pi, dtype=dtype), xf=torch.full((D,), math.pi, dtype=dtype),
                                n_bins=8, circular=True)
+    elif name == 'cfg2mix':      # cfg2's "dihedral / Cartesian mix": circular splines on the torsions f % 3 == 2,
+        D, L = D or 66, n_layers or 4            # ordinary splines on [-4, 4] for the other features
+        tors = [f for f in range(D) if f % 3 == 2]
+        cart = [f for f in range(D) if f % 3 != 2]
+        mk = lambda: fo.Mixed([fo.Spline(x0=torch.full((len(tors),), -math.pi, dtype=dtype),
+                                         xf=torch.full((len(tors),), math.pi, dtype=dtype), n_bins=8, circular=True),
+                               fo.Spline(x0=torch.full((len(cart),), -4.0, dtype=dtype),
+                                         xf=torch.full((len(cart),), 4.0, dtype=dtype), n_bins=8)], [tors, cart])
     elif name == 'cfg5':         # 8 x MAF spline K=8 (non circular), D=3000 (scaled down in tests)
         D, L = D or 3000, n_layers or 8
         mk = lambda: fo.Spline(x0=torch.full((D,), -5.0, dtype=dtype), xf=torch.full((D,), 5.0, dtype=dtype), n_bins=8)
@@ -225,4 +233,10 @@ def cfg_flow(name, dtype=torch.float32, n_layers=None, D=None):
 def cfg_input(name, batch, dtype=torch.float32, D=None):
     if name == 'cfg2':
         return uniform((batch, D or 66), 0, -math.pi, math.pi, dtype) * 0.999
+    if name == 'cfg2mix':        # torsions uniform in (-pi, pi), Cartesians normal with a few samples in the spline tails
+        D = D or 66
+        x = normal((batch, D), 0, dtype) * 1.6
+        tors = [f for f in range(D) if f % 3 == 2]
+        x[:, tors] = uniform((batch, len(tors)), 1, -math.pi, math.pi, dtype) * 0.999
+        return x
     return normal((batch, D or {'cfg1': 66, 'cfg3': 300, 'cfg5': 3000}[name]), 0, dtype)

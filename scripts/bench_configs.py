@@ -28,7 +28,7 @@ def out(**kw):
     print(json.dumps(kw), flush=True)
 
 
-which = sys.argv[1:] or ['cfg1', 'cfg2inv', 'cfg3', 'cfg4']
+which = sys.argv[1:] or ['cfg1', 'cfg2inv', 'cfg2mix', 'cfg3', 'cfg4']
 if 'cfg1' in which:
     seq, _ = cfg_flow_modules('cfg1', dev)
     x = cases.cfg_input('cfg1', 1024).to(dev)
@@ -49,6 +49,21 @@ if 'cfg2inv' in which:
     err = float(torch.minimum(d, (2 * torch.pi - d).abs()).max())
     out(config='cfg2 4xMAF spline D=66 B=65536 inverse (degree sweep, fp32)', inverse_ms=msi,
         inverse_samples_per_s=65536 / msi * 1e3, round_trip_max_err=err, logdet_cancel=float((ld + ldi).abs().max()))
+if 'cfg2mix' in which:
+    # BASELINE.json cfg2 "dihedral / Cartesian mix": MixedTransformer(circular spline on 22 torsions, ordinary
+    # spline on 44 Cartesians), 4 layers, tensor-core chain kernels (generic spline epilogue)
+    seq, _ = cfg_flow_modules('cfg2mix', dev)
+    for m in seq:
+        m.precision = 'bf16'
+    x = cases.cfg_input('cfg2mix', 65536).to(dev)
+    with torch.no_grad():
+        ms = timed(lambda: seq(x), 20, 5)
+        y, ld = seq(x)
+        msi = timed(lambda: seq.inverse(y), 5, 2)
+        xi, ldi = seq.inverse(y)
+    out(config='cfg2mix 4xMAF Mixed(circular + ordinary spline) D=66 B=65536, bf16 tensor-core chain kernels',
+        forward_ms=ms, forward_samples_per_s=65536 / ms * 1e3, inverse_ms=msi, inverse_samples_per_s=65536 / msi * 1e3,
+        round_trip_median_err=float((xi - x).abs().max(dim=1).values.median()))
 if 'cfg3' in which:
     B = 262144
     seq, _ = cfg_flow_modules('cfg3', dev)

@@ -181,6 +181,49 @@ def test_long_chain_is_split_into_launches():
     assert float(d.median()) < 1e-4 and float((ld + ldi).abs().median()) < 5e-4
 
 
+@pytest.mark.parametrize('cfg', ['cfg2mix', 'cfg5'])
+def test_mixed_and_non_circular_splines(cfg):
+    """The generic spline epilogue of the fused kernels: a MixedTransformer of circular (torsions) and ordinary
+    splines with linear tails (Cartesians) -- BASELINE.json's "dihedral / Cartesian mix" -- and a purely
+    non-circular flow (cfg5's transformer at D = 66).  Forward against the exact fp32 path (stated bf16 tolerance),
+    inverse as a round trip, chain launch equal to layer-by-layer launches."""
+    seq, flows = cfg_flow_modules(cfg, DEV, n_layers=3, D=66)
+    x = cases.cfg_input(cfg, 1500, D=66).to(DEV)
+    if cfg == 'cfg5':
+        x = x * 2.5                                   # a good share of the samples in the tails beyond +-5
+    period = torch.full((66,), float('inf'))
+    if cfg == 'cfg2mix':
+        period[[f for f in range(66) if f % 3 == 2]] = 2 * math.pi
+
+    def dist(a, b):
+        d = (a.double().cpu() - b.double().cpu()).abs()
+        return torch.minimum(d, (period - d).abs())
+
+    with torch.no_grad():
+        y32, ld32 = seq[0](x)
+        for maf in seq:
+            maf.precision = 'bf16'
+        y, ld = seq[0](x)
+        assert float(dist(y, y32).max()) < 5e-2 and float(dist(y, y32).mean()) < 2e-3
+        assert float((ld - ld32).abs().max()) < 1e-1 and float((ld - ld32).abs().mean()) < 8e-3
+        xi, ldi = seq[0].inverse(y)
+        d = dist(xi, x).max(dim=1).values
+        assert float(d.median()) < 2e-5 and float((d < 2e-2).float().mean()) > 0.97
+        assert float((ld + ldi).abs().median()) < 5e-5
+        # chain: one launch == layer by layer, in both directions
+        yc, ldc = seq(x)
+        cur, tot = x, None
+        for maf in seq:
+            cur, l = maf(cur)
+            tot = l if tot is None else tot + l
+        assert torch.equal(yc, cur) and float((ldc - tot).abs().max()) < 1e-5
+        xc, ldci = seq.inverse(yc)
+        dc = dist(xc, x).max(dim=1).values
+        assert float(dc.median()) < 1e-4 and float((ldc + ldci).abs().median()) < 2e-4
+    if cfg == 'cfg5':
+        assert float((x.abs() > 5).float().mean()) > 0.01          # the tails were exercised
+
+
 def test_inference_only_and_eligibility():
     from tfep_b200._lib import TfepB200Error
     from tfep_b200.nn.conditioners import generate_degrees

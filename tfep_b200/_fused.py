@@ -55,25 +55,41 @@ STEP_DTYPE = np.dtype([('col', '<i4'), ('x0', '<f4'), ('period', '<f4'), ('inv_p
                        ('y0', '<f4'), ('partner', '<i4'), ('h1_first', '<i4'), ('h1_count', '<i4'), ('h2_first', '<i4'),
                        ('h2_count', '<i4')])
 FEAT_DTYPE = np.dtype([('col', '<i4'), ('x0', '<f4'), ('period', '<f4'), ('inv_period', '<f4'), ('rw', '<f4'),
-                       ('rh', '<f4'), ('y0', '<f4'), ('reserved', '<f4')])
+                       ('rh', '<f4'), ('y0', '<f4'), ('kind', '<i4')])
 
 
 def _ceil16(n):
     return (n + 15) // 16 * 16
 
 
+def _spline_parts(maf):
+    """The native parts of the MAF's transformer if they are all 8-bin splines the fused epilogue covers, else a reason."""
+    pk = maf._pack()
+    if pk is False:
+        return 'transformer does not lower to native parts'
+    parts = pk['parts']
+    for p in parts:
+        if p.kind != 'spline':
+            return f'transformer part of kind {p.kind!r} (only neural splines are fused)'
+        t = p.spec
+        if t.n_bins_int != 8 or t.identity_slopes or t.learn_lower or t.learn_upper:
+            return 'only splines with 8 bins, free boundary slopes and fixed limits are fused'
+        if (t.min_bin_size, t.min_slope) != (parts[0].spec.min_bin_size, parts[0].spec.min_slope):
+            return 'spline parts with different min_bin_size / min_slope'
+    return parts
+
+
 def eligibility(maf):
     """None if the fused kernel covers this MAF layer, else the reason it does not."""
-    from .nn.transformers.spline import NeuralSplineTransformer
-    t = maf._transformer
-    if not isinstance(t, NeuralSplineTransformer):
-        return 'transformer is not a NeuralSplineTransformer'
-    if not (t.circular and t.n_bins_int == 8 and not t.identity_slopes):
-        return 'only circular splines with 8 bins and free boundary slopes are fused'
+    parts = _spline_parts(maf)
+    if isinstance(parts, str):
+        return parts
     if maf._embedding is not None or maf._n_conditioner_indices > 0:
         return 'embeddings / conditioner_indices are not fused'
     if len(maf._conditioner._linear_layers()) != 3:
         return 'the fused kernel is built for two hidden layers'
+    if int(maf._degrees_in_host.min()) < 0:
+        return 'conditioning features (degree -1) are not fused'
     D = len(maf._degrees_in_host)
     if (D * 4 * TILE_M) % 16 != 0:
         return 'row length not supported'
@@ -87,7 +103,8 @@ class FusedSplinePlan:
             raise _lib.TfepB200Error(f'fused bf16 path unavailable: {why}')
         pk = maf._pack()
         plan = pk['plan']
-        t = maf._transformer
+        parts = pk['parts']
+        t = parts[0].spec                             # min_bin_size / min_slope are common to all parts
         self.D = len(maf._degrees_in_host)
         self.K1 = _ceil16(self.D + 2)                 # + two constant-one columns carrying the bias
         deg_h1, deg_h2 = plan.packed_degrees[1], plan.packed_degrees[2]
@@ -120,35 +137,47 @@ class FusedSplinePlan:
         self.hidden_split = (self.hidden_chunks1[0][1], self.hidden_chunks2[0][1])
         assert all((b - a) * self.K1 * 2 <= STAGE_BYTES for a, b in self.hidden_chunks1)
 
-        # sorted features -> chunks of 8 slots
-        part = pk['parts'][0]
-        cols = part.x_columns().tolist()
+        # features of all spline parts (a MixedTransformer contributes one part per child), sorted by degree ->
+        # chunks of 4 slots; a feature is (x column, degree, spline module, local index, 25 reference output rows)
         deg_in = maf._degrees_in_host
-        order = sorted(range(part.n_features), key=lambda f: (int(deg_in[cols[f]]), cols[f]))
+        feats_all = []
+        for part in parts:
+            cols_p = part.x_columns().tolist()
+            ref_cols_p = part.ref_columns()                 # (F, 25) rows of the reference output layer
+            dom = [b.detach().float().cpu() for b in (part.spec.x0, part.spec.xf, part.spec._y0, part.spec._yf)]
+            for f in range(part.n_features):
+                feats_all.append(dict(col=cols_p[f], deg=int(deg_in[cols_p[f]]), rows=ref_cols_p[f], circular=part.spec.circular,
+                                      x0=float(dom[0][f]), xf=float(dom[1][f]), y0=float(dom[2][f]), yf=float(dom[3][f])))
+        feats_all.sort(key=lambda d: (d['deg'], d['col']))
+        if len(feats_all) != self.D or sorted(d['col'] for d in feats_all) != list(range(self.D)):
+            raise _lib.TfepB200Error('fused bf16 path: the spline parts must cover every feature exactly once')
+        self._feats_all = feats_all
+        self.mixed = any(not d['circular'] for d in feats_all)
+        order = list(range(len(feats_all)))
+        cols = [d['col'] for d in feats_all]            # indexed by sorted position
         self._order = order
         self._inv, self._inv_why = None, None
         self.n_chunks = math.ceil(len(order) / FEATS_PER_CHUNK)
-        ref_cols = part.ref_columns()                       # (F, 25) rows of the reference output layer
-        x0, xf, y0, yf = (b.detach().float().cpu() for b in (t.x0, t.xf, t._y0, t._yf))
         feats = np.zeros(self.n_chunks * FEATS_PER_CHUNK, dtype=FEAT_DTYPE)
         feats['col'] = -1
         w3_rows = torch.full((self.n_chunks * CHUNK_N,), -1, dtype=torch.long)     # -1 -> zero row
         chunk_maxdeg = []
-        for slot, f in enumerate(order):
+        scale = torch.ones(len(w3_rows))
+        for slot, d in enumerate(feats_all):
             c, j = divmod(slot, FEATS_PER_CHUNK)
-            L = float(xf[f] - x0[f])
+            L = d['xf'] - d['x0']
             mi = 8 * t.min_bin_size
-            feats[slot] = (cols[f], float(x0[f]), L, 1.0 / L, np.float32(L) - np.float32(mi),
-                           np.float32(float(yf[f] - y0[f])) - np.float32(mi), float(y0[f]), 0.0)
-            w3_rows[c * CHUNK_N + j * PSTRIDE:c * CHUNK_N + j * PSTRIDE + NPAR] = ref_cols[f]
+            feats[slot] = (d['col'], d['x0'], L, 1.0 / L, np.float32(L) - np.float32(mi),
+                           np.float32(d['yf'] - d['y0']) - np.float32(mi), d['y0'], 0 if d['circular'] else 1)
+            r0 = c * CHUNK_N + j * PSTRIDE
+            w3_rows[r0:r0 + NPAR] = d['rows']
+            # widths, heights, slopes live in the log2 domain; the shift of a circular spline does not
+            scale[r0:r0 + (24 if d['circular'] else 25)] = LOG2E
         for c in range(self.n_chunks):
             fs = order[c * FEATS_PER_CHUNK:(c + 1) * FEATS_PER_CHUNK]
             chunk_maxdeg.append(max(int(deg_in[cols[f]]) for f in fs))
         self.feats_host = feats
         self.w3_rows = w3_rows
-        scale = torch.ones(len(w3_rows))
-        for i in range(24):                                # widths, heights, slopes: log2 domain; shift: not
-            scale[i::PSTRIDE] = LOG2E
         self.w3_scale = scale
         assert self.n_chunks * CHUNK_N == len(w3_rows)
 
@@ -280,13 +309,12 @@ class FusedSplinePlan:
         plan = pk['plan']
         deg_in = maf._degrees_in_host
         deg_h1, deg_h2 = plan.packed_degrees[1], plan.packed_degrees[2]
-        part = pk['parts'][0]
-        cols = part.x_columns().tolist()
+        cols = [d['col'] for d in self._feats_all]
         order = self._order
         why = None
         if int(deg_in.min()) < 0:
             why = 'conditioning features (degree -1)'
-        degs = [int(deg_in[cols[f]]) for f in order]
+        degs = [d['deg'] for d in self._feats_all]
         if why is None and any(b <= a for a, b in zip(degs, degs[1:])):
             why = 'more than one feature per degree'
         if self.K1 > 128 or self.HP > 352:
@@ -335,6 +363,7 @@ class FusedSplinePlan:
             col = cols[f]
             pc = col ^ 1
             partner = 2 if pc == D else (0 if pc > D else (1 if int(deg_in[pc]) < d else 0))
+            partner |= 0 if self._feats_all[si]['circular'] else 16
             ft = self.feats_host[si]
             steps.append((col, ft['x0'], ft['period'], ft['inv_period'], ft['rw'], ft['rh'], ft['y0'], partner,
                           h1[0], h1[1], h2[0], h2[1]))
@@ -420,6 +449,7 @@ def run_chain(plans_mafs, x, debug_params=None):
                           hidden_split=(ctypes.c_int32 * 2)(*first.hidden_split), layers=layers,
                           tile_flags=None if flags is None else flags.data_ptr(), epoch=_EPOCH[0],
                           debug_mode=int(os.environ.get('TFEPB_FUSED_DEBUG_MODE', '0')),
+                          mixed_splines=int(any(pl.mixed for pl, _ in plans_mafs)), reserved2=0,
                           error_flag=tb['err'].data_ptr(),
                           debug_params=None if debug_params is None else debug_params.data_ptr())
     with torch.cuda.device(x.device):
@@ -465,7 +495,8 @@ def run_inverse_chain(plans_mafs, y):
             flags = tb[key] = torch.zeros(max(need, 4096), dtype=torch.int32, device=y.device)
     _EPOCH[0] = (_EPOCH[0] % 0x7fffffff) + 1
     args = _lib.FusedInvArgs(y=y.data_ptr(), x=x.data_ptr(), logdet=ld.data_ptr(), batch=B, n_features=first.D,
-                             k1=first.K1, hidden_padded=first.HP, n_layers=n_layers, reserved=0, layers=layers,
+                             k1=first.K1, hidden_padded=first.HP, n_layers=n_layers,
+                             reserved=int(any(pl.mixed for pl, _ in plans_mafs)), layers=layers,
                              tile_flags=None if flags is None else flags.data_ptr(), epoch=_EPOCH[0], reserved2=0,
                              error_flag=tb['err'].data_ptr())
     with torch.cuda.device(y.device):

@@ -50,8 +50,9 @@ struct __align__(16) Op {   // same layout as tfepb_fused_op; a_col = absolute T
 struct __align__(16) Step {  // one degree of the sweep (tfepb_fused_inv_step)
     int col;                 // column of the feature in y / x
     float x0, L, invL, Rw, Rh, y0;
-    int partner;             // the other half of the bf16 pair column (col ^ 1): 0 unknown yet (zero), 1 already
-                             // inverted (read it back), 2 the constant-one bias column
+    int partner;             // bits 0-3: the other half of the bf16 pair column (col ^ 1): 0 unknown yet (zero), 1 already
+                             // inverted (read it back), 2 the constant-one bias column; bit 4: spline kind (0 circular,
+                             // 1 not circular: 9 slopes, linear tails)
     int h1_a, h1_n, h2_a, h2_n;   // packed positions of the hidden units that become computable (n = 0: none)
 };
 
@@ -78,16 +79,19 @@ struct Smem {
     uint32_t pad[3];
 };
 
-// Inverse of the circular 8-bin spline for one feature of one sample (reference nn/transformers/spline.py:
-// 504-543, 257-259).  r[0..24] as in the forward epilogue (log2-domain widths / heights / slopes, shift).
-// Returns log|dx/dy|.
-__device__ __forceinline__ float spline8_circular_inverse(const uint32_t (&r)[32], float yv, const Step& fc, float min_bin,
-                                                          float min_slope, float slope_offset2, float& x) {
+// Inverse of the 8-bin spline for one feature of one sample (reference nn/transformers/spline.py:504-543,
+// 257-259).  r[0..24] as in the forward epilogue (log2-domain widths / heights / slopes; circular: the shift in
+// r[24]; not circular (MIXED instantiations): the ninth slope, linear tails outside [y0, yf]).  Returns log|dx/dy|.
+template <bool MIXED>
+__device__ __forceinline__ float spline8_inverse(const uint32_t (&r)[32], float yv, const Step& fc, float min_bin,
+                                                 float min_slope, float slope_offset2, float& x) {
     float p[NPAR];
 #pragma unroll
     for (int i = 0; i < NPAR; ++i) p[i] = __uint_as_float(r[i]);
-    float t = yv - fc.y0;
-    t = fminf(fmaxf(t, 0.f), fc.L);
+    const bool circ = !MIXED || (fc.partner & 16) == 0;
+    const float Ly = fmaf(8.f, min_bin, fc.Rh);                  // yf - y0
+    const float t0 = yv - fc.y0;
+    const float t = fminf(fmaxf(t0, 0.f), Ly);
     float mw = fmaxf(fmaxf(fmaxf(p[0], p[1]), fmaxf(p[2], p[3])), fmaxf(fmaxf(p[4], p[5]), fmaxf(p[6], p[7])));
     float mh = fmaxf(fmaxf(fmaxf(p[8], p[9]), fmaxf(p[10], p[11])), fmaxf(fmaxf(p[12], p[13]), fmaxf(p[14], p[15])));
     float ew[8], eh[8];
@@ -103,6 +107,7 @@ __device__ __forceinline__ float spline8_circular_inverse(const uint32_t (&r)[32
     float wk = fmaf(ew[0], rw, min_bin), hk = fmaf(eh[0], rh, min_bin);
     float left = wk, bottom = hk, w_sel = wk, h_sel = hk, xk = 0.f, yk = 0.f;
     float raw0 = p[16], raw1 = p[17];
+    const float raw_last = (MIXED && !circ) ? p[24] : p[16];
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
         if (k > 0) { left += wk; bottom += hk; }
@@ -114,7 +119,7 @@ __device__ __forceinline__ float spline8_circular_inverse(const uint32_t (&r)[32
         xk = adv ? left : xk;
         yk = adv ? bottom : yk;
         raw0 = adv ? p[16 + k + 1] : raw0;
-        raw1 = adv ? p[16 + ((k + 2) & 7)] : raw1;
+        raw1 = adv ? (k == 6 ? raw_last : p[16 + k + 2]) : raw1;
     }
     const float dk = softplus_l2(raw0 + slope_offset2) + min_slope;
     const float dk1 = softplus_l2(raw1 + slope_offset2) + min_slope;
@@ -131,17 +136,29 @@ __device__ __forceinline__ float spline8_circular_inverse(const uint32_t (&r)[32
     const float iden = rcp(den);
     const float nn = fmaf(dk1, e2, fmaf(2.f * s, u, dk * ome * ome));
     const float rr = s * iden;
-    // un-shift and wrap into [x0, x0 + L)
-    float xr = fmaf(e, w_sel, xk) - p[24];
-    xr = xr - fc.L * floorf(xr * fc.invL);
-    xr = (xr < 0.f) ? xr + fc.L : xr;
-    xr = (xr >= fc.L) ? xr - fc.L : xr;
+    float xr = fmaf(e, w_sel, xk);
+    float ld = -LN2 * lg2(nn * rr * rr);
+    if (circ) {
+        // un-shift and wrap into [x0, x0 + L)
+        xr -= p[24];
+        xr = xr - fc.L * floorf(xr * fc.invL);
+        xr = (xr < 0.f) ? xr + fc.L : xr;
+        xr = (xr >= fc.L) ? xr - fc.L : xr;
+    } else {
+        // linear tails: below y0 the first bin is selected (dk = slope at knot 0), above yf the last one (dk1)
+        const bool lo = t0 < 0.f, hi = t0 > Ly;
+        const float xt = lo ? t0 * rcp(dk) : fmaf(t0 - Ly, rcp(dk1), fc.L);
+        const float lt = -LN2 * lg2(lo ? dk : dk1);
+        xr = (lo || hi) ? xt : xr;
+        ld = (lo || hi) ? lt : ld;
+    }
     x = fc.x0 + xr;
-    return -LN2 * lg2(nn * rr * rr);
+    return ld;
 }
 
 __device__ __forceinline__ float elu_l2(float t, float l2e) { return fmaxf(t, fmaf(ex2(fminf(t, 0.f)), l2e, -LOG2E)); }
 
+template <bool MIXED>
 __global__ void __launch_bounds__(THREADS, 1) maf_spline_inv_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* sW = smem_raw;
@@ -388,10 +405,11 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_inv_kernel(const __grid
                     tmem_ld1(lane_addr + ACC_OUT + 24, r + 24);
                     tmem_wait8(r); tmem_wait8(r + 8); tmem_wait8(r + 16); tmem_wait1(r + 24);
                     float xv;
-                    ld += spline8_circular_inverse(r, xrow[st.col], st, min_bin, min_slope, slope_offset2, xv);
+                    ld += spline8_inverse<MIXED>(r, xrow[st.col], st, min_bin, min_slope, slope_offset2, xv);
                     xrow[st.col] = xv;
                     // bf16 pair column of the x operand: the partner is known (already x) or still zero
-                    const float other = st.partner == 1 ? xrow[st.col ^ 1] : (st.partner == 2 ? 1.f : 0.f);
+                    const int pk = st.partner & 15;
+                    const float other = pk == 1 ? xrow[st.col ^ 1] : (pk == 2 ? 1.f : 0.f);
                     const uint32_t q = (st.col & 1) ? pack_bf16(other, xv) : pack_bf16(xv, other);
                     tmem_st1(lane_addr + A0_COL + (st.col >> 1), q);
                     tmem_st_wait();
@@ -499,12 +517,14 @@ extern "C" int tfepb_maf_spline_inverse_bf16(const tfepb_fused_inv_args* a, tfep
     }
     const size_t smem = finv::smem_bytes(p);
     TFEPB_CHECK_ARG(smem <= 227 * 1024, "shared memory plan of %zu bytes exceeds 227 KB", smem);
-    static thread_local size_t configured = 0;
-    if (configured < smem) {
-        TFEPB_CUDA(cudaFuncSetAttribute(finv::maf_spline_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    const bool mixed = a->reserved != 0;           // `reserved` = mixed_splines: some features are not circular
+    auto kernel = mixed ? finv::maf_spline_inv_kernel<true> : finv::maf_spline_inv_kernel<false>;
+    static thread_local size_t configured[2] = {0, 0};
+    if (configured[mixed] < smem) {
+        TFEPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[mixed] = smem;
     }
     const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
-    finv::maf_spline_inv_kernel<<<grid, finv::THREADS, smem, as_stream(stream)>>>(p);
+    kernel<<<grid, finv::THREADS, smem, as_stream(stream)>>>(p);
     return check_launch("maf_spline_inv_kernel");
 }

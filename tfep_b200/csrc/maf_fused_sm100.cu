@@ -87,7 +87,9 @@ enum : uint32_t {
 
 struct __align__(16) FeatConst {   // per sorted feature
     int col;                // column in x / y, -1 = padding
-    float x0, L, invL, Rw, Rh, y0, pad;
+    float x0, L;
+    float invL, Rw, Rh, y0; // Rw = L - 8 min_bin, Rh = (yf - y0) - 8 min_bin
+    int kind;               // 0 circular (8 slopes + shift), 1 not circular (9 slopes, linear tails)
 };
 
 struct LayerP {
@@ -126,20 +128,27 @@ struct Smem {
 };
 
 // Spline epilogue for ONE feature of one sample.  r[0..24] = conditioner outputs of the feature (bias
-// included by the GEMM); widths r[0..7], heights r[8..15] and slopes r[16..23] arrive pre-multiplied by
-// log2(e), the shift r[24] does not.  Circular spline with K = 8 (reference nn/transformers/spline.py:
-// 184-241, 319-417, 424-501): after the wrap the far tails cannot be reached, and x exactly on the first
-// knot gives the same value through the first bin.
-__device__ __forceinline__ float spline8_circular(const uint32_t (&r)[32], float x, const FeatConst& fc, float min_bin,
-                                                  float min_slope, float slope_offset2, float& y) {
+// included by the GEMM); widths r[0..7], heights r[8..15] and slopes r[16..] arrive pre-multiplied by
+// log2(e).  K = 8 bins (reference nn/transformers/spline.py:184-241, 319-417, 424-501, 546-650).
+//   circular (kind 0): 8 slopes + the shift r[24] (not pre-multiplied); after the wrap the far tails cannot be
+//     reached, and x exactly on the first knot gives the same value through the first bin;
+//   not circular (kind 1, only in MIXED instantiations): 9 slopes; outside [x0, xf] the map is the linear
+//     continuation with the boundary slope (the reference's far-tail bins are exactly linear).
+template <bool MIXED>
+__device__ __forceinline__ float spline8(const uint32_t (&r)[32], float x, const FeatConst& fc, float min_bin,
+                                         float min_slope, float slope_offset2, float& y) {
     float p[NPAR];
 #pragma unroll
     for (int i = 0; i < NPAR; ++i) p[i] = __uint_as_float(r[i]);
-    // wrap: (x - x0 + shift) mod L, result in [0, L)
-    float t = x - fc.x0 + p[24];
-    t = t - fc.L * floorf(t * fc.invL);
-    t = (t < 0.f) ? t + fc.L : t;
-    t = (t >= fc.L) ? t - fc.L : t;
+    const bool circ = !MIXED || fc.kind == 0;
+    float t = x - fc.x0;
+    if (circ) {
+        // wrap: (x - x0 + shift) mod L, result in [0, L)
+        t += p[24];
+        t = t - fc.L * floorf(t * fc.invL);
+        t = (t < 0.f) ? t + fc.L : t;
+        t = (t >= fc.L) ? t - fc.L : t;
+    }
     // softmax numerators (log2 domain)
     float mw = fmaxf(fmaxf(fmaxf(p[0], p[1]), fmaxf(p[2], p[3])), fmaxf(fmaxf(p[4], p[5]), fmaxf(p[6], p[7])));
     float mh = fmaxf(fmaxf(fmaxf(p[8], p[9]), fmaxf(p[10], p[11])), fmaxf(fmaxf(p[12], p[13]), fmaxf(p[14], p[15])));
@@ -156,6 +165,7 @@ __device__ __forceinline__ float spline8_circular(const uint32_t (&r)[32], float
     float wk = fmaf(ew[0], rw, min_bin), hk = fmaf(eh[0], rh, min_bin);
     float left = wk, bottom = hk, w_sel = wk, h_sel = hk, xk = 0.f, yk = 0.f;
     float raw0 = p[16], raw1 = p[17];
+    const float raw_last = (MIXED && !circ) ? p[24] : p[16];      // slope at the last knot: tied to knot 0 if circular
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
         if (k > 0) { left += wk; bottom += hk; }
@@ -167,7 +177,7 @@ __device__ __forceinline__ float spline8_circular(const uint32_t (&r)[32], float
         xk = adv ? left : xk;
         yk = adv ? bottom : yk;
         raw0 = adv ? p[16 + k + 1] : raw0;
-        raw1 = adv ? p[16 + ((k + 2) & 7)] : raw1;       // knot 8 is tied to knot 0 (circular)
+        raw1 = adv ? (k == 6 ? raw_last : p[16 + k + 2]) : raw1;
     }
     const float dk = softplus_l2(raw0 + slope_offset2) + min_slope;
     const float dk1 = softplus_l2(raw1 + slope_offset2) + min_slope;
@@ -181,7 +191,16 @@ __device__ __forceinline__ float spline8_circular(const uint32_t (&r)[32], float
     y = fc.y0 + yk + h_sel * fmaf(s, e2, dk * u) * iden;
     const float nn = fmaf(dk1, e2, fmaf(2.f * s, u, dk * ome * ome));
     const float rr = s * iden;
-    return LN2 * lg2(nn * rr * rr);
+    float ld = LN2 * lg2(nn * rr * rr);
+    if (MIXED && !circ) {
+        // linear tails: below x0 the first bin is selected (dk = slope at knot 0), above xf the last one (dk1 = slope at knot 8)
+        const bool lo = t < 0.f, hi = t > fc.L;
+        const float yt = lo ? fmaf(dk, t, fc.y0) : fmaf(dk1, t - fc.L, fc.y0 + fmaf(8.f, min_bin, fc.Rh));   // yf = y0 + Rh + 8 min_bin
+        const float lt = LN2 * lg2(lo ? dk : dk1);
+        y = (lo || hi) ? yt : y;
+        ld = (lo || hi) ? lt : ld;
+    }
+    return ld;
 }
 
 // development aid: CTA 0 stamps clock64() of key events into debug_params (as long long) when debug_mode & 16
@@ -199,7 +218,7 @@ __device__ __forceinline__ void trace(const Params& p, int role, int& slot, int 
     }
 }
 
-template <bool DEBUG>
+template <bool DEBUG, bool MIXED>
 __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid_constant__ Params p) {
     const int dmode = DEBUG ? p.debug_mode : 0;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -559,7 +578,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
                             for (int i = 0; i < NPAR; ++i) dbg[i] = __uint_as_float(r[i]);
                         }
                         float yv;
-                        ld += spline8_circular(r, xrow[fc.col], fc, min_bin, min_slope, slope_offset2, yv);
+                        ld += spline8<MIXED>(r, xrow[fc.col], fc, min_bin, min_slope, slope_offset2, yv);
                         xrow[fc.col] = yv;
                     }
                 }
@@ -645,11 +664,14 @@ extern "C" int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_st
     const size_t smem = fused::smem_bytes(p);
     TFEPB_CHECK_ARG(smem <= 227 * 1024, "shared memory plan of %zu bytes exceeds 227 KB", smem);
     const bool debug = p.debug_mode != 0 || p.debug_params != nullptr;
-    auto kernel = debug ? fused::maf_spline_fwd_kernel<true> : fused::maf_spline_fwd_kernel<false>;
-    static thread_local size_t configured[2] = {0, 0};
-    if (configured[debug] < smem) {
+    const bool mixed = a->mixed_splines != 0;      // some features are not circular: generic spline epilogue
+    auto kernel = debug ? (mixed ? fused::maf_spline_fwd_kernel<true, true> : fused::maf_spline_fwd_kernel<true, false>)
+                        : (mixed ? fused::maf_spline_fwd_kernel<false, true> : fused::maf_spline_fwd_kernel<false, false>);
+    static thread_local size_t configured[4] = {0, 0, 0, 0};
+    const int variant = (debug ? 2 : 0) + (mixed ? 1 : 0);
+    if (configured[variant] < smem) {
         TFEPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[debug] = smem;
+        configured[variant] = smem;
     }
     // one CTA per SM; never more CTAs than tiles, so that the items a CTA waits for belong to CTAs that run
     const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
