@@ -221,3 +221,15 @@ def test_host_pipeline_matches_direct_call():
         yh, ldh = pipe(x)
         torch.cuda.synchronize()
         assert torch.equal(yh, y.cpu()) and torch.equal(ldh, ld.cpu())
+    # overlapped across batches (wait=False) and CUDA-graph mode: every staging set must hold the same result
+    for maf in seq:
+        maf.precision = 'bf16'
+    with torch.no_grad():
+        yb, ldb = seq(x.to(DEV))
+    for mode in ('streams', 'graph'):
+        pipe = HostPipeline(seq, 5000, 66, DEV, n_chunks=1, depth=3)
+        outs = [pipe(x, wait=False) if mode == 'streams' else pipe.step_graph(x) for _ in range(7)]
+        pipe.join()
+        torch.cuda.synchronize()
+        for yh, ldh in outs[-3:]:
+            assert torch.equal(yh, yb.cpu()) and torch.equal(ldh, ldb.cpu()), mode

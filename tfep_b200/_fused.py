@@ -444,6 +444,8 @@ def run_chain(plans_mafs, x, debug_params=None):
         if flags is None or flags.numel() < need:
             flags = tb[key] = torch.zeros(max(need, 4096), dtype=torch.int32, device=x.device)
     _EPOCH[0] = (_EPOCH[0] % 0x7fffffff) + 1
+    if flags is not None and torch.cuda.is_current_stream_capturing():
+        flags.zero_()           # a replayed CUDA graph re-uses the captured epoch: reset the flags inside the graph
     args = _lib.FusedArgs(x=x.data_ptr(), y=y.data_ptr(), logdet=ld.data_ptr(), batch=B, n_features=first.D,
                           k1=first.K1, hidden_padded=first.HP, n_layers=n_layers, hidden_halves=first.halves,
                           hidden_split=(ctypes.c_int32 * 2)(*first.hidden_split), layers=layers,
@@ -494,6 +496,8 @@ def run_inverse_chain(plans_mafs, y):
         if flags is None or flags.numel() < need:
             flags = tb[key] = torch.zeros(max(need, 4096), dtype=torch.int32, device=y.device)
     _EPOCH[0] = (_EPOCH[0] % 0x7fffffff) + 1
+    if flags is not None and torch.cuda.is_current_stream_capturing():
+        flags.zero_()
     args = _lib.FusedInvArgs(y=y.data_ptr(), x=x.data_ptr(), logdet=ld.data_ptr(), batch=B, n_features=first.D,
                              k1=first.K1, hidden_padded=first.HP, n_layers=n_layers,
                              reserved=int(any(pl.mixed for pl, _ in plans_mafs)), layers=layers,

@@ -4,7 +4,7 @@ The reference keeps trajectories on the host and feeds the mapped coordinates to
 (tfep/app/base.py:790-797), so in practice x arrives from, and y / log_det_J return to, host memory.  The
 batch is cut into chunks that travel through three CUDA streams -- host->device copy, flow kernels,
 device->host copy -- so that PCIe transfers in both directions hide behind the compute of neighbouring chunks;
-with ``wait=False`` consecutive batches overlap as well (double-buffered staging on both sides): the upload
+with ``wait=False`` consecutive batches overlap as well (``depth`` staging sets on both sides): the upload
 of batch g + 1 and the download of batch g - 1 run while batch g is in the kernels.
 """
 
@@ -14,27 +14,30 @@ import torch
 class HostPipeline:
     """Reusable pinned / device staging buffers for ``flow`` evaluated on batches of ``batch`` samples."""
 
-    def __init__(self, flow, batch, n_features, device, n_chunks=4, dtype=torch.float32):
+    def __init__(self, flow, batch, n_features, device, n_chunks=4, dtype=torch.float32, depth=3):
         self.flow, self.device = flow, torch.device(device)
         self.bounds = [(i * batch // n_chunks, (i + 1) * batch // n_chunks) for i in range(n_chunks)]
         self.bounds = [(a, b) for a, b in self.bounds if b > a]
-        self.x_dev = [torch.empty(batch, n_features, dtype=dtype, device=self.device) for _ in range(2)]
-        self.y_hosts = [torch.empty(batch, n_features, dtype=dtype).pin_memory() for _ in range(2)]
-        self.ld_hosts = [torch.empty(batch, dtype=dtype).pin_memory() for _ in range(2)]
+        # `depth` staging sets: a batch occupies upload, kernels and download one after the other, so three batches
+        # in flight are needed to keep the two copy engines and the SMs busy at the same time
+        self.depth = depth
+        self.x_dev = [torch.empty(batch, n_features, dtype=dtype, device=self.device) for _ in range(depth)]
+        self.y_hosts = [torch.empty(batch, n_features, dtype=dtype).pin_memory() for _ in range(depth)]
+        self.ld_hosts = [torch.empty(batch, dtype=dtype).pin_memory() for _ in range(depth)]
         self.s_in = torch.cuda.Stream(self.device)
         self.s_out = torch.cuda.Stream(self.device)
         self.generation = 0
-        self._computed = [None, None]        # event: kernels that read x_dev[i] have finished
-        self._downloaded = [None, None]      # event: y_hosts[i] / ld_hosts[i] are complete
+        self._computed = [None] * depth      # event: kernels that read x_dev[i] have finished
+        self._downloaded = [None] * depth    # event: y_hosts[i] / ld_hosts[i] are complete
 
     @property
     def y_host(self):
         """Output buffers of the most recent call."""
-        return self.y_hosts[(self.generation - 1) % 2]
+        return self.y_hosts[(self.generation - 1) % self.depth]
 
     @property
     def ld_host(self):
-        return self.ld_hosts[(self.generation - 1) % 2]
+        return self.ld_hosts[(self.generation - 1) % self.depth]
 
     def __call__(self, x_host, inverse=False, wait=True):
         """x_host: pinned (batch, n_features) tensor.  Returns pinned ``(y_host, ld_host)``.
@@ -42,9 +45,9 @@ class HostPipeline:
         ``wait=True``: the current stream has been joined with the output stream when the call returns (results
         valid after a synchronize of the current stream).  ``wait=False``: nothing is joined, so the next call
         may start uploading while this batch computes and downloads; results of this call are valid after
-        :meth:`join` (or once two more calls have been issued, the buffers are reused)."""
+        :meth:`join` (after ``depth`` more calls the buffers are reused)."""
         main = torch.cuda.current_stream(self.device)
-        g = self.generation % 2
+        g = self.generation % self.depth
         self.generation += 1
         x_dev, y_host, ld_host = self.x_dev[g], self.y_hosts[g], self.ld_hosts[g]
         if self._computed[g] is not None:
@@ -74,4 +77,46 @@ class HostPipeline:
 
     def join(self):
         """Make the current stream wait for every download issued so far."""
-        torch.cuda.current_stream(self.device).wait_stream(self.s_out)
+        main = torch.cuda.current_stream(self.device)
+        main.wait_stream(self.s_out)
+        for st in getattr(self, '_graph_streams', ()):
+            main.wait_stream(st)
+
+    # -- CUDA-graph mode: the whole step (upload, kernels, download) replayed with one launch -----------------
+    def step_graph(self, x_host, inverse=False):
+        """Same work as ``__call__(x_host, wait=False)`` with the host cost of ONE graph launch per batch.
+
+        One graph per staging buffer set is captured on its own stream and they are replayed in turn, so the
+        upload / kernels / download of consecutive batches overlap while each batch stays ordered on its own
+        stream.  ``x_host`` must be the same pinned tensor at every call (its address is part of the graph; a
+        different tensor triggers a re-capture).  Results: ``y_host`` / ``ld_host`` after :meth:`join`."""
+        key = (x_host.data_ptr(), bool(inverse))
+        if getattr(self, '_graph_key', None) != key:
+            self._capture(x_host, inverse)
+            self._graph_key = key
+        g = self.generation % self.depth
+        self.generation += 1
+        with torch.cuda.stream(self._graph_streams[g]):
+            self._graphs[g].replay()
+        return self.y_hosts[g], self.ld_hosts[g]
+
+    def _capture(self, x_host, inverse):
+        fn = self.flow.inverse if inverse else self.flow
+        main = torch.cuda.current_stream(self.device)
+        self._graph_streams = [torch.cuda.Stream(self.device) for _ in range(self.depth)]
+        self._graphs = []
+        with torch.no_grad():
+            fn(self.x_dev[0])                         # warm-up outside capture: packs weights, allocates workspaces
+        torch.cuda.synchronize(self.device)
+        for g in range(self.depth):
+            st = self._graph_streams[g]
+            st.wait_stream(main)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(st), torch.no_grad():
+                with torch.cuda.graph(graph, stream=st):
+                    self.x_dev[g].copy_(x_host, non_blocking=True)
+                    y, ld = fn(self.x_dev[g])
+                    self.y_hosts[g].copy_(y, non_blocking=True)
+                    self.ld_hosts[g].copy_(ld, non_blocking=True)
+            self._graphs.append(graph)
+        torch.cuda.synchronize(self.device)
