@@ -36,7 +36,12 @@ def linear_forward(x, w, bias=None, activation=ACT_NONE, k_ranges=None, out=None
     B, K = x.shape
     N = w.shape[0]
     assert w.shape[1] == K, (w.shape, x.shape)
-    y = out if out is not None else torch.empty((B, N), dtype=x.dtype, device=x.device)
+    if out is not None:
+        y = out
+    else:
+        # leading dimension padded to 16 bytes: the 128 x 128 GEMM kernel needs 16-byte aligned rows of the next layer's input
+        pad = 16 // x.element_size()
+        y = torch.empty((B, (N + pad - 1) // pad * pad), dtype=x.dtype, device=x.device)[:, :N]
     if B == 0:
         return y
     a = LinearFwdArgs(dtype=dtype_code(x), batch=B, in_features=K, out_features=N,
@@ -55,7 +60,11 @@ def linear_backward_input(grad_y, w, act_out=None, n_ranges=None, out=None, accu
     grad_y, w = _rows(grad_y), _rows(w)
     B, N = grad_y.shape
     K = w.shape[1]
-    gx = out if out is not None else torch.empty((B, K), dtype=grad_y.dtype, device=grad_y.device)
+    if out is not None:
+        gx = out
+    else:
+        pad = 16 // grad_y.element_size()
+        gx = torch.empty((B, (K + pad - 1) // pad * pad), dtype=grad_y.dtype, device=grad_y.device)[:, :K]
     if B == 0:
         return gx
     if act_out is not None:
@@ -219,8 +228,8 @@ def transformer_vjp(kind, spec, x, par, layout, n_features, grad_y, grad_logdet,
     x, par, grad_y = _rows(x), _rows(par), _rows(grad_y)
     if grad_x is None:
         grad_x = torch.zeros_like(x)
-    if grad_par is None:
-        grad_par = torch.zeros_like(par)
+    if grad_par is None:          # same leading dimension as par (which may be a view of a padded buffer)
+        grad_par = torch.zeros((par.shape[0], _ld(par)), dtype=par.dtype, device=par.device)[:, :par.shape[1]]
     assert _ld(grad_par) == _ld(par)
     if x.shape[0] == 0 or n_features == 0:
         return grad_x, grad_par

@@ -89,7 +89,13 @@ class MadePlan:
             w = w.index_select(0, perms[l + 1])
             if l > 0:
                 w = w.index_select(1, perms[l])
-            pw.append(w.contiguous())
+            # rows padded to 16 bytes (zero columns): 16-byte aligned operands for the 128 x 128 GEMM kernel
+            pad = (-w.shape[1]) % (16 // w.element_size())
+            if pad:
+                w = torch.nn.functional.pad(w, (0, pad))[:, :w.shape[1]]
+            else:
+                w = w.contiguous()
+            pw.append(w)
             pb.append(b.index_select(0, perms[l + 1]).contiguous())
         return pw, pb
 

@@ -161,9 +161,202 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(GemmParams<T> p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// fp32 fast path: 128 x 128 x 16 tiles, 8 x 8 register micro-tiles (64 FFMA per four 16-byte shared-memory loads),
+// 16-byte global loads, double-buffered shared memory (one CTA barrier per k-tile).  Same operands, reduction
+// ranges, split-K and epilogue semantics as gemm_kernel; requires 16-byte aligned operands (leading dimensions
+// multiples of 4, checked by the launcher, which otherwise falls back to gemm_kernel).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int BM2 = 128, BN2 = 128, LD2 = BM2 + 4;
+
+template <bool KC>
+__device__ __forceinline__ void load_tile128(const float* __restrict__ G, int64_t ld, int rows0, int rows, int k0, int K,
+                                             int tid, float4 (&r)[2]) {
+    // KC: element (row, k) at G[row * ld + k] -> 16-byte loads along k; else element at G[k * ld + row] -> along rows
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int q = tid + i * THREADS;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (KC) {
+            const int row = rows0 + q / 4, k = k0 + (q % 4) * 4;
+            if (row < rows) {
+                const float* src = G + (int64_t)row * ld + k;
+                if (k + 3 < K) v = __ldg(reinterpret_cast<const float4*>(src));
+                else {
+                    if (k < K) v.x = __ldg(src);
+                    if (k + 1 < K) v.y = __ldg(src + 1);
+                    if (k + 2 < K) v.z = __ldg(src + 2);
+                }
+            }
+        } else {
+            const int k = k0 + q / 32, row = rows0 + (q % 32) * 4;
+            if (k < K) {
+                const float* src = G + (int64_t)k * ld + row;
+                if (row + 3 < rows) v = __ldg(reinterpret_cast<const float4*>(src));
+                else {
+                    if (row < rows) v.x = __ldg(src);
+                    if (row + 1 < rows) v.y = __ldg(src + 1);
+                    if (row + 2 < rows) v.z = __ldg(src + 2);
+                }
+            }
+        }
+        r[i] = v;
+    }
+}
+
+template <bool KC>
+__device__ __forceinline__ void store_tile128(float (*S)[LD2], int tid, const float4 (&r)[2]) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int q = tid + i * THREADS;
+        if (KC) {
+            const int row = q / 4, k = (q % 4) * 4;
+            S[k][row] = r[i].x; S[k + 1][row] = r[i].y; S[k + 2][row] = r[i].z; S[k + 3][row] = r[i].w;
+        } else {
+            const int k = q / 32, row = (q % 32) * 4;
+            *reinterpret_cast<float4*>(&S[k][row]) = r[i];
+        }
+    }
+}
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(THREADS, 2) gemm128_kernel(GemmParams<float> p) {
+    __shared__ __align__(16) float As[2][BK][LD2];
+    __shared__ __align__(16) float Bs[2][BK][LD2];
+    const int tid = threadIdx.x;
+    const int tx = tid % 16, ty = tid / 16;
+    const int m0 = blockIdx.y * BM2, n0 = blockIdx.x * BN2;
+
+    int kb = 0, ke = p.K;
+    if (p.ranges != nullptr) {             // ranges are per 64-column tile: take the union of the two halves
+        const int t0 = 2 * blockIdx.x, t1 = t0 + 1;
+        int b0 = p.ranges[2 * t0], e0 = p.ranges[2 * t0 + 1];
+        if (n0 + 64 < p.N) {
+            const int b1 = p.ranges[2 * t1], e1 = p.ranges[2 * t1 + 1];
+            if (e1 > b1) {
+                if (e0 > b0) { b0 = min(b0, b1); e0 = max(e0, e1); }
+                else { b0 = b1; e0 = e1; }
+            }
+        }
+        kb = max(0, b0) & ~3;              // 16-byte aligned start: the extra columns multiply masked (zero) weights
+        ke = min(p.K, e0);
+    }
+    if (p.k_chunk > 0) {
+        kb = max(kb, (int)blockIdx.z * p.k_chunk);
+        ke = min(ke, ((int)blockIdx.z + 1) * p.k_chunk);
+    }
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    float rsum[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rsum[i] = 0.f;
+    const bool want_rsum = (p.row_sums != nullptr) && (blockIdx.x == 0) && (tx == 0);
+
+    float4 ra[2], rb[2];
+    int buf = 0;
+    if (kb < ke) {
+        load_tile128<A_KC>(p.A, p.lda, m0, p.M, kb, ke, tid, ra);
+        load_tile128<B_KC>(p.B, p.ldb, n0, p.N, kb, ke, tid, rb);
+        store_tile128<A_KC>(As[0], tid, ra);
+        store_tile128<B_KC>(Bs[0], tid, rb);
+    }
+    __syncthreads();
+    for (int k0 = kb; k0 < ke; k0 += BK) {
+        const bool more = k0 + BK < ke;
+        if (more) {
+            load_tile128<A_KC>(p.A, p.lda, m0, p.M, k0 + BK, ke, tid, ra);
+            load_tile128<B_KC>(p.B, p.ldb, n0, p.N, k0 + BK, ke, tid, rb);
+        }
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            if (want_rsum) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) rsum[i] += a[i];
+            }
+        }
+        if (more) {
+            store_tile128<A_KC>(As[buf ^ 1], tid, ra);
+            store_tile128<B_KC>(Bs[buf ^ 1], tid, rb);
+        }
+        __syncthreads();
+        buf ^= 1;
+    }
+
+    // epilogue: rows ty * 4 + {0..3} and 64 + ty * 4 + {0..3}; columns tx * 4 + {0..3} and 64 + tx * 4 + {0..3}
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (gm >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            if (gn >= p.N) continue;
+            float v = acc[i][j];
+            float* c = p.C + (int64_t)gm * p.ldc + gn;
+            if (p.atomic) {
+                atomicAdd(c, v);
+                continue;
+            }
+            if (p.bias != nullptr) v += p.bias[gn];
+            if (p.act == TFEPB_ACT_ELU) v = elu(v);
+            if (p.aux != nullptr) {
+                const float h = p.aux[(int64_t)gm * p.ldaux + gn];
+                v *= (h > 0.f) ? 1.f : (h + 1.f);
+            }
+            if (p.accumulate) v += *c;
+            *c = v;
+        }
+        if (want_rsum) atomicAdd(p.row_sums + gm, rsum[i]);
+    }
+}
+
+template <typename T>
+bool aligned16(const GemmParams<T>&) { return false; }
+template <>
+bool aligned16<float>(const GemmParams<float>& p) {
+    return p.N > 64 && p.lda % 4 == 0 && p.ldb % 4 == 0 && (reinterpret_cast<uintptr_t>(p.A) & 15) == 0 &&
+           (reinterpret_cast<uintptr_t>(p.B) & 15) == 0 && (p.k_chunk % 4 == 0);
+}
+
+template <typename T, bool A_KC, bool B_KC>
+int launch128(const GemmParams<T>&, int, cudaStream_t, const char*) { return -1; }
+template <>
+int launch128<float, true, true>(const GemmParams<float>& p, int splits, cudaStream_t stream, const char* what) {
+    dim3 grid((p.N + BN2 - 1) / BN2, (p.M + BM2 - 1) / BM2, splits);
+    gemm128_kernel<true, true><<<grid, THREADS, 0, stream>>>(p);
+    return check_launch(what);
+}
+template <>
+int launch128<float, true, false>(const GemmParams<float>& p, int splits, cudaStream_t stream, const char* what) {
+    dim3 grid((p.N + BN2 - 1) / BN2, (p.M + BM2 - 1) / BM2, splits);
+    gemm128_kernel<true, false><<<grid, THREADS, 0, stream>>>(p);
+    return check_launch(what);
+}
+template <>
+int launch128<float, false, false>(const GemmParams<float>& p, int splits, cudaStream_t stream, const char* what) {
+    dim3 grid((p.N + BN2 - 1) / BN2, (p.M + BM2 - 1) / BM2, splits);
+    gemm128_kernel<false, false><<<grid, THREADS, 0, stream>>>(p);
+    return check_launch(what);
+}
+
 template <typename T, bool A_KC, bool B_KC>
 int launch(const GemmParams<T>& p, int splits, cudaStream_t stream, const char* what) {
     if (p.M <= 0 || p.N <= 0) return 0;
+    if (aligned16<T>(p)) return launch128<T, A_KC, B_KC>(p, splits, stream, what);
     dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, splits);
     gemm_kernel<T, A_KC, B_KC><<<grid, THREADS, 0, stream>>>(p);
     return check_launch(what);
@@ -204,7 +397,8 @@ int bwd_weight_t(const tfepb_linear_bwd_weight_args* a, cudaStream_t s) {
     p.atomic = 1;
     p.row_sums = (T*)a->grad_bias;
     // split the batch reduction so that the grid covers the machine a few times over
-    const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+    const int bn = (sizeof(T) == 4 && p.N > 64) ? BN2 : BN;       // tile width of the kernel the launcher will pick
+    const int tiles = ((p.M + BM - 1) / BM) * ((p.N + bn - 1) / bn);
     int splits = (4 * sm_count() + tiles - 1) / tiles;
     const int max_splits = (p.K + 4 * BK - 1) / (4 * BK);
     if (splits > max_splits) splits = max_splits;
