@@ -94,6 +94,9 @@ typedef struct {
     const void* x;       int64_t ldx;    /* (batch, in) */
     void* grad_w;        int64_t ldgw;   /* (out, in); must be zero-filled by the caller (split-batch atomics) */
     void* grad_bias;                     /* (out,) zero-filled, or NULL */
+    const int32_t* n_ranges;             /* NULL or (ceil(in/TILE_N), 2): per tile of TILE_N input columns the rows
+                                            [begin, end) of grad_w the mask can leave non-zero; tiles outside are
+                                            skipped and stay zero (the bias gradient is always complete) */
 } tfepb_linear_bwd_weight_args;
 /* grad_w += grad_y^T x ; grad_bias += sum_b grad_y   (the caller applies the mask, nn/masked.py:296-297) */
 int tfepb_masked_linear_backward_weight(const tfepb_linear_bwd_weight_args* a, tfepb_stream_t stream);

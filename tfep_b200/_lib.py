@@ -39,7 +39,7 @@ class LinearBwdInputArgs(Structure):
 class LinearBwdWeightArgs(Structure):
     _fields_ = [('dtype', c_int32), ('batch', c_int32), ('in_features', c_int32), ('out_features', c_int32),
                 ('grad_y', c_void_p), ('ldgy', c_int64), ('x', c_void_p), ('ldx', c_int64),
-                ('grad_w', c_void_p), ('ldgw', c_int64), ('grad_bias', c_void_p)]
+                ('grad_w', c_void_p), ('ldgw', c_int64), ('grad_bias', c_void_p), ('n_ranges', c_void_p)]
 
 
 class TxIo(Structure):

@@ -81,8 +81,9 @@ def linear_backward_input(grad_y, w, act_out=None, n_ranges=None, out=None, accu
     return gx
 
 
-def linear_backward_weight(grad_y, x, need_bias=True):
-    """(grad_w, grad_bias) = (grad_y^T x, sum_b grad_y); see tfepb_masked_linear_backward_weight."""
+def linear_backward_weight(grad_y, x, need_bias=True, n_ranges=None):
+    """(grad_w, grad_bias) = (grad_y^T x, sum_b grad_y); see tfepb_masked_linear_backward_weight.  With ``n_ranges``
+    (the per-column-tile row ranges of a staircase mask) tiles the mask zeroes anyway are skipped."""
     require_cuda(grad_y, x)
     grad_y, x = _rows(grad_y), _rows(x)
     B, N = grad_y.shape
@@ -93,7 +94,8 @@ def linear_backward_weight(grad_y, x, need_bias=True):
         return gw, gb
     a = LinearBwdWeightArgs(dtype=dtype_code(x), batch=B, in_features=K, out_features=N,
                             grad_y=grad_y.data_ptr(), ldgy=_ld(grad_y), x=x.data_ptr(), ldx=_ld(x),
-                            grad_w=gw.data_ptr(), ldgw=K, grad_bias=None if gb is None else gb.data_ptr())
+                            grad_w=gw.data_ptr(), ldgw=K, grad_bias=None if gb is None else gb.data_ptr(),
+                            n_ranges=None if n_ranges is None else n_ranges.data_ptr())
     with torch.cuda.device(x.device):
         check(_lib.load().tfepb_masked_linear_backward_weight(ctypes.byref(a), stream_ptr(x)))
     return gw, gb
@@ -134,7 +136,8 @@ class MadeFunction(torch.autograd.Function):
         gx = None
         for l in range(L - 1, -1, -1):
             if ctx.needs_input_grad[4 + l] or ctx.needs_input_grad[4 + L + l]:
-                gws[l], gbs[l] = linear_backward_weight(g, acts[l])
+                gws[l], gbs[l] = linear_backward_weight(g, acts[l],
+                                                        n_ranges=None if ctx.n_ranges is None else ctx.n_ranges[l])
             if l > 0:
                 g = linear_backward_input(g, ws[l], act_out=acts[l],
                                           n_ranges=None if ctx.n_ranges is None else ctx.n_ranges[l])

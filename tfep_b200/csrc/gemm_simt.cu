@@ -35,6 +35,7 @@ struct GemmParams {
     const int* ranges;      // per N-tile [begin, end) of the reduction, or null
     int k_chunk;            // split-K chunk length (blockIdx.z), 0 = no split
     T* row_sums;            // (M,) += sum_k A[m, k] (bias gradient), or null; only N-tile 0 contributes
+    const int* skip_ranges; // per 64-column tile of C: [begin, end) rows that can be non-zero (masked weight gradient), or null
 };
 
 template <typename T, bool A_KC, bool B_KC>
@@ -45,6 +46,10 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(GemmParams<T> p) {
     const int tid = threadIdx.x;
     const int tx = tid % 16, ty = tid / 16;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    if (p.skip_ranges != nullptr && blockIdx.x != 0) {      // tile of the weight gradient that the mask zeroes anyway
+        const int rb = p.skip_ranges[2 * blockIdx.x], re = p.skip_ranges[2 * blockIdx.x + 1];
+        if (m0 + BM <= rb || m0 >= re) return;
+    }
 
     int kb = 0, ke = p.K;
     if (p.ranges != nullptr) {
@@ -226,6 +231,17 @@ __global__ void __launch_bounds__(THREADS, 2) gemm128_kernel(GemmParams<float> p
     const int tid = threadIdx.x;
     const int tx = tid % 16, ty = tid / 16;
     const int m0 = blockIdx.y * BM2, n0 = blockIdx.x * BN2;
+    if (p.skip_ranges != nullptr && blockIdx.x != 0) {      // tile of the weight gradient that the mask zeroes anyway
+        int rb = p.skip_ranges[4 * blockIdx.x], re = p.skip_ranges[4 * blockIdx.x + 1];
+        if (n0 + 64 < p.N) {
+            const int rb1 = p.skip_ranges[4 * blockIdx.x + 2], re1 = p.skip_ranges[4 * blockIdx.x + 3];
+            if (re1 > rb1) {
+                if (re > rb) { rb = min(rb, rb1); re = max(re, re1); }
+                else { rb = rb1; re = re1; }
+            }
+        }
+        if (m0 + BM2 <= rb || m0 >= re) return;
+    }
 
     int kb = 0, ke = p.K;
     if (p.ranges != nullptr) {             // ranges are per 64-column tile: take the union of the two halves
@@ -396,6 +412,7 @@ int bwd_weight_t(const tfepb_linear_bwd_weight_args* a, cudaStream_t s) {
     p.M = a->out_features; p.N = a->in_features; p.K = a->batch;
     p.atomic = 1;
     p.row_sums = (T*)a->grad_bias;
+    p.skip_ranges = a->n_ranges;
     // split the batch reduction so that the grid covers the machine a few times over
     const int bn = (sizeof(T) == 4 && p.N > 64) ? BN2 : BN;       // tile width of the kernel the launcher will pick
     const int tiles = ((p.M + BM - 1) / BM) * ((p.N + bn - 1) / bn);
