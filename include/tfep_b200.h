@@ -177,6 +177,36 @@ int tfepb_moebius_backward(const tfepb_tx_io* io, int32_t dimension, double max_
                            const tfepb_tx_grads* g, tfepb_stream_t stream);
 
 /* ----------------------------------------------------------------------------------------------
+ * General masked linear layers on the tensor cores (tcgen05, bf16 operands, fp32 accumulation): any MADE shape,
+ * forward and backward.  C[m x n] = A[m x k] . B[n x k]^T with operand IMAGES made by tfepb_tc_pack: blocks of
+ * (block_rows x 64 k) bf16, block (rb, kb) at (rb * ceil(k / 64) + kb) * block_rows * 128 bytes, inside a block the
+ * shared-memory operand layout (for each slab of 8 k-values: block_rows x 16 bytes), so a block is one bulk copy.
+ * A operands use block_rows = 128, B operands 256.  The three products of nn/masked.py:266-302:
+ *   forward          A = image(x),           B = image(w_eff)              (+ bias, ELU, image of the result = next A)
+ *   backward input   A = image(grad_y),      B = image(w_eff^T, transpose) (+ ELU' multiplier `aux`)
+ *   backward weight  A = image(grad_y^T),    B = image(x^T), both transposed, split_k > 1 (fp32 atomics into a
+ *                    zero-filled C; the reduction runs over the batch)
+ * -------------------------------------------------------------------------------------------- */
+int64_t tfepb_tc_image_bytes(int64_t rows, int64_t k, int32_t block_rows);
+/* src fp32: element (row, k) at src[row * ld + k], or src[k * ld + row] if transpose */
+int tfepb_tc_pack(const float* src, int64_t ld, int32_t rows, int32_t k, int32_t block_rows, int32_t transpose,
+                  void* image, tfepb_stream_t stream);
+typedef struct {
+    const void* a_image; const void* b_image;
+    int32_t m, n, k;
+    int32_t activation;                  /* TFEPB_ACT_* applied after the bias */
+    void* c; int64_t ldc;                /* fp32 (m, n) row-major, or NULL */
+    const void* bias;                    /* fp32 (n,) or NULL */
+    const void* aux; int64_t ldaux;      /* NULL, or fp32 (m, n): the result is multiplied by ELU'(aux) */
+    void* out_image;                     /* NULL, or the bf16 image (block_rows = 128, k = n) of the result */
+    const int32_t* k_block_ranges;       /* device, NULL or (ceil(n / 256), 2): [first, end) 64-wide k-blocks that are
+                                            non-zero for each tile of 256 output columns (staircase masks) */
+    int32_t split_k, reserved;           /* > 1: the reduction is split over that many CTAs per tile */
+    int32_t* error_flag;
+} tfepb_tc_gemm_args;
+int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------------
  * PeriodicEmbedding of the MADE input (nn/embeddings/mafembed.py:112-142): input column c is copied to output
  * column out_col[c], or, if periodic[c], lifted to out[out_col[c]], out[out_col[c] + 1] =
  * cos, sin((x - lower) * scale) with scale = 2 pi / (upper - lower).  Backward: grad_x from grad_out.

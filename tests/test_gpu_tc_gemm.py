@@ -1,0 +1,60 @@
+"""General tensor-core GEMM (tfepb_tc_pack / tfepb_tc_gemm) against a double-precision product of the same
+bf16-rounded operands: forward (bias, ELU, image of the result chained into a second product), backward input
+(ELU' multiplier), weight gradient (transposed images, split-K atomics), staircase k-block ranges, ragged sizes."""
+
+import pytest
+import torch
+
+from tfep_b200 import _ops
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).double()
+
+
+def _rand(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g).to(DEV)
+
+
+@pytest.mark.parametrize('m,n,k', [(128, 256, 64), (1000, 670, 300), (257, 1500, 670), (5, 7, 9)])
+def test_forward_bias_elu_and_chained_image(m, n, k):
+    x, w, b = _rand((m, k), 1), _rand((n, k), 2) / k ** 0.5, _rand((n,), 3)
+    ai, bi = _ops.tc_pack(x, 128), _ops.tc_pack(w, 256)
+    c, img = _ops.tc_gemm(ai, bi, m, n, k, c=True, bias=b, activation=_ops.ACT_ELU, out_image=True)
+    ref = torch.nn.functional.elu(_bf(x) @ _bf(w).T + b.double())
+    assert c.shape == (m, n)
+    assert float((c.double() - ref).abs().max()) < 2e-4 * (1 + float(ref.abs().max()))
+    # the image of the result is the A operand of a second product
+    n2 = 130
+    w2 = _rand((n2, n), 4) / n ** 0.5
+    c2, _ = _ops.tc_gemm(img, _ops.tc_pack(w2, 256), m, n2, n, c=True)
+    ref2 = _bf(c) @ _bf(w2).T
+    assert float((c2.double() - ref2).abs().max()) < 2e-4 * (1 + float(ref2.abs().max()))
+
+
+def test_backward_products_and_k_ranges():
+    m, n, k = 700, 328, 1650                          # dX = dY W: reduction over the 1650 outputs
+    gy, w, h = _rand((m, k), 5), _rand((k, n), 6) / k ** 0.5, _rand((m, n), 7)
+    gx, _ = _ops.tc_gemm(_ops.tc_pack(gy, 128), _ops.tc_pack(w, 256, transpose=True), m, n, k, c=True, aux=h)
+    ref = (_bf(gy) @ _bf(w)) * torch.where(h > 0, torch.ones_like(h), h + 1).double()
+    assert float((gx.double() - ref).abs().max()) < 3e-4 * (1 + float(ref.abs().max()))
+    # weight gradient dW = dY^T X over a batch of 5000, split-K with atomics into a zero-filled C
+    B, no, ni = 5000, 300, 200
+    gy, x = _rand((B, no), 8), _rand((B, ni), 9)
+    gw, _ = _ops.tc_gemm(_ops.tc_pack(gy, 128, transpose=True), _ops.tc_pack(x, 256, transpose=True), no, ni, B, c=True, split_k=16)
+    ref = _bf(gy).T @ _bf(x)
+    assert float((gw.double() - ref).abs().max()) < 3e-4 * (1 + float(ref.abs().max()))
+    # staircase: only the k-blocks inside the given range are multiplied
+    m, n, k = 300, 512, 640
+    x, w = _rand((m, k), 10), _rand((n, k), 11)
+    ranges = torch.tensor([[0, 3], [2, 10]], dtype=torch.int32, device=DEV)      # n-tile 0: k < 192; n-tile 1: k >= 128
+    c, _ = _ops.tc_gemm(_ops.tc_pack(x, 128), _ops.tc_pack(w, 256), m, n, k, c=True, k_block_ranges=ranges)
+    wm = w.clone()
+    wm[:256, 192:] = 0
+    wm[256:, :128] = 0
+    ref = _bf(x) @ _bf(wm).T
+    assert float((c.double() - ref).abs().max()) < 3e-4 * (1 + float(ref.abs().max()))

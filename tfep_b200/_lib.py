@@ -88,6 +88,13 @@ class FusedInvArgs(Structure):
                 ('error_flag', c_void_p)]
 
 
+class TcGemmArgs(Structure):
+    _fields_ = [('a_image', c_void_p), ('b_image', c_void_p), ('m', c_int32), ('n', c_int32), ('k', c_int32),
+                ('activation', c_int32), ('c', c_void_p), ('ldc', c_int64), ('bias', c_void_p), ('aux', c_void_p),
+                ('ldaux', c_int64), ('out_image', c_void_p), ('k_block_ranges', c_void_p), ('split_k', c_int32),
+                ('reserved', c_int32), ('error_flag', c_void_p)]
+
+
 class SweepArgs(Structure):
     _fields_ = [('dtype', c_int32), ('batch', c_int32), ('n_features', c_int32), ('n_linear', c_int32),
                 ('y', c_void_p), ('ldy', c_int64), ('x', c_void_p), ('ldx', c_int64), ('logdet', c_void_p),
@@ -116,6 +123,9 @@ SYMBOLS = {
     'tfepb_spline_backward': (c_int32, [POINTER(TxIo), POINTER(SplineCfg), POINTER(TxGrads), c_void_p]),
     'tfepb_sos_backward': (c_int32, [POINTER(TxIo), c_int32, POINTER(TxGrads), c_void_p]),
     'tfepb_moebius_backward': (c_int32, [POINTER(TxIo), c_int32, c_double, c_int32, POINTER(TxGrads), c_void_p]),
+    'tfepb_tc_image_bytes': (c_int64, [c_int64, c_int64, c_int32]),
+    'tfepb_tc_pack': (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    'tfepb_tc_gemm': (c_int32, [POINTER(TcGemmArgs), c_void_p]),
     'tfepb_periodic_embedding': (c_int32, [c_int32, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_double, c_double,
                                            c_void_p, c_int64, c_void_p]),
     'tfepb_periodic_embedding_backward': (c_int32, [c_int32, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_double,

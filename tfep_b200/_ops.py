@@ -328,3 +328,47 @@ def mt19937_indices(state_dev, count, max_idx, out=None):
         check(_lib.load().tfepb_mt19937_indices(ptr(state_dev), int(count), int(max_idx), ptr(idx),
                                                 stream_ptr(state_dev)))
     return idx
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core GEMM (bf16 operand images, fp32 accumulation)
+# ---------------------------------------------------------------------------------------------
+
+def tc_pack(src, block_rows, transpose=False, out=None):
+    """bf16 operand image of a 2-D fp32 CUDA tensor (rows x k, or its transpose if ``transpose``); see tfepb_tc_pack."""
+    require_cuda(src)
+    if src.dtype != torch.float32:
+        raise _lib.TfepB200Error('tc_pack takes float32 tensors')
+    src = _rows(src)
+    rows, k = (src.shape[1], src.shape[0]) if transpose else (src.shape[0], src.shape[1])
+    lib = _lib.load()
+    nbytes = lib.tfepb_tc_image_bytes(rows, k, block_rows)
+    img = out if out is not None else torch.empty(nbytes, dtype=torch.uint8, device=src.device)
+    assert img.numel() >= nbytes
+    with torch.cuda.device(src.device):
+        check(lib.tfepb_tc_pack(ptr(src), _ld(src), rows, k, block_rows, int(transpose), ptr(img), stream_ptr(src)))
+    return img
+
+
+def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, aux=None, out_image=False,
+            k_block_ranges=None, split_k=1, error_flag=None):
+    """C = act(A B^T + bias) [* ELU'(aux)] from operand images; returns (c, out_img).  ``c``: True to allocate, a
+    tensor to write into (zero-filled by the caller when split_k > 1), None for no fp32 output."""
+    lib = _lib.load()
+    dev = a_img.device
+    if c is True:
+        pad4 = (n + 3) // 4 * 4
+        c = (torch.zeros if split_k > 1 else torch.empty)((m, pad4), dtype=torch.float32, device=dev)[:, :n]
+    img = None
+    if out_image:
+        img = torch.empty(lib.tfepb_tc_image_bytes(m, n, 128), dtype=torch.uint8, device=dev)
+    a = _lib.TcGemmArgs(a_image=a_img.data_ptr(), b_image=b_img.data_ptr(), m=m, n=n, k=k, activation=activation,
+                        c=None if c is None else c.data_ptr(), ldc=0 if c is None else _ld(c),
+                        bias=None if bias is None else bias.data_ptr(),
+                        aux=None if aux is None else aux.data_ptr(), ldaux=0 if aux is None else _ld(aux),
+                        out_image=None if img is None else img.data_ptr(),
+                        k_block_ranges=None if k_block_ranges is None else k_block_ranges.data_ptr(),
+                        split_k=int(split_k), reserved=0, error_flag=None if error_flag is None else error_flag.data_ptr())
+    with torch.cuda.device(dev):
+        check(lib.tfepb_tc_gemm(ctypes.byref(a), stream_ptr(a_img)))
+    return c, img

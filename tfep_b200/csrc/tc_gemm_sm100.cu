@@ -1,0 +1,344 @@
+// General masked linear layers on the tcgen05 tensor cores (bf16 operands, fp32 accumulation), for any MADE
+// shape and for training: the three products of nn/masked.py:266-302
+//     forward         Y  = act(X W^T + b)
+//     backward input  dX = (dY W) * ELU'(H_prev)
+//     backward weight dW += dY^T X
+// are all C[M x N] = A[M x K] . B[N x K]^T with both operands K-major, so ONE kernel serves them; what differs is
+// how the operand IMAGES are produced (tfepb_tc_pack: fp32 row-major matrix, optionally transposed, -> bf16 blocks
+// that are exact images of the shared-memory operand layout, so a block moves with one bulk copy).
+//
+// Image of an operand with R rows and K reduction elements, blocked (BR rows x 64 k), BR = 128 (A) or 256 (B):
+//     block (rb, kb) at byte offset (rb * ceil(K / 64) + kb) * BR * 128;
+//     inside a block: for each slab s of 8 k-values (8 slabs): BR rows x 16 bytes (K-major core matrices, no swizzle).
+//
+// Kernel: persistent CTAs walk the (m-tile of 128 rows, n-tile of 256 columns) output tiles, n fastest (the A rows
+// of an m-tile stay in L2 across its n-tiles).  Warp 0 streams (A block, B block) stages of 48 KB through a 4-deep
+// mbarrier ring with bulk copies; warp 1 issues tcgen05.mma (M = 128, N = 256, K = 16, both operands from shared
+// memory) into one of TWO 256-column accumulators in tensor memory; warps 2-9 drain the other accumulator:
+// bias, ELU or ELU' multiplier, fp32 store, and optionally the bf16 image of the result, which is the A operand of
+// the next layer (written coalesced: consecutive rows are consecutive 16-byte chunks of a slab).  A per-n-tile range
+// of k-blocks skips the all-zero part of a degree-sorted (staircase) masked weight; split-K with fp32 atomics serves
+// the weight gradient, whose reduction runs over the batch.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace tfepb {
+namespace tcg {
+
+using namespace tc;
+
+constexpr int BM = 128, BN = 256, KB = 64;
+constexpr int A_BLOCK = BM * KB * 2, B_BLOCK = BN * KB * 2, STAGE_BYTES = A_BLOCK + B_BLOCK;   // 16 + 32 KB
+constexpr int STAGES = 4;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 64 + EPI_WARPS * 32;
+
+struct Params {
+    const uint8_t* a_img; const uint8_t* b_img;
+    int M, N, K, k_blocks;              // k_blocks = ceil(K / 64)
+    float* C; int64_t ldc;              // fp32 output (row-major) or null
+    const float* bias;                  // (N,) or null
+    int act;                            // TFEPB_ACT_*
+    const float* aux; int64_t ldaux;    // multiply by ELU'(aux) = (h > 0 ? 1 : h + 1), or null
+    uint8_t* out_img; int out_k_blocks; // bf16 image (128-row blocks, k = column index) of the result, or null
+    const int* kranges;                 // per n-tile: [first, end) k-block, or null
+    int atomic;                         // atomicAdd into C (split-K)
+    int k_chunk_blocks;                 // split-K: k-blocks per blockIdx.y slice, 0 = no split
+    int tiles_m, tiles_n;
+    int* error;
+};
+
+struct Smem {
+    uint64_t full[STAGES], empty[STAGES];
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad[3];
+};
+
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_constant__ Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* ring = smem_raw;
+    Smem* sm = reinterpret_cast<Smem*>(ring + (size_t)STAGES * STAGE_BYTES);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_tiles = p.tiles_m * p.tiles_n;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&sm->acc_full[b], 1); mbar_init(&sm->acc_empty[b], EPI_WARPS * 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(&sm->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm->tmem_base;
+
+    // k-block range of a tile (staircase range of its n-tile, intersected with this CTA's split-K slice)
+    auto krange = [&](int tn, int& k0, int& k1) {
+        k0 = 0; k1 = p.k_blocks;
+        if (p.kranges != nullptr) { k0 = max(0, p.kranges[2 * tn]); k1 = min(p.k_blocks, p.kranges[2 * tn + 1]); }
+        if (p.k_chunk_blocks > 0) {
+            k0 = max(k0, (int)blockIdx.y * p.k_chunk_blocks);
+            k1 = min(k1, ((int)blockIdx.y + 1) * p.k_chunk_blocks);
+        }
+        if (k1 < k0) k1 = k0;
+    };
+
+    if (warp == 0) {
+        // =========================== producer ===========================
+        uint32_t stage = 0, phase = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+            int k0, k1;
+            krange(tn, k0, k1);
+            for (int kb = k0; kb < k1; ++kb) {
+                mbar_wait(&sm->empty[stage], phase ^ 1, p.error, 1);
+                if (elect_one()) {
+                    uint8_t* dst = ring + (size_t)stage * STAGE_BYTES;
+                    mbar_expect_tx(&sm->full[stage], STAGE_BYTES);
+                    bulk_g2s(dst, p.a_img + ((size_t)tm * p.k_blocks + kb) * A_BLOCK, A_BLOCK, &sm->full[stage]);
+                    bulk_g2s(dst + A_BLOCK, p.b_img + ((size_t)tn * p.k_blocks + kb) * B_BLOCK, B_BLOCK, &sm->full[stage]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer ===========================
+        uint32_t stage = 0, phase = 0, tcount = 0;
+        const uint32_t ring16 = smem_u32(ring) >> 4;
+        // kind::f16, A = B = bf16, D = fp32, both K-major, M = 128, N = 256
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
+            const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+            int k0, k1;
+            krange(tn, k0, k1);
+            const uint32_t buf = tcount & 1;
+            mbar_wait(&sm->acc_empty[buf], ((tcount >> 1) & 1) ^ 1, p.error, 2);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem + buf * BN;
+            uint32_t accumulate = 0u;
+            for (int kb = k0; kb < k1; ++kb) {
+                mbar_wait(&sm->full[stage], phase, p.error, 3);
+                tc_fence_after();
+                const uint32_t a16 = ring16 + stage * (STAGE_BYTES >> 4);
+                const uint32_t b16 = a16 + (A_BLOCK >> 4);
+                if (elect_one()) {
+#pragma unroll
+                    for (uint32_t ks = 0; ks < KB / 16; ++ks) {
+                        // per K = 16 step two 8-k slabs: A slab = 128 rows x 16 B = 2 KB, B slab = 256 rows x 16 B = 4 KB
+                        const uint64_t da = ((uint64_t)DESC_HI << 32) | (a16 + ks * 256u + ((2048u >> 4) << 16));
+                        const uint64_t db = ((uint64_t)DESC_HI << 32) | (b16 + ks * 512u + ((4096u >> 4) << 16));
+                        umma_ss(d_tmem, da, db, idesc, accumulate);
+                        accumulate = 1u;
+                    }
+                    umma_commit(&sm->empty[stage]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (elect_one()) umma_commit(&sm->acc_full[buf]);
+            __syncwarp();
+        }
+    } else {
+        // =========================== epilogue: 8 warps, two column halves x four lane quadrants ===========================
+        const int ew = warp - 2;
+        const int half = ew >> 2;                      // columns [half * 128, half * 128 + 128) of the tile
+        const int row = (warp & 3) * 32 + lane;        // TMEM lane = row of the tile
+        const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t tcount = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
+            const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+            int k0, k1;
+            krange(tn, k0, k1);
+            const uint32_t buf = tcount & 1;
+            mbar_wait(&sm->acc_full[buf], (tcount >> 1) & 1, p.error, 4);
+            tc_fence_after();
+            const int gm = tm * BM + row;
+            const bool row_ok = gm < p.M;
+            const bool empty = k1 <= k0;               // nothing was accumulated: the tile is all zeros
+#pragma unroll 1
+            for (int c16 = 0; c16 < 8; ++c16) {
+                const int col0 = half * 128 + c16 * 16;
+                const int gn0 = tn * BN + col0;
+                uint32_t r[16];
+                if (!empty) {
+                    tmem_ld16(lane_addr + buf * BN + col0, r);
+                    tmem_wait8(r); tmem_wait8(r + 8);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) r[i] = 0u;
+                }
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int gn = gn0 + i;
+                    float x = __uint_as_float(r[i]);
+                    if (!p.atomic) {
+                        if (p.bias != nullptr && gn < p.N) x += __ldg(p.bias + gn);
+                        if (p.act == TFEPB_ACT_ELU) x = x > 0.f ? x : ex2(x * LOG2E) - 1.f;
+                        if (p.aux != nullptr && row_ok && gn < p.N) {
+                            const float h = __ldg(p.aux + (int64_t)gm * p.ldaux + gn);
+                            x *= (h > 0.f) ? 1.f : (h + 1.f);
+                        }
+                        if (gn >= p.N) x = 0.f;
+                    }
+                    v[i] = x;
+                }
+                if (p.C != nullptr && row_ok) {
+                    float* c = p.C + (int64_t)gm * p.ldc + gn0;
+                    if (p.atomic) {
+                        if (!empty) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (gn0 + i < p.N) atomicAdd(c + i, v[i]);
+                        }
+                    } else if (gn0 + 15 < p.N && (p.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0)) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            reinterpret_cast<float4*>(c)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (gn0 + i < p.N) c[i] = v[i];
+                    }
+                }
+                if (p.out_img != nullptr) {
+                    // columns are the reduction index of the next product: k-block = gn / 64, slab = (gn % 64) / 8
+                    const int kblk = gn0 >> 6;
+                    if (kblk < p.out_k_blocks) {
+                        uint8_t* blk = p.out_img + ((size_t)tm * p.out_k_blocks + kblk) * A_BLOCK + (size_t)row * 16;
+                        const int slab = (gn0 & 63) >> 3;
+                        uint4 q0, q1;
+                        q0.x = pack_bf16(v[0], v[1]); q0.y = pack_bf16(v[2], v[3]); q0.z = pack_bf16(v[4], v[5]); q0.w = pack_bf16(v[6], v[7]);
+                        q1.x = pack_bf16(v[8], v[9]); q1.y = pack_bf16(v[10], v[11]); q1.z = pack_bf16(v[12], v[13]); q1.w = pack_bf16(v[14], v[15]);
+                        *reinterpret_cast<uint4*>(blk + (size_t)slab * 2048) = q0;
+                        *reinterpret_cast<uint4*>(blk + (size_t)(slab + 1) * 2048) = q1;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&sm->acc_empty[buf]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// fp32 row-major (or its transpose) -> bf16 image.  One CTA per (row block, k block); 256 threads.
+//   transpose == 0: element (row, k) = src[row * ld + k];  transpose == 1: element (row, k) = src[k * ld + row].
+__global__ void __launch_bounds__(256) tc_pack_kernel(const float* __restrict__ src, int64_t ld, int rows, int K, int block_rows,
+                                                      int transpose, uint8_t* __restrict__ img) {
+    __shared__ float tile[64][65];
+    const int k_blocks = (K + KB - 1) / KB;
+    const int rb = blockIdx.y, kb = blockIdx.x;
+    uint8_t* blk = img + ((size_t)rb * k_blocks + kb) * (size_t)block_rows * 128;
+    const int r0 = rb * block_rows, k0 = kb * KB;
+    if (!transpose) {
+        // thread -> (row, slab): 8 consecutive k per thread; consecutive threads = consecutive rows (coalesced image write)
+        for (int i = threadIdx.x; i < block_rows * 8; i += 256) {
+            const int row = i % block_rows, slab = i / block_rows;
+            const int gr = r0 + row, gk = k0 + slab * 8;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (gr < rows && gk + j < K) ? __ldg(src + (int64_t)gr * ld + gk + j) : 0.f;
+            uint4 q;
+            q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]); q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
+            *reinterpret_cast<uint4*>(blk + (size_t)slab * block_rows * 16 + (size_t)row * 16) = q;
+        }
+    } else {
+        // 64 rows of the image at a time: read src[k][row] coalesced along rows, transpose through shared memory
+        for (int rs = 0; rs < block_rows; rs += 64) {
+            for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+                const int kk = i / 64, rr = i % 64;
+                const int gr = r0 + rs + rr, gk = k0 + kk;
+                tile[kk][rr] = (gr < rows && gk < K) ? __ldg(src + (int64_t)gk * ld + gr) : 0.f;
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < 64 * 8; i += 256) {
+                const int rr = i % 64, slab = i / 64;
+                uint4 q;
+                q.x = pack_bf16(tile[slab * 8 + 0][rr], tile[slab * 8 + 1][rr]);
+                q.y = pack_bf16(tile[slab * 8 + 2][rr], tile[slab * 8 + 3][rr]);
+                q.z = pack_bf16(tile[slab * 8 + 4][rr], tile[slab * 8 + 5][rr]);
+                q.w = pack_bf16(tile[slab * 8 + 6][rr], tile[slab * 8 + 7][rr]);
+                *reinterpret_cast<uint4*>(blk + (size_t)slab * block_rows * 16 + (size_t)(rs + rr) * 16) = q;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace tcg
+}  // namespace tfepb
+
+using namespace tfepb;
+
+extern "C" int64_t tfepb_tc_image_bytes(int64_t rows, int64_t k, int32_t block_rows) {
+    if (rows < 0 || k < 0 || (block_rows != 128 && block_rows != 256)) return -1;
+    const int64_t rb = (rows + block_rows - 1) / block_rows, kb = (k + tcg::KB - 1) / tcg::KB;
+    return rb * kb * (int64_t)block_rows * 128;
+}
+
+extern "C" int tfepb_tc_pack(const float* src, int64_t ld, int32_t rows, int32_t k, int32_t block_rows, int32_t transpose,
+                             void* image, tfepb_stream_t stream) {
+    TFEPB_CHECK_ARG(src && image, "null buffer");
+    TFEPB_CHECK_ARG(rows > 0 && k > 0, "bad sizes");
+    TFEPB_CHECK_ARG(block_rows == 128 || block_rows == 256, "block_rows must be 128 (A operand) or 256 (B operand)");
+    TFEPB_CHECK_ARG((reinterpret_cast<uintptr_t>(image) & 15) == 0, "the image must be 16-byte aligned");
+    if (int rc = require_sm100()) return rc;
+    dim3 grid((unsigned)((k + tcg::KB - 1) / tcg::KB), (unsigned)((rows + block_rows - 1) / block_rows));
+    tcg::tc_pack_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, ld, rows, k, block_rows, transpose, (uint8_t*)image);
+    return check_launch("tc_pack");
+}
+
+extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream) {
+    TFEPB_CHECK_ARG(a != nullptr, "null argument struct");
+    TFEPB_CHECK_ARG(a->a_image && a->b_image, "null operand image");
+    TFEPB_CHECK_ARG(a->m > 0 && a->n > 0 && a->k > 0, "bad sizes");
+    TFEPB_CHECK_ARG(a->c != nullptr || a->out_image != nullptr, "no output");
+    TFEPB_CHECK_ARG(a->c == nullptr || a->ldc >= a->n, "leading dimension smaller than the row length");
+    TFEPB_CHECK_ARG(!(a->split_k > 1) || (a->c != nullptr && a->out_image == nullptr && a->bias == nullptr && a->aux == nullptr &&
+                                          a->activation == TFEPB_ACT_NONE),
+                    "split-K accumulates raw products into a zero-filled fp32 C only");
+    TFEPB_CHECK_ARG(((uintptr_t)a->a_image % 16 == 0) && ((uintptr_t)a->b_image % 16 == 0) && ((uintptr_t)a->out_image % 16 == 0),
+                    "operand images must be 16-byte aligned");
+    if (int rc = require_sm100()) return rc;
+    tcg::Params p{};
+    p.a_img = (const uint8_t*)a->a_image; p.b_img = (const uint8_t*)a->b_image;
+    p.M = a->m; p.N = a->n; p.K = a->k; p.k_blocks = (a->k + tcg::KB - 1) / tcg::KB;
+    p.C = (float*)a->c; p.ldc = a->ldc; p.bias = (const float*)a->bias; p.act = a->activation;
+    p.aux = (const float*)a->aux; p.ldaux = a->ldaux;
+    p.out_img = (uint8_t*)a->out_image; p.out_k_blocks = (a->n + tcg::KB - 1) / tcg::KB;
+    p.kranges = a->k_block_ranges;
+    p.tiles_m = (a->m + tcg::BM - 1) / tcg::BM; p.tiles_n = (a->n + tcg::BN - 1) / tcg::BN;
+    p.error = a->error_flag;
+    int splits = a->split_k > 1 ? a->split_k : 1;
+    if (splits > p.k_blocks) splits = p.k_blocks;
+    p.atomic = splits > 1 ? 1 : 0;
+    p.k_chunk_blocks = splits > 1 ? (p.k_blocks + splits - 1) / splits : 0;
+    if (splits > 1) splits = (p.k_blocks + p.k_chunk_blocks - 1) / p.k_chunk_blocks;
+    const size_t smem = (size_t)tcg::STAGES * tcg::STAGE_BYTES + sizeof(tcg::Smem) + 1024;
+    static thread_local bool configured = false;
+    if (!configured) {
+        TFEPB_CUDA(cudaFuncSetAttribute(tcg::tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int tiles = p.tiles_m * p.tiles_n;
+    int gx = sm_count() / splits;
+    if (gx < 1) gx = 1;
+    if (gx > tiles) gx = tiles;
+    dim3 grid((unsigned)gx, (unsigned)splits);
+    tcg::tc_gemm_kernel<<<grid, tcg::THREADS, smem, as_stream(stream)>>>(p);
+    return check_launch("tc_gemm_kernel");
+}
