@@ -66,21 +66,27 @@ if 'cfg2mix' in which:
         round_trip_median_err=float((xi - x).abs().max(dim=1).values.median()))
 if 'cfg3' in which:
     B = 262144
-    seq, _ = cfg_flow_modules('cfg3', dev)
-    x = cases.cfg_input('cfg3', B).to(dev)
-    opt = torch.optim.AdamW(seq.parameters(), lr=1e-4)
+    for precision in ('fp32', 'bf16'):
+        seq, _ = cfg_flow_modules('cfg3', dev)
+        for m in seq:
+            m.precision = precision
+        x = cases.cfg_input('cfg3', B).to(dev)
+        opt = torch.optim.AdamW(seq.parameters(), lr=1e-4)
 
-    def step():
-        opt.zero_grad(set_to_none=True)
-        y, ld = seq(x)
-        u = 0.5 * ((y - 0.5) ** 2).sum(dim=1)             # harmonic target potential
-        loss = (u - ld).mean()
-        loss.backward()
-        opt.step()
-        return loss
-    ms = timed(step, 3, 1)
-    out(config='cfg3 6xMAF (3 SOS + 3 Moebius) D=300 B=262144 training step (fwd+bwd+AdamW, fp32)', step_ms=ms,
-        samples_per_s=B / ms * 1e3, loss=float(step()))
+        def step():
+            opt.zero_grad(set_to_none=True)
+            y, ld = seq(x)
+            u = 0.5 * ((y - 0.5) ** 2).sum(dim=1)             # harmonic target potential
+            loss = (u - ld).mean()
+            loss.backward()
+            opt.step()
+            return loss
+        ms = timed(step, 3, 1)
+        kind = 'exact fp32 FFMA GEMMs' if precision == 'fp32' else 'tcgen05 GEMMs (bf16 operands, fp32 accumulation) forward and backward'
+        out(config=f'cfg3 6xMAF (3 SOS + 3 Moebius) D=300 B=262144 training step (fwd+bwd+AdamW), {kind}', step_ms=ms,
+            samples_per_s=B / ms * 1e3, loss=float(step().detach()))
+        del seq, opt, x
+        torch.cuda.empty_cache()
 if 'cfg4' in which:
     from tfep_b200.analysis import bootstrap, fep_estimator
     n = 100_000_000

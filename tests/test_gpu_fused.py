@@ -224,15 +224,41 @@ def test_mixed_and_non_circular_splines(cfg):
         assert float((x.abs() > 5).float().mean()) > 0.01          # the tails were exercised
 
 
-def test_inference_only_and_eligibility():
-    from tfep_b200._lib import TfepB200Error
+def test_bf16_outside_the_fused_kernel_uses_the_tensor_core_gemm():
+    """precision='bf16' where the one-launch kernel does not apply -- training (autograd) and other transformers --
+    runs the MADE conditioner on the general tensor-core GEMM, forward and backward, with the exact transformer
+    kernels: results and gradients agree with the fp32 path to bf16 operand rounding."""
     from tfep_b200.nn.conditioners import generate_degrees
     from tfep_b200.nn.flows import MAF
+    # (a) spline flow under autograd: gradients w.r.t. x and every parameter
     seq, _ = cfg_flow_modules('cfg2', DEV, n_layers=1)
-    seq[0].precision = 'bf16'
-    with pytest.raises(NotImplementedError, match='inference path'):
-        seq[0](cases.cfg_input('cfg2', 8).to(DEV))          # parameters require grad and grad mode is on
+    maf = seq[0]
+    x = cases.cfg_input('cfg2', 300).to(DEV)
+    cy, cl = cases.normal((300, 66), 78).to(DEV), cases.normal((300,), 79).to(DEV)
+
+    def grads(precision):
+        maf.precision = precision
+        maf.zero_grad(set_to_none=True)
+        xg = x.clone().requires_grad_(True)
+        y, ld = maf(xg)
+        ((y * cy).sum() + (ld * cl).sum()).backward()
+        return y.detach(), ld.detach(), xg.grad, {k: p.grad.clone() for k, p in maf.named_parameters()}
+
+    y32, ld32, gx32, gp32 = grads('fp32')
+    y16, ld16, gx16, gp16 = grads('bf16')
+    assert float(_circ(y16, y32).mean()) < 2e-3 and float((ld16 - ld32).abs().mean()) < 8e-3
+
+    def rel(a, b):
+        return float((a - b).norm() / (b.norm() + 1e-12))
+
+    assert rel(gx16, gx32) < 5e-2
+    for k in gp32:
+        assert rel(gp16[k], gp32[k]) < 5e-2, k
+    # (b) a transformer the fused kernel does not cover (affine), inference
     affine = MAF(generate_degrees(6), initialize_identity=False).to(DEV)
-    affine.precision = 'bf16'
-    with pytest.raises(TfepB200Error, match='fused bf16 path unavailable'), torch.no_grad():
-        affine(torch.randn(4, 6, device=DEV))
+    xa = torch.randn(40, 6, device=DEV)
+    with torch.no_grad():
+        ya, lda = affine(xa)
+        affine.precision = 'bf16'
+        yb, ldb = affine(xa)
+    assert float((ya - yb).abs().max()) < 5e-2 and float((lda - ldb).abs().max()) < 5e-2

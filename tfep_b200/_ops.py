@@ -372,3 +372,66 @@ def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, au
     with torch.cuda.device(dev):
         check(lib.tfepb_tc_gemm(ctypes.byref(a), stream_ptr(a_img)))
     return c, img
+
+
+class MadeFunctionTC(torch.autograd.Function):
+    """All layers of a MADE conditioner on the tensor cores (tfepb_tc_gemm), as one autograd node.
+
+    Same contract as :class:`MadeFunction` (packed effective weights in, dense gradients out) with bf16 operands and
+    fp32 accumulation: the forward pass chains the bf16 image of every hidden activation into the next product; the
+    backward pass runs dX = (dY W) * ELU'(h) and dW = dY^T X (split over the batch, fp32 atomics) on the same kernel
+    from images of dY, W^T and the transposed activations.  ``kb_fwd[l]`` / ``kb_bwd[l]`` are the per-256-column-tile
+    ranges of non-zero 64-wide k-blocks of the staircase masks (or None).
+    """
+
+    @staticmethod
+    def forward(ctx, x, n_layers, kb_fwd, kb_bwd, *wb):
+        ws, bs = wb[:n_layers], wb[n_layers:]
+        B = x.shape[0]
+        acts = [x]
+        img = tc_pack(x, 128)
+        h = x
+        for l in range(n_layers):
+            last = l == n_layers - 1
+            N, K = ws[l].shape
+            wimg = tc_pack(ws[l], 256)
+            h, img = tc_gemm(img, wimg, B, N, K, c=True, bias=bs[l], activation=ACT_NONE if last else ACT_ELU,
+                             out_image=not last, k_block_ranges=None if kb_fwd is None else kb_fwd[l])
+            if not last:
+                acts.append(h)
+        ctx.save_for_backward(*acts, *ws)
+        ctx.n_layers = n_layers
+        ctx.kb_bwd = kb_bwd
+        return h
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        L = ctx.n_layers
+        saved = ctx.saved_tensors
+        acts, ws = saved[:L], saved[L:]
+        B = grad_out.shape[0]
+        g = _rows(grad_out.contiguous())
+        gimg = tc_pack(g, 128)
+        gws, gbs = [None] * L, [None] * L
+        gx = None
+        n_sm = torch.cuda.get_device_properties(g.device).multi_processor_count
+        for l in range(L - 1, -1, -1):
+            N, K = ws[l].shape
+            if ctx.needs_input_grad[4 + l] or ctx.needs_input_grad[4 + L + l]:
+                # dW[N x K] = dY^T X: reduction over the batch, split so that the grid fills the machine
+                tiles = ((N + 127) // 128) * ((K + 255) // 256)
+                split = max(1, min((B + 63) // 64, (2 * n_sm + tiles - 1) // tiles))
+                gws[l], _ = tc_gemm(tc_pack(g, 128, transpose=True), tc_pack(acts[l], 256, transpose=True), N, K, B,
+                                    c=True, split_k=split)
+                gbs[l] = g.sum(dim=0)
+            if l > 0 or ctx.needs_input_grad[0]:
+                wt = tc_pack(ws[l], 256, transpose=True)            # rows = inputs of the layer, k = its outputs
+                g, gimg = tc_gemm(gimg, wt, B, K, N, c=True, aux=acts[l] if l > 0 else None, out_image=l > 0,
+                                  k_block_ranges=None if ctx.kb_bwd is None else ctx.kb_bwd[l])
+                if l == 0:
+                    gx = g
+        return (gx, None, None, None, *gws, *gbs)
+
+
+def made_forward_tc(x, weights, biases, kb_fwd=None, kb_bwd=None):
+    return MadeFunctionTC.apply(x, len(weights), kb_fwd, kb_bwd, *weights, *biases)

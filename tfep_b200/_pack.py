@@ -80,6 +80,24 @@ class MadePlan:
                                        [p.to(device) for p in self.perms])
         return self._device_cache[key]
 
+    def tc_ranges(self, device):
+        """Per layer, for the tensor-core GEMM (tiles of 256 output columns, k-blocks of 64): the non-zero k-block
+        range [first, end) of every tile, forward (tiles over the layer's outputs, k over its inputs) and backward
+        input (tiles over the inputs, k over the outputs).  Lists of int32 (tiles, 2) device tensors."""
+        key = ('tc', str(device))
+        if key not in self._device_cache:
+            fwd, bwd = [], []
+            for l in range(self.n_layers):
+                d_in, d_out = self.packed_degrees[l], self.packed_degrees[l + 1]
+                strict = l == self.n_layers - 1
+                mask = (d_out[:, None] > d_in[None, :]) if strict else (d_out[:, None] >= d_in[None, :])
+                for m, dst in ((mask, fwd), (mask.t(), bwd)):
+                    r = _ranges(m, 256, axis=0)                    # per 256-row tile: bounding column range
+                    kb = torch.stack([r[:, 0] // 64, (r[:, 1] + 63) // 64], dim=1).to(torch.int32)
+                    dst.append(kb.contiguous().to(device))
+            self._device_cache[key] = (fwd, bwd)
+        return self._device_cache[key]
+
     def pack(self, weights, biases):
         """Permute effective weights / biases given in the reference's order into packed order."""
         device = weights[0].device

@@ -169,9 +169,15 @@ class MADE(_conditioner.Conditioner):
             self._packed_cache[id(plan)] = hit
         return hit[1]
 
-    def run_plan(self, x, plan):
-        """Conditioner output in the packed output order of ``plan``."""
+    def run_plan(self, x, plan, precision='fp32'):
+        """Conditioner output in the packed output order of ``plan``.  ``precision='bf16'``: the three products of
+        every layer (forward, and both backward products under autograd) run on the tensor cores."""
         pw, pb = self.packed_weights(plan)
+        if precision == 'bf16':
+            if x.dtype != torch.float32:
+                raise _ops._lib.TfepB200Error("precision='bf16' takes float32 inputs")
+            kb_fwd, kb_bwd = plan.tc_ranges(x.device)
+            return _ops.made_forward_tc(x, pw, pb, kb_fwd, kb_bwd)
         k_ranges, n_ranges, _ = plan.tables(x.device)
         return _ops.made_forward(x, pw, pb, k_ranges, n_ranges)
 

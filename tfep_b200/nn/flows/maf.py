@@ -138,16 +138,26 @@ class MAF(AutoregressiveFlow):
     def forward(self, x: torch.Tensor):
         """Returns ``(y, log_det_J)`` with shapes ``(batch, n_features)`` and ``(batch,)``."""
         pk = self._pack()
-        if self.precision == 'bf16':
-            return self._forward_fused(x)
-        if self.precision != 'fp32':
+        if self.precision not in ('fp32', 'bf16'):
             raise ValueError("precision must be 'fp32' or 'bf16'")
+        if self.precision == 'bf16' and self._use_fused(x):
+            return self._forward_fused(x)
         if pk is False or self._n_conditioner_indices > 0:
             return super().forward(x)
         layouts, _ = self._packed_tables(x.device)
         xc = x if self._embedding is None else self._embedding(x)
-        par = self._conditioner.run_plan(xc.contiguous(), pk['plan'])
+        # precision='bf16' outside the fused kernel (other transformers, training): the MADE conditioner runs on the
+        # general tensor-core GEMM, forward and backward; the transformer kernels stay exact
+        par = self._conditioner.run_plan(xc.contiguous(), pk['plan'], precision=self.precision)
         return _program.run(pk['parts'], x.contiguous(), par, layouts, passthrough=self.has_fixed_indices)
+
+    def _use_fused(self, x):
+        """The one-launch fused kernel serves inference of the splines it covers; everything else that asks for
+        precision='bf16' goes through the general tensor-core GEMM."""
+        from ... import _fused
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return False
+        return _fused.eligibility(self) is None
 
     def _forward_fused(self, x):
         """Tensor-core path: the whole layer in one kernel launch (no autograd, no silent fallback)."""

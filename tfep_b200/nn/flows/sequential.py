@@ -30,12 +30,9 @@ class SequentialFlow(torch.nn.Sequential):
     # -- tensor-core fast path: the whole chain of precision='bf16' MAF layers in ONE kernel launch --------
     def _fused_chain_ok(self, x):
         from .maf import MAF
-        from ... import _fused
         if not all(isinstance(f, MAF) and f.precision == 'bf16' for f in self):
             return False
-        if any(_fused.eligibility(f) is not None for f in self):
-            return False
-        return True
+        return all(f._use_fused(x) for f in self)
 
     def _forward_fused_chain(self, x):
         from ... import _fused
