@@ -203,6 +203,9 @@ typedef struct {
                                             non-zero for each tile of 256 output columns (staircase masks) */
     int32_t split_k, reserved;           /* > 1: the reduction is split over that many CTAs per tile */
     int32_t* error_flag;
+    const int32_t* row_ranges;           /* device, NULL or (ceil(n / 256), 2): rows [begin, end) of C that can be
+                                            non-zero for each tile of 256 columns; tiles outside are skipped and
+                                            left untouched (masked weight gradient into a zero-filled C) */
 } tfepb_tc_gemm_args;
 int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream);
 

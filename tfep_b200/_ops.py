@@ -351,7 +351,7 @@ def tc_pack(src, block_rows, transpose=False, out=None):
 
 
 def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, aux=None, out_image=False,
-            k_block_ranges=None, split_k=1, error_flag=None):
+            k_block_ranges=None, row_ranges=None, split_k=1, error_flag=None):
     """C = act(A B^T + bias) [* ELU'(aux)] from operand images; returns (c, out_img).  ``c``: True to allocate, a
     tensor to write into (zero-filled by the caller when split_k > 1), None for no fp32 output."""
     lib = _lib.load()
@@ -368,7 +368,8 @@ def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, au
                         aux=None if aux is None else aux.data_ptr(), ldaux=0 if aux is None else _ld(aux),
                         out_image=None if img is None else img.data_ptr(),
                         k_block_ranges=None if k_block_ranges is None else k_block_ranges.data_ptr(),
-                        split_k=int(split_k), reserved=0, error_flag=None if error_flag is None else error_flag.data_ptr())
+                        split_k=int(split_k), reserved=0, error_flag=None if error_flag is None else error_flag.data_ptr(),
+                        row_ranges=None if row_ranges is None else row_ranges.data_ptr())
     with torch.cuda.device(dev):
         check(lib.tfepb_tc_gemm(ctypes.byref(a), stream_ptr(a_img)))
     return c, img
@@ -385,7 +386,7 @@ class MadeFunctionTC(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, n_layers, kb_fwd, kb_bwd, *wb):
+    def forward(ctx, x, n_layers, kb_fwd, kb_bwd, rr_w, *wb):
         ws, bs = wb[:n_layers], wb[n_layers:]
         B = x.shape[0]
         acts = [x]
@@ -402,6 +403,7 @@ class MadeFunctionTC(torch.autograd.Function):
         ctx.save_for_backward(*acts, *ws)
         ctx.n_layers = n_layers
         ctx.kb_bwd = kb_bwd
+        ctx.rr_w = rr_w
         return h
 
     @staticmethod
@@ -417,12 +419,12 @@ class MadeFunctionTC(torch.autograd.Function):
         n_sm = torch.cuda.get_device_properties(g.device).multi_processor_count
         for l in range(L - 1, -1, -1):
             N, K = ws[l].shape
-            if ctx.needs_input_grad[4 + l] or ctx.needs_input_grad[4 + L + l]:
+            if ctx.needs_input_grad[5 + l] or ctx.needs_input_grad[5 + L + l]:
                 # dW[N x K] = dY^T X: reduction over the batch, split so that the grid fills the machine
                 tiles = ((N + 127) // 128) * ((K + 255) // 256)
                 split = max(1, min((B + 63) // 64, (2 * n_sm + tiles - 1) // tiles))
                 gws[l], _ = tc_gemm(tc_pack(g, 128, transpose=True), tc_pack(acts[l], 256, transpose=True), N, K, B,
-                                    c=True, split_k=split)
+                                    c=True, split_k=split, row_ranges=None if ctx.rr_w is None else ctx.rr_w[l])
                 gbs[l] = g.sum(dim=0)
             if l > 0 or ctx.needs_input_grad[0]:
                 wt = tc_pack(ws[l], 256, transpose=True)            # rows = inputs of the layer, k = its outputs
@@ -430,8 +432,8 @@ class MadeFunctionTC(torch.autograd.Function):
                                   k_block_ranges=None if ctx.kb_bwd is None else ctx.kb_bwd[l])
                 if l == 0:
                     gx = g
-        return (gx, None, None, None, *gws, *gbs)
+        return (gx, None, None, None, None, *gws, *gbs)
 
 
-def made_forward_tc(x, weights, biases, kb_fwd=None, kb_bwd=None):
-    return MadeFunctionTC.apply(x, len(weights), kb_fwd, kb_bwd, *weights, *biases)
+def made_forward_tc(x, weights, biases, kb_fwd=None, kb_bwd=None, rr_w=None):
+    return MadeFunctionTC.apply(x, len(weights), kb_fwd, kb_bwd, rr_w, *weights, *biases)

@@ -83,10 +83,11 @@ class MadePlan:
     def tc_ranges(self, device):
         """Per layer, for the tensor-core GEMM (tiles of 256 output columns, k-blocks of 64): the non-zero k-block
         range [first, end) of every tile, forward (tiles over the layer's outputs, k over its inputs) and backward
-        input (tiles over the inputs, k over the outputs).  Lists of int32 (tiles, 2) device tensors."""
+        input (tiles over the inputs, k over the outputs), and for the weight gradient the row range of every tile of 256
+        input columns.  Lists of int32 (tiles, 2) device tensors."""
         key = ('tc', str(device))
         if key not in self._device_cache:
-            fwd, bwd = [], []
+            fwd, bwd, roww = [], [], []
             for l in range(self.n_layers):
                 d_in, d_out = self.packed_degrees[l], self.packed_degrees[l + 1]
                 strict = l == self.n_layers - 1
@@ -95,7 +96,9 @@ class MadePlan:
                     r = _ranges(m, 256, axis=0)                    # per 256-row tile: bounding column range
                     kb = torch.stack([r[:, 0] // 64, (r[:, 1] + 63) // 64], dim=1).to(torch.int32)
                     dst.append(kb.contiguous().to(device))
-            self._device_cache[key] = (fwd, bwd)
+                # weight gradient (rows = outputs, tiles of 256 input columns): rows the mask leaves non-zero per tile
+                roww.append(_ranges(mask, 256, axis=1).contiguous().to(device))
+            self._device_cache[key] = (fwd, bwd, roww)
         return self._device_cache[key]
 
     def pack(self, weights, biases):

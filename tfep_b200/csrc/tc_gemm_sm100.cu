@@ -42,6 +42,7 @@ struct Params {
     const float* aux; int64_t ldaux;    // multiply by ELU'(aux) = (h > 0 ? 1 : h + 1), or null
     uint8_t* out_img; int out_k_blocks; // bf16 image (128-row blocks, k = column index) of the result, or null
     const int* kranges;                 // per n-tile: [first, end) k-block, or null
+    const int* row_ranges;              // per n-tile: rows [begin, end) of C that can be non-zero; other tiles are skipped, or null
     int atomic;                         // atomicAdd into C (split-K)
     int k_chunk_blocks;                 // split-K: k-blocks per blockIdx.y slice, 0 = no split
     int tiles_m, tiles_n;
@@ -82,6 +83,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     const uint32_t tmem = sm->tmem_base;
 
     // k-block range of a tile (staircase range of its n-tile, intersected with this CTA's split-K slice)
+    auto skipped = [&](int tm, int tn) -> bool {
+        if (p.row_ranges == nullptr) return false;
+        const int rb = p.row_ranges[2 * tn], re = p.row_ranges[2 * tn + 1];
+        return tm * BM + BM <= rb || tm * BM >= re;
+    };
     auto krange = [&](int tn, int& k0, int& k1) {
         k0 = 0; k1 = p.k_blocks;
         if (p.kranges != nullptr) { k0 = max(0, p.kranges[2 * tn]); k1 = min(p.k_blocks, p.kranges[2 * tn + 1]); }
@@ -97,6 +103,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
         uint32_t stage = 0, phase = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+            if (skipped(tm, tn)) continue;
             int k0, k1;
             krange(tn, k0, k1);
             for (int kb = k0; kb < k1; ++kb) {
@@ -117,8 +124,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
         const uint32_t ring16 = smem_u32(ring) >> 4;
         // kind::f16, A = B = bf16, D = fp32, both K-major, M = 128, N = 256
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+            if (skipped(tm, tn)) continue;
             int k0, k1;
             krange(tn, k0, k1);
             const uint32_t buf = tcount & 1;
@@ -147,6 +155,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             }
             if (elect_one()) umma_commit(&sm->acc_full[buf]);
             __syncwarp();
+            ++tcount;
         }
     } else {
         // =========================== epilogue: 8 warps, two column halves x four lane quadrants ===========================
@@ -155,8 +164,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
         const int row = (warp & 3) * 32 + lane;        // TMEM lane = row of the tile
         const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t tcount = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+            if (skipped(tm, tn)) continue;
             int k0, k1;
             krange(tn, k0, k1);
             const uint32_t buf = tcount & 1;
@@ -179,19 +189,46 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                 }
                 float v[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int gn = gn0 + i;
-                    float x = __uint_as_float(r[i]);
-                    if (!p.atomic) {
-                        if (p.bias != nullptr && gn < p.N) x += __ldg(p.bias + gn);
-                        if (p.act == TFEPB_ACT_ELU) x = x > 0.f ? x : ex2(x * LOG2E) - 1.f;
-                        if (p.aux != nullptr && row_ok && gn < p.N) {
-                            const float h = __ldg(p.aux + (int64_t)gm * p.ldaux + gn);
-                            x *= (h > 0.f) ? 1.f : (h + 1.f);
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+                if (!p.atomic) {
+                    const bool full = gn0 + 15 < p.N;
+                    if (p.bias != nullptr) {
+                        if (full && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gn0) + i);
+                                v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (gn0 + i < p.N) v[i] += __ldg(p.bias + gn0 + i);
                         }
-                        if (gn >= p.N) x = 0.f;
                     }
-                    v[i] = x;
+                    if (p.act == TFEPB_ACT_ELU) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], ex2(fminf(v[i], 0.f) * LOG2E) - 1.f);
+                    }
+                    if (p.aux != nullptr && row_ok) {
+                        const float* hrow = p.aux + (int64_t)gm * p.ldaux + gn0;
+                        if (full && (p.ldaux & 3) == 0 && (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float4 h4 = __ldg(reinterpret_cast<const float4*>(hrow) + i);
+                                v[4 * i] *= fminf(h4.x, 0.f) + 1.f; v[4 * i + 1] *= fminf(h4.y, 0.f) + 1.f;
+                                v[4 * i + 2] *= fminf(h4.z, 0.f) + 1.f; v[4 * i + 3] *= fminf(h4.w, 0.f) + 1.f;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (gn0 + i < p.N) v[i] *= fminf(__ldg(hrow + i), 0.f) + 1.f;
+                        }
+                    }
+                    if (!full) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (gn0 + i >= p.N) v[i] = 0.f;
+                    }
                 }
                 if (p.C != nullptr && row_ok) {
                     float* c = p.C + (int64_t)gm * p.ldc + gn0;
@@ -227,6 +264,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             }
             tc_fence_before();
             mbar_arrive(&sm->acc_empty[buf]);
+            ++tcount;
         }
     }
 
@@ -321,6 +359,7 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
     p.aux = (const float*)a->aux; p.ldaux = a->ldaux;
     p.out_img = (uint8_t*)a->out_image; p.out_k_blocks = (a->n + tcg::KB - 1) / tcg::KB;
     p.kranges = a->k_block_ranges;
+    p.row_ranges = a->row_ranges;
     p.tiles_m = (a->m + tcg::BM - 1) / tcg::BM; p.tiles_n = (a->n + tcg::BN - 1) / tcg::BN;
     p.error = a->error_flag;
     int splits = a->split_k > 1 ? a->split_k : 1;

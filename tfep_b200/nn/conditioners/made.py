@@ -176,8 +176,8 @@ class MADE(_conditioner.Conditioner):
         if precision == 'bf16':
             if x.dtype != torch.float32:
                 raise _ops._lib.TfepB200Error("precision='bf16' takes float32 inputs")
-            kb_fwd, kb_bwd = plan.tc_ranges(x.device)
-            return _ops.made_forward_tc(x, pw, pb, kb_fwd, kb_bwd)
+            kb_fwd, kb_bwd, rr_w = plan.tc_ranges(x.device)
+            return _ops.made_forward_tc(x, pw, pb, kb_fwd, kb_bwd, rr_w)
         k_ranges, n_ranges, _ = plan.tables(x.device)
         return _ops.made_forward(x, pw, pb, k_ranges, n_ranges)
 
