@@ -29,8 +29,10 @@ using namespace tc;
 
 constexpr int BM = 128, BN = 256, KB = 64;
 constexpr int A_BLOCK = BM * KB * 2, B_BLOCK = BN * KB * 2, STAGE_BYTES = A_BLOCK + B_BLOCK;   // 16 + 32 KB
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
 constexpr int EPI_WARPS = 8;
+constexpr int XP_LD = 33;                                  // transposition buffer: [64 columns][33] floats per epilogue warp
+constexpr int XP_FLOATS = 64 * XP_LD;
 constexpr int THREADS = 64 + EPI_WARPS * 32;
 
 struct Params {
@@ -67,7 +69,8 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* ring = smem_raw;
-    Smem* sm = reinterpret_cast<Smem*>(ring + (size_t)STAGES * STAGE_BYTES);
+    float* xpose = reinterpret_cast<float*>(ring + (size_t)STAGES * STAGE_BYTES);
+    Smem* sm = reinterpret_cast<Smem*>(xpose + EPI_WARPS * XP_FLOATS);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_tiles = p.tiles_m * p.tiles_n;
 
@@ -172,96 +175,118 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             const uint32_t buf = tcount & 1;
             mbar_wait(&sm->acc_full[buf], (tcount >> 1) & 1, p.error, 4);
             tc_fence_after();
-            const int gm = tm * BM + row;
+            // Every warp owns 32 rows (its TMEM lane quadrant) x 128 columns, processed as two sub-tiles of 64 columns
+            // that go through a per-warp transposition buffer: a thread holds one ROW of the accumulator, but global
+            // memory wants a warp instruction to cover one row segment (128 contiguous bytes), both for the ELU'
+            // operand coming in and for the fp32 result going out.
+            float* xp = xpose + ew * XP_FLOATS;
+            const int gm0 = tm * BM + (warp & 3) * 32;         // first row of this warp
+            const int gm = gm0 + lane;
             const bool row_ok = gm < p.M;
-            const bool empty = k1 <= k0;               // nothing was accumulated: the tile is all zeros
+            const bool empty = k1 <= k0;                       // nothing was accumulated: the tile is all zeros
 #pragma unroll 1
-            for (int c16 = 0; c16 < 8; ++c16) {
-                const int col0 = half * 128 + c16 * 16;
-                const int gn0 = tn * BN + col0;
-                uint32_t r[16];
-                if (!empty) {
-                    tmem_ld16(lane_addr + buf * BN + col0, r);
-                    tmem_wait8(r); tmem_wait8(r + 8);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) r[i] = 0u;
+            for (int sub = 0; sub < 2; ++sub) {
+                const int scol = half * 128 + sub * 64;        // first column of the sub-tile inside the tile
+                const int gns = tn * BN + scol;
+                if (gns >= p.N && p.out_img == nullptr) continue;      // warp-uniform
+                if (p.aux != nullptr && !p.atomic) {
+                    // coalesced load of the 32 x 64 ELU' operand: lane = column, transposed into the buffer
+#pragma unroll 4
+                    for (int r = 0; r < 32; ++r) {
+                        const int grow = gm0 + r;
+                        const float* hrow = p.aux + (int64_t)grow * p.ldaux + gns;
+                        const bool rk = grow < p.M;
+                        xp[lane * XP_LD + r] = (rk && gns + lane < p.N) ? __ldg(hrow + lane) : 0.f;
+                        xp[(lane + 32) * XP_LD + r] = (rk && gns + lane + 32 < p.N) ? __ldg(hrow + lane + 32) : 0.f;
+                    }
+                    __syncwarp();
                 }
-                float v[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-                if (!p.atomic) {
-                    const bool full = gn0 + 15 < p.N;
-                    if (p.bias != nullptr) {
-                        if (full && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gn0) + i);
-                                v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (gn0 + i < p.N) v[i] += __ldg(p.bias + gn0 + i);
-                        }
-                    }
-                    if (p.act == TFEPB_ACT_ELU) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], ex2(fminf(v[i], 0.f) * LOG2E) - 1.f);
-                    }
-                    if (p.aux != nullptr && row_ok) {
-                        const float* hrow = p.aux + (int64_t)gm * p.ldaux + gn0;
-                        if (full && (p.ldaux & 3) == 0 && (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float4 h4 = __ldg(reinterpret_cast<const float4*>(hrow) + i);
-                                v[4 * i] *= fminf(h4.x, 0.f) + 1.f; v[4 * i + 1] *= fminf(h4.y, 0.f) + 1.f;
-                                v[4 * i + 2] *= fminf(h4.z, 0.f) + 1.f; v[4 * i + 3] *= fminf(h4.w, 0.f) + 1.f;
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (gn0 + i < p.N) v[i] *= fminf(__ldg(hrow + i), 0.f) + 1.f;
-                        }
-                    }
-                    if (!full) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (gn0 + i >= p.N) v[i] = 0.f;
-                    }
-                }
-                if (p.C != nullptr && row_ok) {
-                    float* c = p.C + (int64_t)gm * p.ldc + gn0;
-                    if (p.atomic) {
-                        if (!empty) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (gn0 + i < p.N) atomicAdd(c + i, v[i]);
-                        }
-                    } else if (gn0 + 15 < p.N && (p.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0)) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            reinterpret_cast<float4*>(c)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+#pragma unroll 1
+                for (int c16 = 0; c16 < 4; ++c16) {
+                    const int col0 = scol + c16 * 16;
+                    const int gn0 = tn * BN + col0;
+                    uint32_t r[16];
+                    if (!empty) {
+                        tmem_ld16(lane_addr + buf * BN + col0, r);
+                        tmem_wait8(r); tmem_wait8(r + 8);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (gn0 + i < p.N) c[i] = v[i];
+                        for (int i = 0; i < 16; ++i) r[i] = 0u;
+                    }
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+                    if (!p.atomic) {
+                        const bool full = gn0 + 15 < p.N;
+                        if (p.bias != nullptr) {
+                            if (full && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gn0) + i);
+                                    v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    if (gn0 + i < p.N) v[i] += __ldg(p.bias + gn0 + i);
+                            }
+                        }
+                        if (p.act == TFEPB_ACT_ELU) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], ex2(fminf(v[i], 0.f) * LOG2E) - 1.f);
+                        }
+                        if (p.aux != nullptr) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] *= fminf(xp[(c16 * 16 + i) * XP_LD + lane], 0.f) + 1.f;
+                        }
+                        if (!full) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (gn0 + i >= p.N) v[i] = 0.f;
+                        }
+                    }
+                    if (p.C != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) xp[(c16 * 16 + i) * XP_LD + lane] = v[i];
+                    }
+                    if (p.out_img != nullptr) {
+                        // columns are the reduction index of the next product: k-block = gn / 64, slab = (gn % 64) / 8;
+                        // consecutive rows are consecutive 16-byte chunks of a slab (coalesced as is)
+                        const int kblk = gn0 >> 6;
+                        if (kblk < p.out_k_blocks) {
+                            uint8_t* blk = p.out_img + ((size_t)tm * p.out_k_blocks + kblk) * A_BLOCK + (size_t)row * 16;
+                            const int slab = (gn0 & 63) >> 3;
+                            uint4 q0, q1;
+                            q0.x = pack_bf16(v[0], v[1]); q0.y = pack_bf16(v[2], v[3]); q0.z = pack_bf16(v[4], v[5]); q0.w = pack_bf16(v[6], v[7]);
+                            q1.x = pack_bf16(v[8], v[9]); q1.y = pack_bf16(v[10], v[11]); q1.z = pack_bf16(v[12], v[13]); q1.w = pack_bf16(v[14], v[15]);
+                            *reinterpret_cast<uint4*>(blk + (size_t)slab * 2048) = q0;
+                            *reinterpret_cast<uint4*>(blk + (size_t)(slab + 1) * 2048) = q1;
+                        }
                     }
                 }
-                if (p.out_img != nullptr) {
-                    // columns are the reduction index of the next product: k-block = gn / 64, slab = (gn % 64) / 8
-                    const int kblk = gn0 >> 6;
-                    if (kblk < p.out_k_blocks) {
-                        uint8_t* blk = p.out_img + ((size_t)tm * p.out_k_blocks + kblk) * A_BLOCK + (size_t)row * 16;
-                        const int slab = (gn0 & 63) >> 3;
-                        uint4 q0, q1;
-                        q0.x = pack_bf16(v[0], v[1]); q0.y = pack_bf16(v[2], v[3]); q0.z = pack_bf16(v[4], v[5]); q0.w = pack_bf16(v[6], v[7]);
-                        q1.x = pack_bf16(v[8], v[9]); q1.y = pack_bf16(v[10], v[11]); q1.z = pack_bf16(v[12], v[13]); q1.w = pack_bf16(v[14], v[15]);
-                        *reinterpret_cast<uint4*>(blk + (size_t)slab * 2048) = q0;
-                        *reinterpret_cast<uint4*>(blk + (size_t)(slab + 1) * 2048) = q1;
+                if (p.C != nullptr) {
+                    __syncwarp();
+                    const bool c0 = gns + lane < p.N, c1 = gns + lane + 32 < p.N;
+                    if (!(p.atomic && empty)) {
+#pragma unroll 4
+                        for (int r = 0; r < 32; ++r) {
+                            const int grow = gm0 + r;
+                            if (grow >= p.M) break;                    // warp-uniform
+                            float* crow = p.C + (int64_t)grow * p.ldc + gns;
+                            const float a0 = xp[lane * XP_LD + r], a1 = xp[(lane + 32) * XP_LD + r];
+                            if (p.atomic) {
+                                if (c0) atomicAdd(crow + lane, a0);
+                                if (c1) atomicAdd(crow + lane + 32, a1);
+                            } else {
+                                if (c0) crow[lane] = a0;
+                                if (c1) crow[lane + 32] = a1;
+                            }
+                        }
                     }
+                    __syncwarp();
                 }
             }
+            (void)row_ok;
             tc_fence_before();
             mbar_arrive(&sm->acc_empty[buf]);
             ++tcount;
@@ -367,7 +392,7 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
     p.atomic = splits > 1 ? 1 : 0;
     p.k_chunk_blocks = splits > 1 ? (p.k_blocks + splits - 1) / splits : 0;
     if (splits > 1) splits = (p.k_blocks + p.k_chunk_blocks - 1) / p.k_chunk_blocks;
-    const size_t smem = (size_t)tcg::STAGES * tcg::STAGE_BYTES + sizeof(tcg::Smem) + 1024;
+    const size_t smem = (size_t)tcg::STAGES * tcg::STAGE_BYTES + (size_t)tcg::EPI_WARPS * tcg::XP_FLOATS * 4 + sizeof(tcg::Smem) + 1024;
     static thread_local bool configured = false;
     if (!configured) {
         TFEPB_CUDA(cudaFuncSetAttribute(tcg::tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
