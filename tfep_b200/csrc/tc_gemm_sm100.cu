@@ -30,9 +30,9 @@ using namespace tc;
 constexpr int BM = 128, BN = 256, KB = 64;
 constexpr int A_BLOCK = BM * KB * 2, B_BLOCK = BN * KB * 2, STAGE_BYTES = A_BLOCK + B_BLOCK;   // 16 + 32 KB
 constexpr int STAGES = 3;
-constexpr int EPI_WARPS = 8;
-constexpr int XP_LD = 33;                                  // transposition buffer: [64 columns][33] floats per epilogue warp
-constexpr int XP_FLOATS = 64 * XP_LD;
+constexpr int EPI_WARPS = 16;
+constexpr int XP_LD = 33;                                  // transposition buffer: [32 columns][33] floats per epilogue warp
+constexpr int XP_FLOATS = 32 * XP_LD;
 constexpr int THREADS = 64 + EPI_WARPS * 32;
 
 struct Params {
@@ -161,9 +161,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             ++tcount;
         }
     } else {
-        // =========================== epilogue: 8 warps, two column halves x four lane quadrants ===========================
+        // =========================== epilogue: 16 warps, four column groups x four lane quadrants ===========================
         const int ew = warp - 2;
-        const int half = ew >> 2;                      // columns [half * 128, half * 128 + 128) of the tile
+        const int cgroup = ew >> 2;                    // columns [cgroup * 64, cgroup * 64 + 64) of the tile
         const int row = (warp & 3) * 32 + lane;        // TMEM lane = row of the tile
         const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t tcount = 0;
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             const uint32_t buf = tcount & 1;
             mbar_wait(&sm->acc_full[buf], (tcount >> 1) & 1, p.error, 4);
             tc_fence_after();
-            // Every warp owns 32 rows (its TMEM lane quadrant) x 128 columns, processed as two sub-tiles of 64 columns
+            // Every warp owns 32 rows (its TMEM lane quadrant) x 64 columns, processed as two sub-tiles of 32 columns
             // that go through a per-warp transposition buffer: a thread holds one ROW of the accumulator, but global
             // memory wants a warp instruction to cover one row segment (128 contiguous bytes), both for the ELU'
             // operand coming in and for the fp32 result going out.
@@ -186,23 +186,20 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             const bool empty = k1 <= k0;                       // nothing was accumulated: the tile is all zeros
 #pragma unroll 1
             for (int sub = 0; sub < 2; ++sub) {
-                const int scol = half * 128 + sub * 64;        // first column of the sub-tile inside the tile
+                const int scol = cgroup * 64 + sub * 32;       // first column of the sub-tile inside the tile
                 const int gns = tn * BN + scol;
                 if (gns >= p.N && p.out_img == nullptr) continue;      // warp-uniform
                 if (p.aux != nullptr && !p.atomic) {
-                    // coalesced load of the 32 x 64 ELU' operand: lane = column, transposed into the buffer
-#pragma unroll 4
+                    // coalesced load of the 32 x 32 ELU' operand: lane = column, transposed into the buffer
+#pragma unroll 8
                     for (int r = 0; r < 32; ++r) {
                         const int grow = gm0 + r;
-                        const float* hrow = p.aux + (int64_t)grow * p.ldaux + gns;
-                        const bool rk = grow < p.M;
-                        xp[lane * XP_LD + r] = (rk && gns + lane < p.N) ? __ldg(hrow + lane) : 0.f;
-                        xp[(lane + 32) * XP_LD + r] = (rk && gns + lane + 32 < p.N) ? __ldg(hrow + lane + 32) : 0.f;
+                        xp[lane * XP_LD + r] = (grow < p.M && gns + lane < p.N) ? __ldg(p.aux + (int64_t)grow * p.ldaux + gns + lane) : 0.f;
                     }
                     __syncwarp();
                 }
 #pragma unroll 1
-                for (int c16 = 0; c16 < 4; ++c16) {
+                for (int c16 = 0; c16 < 2; ++c16) {
                     const int col0 = scol + c16 * 16;
                     const int gn0 = tn * BN + col0;
                     uint32_t r[16];
@@ -266,21 +263,16 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                 }
                 if (p.C != nullptr) {
                     __syncwarp();
-                    const bool c0 = gns + lane < p.N, c1 = gns + lane + 32 < p.N;
-                    if (!(p.atomic && empty)) {
+                    const bool c0 = gns + lane < p.N;
+                    if (c0 && !(p.atomic && empty)) {
+                        const int nrows = min(32, p.M - gm0);
+                        float* cptr = p.C + (int64_t)gm0 * p.ldc + gns + lane;
+                        if (p.atomic) {
 #pragma unroll 4
-                        for (int r = 0; r < 32; ++r) {
-                            const int grow = gm0 + r;
-                            if (grow >= p.M) break;                    // warp-uniform
-                            float* crow = p.C + (int64_t)grow * p.ldc + gns;
-                            const float a0 = xp[lane * XP_LD + r], a1 = xp[(lane + 32) * XP_LD + r];
-                            if (p.atomic) {
-                                if (c0) atomicAdd(crow + lane, a0);
-                                if (c1) atomicAdd(crow + lane + 32, a1);
-                            } else {
-                                if (c0) crow[lane] = a0;
-                                if (c1) crow[lane + 32] = a1;
-                            }
+                            for (int r = 0; r < nrows; ++r) atomicAdd(cptr + (int64_t)r * p.ldc, xp[lane * XP_LD + r]);
+                        } else {
+#pragma unroll 8
+                            for (int r = 0; r < nrows; ++r) cptr[(int64_t)r * p.ldc] = xp[lane * XP_LD + r];
                         }
                     }
                     __syncwarp();
