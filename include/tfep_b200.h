@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TFEPB_ABI_VERSION 2
+#define TFEPB_ABI_VERSION 3
 
 enum { TFEPB_F32 = 0, TFEPB_F64 = 1 };
 enum { TFEPB_ACT_NONE = 0, TFEPB_ACT_ELU = 1 };
@@ -267,6 +267,12 @@ typedef struct {
     const tfepb_fused_feature* feats;    /* device: n_chunks * 4 */
     float min_bin_size, min_slope, slope_offset;   /* slope_offset = log(exp(1 - min_slope) - 1) */
     int32_t reserved;
+    const int32_t* input_map;            /* device, k1 entries, or NULL (conditioner input k = x column k, then the two
+                                            constant ones).  Entry k: bits 0-15 the x column, bits 16-18 what enters the
+                                            conditioner: 0 x, 1 cos(a), 2 sin(a) with a = (x - emb_lower) * emb_scale
+                                            (PeriodicEmbedding fused into the operand staging, reference
+                                            nn/embeddings/mafembed.py:112-142), 3 the constant one, 4 zero */
+    float emb_lower, emb_scale;          /* emb_scale = 2 pi / (upper - lower) */
 } tfepb_fused_layer;
 
 typedef struct {
@@ -287,7 +293,8 @@ typedef struct {
     uint32_t epoch;                                /* any value the words do not hold yet (e.g. a call counter) */
     int32_t debug_mode;                            /* development only, 0 */
     int32_t mixed_splines;                         /* 1 if any feature has kind != 0 (selects the generic spline epilogue) */
-    int32_t reserved2;
+    int32_t n_inputs;                              /* conditioner inputs before the two constant ones (n_features plus one
+                                                      per lifted periodic feature); 0 = n_features.  k1 >= n_inputs + 2 */
     int32_t* error_flag;                           /* device int, set if an internal wait times out; may be NULL */
     float* debug_params;                           /* NULL, or (batch, n_chunks * 112): conditioner outputs (+bias)
                                                       of layer 0 in packed order, for parity tests of the GEMM chain */
@@ -307,8 +314,11 @@ int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_stream_t stre
 typedef struct {
     int32_t col;                         /* column of the feature of this degree in y / x */
     float x0, period, inv_period, rescaled_width, rescaled_height, y0;
-    int32_t partner;                     /* bits 0-3: other half of the bf16 pair column of x: 0 not known yet, 1 known,
-                                            2 constant one; bit 4: spline kind (0 circular, 1 not circular) */
+    int32_t partner;                     /* bits 0-3: other half of the bf16 pair column of the conditioner input: 0 not
+                                            known yet, 1 known, 2 constant one; bit 4: spline kind (0 circular, 1 not
+                                            circular); bit 5: the feature enters the conditioner as (cos, sin) in the
+                                            input columns (c, c + 1), c even (PeriodicEmbedding); bits 8-15: input
+                                            column c of the feature; bits 16-23: x column of the pair partner */
     int32_t h1_first, h1_count, h2_first, h2_count;   /* packed hidden units computable after the feature (<= 15) */
 } tfepb_fused_inv_step;
 
@@ -319,6 +329,7 @@ typedef struct {
     const void* weights;                 /* device, packed bf16 blocks */
     float min_bin_size, min_slope, slope_offset;
     int32_t reserved;
+    float emb_lower, emb_scale;          /* as in tfepb_fused_layer (used by steps with bit 5 set) */
 } tfepb_fused_inv_layer;
 
 typedef struct {
@@ -330,7 +341,7 @@ typedef struct {
     const tfepb_fused_inv_layer* layers;           /* HOST array of n_layers entries */
     uint32_t* tile_flags;                          /* as for the forward kernel */
     uint32_t epoch;
-    int32_t reserved2;
+    int32_t n_inputs;                              /* as in tfepb_fused_args; 0 = n_features */
     int32_t* error_flag;
 } tfepb_fused_inv_args;
 int tfepb_maf_spline_inverse_bf16(const tfepb_fused_inv_args* a, tfepb_stream_t stream);

@@ -198,8 +198,9 @@ def cfg_flow(name, dtype=torch.float32, n_layers=None, D=None):
         D, L = D or 66, n_layers or 4
         mk = lambda: fo.Spline(x0=torch.full((D,), -math.pi, dtype=dtype), xf=torch.full((D,), math.pi, dtype=dtype),
                                n_bins=8, circular=True)
-    elif name == 'cfg2mix':      # cfg2's "dihedral / Cartesian mix": circular splines on the torsions f % 3 == 2,
-        D, L = D or 66, n_layers or 4            # ordinary splines on [-4, 4] for the other features
+    elif name in ('cfg2mix', 'cfg2mixemb'):      # cfg2's "dihedral / Cartesian mix": circular splines on the torsions
+        D, L = D or 66, n_layers or 4            # f % 3 == 2, ordinary splines on [-4, 4] for the others;
+                                                 # 'emb': torsions enter the conditioner as (cos, sin), app/mixedmaf.py:341-353
         tors = [f for f in range(D) if f % 3 == 2]
         cart = [f for f in range(D) if f % 3 != 2]
         mk = lambda: fo.Mixed([fo.Spline(x0=torch.full((len(tors),), -math.pi, dtype=dtype),
@@ -224,7 +225,10 @@ def cfg_flow(name, dtype=torch.float32, n_layers=None, D=None):
                 spec, deg = fo.Moebius(dimension=3), fo.gen_degrees(D, order=order, repeats=3)
         else:
             spec, deg = mk(), fo.gen_degrees(D, order=order)
-        m = fo.MafOracle(deg, spec)
+        emb = None
+        if name == 'cfg2mixemb':
+            emb = fo.PeriodicEmbed(D, torch.tensor([-math.pi, math.pi], dtype=dtype), [f for f in range(D) if f % 3 == 2])
+        m = fo.MafOracle(deg, spec, embedding=emb)
         sd = seeded_state([k.to(dtype) for k in m.masks], 1234 + l, dtype)
         flows.append((m.load(sd), sd))
     return flows
@@ -233,7 +237,7 @@ def cfg_flow(name, dtype=torch.float32, n_layers=None, D=None):
 def cfg_input(name, batch, dtype=torch.float32, D=None):
     if name == 'cfg2':
         return uniform((batch, D or 66), 0, -math.pi, math.pi, dtype) * 0.999
-    if name == 'cfg2mix':        # torsions uniform in (-pi, pi), Cartesians normal with a few samples in the spline tails
+    if name in ('cfg2mix', 'cfg2mixemb'):        # torsions uniform in (-pi, pi), Cartesians normal with a few samples in the spline tails
         D = D or 66
         x = normal((batch, D), 0, dtype) * 1.6
         tors = [f for f in range(D) if f % 3 == 2]

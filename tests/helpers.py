@@ -62,7 +62,7 @@ def cfg_flow_modules(name, device, n_layers=None, D=None, dtype=torch.float32):
     flows = cases.cfg_flow(name, torch.float32, n_layers=n_layers, D=D)
     mafs = []
     for m, sd in flows:
-        case = dict(degrees_in=m.degrees_in, spec=m.transformer, hidden_layers=2, weight_norm=True)
+        case = dict(degrees_in=m.degrees_in, spec=m.transformer, hidden_layers=2, weight_norm=True, embedding=m.embedding)
         mafs.append(to_maf(case, {k: v.to(dtype) for k, v in sd.items()}, dtype=dtype))
     return SequentialFlow(*mafs).to(device), flows
 

@@ -181,19 +181,23 @@ def test_long_chain_is_split_into_launches():
     assert float(d.median()) < 1e-4 and float((ld + ldi).abs().median()) < 5e-4
 
 
-@pytest.mark.parametrize('cfg', ['cfg2mix', 'cfg5'])
-def test_mixed_and_non_circular_splines(cfg):
+@pytest.mark.parametrize('cfg,D', [('cfg2mix', 66), ('cfg5', 66), ('cfg2mixemb', 48)])
+def test_mixed_and_non_circular_splines(cfg, D):
     """The generic spline epilogue of the fused kernels: a MixedTransformer of circular (torsions) and ordinary
-    splines with linear tails (Cartesians) -- BASELINE.json's "dihedral / Cartesian mix" -- and a purely
-    non-circular flow (cfg5's transformer at D = 66).  Forward against the exact fp32 path (stated bf16 tolerance),
+    splines with linear tails (Cartesians) -- BASELINE.json's "dihedral / Cartesian mix" -- a purely
+    non-circular flow (cfg5's transformer at D = 66), and the mix with a PeriodicEmbedding in front of the
+    conditioner (what the reference's MixedMAFMap runs, app/mixedmaf.py:341-353: the (cos, sin) lift is fused into
+    the operand staging of both kernels).  Forward against the exact fp32 path (stated bf16 tolerance),
     inverse as a round trip, chain launch equal to layer-by-layer launches."""
-    seq, flows = cfg_flow_modules(cfg, DEV, n_layers=3, D=66)
-    x = cases.cfg_input(cfg, 1500, D=66).to(DEV)
+    seq, flows = cfg_flow_modules(cfg, DEV, n_layers=3, D=D)
+    x = cases.cfg_input(cfg, 1500, D=D).to(DEV)
     if cfg == 'cfg5':
         x = x * 2.5                                   # a good share of the samples in the tails beyond +-5
-    period = torch.full((66,), float('inf'))
-    if cfg == 'cfg2mix':
-        period[[f for f in range(66) if f % 3 == 2]] = 2 * math.pi
+    period = torch.full((D,), float('inf'))
+    if cfg != 'cfg5':
+        period[[f for f in range(D) if f % 3 == 2]] = 2 * math.pi
+    if cfg == 'cfg2mixemb':
+        assert all(m._embedding is not None for m in seq)
 
     def dist(a, b):
         d = (a.double().cpu() - b.double().cpu()).abs()
@@ -222,6 +226,53 @@ def test_mixed_and_non_circular_splines(cfg):
         assert float(dc.median()) < 1e-4 and float((ldc + ldci).abs().median()) < 2e-4
     if cfg == 'cfg5':
         assert float((x.abs() > 5).float().mean()) > 0.01          # the tails were exercised
+
+
+@pytest.mark.parametrize('cfg,D', [('cfg2mixemb', 46), ('cfg2mixemb', 33), ('cfg2mix', 12), ('cfg2mix', 3)])
+def test_narrow_and_odd_widths(cfg, D):
+    """Odd numbers of conditioner inputs (the constant-one columns then straddle two bf16 pair columns), lifted
+    (cos, sin) pairs next to plain features, and layers too narrow for the two-half hand-over of the hidden
+    layers (one half, one output chunk): forward against the exact path, inverse as a round trip."""
+    seq, _ = cfg_flow_modules(cfg, DEV, n_layers=2, D=D)
+    x = cases.cfg_input(cfg, 700, D=D).to(DEV)
+    period = torch.full((D,), float('inf'))
+    period[[f for f in range(D) if f % 3 == 2]] = 2 * math.pi
+
+    def dist(a, b):
+        d = (a.double().cpu() - b.double().cpu()).abs()
+        return torch.minimum(d, (period - d).abs())
+
+    with torch.no_grad():
+        for maf in seq:
+            y32, ld32 = maf(x)
+            maf.precision = 'bf16'
+            assert maf._fused_plan() is not None, maf._fused_why
+            y, ld = maf(x)
+            xi, ldi = maf.inverse(y)
+            assert float(dist(y, y32).max()) < 5e-2 and float(dist(y, y32).mean()) < 2e-3
+            assert float((ld - ld32).abs().mean()) < 8e-3
+            d = dist(xi, x).max(dim=1).values
+            assert float(d.median()) < 2e-5 and float((ld + ldi).abs().median()) < 5e-5
+
+
+def test_layers_beyond_the_tensor_memory_plan_use_the_general_gemm():
+    """D = 66 with 22 lifted torsions asks for hidden layers of 381 units: more than the tensor-memory plan of the
+    one-launch kernel holds.  precision='bf16' then runs the conditioner on the general tensor-core GEMM (and the
+    inverse on the exact sweep) instead of failing."""
+    seq, _ = cfg_flow_modules('cfg2mixemb', DEV, n_layers=1, D=66)
+    maf = seq[0]
+    x = cases.cfg_input('cfg2mixemb', 300, D=66).to(DEV)
+    with torch.no_grad():
+        y32, ld32 = maf(x)
+        maf.precision = 'bf16'
+        assert maf._fused_plan() is None and 'tensor-memory plan' in maf._fused_why
+        y, ld = maf(x)
+        xi, ldi = maf.inverse(y)
+    assert float((ld - ld32).abs().mean()) < 8e-3
+    # forward with bf16 operands, inverse exact: the round trip closes to the stated bf16 tolerance
+    d = (xi - x).abs()
+    d = torch.minimum(d, (2 * math.pi - d).abs())
+    assert float(d.max()) < 5e-2 and float(d.mean()) < 2e-3
 
 
 def test_bf16_outside_the_fused_kernel_uses_the_tensor_core_gemm():

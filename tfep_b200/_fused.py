@@ -84,8 +84,11 @@ def eligibility(maf):
     parts = _spline_parts(maf)
     if isinstance(parts, str):
         return parts
-    if maf._embedding is not None or maf._n_conditioner_indices > 0:
-        return 'embeddings / conditioner_indices are not fused'
+    from .nn.embeddings import PeriodicEmbedding
+    if maf._embedding is not None and type(maf._embedding) is not PeriodicEmbedding:
+        return 'only PeriodicEmbedding is fused into the operand staging'
+    if maf._n_conditioner_indices > 0:
+        return 'conditioner_indices are not fused'
     if len(maf._conditioner._linear_layers()) != 3:
         return 'the fused kernel is built for two hidden layers'
     if int(maf._degrees_in_host.min()) < 0:
@@ -106,7 +109,32 @@ class FusedSplinePlan:
         parts = pk['parts']
         t = parts[0].spec                             # min_bin_size / min_slope are common to all parts
         self.D = len(maf._degrees_in_host)
-        self.K1 = _ceil16(self.D + 2)                 # + two constant-one columns carrying the bias
+        # Conditioner input columns as the kernels lay them out: the (cos, sin) pairs of the features a
+        # PeriodicEmbedding lifts (reference nn/embeddings/mafembed.py:112-142) first, on even columns, then the
+        # plain features, then the two constant ones.  Without embedding: input column k = x column k.
+        emb = maf._embedding
+        per = [] if emb is None else emb._periodic_indices.tolist()
+        nonper = list(range(self.D)) if emb is None else emb._nonperiodic_indices.tolist()
+        self.Din = self.D + len(per)
+        self.input_of_x = {c: 2 * j for j, c in enumerate(per)}
+        self.input_of_x.update({c: 2 * len(per) + i for i, c in enumerate(nonper)})
+        self.lifted = set(per)
+        # reference order of the embedded features (plain ones first, then the pairs) -> kernel input column
+        self.input_cols = torch.tensor([self.input_of_x[c] for c in nonper] +
+                                       [self.input_of_x[c] + s for c in per for s in (0, 1)], dtype=torch.long)
+        self.K1 = _ceil16(self.Din + 2)               # + two constant-one columns carrying the bias
+        if emb is None:
+            self.input_map_host, self.emb_lower, self.emb_scale = None, 0.0, 0.0
+        else:
+            imap = np.full(self.K1, 4 << 16, dtype=np.int32)
+            for c in range(self.D):
+                k = self.input_of_x[c]
+                if c in self.lifted:
+                    imap[k], imap[k + 1] = c | (1 << 16), c | (2 << 16)
+                else:
+                    imap[k] = c
+            imap[self.Din] = imap[self.Din + 1] = 3 << 16
+            self.input_map_host, self.emb_lower, self.emb_scale = imap, emb._lower, emb._scale
         deg_h1, deg_h2 = plan.packed_degrees[1], plan.packed_degrees[2]
         H1, H2 = len(deg_h1), len(deg_h2)
         if H1 != H2:
@@ -135,7 +163,6 @@ class FusedSplinePlan:
         else:
             self.hidden_chunks1 = self.hidden_chunks2 = [(0, self.HP)]
         self.hidden_split = (self.hidden_chunks1[0][1], self.hidden_chunks2[0][1])
-        assert all((b - a) * self.K1 * 2 <= STAGE_BYTES for a, b in self.hidden_chunks1)
 
         # features of all spline parts (a MixedTransformer contributes one part per child), sorted by degree ->
         # chunks of 4 slots; a feature is (x column, degree, spline module, local index, 25 reference output rows)
@@ -180,6 +207,15 @@ class FusedSplinePlan:
         self.w3_rows = w3_rows
         self.w3_scale = scale
         assert self.n_chunks * CHUNK_N == len(w3_rows)
+
+        # the first output chunk must live on the first half of h2 (see GEMM3 below); narrow layers are not split
+        if self.halves == 2 and (_ceil16(2 + int((deg_h2 < chunk_maxdeg[0]).sum())) > self.hidden_split[1] or
+                                 CHUNK_N > self.hidden_split[1] or self.n_chunks < 2):
+            self.halves = 1
+            self.hidden_chunks1 = self.hidden_chunks2 = [(0, self.HP)]
+            self.hidden_split = (self.HP, self.HP)
+        if any((b - a) * self.K1 * 2 > STAGE_BYTES for a, b in self.hidden_chunks1):
+            raise _lib.TfepB200Error('fused bf16 path: first-layer weight block exceeds a ring stage')
 
         # ---- schedule ----
         ops, gather = [], []           # gather: per op, index tensor into the concatenated padded matrices
@@ -248,7 +284,8 @@ class FusedSplinePlan:
         key = str(device)
         if key not in self._dev:
             feats = torch.from_numpy(self.feats_host.view(np.uint8).copy()).to(device)
-            self._dev[key] = dict(feats=feats, gather=self.gather_host.to(device),
+            imap = None if self.input_map_host is None else torch.from_numpy(self.input_map_host).to(device)
+            self._dev[key] = dict(feats=feats, gather=self.gather_host.to(device), input_map=imap, input_cols=self.input_cols.to(device),
                                   w3_rows=self.w3_rows.to(device), w3_scale=self.w3_scale.to(device),
                                   perm1=self.perm1.to(device),
                                   perm2=self.perm2.to(device), err=torch.zeros(1, dtype=torch.int32, device=device))
@@ -264,7 +301,7 @@ class FusedSplinePlan:
             (w1, b1), (w2, b2), (w3, b3) = made.effective_weights()
             dev = w1.device
             tb = self._tables(dev)
-            H, HP, K1, D = self.H, self.HP, self.K1, self.D
+            H, HP, K1, D = self.H, self.HP, self.K1, self.Din      # D: conditioner inputs (lifted pairs included)
 
             def hi_lo(b):
                 hi = b.to(torch.bfloat16).float()
@@ -275,7 +312,7 @@ class FusedSplinePlan:
             # layer 2 sees a' and is scaled by log2(e) itself -> weights unchanged, bias scaled; the output rows
             # see a' -> divide by log2(e), then the log2-domain rows are multiplied by it again.
             W1p = torch.zeros(HP, K1, device=dev)
-            W1p[2:2 + H, :D] = w1.index_select(0, tb['perm1']) * LOG2E
+            W1p[2:2 + H, tb['input_cols']] = w1.index_select(0, tb['perm1']) * LOG2E
             W1p[2:2 + H, D], W1p[2:2 + H, D + 1] = hi_lo(b1.index_select(0, tb['perm1']) * LOG2E)
             W1p[0, D] = W1p[1, D] = 1.0                   # hidden units 0, 1: t = 1 > 0 -> a' = 1 (constant ones)
             W2p = torch.zeros(HP, HP, device=dev)
@@ -298,10 +335,11 @@ class FusedSplinePlan:
     # ---------------------------------------------------------------------------------------------
     # inverse direction (tfepb_maf_spline_inverse_bf16): one block per product of the degree sweep
     # ---------------------------------------------------------------------------------------------
-    def inverse_eligibility(self):
-        if self._inv is False:
-            return self._inv_why
-        return None
+    def inverse_eligibility(self, maf):
+        """None if the tensor-core inverse sweep covers this layer, else the reason it does not."""
+        if self._inv is None:
+            self._build_inverse(maf)
+        return self._inv_why if self._inv is False else None
 
     def _build_inverse(self, maf):
         """Schedule, step table and gather indices of the degree-ordered sweep (host integer work, once)."""
@@ -361,8 +399,15 @@ class FusedSplinePlan:
                 kmax2 = _ceil16(2 + int((deg_h1 <= d).sum()))
                 add(list(range(h2[0], h2[0] + h2[1])), 16, kmax2, INV_A1_COL, INV_ACC_HID, off1, self.HP)
             col = cols[f]
-            pc = col ^ 1
-            partner = 2 if pc == D else (0 if pc > D else (1 if int(deg_in[pc]) < d else 0))
+            ic = self.input_of_x[col]                      # conditioner input column of the feature
+            if col in self.lifted:
+                partner = 32 | (ic << 8)                   # (cos, sin) fill the pair column on their own
+            else:
+                x_of_input = {k: c for c, k in self.input_of_x.items() if c not in self.lifted}
+                pi = ic ^ 1
+                pc = x_of_input.get(pi, 0)
+                partner = 2 if pi == self.Din else (1 if (pi in x_of_input and int(deg_in[pc]) < d) else 0)
+                partner |= (ic << 8) | (pc << 16)
             partner |= 0 if self._feats_all[si]['circular'] else 16
             ft = self.feats_host[si]
             steps.append((col, ft['x0'], ft['period'], ft['inv_period'], ft['rw'], ft['rh'], ft['y0'], partner,
@@ -400,6 +445,15 @@ class FusedSplinePlan:
 _EPOCH = [0]
 
 
+def _chain_key(pl):
+    return (pl.D, pl.Din, pl.K1, pl.HP, pl.halves, pl.hidden_split)
+
+
+def chain_compatible(plans):
+    """One launch serves a chain of layers only if they share the widths and the hidden-layer split."""
+    return all(_chain_key(pl) == _chain_key(plans[0]) for pl in plans)
+
+
 LAYERS_PER_LAUNCH = 4          # the feature tables of all layers of a launch share the 227 KB of shared memory
 
 
@@ -418,7 +472,7 @@ def run_chain(plans_mafs, x, debug_params=None):
     first = plans_mafs[0][0]
     if n_layers > MAX_LAYERS or sum(len(pl.ops_host) for pl, _ in plans_mafs) > MAX_OPS:
         raise _lib.TfepB200Error('chain too long for one fused launch')
-    if any((pl.D, pl.K1, pl.HP, pl.halves, pl.hidden_split) != (first.D, first.K1, first.HP, first.halves, first.hidden_split) for pl, _ in plans_mafs):
+    if not chain_compatible([pl for pl, _ in plans_mafs]):
         raise _lib.TfepB200Error('fused chain needs layers of identical widths')
     x = x.contiguous()
     B = x.shape[0]
@@ -432,7 +486,9 @@ def run_chain(plans_mafs, x, debug_params=None):
         keep.append(packed)
         layers[i] = _lib.FusedLayer(ops=pl.ops_host.ctypes.data, n_ops=len(pl.ops_host), n_chunks=pl.n_chunks,
                                     weights=packed.data_ptr(), feats=tb['feats'].data_ptr(), min_bin_size=pl.min_bin,
-                                    min_slope=pl.min_slope, slope_offset=pl.slope_offset, reserved=0)
+                                    min_slope=pl.min_slope, slope_offset=pl.slope_offset, reserved=0,
+                                    input_map=None if tb['input_map'] is None else tb['input_map'].data_ptr(),
+                                    emb_lower=pl.emb_lower, emb_scale=pl.emb_scale)
     tb = first._tables(x.device)
     flags = None
     if n_layers > 1:
@@ -451,7 +507,7 @@ def run_chain(plans_mafs, x, debug_params=None):
                           hidden_split=(ctypes.c_int32 * 2)(*first.hidden_split), layers=layers,
                           tile_flags=None if flags is None else flags.data_ptr(), epoch=_EPOCH[0],
                           debug_mode=int(os.environ.get('TFEPB_FUSED_DEBUG_MODE', '0')),
-                          mixed_splines=int(any(pl.mixed for pl, _ in plans_mafs)), reserved2=0,
+                          mixed_splines=int(any(pl.mixed for pl, _ in plans_mafs)), n_inputs=first.Din,
                           error_flag=tb['err'].data_ptr(),
                           debug_params=None if debug_params is None else debug_params.data_ptr())
     with torch.cuda.device(x.device):
@@ -473,7 +529,7 @@ def run_inverse_chain(plans_mafs, y):
         raise _lib.TfepB200Error('the fused bf16 path takes float32 inputs')
     n_layers = len(plans_mafs)
     first = plans_mafs[0][0]
-    if any((pl.D, pl.K1, pl.HP) != (first.D, first.K1, first.HP) for pl, _ in plans_mafs):
+    if any((pl.D, pl.Din, pl.K1, pl.HP) != (first.D, first.Din, first.K1, first.HP) for pl, _ in plans_mafs):
         raise _lib.TfepB200Error('fused chain needs layers of identical widths')
     y = y.contiguous()
     B = y.shape[0]
@@ -486,7 +542,8 @@ def run_inverse_chain(plans_mafs, y):
         keep.append((ops, steps, packed))
         layers[i] = _lib.FusedInvLayer(ops=ops.data_ptr(), steps=steps.data_ptr(), n_ops=len(pl._inv['ops']),
                                        n_steps=len(pl._inv['steps']), weights=packed.data_ptr(), min_bin_size=pl.min_bin,
-                                       min_slope=pl.min_slope, slope_offset=pl.slope_offset, reserved=0)
+                                       min_slope=pl.min_slope, slope_offset=pl.slope_offset, reserved=0,
+                                       emb_lower=pl.emb_lower, emb_scale=pl.emb_scale)
     tb = first._tables(y.device)
     flags = None
     if n_layers > 1:
@@ -501,7 +558,7 @@ def run_inverse_chain(plans_mafs, y):
     args = _lib.FusedInvArgs(y=y.data_ptr(), x=x.data_ptr(), logdet=ld.data_ptr(), batch=B, n_features=first.D,
                              k1=first.K1, hidden_padded=first.HP, n_layers=n_layers,
                              reserved=int(any(pl.mixed for pl, _ in plans_mafs)), layers=layers,
-                             tile_flags=None if flags is None else flags.data_ptr(), epoch=_EPOCH[0], reserved2=0,
+                             tile_flags=None if flags is None else flags.data_ptr(), epoch=_EPOCH[0], n_inputs=first.Din,
                              error_flag=tb['err'].data_ptr())
     with torch.cuda.device(y.device):
         check(_lib.load().tfepb_maf_spline_inverse_bf16(ctypes.byref(args), stream_ptr(y)))

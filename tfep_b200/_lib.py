@@ -15,7 +15,7 @@ from . import _build
 F32, F64 = 0, 1
 ACT_NONE, ACT_ELU = 0, 1
 GEMM_TILE_N = 64
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class TfepB200Error(RuntimeError):
@@ -66,25 +66,27 @@ class TxGrads(Structure):
 
 class FusedLayer(Structure):
     _fields_ = [('ops', c_void_p), ('n_ops', c_int32), ('n_chunks', c_int32), ('weights', c_void_p), ('feats', c_void_p),
-                ('min_bin_size', c_float), ('min_slope', c_float), ('slope_offset', c_float), ('reserved', c_int32)]
+                ('min_bin_size', c_float), ('min_slope', c_float), ('slope_offset', c_float), ('reserved', c_int32),
+                ('input_map', c_void_p), ('emb_lower', c_float), ('emb_scale', c_float)]
 
 
 class FusedArgs(Structure):
     _fields_ = [('x', c_void_p), ('y', c_void_p), ('logdet', c_void_p), ('batch', c_int32), ('n_features', c_int32),
                 ('k1', c_int32), ('hidden_padded', c_int32), ('n_layers', c_int32), ('hidden_halves', c_int32), ('hidden_split', c_int32 * 2),
                 ('layers', POINTER(FusedLayer)), ('tile_flags', c_void_p), ('epoch', c_uint32), ('debug_mode', c_int32),
-                ('mixed_splines', c_int32), ('reserved2', c_int32), ('error_flag', c_void_p), ('debug_params', c_void_p)]
+                ('mixed_splines', c_int32), ('n_inputs', c_int32), ('error_flag', c_void_p), ('debug_params', c_void_p)]
 
 
 class FusedInvLayer(Structure):
     _fields_ = [('ops', c_void_p), ('steps', c_void_p), ('n_ops', c_int32), ('n_steps', c_int32), ('weights', c_void_p),
-                ('min_bin_size', c_float), ('min_slope', c_float), ('slope_offset', c_float), ('reserved', c_int32)]
+                ('min_bin_size', c_float), ('min_slope', c_float), ('slope_offset', c_float), ('reserved', c_int32),
+                ('emb_lower', c_float), ('emb_scale', c_float)]
 
 
 class FusedInvArgs(Structure):
     _fields_ = [('y', c_void_p), ('x', c_void_p), ('logdet', c_void_p), ('batch', c_int32), ('n_features', c_int32),
                 ('k1', c_int32), ('hidden_padded', c_int32), ('n_layers', c_int32), ('reserved', c_int32),
-                ('layers', POINTER(FusedInvLayer)), ('tile_flags', c_void_p), ('epoch', c_uint32), ('reserved2', c_int32),
+                ('layers', POINTER(FusedInvLayer)), ('tile_flags', c_void_p), ('epoch', c_uint32), ('n_inputs', c_int32),
                 ('error_flag', c_void_p)]
 
 

@@ -50,9 +50,11 @@ struct __align__(16) Op {   // same layout as tfepb_fused_op; a_col = absolute T
 struct __align__(16) Step {  // one degree of the sweep (tfepb_fused_inv_step)
     int col;                 // column of the feature in y / x
     float x0, L, invL, Rw, Rh, y0;
-    int partner;             // bits 0-3: the other half of the bf16 pair column (col ^ 1): 0 unknown yet (zero), 1 already
-                             // inverted (read it back), 2 the constant-one bias column; bit 4: spline kind (0 circular,
-                             // 1 not circular: 9 slopes, linear tails)
+    int partner;             // bits 0-3: the other half of the bf16 pair column of the conditioner input: 0 unknown yet
+                             // (zero), 1 already inverted (read it back), 2 the constant-one bias column; bit 4: spline
+                             // kind (0 circular, 1 not circular: 9 slopes, linear tails); bit 5: enters the conditioner as
+                             // (cos, sin) (PeriodicEmbedding); bits 8-15: conditioner input column; bits 16-23: x column
+                             // of the pair partner
     int h1_a, h1_n, h2_a, h2_n;   // packed positions of the hidden units that become computable (n = 0: none)
 };
 
@@ -62,11 +64,13 @@ struct LayerP {
     const Step* steps;       // device
     int n_ops, n_steps;
     float min_bin, min_slope, slope_offset2;
+    float emb_lower, emb_scale;
 };
 
 struct Params {
     const float* y; float* x; float* logdet;
     int batch, D, K1, HP, n_layers, n_tiles;
+    int Din;                 // conditioner inputs before the two constant ones (D + lifted periodic features)
     uint32_t* flags; uint32_t epoch;
     int* error;
     LayerP layers[MAX_LAYERS];
@@ -369,11 +373,11 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_inv_kernel(const __grid
                 }
                 tmem_st_wait();
                 const uint32_t one2 = pack_bf16(1.f, 1.f);
-                if (p.D & 1) {
-                    tmem_st1(lane_addr + A0_COL + p.D / 2, pack_bf16(0.f, 1.f));     // columns D (high half), D + 1
-                    tmem_st1(lane_addr + A0_COL + p.D / 2 + 1, pack_bf16(1.f, 0.f));
+                if (p.Din & 1) {
+                    tmem_st1(lane_addr + A0_COL + p.Din / 2, pack_bf16(0.f, 1.f));     // columns Din (high half), Din + 1
+                    tmem_st1(lane_addr + A0_COL + p.Din / 2 + 1, pack_bf16(1.f, 0.f));
                 } else {
-                    tmem_st1(lane_addr + A0_COL + p.D / 2, one2);
+                    tmem_st1(lane_addr + A0_COL + p.Din / 2, one2);
                 }
                 tmem_st1(lane_addr + A1_COL, one2);
                 tmem_st1(lane_addr + A2_COL, one2);
@@ -407,11 +411,19 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_inv_kernel(const __grid
                     float xv;
                     ld += spline8_inverse<MIXED>(r, xrow[st.col], st, min_bin, min_slope, slope_offset2, xv);
                     xrow[st.col] = xv;
-                    // bf16 pair column of the x operand: the partner is known (already x) or still zero
-                    const int pk = st.partner & 15;
-                    const float other = pk == 1 ? xrow[st.col ^ 1] : (pk == 2 ? 1.f : 0.f);
-                    const uint32_t q = (st.col & 1) ? pack_bf16(other, xv) : pack_bf16(xv, other);
-                    tmem_st1(lane_addr + A0_COL + (st.col >> 1), q);
+                    // bf16 pair column of the conditioner input: (cos, sin) of a lifted periodic feature, or the
+                    // feature next to its partner, which is known (already x), the constant one, or still zero
+                    const int ic = (st.partner >> 8) & 0xff;
+                    uint32_t q;
+                    if (st.partner & 32) {
+                        const float ang = (xv - L.emb_lower) * L.emb_scale;
+                        q = pack_bf16(__cosf(ang), __sinf(ang));
+                    } else {
+                        const int pk = st.partner & 15;
+                        const float other = pk == 1 ? xrow[(st.partner >> 16) & 0xff] : (pk == 2 ? 1.f : 0.f);
+                        q = (ic & 1) ? pack_bf16(other, xv) : pack_bf16(xv, other);
+                    }
+                    tmem_st1(lane_addr + A0_COL + (ic >> 1), q);
                     tmem_st_wait();
                 }
                 // one hand-over per product that follows in this item (the last x of a tile has no consumer)
@@ -489,8 +501,11 @@ extern "C" int tfepb_maf_spline_inverse_bf16(const tfepb_fused_inv_args* a, tfep
     TFEPB_CHECK_ARG(a->batch >= 0 && a->n_features > 0, "bad sizes");
     TFEPB_CHECK_ARG(a->n_layers >= 1 && a->n_layers <= finv::MAX_LAYERS, "n_layers must be in [1, %d]", finv::MAX_LAYERS);
     TFEPB_CHECK_ARG(a->n_layers == 1 || a->tile_flags != nullptr, "a chain of layers needs the tile_flags workspace");
-    TFEPB_CHECK_ARG(a->k1 % 16 == 0 && a->k1 >= a->n_features + 2 && a->k1 <= 2 * (finv::A1_COL - finv::A0_COL),
-                    "k1 must hold n_features + 2 bias columns, rounded up to 16, and fit the tensor-memory plan");
+    const int n_inputs = a->n_inputs > 0 ? a->n_inputs : a->n_features;
+    TFEPB_CHECK_ARG(n_inputs >= a->n_features && n_inputs <= 2 * a->n_features, "n_inputs must be in [n_features, 2 n_features]");
+    TFEPB_CHECK_ARG(a->k1 % 16 == 0 && a->k1 >= n_inputs + 2 && a->k1 <= 2 * (finv::A1_COL - finv::A0_COL),
+                    "k1 must hold n_inputs + 2 bias columns, rounded up to 16, and fit the tensor-memory plan");
+    TFEPB_CHECK_ARG(a->n_features <= 256, "at most 256 features (step table encoding)");
     TFEPB_CHECK_ARG(a->hidden_padded % 16 == 0 && a->hidden_padded > 0 && a->hidden_padded <= 352,
                     "hidden width (padded) must be a multiple of 16 and at most 352 (tensor-memory plan)");
     TFEPB_CHECK_ARG((a->n_features * 4 * tc::TILE_M) % 16 == 0, "tile of y must be a multiple of 16 bytes");
@@ -500,6 +515,7 @@ extern "C" int tfepb_maf_spline_inverse_bf16(const tfepb_fused_inv_args* a, tfep
     finv::Params p{};
     p.y = (const float*)a->y; p.x = (float*)a->x; p.logdet = (float*)a->logdet;
     p.batch = a->batch; p.D = a->n_features; p.K1 = a->k1; p.HP = a->hidden_padded;
+    p.Din = n_inputs;
     p.n_layers = a->n_layers;
     p.n_tiles = (a->batch + tc::TILE_M - 1) / tc::TILE_M;
     p.flags = a->tile_flags; p.epoch = a->epoch; p.error = a->error_flag;
@@ -514,6 +530,7 @@ extern "C" int tfepb_maf_spline_inverse_bf16(const tfepb_fused_inv_args* a, tfep
         d.ops = (const finv::Op*)s.ops; d.steps = (const finv::Step*)s.steps;
         d.n_ops = s.n_ops; d.n_steps = s.n_steps;
         d.min_bin = s.min_bin_size; d.min_slope = s.min_slope; d.slope_offset2 = s.slope_offset * tc::LOG2E;
+        d.emb_lower = s.emb_lower; d.emb_scale = s.emb_scale;
     }
     const size_t smem = finv::smem_bytes(p);
     TFEPB_CHECK_ARG(smem <= 227 * 1024, "shared memory plan of %zu bytes exceeds 227 KB", smem);

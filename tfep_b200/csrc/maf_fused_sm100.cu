@@ -97,6 +97,8 @@ struct LayerP {
     const FeatConst* feats;     // n_chunks * FEATS_PER_CHUNK
     int op_base, n_ops, n_chunks;
     float min_bin, min_slope, slope_offset2;   // slope_offset2 = log2(e) * log(exp(1 - min_slope) - 1)
+    const int* input_map;       // NULL, or per conditioner input column: x column | what enters << 16 (tfepb_fused_layer)
+    float emb_lower, emb_scale;
 };
 
 struct Params {
@@ -472,12 +474,29 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
             }
             for (int c0 = wg * 8; c0 < p.K1 / 2; c0 += EPI_WGS * 8) {      // 8 TMEM columns = 16 inputs per step
                 uint32_t q[8];
+                if (L.input_map == nullptr) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int k = (c0 + i) * 2;
-                    const float v0 = k < p.D ? xrow[k] : (k < p.D + 2 ? 1.f : 0.f);
-                    const float v1 = k + 1 < p.D ? xrow[k + 1] : (k + 1 < p.D + 2 ? 1.f : 0.f);
-                    q[i] = pack_bf16(v0, v1);
+                    for (int i = 0; i < 8; ++i) {
+                        const int k = (c0 + i) * 2;
+                        const float v0 = k < p.D ? xrow[k] : (k < p.D + 2 ? 1.f : 0.f);
+                        const float v1 = k + 1 < p.D ? xrow[k + 1] : (k + 1 < p.D + 2 ? 1.f : 0.f);
+                        q[i] = pack_bf16(v0, v1);
+                    }
+                } else {
+                    // PeriodicEmbedding fused into the operand staging (reference mafembed.py:112-142): periodic
+                    // features enter the conditioner as cos / sin of their angle
+                    auto input = [&](int k) -> float {
+                        const int e = __ldg(L.input_map + k);
+                        const int what = e >> 16;
+                        float v = what >= 3 ? (what == 3 ? 1.f : 0.f) : xrow[e & 0xffff];
+                        if (what == 1 || what == 2) {
+                            const float ang = (v - L.emb_lower) * L.emb_scale;
+                            v = what == 1 ? __cosf(ang) : __sinf(ang);
+                        }
+                        return v;
+                    };
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) q[i] = pack_bf16(input((c0 + i) * 2), input((c0 + i) * 2 + 1));
                 }
                 tmem_st8(lane_addr + A_COL + c0, q);
             }
@@ -491,12 +510,14 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
             // starts on the first half of h2.
             for (int hl = 0; hl < 2; ++hl) {
                 for (int half = 0; half < p.n_halves; ++half) {
-                    // h2 overwrites h1 in place (same A-operand columns), so the second layer may only be written
-                    // once BOTH halves of GEMM2 have read h1; the first layer starts on its first half right away
-                    if (hl == 0 || half == 0) {
-                        mbar_wait(&sm->hid_full[half], (hid_par >> half) & 1u, p.error, 7);
-                        hid_par ^= 1u << half;
-                        if (hl == 1 && p.n_halves == 2) {
+                    // The activations overwrite the A operand of the GEMM that produced them (h1 over x, h2 over h1:
+                    // same tensor-memory columns), so they may only be written once BOTH halves of that GEMM have
+                    // read it.  GEMM1 is tiny (its second half is done ~100 cycles after the first); for GEMM2 the
+                    // overlap that matters is the one with the ELU of the second half of h1, which is kept.
+                    if (half == 0) {
+                        mbar_wait(&sm->hid_full[0], hid_par & 1u, p.error, 7);
+                        hid_par ^= 1u;
+                        if (p.n_halves == 2) {
                             mbar_wait(&sm->hid_full[1], (hid_par >> 1) & 1u, p.error, 7);
                             hid_par ^= 2u;
                         }
@@ -622,7 +643,9 @@ extern "C" int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_st
     TFEPB_CHECK_ARG(a->batch >= 0 && a->n_features > 0, "bad sizes");
     TFEPB_CHECK_ARG(a->n_layers >= 1 && a->n_layers <= fused::MAX_LAYERS, "n_layers must be in [1, %d]", fused::MAX_LAYERS);
     TFEPB_CHECK_ARG(a->n_layers == 1 || a->tile_flags != nullptr, "a chain of layers needs the tile_flags workspace");
-    TFEPB_CHECK_ARG(a->k1 % 16 == 0 && a->k1 >= a->n_features + 2, "k1 must hold n_features + 2 bias columns, rounded up to 16");
+    const int n_inputs = a->n_inputs > 0 ? a->n_inputs : a->n_features;
+    TFEPB_CHECK_ARG(n_inputs >= a->n_features && n_inputs <= 2 * a->n_features, "n_inputs must be in [n_features, 2 n_features]");
+    TFEPB_CHECK_ARG(a->k1 % 16 == 0 && a->k1 >= n_inputs + 2, "k1 must hold n_inputs + 2 bias columns, rounded up to 16");
     TFEPB_CHECK_ARG(a->hidden_padded % 16 == 0 && a->hidden_padded > 0 && a->hidden_padded <= fused::ACC_COLS,
                     "hidden width (padded) must be a multiple of 16 and at most 336 (tensor-memory plan)");
     TFEPB_CHECK_ARG(a->k1 <= 2 * (512 - fused::A_COL), "too many input features for the tensor-memory plan");
@@ -652,6 +675,8 @@ extern "C" int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_st
         d.feats = (const fused::FeatConst*)s.feats;
         d.op_base = op_base; d.n_ops = s.n_ops; d.n_chunks = s.n_chunks;
         d.min_bin = s.min_bin_size; d.min_slope = s.min_slope; d.slope_offset2 = s.slope_offset * fused::LOG2E;
+        TFEPB_CHECK_ARG(s.input_map != nullptr || n_inputs == a->n_features, "layer %d: n_inputs > n_features needs an input_map", l);
+        d.input_map = s.input_map; d.emb_lower = s.emb_lower; d.emb_scale = s.emb_scale;
         memcpy(p.ops + op_base, s.ops, sizeof(fused::Op) * (size_t)s.n_ops);
         op_base += s.n_ops;
         if (s.n_chunks * fused::FEATS_PER_CHUNK > feat_stride) feat_stride = s.n_chunks * fused::FEATS_PER_CHUNK;

@@ -157,15 +157,27 @@ class MAF(AutoregressiveFlow):
         from ... import _fused
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             return False
-        return _fused.eligibility(self) is None
+        return self._fused_plan() is not None
+
+    def _fused_plan(self):
+        """The plan of the fused kernels, or None if they do not cover this layer (``_fused_why`` says why: transformer
+        kind, widths beyond the tensor-memory plan, ...)."""
+        from ... import _fused, _lib
+        if self._fused is None:
+            why = _fused.eligibility(self)
+            if why is None:
+                try:
+                    self._fused = _fused.FusedSplinePlan(self)
+                except _lib.TfepB200Error as e:
+                    why = str(e)
+            if why is not None:
+                self._fused, self._fused_why = False, why
+        return self._fused or None
 
     def _forward_fused(self, x):
         """Tensor-core path: the whole layer in one kernel launch (no autograd, no silent fallback)."""
-        from ... import _fused
         self._check_fused_inference(x)
-        if self._fused is None:
-            self._fused = _fused.FusedSplinePlan(self)
-        return self._fused.forward(self, x)
+        return self._fused_plan().forward(self, x)
 
     def _check_fused_inference(self, x):
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
@@ -185,9 +197,10 @@ class MAF(AutoregressiveFlow):
             raise NotImplementedError('tfep_b200: MAF.inverse is not differentiable yet; call it under torch.no_grad()')
         if self.precision == 'bf16':
             from ... import _fused
-            if self._fused is None:
-                self._fused = _fused.FusedSplinePlan(self)
-            return _fused.run_inverse_chain([(self._fused, self)], y)
+            plan = self._fused_plan()
+            if plan is not None and plan.inverse_eligibility(self) is None:
+                return _fused.run_inverse_chain([(plan, self)], y)
+            # (flows the tensor-core sweep does not cover are inverted by the exact sweep below)
         from ... import _sweep
         if _sweep.eligibility(self, pk) is not None:
             return self._inverse_host_sweep(y)

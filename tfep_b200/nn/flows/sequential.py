@@ -17,7 +17,7 @@ class SequentialFlow(torch.nn.Sequential):
         return self._pass(y, inverse=True)
 
     def _pass(self, x, inverse):
-        if len(self) > 1 and self._fused_chain_ok(x):
+        if len(self) > 1 and self._fused_chain_ok(x, inverse):
             return self._inverse_fused_chain(x) if inverse else self._forward_fused_chain(x)
         cumulative_log_det_J = None
         for flow in (reversed(self) if inverse else self):
@@ -28,23 +28,21 @@ class SequentialFlow(torch.nn.Sequential):
         return x, cumulative_log_det_J
 
     # -- tensor-core fast path: the whole chain of precision='bf16' MAF layers in ONE kernel launch --------
-    def _fused_chain_ok(self, x):
+    def _fused_chain_ok(self, x, inverse=False):
         from .maf import MAF
         if not all(isinstance(f, MAF) and f.precision == 'bf16' for f in self):
             return False
-        return all(f._use_fused(x) for f in self)
+        if not all(f._use_fused(x) for f in self):
+            return False
+        return not inverse or all(f._fused_plan().inverse_eligibility(f) is None for f in self)
 
     def _forward_fused_chain(self, x):
         from ... import _fused
         pairs = []
         for f in self:
             f._check_fused_inference(x)
-            if f._fused is None:
-                f._fused = _fused.FusedSplinePlan(f)
-            pairs.append((f._fused, f))
-        first = pairs[0][0]
-        if any((pl.D, pl.K1, pl.HP) != (first.D, first.K1, first.HP) for pl, _ in pairs) or \
-                sum(len(pl.ops_host) for pl, _ in pairs) > _fused.MAX_OPS:
+            pairs.append((f._fused_plan(), f))
+        if not _fused.chain_compatible([pl for pl, _ in pairs]) or sum(len(pl.ops_host) for pl, _ in pairs) > _fused.MAX_OPS:
             y, ld = x, None
             for pl, f in pairs:
                 y, l = pl.forward(f, y)
@@ -57,11 +55,8 @@ class SequentialFlow(torch.nn.Sequential):
         pairs = []
         for f in reversed(self):
             f._check_fused_inference(y)
-            if f._fused is None:
-                f._fused = _fused.FusedSplinePlan(f)
-            pairs.append((f._fused, f))
-        first = pairs[0][0]
-        if any((pl.D, pl.K1, pl.HP) != (first.D, first.K1, first.HP) for pl, _ in pairs):
+            pairs.append((f._fused_plan(), f))
+        if not _fused.chain_compatible([pl for pl, _ in pairs]):
             x, ld = y, None
             for pl, f in pairs:
                 x, l = _fused.run_inverse_chain([(pl, f)], x)
