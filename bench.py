@@ -306,7 +306,11 @@ def run_ours(args, rank, world, local_rank):
     achieved = flops_per_launch / (k_ms * 1e-3) / 1e12
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': pk_peaks['bf16_tflops'], 'unit': 'TFLOP/s',
                 'frac': achieved / pk_peaks['bf16_tflops'],
-                'traffic': None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture of the
+                # bf16 chain launch at this workload (profiles/r01_ncu_fused_fwd_v6_chain_details.md): 21.08 MB read
+                # (x 17.3 MB + packed weights) + 0.15 MB written -- the 17.6 MB of y / logdet were still in L2 when
+                # the kernel ended; the algorithmic HBM bytes are 34.9 MB per launch
+                'traffic': 21.23e6 if (args.precision == 'bf16' and BATCH == 65536) else None,
                 'kernel': kernel,
                 'kernel_ms': k_ms, 'peak_source': pk_peaks['source'] + ', bf16 burst',
                 'whole_step_frac': (2.0 * plan.masked_macs * 4 * BATCH * args.steps / (total_ms * 1e-3) / 1e12)

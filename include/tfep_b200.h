@@ -148,7 +148,10 @@ int tfepb_sos(const tfepb_tx_io* io, int32_t n_polynomials, tfepb_stream_t strea
 
 /* MoebiusTransformer forward; the inverse is the same map with -par (moebius.py:142-147),
  * selected with io->inverse.  n_features must be a multiple of `dimension` (<= 16).
- * nn/transformers/moebius.py:374-478. */
+ * nn/transformers/moebius.py:374-478.
+ * `unit_sphere` selects the variant: 0 sphere of radius |x|, 1 unit sphere, 2 SymmetrizedMoebiusTransformer
+ * (nn/transformers/moebius.py:481-629: y = |x| s / |s|, s = f(x; w) + f(x; -w), closed-form log-det, analytic
+ * inverse with io->inverse). */
 int tfepb_moebius(const tfepb_tx_io* io, int32_t dimension, double max_radius, int32_t unit_sphere,
                   tfepb_stream_t stream);
 
@@ -369,7 +372,7 @@ typedef struct {
 typedef struct {
     int32_t kind;                        /* TFEPB_SWEEP_* */
     int32_t n_bins, circular, identity_boundary_slopes, learn_lower_bound, learn_upper_bound;   /* spline */
-    int32_t dimension, unit_sphere;      /* moebius */
+    int32_t dimension, unit_sphere;      /* moebius (unit_sphere: variant as in tfepb_moebius) */
     const void *x0, *xf, *y0, *yf;       /* spline domain per feature of the part (dtype of the call);
                                             shift: x0 = period table (0 = not periodic), xf = lower-limit table */
     double min_bin_size, min_slope, max_radius;

@@ -120,6 +120,8 @@ def transformer_cases(dtype=torch.float32):
     add('moebius_d2', fo.Moebius(dimension=2), 6, normal((B, 6), 13, dtype))
     add('moebius_d4_unit', fo.Moebius(dimension=4, unit_sphere=True), 8,
         torch.nn.functional.normalize(normal((B, 2, 4), 14, dtype), dim=-1).reshape(B, 8))
+    add('symmoebius_d3', fo.SymMoebius(dimension=3), 6, normal((B, 6), 19, dtype))
+    add('symmoebius_d2', fo.SymMoebius(dimension=2, max_radius=0.9), 6, normal((B, 6), 20, dtype), pscale=2.0)
     mixed = fo.Mixed([_spline(2, dtype, n_bins=4, circular=True, x0=-math.pi, xf=math.pi),
                       fo.Affine(), _spline(3, dtype, n_bins=4, x0=-4.0, xf=4.0)],
                      [[1, 4], [0, 6], [2, 3, 5]])
@@ -155,6 +157,8 @@ def maf_cases(dtype=torch.float32):
         _spline(6, dtype, n_bins=5, x0=-4.0, xf=4.0), normal((B, 7), 26, dtype))
     add('sos2', fo.gen_degrees(6), fo.SOS(2), normal((B, 6), 27, dtype), invertible=False, gain=1.0)
     add('moebius_d3', fo.gen_degrees(6, repeats=3), fo.Moebius(dimension=3), normal((B, 6), 28, dtype))
+    add('symmoebius_d3', fo.gen_degrees(6, repeats=3, order='descending'), fo.SymMoebius(dimension=3),
+        normal((B, 6), 37, dtype))
     add('moebius_d2_cond', fo.gen_degrees(8, conditioning_indices=[0, 1], repeats=2, order='descending'),
         fo.Moebius(dimension=2), normal((B, 8), 29, dtype))
     mixed = fo.Mixed([_spline(2, dtype, n_bins=4, circular=True, x0=-math.pi, xf=math.pi),

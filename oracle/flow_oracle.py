@@ -451,12 +451,77 @@ class Moebius(_Spec):
         ld = torch.linalg.slogdet(jac)[1].sum(dim=-1)
         return y.reshape(B, n), ld
 
+    def _map_only(self, x, w):
+        """The map without its Jacobian (return_log_det_J=False, moebius.py:455-457), radius |x|."""
+        B, n = x.shape
+        x = x.reshape(B, -1, self.dimension)
+        w = w.reshape(B, -1, self.dimension)
+        wn = torch.linalg.norm(w, dim=-1, keepdim=True)
+        xn = torch.linalg.norm(x, dim=-1, keepdim=True)
+        resc = self.max_radius / (1 + wn)
+        resc = xn * resc
+        w, wn = resc * w, resc * wn
+        diff = x - w
+        return ((xn**2 - wn**2) / torch.linalg.norm(diff, dim=-1, keepdim=True).pow(2) * diff - w).reshape(B, n)
+
     def forward(self, x, par):
         return self._map(x, par)
 
     def inverse(self, y, par):
         """moebius.py:119-151: same map with the sign of the parameters flipped."""
         return self._map(y, -par)
+
+
+@dataclass
+class SymMoebius(_Spec):
+    """SymmetrizedMoebiusTransformer: nn/transformers/moebius.py:193-372 (class), 481-550 (forward), 553-600
+    (analytic inverse), 607-629 (closed-form log-det)."""
+    dimension: int = 3
+    max_radius: float = 0.99
+    identity_eps: float = 1e-9
+    n_params_per_feature: int = 1
+
+    def degrees_out(self, degrees_in):
+        return degrees_in.detach().clone()
+
+    def identity_params(self, n):
+        return (2 * torch.rand(n) - 1) * self.identity_eps
+
+    def _unit_w(self, w):
+        wn = torch.linalg.norm(w, dim=-1, keepdim=True)
+        resc = self.max_radius / (1 + wn)
+        return resc * w, (resc * wn)**2
+
+    def _logdet(self, x_unit, w_unit, r2):
+        d = self.dimension
+        qy2 = r2 - (x_unit * w_unit).sum(dim=-1, keepdim=True)**2
+        dV = (1 - r2) * (1 + r2)**(d - 1) / (4 * qy2 + (1 - r2)**2)**(d / 2)
+        return torch.log(dV).squeeze(-1).sum(dim=1)
+
+    def forward(self, x, par):
+        B, n = x.shape
+        plain = Moebius(self.dimension, self.max_radius, unit_sphere=False)
+        f = plain._map_only(x, par) + plain._map_only(x, -par)
+        x3, f3, w3 = (t.reshape(B, -1, self.dimension) for t in (x, f, par))
+        xn = torch.linalg.norm(x3, dim=-1, keepdim=True)
+        y = xn / torch.linalg.norm(f3, dim=-1, keepdim=True) * f3
+        w_unit, r2 = self._unit_w(w3)
+        return y.reshape(B, n), self._logdet(x3 / xn, w_unit, r2)
+
+    def inverse(self, y, par):
+        B, n = y.shape
+        y3, w3 = y.reshape(B, -1, self.dimension), par.reshape(B, -1, self.dimension)
+        yn = torch.linalg.norm(y3, dim=-1, keepdim=True)
+        y_unit = y3 / yn
+        w_unit, r2 = self._unit_w(w3)
+        da = w_unit / torch.sqrt(r2)
+        a = (y_unit * da).sum(dim=-1, keepdim=True)
+        db = y_unit - a * da
+        db = db / torch.linalg.norm(db, dim=-1, keepdim=True)
+        a_inv = -a * (r2 + 1.0) / torch.sqrt(1 + r2**2 + r2 * (4 * a**2 - 2))
+        b_inv = -torch.sqrt(1 - a_inv**2)
+        x_unit = -(a_inv * da + b_inv * db)
+        return (yn * x_unit).reshape(B, n), -self._logdet(x_unit, w_unit, r2)
 
 
 @dataclass

@@ -32,6 +32,8 @@ def to_module(spec):
         return T.SOSPolynomialTransformer(spec.n_polynomials)
     if isinstance(spec, fo.Moebius):
         return T.MoebiusTransformer(spec.dimension, max_radius=spec.max_radius, unit_sphere=spec.unit_sphere)
+    if isinstance(spec, fo.SymMoebius):
+        return T.SymmetrizedMoebiusTransformer(spec.dimension, max_radius=spec.max_radius, identity_eps=spec.identity_eps)
     if isinstance(spec, fo.Mixed):
         return T.MixedTransformer([to_module(t) for t in spec.transformers], [i.tolist() for i in spec.indices])
     raise TypeError(spec)

@@ -82,7 +82,14 @@ void moebius(const Io<T>& io, int d, double max_radius, int unit, int inverse, i
         T acc = 0;
         for (int u = 0; u < io.F / d; ++u) {
             const int64_t i = (int64_t)b * io.F + u * d;
-            if (backward)
+            if (unit == 2) {          // symmetrized variant
+                if (backward)
+                    symmoebius_vjp<T>(io.x + i, 1, io.par + i, 1, d, (T)max_radius, io.gy + i, 1, io.gl[b], io.gx + i, 1,
+                                      io.gpar + i, 1);
+                else
+                    acc += inverse ? symmoebius_inverse<T>(io.x + i, 1, io.par + i, 1, d, (T)max_radius, io.y + i, 1)
+                                   : symmoebius_eval<T>(io.x + i, 1, io.par + i, 1, d, (T)max_radius, io.y + i, 1);
+            } else if (backward)
                 moebius_vjp<T>(io.x + i, 1, io.par + i, 1, d, (T)max_radius, unit != 0, io.gy + i, 1, io.gl[b],
                                io.gx + i, 1, io.gpar + i, 1);
             else

@@ -22,6 +22,8 @@ def _run(spec, x, par, inverse=False, **kw):
         return hc.shift(x, par, spec, inverse, **kw)
     if isinstance(spec, fo.SOS):
         return hc.sos(x, par, spec.n_polynomials, **{k: v for k, v in kw.items() if k == 'gy'})
+    if isinstance(spec, fo.SymMoebius):
+        return hc.moebius(x, par, spec.dimension, spec.max_radius, 2, inverse, **kw)
     if isinstance(spec, fo.Moebius):
         return hc.moebius(x, par, spec.dimension, spec.max_radius, spec.unit_sphere, inverse, **kw)
     return hc.spline(x, par, spec, inverse, **kw)

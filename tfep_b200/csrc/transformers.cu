@@ -266,6 +266,7 @@ extern "C" int tfepb_moebius(const tfepb_tx_io* io, int32_t dimension, double ma
     if (int rc = check_io(io, nullptr)) return rc;
     TFEPB_CHECK_ARG(dimension >= 1 && dimension <= 16, "dimension must be in [1, 16]");
     TFEPB_CHECK_ARG(io->n_features % dimension == 0, "n_features must be a multiple of the vector dimension");
+    TFEPB_CHECK_ARG(unit_sphere >= 0 && unit_sphere <= 2, "unit_sphere (variant) must be 0, 1 or 2");
     if (io->dtype == TFEPB_F32)
         return run<float>(io, nullptr, MoebiusOp<float>{dimension, (float)max_radius, unit_sphere}, as_stream(stream), "moebius");
     return run<double>(io, nullptr, MoebiusOp<double>{dimension, max_radius, unit_sphere}, as_stream(stream), "moebius");
@@ -277,6 +278,7 @@ extern "C" int tfepb_moebius_backward(const tfepb_tx_io* io, int32_t dimension, 
     if (int rc = check_io(io, g)) return rc;
     TFEPB_CHECK_ARG(dimension >= 1 && dimension <= 16, "dimension must be in [1, 16]");
     TFEPB_CHECK_ARG(io->n_features % dimension == 0, "n_features must be a multiple of the vector dimension");
+    TFEPB_CHECK_ARG(unit_sphere >= 0 && unit_sphere <= 2, "unit_sphere (variant) must be 0, 1 or 2");
     if (io->dtype == TFEPB_F32)
         return run<float>(io, g, MoebiusOp<float>{dimension, (float)max_radius, unit_sphere}, as_stream(stream),
                           "moebius_backward");

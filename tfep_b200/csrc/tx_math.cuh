@@ -208,6 +208,118 @@ TFEPB_HD void moebius_vjp(const T* x, int64_t sx, const T* v, int64_t sv, int d,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Symmetrized Moebius (reference moebius.py:481-629): y = |x| s / |s| with s = f(x; w) + f(x; -w), f the Moebius map on
+// the sphere of radius |x|.  The log-det has the closed form of the reference (moebius.py:607-629)
+//   log[(1 - r2) (1 + r2)^(d-1) / (4 (r2 - t^2) + (1 - r2)^2)^(d/2)],  r2 = |w_u|^2, t = (x / |x|) . w_u,
+//   w_u = max_radius / (1 + |w|) w  (the parameter vector inside the unit ball).
+// d <= 16.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+TFEPB_HD T symmoebius_logdet(T r2, T t, int d) {
+    const T q = r2 - t * t;
+    const T om = T(1) - r2;
+    const T E = T(4) * q + om * om;
+    return Math<T>::log(om) + T(d - 1) * Math<T>::log(T(1) + r2) - T(0.5) * T(d) * Math<T>::log(E);
+}
+
+template <typename T>
+TFEPB_HD T symmoebius_eval(const T* x, int64_t sx, const T* v, int64_t sv, int d, T max_radius, T* y, int64_t sy) {
+    T f1[16], f2[16];
+    moebius_eval<T>(x, sx, v, sv, T(1), d, max_radius, false, f1, 1);
+    moebius_eval<T>(x, sx, v, sv, T(-1), d, max_radius, false, f2, 1);
+    T s2 = T(0), r2x = T(0), n2 = T(0), xv = T(0);
+    for (int i = 0; i < d; ++i) {
+        f1[i] += f2[i];
+        s2 += f1[i] * f1[i];
+        r2x += x[i * sx] * x[i * sx];
+        n2 += v[i * sv] * v[i * sv];
+        xv += x[i * sx] * v[i * sv];
+    }
+    const T r = Math<T>::sqrt(r2x);
+    const T scale = r / Math<T>::sqrt(s2);
+    for (int i = 0; i < d; ++i) y[i * sy] = scale * f1[i];
+    const T n = Math<T>::sqrt(n2);
+    const T alpha = max_radius / (T(1) + n);
+    const T rho = alpha * n;
+    return symmoebius_logdet<T>(rho * rho, alpha * xv / r, d);
+}
+
+// analytic inverse (moebius.py:553-600): in the plane spanned by w and x the map acts on the angle only
+template <typename T>
+TFEPB_HD T symmoebius_inverse(const T* yv, int64_t sy, const T* v, int64_t sv, int d, T max_radius, T* x, int64_t sx) {
+    T r2y = T(0), n2 = T(0);
+    for (int i = 0; i < d; ++i) {
+        r2y += yv[i * sy] * yv[i * sy];
+        n2 += v[i * sv] * v[i * sv];
+    }
+    const T r = Math<T>::sqrt(r2y), n = Math<T>::sqrt(n2);
+    const T alpha = max_radius / (T(1) + n);
+    const T rho = alpha * n;
+    // da = w / |w| ; a = y_unit . da ; db = (y_unit - a da) / b
+    T a = T(0);
+    for (int i = 0; i < d; ++i) a += (yv[i * sy] / r) * (v[i * sv] / n);
+    T db[16], b2 = T(0);
+    for (int i = 0; i < d; ++i) {
+        db[i] = yv[i * sy] / r - a * (v[i * sv] / n);
+        b2 += db[i] * db[i];
+    }
+    const T b = Math<T>::sqrt(b2);
+    const T r2 = rho * rho;
+    const T a_inv = -a * (r2 + T(1)) / Math<T>::sqrt(T(1) + r2 * r2 + r2 * (T(4) * a * a - T(2)));
+    const T b_inv = -Math<T>::sqrt(T(1) - a_inv * a_inv);
+    T t = T(0);                                        // x_unit_inv . w_u
+    for (int i = 0; i < d; ++i) {
+        const T u = -(a_inv * (v[i * sv] / n) + b_inv * (db[i] / b));
+        t += u * alpha * v[i * sv];
+        x[i * sx] = r * u;
+    }
+    return -symmoebius_logdet<T>(r2, t, d);
+}
+
+// VJP of the forward map: through the two Moebius maps, the projection back on the sphere and the closed-form log-det
+template <typename T>
+TFEPB_HD void symmoebius_vjp(const T* x, int64_t sx, const T* v, int64_t sv, int d, T max_radius,
+                             const T* gy, int64_t sgy, T gl, T* gx, int64_t sgx, T* gv, int64_t sgv) {
+    T s[16], f2[16], xs[16], vs[16], vneg[16];
+    for (int i = 0; i < d; ++i) {
+        xs[i] = x[i * sx];
+        vs[i] = v[i * sv];
+        vneg[i] = -vs[i];
+    }
+    moebius_eval<T>(xs, 1, vs, 1, T(1), d, max_radius, false, s, 1);
+    moebius_eval<T>(xs, 1, vs, 1, T(-1), d, max_radius, false, f2, 1);
+    T s2 = T(0), r2x = T(0), n2 = T(0), xv = T(0), sg = T(0);
+    for (int i = 0; i < d; ++i) {
+        s[i] += f2[i];
+        s2 += s[i] * s[i];
+        r2x += xs[i] * xs[i];
+        n2 += vs[i] * vs[i];
+        xv += xs[i] * vs[i];
+    }
+    const T sn = Math<T>::sqrt(s2), r = Math<T>::sqrt(r2x), n = Math<T>::sqrt(n2);
+    for (int i = 0; i < d; ++i) sg += (s[i] / sn) * gy[i * sgy];          // s_hat . gy = cotangent of r
+    T gs[16];
+    for (int i = 0; i < d; ++i) gs[i] = (r / sn) * (gy[i * sgy] - (s[i] / sn) * sg);
+    T gx1[16], gv1[16], gx2[16], gv2[16];
+    moebius_vjp<T>(xs, 1, vs, 1, d, max_radius, false, gs, 1, T(0), gx1, 1, gv1, 1);
+    moebius_vjp<T>(xs, 1, vneg, 1, d, max_radius, false, gs, 1, T(0), gx2, 1, gv2, 1);
+    // log-det: ld(r2, t), r2 = rho^2, rho = alpha n, t = alpha (x . v) / r
+    const T alpha = max_radius / (T(1) + n);
+    const T rho = alpha * n, r2 = rho * rho;
+    const T t = alpha * xv / r;
+    const T om = T(1) - r2, E = T(4) * (r2 - t * t) + om * om;
+    const T dld_dr2 = -T(1) / om + T(d - 1) / (T(1) + r2) - T(0.5) * T(d) * (T(4) - T(2) * om) / E;
+    const T dld_dt = T(4) * T(d) * t / E;
+    const T drho_dn = alpha / (T(1) + n), dalpha_dn = -alpha / (T(1) + n);
+    const T gn = gl * (dld_dr2 * T(2) * rho * drho_dn + dld_dt * dalpha_dn * xv / r);     // cotangent of n = |v|
+    const T gt = gl * dld_dt;
+    for (int i = 0; i < d; ++i) {
+        gx[i * sgx] = gx1[i] + gx2[i] + sg * xs[i] / r + gt * alpha * (vs[i] / r - xv * xs[i] / (r * r * r));
+        gv[i * sgv] = gv1[i] - gv2[i] + gt * alpha * xs[i] / r + (n > T(0) ? gn * vs[i] / n : T(0));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // rational-quadratic neural spline
 // ---------------------------------------------------------------------------------------------
 template <typename T>

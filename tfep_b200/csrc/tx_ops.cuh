@@ -98,12 +98,23 @@ template <typename T>
 struct MoebiusOp {
     int d;
     T max_radius;
-    int unit_sphere;
+    int unit_sphere;         // variant: 0 sphere of radius |x|, 1 unit sphere, 2 symmetrized (moebius.py:481-600)
     __device__ int units(int F) const { return F / d; }
     // Vector blocks are `d` consecutive TRANSFORMER features; their columns go through `cols`.
     // With cols == nullptr the block is contiguous in x / y (stride 1).
     __device__ T apply(const TxView<T>& v, int b, int u) const {
         const int f0 = v.fid(u * d);
+        if (unit_sphere == 2) {
+            T xs[16], vs[16], ys[16];
+            for (int i = 0; i < d; ++i) {
+                xs[i] = v.x[(int64_t)b * v.ldx + v.col(f0 + i)];
+                vs[i] = v.par[v.poffset(b, f0 + i)];
+            }
+            const T ld = v.inverse ? symmoebius_inverse<T>(xs, 1, vs, 1, d, max_radius, ys, 1)
+                                   : symmoebius_eval<T>(xs, 1, vs, 1, d, max_radius, ys, 1);
+            for (int i = 0; i < d; ++i) v.y[(int64_t)b * v.ldy + v.col(f0 + i)] = ys[i];
+            return ld;
+        }
         if (v.cols == nullptr && v.pbase == nullptr) {
             return moebius_eval<T>(v.x + (int64_t)b * v.ldx + f0, 1, v.par + v.poffset(b, f0), v.sf,
                                    v.inverse ? T(-1) : T(1), d, max_radius, unit_sphere != 0,
@@ -128,7 +139,8 @@ struct MoebiusOp {
             gys[i] = v.gy[(int64_t)b * v.ldgy + c];
             vs[i] = v.par[v.poffset(b, f0 + i)];
         }
-        moebius_vjp<T>(xs, 1, vs, 1, d, max_radius, unit_sphere != 0, gys, 1, gl, gxs, 1, gvs, 1);
+        if (unit_sphere == 2) symmoebius_vjp<T>(xs, 1, vs, 1, d, max_radius, gys, 1, gl, gxs, 1, gvs, 1);
+        else moebius_vjp<T>(xs, 1, vs, 1, d, max_radius, unit_sphere != 0, gys, 1, gl, gxs, 1, gvs, 1);
         for (int i = 0; i < d; ++i) {
             v.gx[(int64_t)b * v.ldgx + v.col(f0 + i)] = gxs[i];
             v.gpar[v.poffset(b, f0 + i)] = gvs[i];
