@@ -182,6 +182,44 @@ def maf_cases(dtype=torch.float32):
     return c
 
 
+def wrapper_cases(dtype=torch.float32):
+    """name -> dict(layers=[(kind, kwargs), ...] outermost first, inner=<MAF case on the propagated features>, x,
+    invertible).  Kinds: 'partial', 'centroid', 'oriented' (reference nn/flows/{partial,centroid,oriented}.py)."""
+    B = 12
+    c = {}
+
+    def inner(n, seed, spec=None):
+        return dict(degrees_in=fo.gen_degrees(n), spec=spec or fo.Affine(), hidden_layers=2, weight_norm=True, seed=seed,
+                    gain=2.0, embedding=None)
+
+    def add(name, layers, n_in, n_inner, seed, invertible=True, spec=None):
+        c[name] = dict(layers=layers, inner=inner(n_inner, 300 + seed, spec), x=normal((B, n_in), 200 + seed, dtype) * 1.5,
+                       invertible=invertible)
+
+    add('partial', [('partial', dict(fixed_indices=[1, 4]))], 7, 5, 1)
+    add('partial_return', [('partial', dict(fixed_indices=[0], return_partial=True))], 5, 4, 2, invertible=False)
+    add('centroid', [('centroid', dict(space_dimension=3))], 12, 9, 3)
+    add('centroid_weighted_subset',
+        [('centroid', dict(space_dimension=3, subset_point_indices=[0, 2, 3], weights=[1.0, 2.0, 3.0], fixed_point_idx=1,
+                           origin=[0.5, -1.0, 2.0]))], 12, 9, 4)
+    add('centroid_2d_no_back', [('centroid', dict(space_dimension=2, translate_back=False))], 8, 6, 5, invertible=False)
+    add('oriented', [('oriented', dict())], 12, 9, 6, spec=_spline(9, dtype, n_bins=5, x0=-6.0, xf=6.0))
+    add('oriented_z_yz', [('oriented', dict(axis_point_idx=2, plane_point_idx=0, axis='z', plane='yz'))], 12, 9, 7)
+    add('centroid_oriented', [('centroid', dict(space_dimension=3, fixed_point_idx=1)),
+                              ('oriented', dict(axis_point_idx=0, plane_point_idx=2))], 15, 9, 8)
+    return c
+
+
+def build_wrapper_oracle(case, dtype=torch.float32):
+    """(oracle flow, state dict of the innermost MAF) of a wrapper case."""
+    from . import wrappers_oracle as wo
+    flow, sd = build_oracle(case['inner'], dtype)
+    for kind, kw in reversed(case['layers']):
+        kw = {k: (torch.tensor(v, dtype=dtype) if k in ('weights', 'origin') else v) for k, v in kw.items()}
+        flow = {'partial': wo.Partial, 'centroid': wo.Centroid, 'oriented': wo.Oriented}[kind](flow, **kw)
+    return flow, sd
+
+
 def build_oracle(case, dtype=torch.float32):
     m = fo.MafOracle(case['degrees_in'], case['spec'], hidden_layers=case['hidden_layers'],
                      weight_norm=case['weight_norm'], embedding=case.get('embedding'))

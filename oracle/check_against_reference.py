@@ -127,6 +127,31 @@ def check_mafs(ref, dtype, fails):
                 _same(ldi_o, ldi_r, f'maf {name}/{dtype}/inverse logdet', fails)
 
 
+def to_reference_wrapper(ref, case, state_dict, dtype):
+    """The reference's wrapper flows around the reference MAF of a wrapper case (cases.wrapper_cases)."""
+    flow = to_reference_maf(ref, case['inner'], state_dict)
+    for kind, kw in reversed(case['layers']):
+        kw = {k: (torch.tensor(v, dtype=dtype) if k in ('weights', 'origin') else v) for k, v in kw.items()}
+        flow = {'partial': ref.PartialFlow, 'centroid': ref.CenteredCentroidFlow, 'oriented': ref.OrientedFlow}[kind](flow, **kw)
+    return flow
+
+
+def check_wrappers(ref, dtype, fails):
+    for name, case in cases.wrapper_cases(dtype).items():
+        oracle, sd = cases.build_wrapper_oracle(case, dtype)
+        flow = to_reference_wrapper(ref, case, sd, dtype)
+        with torch.no_grad():
+            y_r, ld_r = flow(case['x'].clone())
+            y_o, ld_o = oracle.forward(case['x'].clone())
+            _same(y_o, y_r, f'wrapper {name}/{dtype}/forward y', fails)
+            _same(ld_o, ld_r, f'wrapper {name}/{dtype}/forward logdet', fails)
+            if case['invertible']:
+                x_r, ldi_r = flow.inverse(y_r.clone())
+                x_o, ldi_o = oracle.inverse(y_r.clone())
+                _same(x_o, x_r, f'wrapper {name}/{dtype}/inverse x', fails)
+                _same(ldi_o, ldi_r, f'wrapper {name}/{dtype}/inverse logdet', fails)
+
+
 def check_cfg2_slice(ref, fails):
     """Two layers of the headline configuration at a small batch, through SequentialFlow."""
     flows = cases.cfg_flow('cfg2', n_layers=2)
@@ -187,6 +212,7 @@ def run_all():
         try:
             check_transformers(ref, dtype, fails)
             check_mafs(ref, dtype, fails)
+            check_wrappers(ref, dtype, fails)
         finally:
             torch.set_default_dtype(old)
     check_cfg2_slice(ref, fails)

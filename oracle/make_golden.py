@@ -16,7 +16,7 @@ import torch
 
 from . import cases
 from . import flow_oracle as fo
-from .check_against_reference import to_reference_maf, to_reference_transformer
+from .check_against_reference import to_reference_maf, to_reference_transformer, to_reference_wrapper
 from .ref_import import import_reference
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
@@ -69,6 +69,27 @@ def golden_mafs(ref, dtype, tag):
         for k, p in maf.named_parameters():
             out[f'{name}/grad/{k}'] = _np(p.grad)
     np.savez_compressed(os.path.join(OUT, f'maf_{tag}.npz'), **out)
+
+
+def golden_wrappers(ref, dtype, tag):
+    """PartialFlow / CenteredCentroidFlow / OrientedFlow around a reference MAF: outputs, inverse, gradient w.r.t. x."""
+    out = {}
+    for name, case in cases.wrapper_cases(dtype).items():
+        _, sd = cases.build_wrapper_oracle(case, dtype)
+        flow = to_reference_wrapper(ref, case, sd, dtype)
+        with torch.no_grad():
+            y, ld = flow(case['x'].clone())
+            out[f'{name}/x'], out[f'{name}/y'], out[f'{name}/ld'] = _np(case['x']), _np(y), _np(ld)
+            out[f'{name}/checksum'] = np.float64(cases.checksum(sd))
+            if case['invertible']:
+                xi, ldi = flow.inverse(y.clone())
+                out[f'{name}/xinv'], out[f'{name}/ldinv'] = _np(xi), _np(ldi)
+        xg = case['x'].clone().requires_grad_(True)
+        y, ld = flow(xg)
+        cy, cl = cases.normal(tuple(y.shape), 78, dtype), cases.normal(tuple(ld.shape), 79, dtype)
+        ((y * cy).sum() + (ld * cl).sum()).backward()
+        out[f'{name}/gx'] = _np(xg.grad)
+    np.savez_compressed(os.path.join(OUT, f'wrappers_{tag}.npz'), **out)
 
 
 def golden_cfg(ref):
@@ -187,6 +208,7 @@ def main():
         try:
             golden_transformers(ref, dtype, tag)
             golden_mafs(ref, dtype, tag)
+            golden_wrappers(ref, dtype, tag)
         finally:
             torch.set_default_dtype(old)
     golden_cfg(ref)

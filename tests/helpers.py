@@ -58,6 +58,33 @@ def to_maf(case, state_dict, device=None, dtype=None):
     return maf
 
 
+def to_wrapper(case, inner_flow, dtype=torch.float32):
+    """The tfep_b200 wrapper flows of a wrapper case (oracle.cases.wrapper_cases) around ``inner_flow``."""
+    from tfep_b200.nn.flows import CenteredCentroidFlow, OrientedFlow, PartialFlow
+    flow = inner_flow
+    for kind, kw in reversed(case['layers']):
+        kw = {k: (torch.tensor(v, dtype=dtype) if k in ('weights', 'origin') else v) for k, v in kw.items()}
+        flow = {'partial': PartialFlow, 'centroid': CenteredCentroidFlow, 'oriented': OrientedFlow}[kind](flow, **kw)
+    return flow
+
+
+class OracleFlowModule(torch.nn.Module):
+    """A CPU flow for host-side tests of the wrapper logic: forward / inverse of an oracle flow (autograd works)."""
+
+    def __init__(self, oracle):
+        super().__init__()
+        self.oracle = oracle
+
+    def forward(self, x):
+        return self.oracle.forward(x)
+
+    def inverse(self, y):
+        return self.oracle.inverse(y)
+
+    def n_parameters(self):
+        return 0
+
+
 def cfg_flow_modules(name, device, n_layers=None, D=None, dtype=torch.float32):
     """BASELINE.json configuration as (tfep_b200 SequentialFlow on `device`, [oracle flows])."""
     from tfep_b200.nn.flows import SequentialFlow

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import cfg_flow_modules, golden, rel_err, to_maf
+from helpers import cfg_flow_modules, golden, rel_err, to_maf, to_wrapper
 from oracle import cases
 from oracle import flow_oracle as fo
 
@@ -233,3 +233,23 @@ def test_host_pipeline_matches_direct_call():
         torch.cuda.synchronize()
         for yh, ldh in outs[-3:]:
             assert torch.equal(yh, yb.cpu()) and torch.equal(ldh, ldb.cpu()), mode
+
+
+def test_wrapper_flows_around_the_maf_kernels(prec):
+    """PartialFlow / CenteredCentroidFlow / OrientedFlow (reference nn/flows/{partial,centroid,oriented}.py) around the
+    CUDA MAF: forward, inverse and the gradient w.r.t. x (autograd through the frame algebra AND the hand-written
+    MAF backward kernels) against the reference's golden vectors."""
+    g = golden(f'wrappers_{prec}.npz')
+    for name, case in cases.wrapper_cases(DT[prec]).items():
+        _, sd = cases.build_oracle(case['inner'], DT[prec])
+        flow = to_wrapper(case, to_maf(case['inner'], sd, DEV, DT[prec]), DT[prec]).to(DEV)
+        x = case['x'].to(DEV).requires_grad_(True)
+        y, ld = flow(x)
+        assert rel_err(y, g[f'{name}/y']) < 5 * TOL[prec] and rel_err(ld, g[f'{name}/ld']) < 5 * TOL[prec], name
+        cy, cl = cases.normal(tuple(y.shape), 78, DT[prec]).to(DEV), cases.normal(tuple(ld.shape), 79, DT[prec]).to(DEV)
+        ((y * cy).sum() + (ld * cl).sum()).backward()
+        assert rel_err(x.grad, g[f'{name}/gx']) < 50 * TOL[prec], name
+        if case['invertible']:
+            with torch.no_grad():
+                xi, ldi = flow.inverse(torch.from_numpy(g[f'{name}/y']).to(DEV))
+            assert rel_err(xi, g[f'{name}/xinv']) < 50 * TOL[prec] and rel_err(ldi, g[f'{name}/ldinv']) < 50 * TOL[prec], name

@@ -202,3 +202,61 @@ def test_no_cpu_fallback():
 def test_sequential_flow_container():
     seq = SequentialFlow(MAF(generate_degrees(3)), MAF(generate_degrees(3, order='descending')))
     assert int(seq.n_parameters()) == sum(int(f.n_parameters()) for f in seq)
+
+
+@pytest.mark.parametrize('prec', ['f32', 'f64'])
+def test_wrapper_flows_on_host(prec):
+    """PartialFlow / CenteredCentroidFlow / OrientedFlow (device-agnostic tensor algebra either side of the MAF
+    kernels) around an oracle-backed CPU flow: outputs, inverse and the gradient w.r.t. x against the reference's
+    golden vectors, plus the constraints the wrappers exist for."""
+    from helpers import OracleFlowModule, golden, rel_err, to_wrapper
+    dtype = {'f32': torch.float32, 'f64': torch.float64}[prec]
+    tol = {'f32': 1e-5, 'f64': 1e-11}[prec]
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)
+    try:
+        g = golden(f'wrappers_{prec}.npz')
+        for name, case in cases.wrapper_cases(dtype).items():
+            inner, _ = cases.build_oracle(case['inner'], dtype)
+            flow = to_wrapper(case, OracleFlowModule(inner), dtype)
+            x = case['x'].clone().requires_grad_(True)
+            y, ld = flow(x)
+            assert rel_err(y, g[f'{name}/y']) < tol and rel_err(ld, g[f'{name}/ld']) < tol, name
+            cy, cl = cases.normal(tuple(y.shape), 78, dtype), cases.normal(tuple(ld.shape), 79, dtype)
+            ((y * cy).sum() + (ld * cl).sum()).backward()
+            assert rel_err(x.grad, g[f'{name}/gx']) < 20 * tol, name
+            if case['invertible']:
+                with torch.no_grad():
+                    xi, ldi = flow.inverse(torch.from_numpy(g[f'{name}/y']))
+                assert rel_err(xi, g[f'{name}/xinv']) < 20 * tol and rel_err(ldi, g[f'{name}/ldinv']) < 20 * tol, name
+                assert rel_err(xi, case['x']) < 1e3 * tol and rel_err(ld.detach() + ldi, torch.zeros_like(ldi)) < 1e3 * tol, name
+        # the constraints: fixed features untouched; centroid preserved; constrained coordinates stay zero in the frame
+        case = cases.wrapper_cases(dtype)['partial']
+        y = torch.from_numpy(g['partial/y'])
+        assert torch.equal(y[:, [1, 4]], case['x'][:, [1, 4]])
+        case = cases.wrapper_cases(dtype)['centroid']
+        yc = torch.from_numpy(g['centroid/y']).reshape(12, 4, 3).mean(dim=1)
+        assert rel_err(yc, case['x'].reshape(12, 4, 3).mean(dim=1)) < 10 * tol
+    finally:
+        torch.set_default_dtype(old)
+
+
+def test_wrapper_flow_constructor_errors():
+    from tfep_b200.nn.flows import CenteredCentroidFlow, OrientedFlow
+    inner = torch.nn.Identity()
+    with pytest.raises(ValueError, match="'return_partial=True' is supported only if 'translate_back=False'"):
+        CenteredCentroidFlow(inner, 3, return_partial=True)
+    with pytest.raises(ValueError, match="'origin' must have length equal to 'space_dimension'"):
+        CenteredCentroidFlow(inner, 3, origin=[0.0, 1.0])
+    with pytest.raises(ValueError, match="'weights' must have the same length as 'subset_point_indices'"):
+        CenteredCentroidFlow(inner, 3, subset_point_indices=[0, 1], weights=[1.0, 2.0, 3.0])
+    with pytest.raises(ValueError, match="'return_partial=True' is supported only if 'rotate_back=False'"):
+        OrientedFlow(inner, return_partial=True)
+    with pytest.raises(ValueError, match="must be different"):
+        OrientedFlow(inner, axis_point_idx=1, plane_point_idx=1)
+    with pytest.raises(ValueError, match="must be constrained on an axis on the same plane"):
+        OrientedFlow(inner, axis='z', plane='xy')
+    with pytest.raises(ValueError, match="only if 'translate_back' is set to True"):
+        CenteredCentroidFlow(inner, 3, translate_back=False).inverse(torch.zeros(2, 6))
+    with pytest.raises(ValueError, match="only if 'rotate_back' is set to True"):
+        OrientedFlow(inner, rotate_back=False).inverse(torch.zeros(2, 9))

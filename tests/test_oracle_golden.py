@@ -69,6 +69,19 @@ def test_mafs_match_golden(prec):
             assert rel_err(ldi, g[f'{name}/ldinv']) < 20 * TOL[prec], name
 
 
+def test_wrapper_flows_match_golden(prec):
+    """oracle/wrappers_oracle.py (Partial / CenteredCentroid / Oriented flows) against the reference's outputs."""
+    g = golden(f'wrappers_{prec}.npz')
+    for name, case in cases.wrapper_cases(DT[prec]).items():
+        oracle, sd = cases.build_wrapper_oracle(case, DT[prec])
+        assert abs(cases.checksum(sd) - float(g[f'{name}/checksum'])) < 1e-9 * float(g[f'{name}/checksum']), name
+        y, ld = oracle.forward(case['x'].clone())
+        assert rel_err(y, g[f'{name}/y']) < 5 * TOL[prec] and rel_err(ld, g[f'{name}/ld']) < 5 * TOL[prec], name
+        if case['invertible']:
+            xi, ldi = oracle.inverse(torch.from_numpy(g[f'{name}/y']).clone())
+            assert rel_err(xi, g[f'{name}/xinv']) < 20 * TOL[prec] and rel_err(ldi, g[f'{name}/ldinv']) < 20 * TOL[prec], name
+
+
 def test_config_slices_match_golden():
     g = golden('cfg_slices.npz')
     for cfg, nl, B, D in (('cfg1', 2, 64, None), ('cfg2', 4, 64, None), ('cfg3', 6, 32, 30), ('cfg5', 2, 32, 24)):
