@@ -315,7 +315,8 @@ int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_stream_t stre
  * tmem_col the accumulator: 0 output rows, 32 hidden units), `steps` one entry per degree.
  * -------------------------------------------------------------------------------------------- */
 typedef struct {
-    int32_t col;                         /* column of the feature of this degree in y / x */
+    int32_t col;                         /* column of the feature of this degree in y / x; -1: no feature, the step only
+                                            brings in hidden units that depend on conditioning features alone */
     float x0, period, inv_period, rescaled_width, rescaled_height, y0;
     int32_t partner;                     /* bits 0-3: other half of the bf16 pair column of the conditioner input: 0 not
                                             known yet, 1 known, 2 constant one; bit 4: spline kind (0 circular, 1 not
@@ -333,6 +334,10 @@ typedef struct {
     float min_bin_size, min_slope, slope_offset;
     int32_t reserved;
     float emb_lower, emb_scale;          /* as in tfepb_fused_layer (used by steps with bit 5 set) */
+    const int32_t* init_map;             /* NULL, or device, k1 entries in the encoding of tfepb_fused_layer.input_map: what
+                                            every conditioner input column holds BEFORE the sweep -- conditioning features
+                                            (degree -1, nn/flows/autoregressive.py:204), the constant ones, zero for the
+                                            features still to be inverted */
 } tfepb_fused_inv_layer;
 
 typedef struct {

@@ -240,6 +240,10 @@ def cfg_flow(name, dtype=torch.float32, n_layers=None, D=None):
         D, L = D or 66, n_layers or 4
         mk = lambda: fo.Spline(x0=torch.full((D,), -math.pi, dtype=dtype), xf=torch.full((D,), math.pi, dtype=dtype),
                                n_bins=8, circular=True)
+    elif name in ('cfg2cond', 'cfg2condemb'):     # cfg2 with the first two atoms (6 features) as conditioning features (degree -1):
+        D, L = D or 66, n_layers or 4            # they steer the conditioner and pass through unchanged
+        mk = lambda: fo.Spline(x0=torch.full((D - 6,), -math.pi, dtype=dtype), xf=torch.full((D - 6,), math.pi, dtype=dtype),
+                               n_bins=8, circular=True)
     elif name in ('cfg2mix', 'cfg2mixemb'):      # cfg2's "dihedral / Cartesian mix": circular splines on the torsions
         D, L = D or 66, n_layers or 4            # f % 3 == 2, ordinary splines on [-4, 4] for the others;
                                                  # 'emb': torsions enter the conditioner as (cos, sin), app/mixedmaf.py:341-353
@@ -265,11 +269,15 @@ def cfg_flow(name, dtype=torch.float32, n_layers=None, D=None):
                 spec, deg = fo.SOS(2), fo.gen_degrees(D, order=order)
             else:
                 spec, deg = fo.Moebius(dimension=3), fo.gen_degrees(D, order=order, repeats=3)
+        elif name in ('cfg2cond', 'cfg2condemb'):
+            spec, deg = mk(), fo.gen_degrees(D, order=order, conditioning_indices=list(range(6)))
         else:
             spec, deg = mk(), fo.gen_degrees(D, order=order)
         emb = None
         if name == 'cfg2mixemb':
             emb = fo.PeriodicEmbed(D, torch.tensor([-math.pi, math.pi], dtype=dtype), [f for f in range(D) if f % 3 == 2])
+        if name == 'cfg2condemb':       # every feature, the conditioning ones included, enters as (cos, sin)
+            emb = fo.PeriodicEmbed(D, torch.tensor([-math.pi, math.pi], dtype=dtype))
         m = fo.MafOracle(deg, spec, embedding=emb)
         sd = seeded_state([k.to(dtype) for k in m.masks], 1234 + l, dtype)
         flows.append((m.load(sd), sd))
@@ -277,7 +285,7 @@ def cfg_flow(name, dtype=torch.float32, n_layers=None, D=None):
 
 
 def cfg_input(name, batch, dtype=torch.float32, D=None):
-    if name == 'cfg2':
+    if name in ('cfg2', 'cfg2cond', 'cfg2condemb'):
         return uniform((batch, D or 66), 0, -math.pi, math.pi, dtype) * 0.999
     if name in ('cfg2mix', 'cfg2mixemb'):        # torsions uniform in (-pi, pi), Cartesians normal with a few samples in the spline tails
         D = D or 66

@@ -255,6 +255,47 @@ def test_narrow_and_odd_widths(cfg, D):
             assert float(d.median()) < 2e-5 and float((ld + ldi).abs().median()) < 5e-5
 
 
+@pytest.mark.parametrize('cfg,D', [('cfg2cond', 66), ('cfg2condemb', 36)])
+def test_conditioning_features(cfg, D):
+    """Features of degree -1 (conditioning atoms) feed the conditioner and pass through.  Forward: no slot, no output
+    rows.  Inverse: they are staged into the x operand before the sweep and leading steps without a feature bring
+    in the hidden units that depend on them alone (30 units of each layer at D = 66: chunks of 15).  With a
+    PeriodicEmbedding the conditioning features are lifted to (cos, sin) as well."""
+    seq, _ = cfg_flow_modules(cfg, DEV, n_layers=3, D=D)
+    x = cases.cfg_input(cfg, 1000, D=D).to(DEV)
+    with torch.no_grad():
+        y32, ld32 = seq[0](x)
+        s32, sl32 = seq(x)
+        for maf in seq:
+            maf.precision = 'bf16'
+            assert maf._fused_plan() is not None, maf._fused_why
+            assert maf._fused_plan().inverse_eligibility(maf) is None
+        y, ld = seq[0](x)
+        assert torch.equal(y[:, :6], x[:, :6])
+        assert float(_circ(y, y32).max()) < 5e-2 and float(_circ(y, y32).mean()) < 2e-3
+        assert float((ld - ld32).abs().mean()) < 8e-3
+        xi, ldi = seq[0].inverse(y)
+        d = _circ(xi, x).max(dim=1).values
+        assert torch.equal(xi[:, :6], x[:, :6])
+        assert float(d.median()) < 2e-5 and float((d < 2e-2).float().mean()) > 0.97
+        assert float((ld + ldi).abs().median()) < 5e-5
+        seq[0].precision = 'fp32'
+        xe, lde = seq[0].inverse(y)                  # exact sweep of the same y
+        seq[0].precision = 'bf16'
+        assert float(_circ(xi, xe).mean()) < 2e-3 and float((ldi - lde).abs().mean()) < 8e-3
+        yc, ldc = seq(x)
+        cur, tot = x, None
+        for maf in seq:
+            cur, l = maf(cur)
+            tot = l if tot is None else tot + l
+        assert torch.equal(yc, cur) and float((ldc - tot).abs().max()) < 1e-5
+        assert float(_circ(yc, s32).max(dim=1).values.median()) < 5e-3
+        xc, ldci = seq.inverse(yc)
+        dc = _circ(xc, x).max(dim=1).values
+        assert float(dc.median()) < 1e-4 and float((ldc + ldci).abs().median()) < 2e-4
+        assert int(seq[0]._fused._tables(torch.device(DEV))['err'].item()) == 0
+
+
 def test_layers_beyond_the_tensor_memory_plan_use_the_general_gemm():
     """D = 66 with 22 lifted torsions asks for hidden layers of 381 units: more than the tensor-memory plan of the
     one-launch kernel holds.  precision='bf16' then runs the conditioner on the general tensor-core GEMM (and the

@@ -91,8 +91,6 @@ def eligibility(maf):
         return 'conditioner_indices are not fused'
     if len(maf._conditioner._linear_layers()) != 3:
         return 'the fused kernel is built for two hidden layers'
-    if int(maf._degrees_in_host.min()) < 0:
-        return 'conditioning features (degree -1) are not fused'
     D = len(maf._degrees_in_host)
     if (D * 4 * TILE_M) % 16 != 0:
         return 'row length not supported'
@@ -176,8 +174,9 @@ class FusedSplinePlan:
                 feats_all.append(dict(col=cols_p[f], deg=int(deg_in[cols_p[f]]), rows=ref_cols_p[f], circular=part.spec.circular,
                                       x0=float(dom[0][f]), xf=float(dom[1][f]), y0=float(dom[2][f]), yf=float(dom[3][f])))
         feats_all.sort(key=lambda d: (d['deg'], d['col']))
-        if len(feats_all) != self.D or sorted(d['col'] for d in feats_all) != list(range(self.D)):
-            raise _lib.TfepB200Error('fused bf16 path: the spline parts must cover every feature exactly once')
+        # conditioning features (degree -1) enter the conditioner and pass through: no slot, no output rows
+        if sorted(d['col'] for d in feats_all) != [c for c in range(self.D) if int(deg_in[c]) >= 0]:
+            raise _lib.TfepB200Error('fused bf16 path: the spline parts must cover every mapped feature exactly once')
         self._feats_all = feats_all
         self.mixed = any(not d['circular'] for d in feats_all)
         order = list(range(len(feats_all)))
@@ -350,8 +349,6 @@ class FusedSplinePlan:
         cols = [d['col'] for d in self._feats_all]
         order = self._order
         why = None
-        if int(deg_in.min()) < 0:
-            why = 'conditioning features (degree -1)'
         degs = [d['deg'] for d in self._feats_all]
         if why is None and any(b <= a for a, b in zip(degs, degs[1:])):
             why = 'more than one feature per degree'
@@ -376,7 +373,28 @@ class FusedSplinePlan:
             ops.append((w_off, _idesc(n), n, tmem_col, a_col, ksteps, 0))
             w_off += nbytes
 
-        D = self.D
+        # Conditioning features (degree -1) are known from the start: the kernel stages them into the x operand from
+        # `init_map`, and leading steps without a feature (col = -1) bring in the hidden units that depend on them
+        # alone, in chunks of at most 15 units (first all of layer 1, then layer 2, which sees every such unit).
+        cond = [c for c in range(self.D) if int(deg_in[c]) < 0]
+        init_map = None
+        if cond and why is None:
+            init_map = np.full(self.K1, 4 << 16, dtype=np.int32)
+            for c in cond:
+                k = self.input_of_x[c]
+                if c in self.lifted:
+                    init_map[k], init_map[k + 1] = c | (1 << 16), c | (2 << 16)
+                else:
+                    init_map[k] = c
+            init_map[self.Din] = init_map[self.Din + 1] = 3 << 16
+            for layer, (deg_h, a_col, base, ld) in enumerate(((deg_h1, INV_A0_COL, 0, self.K1), (deg_h2, INV_A1_COL, off1, self.HP))):
+                units = (deg_h == -1).nonzero().flatten()
+                kmax = self.K1 if layer == 0 else _ceil16(2 + int((deg_h1 <= -1).sum()))
+                for i in range(0, len(units), 15):
+                    first, n = 2 + int(units[i]), len(units[i:i + 15])
+                    add(list(range(first, first + n)), 16, kmax, a_col, INV_ACC_HID, base, ld)
+                    h = (first, n, 0, 0) if layer == 0 else (0, 0, first, n)
+                    steps.append((-1, 0.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0) + h)
         for si, f in enumerate(order if why is None else []):
             d = degs[si]
             c, j = divmod(si, FEATS_PER_CHUNK)
@@ -416,7 +434,7 @@ class FusedSplinePlan:
             self._inv, self._inv_why = False, why
             return
         self._inv = dict(ops=np.array(ops, dtype=OP_DTYPE), steps=np.array(steps, dtype=STEP_DTYPE),
-                         gather=torch.cat(gather), dev={}, cache=None)
+                         gather=torch.cat(gather), init_map=init_map, dev={}, cache=None)
 
     def inverse_tables(self, maf, device):
         """(ops, steps, packed weights) on the device for the current parameters."""
@@ -429,13 +447,14 @@ class FusedSplinePlan:
         if key not in inv['dev']:
             inv['dev'][key] = dict(ops=torch.from_numpy(inv['ops'].view(np.uint8).reshape(-1).copy()).to(device),
                                    steps=torch.from_numpy(inv['steps'].view(np.uint8).reshape(-1).copy()).to(device),
-                                   gather=inv['gather'].to(device))
+                                   gather=inv['gather'].to(device),
+                                   init_map=None if inv['init_map'] is None else torch.from_numpy(inv['init_map']).to(device))
         tb = inv['dev'][key]
         self.pack(maf)                                   # refreshes the padded source matrices if parameters changed
         ver, _, src = self._cache
         if inv['cache'] is None or inv['cache'][0] != (ver, key):
             inv['cache'] = ((ver, key), src.index_select(0, tb['gather']).contiguous())
-        return tb['ops'], tb['steps'], inv['cache'][1]
+        return tb['ops'], tb['steps'], inv['cache'][1], tb['init_map']
 
     def forward(self, maf, x, debug_params=None):
         """y, log_det_J = fused layer on a contiguous fp32 CUDA tensor (no autograd)."""
@@ -538,12 +557,13 @@ def run_inverse_chain(plans_mafs, y):
     layers = (_lib.FusedInvLayer * n_layers)()
     keep = []
     for i, (pl, maf) in enumerate(plans_mafs):
-        ops, steps, packed = pl.inverse_tables(maf, y.device)
-        keep.append((ops, steps, packed))
+        ops, steps, packed, init_map = pl.inverse_tables(maf, y.device)
+        keep.append((ops, steps, packed, init_map))
         layers[i] = _lib.FusedInvLayer(ops=ops.data_ptr(), steps=steps.data_ptr(), n_ops=len(pl._inv['ops']),
                                        n_steps=len(pl._inv['steps']), weights=packed.data_ptr(), min_bin_size=pl.min_bin,
                                        min_slope=pl.min_slope, slope_offset=pl.slope_offset, reserved=0,
-                                       emb_lower=pl.emb_lower, emb_scale=pl.emb_scale)
+                                       emb_lower=pl.emb_lower, emb_scale=pl.emb_scale,
+                                       init_map=None if init_map is None else init_map.data_ptr())
     tb = first._tables(y.device)
     flags = None
     if n_layers > 1:

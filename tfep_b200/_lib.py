@@ -80,7 +80,7 @@ class FusedArgs(Structure):
 class FusedInvLayer(Structure):
     _fields_ = [('ops', c_void_p), ('steps', c_void_p), ('n_ops', c_int32), ('n_steps', c_int32), ('weights', c_void_p),
                 ('min_bin_size', c_float), ('min_slope', c_float), ('slope_offset', c_float), ('reserved', c_int32),
-                ('emb_lower', c_float), ('emb_scale', c_float)]
+                ('emb_lower', c_float), ('emb_scale', c_float), ('init_map', c_void_p)]
 
 
 class FusedInvArgs(Structure):

@@ -65,6 +65,7 @@ struct LayerP {
     int n_ops, n_steps;
     float min_bin, min_slope, slope_offset2;
     float emb_lower, emb_scale;
+    const int* init_map;     // NULL, or per conditioner input column what it holds BEFORE the sweep (tfepb_fused_inv_layer)
 };
 
 struct Params {
@@ -389,6 +390,27 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_inv_kernel(const __grid
                 for (int i = et; i < TILE_M * p.D; i += EPI_THREADS) sX[i] = i < rows * p.D ? __ldcg(src + i) : 0.f;
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
+            if (L.init_map != nullptr) {
+                // conditioning features (degree -1) are known from the start: stage them (lifted to (cos, sin) where the
+                // embedding says so) next to the constant ones; everything else starts at zero
+                auto input = [&](int k) -> float {
+                    const int e = __ldg(L.init_map + k);
+                    const int what = e >> 16;
+                    float v = what >= 3 ? (what == 3 ? 1.f : 0.f) : xrow[e & 0xffff];
+                    if (what == 1 || what == 2) {
+                        const float ang = (v - L.emb_lower) * L.emb_scale;
+                        v = what == 1 ? __cosf(ang) : __sinf(ang);
+                    }
+                    return v;
+                };
+                for (int c0 = 0; c0 < p.K1 / 2; c0 += 8) {
+                    uint32_t q[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) q[i] = pack_bf16(input((c0 + i) * 2), input((c0 + i) * 2 + 1));
+                    tmem_st8(lane_addr + A0_COL + c0, q);
+                }
+                tmem_st_wait();
+            }
             tc_fence_before();
             mbar_arrive(&sm->a_ready);
             // ---- degree sweep ----
@@ -398,7 +420,11 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_inv_kernel(const __grid
             const float min_bin = L.min_bin, min_slope = L.min_slope, slope_offset2 = L.slope_offset2;
             for (int d = 0; d < n_steps; ++d) {
                 const Step st = L.steps[d];
-                // OUT_d: parameters of the feature -> x_d
+                // one hand-over per product that follows in this item (the last x of a tile has no consumer)
+                const bool last = d + 1 == n_steps;
+                // OUT_d: parameters of the feature -> x_d  (steps with col < 0 only bring in the hidden units that depend
+                // on conditioning features alone: no feature to invert, the hand-over at the start of the item released them)
+                if (st.col >= 0) {
                 mbar_wait(&sm->acc_full, acc_par, p.error, 8);
                 acc_par ^= 1u;
                 tc_fence_after();
@@ -426,10 +452,9 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_inv_kernel(const __grid
                     tmem_st1(lane_addr + A0_COL + (ic >> 1), q);
                     tmem_st_wait();
                 }
-                // one hand-over per product that follows in this item (the last x of a tile has no consumer)
-                const bool last = d + 1 == n_steps;
                 tc_fence_before();
                 if (st.h1_n != 0 || st.h2_n != 0 || !last) mbar_arrive(&sm->a_ready);
+                }
                 // H1_d, H2_d: the hidden units of this degree -> A operands (up to 15 units, 8 pair columns; the
                 // padding rows of the block give exact zeros, which is what the not-yet-known units must hold)
 #pragma unroll
@@ -531,6 +556,7 @@ extern "C" int tfepb_maf_spline_inverse_bf16(const tfepb_fused_inv_args* a, tfep
         d.n_ops = s.n_ops; d.n_steps = s.n_steps;
         d.min_bin = s.min_bin_size; d.min_slope = s.min_slope; d.slope_offset2 = s.slope_offset * tc::LOG2E;
         d.emb_lower = s.emb_lower; d.emb_scale = s.emb_scale;
+        d.init_map = s.init_map;
     }
     const size_t smem = finv::smem_bytes(p);
     TFEPB_CHECK_ARG(smem <= 227 * 1024, "shared memory plan of %zu bytes exceeds 227 KB", smem);
