@@ -438,12 +438,16 @@ int tfepb_mt19937_indices(uint32_t* state625_dev, int64_t count, uint32_t max_id
  * stream when idx == NULL) out_sums[r] = sum_j e[idx[r, j]] in double, where e_i = exp(v_i - max)
  * was produced by tfepb_exp_table.  analysis/bootstrap.py:185-233 with statistic = fep_estimator.
  * `e` holds the n entries [shard_lo, shard_lo + n) of the global table (shard_lo = 0, n = everything on
- * one GPU); draws outside the shard contribute zero, so the sums of batch-sharded ranks add up. */
+ * one GPU); draws outside the shard contribute zero, so the sums of batch-sharded ranks add up.
+ * `sample_sizes` (device, n_resamples entries, Philox stream only) or NULL: per-resample number of draws, at most
+ * `sample_size` -- stratified resampling: a resample of n uniform draws is the same as Multinomial(n; tile sizes / n)
+ * counts per table tile plus that many uniform draws INSIDE each tile, so each call can work on an L2-resident
+ * tile (e + its max_idx = the tile) and no draw is generated twice. */
 int tfepb_exp_table(int32_t dtype, const void* w, int64_t n, double scale, const double* max_dev,
                     float* e, tfepb_stream_t stream);
 int tfepb_bootstrap_sums(const float* e, int64_t n, int64_t shard_lo, uint32_t max_idx, const int32_t* idx, int64_t ldidx,
                          int32_t n_resamples, int64_t sample_size, uint64_t philox_seed,
-                         uint64_t philox_offset, double* out_sums, tfepb_stream_t stream);
+                         uint64_t philox_offset, const int64_t* sample_sizes, double* out_sums, tfepb_stream_t stream);
 /* Bayesian bootstrap of the FEP estimator (analysis/bootstrap.py:236-262, estimator.py:78-79): per resample r
  * out_sums[r] = sum_i e[i] g_ri and out_weight_sums[r] = sum_i g_ri with g_ri ~ Exp(1) from Philox4x32-10
  * (counter = philox_offset + r * ceil(n / 4) + i / 4), i.e. Dirichlet(1, ..., 1) weights g_ri / sum_i g_ri.

@@ -112,6 +112,35 @@ def test_philox_bootstrap_is_statistically_equivalent():
     assert 0.85 < float(b['standard_deviation']) / float(a['standard_deviation']) < 1.18
 
 
+def test_philox_bootstrap_over_l2_tiles(monkeypatch):
+    """Tables larger than the L2 tile are resampled cell by cell: Multinomial counts of draws per cell (host, exact)
+    plus uniform draws inside each cell.  Same distribution as uniform draws over the whole table: checked against
+    the reference-stream bootstrap; the counts conserve the number of draws."""
+    from tfep_b200.analysis import bootstrap, fep_estimator
+    import sys
+    mod = sys.modules['tfep_b200.analysis.bootstrap']
+    w = cases.normal((200000,), 5).to(DEV)
+    R = 2000
+    a = bootstrap(w, fep_estimator, n_resamples=R, batch=100, generator=torch.Generator().manual_seed(1))
+    monkeypatch.setattr(mod, 'L2_TILE_ENTRIES', 30000)
+    cells = mod.table_cells(0, 200000)
+    assert len(cells) == 7 and cells[0][0] == 0 and cells[-1][1] == 200000
+    counts = mod.stratified_counts(50, 200000, cells, 200000, seed=7)
+    assert counts.shape == (50, 7) and (counts.sum(axis=1) == 200000).all()
+    b = bootstrap(w, fep_estimator, n_resamples=R, generator=torch.Generator().manual_seed(1), rng='philox')
+    c = bootstrap(w, fep_estimator, n_resamples=R, generator=torch.Generator().manual_seed(1), rng='philox')
+    assert float(b['mean']) == float(c['mean'])                      # deterministic given the generator
+    assert abs(float(a['mean']) - float(b['mean'])) < 5 * 2 ** 0.5 * float(a['standard_deviation']) / R ** 0.5
+    assert 0.85 < float(b['standard_deviation']) / float(a['standard_deviation']) < 1.18
+    # take_first_only sweeps: the table is the first S entries
+    d = bootstrap(w, fep_estimator, n_resamples=200, bootstrap_sample_size=[50000, 120000], take_first_only=True,
+                  generator=torch.Generator().manual_seed(3), rng='philox')
+    e = bootstrap(w, fep_estimator, n_resamples=200, batch=50, bootstrap_sample_size=[50000, 120000], take_first_only=True,
+                  generator=torch.Generator().manual_seed(3))
+    for x, y in zip(d, e):
+        assert abs(float(x['mean']) - float(y['mean'])) < 6 * 2 ** 0.5 * float(y['standard_deviation']) / 200 ** 0.5
+
+
 def test_bayesian_bootstrap_statistical_parity():
     """Bayesian bootstrap (Dirichlet(1..1) weights; reference bootstrap.py:236-262).  The reference draws the
     weights from the global generator, so parity is statistical: the fused streaming kernel, the generic

@@ -142,7 +142,7 @@ SYMBOLS = {
     'tfepb_exp_table': (c_int32, [c_int32, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p]),
     'tfepb_bayesian_bootstrap_sums': (c_int32, [c_void_p, c_int64, c_int32, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p]),
     'tfepb_bootstrap_sums': (c_int32, [c_void_p, c_int64, c_int64, c_uint32, c_void_p, c_int64, c_int32, c_int64, c_uint64,
-                                       c_uint64, c_void_p, c_void_p]),
+                                       c_uint64, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

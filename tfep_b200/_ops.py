@@ -291,14 +291,17 @@ def exp_table(w, scale, max_dev):
     return e
 
 
-def bootstrap_sums(e, max_idx, n_resamples, sample_size, idx=None, philox_seed=0, philox_offset=0, shard_lo=0):
-    """Per-resample sums of the exp table ``e`` (the shard starting at global index ``shard_lo``)."""
-    require_cuda(e, idx)
+def bootstrap_sums(e, max_idx, n_resamples, sample_size, idx=None, philox_seed=0, philox_offset=0, shard_lo=0,
+                   sample_sizes=None):
+    """Per-resample sums of the exp table ``e`` (the shard starting at global index ``shard_lo``).  ``sample_sizes``:
+    optional int64 device tensor with the number of draws of every resample (Philox stream; at most ``sample_size``)."""
+    require_cuda(e, idx, sample_sizes)
     out = torch.empty(n_resamples, dtype=torch.float64, device=e.device)
     with torch.cuda.device(e.device):
         check(_lib.load().tfepb_bootstrap_sums(ptr(e), e.numel(), int(shard_lo), int(max_idx), ptr(idx),
                                                0 if idx is None else idx.stride(0), int(n_resamples), int(sample_size),
-                                               int(philox_seed), int(philox_offset), ptr(out), stream_ptr(e)))
+                                               int(philox_seed), int(philox_offset), ptr(sample_sizes), ptr(out),
+                                               stream_ptr(e)))
     return out
 
 

@@ -5,9 +5,13 @@ Every sample is independent through the flow, so nothing is exchanged until the 
 
 * estimator: each rank reduces its shard to ``(max, sum exp(v - max))`` with the single-pass kernel; ONE
   all-gather of 2 doubles per rank and a rescale combine them (``combine_lse_partials``);
-* bootstrap: every rank walks the SAME global index stream (the reference's MT19937 stream, or Philox) and
-  sums the draws that fall into its shard against its own exp table; the per-resample sums are rescaled to the
-  global maximum and added with ONE all-reduce of ``n_resamples`` doubles (``combine_bootstrap_sums``).
+* bootstrap, reference index stream (MT19937): every rank walks the SAME global stream and sums the draws that fall
+  into its shard against its own exp table;
+* bootstrap, Philox: the shards are cut into L2-sized cells, every rank draws the same Multinomial counts of
+  draws per cell (same seed) and generates only the draws of its own cells (``stratified_counts``) -- no draw is
+  generated twice, so the work divides by the number of ranks;
+* either way the per-resample sums are rescaled to the global maximum and added with ONE all-reduce of
+  ``n_resamples`` doubles (``combine_bootstrap_sums``).
 
 The collective helpers work on CPU tensors with the gloo backend too (that is how the host logic is tested
 without GPUs); the local reductions are CUDA kernels.
@@ -17,7 +21,8 @@ import torch
 import torch.distributed as dist
 
 from .. import _ops
-from .bootstrap import _fused_kT, _generator_to_state, _state_to_generator
+from .bootstrap import (_fused_kT, _generator_to_state, _state_to_generator, philox_cell_sums, stratified_counts,
+                        table_cells)
 from .estimator import _log_n, combine_partials
 
 
@@ -52,6 +57,29 @@ def _total(n_local, device, group):
     return int(t.item())
 
 
+def shard_cells(shard_offset, shard_len, n_total, device, group=None):
+    """The L2-sized cells of every rank's shard, in global index order, and the rank owning each: ``(cells, owner)``.
+    One all-gather of two integers per rank."""
+    mine = torch.tensor([shard_offset, shard_len], dtype=torch.int64, device=device)
+    if _world(group) > 1:
+        parts = [torch.empty_like(mine) for _ in range(_world(group))]
+        dist.all_gather(parts, mine, group=group)
+        shards = [(int(p[0]), int(p[1]), r) for r, p in enumerate(torch.stack(parts).cpu())]
+    else:
+        shards = [(int(shard_offset), int(shard_len), 0)]
+    cells, owner, pos = [], [], 0
+    for off, ln, r in sorted(shards):
+        if off != pos:
+            raise ValueError('the shards of the ranks must tile [0, n_total) without gaps or overlaps')
+        cs = table_cells(off, off + ln) if ln > 0 else []
+        cells += cs
+        owner += [r] * len(cs)
+        pos = off + ln
+    if pos != n_total:
+        raise ValueError('the shards of the ranks must tile [0, n_total) without gaps or overlaps')
+    return cells, owner
+
+
 def fep_estimator_sharded(work_shard, kT=1.0, group=None):
     """``-kT logsumexp(-w / kT - log n)`` over the union of all ranks' shards (same value on every rank)."""
     m, s = combine_lse_partials(_ops.lse(work_shard, -1.0 / kT), group)
@@ -73,10 +101,11 @@ def bootstrap_statistics_sharded(work_shard, shard_offset, n_total, kT=1.0, n_re
     sums = torch.empty(n_resamples, dtype=torch.float64, device=dev)
     if rng == 'philox':
         seed = int(torch.randint(0, 2**62, (1,), generator=generator).item())
-        for k in range(0, n_resamples, 65535):
-            nb = min(65535, n_resamples - k)
-            sums[k:k + nb] = _ops.bootstrap_sums(e, n_total, nb, n_total, None, seed, k * ((n_total + 3) // 4),
-                                                 shard_lo=shard_offset)
+        cells, owner = shard_cells(shard_offset, work_shard.numel(), n_total, dev, group)
+        counts = stratified_counts(n_resamples, n_total, cells, n_total, seed)
+        rank = dist.get_rank(group) if _world(group) > 1 else 0
+        sums = philox_cell_sums(e, shard_offset, cells, [i for i, o in enumerate(owner) if o == rank], counts, seed,
+                                n_resamples, n_total)
     else:
         gen = torch.default_generator if generator is None else generator
         state = _generator_to_state(gen).to(dev)

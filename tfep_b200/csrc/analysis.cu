@@ -227,9 +227,17 @@ __global__ void __launch_bounds__(BS_THREADS) bootstrap_sums_kernel(const float*
                                                                     const int32_t* __restrict__ idx, int64_t ldidx,
                                                                     int64_t sample_size, uint64_t seed, uint64_t offset,
                                                                     uint32_t shard_lo, uint32_t shard_len,
+                                                                    const int64_t* __restrict__ sizes,
                                                                     double* __restrict__ out) {
     const int r = blockIdx.y;
     const int64_t j0 = (int64_t)blockIdx.x * BS_CHUNK;
+    // per-resample number of draws (stratified resampling: multinomial counts per table tile); the Philox counters
+    // keep the stride of the largest one
+    const int64_t stride4 = (sample_size + 3) / 4;
+    if (sizes != nullptr) {
+        sample_size = sizes[r];
+        if (j0 >= sample_size) return;
+    }
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
     if (idx != nullptr) {
         const int32_t* row = idx + (int64_t)r * ldidx;
@@ -248,7 +256,7 @@ __global__ void __launch_bounds__(BS_THREADS) bootstrap_sums_kernel(const float*
             // 4 consecutive draws of this resample per Philox call
             const int64_t j = j0 + ((int64_t)k * BS_THREADS + threadIdx.x) * 4;
             if (j < sample_size) {
-                const uint64_t c = offset + ((uint64_t)r * (uint64_t)((sample_size + 3) / 4)) + (uint64_t)(j >> 2);
+                const uint64_t c = offset + ((uint64_t)r * (uint64_t)stride4) + (uint64_t)(j >> 2);
                 const uint4 u = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), key);
                 acc0 += shard_fetch(e, __umulhi(u.x, max_idx), shard_lo, shard_len);
                 if (j + 1 < sample_size) acc1 += shard_fetch(e, __umulhi(u.y, max_idx), shard_lo, shard_len);
@@ -434,8 +442,10 @@ extern "C" int tfepb_exp_table(int32_t dtype, const void* w, int64_t n, double s
 
 extern "C" int tfepb_bootstrap_sums(const float* e, int64_t n, int64_t shard_lo, uint32_t max_idx, const int32_t* idx,
                                     int64_t ldidx, int32_t n_resamples, int64_t sample_size, uint64_t philox_seed,
-                                    uint64_t philox_offset, double* out_sums, tfepb_stream_t stream) {
+                                    uint64_t philox_offset, const int64_t* sample_sizes, double* out_sums,
+                                    tfepb_stream_t stream) {
     TFEPB_CHECK_ARG(e && out_sums, "null buffer");
+    TFEPB_CHECK_ARG(sample_sizes == nullptr || idx == nullptr, "per-resample sizes go with the Philox stream only");
     TFEPB_CHECK_ARG(n_resamples > 0 && sample_size > 0, "bad sizes");
     TFEPB_CHECK_ARG(max_idx > 0 && shard_lo >= 0 && n > 0 && n <= 0x7fffffff, "index range out of bounds");
     TFEPB_CHECK_ARG(n_resamples <= 65535, "at most 65535 resamples per call");
@@ -444,7 +454,7 @@ extern "C" int tfepb_bootstrap_sums(const float* e, int64_t n, int64_t shard_lo,
     TFEPB_CUDA(cudaMemsetAsync(out_sums, 0, sizeof(double) * n_resamples, s));
     dim3 grid((unsigned)((sample_size + BS_CHUNK - 1) / BS_CHUNK), (unsigned)n_resamples);
     bootstrap_sums_kernel<<<grid, BS_THREADS, 0, s>>>(e, max_idx, idx, ldidx, sample_size, philox_seed, philox_offset,
-                                                      (uint32_t)shard_lo, (uint32_t)n, out_sums);
+                                                      (uint32_t)shard_lo, (uint32_t)n, sample_sizes, out_sums);
     return check_launch("bootstrap_sums");
 }
 
