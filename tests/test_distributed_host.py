@@ -48,7 +48,20 @@ def _worker(rank, world, port, n, kT, out):
         stats = (-kT * (gmax + torch.log(gs) - _log_n(n))).float()
         ref_stats = ao.bootstrap_statistics(w, lambda d, vectorized=False: ao.fep_estimator(d, kT=kT, vectorized=vectorized),
                                             R, generator=torch.Generator().manual_seed(7))
-        out.put((rank, float((df - ref).abs()), float((stats - ref_stats).abs().max())))
+        # stratified Philox bootstrap: every rank derives the same cells / owners / multinomial counts
+        import tfep_b200.analysis.bootstrap  # noqa: F401
+        bmod = sys.modules['tfep_b200.analysis.bootstrap']
+        bmod.L2_TILE_ENTRIES = 700
+        cells, owner = D.shard_cells(lo, hi - lo, n, 'cpu')
+        counts = bmod.stratified_counts(R, n, cells, n, seed=99)
+        ok = (cells[0][0] == 0 and cells[-1][1] == n and all(a[1] == b[0] for a, b in zip(cells, cells[1:]))
+              and all(b - a <= 700 for a, b in cells) and sorted(set(owner)) == [0, 1]
+              and all(lo <= a and b <= hi for (a, b), o in zip(cells, owner) if o == rank)
+              and bool((counts.sum(axis=1) == n).all()))
+        gathered = [None, None]
+        dist.all_gather_object(gathered, (cells, owner, counts.tolist()))
+        ok = ok and gathered[0] == gathered[1]
+        out.put((rank, float((df - ref).abs()), float((stats - ref_stats).abs().max()), ok))
     finally:
         dist.destroy_process_group()
 
@@ -65,8 +78,9 @@ def test_two_rank_estimator_and_bootstrap_match_single_process(kT):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, err_df, err_boot in res:
+    for rank, err_df, err_boot, cells_ok in res:
         assert err_df < 2e-6 and err_boot < 2e-6, (rank, err_df, err_boot)
+        assert cells_ok, rank
 
 
 def test_combine_partials_is_order_and_split_invariant():
