@@ -276,6 +276,8 @@ typedef struct {
                                             (PeriodicEmbedding fused into the operand staging, reference
                                             nn/embeddings/mafembed.py:112-142), 3 the constant one, 4 zero */
     float emb_lower, emb_scale;          /* emb_scale = 2 pi / (upper - lower) */
+    int32_t hidden_split[2];             /* this layer's split of the two hidden layers (see tfepb_fused_args); 0 = the
+                                            chain-wide value */
 } tfepb_fused_layer;
 
 typedef struct {
@@ -345,7 +347,7 @@ typedef struct {
     int32_t batch, n_features;
     int32_t k1, hidden_padded;
     int32_t n_layers;
-    int32_t reserved;                              /* mixed_splines: 1 if any step has the not-circular kind bit */
+    int32_t mixed_splines;                         /* 1 if any step has the not-circular kind bit (generic spline epilogue) */
     const tfepb_fused_inv_layer* layers;           /* HOST array of n_layers entries */
     uint32_t* tile_flags;                          /* as for the forward kernel */
     uint32_t epoch;

@@ -283,6 +283,9 @@ def test_conditioning_features(cfg, D):
         xe, lde = seq[0].inverse(y)                  # exact sweep of the same y
         seq[0].precision = 'bf16'
         assert float(_circ(xi, xe).mean()) < 2e-3 and float((ldi - lde).abs().mean()) < 8e-3
+        from tfep_b200 import _fused
+        plans = [maf._fused_plan() for maf in seq]
+        assert _fused.chain_compatible(plans)        # one launch even where the layers split their hidden layers differently
         yc, ldc = seq(x)
         cur, tot = x, None
         for maf in seq:

@@ -465,11 +465,11 @@ _EPOCH = [0]
 
 
 def _chain_key(pl):
-    return (pl.D, pl.Din, pl.K1, pl.HP, pl.halves, pl.hidden_split)
+    return (pl.D, pl.Din, pl.K1, pl.HP, pl.halves)
 
 
 def chain_compatible(plans):
-    """One launch serves a chain of layers only if they share the widths and the hidden-layer split."""
+    """One launch serves a chain of layers only if they share the widths (the split of the hidden layers is per layer)."""
     return all(_chain_key(pl) == _chain_key(plans[0]) for pl in plans)
 
 
@@ -507,7 +507,8 @@ def run_chain(plans_mafs, x, debug_params=None):
                                     weights=packed.data_ptr(), feats=tb['feats'].data_ptr(), min_bin_size=pl.min_bin,
                                     min_slope=pl.min_slope, slope_offset=pl.slope_offset, reserved=0,
                                     input_map=None if tb['input_map'] is None else tb['input_map'].data_ptr(),
-                                    emb_lower=pl.emb_lower, emb_scale=pl.emb_scale)
+                                    emb_lower=pl.emb_lower, emb_scale=pl.emb_scale,
+                                    hidden_split=(ctypes.c_int32 * 2)(*pl.hidden_split))
     tb = first._tables(x.device)
     flags = None
     if n_layers > 1:
@@ -577,7 +578,7 @@ def run_inverse_chain(plans_mafs, y):
         flags.zero_()
     args = _lib.FusedInvArgs(y=y.data_ptr(), x=x.data_ptr(), logdet=ld.data_ptr(), batch=B, n_features=first.D,
                              k1=first.K1, hidden_padded=first.HP, n_layers=n_layers,
-                             reserved=int(any(pl.mixed for pl, _ in plans_mafs)), layers=layers,
+                             mixed_splines=int(any(pl.mixed for pl, _ in plans_mafs)), layers=layers,
                              tile_flags=None if flags is None else flags.data_ptr(), epoch=_EPOCH[0], n_inputs=first.Din,
                              error_flag=tb['err'].data_ptr())
     with torch.cuda.device(y.device):

@@ -67,7 +67,7 @@ class TxGrads(Structure):
 class FusedLayer(Structure):
     _fields_ = [('ops', c_void_p), ('n_ops', c_int32), ('n_chunks', c_int32), ('weights', c_void_p), ('feats', c_void_p),
                 ('min_bin_size', c_float), ('min_slope', c_float), ('slope_offset', c_float), ('reserved', c_int32),
-                ('input_map', c_void_p), ('emb_lower', c_float), ('emb_scale', c_float)]
+                ('input_map', c_void_p), ('emb_lower', c_float), ('emb_scale', c_float), ('hidden_split', c_int32 * 2)]
 
 
 class FusedArgs(Structure):
@@ -85,7 +85,7 @@ class FusedInvLayer(Structure):
 
 class FusedInvArgs(Structure):
     _fields_ = [('y', c_void_p), ('x', c_void_p), ('logdet', c_void_p), ('batch', c_int32), ('n_features', c_int32),
-                ('k1', c_int32), ('hidden_padded', c_int32), ('n_layers', c_int32), ('reserved', c_int32),
+                ('k1', c_int32), ('hidden_padded', c_int32), ('n_layers', c_int32), ('mixed_splines', c_int32),
                 ('layers', POINTER(FusedInvLayer)), ('tile_flags', c_void_p), ('epoch', c_uint32), ('n_inputs', c_int32),
                 ('error_flag', c_void_p)]
 

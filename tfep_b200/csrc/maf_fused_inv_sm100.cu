@@ -560,7 +560,7 @@ extern "C" int tfepb_maf_spline_inverse_bf16(const tfepb_fused_inv_args* a, tfep
     }
     const size_t smem = finv::smem_bytes(p);
     TFEPB_CHECK_ARG(smem <= 227 * 1024, "shared memory plan of %zu bytes exceeds 227 KB", smem);
-    const bool mixed = a->reserved != 0;           // `reserved` = mixed_splines: some features are not circular
+    const bool mixed = a->mixed_splines != 0;      // some features are not circular: generic spline epilogue
     auto kernel = mixed ? finv::maf_spline_inv_kernel<true> : finv::maf_spline_inv_kernel<false>;
     static thread_local size_t configured[2] = {0, 0};
     if (configured[mixed] < smem) {

@@ -99,6 +99,7 @@ struct LayerP {
     float min_bin, min_slope, slope_offset2;   // slope_offset2 = log2(e) * log(exp(1 - min_slope) - 1)
     const int* input_map;       // NULL, or per conditioner input column: x column | what enters << 16 (tfepb_fused_layer)
     float emb_lower, emb_scale;
+    int hsplit[2];              // first column of the second half, per hidden layer (multiple of 16)
 };
 
 struct Params {
@@ -108,7 +109,6 @@ struct Params {
     int HP;                     // hidden width (+2) padded to a multiple of 16
     int n_layers, n_tiles, feat_stride;   // feat_stride: feature slots reserved per layer in shared memory
     int n_halves;               // column halves of a hidden layer (1 or 2), each its own accumulator group and hand-over
-    int hsplit[2];              // first column of the second half, per hidden layer (multiple of 16)
     uint32_t* flags;            // (n_layers - 1) x n_tiles: == epoch once the tile of that layer is in y
     uint32_t epoch;
     int* error;                 // device int: set on watchdog timeout
@@ -524,8 +524,8 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
                     }
                     tc_fence_after();
                     trace<DEBUG>(p, 2, ts, 3010 + 2 * hl + half);
-                    const int cbeg = half == 0 ? 0 : p.hsplit[hl];
-                    const int cend = (half == 0 && p.n_halves == 2) ? p.hsplit[hl] : p.HP;
+                    const int cbeg = half == 0 ? 0 : L.hsplit[hl];
+                    const int cend = (half == 0 && p.n_halves == 2) ? L.hsplit[hl] : p.HP;
                     // 16 accumulator columns per step, two register sets in ping-pong: the load of the next step is
                     // in flight while this one is processed
                     uint32_t ra[16], rb[16];
@@ -650,10 +650,6 @@ extern "C" int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_st
                     "hidden width (padded) must be a multiple of 16 and at most 336 (tensor-memory plan)");
     TFEPB_CHECK_ARG(a->k1 <= 2 * (512 - fused::A_COL), "too many input features for the tensor-memory plan");
     TFEPB_CHECK_ARG(a->hidden_halves == 1 || a->hidden_halves == 2, "hidden_halves must be 1 or 2");
-    for (int i = 0; i < 2; ++i)
-        TFEPB_CHECK_ARG(a->hidden_halves == 1 || (a->hidden_split[i] % 16 == 0 && a->hidden_split[i] > 0 &&
-                                                   a->hidden_split[i] < a->hidden_padded),
-                        "hidden_split must be a multiple of 16 inside the hidden width");
     TFEPB_CHECK_ARG((a->n_features * 4 * fused::TILE_M) % 16 == 0, "tile of x must be a multiple of 16 bytes");
     TFEPB_CHECK_ARG(((uintptr_t)a->x % 16 == 0) && ((uintptr_t)a->y % 16 == 0), "x and y must be 16-byte aligned");
     if (int rc = require_sm100()) return rc;
@@ -677,12 +673,17 @@ extern "C" int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_st
         d.min_bin = s.min_bin_size; d.min_slope = s.min_slope; d.slope_offset2 = s.slope_offset * fused::LOG2E;
         TFEPB_CHECK_ARG(s.input_map != nullptr || n_inputs == a->n_features, "layer %d: n_inputs > n_features needs an input_map", l);
         d.input_map = s.input_map; d.emb_lower = s.emb_lower; d.emb_scale = s.emb_scale;
+        for (int i = 0; i < 2; ++i) {        // per-layer split, else the chain-wide one
+            d.hsplit[i] = s.hidden_split[i] > 0 ? s.hidden_split[i] : a->hidden_split[i];
+            TFEPB_CHECK_ARG(a->hidden_halves == 1 || (d.hsplit[i] % 16 == 0 && d.hsplit[i] > 0 && d.hsplit[i] < a->hidden_padded),
+                            "layer %d: hidden_split must be a multiple of 16 inside the hidden width", l);
+        }
         memcpy(p.ops + op_base, s.ops, sizeof(fused::Op) * (size_t)s.n_ops);
         op_base += s.n_ops;
         if (s.n_chunks * fused::FEATS_PER_CHUNK > feat_stride) feat_stride = s.n_chunks * fused::FEATS_PER_CHUNK;
     }
     p.feat_stride = feat_stride;
-    p.n_halves = a->hidden_halves; p.hsplit[0] = a->hidden_split[0]; p.hsplit[1] = a->hidden_split[1];
+    p.n_halves = a->hidden_halves;
     p.error = a->error_flag;
     p.debug_params = a->debug_params;
     p.debug_mode = a->debug_mode;
