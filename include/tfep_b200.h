@@ -204,11 +204,17 @@ typedef struct {
     void* out_image;                     /* NULL, or the bf16 image (block_rows = 128, k = n) of the result */
     const int32_t* k_block_ranges;       /* device, NULL or (ceil(n / 256), 2): [first, end) 64-wide k-blocks that are
                                             non-zero for each tile of 256 output columns (staircase masks) */
-    int32_t split_k, reserved;           /* > 1: the reduction is split over that many CTAs per tile */
+    int32_t split_k;                     /* > 1: the reduction is split over that many CTAs per tile */
+    int32_t out_image_t_rows;            /* block_rows of out_image_t: 128 (it will be an A operand) or 256 (a B operand) */
     int32_t* error_flag;
     const int32_t* row_ranges;           /* device, NULL or (ceil(n / 256), 2): rows [begin, end) of C that can be
                                             non-zero for each tile of 256 columns; tiles outside are skipped and
                                             left untouched (masked weight gradient into a zero-filled C) */
+    void* out_image_t;                   /* NULL, or the bf16 image of the TRANSPOSED result (rows = the n columns, k = the m
+                                            rows; entries with k >= m are zero): the operand the weight-gradient product
+                                            needs, written by the epilogue instead of a separate pack launch */
+    float* column_sums;                  /* NULL, or fp32 (n,), zero-filled by the caller: += sum over the m rows of the
+                                            result (the bias gradient of nn/masked.py:298-300 when the result is grad_y) */
 } tfepb_tc_gemm_args;
 int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream);
 

@@ -58,3 +58,20 @@ def test_backward_products_and_k_ranges():
     wm[256:, :128] = 0
     ref = _bf(x) @ _bf(wm).T
     assert float((c.double() - ref).abs().max()) < 3e-4 * (1 + float(ref.abs().max()))
+
+
+@pytest.mark.parametrize('m,n,k,rows', [(1000, 670, 300, 256), (257, 300, 670, 128), (5, 7, 9, 256), (4096, 1500, 128, 128)])
+def test_transposed_image_and_column_sums_from_the_epilogue(m, n, k, rows):
+    """The epilogue can also emit the image of the TRANSPOSED result (the operand of the weight-gradient product) and
+    the column sums (the bias gradient): bit-identical to packing the fp32 result, sums equal to the row sum."""
+    x, w, b, h = _rand((m, k), 21), _rand((n, k), 22) / k ** 0.5, _rand((n,), 23), _rand((m, n), 24)
+    ai, bi = _ops.tc_pack(x, 128), _ops.tc_pack(w, 256)
+    for kw in (dict(bias=b, activation=_ops.ACT_ELU), dict(aux=h)):
+        c, img, img_t, sums = _ops.tc_gemm(ai, bi, m, n, k, c=True, out_image=True, out_image_t=rows, column_sums=True, **kw)
+        assert torch.equal(img_t, _ops.tc_pack(c, rows, transpose=True))
+        ref = c.double().sum(dim=0)
+        assert float((sums.double() - ref).abs().max()) < 1e-5 * (1 + float(c.abs().sum(dim=0).max()))
+        # without the fp32 result
+        _, _, img_t2, sums2 = _ops.tc_gemm(ai, bi, m, n, k, out_image_t=rows, column_sums=True, **kw)
+        assert torch.equal(img_t2, img_t)
+        assert float((sums2 - sums).abs().max()) < 1e-5 * (1 + float(c.abs().sum(dim=0).max()))

@@ -94,7 +94,8 @@ class TcGemmArgs(Structure):
     _fields_ = [('a_image', c_void_p), ('b_image', c_void_p), ('m', c_int32), ('n', c_int32), ('k', c_int32),
                 ('activation', c_int32), ('c', c_void_p), ('ldc', c_int64), ('bias', c_void_p), ('aux', c_void_p),
                 ('ldaux', c_int64), ('out_image', c_void_p), ('k_block_ranges', c_void_p), ('split_k', c_int32),
-                ('reserved', c_int32), ('error_flag', c_void_p), ('row_ranges', c_void_p)]
+                ('out_image_t_rows', c_int32), ('error_flag', c_void_p), ('row_ranges', c_void_p),
+                ('out_image_t', c_void_p), ('column_sums', c_void_p)]
 
 
 class SweepArgs(Structure):

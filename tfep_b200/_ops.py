@@ -354,9 +354,11 @@ def tc_pack(src, block_rows, transpose=False, out=None):
 
 
 def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, aux=None, out_image=False,
-            k_block_ranges=None, row_ranges=None, split_k=1, error_flag=None):
+            k_block_ranges=None, row_ranges=None, split_k=1, error_flag=None, out_image_t=None, column_sums=False):
     """C = act(A B^T + bias) [* ELU'(aux)] from operand images; returns (c, out_img).  ``c``: True to allocate, a
-    tensor to write into (zero-filled by the caller when split_k > 1), None for no fp32 output."""
+    tensor to write into (zero-filled by the caller when split_k > 1), None for no fp32 output.
+    ``out_image_t`` = 128 / 256: also the image of the transposed result with that block_rows; ``column_sums``: also
+    the sums over the m rows; with either, returns (c, out_img, out_img_t, column_sums)."""
     lib = _lib.load()
     dev = a_img.device
     if c is True:
@@ -365,16 +367,25 @@ def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, au
     img = None
     if out_image:
         img = torch.empty(lib.tfepb_tc_image_bytes(m, n, 128), dtype=torch.uint8, device=dev)
+    img_t = None
+    if out_image_t:
+        img_t = torch.empty(lib.tfepb_tc_image_bytes(n, m, int(out_image_t)), dtype=torch.uint8, device=dev)
+    sums = torch.zeros(n, dtype=torch.float32, device=dev) if column_sums else None
     a = _lib.TcGemmArgs(a_image=a_img.data_ptr(), b_image=b_img.data_ptr(), m=m, n=n, k=k, activation=activation,
                         c=None if c is None else c.data_ptr(), ldc=0 if c is None else _ld(c),
                         bias=None if bias is None else bias.data_ptr(),
                         aux=None if aux is None else aux.data_ptr(), ldaux=0 if aux is None else _ld(aux),
                         out_image=None if img is None else img.data_ptr(),
                         k_block_ranges=None if k_block_ranges is None else k_block_ranges.data_ptr(),
-                        split_k=int(split_k), reserved=0, error_flag=None if error_flag is None else error_flag.data_ptr(),
-                        row_ranges=None if row_ranges is None else row_ranges.data_ptr())
+                        split_k=int(split_k), out_image_t_rows=int(out_image_t or 0),
+                        error_flag=None if error_flag is None else error_flag.data_ptr(),
+                        row_ranges=None if row_ranges is None else row_ranges.data_ptr(),
+                        out_image_t=None if img_t is None else img_t.data_ptr(),
+                        column_sums=None if sums is None else sums.data_ptr())
     with torch.cuda.device(dev):
         check(lib.tfepb_tc_gemm(ctypes.byref(a), stream_ptr(a_img)))
+    if out_image_t or column_sums:
+        return c, img, img_t, sums
     return c, img
 
 
@@ -392,18 +403,27 @@ class MadeFunctionTC(torch.autograd.Function):
     def forward(ctx, x, n_layers, kb_fwd, kb_bwd, rr_w, *wb):
         ws, bs = wb[:n_layers], wb[n_layers:]
         B = x.shape[0]
-        acts = [x]
+        train = any(ctx.needs_input_grad[5:5 + 2 * n_layers])      # weight gradients wanted: keep transposed images
+        acts, acts_t = [x], [None]
         img = tc_pack(x, 128)
         h = x
         for l in range(n_layers):
             last = l == n_layers - 1
             N, K = ws[l].shape
             wimg = tc_pack(ws[l], 256)
-            h, img = tc_gemm(img, wimg, B, N, K, c=True, bias=bs[l], activation=ACT_NONE if last else ACT_ELU,
-                             out_image=not last, k_block_ranges=None if kb_fwd is None else kb_fwd[l])
+            if train and not last:
+                # the epilogue also writes the image of h^T: the B operand of the next layer's weight gradient
+                h, img, img_t, _ = tc_gemm(img, wimg, B, N, K, c=True, bias=bs[l], activation=ACT_ELU, out_image=True,
+                                           out_image_t=256, k_block_ranges=None if kb_fwd is None else kb_fwd[l])
+                acts_t.append(img_t)
+            else:
+                h, img = tc_gemm(img, wimg, B, N, K, c=True, bias=bs[l], activation=ACT_NONE if last else ACT_ELU,
+                                 out_image=not last, k_block_ranges=None if kb_fwd is None else kb_fwd[l])
+                acts_t.append(None)
             if not last:
                 acts.append(h)
         ctx.save_for_backward(*acts, *ws)
+        ctx.acts_t = acts_t[:n_layers]
         ctx.n_layers = n_layers
         ctx.kb_bwd = kb_bwd
         ctx.rr_w = rr_w
@@ -417,6 +437,9 @@ class MadeFunctionTC(torch.autograd.Function):
         B = grad_out.shape[0]
         g = _rows(grad_out.contiguous())
         gimg = tc_pack(g, 128)
+        # image of g^T (A operand of the weight gradient) and the bias gradient: packed / summed here for the top layer,
+        # written by the epilogue of the backward-input product for the layers below
+        gimg_t, gb = None, None
         gws, gbs = [None] * L, [None] * L
         gx = None
         n_sm = torch.cuda.get_device_properties(g.device).multi_processor_count
@@ -426,15 +449,25 @@ class MadeFunctionTC(torch.autograd.Function):
                 # dW[N x K] = dY^T X: reduction over the batch, split so that the grid fills the machine
                 tiles = ((N + 127) // 128) * ((K + 255) // 256)
                 split = max(1, min((B + 63) // 64, (2 * n_sm + tiles - 1) // tiles))
-                gws[l], _ = tc_gemm(tc_pack(g, 128, transpose=True), tc_pack(acts[l], 256, transpose=True), N, K, B,
-                                    c=True, split_k=split, row_ranges=None if ctx.rr_w is None else ctx.rr_w[l])
-                gbs[l] = g.sum(dim=0)
+                a_t = gimg_t if gimg_t is not None else tc_pack(g, 128, transpose=True)
+                b_t = ctx.acts_t[l] if ctx.acts_t[l] is not None else tc_pack(acts[l], 256, transpose=True)
+                gws[l], _ = tc_gemm(a_t, b_t, N, K, B, c=True, split_k=split,
+                                    row_ranges=None if ctx.rr_w is None else ctx.rr_w[l])
+                gbs[l] = gb if gb is not None else g.sum(dim=0)
+            gimg_t, gb = None, None
             if l > 0 or ctx.needs_input_grad[0]:
                 wt = tc_pack(ws[l], 256, transpose=True)            # rows = inputs of the layer, k = its outputs
-                g, gimg = tc_gemm(gimg, wt, B, K, N, c=True, aux=acts[l] if l > 0 else None, out_image=l > 0,
-                                  k_block_ranges=None if ctx.kb_bwd is None else ctx.kb_bwd[l])
+                below = l > 0 and (ctx.needs_input_grad[5 + l - 1] or ctx.needs_input_grad[5 + L + l - 1])
+                if below:
+                    g, gimg, gimg_t, gb = tc_gemm(gimg, wt, B, K, N, c=True, aux=acts[l], out_image=True, out_image_t=128,
+                                                  column_sums=True,
+                                                  k_block_ranges=None if ctx.kb_bwd is None else ctx.kb_bwd[l])
+                else:
+                    g, gimg = tc_gemm(gimg, wt, B, K, N, c=True, aux=acts[l] if l > 0 else None, out_image=l > 0,
+                                      k_block_ranges=None if ctx.kb_bwd is None else ctx.kb_bwd[l])
                 if l == 0:
                     gx = g
+        ctx.acts_t = None
         return (gx, None, None, None, None, *gws, *gbs)
 
 

@@ -43,6 +43,9 @@ struct Params {
     int act;                            // TFEPB_ACT_*
     const float* aux; int64_t ldaux;    // multiply by ELU'(aux) = (h > 0 ? 1 : h + 1), or null
     uint8_t* out_img; int out_k_blocks; // bf16 image (128-row blocks, k = column index) of the result, or null
+    uint8_t* out_img_t;                 // bf16 image of the transposed result (rows = columns of C, k = rows of C), or null
+    int t_rows, t_k_blocks, t_rows_padded;   // its block_rows (128 / 256), ceil(M / 64), rows rounded up to block_rows
+    float* colsum;                      // (N,) += column sums of the result, or null
     const int* kranges;                 // per n-tile: [first, end) k-block, or null
     const int* row_ranges;              // per n-tile: rows [begin, end) of C that can be non-zero; other tiles are skipped, or null
     int atomic;                         // atomicAdd into C (split-K)
@@ -188,7 +191,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             for (int sub = 0; sub < 2; ++sub) {
                 const int scol = cgroup * 64 + sub * 32;       // first column of the sub-tile inside the tile
                 const int gns = tn * BN + scol;
-                if (gns >= p.N && p.out_img == nullptr) continue;      // warp-uniform
+                if (gns >= p.N && p.out_img == nullptr && (p.out_img_t == nullptr || gns >= p.t_rows_padded)) continue;   // warp-uniform
                 if (p.aux != nullptr && !p.atomic) {
                     // coalesced load of the 32 x 32 ELU' operand: lane = column, transposed into the buffer
 #pragma unroll 8
@@ -242,7 +245,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                                 if (gn0 + i >= p.N) v[i] = 0.f;
                         }
                     }
-                    if (p.C != nullptr) {
+                    if (p.C != nullptr || p.out_img_t != nullptr || p.colsum != nullptr) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) xp[(c16 * 16 + i) * XP_LD + lane] = v[i];
                     }
@@ -260,6 +263,34 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                             *reinterpret_cast<uint4*>(blk + (size_t)(slab + 1) * 2048) = q1;
                         }
                     }
+                }
+                if (p.out_img_t != nullptr || p.colsum != nullptr) {
+                    // lane = column of C = row of the transposed image; its 32 k-values (rows gm0 .. gm0 + 31 of C) are
+                    // four 16-byte chunks of consecutive slabs, and consecutive lanes write consecutive chunks
+                    __syncwarp();
+                    const int n = gns + lane;
+                    const int nrows = min(32, p.M - gm0);              // rows beyond M carry the bias only: zero them
+                    float cs = 0.f;
+                    uint32_t q[16];
+#pragma unroll
+                    for (int r = 0; r < 32; r += 2) {
+                        const float v0 = r < nrows ? xp[lane * XP_LD + r] : 0.f;
+                        const float v1 = r + 1 < nrows ? xp[lane * XP_LD + r + 1] : 0.f;
+                        cs += v0 + v1;
+                        q[r >> 1] = pack_bf16(v0, v1);
+                    }
+                    if (p.out_img_t != nullptr && n < p.t_rows_padded && (gm0 >> 6) < p.t_k_blocks) {
+                        const size_t block_bytes = (size_t)p.t_rows * 128;
+                        uint8_t* blk = p.out_img_t + ((size_t)(n / p.t_rows) * p.t_k_blocks + (gm0 >> 6)) * block_bytes +
+                                       (size_t)(n % p.t_rows) * 16;
+                        const int slab0 = (gm0 & 63) >> 3;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4*>(blk + (size_t)(slab0 + j) * p.t_rows * 16) =
+                                make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
+                    }
+                    if (p.colsum != nullptr && n < p.N) atomicAdd(p.colsum + n, cs);
+                    if (p.C == nullptr) __syncwarp();
                 }
                 if (p.C != nullptr) {
                     __syncwarp();
@@ -361,9 +392,13 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
     TFEPB_CHECK_ARG(a != nullptr, "null argument struct");
     TFEPB_CHECK_ARG(a->a_image && a->b_image, "null operand image");
     TFEPB_CHECK_ARG(a->m > 0 && a->n > 0 && a->k > 0, "bad sizes");
-    TFEPB_CHECK_ARG(a->c != nullptr || a->out_image != nullptr, "no output");
+    TFEPB_CHECK_ARG(a->c != nullptr || a->out_image != nullptr || a->out_image_t != nullptr, "no output");
+    TFEPB_CHECK_ARG(a->out_image_t == nullptr || a->out_image_t_rows == 128 || a->out_image_t_rows == 256,
+                    "out_image_t_rows must be 128 or 256");
+    TFEPB_CHECK_ARG((uintptr_t)a->out_image_t % 16 == 0, "operand images must be 16-byte aligned");
     TFEPB_CHECK_ARG(a->c == nullptr || a->ldc >= a->n, "leading dimension smaller than the row length");
-    TFEPB_CHECK_ARG(!(a->split_k > 1) || (a->c != nullptr && a->out_image == nullptr && a->bias == nullptr && a->aux == nullptr &&
+    TFEPB_CHECK_ARG(!(a->split_k > 1) || (a->c != nullptr && a->out_image == nullptr && a->out_image_t == nullptr &&
+                                          a->column_sums == nullptr && a->bias == nullptr && a->aux == nullptr &&
                                           a->activation == TFEPB_ACT_NONE),
                     "split-K accumulates raw products into a zero-filled fp32 C only");
     TFEPB_CHECK_ARG(((uintptr_t)a->a_image % 16 == 0) && ((uintptr_t)a->b_image % 16 == 0) && ((uintptr_t)a->out_image % 16 == 0),
@@ -375,6 +410,9 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
     p.C = (float*)a->c; p.ldc = a->ldc; p.bias = (const float*)a->bias; p.act = a->activation;
     p.aux = (const float*)a->aux; p.ldaux = a->ldaux;
     p.out_img = (uint8_t*)a->out_image; p.out_k_blocks = (a->n + tcg::KB - 1) / tcg::KB;
+    p.out_img_t = (uint8_t*)a->out_image_t; p.t_rows = a->out_image_t != nullptr ? a->out_image_t_rows : 128;
+    p.t_k_blocks = (a->m + tcg::KB - 1) / tcg::KB; p.t_rows_padded = (a->n + p.t_rows - 1) / p.t_rows * p.t_rows;
+    p.colsum = a->column_sums;
     p.kranges = a->k_block_ranges;
     p.row_ranges = a->row_ranges;
     p.tiles_m = (a->m + tcg::BM - 1) / tcg::BM; p.tiles_n = (a->n + tcg::BN - 1) / tcg::BN;
