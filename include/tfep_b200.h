@@ -194,6 +194,10 @@ int64_t tfepb_tc_image_bytes(int64_t rows, int64_t k, int32_t block_rows);
 /* src fp32: element (row, k) at src[row * ld + k], or src[k * ld + row] if transpose */
 int tfepb_tc_pack(const float* src, int64_t ld, int32_t rows, int32_t k, int32_t block_rows, int32_t transpose,
                   void* image, tfepb_stream_t stream);
+/* One pass over src (rows x cols fp32): its image with 128-row blocks (or NULL), the image of its transpose with
+ * t_block_rows = 128 / 256 (or NULL) and, if column_sums != NULL (zero-filled by the caller), += the sums over the rows. */
+int tfepb_tc_pack_dual(const float* src, int64_t ld, int32_t rows, int32_t cols, void* image, void* image_t,
+                       int32_t t_block_rows, float* column_sums, tfepb_stream_t stream);
 typedef struct {
     const void* a_image; const void* b_image;
     int32_t m, n, k;

@@ -75,3 +75,19 @@ def test_transposed_image_and_column_sums_from_the_epilogue(m, n, k, rows):
         _, _, img_t2, sums2 = _ops.tc_gemm(ai, bi, m, n, k, out_image_t=rows, column_sums=True, **kw)
         assert torch.equal(img_t2, img_t)
         assert float((sums2 - sums).abs().max()) < 1e-5 * (1 + float(c.abs().sum(dim=0).max()))
+
+
+@pytest.mark.parametrize('rows,cols,t_rows', [(1000, 670, 128), (257, 300, 256), (5, 7, 128), (4096, 1500, 256), (64, 64, 256)])
+def test_dual_pack_equals_the_separate_packs(rows, cols, t_rows):
+    src = _rand((rows, cols), 31)
+    img, img_t, sums = _ops.tc_pack_dual(src, t_rows, column_sums=True)
+    assert torch.equal(img, _ops.tc_pack(src, 128))
+    assert torch.equal(img_t, _ops.tc_pack(src, t_rows, transpose=True))
+    assert float((sums.double() - src.double().sum(dim=0)).abs().max()) < 1e-5 * (1 + float(src.abs().sum(dim=0).max()))
+    img2, none_t, none_s = _ops.tc_pack_dual(src)
+    assert torch.equal(img2, img) and none_t is None and none_s is None
+    # padded leading dimension (a column slice of a wider tensor)
+    wide = _rand((rows, cols + 5), 32)
+    i3, t3, _ = _ops.tc_pack_dual(wide[:, :cols], t_rows)
+    assert torch.equal(i3, _ops.tc_pack(wide[:, :cols].contiguous(), 128))
+    assert torch.equal(t3, _ops.tc_pack(wide[:, :cols].contiguous(), t_rows, transpose=True))

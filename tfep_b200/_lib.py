@@ -128,6 +128,7 @@ SYMBOLS = {
     'tfepb_moebius_backward': (c_int32, [POINTER(TxIo), c_int32, c_double, c_int32, POINTER(TxGrads), c_void_p]),
     'tfepb_tc_image_bytes': (c_int64, [c_int64, c_int64, c_int32]),
     'tfepb_tc_pack': (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    'tfepb_tc_pack_dual': (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     'tfepb_tc_gemm': (c_int32, [POINTER(TcGemmArgs), c_void_p]),
     'tfepb_periodic_embedding': (c_int32, [c_int32, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_double, c_double,
                                            c_void_p, c_int64, c_void_p]),

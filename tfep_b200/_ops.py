@@ -353,6 +353,26 @@ def tc_pack(src, block_rows, transpose=False, out=None):
     return img
 
 
+def tc_pack_dual(src, t_block_rows=None, column_sums=False, image=True):
+    """One pass over a 2-D fp32 CUDA tensor: (its image with 128-row blocks, the image of its transpose with
+    ``t_block_rows`` = 128 / 256, its column sums); see tfepb_tc_pack_dual.  Parts not asked for are None."""
+    require_cuda(src)
+    if src.dtype != torch.float32:
+        raise _lib.TfepB200Error('tc_pack_dual takes float32 tensors')
+    src = _rows(src)
+    rows, cols = src.shape
+    lib = _lib.load()
+    img = torch.empty(lib.tfepb_tc_image_bytes(rows, cols, 128), dtype=torch.uint8, device=src.device) if image else None
+    img_t = None
+    if t_block_rows:
+        img_t = torch.empty(lib.tfepb_tc_image_bytes(cols, rows, int(t_block_rows)), dtype=torch.uint8, device=src.device)
+    sums = torch.zeros(cols, dtype=torch.float32, device=src.device) if column_sums else None
+    with torch.cuda.device(src.device):
+        check(lib.tfepb_tc_pack_dual(ptr(src), _ld(src), rows, cols, ptr(img), ptr(img_t), int(t_block_rows or 0), ptr(sums),
+                                     stream_ptr(src)))
+    return img, img_t, sums
+
+
 def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, aux=None, out_image=False,
             k_block_ranges=None, row_ranges=None, split_k=1, error_flag=None, out_image_t=None, column_sums=False):
     """C = act(A B^T + bias) [* ELU'(aux)] from operand images; returns (c, out_img).  ``c``: True to allocate, a
@@ -404,8 +424,9 @@ class MadeFunctionTC(torch.autograd.Function):
         ws, bs = wb[:n_layers], wb[n_layers:]
         B = x.shape[0]
         train = any(ctx.needs_input_grad[5:5 + 2 * n_layers])      # weight gradients wanted: keep transposed images
-        acts, acts_t = [x], [None]
-        img = tc_pack(x, 128)
+        # x: one pass gives the A operand of the first product and, for training, the B operand of its weight gradient
+        img, x_t, _ = tc_pack_dual(x, 256 if train else None)
+        acts, acts_t = [x], [x_t]
         h = x
         for l in range(n_layers):
             last = l == n_layers - 1
@@ -436,10 +457,10 @@ class MadeFunctionTC(torch.autograd.Function):
         acts, ws = saved[:L], saved[L:]
         B = grad_out.shape[0]
         g = _rows(grad_out.contiguous())
-        gimg = tc_pack(g, 128)
-        # image of g^T (A operand of the weight gradient) and the bias gradient: packed / summed here for the top layer,
-        # written by the epilogue of the backward-input product for the layers below
-        gimg_t, gb = None, None
+        # image of g, image of g^T (A operand of the weight gradient) and the bias gradient: one pass over grad_out for the
+        # top layer, written by the epilogue of the backward-input product for the layers below
+        top = ctx.needs_input_grad[5 + L - 1] or ctx.needs_input_grad[5 + 2 * L - 1]
+        gimg, gimg_t, gb = tc_pack_dual(g, 128 if top else None, column_sums=top)
         gws, gbs = [None] * L, [None] * L
         gx = None
         n_sm = torch.cuda.get_device_properties(g.device).multi_processor_count

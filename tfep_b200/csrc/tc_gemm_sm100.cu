@@ -365,6 +365,53 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const float* __restrict__ 
     }
 }
 
+// One pass over an fp32 matrix (R x C, row-major) -> the image of the matrix (A operand: 128-row blocks, k = columns), the
+// image of its transpose (rows = columns, k = rows; block_rows = t_rows) and the column sums: what the backward pass
+// needs of grad_y (operand of the backward-input product, operand of the weight gradient, bias gradient) and the forward
+// pass of x.  One CTA per 64 x 64 tile; every block of both images is written completely (zero padding included).
+__global__ void __launch_bounds__(256) tc_pack_dual_kernel(const float* __restrict__ src, int64_t ld, int R, int C,
+                                                           uint8_t* __restrict__ img, uint8_t* __restrict__ img_t, int t_rows,
+                                                           float* __restrict__ colsum) {
+    __shared__ float tile[64][65];
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+        const int rr = i >> 6, cc = i & 63;
+        tile[rr][cc] = (r0 + rr < R && c0 + cc < C) ? __ldg(src + (int64_t)(r0 + rr) * ld + c0 + cc) : 0.f;
+    }
+    __syncthreads();
+    const int kb_a = (C + KB - 1) / KB, kb_t = (R + KB - 1) / KB;
+    if (img != nullptr && blockIdx.x < kb_a) {
+        uint8_t* blk = img + ((size_t)(r0 >> 7) * kb_a + blockIdx.x) * A_BLOCK;
+        for (int i = threadIdx.x; i < 64 * 8; i += 256) {
+            const int rr = i & 63, slab = i >> 6;
+            uint4 q;
+            q.x = pack_bf16(tile[rr][slab * 8 + 0], tile[rr][slab * 8 + 1]);
+            q.y = pack_bf16(tile[rr][slab * 8 + 2], tile[rr][slab * 8 + 3]);
+            q.z = pack_bf16(tile[rr][slab * 8 + 4], tile[rr][slab * 8 + 5]);
+            q.w = pack_bf16(tile[rr][slab * 8 + 6], tile[rr][slab * 8 + 7]);
+            *reinterpret_cast<uint4*>(blk + (size_t)slab * 2048 + (size_t)((r0 & 127) + rr) * 16) = q;
+        }
+    }
+    if (img_t != nullptr && blockIdx.y < kb_t) {
+        uint8_t* blk = img_t + ((size_t)(c0 / t_rows) * kb_t + blockIdx.y) * (size_t)t_rows * 128;
+        for (int i = threadIdx.x; i < 64 * 8; i += 256) {
+            const int cc = i & 63, slab = i >> 6;
+            uint4 q;
+            q.x = pack_bf16(tile[slab * 8 + 0][cc], tile[slab * 8 + 1][cc]);
+            q.y = pack_bf16(tile[slab * 8 + 2][cc], tile[slab * 8 + 3][cc]);
+            q.z = pack_bf16(tile[slab * 8 + 4][cc], tile[slab * 8 + 5][cc]);
+            q.w = pack_bf16(tile[slab * 8 + 6][cc], tile[slab * 8 + 7][cc]);
+            *reinterpret_cast<uint4*>(blk + (size_t)slab * t_rows * 16 + (size_t)((c0 % t_rows) + cc) * 16) = q;
+        }
+    }
+    if (colsum != nullptr && threadIdx.x < 64 && c0 + threadIdx.x < C) {
+        float s = 0.f;
+#pragma unroll 8
+        for (int rr = 0; rr < 64; ++rr) s += tile[rr][threadIdx.x];
+        atomicAdd(colsum + c0 + threadIdx.x, s);
+    }
+}
+
 }  // namespace tcg
 }  // namespace tfepb
 
@@ -386,6 +433,22 @@ extern "C" int tfepb_tc_pack(const float* src, int64_t ld, int32_t rows, int32_t
     dim3 grid((unsigned)((k + tcg::KB - 1) / tcg::KB), (unsigned)((rows + block_rows - 1) / block_rows));
     tcg::tc_pack_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, ld, rows, k, block_rows, transpose, (uint8_t*)image);
     return check_launch("tc_pack");
+}
+
+extern "C" int tfepb_tc_pack_dual(const float* src, int64_t ld, int32_t rows, int32_t cols, void* image, void* image_t,
+                                  int32_t t_block_rows, float* column_sums, tfepb_stream_t stream) {
+    TFEPB_CHECK_ARG(src != nullptr && (image != nullptr || image_t != nullptr), "null buffer");
+    TFEPB_CHECK_ARG(rows > 0 && cols > 0 && ld >= cols, "bad sizes");
+    TFEPB_CHECK_ARG(image_t == nullptr || t_block_rows == 128 || t_block_rows == 256, "t_block_rows must be 128 or 256");
+    TFEPB_CHECK_ARG(((uintptr_t)image % 16 == 0) && ((uintptr_t)image_t % 16 == 0), "operand images must be 16-byte aligned");
+    if (int rc = require_sm100()) return rc;
+    const int tr = image_t != nullptr ? t_block_rows : 128;
+    // cover every block of both images: rows up to a multiple of 128, columns up to a multiple of the transposed block
+    const unsigned gy = (unsigned)((rows + 127) / 128 * 2);
+    const unsigned gx = (unsigned)((cols + tr - 1) / tr * (tr / 64));
+    tcg::tc_pack_dual_kernel<<<dim3(gx, gy), 256, 0, as_stream(stream)>>>(src, ld, rows, cols, (uint8_t*)image, (uint8_t*)image_t,
+                                                                         tr, column_sums);
+    return check_launch("tc_pack_dual");
 }
 
 extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream) {
