@@ -156,12 +156,15 @@ def run_ours(args, rank, world, local_rank):
 
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
+    from tfep_b200.utils.host_pipeline import gpu_numa_affinity
     seq, _ = cfg_flow_modules('cfg2', dev)
     seq.eval()
     for maf in seq:
         maf.precision = args.precision
     # contiguous batch shards of one global synthetic data set (seeded on the host)
-    x_host = cases.cfg_input('cfg2', BATCH * world)[rank * BATCH:(rank + 1) * BATCH].contiguous().pin_memory()
+    x_host = cases.cfg_input('cfg2', BATCH * world)[rank * BATCH:(rank + 1) * BATCH].contiguous()
+    with gpu_numa_affinity(dev):              # pinned input buffer on the NUMA node of this rank's GPU
+        x_host = x_host.pin_memory()
     x = x_host.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 

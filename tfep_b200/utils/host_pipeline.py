@@ -8,7 +8,38 @@ with ``wait=False`` consecutive batches overlap as well (``depth`` staging sets 
 of batch g + 1 and the download of batch g - 1 run while batch g is in the kernels.
 """
 
+import contextlib
+import os
+
 import torch
+
+
+@contextlib.contextmanager
+def gpu_numa_affinity(device):
+    """While active, the calling thread runs on the CPU cores closest to ``device`` (NVML's ideal affinity: the NUMA node
+    the GPU hangs off), so that pinned staging buffers allocated inside are local to the GPU's PCIe root.  The previous
+    affinity is restored on exit; without NVML (or permission) this does nothing."""
+    previous = None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        index = torch.device(device).index or 0
+        visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+        if visible:
+            entry = visible.split(',')[index].strip()
+            handle = pynvml.nvmlDeviceGetHandleByUUID(entry) if entry.startswith('GPU-') else \
+                pynvml.nvmlDeviceGetHandleByIndex(int(entry))
+        else:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        previous = os.sched_getaffinity(0)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+    except Exception:                      # no NVML, no permission, exotic topology: keep the inherited affinity
+        previous = None
+    try:
+        yield
+    finally:
+        if previous is not None:
+            os.sched_setaffinity(0, previous)
 
 
 class HostPipeline:
@@ -22,8 +53,9 @@ class HostPipeline:
         # in flight are needed to keep the two copy engines and the SMs busy at the same time
         self.depth = depth
         self.x_dev = [torch.empty(batch, n_features, dtype=dtype, device=self.device) for _ in range(depth)]
-        self.y_hosts = [torch.empty(batch, n_features, dtype=dtype).pin_memory() for _ in range(depth)]
-        self.ld_hosts = [torch.empty(batch, dtype=dtype).pin_memory() for _ in range(depth)]
+        with gpu_numa_affinity(self.device):
+            self.y_hosts = [torch.empty(batch, n_features, dtype=dtype).pin_memory() for _ in range(depth)]
+            self.ld_hosts = [torch.empty(batch, dtype=dtype).pin_memory() for _ in range(depth)]
         self.s_in = torch.cuda.Stream(self.device)
         self.s_out = torch.cuda.Stream(self.device)
         self.generation = 0
