@@ -310,6 +310,13 @@ typedef struct {
     int32_t mixed_splines;                         /* 1 if any feature has kind != 0 (selects the generic spline epilogue) */
     int32_t n_inputs;                              /* conditioner inputs before the two constant ones (n_features plus one
                                                       per lifted periodic feature); 0 = n_features.  k1 >= n_inputs + 2 */
+    int32_t x_operand_column;                      /* first tensor-memory column of the x operand inside the 176-column A
+                                                      operand region (multiple of 8; the first-layer blocks carry it in
+                                                      a_col).  The hidden activations are written from column 0: with x at
+                                                      the end of the region, clear of the first half of h1
+                                                      (>= hidden_split[0] / 2), that half is written while the second half
+                                                      of the first product still reads x */
+    int32_t reserved3;
     int32_t* error_flag;                           /* device int, set if an internal wait times out; may be NULL */
     float* debug_params;                           /* NULL, or (batch, n_chunks * 112): conditioner outputs (+bias)
                                                       of layer 0 in packed order, for parity tests of the GEMM chain */

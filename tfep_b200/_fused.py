@@ -216,6 +216,10 @@ class FusedSplinePlan:
         if any((b - a) * self.K1 * 2 > STAGE_BYTES for a, b in self.hidden_chunks1):
             raise _lib.TfepB200Error('fused bf16 path: first-layer weight block exceeds a ring stage')
 
+        # x sits at the end of the A operand region (176 tensor-memory columns, two k-values each), clear of the first
+        # half of h1, which is then written while the second half of GEMM1 still reads x
+        self.x_col = (176 - self.K1 // 2) // 8 * 8
+
         # ---- schedule ----
         ops, gather = [], []           # gather: per op, index tensor into the concatenated padded matrices
         off1, off2 = self.HP * self.K1, self.HP * self.K1 + self.HP * self.HP
@@ -240,7 +244,7 @@ class FusedSplinePlan:
         # GEMM1: full K1 per half (the first layer is tiny; no staircase); both halves need only x
         for i, (a, b) in enumerate(self.hidden_chunks1):
             fl = OP_FIRST | OP_COMMIT | OP_HIDDEN | (i << OP_ACC_SHIFT) | (OP_WAIT_A if i == 0 else 0) | (OP_OWNER1 if i & 1 else 0)
-            add(b - a, a, 0, self.K1, 0, fl, 0, self.K1, a)
+            add(b - a, a, 0, self.K1, self.x_col // 4, fl, 0, self.K1, a)
         # GEMM2: rows see layer-1 units of degree <= their own; half i waits for half i of h1
         for i, (a, b) in enumerate(self.hidden_chunks2):
             kmax = kmax2(b)
@@ -465,7 +469,7 @@ _EPOCH = [0]
 
 
 def _chain_key(pl):
-    return (pl.D, pl.Din, pl.K1, pl.HP, pl.halves)
+    return (pl.D, pl.Din, pl.K1, pl.HP, pl.halves, pl.x_col)
 
 
 def chain_compatible(plans):
@@ -528,6 +532,7 @@ def run_chain(plans_mafs, x, debug_params=None):
                           tile_flags=None if flags is None else flags.data_ptr(), epoch=_EPOCH[0],
                           debug_mode=int(os.environ.get('TFEPB_FUSED_DEBUG_MODE', '0')),
                           mixed_splines=int(any(pl.mixed for pl, _ in plans_mafs)), n_inputs=first.Din,
+                          x_operand_column=first.x_col, reserved3=0,
                           error_flag=tb['err'].data_ptr(),
                           debug_params=None if debug_params is None else debug_params.data_ptr())
     with torch.cuda.device(x.device):

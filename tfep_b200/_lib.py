@@ -74,7 +74,8 @@ class FusedArgs(Structure):
     _fields_ = [('x', c_void_p), ('y', c_void_p), ('logdet', c_void_p), ('batch', c_int32), ('n_features', c_int32),
                 ('k1', c_int32), ('hidden_padded', c_int32), ('n_layers', c_int32), ('hidden_halves', c_int32), ('hidden_split', c_int32 * 2),
                 ('layers', POINTER(FusedLayer)), ('tile_flags', c_void_p), ('epoch', c_uint32), ('debug_mode', c_int32),
-                ('mixed_splines', c_int32), ('n_inputs', c_int32), ('error_flag', c_void_p), ('debug_params', c_void_p)]
+                ('mixed_splines', c_int32), ('n_inputs', c_int32), ('x_operand_column', c_int32), ('reserved3', c_int32),
+                ('error_flag', c_void_p), ('debug_params', c_void_p)]
 
 
 class FusedInvLayer(Structure):

@@ -109,6 +109,7 @@ struct Params {
     int HP;                     // hidden width (+2) padded to a multiple of 16
     int n_layers, n_tiles, feat_stride;   // feat_stride: feature slots reserved per layer in shared memory
     int n_halves;               // column halves of a hidden layer (1 or 2), each its own accumulator group and hand-over
+    int x_col;                  // first column of the x operand inside the A operand region
     uint32_t* flags;            // (n_layers - 1) x n_tiles: == epoch once the tile of that layer is in y
     uint32_t epoch;
     int* error;                 // device int: set on watchdog timeout
@@ -498,7 +499,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
 #pragma unroll
                     for (int i = 0; i < 8; ++i) q[i] = pack_bf16(input((c0 + i) * 2), input((c0 + i) * 2 + 1));
                 }
-                tmem_st8(lane_addr + A_COL + c0, q);
+                tmem_st8(lane_addr + A_COL + p.x_col + c0, q);
             }
             tmem_st_wait();
             tc_fence_before();
@@ -510,14 +511,16 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
             // starts on the first half of h2.
             for (int hl = 0; hl < 2; ++hl) {
                 for (int half = 0; half < p.n_halves; ++half) {
-                    // The activations overwrite the A operand of the GEMM that produced them (h1 over x, h2 over h1:
-                    // same tensor-memory columns), so they may only be written once BOTH halves of that GEMM have
-                    // read it.  GEMM1 is tiny (its second half is done ~100 cycles after the first); for GEMM2 the
-                    // overlap that matters is the one with the ELU of the second half of h1, which is kept.
-                    if (half == 0) {
-                        mbar_wait(&sm->hid_full[0], hid_par & 1u, p.error, 7);
-                        hid_par ^= 1u;
-                        if (p.n_halves == 2) {
+                    // The activations overwrite the A operand region.  h2 over h1: same columns, so the second layer
+                    // waits for BOTH halves of GEMM2.  h1 over x: the planner puts x at the END of the region
+                    // (p.x_col), clear of the first half of h1, so that half is written while the second half of
+                    // GEMM1 still reads x; the second half of h1 (which may reach x) waits for its own GEMM1 half,
+                    // issued after the first.  Without that placement the first layer waits for both halves too.
+                    const bool both = p.n_halves == 2 && (hl == 1 || p.x_col < L.hsplit[0] / 2);
+                    if (half == 0 || !both) {
+                        mbar_wait(&sm->hid_full[half], (hid_par >> half) & 1u, p.error, 7);
+                        hid_par ^= 1u << half;
+                        if (half == 0 && both) {
                             mbar_wait(&sm->hid_full[1], (hid_par >> 1) & 1u, p.error, 7);
                             hid_par ^= 2u;
                         }
@@ -684,6 +687,9 @@ extern "C" int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_st
     }
     p.feat_stride = feat_stride;
     p.n_halves = a->hidden_halves;
+    TFEPB_CHECK_ARG(a->x_operand_column >= 0 && a->x_operand_column % 8 == 0 &&
+                    a->x_operand_column + a->k1 / 2 <= 512 - fused::A_COL, "x_operand_column outside the A operand region");
+    p.x_col = a->x_operand_column;
     p.error = a->error_flag;
     p.debug_params = a->debug_params;
     p.debug_mode = a->debug_mode;
