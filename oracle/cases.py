@@ -220,6 +220,27 @@ def build_wrapper_oracle(case, dtype=torch.float32):
     return flow, sd
 
 
+def embedding_cases():
+    """name -> (builder(namespace) -> module, n_features_in, degrees_in): embeddings with learnable parameters, built from
+    a namespace that provides FlipInvariantEmbedding / MixedEmbedding / PeriodicEmbedding (the reference or tfep_b200)."""
+    def flip(ns):
+        return ns.FlipInvariantEmbedding(n_features_in=11, embedding_dimension=5, embedded_indices=[1, 2, 3, 4, 7, 8, 9, 10])
+
+    def mixed_flips(ns):
+        return ns.MixedEmbedding(12, [ns.FlipInvariantEmbedding(4, 3, vector_dimension=4, hidden_layer_width=8),
+                                      ns.FlipInvariantEmbedding(6, 2, vector_dimension=2, hidden_layer_width=6)],
+                                 [[0, 1, 2, 3], [5, 6, 8, 9, 10, 11]])
+
+    def mixed_periodic(ns):
+        return ns.MixedEmbedding(9, [ns.PeriodicEmbedding(3, [-math.pi, math.pi]),
+                                     ns.FlipInvariantEmbedding(4, 6, hidden_layer_width=16)], [[0, 4, 8], [2, 3, 5, 6]])
+
+    deg11 = torch.tensor([0, 1, 1, 1, 1, 2, 3, 4, 4, 4, 4])
+    deg12 = torch.tensor([0, 0, 0, 0, 1, 2, 2, 3, 4, 4, 5, 5])
+    deg9 = torch.tensor([0, 1, 2, 2, 3, 2, 2, 4, 5])
+    return {'flip': (flip, 11, deg11), 'mixed_flips': (mixed_flips, 12, deg12), 'mixed_periodic': (mixed_periodic, 9, deg9)}
+
+
 def build_oracle(case, dtype=torch.float32):
     m = fo.MafOracle(case['degrees_in'], case['spec'], hidden_layers=case['hidden_layers'],
                      weight_norm=case['weight_norm'], embedding=case.get('embedding'))

@@ -92,6 +92,25 @@ def golden_wrappers(ref, dtype, tag):
     np.savez_compressed(os.path.join(OUT, f'wrappers_{tag}.npz'), **out)
 
 
+def golden_embeddings(ref):
+    """FlipInvariantEmbedding / MixedEmbedding of the reference with seeded parameters: state dict, input, output,
+    output degrees and the gradient of sum(out * c) w.r.t. x."""
+    out = {}
+    for name, (build, n, deg) in cases.embedding_cases().items():
+        torch.manual_seed(40)
+        emb = build(ref)
+        x = cases.normal((9, n), 41)
+        xg = x.clone().requires_grad_(True)
+        y = emb(xg)
+        c = cases.normal(tuple(y.shape), 42)
+        (y * c).sum().backward()
+        out[f'{name}/x'], out[f'{name}/y'], out[f'{name}/gx'] = _np(x), _np(y), _np(xg.grad)
+        out[f'{name}/deg'] = _np(emb.get_degrees_out(deg))
+        for k, v in emb.state_dict().items():
+            out[f'{name}/sd/{k}'] = _np(v)
+    np.savez_compressed(os.path.join(OUT, 'embeddings.npz'), **out)
+
+
 def golden_cfg(ref):
     """Slices of the BASELINE.json configurations, fp32 reference plus fp64 reference of the same bits."""
     out = {}
@@ -211,6 +230,7 @@ def main():
             golden_wrappers(ref, dtype, tag)
         finally:
             torch.set_default_dtype(old)
+    golden_embeddings(ref)
     golden_cfg(ref)
     golden_analysis(ref)
     for f in sorted(os.listdir(OUT)):

@@ -253,3 +253,33 @@ def test_wrapper_flows_around_the_maf_kernels(prec):
             with torch.no_grad():
                 xi, ldi = flow.inverse(torch.from_numpy(g[f'{name}/y']).to(DEV))
             assert rel_err(xi, g[f'{name}/xinv']) < 50 * TOL[prec] and rel_err(ldi, g[f'{name}/ldinv']) < 50 * TOL[prec], name
+
+
+def test_mixed_embedding_in_front_of_the_conditioner():
+    """MixedEmbedding of a PeriodicEmbedding (CUDA kernel) and a learnable FlipInvariantEmbedding (reference
+    mafembed.py:174-446) against the reference's golden output, and as the `embedding=` of a MAF (conditioner input
+    degrees from get_degrees_out; forward / inverse round trip through the generic per-degree inverse)."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_host_api import _load_embedding
+    from tfep_b200.nn.flows import MAF
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float32)
+    try:
+        emb, g, deg = _load_embedding('mixed_periodic', DEV)
+        x = torch.from_numpy(g['mixed_periodic/x']).to(DEV).requires_grad_(True)
+        y = emb(x)
+        assert rel_err(y, g['mixed_periodic/y']) < 1e-5
+        (y * cases.normal(tuple(y.shape), 42).to(DEV)).sum().backward()
+        assert rel_err(x.grad, g['mixed_periodic/gx']) < 1e-4
+        assert torch.equal(emb.get_degrees_out(deg).cpu(), torch.from_numpy(g['mixed_periodic/deg']))
+        torch.manual_seed(3)
+        maf = MAF(degrees_in=deg, embedding=emb, initialize_identity=False).to(DEV)
+        xs = cases.normal((50, 9), 43).to(DEV)
+        with torch.no_grad():
+            ys, ld = maf(xs)
+            xi, ldi = maf.inverse(ys)
+        assert rel_err(xi, xs) < 1e-4 and rel_err(ld + ldi, torch.zeros_like(ld)) < 1e-4
+    finally:
+        torch.set_default_dtype(old)

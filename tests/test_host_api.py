@@ -260,3 +260,43 @@ def test_wrapper_flow_constructor_errors():
         CenteredCentroidFlow(inner, 3, translate_back=False).inverse(torch.zeros(2, 6))
     with pytest.raises(ValueError, match="only if 'rotate_back' is set to True"):
         OrientedFlow(inner, rotate_back=False).inverse(torch.zeros(2, 9))
+
+
+def _load_embedding(name, device='cpu'):
+    """tfep_b200 embedding of an oracle.cases.embedding_cases entry with the reference's seeded parameters."""
+    import types
+    import tfep_b200.nn.embeddings as E
+    from helpers import golden
+    g = golden('embeddings.npz')
+    build, n, deg = cases.embedding_cases()[name]
+    emb = build(types.SimpleNamespace(FlipInvariantEmbedding=E.FlipInvariantEmbedding, MixedEmbedding=E.MixedEmbedding,
+                                      PeriodicEmbedding=E.PeriodicEmbedding))
+    sd = {k[len(name) + 4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith(f'{name}/sd/')}
+    missing, unexpected = emb.load_state_dict(sd, strict=False)
+    assert not unexpected and not [k for k in missing if 'weight' in k or 'bias' in k], (missing, unexpected)
+    return emb.to(device), g, deg
+
+
+@pytest.mark.parametrize('name', ['flip', 'mixed_flips'])
+def test_learnable_embeddings_match_reference_golden(name):
+    """FlipInvariantEmbedding / MixedEmbedding (reference mafembed.py:174-446): same parameter names, outputs, output
+    degrees and input gradients as the reference; invariant to flipping the sign of an embedded vector."""
+    from helpers import rel_err
+    emb, g, deg = _load_embedding(name)
+    x = torch.from_numpy(g[f'{name}/x']).requires_grad_(True)
+    y = emb(x)
+    assert rel_err(y, g[f'{name}/y']) < 1e-6
+    (y * cases.normal(tuple(y.shape), 42)).sum().backward()
+    assert rel_err(x.grad, g[f'{name}/gx']) < 1e-5
+    assert torch.equal(emb.get_degrees_out(deg), torch.from_numpy(g[f'{name}/deg']))
+    if name == 'flip':
+        xf = x.detach().clone()
+        xf[:, [1, 2, 3, 4]] *= -1
+        assert rel_err(emb(xf), y.detach()) < 1e-6
+        with pytest.raises(ValueError, match='same degree must be assigned'):
+            emb.get_degrees_out(torch.arange(11))
+        with pytest.raises(ValueError, match='duplicated indices'):
+            type(emb)(4, 2, embedded_indices=[0, 0, 1, 2])
+    else:
+        with pytest.raises(ValueError, match='must be assigned to different feature indices'):
+            type(emb)(6, list(emb.embedding_layers), [[0, 1, 2, 3], [3, 4]])

@@ -1,5 +1,8 @@
 """Embedding layers for MAF conditioners (reference tfep/nn/embeddings/mafembed.py:30-172).
 
+``FlipInvariantEmbedding`` and ``MixedEmbedding`` (reference mafembed.py:174-446) are small learnable / composite
+modules evaluated with tensor algebra in front of the conditioner kernels.
+
 ``PeriodicEmbedding`` lifts periodic features to ``(cos, sin)`` before they enter the MADE conditioner -- what the
 reference's ``MixedMAFMap`` runs (app/mixedmaf.py:341-353).  Kernels: tfepb_periodic_embedding /
 tfepb_periodic_embedding_backward (one thread per input element, forward plus hand-written backward); inside
@@ -112,5 +115,97 @@ class PeriodicEmbedding(MAFEmbedding):
         return _PeriodicEmbeddingFunction.apply(x, self)
 
     def get_degrees_out(self, degrees_in: torch.Tensor) -> torch.Tensor:
-        return torch.cat([degrees_in[self._nonperiodic_indices],
-                          degrees_in[self._periodic_indices].repeat_interleave(2)])
+        dev = degrees_in.device                  # (the degrees usually live on the host, the module may not)
+        return torch.cat([degrees_in[self._nonperiodic_indices.to(dev)],
+                          degrees_in[self._periodic_indices.to(dev)].repeat_interleave(2)])
+
+
+def _complement(n_features_in, indices):
+    """Sorted indices of range(n_features_in) that are not in ``indices``."""
+    keep = torch.ones(n_features_in, dtype=torch.bool)
+    keep[indices] = False
+    return keep.nonzero().flatten()
+
+
+class FlipInvariantEmbedding(MAFEmbedding):
+    """Embed vector features (e.g. quaternions) into a representation invariant to a sign flip of the vector
+    (reference mafembed.py:174-351, Koehler et al. 2023, SI eq. 46): a softmax-weighted average of a small
+    network evaluated at ``v`` and ``-v``, ``sum_s softmax_s(w(s v)) e(s v)``.
+
+    Output: the non-embedded features first, then ``embedding_dimension`` values per vector; all components of a
+    vector must share one degree.  Parameter names (``embedding_layer.{0,2}``, ``weight_layer.{0,2}``) as in the reference.
+    """
+
+    def __init__(self, n_features_in, embedding_dimension, embedded_indices=None, vector_dimension=4, hidden_layer_width=32):
+        super().__init__()
+        self.embedding_layer = torch.nn.Sequential(
+            torch.nn.Linear(vector_dimension, hidden_layer_width), torch.nn.ELU(),
+            torch.nn.Linear(hidden_layer_width, embedding_dimension))
+        self.weight_layer = torch.nn.Sequential(
+            torch.nn.Linear(vector_dimension, hidden_layer_width), torch.nn.ELU(),
+            torch.nn.Linear(hidden_layer_width, 1))
+        if embedded_indices is None:
+            embedded_indices = torch.arange(n_features_in)
+        else:
+            embedded_indices = ensure_tensor_sequence(embedded_indices)
+            if len(embedded_indices.unique()) < len(embedded_indices):
+                raise ValueError('Found duplicated indices in embedded_indices.')
+        self.register_buffer('_embedded_indices', embedded_indices)
+        self.register_buffer('_nonembedded_indices', _complement(n_features_in, embedded_indices))
+
+    @property
+    def vector_dimension(self) -> int:
+        return self.embedding_layer[0].in_features
+
+    @property
+    def embedding_dimension(self) -> int:
+        return self.embedding_layer[-1].out_features
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        batch = x.shape[0]
+        v = x[:, self._embedded_indices].reshape(-1, self.vector_dimension)
+        both = torch.stack([v, -v], dim=1)                                  # (n_vectors_total, 2, d)
+        weights = torch.softmax(self.weight_layer(both), dim=1)             # (n_vectors_total, 2, 1)
+        embedded = (weights * self.embedding_layer(both)).sum(dim=1)
+        return torch.cat([x[:, self._nonembedded_indices], embedded.reshape(batch, -1)], dim=1)
+
+    def get_degrees_out(self, degrees_in: torch.Tensor) -> torch.Tensor:
+        dev = degrees_in.device
+        vec = degrees_in[self._embedded_indices.to(dev)].reshape(-1, self.vector_dimension)
+        if not torch.all(vec == vec[:, [0]]):
+            raise ValueError('The same degree must be assigned to all '
+                             'components of each embedded vectors.')
+        return torch.cat([degrees_in[self._nonembedded_indices.to(dev)],
+                          vec[:, [0]].expand(-1, self.embedding_dimension).flatten()])
+
+
+class MixedEmbedding(MAFEmbedding):
+    """Apply several embedding layers, each to its own subset of the features (reference mafembed.py:354-446).
+    Output: the features no layer takes first, then the outputs of the layers in order."""
+
+    def __init__(self, n_features_in, embedding_layers, embedded_indices):
+        super().__init__()
+        if len(embedding_layers) != len(embedded_indices):
+            raise ValueError('Different number of layers and indices.')
+        embedded_indices = [ensure_tensor_sequence(i) for i in embedded_indices]
+        first = set(embedded_indices[0].tolist())
+        for indices in embedded_indices[1:]:
+            if len(first & set(indices.tolist())) > 0:
+                raise ValueError('Different embedding layers must be assigned '
+                                 'to different feature indices.')
+        self.embedding_layers = torch.nn.ModuleList(embedding_layers)
+        for i, indices in enumerate(embedded_indices):
+            self.register_buffer(f'_embedded_indices{i}', indices)
+        self.register_buffer('_nonembedded_indices', _complement(n_features_in, torch.cat(embedded_indices)))
+
+    def _indices(self, i):
+        return getattr(self, f'_embedded_indices{i}')
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        parts = [layer(x[:, self._indices(i)].contiguous()) for i, layer in enumerate(self.embedding_layers)]
+        return torch.cat([x[:, self._nonembedded_indices], *parts], dim=1)
+
+    def get_degrees_out(self, degrees_in: torch.Tensor) -> torch.Tensor:
+        dev = degrees_in.device
+        parts = [layer.get_degrees_out(degrees_in[self._indices(i).to(dev)]) for i, layer in enumerate(self.embedding_layers)]
+        return torch.cat([degrees_in[self._nonembedded_indices.to(dev)], *parts])
