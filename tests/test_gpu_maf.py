@@ -283,3 +283,37 @@ def test_mixed_embedding_in_front_of_the_conditioner():
         assert rel_err(xi, xs) < 1e-4 and rel_err(ld + ldi, torch.zeros_like(ld)) < 1e-4
     finally:
         torch.set_default_dtype(old)
+
+
+def test_gradients_through_the_inverse(prec):
+    """MAF.inverse under autograd (implicit differentiation of F(x) = y on the hand-written backward kernels) against
+    autograd through the oracle's n_degrees-pass inverse loop (= what the reference differentiates): gradients
+    w.r.t. y and w.r.t. the biases of every conditioner layer, for elementwise, vector-block (Moebius) and mixed
+    transformers, with and without conditioning features."""
+    dtype = DT[prec]
+    tol = {'f32': 2e-3, 'f64': 1e-8}[prec]
+    for name in ('affine_asc', 'affine_cond_h1', 'spline_desc_cond', 'moebius_d3', 'moebius_d2_cond', 'mixed_splines',
+                 'repeated_degrees', 'symmoebius_d3', 'spline_embed_periodic'):
+        case = cases.maf_cases(dtype)[name]
+        oracle, sd = cases.build_oracle(case, dtype)
+        maf = to_maf(case, sd, DEV, dtype)
+        with torch.no_grad():
+            y0, _ = maf(case['x'].to(DEV))
+        cx, cl = cases.normal(tuple(y0.shape), 61, dtype), cases.normal((y0.shape[0],), 62, dtype)
+        # oracle: autograd through the loop, leaves = y and the (effective weight, bias) pairs
+        yo = y0.cpu().clone().requires_grad_(True)
+        oracle.layers = [(w.clone().requires_grad_(True), b.clone().requires_grad_(True)) for w, b in oracle.layers]
+        xo, ldo = oracle.inverse(yo)
+        ((xo * cx).sum() + (ldo * cl).sum()).backward()
+        # tfep_b200
+        yg = y0.clone().requires_grad_(True)
+        xi, ldi = maf.inverse(yg)
+        ((xi * cx.to(DEV)).sum() + (ldi * cl.to(DEV)).sum()).backward()
+        assert rel_err(xi.detach(), xo.detach()) < tol and rel_err(ldi.detach(), ldo.detach()) < tol, name
+        scale = 1 + float(yo.grad.abs().max())
+        assert float((yg.grad.cpu() - yo.grad).abs().max()) / scale < tol, name
+        lin = maf._conditioner._linear_layers()
+        for (w_o, b_o), layer in zip(oracle.layers, lin):
+            gb = layer.bias.grad
+            assert gb is not None, name
+            assert float((gb.cpu() - b_o.grad).abs().max()) / (1 + float(b_o.grad.abs().max())) < tol, name

@@ -16,6 +16,75 @@ from ...utils.misc import ensure_tensor_sequence
 from ..transformers.transformer import Transformer
 
 
+def _needs_grad(flow, y):
+    return torch.is_grad_enabled() and (y.requires_grad or any(p.requires_grad for p in flow.parameters()))
+
+
+class _InverseFunction(torch.autograd.Function):
+    """``x, log_det_J = flow.inverse(y)`` (AutoregressiveFlow / MAF) with gradients by implicit differentiation of ``F(x; theta) = y``.
+
+    The reference differentiates through its ``n_degrees`` conditioner passes (autoregressive.py:199-229).  Here the
+    inverse itself runs without autograd (the sweep kernels) and the backward pass solves ``J^T v = gx - g_ld grad_x ld``
+    with ``J = dF/dx`` by back-substitution over the degree groups, highest degree first -- ``J`` is block lower
+    triangular in degree order, its diagonal blocks couple only features of one degree -- using vector-Jacobian
+    products of ONE forward graph (the hand-written backward kernels).  Then ``grad_y = v`` and
+    ``grad_theta = -(dF/dtheta)^T v - g_ld d ld / d theta``.  Cost: a few backward passes per degree.
+    """
+
+    @staticmethod
+    def forward(ctx, maf, y, *params):
+        with torch.no_grad():
+            x, ld = maf.inverse(y)
+        ctx.maf, ctx.n_params = maf, len(params)
+        ctx.save_for_backward(x)
+        return x, ld
+
+    @staticmethod
+    def backward(ctx, gx, gld):
+        maf = ctx.maf
+        (x,) = ctx.saved_tensors
+        params = [p for p in maf.parameters() if p.requires_grad]
+        assert len(params) == ctx.n_params
+        with torch.enable_grad():
+            xg = x.detach().requires_grad_(True)
+            yf, ldf = maf.forward(xg)
+            w = torch.zeros_like(x) if gx is None else gx.clone()
+            ld_grad = gld is not None and ldf.requires_grad
+            if ld_grad:
+                w = w - torch.autograd.grad(ldf, xg, gld, retain_graph=True)[0]
+            v = torch.zeros_like(w)
+            groups = [g.to(x.device) for g in maf._groups_host]
+            fixed = maf._fixed_indices.to(x.device) if maf.has_fixed_indices else None
+            for cols in reversed(groups):
+                # (J^T v) restricted to the group, from the degrees already solved
+                r = w[:, cols]
+                if bool(v.any()):
+                    r = r - torch.autograd.grad(yf, xg, v, retain_graph=True)[0][:, cols]
+                # diagonal block J_gg (per sample, G x G): one vector-Jacobian product per feature of the group
+                G = len(cols)
+                rows = []
+                for j in range(G):
+                    e = torch.zeros_like(w)
+                    e[:, cols[j]] = 1.0
+                    rows.append(torch.autograd.grad(yf, xg, e, retain_graph=True)[0][:, cols])   # row j of J_gg
+                Jgg = torch.stack(rows, dim=1)                                   # (B, G, G): [b, j, k] = dy_j / dx_k
+                if G == 1:
+                    v[:, cols] = r / Jgg[:, 0]
+                else:
+                    v[:, cols] = torch.linalg.solve(Jgg.transpose(1, 2), r.unsqueeze(-1)).squeeze(-1)
+            if fixed is not None and len(fixed) > 0:
+                # conditioning features pass through (identity block) and feed every conditioner
+                v[:, fixed] = w[:, fixed] - torch.autograd.grad(yf, xg, v, retain_graph=True)[0][:, fixed]
+            gparams = [None] * len(params)
+            if params:
+                outs, cots = [yf], [-v]
+                if ld_grad:
+                    outs.append(ldf)
+                    cots.append(-gld)
+                gparams = torch.autograd.grad(outs, params, cots, allow_unused=True)
+        return (None, v, *gparams)
+
+
 class AutoregressiveFlow(torch.nn.Module):
     """Autoregressive flow: ``y_i = T(x_i; conditioner(x_<i))`` for the features in ``transformer_indices``;
     all other features are propagated unchanged.
@@ -118,6 +187,9 @@ class AutoregressiveFlow(torch.nn.Module):
         if self.has_fixed_indices:
             x[:, self._fixed_indices] = y[:, self._fixed_indices]
         native = isinstance(self._transformer, Transformer)
+        if native and _needs_grad(self, y):
+            # the kernels below run without autograd: differentiate implicitly instead
+            return _InverseFunction.apply(self, y, *[p for p in self.parameters() if p.requires_grad])
         if native:
             parts = self._native_parts()
             layouts = [p.ref_layout() for p in parts]

@@ -25,7 +25,7 @@ from ...utils.misc import ensure_tensor_sequence
 from ..conditioners.made import MADE
 from ..transformers.affine import AffineTransformer
 from ..transformers.transformer import Transformer
-from .autoregressive import AutoregressiveFlow
+from .autoregressive import AutoregressiveFlow, _InverseFunction, _needs_grad
 
 
 class MAF(AutoregressiveFlow):
@@ -186,6 +186,8 @@ class MAF(AutoregressiveFlow):
 
     def inverse(self, y: torch.Tensor):
         """Returns ``(x, log_det_J)``: degree-ordered sweep (see the module docstring)."""
+        if _needs_grad(self, y):
+            return _InverseFunction.apply(self, y, *[p for p in self.parameters() if p.requires_grad])
         pk = self._pack()
         from ... import _sweep
         if pk is False or self._n_conditioner_indices > 0 or \
@@ -193,8 +195,6 @@ class MAF(AutoregressiveFlow):
             return super().inverse(y)
         if any(p.kind == 'sos' for p in pk['parts']):
             raise NotImplementedError('Inversion of SOS polynomial transformer has not been implemented yet.')
-        if torch.is_grad_enabled() and (y.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError('tfep_b200: MAF.inverse is not differentiable yet; call it under torch.no_grad()')
         if self.precision == 'bf16':
             from ... import _fused
             plan = self._fused_plan()
