@@ -241,6 +241,49 @@ def embedding_cases():
     return {'flip': (flip, 11, deg11), 'mixed_flips': (mixed_flips, 12, deg12), 'mixed_periodic': (mixed_periodic, 9, deg9)}
 
 
+def logger_script(logger_cls, directory):
+    """One fixed sequence of TFEPLogger operations (reference tfep/io/log.py) on a fresh ``directory``; returns the
+    logger and a dict of everything that was read back.  Used to generate the golden log directory with the reference
+    and to replay it with tfep_b200.io.TFEPLogger."""
+    import warnings
+
+    class _Loader:                                  # the three attributes the logger reads from a DataLoader
+        batch_size, drop_last, dataset = 4, False, range(10)
+
+    def batch(first, n, seed):
+        idx = torch.arange(first, first + n)
+        pot = normal((n,), seed)
+        pot[n // 2] = float('nan') if seed % 2 == 0 else pot[n // 2]
+        return {'dataset_sample_index': idx, 'trajectory_sample_index': 3 * idx + 1, 'potential': pot,
+                'log_det_J': normal((n,), seed + 100).double()}
+
+    log = logger_cls(save_dir_path=directory, data_loader=_Loader())
+    reads = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        # training: epoch 0 complete (3 batches: 4 + 4 + 2 samples), epoch 1 only its middle batch
+        for b, (first, n) in enumerate(((0, 4), (4, 4), (8, 2))):
+            log.save_train_tensors(batch(first, n, 10 + b), epoch_idx=0, batch_idx=b)
+        log.save_train_tensors(batch(4, 4, 20), step_idx=4)
+        log.save_train_tensors({'loss_weight': normal((4,), 21)}, epoch_idx=1, batch_idx=1)      # no indices: warns
+        # evaluation at step 7: two batches appended, then an update that overwrites two samples and adds one
+        log.save_eval_tensors(batch(6, 3, 30), step_idx=7)
+        log.save_eval_tensors(batch(0, 3, 31), epoch_idx=2, batch_idx=1)
+        upd = batch(1, 3, 32)
+        upd['dataset_sample_index'] = torch.tensor([2, 7, 9])
+        upd['trajectory_sample_index'] = 3 * upd['dataset_sample_index'] + 1
+        log.save_eval_tensors(upd, step_idx=7, update=True)
+    reads['train_e0'] = log.read_train_tensors(epoch_idx=0, as_numpy=True)
+    reads['train_e0_b1'] = log.read_train_tensors(names=['potential'], step_idx=1, as_numpy=True)
+    reads['train_e0_nonan'] = log.read_train_tensors(epoch_idx=0, remove_nans=True, as_numpy=True)
+    reads['train_e1'] = log.read_train_tensors(epoch_idx=1, as_numpy=True)
+    reads['train_e1_nonan_pot'] = log.read_train_tensors(epoch_idx=1, remove_nans='potential', as_numpy=True)
+    reads['eval_s7'] = log.read_eval_tensors(step_idx=7, as_numpy=True)
+    reads['eval_s7_nonan'] = log.read_eval_tensors(names=['log_det_J'], step_idx=7, remove_nans='potential', as_numpy=True)
+    reads['eval_s7_sorted'] = log.read_eval_tensors(step_idx=7, sort_by='trajectory_sample_index', as_numpy=True)
+    return log, reads
+
+
 def build_oracle(case, dtype=torch.float32):
     m = fo.MafOracle(case['degrees_in'], case['spec'], hidden_layers=case['hidden_layers'],
                      weight_norm=case['weight_norm'], embedding=case.get('embedding'))

@@ -111,6 +111,16 @@ def golden_embeddings(ref):
     np.savez_compressed(os.path.join(OUT, 'embeddings.npz'), **out)
 
 
+def golden_logger(ref):
+    """A log directory written by the reference's TFEPLogger (tests/golden/tfep_logs) and what it reads back."""
+    import shutil
+    d = os.path.join(OUT, 'tfep_logs')
+    shutil.rmtree(d, ignore_errors=True)
+    _, reads = cases.logger_script(ref.TFEPLogger, d)
+    np.savez_compressed(os.path.join(OUT, 'tfep_logs_reads.npz'),
+                        **{f'{k}/{n}': v for k, r in reads.items() for n, v in r.items()})
+
+
 def golden_cfg(ref):
     """Slices of the BASELINE.json configurations, fp32 reference plus fp64 reference of the same bits."""
     out = {}
@@ -231,6 +241,7 @@ def main():
         finally:
             torch.set_default_dtype(old)
     golden_embeddings(ref)
+    golden_logger(ref)
     golden_cfg(ref)
     golden_analysis(ref)
     for f in sorted(os.listdir(OUT)):
