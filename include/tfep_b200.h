@@ -475,6 +475,50 @@ int tfepb_bayesian_bootstrap_sums(const float* e, int64_t n, int32_t n_resamples
                                   uint64_t philox_offset, double* out_sums, double* out_weight_sums,
                                   tfepb_stream_t stream);
 
+/* ----------------------------------------------------------------------------------------------
+ * Fused pre / post kernels of the wrapper flows (inference): the frame change, the gather of the propagated features
+ * into the contiguous tensor the wrapped flow consumes, and on the way back the scatter, the constrained coordinates
+ * and the inverse frame change -- one launch each side of the flow.
+ *   CenteredCentroidFlow._transform  nn/flows/centroid.py:194-263 (over PartialFlow._pass nn/flows/partial.py:88-121)
+ *   OrientedFlow._transform          nn/flows/oriented.py:182-225, frame: utils/geometry.py:296-411
+ * pre:  out (batch, n_propagated) = propagated features in the new frame; `shift` / `rotation` = the per-sample frame.
+ * post: out (batch, n_features) from y_propagated (the flow's output), the frame and the original input x.
+ * -------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t dtype, batch, n_features, space_dimension;      /* space_dimension <= 4 */
+    const void* x; int64_t ldx;
+    const void* y_propagated; int64_t ldy;                 /* post only */
+    void* out; int64_t ldout;
+    void* shift;                                           /* (batch, space_dimension): origin - centroid */
+    int32_t n_propagated;
+    const int32_t* propagated_columns;                     /* device, n_propagated */
+    const int32_t* column_to_propagated;                   /* device, n_features: position among the propagated, -1 if fixed */
+    const int32_t* centroid_points; int32_t n_centroid_points;   /* device point indices defining the centroid, or NULL = all */
+    const void* weights;                                   /* device, normalised weights of those points, or NULL (mean) */
+    double origin[4];
+    int32_t fixed_point, fixed_slot;                       /* point index of the fixed point; its position in centroid_points */
+    int32_t restore_fixed_point;                           /* post: place the fixed point so that the centroid is preserved */
+    int32_t translate_back;                                /* post: undo the translation */
+} tfepb_centroid_args;
+int tfepb_centroid_pre(const tfepb_centroid_args* a, tfepb_stream_t stream);
+int tfepb_centroid_post(const tfepb_centroid_args* a, tfepb_stream_t stream);
+
+typedef struct {
+    int32_t dtype, batch, n_features, n_propagated;        /* points of 3 coordinates; n_propagated = n_features - 3 */
+    const void* x; int64_t ldx;
+    const void* y_propagated; int64_t ldy;                 /* post only */
+    void* out; int64_t ldout;
+    void* rotation;                                        /* (batch, 9) row-major rotation matrices */
+    const int32_t* propagated_columns;
+    const int32_t* column_to_propagated;
+    int32_t axis_point, plane_point;                       /* point put on the axis / on the plane */
+    int32_t axis, plane_axis;                              /* 0 / 1 / 2 = x / y / z: the axis, the second axis spanning the plane */
+    int32_t round_off_imprecisions;                        /* the constrained coordinates are exactly zero in the frame */
+    int32_t rotate_back;                                   /* post: rotate back into the original frame */
+} tfepb_oriented_args;
+int tfepb_oriented_pre(const tfepb_oriented_args* a, tfepb_stream_t stream);
+int tfepb_oriented_post(const tfepb_oriented_args* a, tfepb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -317,3 +317,37 @@ def test_gradients_through_the_inverse(prec):
             gb = layer.bias.grad
             assert gb is not None, name
             assert float((gb.cpu() - b_o.grad).abs().max()) / (1 + float(b_o.grad.abs().max())) < tol, name
+
+
+def test_wrapper_flows_fused_kernels(prec):
+    """Outside autograd the wrapper flows run their fused pre / post kernels (tfep_b200/csrc/frames.cu): same results as
+    the reference's golden vectors and as the differentiable tensor-algebra path, forward and inverse."""
+    g = golden(f'wrappers_{prec}.npz')
+    for name, case in cases.wrapper_cases(DT[prec]).items():
+        if all(kind == 'partial' for kind, _ in case['layers']):
+            continue
+        _, sd = cases.build_oracle(case['inner'], DT[prec])
+        flow = to_wrapper(case, to_maf(case['inner'], sd, DEV, DT[prec]), DT[prec]).to(DEV)
+        x = case['x'].to(DEV)
+        with torch.no_grad():
+            y, ld = flow(x)                                           # kernels
+        ya, lda = flow(x.clone().requires_grad_(True))                # tensor algebra
+        assert flow._frame is not None, name
+        assert rel_err(y, g[f'{name}/y']) < 5 * TOL[prec] and rel_err(ld, g[f'{name}/ld']) < 5 * TOL[prec], name
+        assert rel_err(y, ya.detach()) < 5 * TOL[prec] and rel_err(ld, lda.detach()) < 5 * TOL[prec], name
+        if case['invertible']:
+            with torch.no_grad():
+                xi, ldi = flow.inverse(torch.from_numpy(g[f'{name}/y']).to(DEV))
+            assert rel_err(xi, g[f'{name}/xinv']) < 50 * TOL[prec] and rel_err(ldi, g[f'{name}/ldinv']) < 50 * TOL[prec], name
+    # a point exactly on the axis (parallel case of the frame) and ragged batch sizes
+    case = cases.wrapper_cases(DT[prec])['oriented']
+    _, sd = cases.build_oracle(case['inner'], DT[prec])
+    flow = to_wrapper(case, to_maf(case['inner'], sd, DEV, DT[prec]), DT[prec]).to(DEV)
+    x = case['x'].to(DEV).clone()
+    x[0, 0:3] = torch.tensor([2.5, 0.0, 0.0])
+    x[1, 0:3] = torch.tensor([-1.5, 0.0, 0.0])
+    for B in (1, 2, 7):
+        with torch.no_grad():
+            y, ld = flow(x[:B])
+        ya, lda = flow(x[:B].clone().requires_grad_(True))
+        assert rel_err(y, ya.detach()) < 5 * TOL[prec] and rel_err(ld, lda.detach()) < 5 * TOL[prec], B

@@ -99,6 +99,23 @@ class TcGemmArgs(Structure):
                 ('out_image_t', c_void_p), ('column_sums', c_void_p)]
 
 
+class CentroidArgs(Structure):
+    _fields_ = [('dtype', c_int32), ('batch', c_int32), ('n_features', c_int32), ('space_dimension', c_int32),
+                ('x', c_void_p), ('ldx', c_int64), ('y_propagated', c_void_p), ('ldy', c_int64), ('out', c_void_p),
+                ('ldout', c_int64), ('shift', c_void_p), ('n_propagated', c_int32), ('propagated_columns', c_void_p),
+                ('column_to_propagated', c_void_p), ('centroid_points', c_void_p), ('n_centroid_points', c_int32),
+                ('weights', c_void_p), ('origin', c_double * 4), ('fixed_point', c_int32), ('fixed_slot', c_int32),
+                ('restore_fixed_point', c_int32), ('translate_back', c_int32)]
+
+
+class OrientedArgs(Structure):
+    _fields_ = [('dtype', c_int32), ('batch', c_int32), ('n_features', c_int32), ('n_propagated', c_int32),
+                ('x', c_void_p), ('ldx', c_int64), ('y_propagated', c_void_p), ('ldy', c_int64), ('out', c_void_p),
+                ('ldout', c_int64), ('rotation', c_void_p), ('propagated_columns', c_void_p),
+                ('column_to_propagated', c_void_p), ('axis_point', c_int32), ('plane_point', c_int32), ('axis', c_int32),
+                ('plane_axis', c_int32), ('round_off_imprecisions', c_int32), ('rotate_back', c_int32)]
+
+
 class SweepArgs(Structure):
     _fields_ = [('dtype', c_int32), ('batch', c_int32), ('n_features', c_int32), ('n_linear', c_int32),
                 ('y', c_void_p), ('ldy', c_int64), ('x', c_void_p), ('ldx', c_int64), ('logdet', c_void_p),
@@ -131,6 +148,10 @@ SYMBOLS = {
     'tfepb_tc_pack': (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     'tfepb_tc_pack_dual': (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     'tfepb_tc_gemm': (c_int32, [POINTER(TcGemmArgs), c_void_p]),
+    'tfepb_centroid_pre': (c_int32, [POINTER(CentroidArgs), c_void_p]),
+    'tfepb_centroid_post': (c_int32, [POINTER(CentroidArgs), c_void_p]),
+    'tfepb_oriented_pre': (c_int32, [POINTER(OrientedArgs), c_void_p]),
+    'tfepb_oriented_post': (c_int32, [POINTER(OrientedArgs), c_void_p]),
     'tfepb_periodic_embedding': (c_int32, [c_int32, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_double, c_double,
                                            c_void_p, c_int64, c_void_p]),
     'tfepb_periodic_embedding_backward': (c_int32, [c_int32, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_double,

@@ -2,6 +2,7 @@
 
 import torch
 
+from ... import _frames
 from ...utils.geometry import atom_to_flattened, atom_to_flattened_indices, flattened_to_atom
 from ...utils.misc import ensure_tensor_sequence
 from .partial import PartialFlow
@@ -46,6 +47,7 @@ class CenteredCentroidFlow(PartialFlow):
         self.register_buffer('_weights', weights)
         self.register_buffer('origin', origin)
         self.translate_back = translate_back
+        self._frame = None
 
     @property
     def space_dimension(self):
@@ -76,7 +78,26 @@ class CenteredCentroidFlow(PartialFlow):
             return centroid - points[:, self._fixed_point_idx] * fixed_weight, fixed_weight
         return centroid
 
+    def _fused(self, x, inverse):
+        """Inference on the GPU: one fused kernel each side of the wrapped flow (tfep_b200/csrc/frames.cu)."""
+        if self._frame is None or self._frame.n_features != x.shape[1]:
+            subset = None if self._subset_point_indices is None else self._subset_point_indices.tolist()
+            slot = int(self._fixed_point_idx)
+            self._frame = _frames.CentroidFrame(
+                x.shape[1], self._space_dimension, self._fixed_indices.tolist(), subset,
+                None if self._weights is None else self._weights.detach().cpu(), slot,
+                slot if subset is None else subset[slot], self.origin.detach().cpu().tolist(),
+                restore=subset is None or len(subset) > 1, translate_back=self.translate_back)
+        x, x_prop, shift = self._frame.pre(x)
+        out = self.flow.inverse(x_prop) if inverse else self.flow(x_prop)
+        if self.return_partial:
+            return out
+        return (self._frame.post(x, out[0], shift), *out[1:])
+
     def _transform(self, x, inverse=False):
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if not needs_grad and _frames.usable(x) and self._space_dimension <= 4:
+            return self._fused(x, inverse)
         dim = self._space_dimension
         points = flattened_to_atom(x, dim)
         shift = (self.origin - self._centroid(points)).unsqueeze(dim=1)

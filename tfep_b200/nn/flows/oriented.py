@@ -2,6 +2,7 @@
 
 import torch
 
+from ... import _frames
 from ...utils.geometry import (atom_to_flattened, atom_to_flattened_indices, batchwise_rotate, flattened_to_atom,
                                get_axis_from_name, reference_frame_rotation_matrix)
 from .partial import PartialFlow
@@ -40,6 +41,7 @@ class OrientedFlow(PartialFlow):
         self.register_buffer('_plane_point_idx', torch.as_tensor(plane_point_idx))
         self.round_off_imprecisions = round_off_imprecisions
         self.rotate_back = rotate_back
+        self._frame = None
 
     def forward(self, x):
         return self._transform(x)
@@ -51,7 +53,22 @@ class OrientedFlow(PartialFlow):
                              " forward and inverse transformations.")
         return self._transform(y, inverse=True)
 
+    def _fused(self, x, inverse):
+        """Inference on the GPU: one fused kernel each side of the wrapped flow (tfep_b200/csrc/frames.cu)."""
+        if self._frame is None or self._frame.n_features != x.shape[1]:
+            self._frame = _frames.OrientedFrame(
+                x.shape[1], self._fixed_indices.tolist(), int(self._axis_point_idx), int(self._plane_point_idx),
+                int(self._axis.argmax()), int(self._plane_axis.argmax()), self.round_off_imprecisions, self.rotate_back)
+        x, x_prop, rot = self._frame.pre(x)
+        out = self.flow.inverse(x_prop) if inverse else self.flow(x_prop)
+        if self.return_partial:
+            return out
+        return (self._frame.post(x, out[0], rot), *out[1:])
+
     def _transform(self, x, inverse=False):
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if not needs_grad and _frames.usable(x) and x.shape[1] % 3 == 0:
+            return self._fused(x, inverse)
         points = flattened_to_atom(x)
         rotations = reference_frame_rotation_matrix(
             axis_atom_positions=points[:, self._axis_point_idx], plane_atom_positions=points[:, self._plane_point_idx],
