@@ -20,6 +20,7 @@ exist on the GPU box, the oracle restates it bit for bit -- see oracle/check_aga
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -31,7 +32,6 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 METRIC = 'MAF fwd+logdet samples/s (D=66, spline)'
 UNIT = 'samples/s'
@@ -104,17 +104,53 @@ class ClockSampler:
         return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
 
 
-def build_cpu_flow():
+N_FEATURES, N_LAYERS, N_BINS = 66, 4, 8
+
+
+def cfg2_degrees(layer):
+    """cfg2: layer l uses ascending degrees if l is even, descending otherwise."""
+    d = torch.arange(N_FEATURES)
+    return d if layer % 2 == 0 else d.flip(0)
+
+
+def cfg2_input(batch, seed=0):
+    """x = (rand * 2 - 1) * pi * 0.999, generated on the host from a seeded generator."""
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(batch, N_FEATURES, generator=g) * 2 - 1) * math.pi * 0.999
+
+
+def build_flow(device):
+    """cfg2 with this package's modules: 4 x MAF(circular spline K = 8) over 66 features, random-init weights
+    (torch.manual_seed(1234), initialize_identity=False as in SURVEY.md 8d: identity init would make the transformer
+    parameters input-independent)."""
+    from tfep_b200.nn.flows import MAF, SequentialFlow
+    from tfep_b200.nn.transformers import NeuralSplineTransformer
+    torch.manual_seed(1234)
+    lim = torch.full((N_FEATURES,), math.pi)
+    mafs = [MAF(degrees_in=cfg2_degrees(l),
+                transformer=NeuralSplineTransformer(x0=-lim, xf=lim, n_bins=N_BINS, circular=True),
+                hidden_layers=2, weight_norm=True, initialize_identity=False) for l in range(N_LAYERS)]
+    return SequentialFlow(*mafs).to(device)
+
+
+def oracle_flow(state_dicts=None):
+    """The same cfg2 flow as a list of oracle layers (CPU restatement of the reference).  Test infrastructure: only the
+    cpu_baseline leg and the reference arm come here.  ``state_dicts``: per layer, the product modules' parameters
+    (reference key names), so that both arms evaluate the same weights; None: the oracle's own seeded weights."""
     from oracle import cases
-    return cases.cfg_flow('cfg2'), cases
+    from oracle import flow_oracle as fo
+    if state_dicts is None:
+        return [m for m, _ in cases.cfg_flow('cfg2')]
+    lim = torch.full((N_FEATURES,), math.pi)
+    return [fo.MafOracle(cfg2_degrees(l), fo.Spline(x0=-lim, xf=lim, n_bins=N_BINS, circular=True)).load(sd)
+            for l, sd in enumerate(state_dicts)]
 
 
-def time_cpu_reference(steps, warmup, sample=CPU_SAMPLE):
+def time_cpu_reference(steps, warmup, sample=CPU_SAMPLE, state_dicts=None):
     """The reference's CPU PyTorch path (oracle restatement), all host threads, no_grad."""
     from oracle import flow_oracle as fo
-    flows, cases = build_cpu_flow()
-    mods = [m for m, _ in flows]
-    x = cases.cfg_input('cfg2', sample)
+    mods = oracle_flow(state_dicts)
+    x = cfg2_input(sample)
     torch.set_num_threads(os.cpu_count() or 1)
     times = []
     with torch.no_grad():
@@ -150,19 +186,17 @@ def run_reference(args, rank):
 
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
-    from helpers import cfg_flow_modules
-    from oracle import cases
     from tfep_b200 import _ops
 
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
     from tfep_b200.utils.host_pipeline import gpu_numa_affinity
-    seq, _ = cfg_flow_modules('cfg2', dev)
+    seq = build_flow(dev)
     seq.eval()
     for maf in seq:
         maf.precision = args.precision
     # contiguous batch shards of one global synthetic data set (seeded on the host)
-    x_host = cases.cfg_input('cfg2', BATCH * world)[rank * BATCH:(rank + 1) * BATCH].contiguous()
+    x_host = cfg2_input(BATCH * world)[rank * BATCH:(rank + 1) * BATCH].contiguous()
     with gpu_numa_affinity(dev):              # pinned input buffer on the NUMA node of this rank's GPU
         x_host = x_host.pin_memory()
     x = x_host.to(dev)
@@ -319,7 +353,8 @@ def run_ours(args, rank, world, local_rank):
                 'whole_step_frac': (2.0 * plan.masked_macs * 4 * BATCH * args.steps / (total_ms * 1e-3) / 1e12)
                 / pk_peaks['bf16_tflops_sustained']}
 
-    sample, times, cores = time_cpu_reference(2, 1)
+    sample, times, cores = time_cpu_reference(2, 1, state_dicts=[{k: v.detach().cpu() for k, v in m.state_dict().items()}
+                                                                  for m in seq])
     cpu_value = sample * len(times) / sum(times)
 
     value = BATCH * world * args.steps / (total_ms * 1e-3)
