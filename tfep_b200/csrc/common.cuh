@@ -38,6 +38,8 @@ inline int check_launch(const char* what) {
 // Refuse to run anywhere but Blackwell datacenter parts: there is no fallback path.
 int require_sm100();
 int sm_count();
+// raise the dynamic shared memory limit of `kernel` on the current device to at least `bytes` (cached)
+int ensure_dynamic_smem(const void* kernel, size_t bytes);
 
 inline cudaStream_t as_stream(tfepb_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

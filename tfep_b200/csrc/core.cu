@@ -48,6 +48,24 @@ int require_sm100() {
     return 0;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of a kernel: remember, per (device, kernel), the
+// largest size configured so far (a process may drive several GPUs from one thread).
+int ensure_dynamic_smem(const void* kernel, size_t bytes) {
+    struct Entry { int device; const void* kernel; size_t bytes; };
+    static thread_local Entry table[64];
+    static thread_local int used = 0;
+    int dev = -1;
+    TFEPB_CUDA(cudaGetDevice(&dev));
+    Entry* e = nullptr;
+    for (int i = 0; i < used; ++i)
+        if (table[i].device == dev && table[i].kernel == kernel) e = &table[i];
+    if (e != nullptr && e->bytes >= bytes) return 0;
+    TFEPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (e == nullptr && used < 64) e = &table[used++];
+    if (e != nullptr) *e = Entry{dev, kernel, bytes};
+    return 0;
+}
+
 int sm_count() {
     DeviceCache c;
     if (query(&c) != 0) return 148;

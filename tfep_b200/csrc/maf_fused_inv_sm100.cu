@@ -562,11 +562,7 @@ extern "C" int tfepb_maf_spline_inverse_bf16(const tfepb_fused_inv_args* a, tfep
     TFEPB_CHECK_ARG(smem <= 227 * 1024, "shared memory plan of %zu bytes exceeds 227 KB", smem);
     const bool mixed = a->mixed_splines != 0;      // some features are not circular: generic spline epilogue
     auto kernel = mixed ? finv::maf_spline_inv_kernel<true> : finv::maf_spline_inv_kernel<false>;
-    static thread_local size_t configured[2] = {0, 0};
-    if (configured[mixed] < smem) {
-        TFEPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[mixed] = smem;
-    }
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), smem)) return rc;
     const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
     kernel<<<grid, finv::THREADS, smem, as_stream(stream)>>>(p);
     return check_launch("maf_spline_inv_kernel");

@@ -699,12 +699,7 @@ extern "C" int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_st
     const bool mixed = a->mixed_splines != 0;      // some features are not circular: generic spline epilogue
     auto kernel = debug ? (mixed ? fused::maf_spline_fwd_kernel<true, true> : fused::maf_spline_fwd_kernel<true, false>)
                         : (mixed ? fused::maf_spline_fwd_kernel<false, true> : fused::maf_spline_fwd_kernel<false, false>);
-    static thread_local size_t configured[4] = {0, 0, 0, 0};
-    const int variant = (debug ? 2 : 0) + (mixed ? 1 : 0);
-    if (configured[variant] < smem) {
-        TFEPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[variant] = smem;
-    }
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), smem)) return rc;
     // one CTA per SM; never more CTAs than tiles, so that the items a CTA waits for belong to CTAs that run
     const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
     kernel<<<grid, fused::THREADS, smem, as_stream(stream)>>>(p);

@@ -486,11 +486,7 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
     p.k_chunk_blocks = splits > 1 ? (p.k_blocks + splits - 1) / splits : 0;
     if (splits > 1) splits = (p.k_blocks + p.k_chunk_blocks - 1) / p.k_chunk_blocks;
     const size_t smem = (size_t)tcg::STAGES * tcg::STAGE_BYTES + (size_t)tcg::EPI_WARPS * tcg::XP_FLOATS * 4 + sizeof(tcg::Smem) + 1024;
-    static thread_local bool configured = false;
-    if (!configured) {
-        TFEPB_CUDA(cudaFuncSetAttribute(tcg::tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(tcg::tc_gemm_kernel), smem)) return rc;
     const int tiles = p.tiles_m * p.tiles_n;
     int gx = sm_count() / splits;
     if (gx < 1) gx = 1;
