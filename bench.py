@@ -344,7 +344,7 @@ def run_ours(args, rank, world, local_rank):
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': pk_peaks['bf16_tflops'], 'unit': 'TFLOP/s',
                 'frac': achieved / pk_peaks['bf16_tflops'],
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture of the
-                # bf16 chain launch at this workload (profiles/r01_ncu_fused_fwd_v6_chain_details.md): 21.08 MB read
+                # bf16 chain launch at this workload (profiles/r01_ncu_fused_fwd_v8_chain_details.md): 21.08 MB read
                 # (x 17.3 MB + packed weights) + 0.15 MB written -- the 17.6 MB of y / logdet were still in L2 when
                 # the kernel ended; the algorithmic HBM bytes are 34.9 MB per launch
                 'traffic': 21.23e6 if (args.precision == 'bf16' and BATCH == 65536) else None,
