@@ -357,3 +357,20 @@ def test_bf16_outside_the_fused_kernel_uses_the_tensor_core_gemm():
         affine.precision = 'bf16'
         yb, ldb = affine(xa)
     assert float((ya - yb).abs().max()) < 5e-2 and float((lda - ldb).abs().max()) < 5e-2
+
+
+def test_empty_batches_through_the_fused_paths():
+    """B = 0 is legal everywhere (the reference's flows accept it): chain forward / inverse, one layer, and the wrapper
+    flows' fused pre / post kernels."""
+    from tfep_b200.nn.flows import CenteredCentroidFlow, OrientedFlow
+    seq, _ = cfg_flow_modules('cfg2', DEV, n_layers=2)
+    for maf in seq:
+        maf.precision = 'bf16'
+    x = torch.empty(0, 66, device=DEV)
+    with torch.no_grad():
+        for fn in (seq, seq.inverse, seq[0], seq[0].inverse):
+            y, ld = fn(x)
+            assert y.shape == (0, 66) and ld.shape == (0,)
+        wrapped = CenteredCentroidFlow(OrientedFlow(seq), space_dimension=3).to(DEV)
+        y, ld = wrapped(torch.empty(0, 72, device=DEV))
+        assert y.shape == (0, 72) and ld.shape == (0,)

@@ -351,3 +351,23 @@ def test_wrapper_flows_fused_kernels(prec):
             y, ld = flow(x[:B])
         ya, lda = flow(x[:B].clone().requires_grad_(True))
         assert rel_err(y, ya.detach()) < 5 * TOL[prec] and rel_err(ld, lda.detach()) < 5 * TOL[prec], B
+
+
+def test_empty_batches(prec):
+    """B = 0 through every MAF path: exact forward / inverse sweep for each transformer family, embedded and
+    conditioned flows, and the general tensor-core conditioner (precision='bf16' outside the fused kernel)."""
+    for name, case in cases.maf_cases(DT[prec]).items():
+        _, sd = cases.build_oracle(case, DT[prec])
+        maf = to_maf(case, sd, DEV, DT[prec])
+        n = case['x'].shape[1]
+        x = torch.empty(0, n, dtype=DT[prec], device=DEV)
+        with torch.no_grad():
+            y, ld = maf(x)
+            assert y.shape == (0, n) and ld.shape == (0,), name
+            if case['invertible']:
+                xi, ldi = maf.inverse(x)
+                assert xi.shape == (0, n) and ldi.shape == (0,), name
+            if prec == 'f32':
+                maf.precision = 'bf16'
+                y, ld = maf(x)
+                assert y.shape == (0, n) and ld.shape == (0,), name

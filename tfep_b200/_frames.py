@@ -72,17 +72,19 @@ class CentroidFrame(_Frame):
         x = x.contiguous()
         out = torch.empty(x.shape[0], self.n_prop, dtype=x.dtype, device=x.device)
         shift = torch.empty(x.shape[0], self.dim, dtype=x.dtype, device=x.device)
-        a = self._args(x, None, out, shift)
-        with torch.cuda.device(x.device):
-            check(_lib.load().tfepb_centroid_pre(ctypes.byref(a), stream_ptr(x)))
+        if x.shape[0] > 0:
+            a = self._args(x, None, out, shift)
+            with torch.cuda.device(x.device):
+                check(_lib.load().tfepb_centroid_pre(ctypes.byref(a), stream_ptr(x)))
         return x, out, shift
 
     def post(self, x, y_prop, shift):
         y_prop = y_prop.contiguous()
         out = torch.empty_like(x)
-        a = self._args(x, y_prop, out, shift)
-        with torch.cuda.device(x.device):
-            check(_lib.load().tfepb_centroid_post(ctypes.byref(a), stream_ptr(x)))
+        if x.shape[0] > 0:
+            a = self._args(x, y_prop, out, shift)
+            with torch.cuda.device(x.device):
+                check(_lib.load().tfepb_centroid_post(ctypes.byref(a), stream_ptr(x)))
         return out
 
 
@@ -107,15 +109,17 @@ class OrientedFrame(_Frame):
         x = x.contiguous()
         out = torch.empty(x.shape[0], self.n_prop, dtype=x.dtype, device=x.device)
         rot = torch.empty(x.shape[0], 9, dtype=x.dtype, device=x.device)
-        a = self._args(x, None, out, rot)
-        with torch.cuda.device(x.device):
-            check(_lib.load().tfepb_oriented_pre(ctypes.byref(a), stream_ptr(x)))
+        if x.shape[0] > 0:
+            a = self._args(x, None, out, rot)
+            with torch.cuda.device(x.device):
+                check(_lib.load().tfepb_oriented_pre(ctypes.byref(a), stream_ptr(x)))
         return x, out, rot
 
     def post(self, x, y_prop, rot):
         y_prop = y_prop.contiguous()
         out = torch.empty_like(x)
-        a = self._args(x, y_prop, out, rot)
-        with torch.cuda.device(x.device):
-            check(_lib.load().tfepb_oriented_post(ctypes.byref(a), stream_ptr(x)))
+        if x.shape[0] > 0:
+            a = self._args(x, y_prop, out, rot)
+            with torch.cuda.device(x.device):
+                check(_lib.load().tfepb_oriented_post(ctypes.byref(a), stream_ptr(x)))
         return out

@@ -501,6 +501,8 @@ def run_chain(plans_mafs, x, debug_params=None):
     B = x.shape[0]
     y = torch.empty_like(x)
     ld = torch.empty(B, dtype=torch.float32, device=x.device)
+    if B == 0:
+        return y, ld
     layers = (_lib.FusedLayer * n_layers)()
     keep = []
     for i, (pl, maf) in enumerate(plans_mafs):
@@ -560,6 +562,8 @@ def run_inverse_chain(plans_mafs, y):
     B = y.shape[0]
     x = torch.empty_like(y)
     ld = torch.empty(B, dtype=torch.float32, device=y.device)
+    if B == 0:
+        return x, ld
     layers = (_lib.FusedInvLayer * n_layers)()
     keep = []
     for i, (pl, maf) in enumerate(plans_mafs):

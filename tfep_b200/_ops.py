@@ -493,4 +493,6 @@ class MadeFunctionTC(torch.autograd.Function):
 
 
 def made_forward_tc(x, weights, biases, kb_fwd=None, kb_bwd=None, rr_w=None):
+    if x.shape[0] == 0:                       # nothing to launch; zero-sized result tied to the inputs for autograd
+        return x.new_zeros((0, weights[-1].shape[0])) + 0.0 * sum(w.sum() + b.sum() for w, b in zip(weights, biases))
     return MadeFunctionTC.apply(x, len(weights), kb_fwd, kb_bwd, rr_w, *weights, *biases)

@@ -160,6 +160,8 @@ class SweepPlan:
         B = y.shape[0]
         x = torch.empty_like(y)
         ld = torch.empty(B, dtype=y.dtype, device=y.device)
+        if B == 0:
+            return x, ld
         a = _lib.SweepArgs()
         a.dtype, a.batch, a.n_features, a.n_linear = dtype_code(y), B, self.D, self.L
         a.y, a.ldy, a.x, a.ldx, a.logdet = y.data_ptr(), y.stride(0) if B > 1 else self.D, x.data_ptr(), self.D, ld.data_ptr()
