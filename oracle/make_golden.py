@@ -121,6 +121,32 @@ def golden_logger(ref):
                         **{f'{k}/{n}': v for k, r in reads.items() for n, v in r.items()})
 
 
+def golden_pca(ref, dtype, tag):
+    """PCAWhitenedFlow of the reference around a reference MAF: its buffers (the eigenvector signs are a LAPACK
+    convention, so tests load them), outputs in both directions and the x-gradient, with and without blackening."""
+    out = {}
+    case = cases.wrapper_cases(dtype)['partial']['inner']
+    _, sd = cases.build_oracle(case, dtype)
+    data = cases.normal((200, 5), 70, dtype) * torch.tensor([1.0, 2.0, 0.5, 3.0, 1.5], dtype=dtype) + 0.3
+    x = cases.normal((12, 5), 71, dtype)
+    for blacken in (True, False):
+        flow = ref.PCAWhitenedFlow(to_reference_maf(ref, case, sd), data, blacken=blacken)
+        key = 'blacken' if blacken else 'whitened'
+        for k, v in flow.state_dict().items():
+            if not k.startswith('flow.'):
+                out[f'{key}/sd/{k}'] = _np(v)
+        xg = x.clone().requires_grad_(True)
+        y, ld = flow(xg)
+        cy, cl = cases.normal(tuple(y.shape), 78, dtype), cases.normal(tuple(ld.shape), 79, dtype)
+        ((y * cy).sum() + (ld * cl).sum()).backward()
+        with torch.no_grad():
+            xi, ldi = flow.inverse(y.detach())
+        out[f'{key}/y'], out[f'{key}/ld'], out[f'{key}/gx'] = _np(y), _np(ld), _np(xg.grad)
+        out[f'{key}/xinv'], out[f'{key}/ldinv'] = _np(xi), _np(ldi)
+    out['data'], out['x'] = _np(data), _np(x)
+    np.savez_compressed(os.path.join(OUT, f'pca_{tag}.npz'), **out)
+
+
 def golden_cfg(ref):
     """Slices of the BASELINE.json configurations, fp32 reference plus fp64 reference of the same bits."""
     out = {}
@@ -238,6 +264,7 @@ def main():
             golden_transformers(ref, dtype, tag)
             golden_mafs(ref, dtype, tag)
             golden_wrappers(ref, dtype, tag)
+            golden_pca(ref, dtype, tag)
         finally:
             torch.set_default_dtype(old)
     golden_embeddings(ref)
