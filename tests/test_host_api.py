@@ -300,3 +300,13 @@ def test_learnable_embeddings_match_reference_golden(name):
     else:
         with pytest.raises(ValueError, match='must be assigned to different feature indices'):
             type(emb)(6, list(emb.embedding_layers), [[0, 1, 2, 3], [3, 4]])
+
+
+def test_sos_function_name_and_coefficients():
+    from tfep_b200.nn.transformers import SOSPolynomialTransformerFunc, sos_polynomial_transformer
+    assert SOSPolynomialTransformerFunc.apply is sos_polynomial_transformer
+    par = cases.normal((5, 7, 3), 55)
+    a0, c1, c2, c3 = SOSPolynomialTransformerFunc.get_sos_poly_coefficients(par)
+    k0, k1 = par[:, 1::2], par[:, 2::2]
+    assert torch.equal(a0, par[:, 0]) and torch.allclose(c1, (k0 ** 2).sum(1)) and torch.allclose(c2, (k0 * k1).sum(1))
+    assert torch.allclose(c3, (k1 ** 2).sum(1) / 3) and c3.shape == (5, 3)

@@ -5,6 +5,6 @@ from .affine import (AffineTransformer, VolumePreservingShiftTransformer, affine
 from .mixed import MixedTransformer
 from .moebius import (MoebiusTransformer, SymmetrizedMoebiusTransformer, moebius_transformer,
                       symmetrized_moebius_transformer, symmetrized_moebius_transformer_inverse)
-from .sos import SOSPolynomialTransformer, sos_polynomial_transformer
+from .sos import SOSPolynomialTransformer, SOSPolynomialTransformerFunc, sos_polynomial_transformer
 from .spline import NeuralSplineTransformer, neural_spline_transformer
 from .transformer import MAFTransformer, Transformer

@@ -60,3 +60,17 @@ def sos_polynomial_transformer(x, parameters):
     batch, n_par, n_features = parameters.shape
     t = SOSPolynomialTransformer((n_par - 1) // 2)
     return _program.run(t._parts(n_features), x, parameters.reshape(batch, -1))
+
+
+class SOSPolynomialTransformerFunc:
+    """Name kept for callers of the reference's ``SOSPolynomialTransformerFunc.apply(x, parameters)`` (sos.py:207-310):
+    the forward and the hand-written backward live in the CUDA kernels (tfepb_sos / tfepb_sos_backward)."""
+
+    apply = staticmethod(sos_polynomial_transformer)
+
+    @staticmethod
+    def get_sos_poly_coefficients(parameters):
+        """List of the four ``(batch, n_features)`` coefficients ``a0, c1, c2, c3`` of ``y = a0 + c1 x + c2 x^2 + c3 x^3``
+        from the ``(batch, 1 + 2 K, n_features)`` parameters (reference sos.py:271-306; host-side helper, tensor algebra)."""
+        k0, k1 = parameters[:, 1::2], parameters[:, 2::2]
+        return [parameters[:, 0], (k0 * k0).sum(dim=1), (k0 * k1).sum(dim=1), (k1 * k1).sum(dim=1) / 3]
