@@ -1,0 +1,52 @@
+"""The JSON line bench.py prints (the driver's contract): keys, types and internal consistency, for the measured arm
+on the GPU and for the CPU reference arm."""
+
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+             'vs_baseline', 'dtype', 'data', 'config', 'e2e', 'gpu_launches', 'cpu_baseline'}
+
+
+def _run(*args):
+    res = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), *args], capture_output=True, text=True,
+                         timeout=900, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith('{')]
+    assert len(lines) == 1, res.stdout
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line():
+    d = _run('--impl', 'reference', '--steps', '1', '--warmup', '1')
+    assert BASE_KEYS <= set(d) and d['impl'] == 'reference'
+    assert d['metric'].startswith('MAF fwd+logdet samples/s') and d['unit'] == 'samples/s' and d['higher_is_better'] is True
+    assert d['value'] > 0 and d['e2e'] == {'value': d['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0,
+                                           'd2h_bytes_per_step': 0}
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert 'workload' in d['config'] and d['gpu_launches'] == 0
+
+
+@pytest.mark.gpu
+def test_measured_arm_line():
+    d = _run('--steps', '5', '--warmup', '3')
+    assert BASE_KEYS | {'clocks', 'roofline'} <= set(d) and 'impl' not in d
+    assert d['n_gpus'] == 1 and d['steps'] == 5 and d['warmup'] == 3 and d['scaling'] == 'weak' and d['dtype'] == 'bf16'
+    assert d['data'] == 'synthetic' and d['vs_baseline'] is None and 'workload' in d['config']
+    assert abs(d['value'] - 65536 / (d['ms_per_step'] * 1e-3)) < 1e-6 * d['value']
+    e = d['e2e']
+    assert 0 < e['value'] <= d['value'] and e['h2d_bytes_per_step'] == 65536 * 66 * 4
+    assert e['d2h_bytes_per_step'] == 65536 * 67 * 4 and e['unit'] == 'samples/s'
+    r = d['roofline']
+    assert r['bound'] == 'tensor' and r['unit'] == 'TFLOP/s' and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9
+    assert 0.05 < r['frac'] < 1.0 and r['traffic'] is not None
+    c = d['cpu_baseline']
+    assert c['kind'] == 'port' and c['value'] > 0 and c['cores'] >= 1 and 'sample' in c
+    assert d['gpu_launches'] == d['steps']                      # one chain launch per step
+    assert set(d['clocks']) >= {'sm_mhz', 'sm_max_mhz', 'reasons'}
+    assert d['value'] > 1000 * c['value']                      # the kernels, not a CPU fallback, produced the number
