@@ -310,3 +310,21 @@ def test_sos_function_name_and_coefficients():
     k0, k1 = par[:, 1::2], par[:, 2::2]
     assert torch.equal(a0, par[:, 0]) and torch.allclose(c1, (k0 ** 2).sum(1)) and torch.allclose(c2, (k0 * k1).sum(1))
     assert torch.allclose(c3, (k1 ** 2).sum(1) / 3) and c3.shape == (5, 3)
+
+
+@pytest.mark.parametrize('axis,plane,expected', [(None, None, (0, 1)), (None, 0, (1, 0)), (0, None, (0, 1)), (2, None, (2, 0)),
+                                                 (None, 3, (0, 3)), (1, 2, (1, 2))])
+def test_oriented_flow_point_selection_and_partial_output(axis, plane, expected):
+    """Automatic choice of the axis / plane points and ``return_partial`` (reference tests/nn/flows/test_oriented.py:
+    test_automatic_axis_plane_selection, test_return_partial)."""
+    from helpers import OracleFlowModule
+    from tfep_b200.nn.flows import OrientedFlow
+    inner, _ = cases.build_oracle(cases.wrapper_cases()['oriented']['inner'], torch.float32)
+    flow = OrientedFlow(OracleFlowModule(inner), axis_point_idx=axis, plane_point_idx=plane)
+    assert (int(flow._axis_point_idx), int(flow._plane_point_idx)) == expected
+    x = cases.normal((3, 12), 5)
+    y, ld = flow(x)
+    assert y.shape == (3, 12) and ld.shape == (3,)
+    flow.return_partial = True
+    y, ld = flow(x)
+    assert y.shape == (3, 9)
