@@ -204,3 +204,21 @@ def test_estimator_unaligned_views_and_sizes():
     d64 = base.double().to(DEV)
     for off in (0, 1):
         assert rel_err(fep_estimator(d64[off:off + 999]), ao.fep_estimator(base[off:off + 999].double())) < 1e-12
+
+
+@pytest.mark.parametrize('method', ['percentile', 'basic'])
+@pytest.mark.parametrize('batch', [None, 100])
+def test_generic_statistic_against_scipy(method, batch):
+    """The reference's own test (tests/analysis/test_bootstrap.py:test_against_scipy): a generic vectorised statistic
+    through the gather path, compared with scipy.stats.bootstrap at the reference's tolerances."""
+    import numpy as np
+    import scipy.stats
+    from tfep_b200.analysis import bootstrap
+    data = torch.randn(100, generator=torch.Generator().manual_seed(0), dtype=torch.float64)
+    ours = bootstrap(data.to(DEV), lambda d, vectorized=True: torch.std(d, dim=-1), n_resamples=10000, batch=batch,
+                     method=method, generator=torch.Generator().manual_seed(1))
+    ref = scipy.stats.bootstrap(data.unsqueeze(0).numpy(), np.std, vectorized=False, n_resamples=10000, method=method,
+                                random_state=np.random.RandomState(0))
+    assert abs(float(ours['confidence_interval']['low']) - ref.confidence_interval.low) < 1e-1
+    assert abs(float(ours['confidence_interval']['high']) - ref.confidence_interval.high) < 1e-1
+    assert abs(float(ours['standard_deviation']) - ref.standard_error) < 1e-2
