@@ -295,7 +295,7 @@ def build_oracle(case, dtype=torch.float32):
 # BASELINE.json configurations
 # ---------------------------------------------------------------------------
 
-def cfg_flow(name, dtype=torch.float32, n_layers=None, D=None):
+def cfg_flow(name, dtype=torch.float32, n_layers=None, D=None, hidden_layers=2):
     """Return a list of (MafOracle, state_dict) for a BASELINE.json configuration."""
     if name == 'cfg1':           # 2 x MAF Affine, D=66
         D, L = D or 66, n_layers or 2
@@ -342,7 +342,7 @@ def cfg_flow(name, dtype=torch.float32, n_layers=None, D=None):
             emb = fo.PeriodicEmbed(D, torch.tensor([-math.pi, math.pi], dtype=dtype), [f for f in range(D) if f % 3 == 2])
         if name == 'cfg2condemb':       # every feature, the conditioning ones included, enters as (cos, sin)
             emb = fo.PeriodicEmbed(D, torch.tensor([-math.pi, math.pi], dtype=dtype))
-        m = fo.MafOracle(deg, spec, embedding=emb)
+        m = fo.MafOracle(deg, spec, hidden_layers=hidden_layers, embedding=emb)
         sd = seeded_state([k.to(dtype) for k in m.masks], 1234 + l, dtype)
         flows.append((m.load(sd), sd))
     return flows

@@ -64,6 +64,19 @@ if 'cfg2mix' in which:
     out(config='cfg2mix 4xMAF Mixed(circular + ordinary spline) D=66 B=65536, bf16 tensor-core chain kernels',
         forward_ms=ms, forward_samples_per_s=65536 / ms * 1e3, inverse_ms=msi, inverse_samples_per_s=65536 / msi * 1e3,
         round_trip_median_err=float((xi - x).abs().max(dim=1).values.median()))
+if 'cfg2mixemb' in which:
+    # the shape of the reference's MixedMAFMap (app/mixedmaf.py:341-353): the mix above with the 22 torsions lifted to
+    # (cos, sin) in front of the conditioner; hidden widths 334 so that the layers fit the fused kernels
+    seq, _ = cfg_flow_modules('cfg2mixemb', dev, hidden_layers=[334, 334])
+    for m in seq:
+        m.precision = 'bf16'
+    x = cases.cfg_input('cfg2mixemb', 65536).to(dev)
+    with torch.no_grad():
+        ms = timed(lambda: seq(x), 20, 5)
+        y, ld = seq(x)
+        msi = timed(lambda: seq.inverse(y), 5, 2)
+    out(config='cfg2mixemb 4xMAF Mixed splines + PeriodicEmbedding (88 conditioner inputs, hidden 334) D=66 B=65536, bf16 chain kernels',
+        forward_ms=ms, forward_samples_per_s=65536 / ms * 1e3, inverse_ms=msi, inverse_samples_per_s=65536 / msi * 1e3)
 if 'cfg3' in which:
     B = 262144
     for precision in ('fp32', 'bf16'):

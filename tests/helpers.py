@@ -85,13 +85,14 @@ class OracleFlowModule(torch.nn.Module):
         return 0
 
 
-def cfg_flow_modules(name, device, n_layers=None, D=None, dtype=torch.float32):
+def cfg_flow_modules(name, device, n_layers=None, D=None, dtype=torch.float32, hidden_layers=2):
     """BASELINE.json configuration as (tfep_b200 SequentialFlow on `device`, [oracle flows])."""
     from tfep_b200.nn.flows import SequentialFlow
-    flows = cases.cfg_flow(name, torch.float32, n_layers=n_layers, D=D)
+    flows = cases.cfg_flow(name, torch.float32, n_layers=n_layers, D=D, hidden_layers=hidden_layers)
     mafs = []
     for m, sd in flows:
-        case = dict(degrees_in=m.degrees_in, spec=m.transformer, hidden_layers=2, weight_norm=True, embedding=m.embedding)
+        case = dict(degrees_in=m.degrees_in, spec=m.transformer, hidden_layers=hidden_layers, weight_norm=True,
+                    embedding=m.embedding)
         mafs.append(to_maf(case, {k: v.to(dtype) for k, v in sd.items()}, dtype=dtype))
     return SequentialFlow(*mafs).to(device), flows
 

@@ -255,6 +255,34 @@ def test_narrow_and_odd_widths(cfg, D):
             assert float(d.median()) < 2e-5 and float((ld + ldi).abs().median()) < 5e-5
 
 
+def test_mixed_maf_map_shape_with_explicit_hidden_widths():
+    """The shape the reference's MixedMAFMap builds at D = 66 (22 torsions lifted to (cos, sin), circular splines on them,
+    ordinary splines on the 44 Cartesians): with the default hidden width (381) the layers fall outside the
+    tensor-memory plan, with ``hidden_layers=[334, 334]`` the whole chain runs on the fused kernels in both directions."""
+    seq, _ = cfg_flow_modules('cfg2mixemb', DEV, n_layers=4, D=66, hidden_layers=[334, 334])
+    x = cases.cfg_input('cfg2mixemb', 4000, D=66).to(DEV)
+    period = torch.full((66,), float('inf'))
+    period[[f for f in range(66) if f % 3 == 2]] = 2 * math.pi
+
+    def dist(a, b):
+        d = (a.double().cpu() - b.double().cpu()).abs()
+        return torch.minimum(d, (period - d).abs())
+
+    with torch.no_grad():
+        y32, ld32 = seq[0](x)
+        for maf in seq:
+            maf.precision = 'bf16'
+            assert maf._fused_plan() is not None and maf._fused_plan().inverse_eligibility(maf) is None, maf._fused_why
+        y, ld = seq[0](x)
+        assert float(dist(y, y32).max()) < 5e-2 and float(dist(y, y32).mean()) < 2e-3
+        assert float((ld - ld32).abs().mean()) < 8e-3
+        yc, ldc = seq(x)                              # one launch for the four layers
+        xc, ldci = seq.inverse(yc)
+        d = dist(xc, x).max(dim=1).values
+        assert float(d.median()) < 1e-4 and float((ldc + ldci).abs().median()) < 2e-4
+        assert int(seq[0]._fused._tables(torch.device(DEV))['err'].item()) == 0
+
+
 @pytest.mark.parametrize('cfg,D', [('cfg2cond', 66), ('cfg2condemb', 36)])
 def test_conditioning_features(cfg, D):
     """Features of degree -1 (conditioning atoms) feed the conditioner and pass through.  Forward: no slot, no output

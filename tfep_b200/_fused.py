@@ -140,7 +140,8 @@ class FusedSplinePlan:
         self.H = H1
         self.HP = _ceil16(H1 + 2)                     # packed units 0, 1 are the constant ones
         if self.HP > 336 or self.K1 > 352:
-            raise _lib.TfepB200Error('layer widths exceed the tensor-memory plan of the fused kernel')
+            raise _lib.TfepB200Error('layer widths exceed the tensor-memory plan of the fused kernel (at most 334 hidden units '
+                                     'and 350 conditioner inputs: e.g. MAF(..., hidden_layers=[334, 334]))')
         self.perm1, self.perm2 = plan.perms[1], plan.perms[2]
 
         # Hidden layers are computed and handed over in two column halves (rows of the GEMM = columns of the
