@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TFEPB_ABI_VERSION 3
+#define TFEPB_ABI_VERSION 4
 
 enum { TFEPB_F32 = 0, TFEPB_F64 = 1 };
 enum { TFEPB_ACT_NONE = 0, TFEPB_ACT_ELU = 1 };
@@ -474,6 +474,24 @@ int tfepb_bootstrap_sums(const float* e, int64_t n, int64_t shard_lo, uint32_t m
 int tfepb_bayesian_bootstrap_sums(const float* e, int64_t n, int32_t n_resamples, uint64_t philox_seed,
                                   uint64_t philox_offset, double* out_sums, double* out_weight_sums,
                                   tfepb_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * BoltzmannKLDivLoss (tfep/loss.py:76-140) as one streaming reduction: rw_i = target_i - log_det_J_i - ref_i
+ * (loss.py:125-129), then mean_i rw_i (loss.py:140; ignore_nan: torch.nanmean, loss.py:139) or, with log_weights,
+ * sum_i softmax(log_weights)_i rw_i (loss.py:132-136; ignore_nan: torch.nansum), the softmax folded into the same
+ * pass as an online (max, sum e, sum e rw) triple.  log_det_J, ref_potentials and log_weights may be NULL.
+ * out5 (device doubles): loss, max log-weight, sum exp(log_w - max), number of kept terms, 1 if a log-weight was NaN;
+ * the backward entry point reads them back as `stats5` and writes the cotangents of the four inputs (any may be NULL)
+ * given the device scalar grad_out.  `workspace`: tfepb_kl_loss_workspace_bytes() bytes.
+ * -------------------------------------------------------------------------------------------- */
+int64_t tfepb_kl_loss_workspace_bytes(void);
+int tfepb_kl_loss(int32_t dtype, const void* target_potentials, const void* log_det_J, const void* ref_potentials,
+                  const void* log_weights, int64_t n, int32_t ignore_nan, void* workspace, double* out5,
+                  tfepb_stream_t stream);
+int tfepb_kl_loss_backward(int32_t dtype, const void* target_potentials, const void* log_det_J,
+                           const void* ref_potentials, const void* log_weights, int64_t n, int32_t ignore_nan,
+                           const double* stats5, const void* grad_out, void* grad_target, void* grad_log_det_J,
+                           void* grad_ref, void* grad_log_weights, tfepb_stream_t stream);
 
 /* ----------------------------------------------------------------------------------------------
  * Fused pre / post kernels of the wrapper flows (inference): the frame change, the gather of the propagated features

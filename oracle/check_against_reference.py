@@ -200,6 +200,17 @@ def check_analysis(ref, fails):
     # loss
     u, ld = cases.normal((64,), 5), cases.normal((64,), 6)
     _same(fo.kl_loss(u, ld), ref.BoltzmannKLDivLoss()(u, ld), 'kl loss', fails)
+    lw, ua = cases.normal((64,), 7), cases.normal((64,), 8)
+    un = u.clone()
+    un[[3, 17]] = float('nan')
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')          # the reference calls softmax without dim
+        for nan in (False, True):
+            L = ref.BoltzmannKLDivLoss(ignore_nan=nan)
+            _same(fo.kl_loss(un, ld, ignore_nan=nan), L(un, ld), f'kl loss nan={nan}', fails)
+            _same(fo.kl_loss(un, ld, ua, lw, ignore_nan=nan), L(un, ld, log_weights=lw, ref_potentials=ua), f'kl loss weighted nan={nan}', fails)
+            _same(fo.kl_loss(u, None, None, lw, ignore_nan=nan), L(u, log_weights=lw), f'kl loss only weights nan={nan}', fails)
 
 
 def run_all():

@@ -663,11 +663,15 @@ def sequential(flows, x, inverse=False):
     return x, total
 
 
-def kl_loss(potentials_b, log_det_J, potentials_a=None, log_weights=None):
-    """loss.py:76-140 (BoltzmannKLDivLoss.forward), without the nan-ignoring variants."""
-    r = potentials_b - log_det_J
+def kl_loss(potentials_b, log_det_J=None, potentials_a=None, log_weights=None, ignore_nan=False):
+    """loss.py:76-140 (BoltzmannKLDivLoss.forward): reduced work loss.py:125-129, weighted sum loss.py:132-136,
+    mean loss.py:138-140."""
+    r = potentials_b
+    if log_det_J is not None:
+        r = r - log_det_J
     if potentials_a is not None:
         r = r - potentials_a
     if log_weights is None:
-        return torch.mean(r)
-    return torch.sum(F.softmax(log_weights, dim=0) * r)
+        return torch.nanmean(r) if ignore_nan else torch.mean(r)
+    w = F.softmax(log_weights, dim=0)
+    return torch.nansum(w * r) if ignore_nan else torch.sum(w * r)

@@ -10,6 +10,7 @@ guarded by a checksum stored next to the outputs.
 
 import json
 import os
+import sys
 
 import numpy as np
 import torch
@@ -121,32 +122,6 @@ def golden_logger(ref):
                         **{f'{k}/{n}': v for k, r in reads.items() for n, v in r.items()})
 
 
-def golden_pca(ref, dtype, tag):
-    """PCAWhitenedFlow of the reference around a reference MAF: its buffers (the eigenvector signs are a LAPACK
-    convention, so tests load them), outputs in both directions and the x-gradient, with and without blackening."""
-    out = {}
-    case = cases.wrapper_cases(dtype)['partial']['inner']
-    _, sd = cases.build_oracle(case, dtype)
-    data = cases.normal((200, 5), 70, dtype) * torch.tensor([1.0, 2.0, 0.5, 3.0, 1.5], dtype=dtype) + 0.3
-    x = cases.normal((12, 5), 71, dtype)
-    for blacken in (True, False):
-        flow = ref.PCAWhitenedFlow(to_reference_maf(ref, case, sd), data, blacken=blacken)
-        key = 'blacken' if blacken else 'whitened'
-        for k, v in flow.state_dict().items():
-            if not k.startswith('flow.'):
-                out[f'{key}/sd/{k}'] = _np(v)
-        xg = x.clone().requires_grad_(True)
-        y, ld = flow(xg)
-        cy, cl = cases.normal(tuple(y.shape), 78, dtype), cases.normal(tuple(ld.shape), 79, dtype)
-        ((y * cy).sum() + (ld * cl).sum()).backward()
-        with torch.no_grad():
-            xi, ldi = flow.inverse(y.detach())
-        out[f'{key}/y'], out[f'{key}/ld'], out[f'{key}/gx'] = _np(y), _np(ld), _np(xg.grad)
-        out[f'{key}/xinv'], out[f'{key}/ldinv'] = _np(xi), _np(ldi)
-    out['data'], out['x'] = _np(data), _np(x)
-    np.savez_compressed(os.path.join(OUT, f'pca_{tag}.npz'), **out)
-
-
 def golden_cfg(ref):
     """Slices of the BASELINE.json configurations, fp32 reference plus fp64 reference of the same bits."""
     out = {}
@@ -213,6 +188,25 @@ def golden_analysis(ref):
     u, ld, lw = cases.normal((64,), 5), cases.normal((64,), 6), cases.normal((64,), 7)
     out['loss/mean'] = _np(ref.BoltzmannKLDivLoss()(u, ld))
     out['loss/weighted'] = _np(ref.BoltzmannKLDivLoss()(u, ld, log_weights=lw, ref_potentials=u * 0.5))
+    # every argument combination, NaN-ignoring variants and reference autograd gradients (loss.py:125-140)
+    un = u.clone()
+    un[[3, 17]] = float('nan')
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for nan in (0, 1):
+            L = ref.BoltzmannKLDivLoss(ignore_nan=bool(nan))
+            for tag, ub in (('clean', u), ('nan', un)):
+                for weighted in (0, 1):
+                    leaves = [t.clone().requires_grad_(True) for t in (ub, ld, lw, u * 0.5)]
+                    val = L(leaves[0], leaves[1], log_weights=leaves[2] if weighted else None, ref_potentials=leaves[3])
+                    key = f'loss/{tag}_w{weighted}_ignore{nan}'
+                    out[key] = _np(val)
+                    if torch.isfinite(val):
+                        val.backward()
+                        for name, t in zip(('target', 'logdet', 'logw', 'ref'), leaves):
+                            if t.grad is not None:
+                                out[f'{key}/grad_{name}'] = _np(torch.nan_to_num(t.grad))
     np.savez_compressed(os.path.join(OUT, 'analysis.npz'), **out)
 
 
@@ -256,6 +250,9 @@ def golden_degrees(ref):
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == 'analysis':      # only tests/golden/analysis.npz
+        golden_analysis(ref)
+        return
     golden_degrees(ref)
     old = torch.get_default_dtype()
     for dtype, tag in ((torch.float32, 'f32'), (torch.float64, 'f64')):
@@ -264,7 +261,6 @@ def main():
             golden_transformers(ref, dtype, tag)
             golden_mafs(ref, dtype, tag)
             golden_wrappers(ref, dtype, tag)
-            golden_pca(ref, dtype, tag)
         finally:
             torch.set_default_dtype(old)
     golden_embeddings(ref)

@@ -371,30 +371,3 @@ def test_empty_batches(prec):
                 maf.precision = 'bf16'
                 y, ld = maf(x)
                 assert y.shape == (0, n) and ld.shape == (0,), name
-
-
-def test_pca_whitened_flow(prec):
-    """PCAWhitenedFlow (reference nn/flows/pca.py:25-125) around the CUDA MAF, the two dense maps on the package's GEMM
-    kernels: with the reference's buffers loaded (eigenvector signs are a LAPACK convention) outputs, inverse and
-    x-gradient equal the reference's; built from the same data, the whitening statistics and log-det agree."""
-    from tfep_b200.nn.flows import PCAWhitenedFlow
-    g = golden(f'pca_{prec}.npz')
-    case = cases.wrapper_cases(DT[prec])['partial']['inner']
-    _, sd = cases.build_oracle(case, DT[prec])
-    data, x = torch.from_numpy(g['data']).to(DEV), torch.from_numpy(g['x']).to(DEV)
-    for key, blacken in (('blacken', True), ('whitened', False)):
-        flow = PCAWhitenedFlow(to_maf(case, sd, DEV, DT[prec]), data, blacken=blacken).to(DEV)
-        assert rel_err(flow.whitening_log_det_J, g[f'{key}/sd/whitening_log_det_J']) < 20 * TOL[prec]
-        white = flow._whiten(data)
-        assert rel_err(white.t() @ white / (len(data) - 1), torch.eye(5)) < 200 * TOL[prec]      # whitened: unit covariance
-        flow.load_state_dict({k[len(key) + 4:]: torch.from_numpy(g[k]).to(DEV) for k in g.files
-                              if k.startswith(f'{key}/sd/')}, strict=False)
-        xg = x.clone().requires_grad_(True)
-        y, ld = flow(xg)
-        assert rel_err(y, g[f'{key}/y']) < 20 * TOL[prec] and rel_err(ld, g[f'{key}/ld']) < 20 * TOL[prec], key
-        cy, cl = cases.normal(tuple(y.shape), 78, DT[prec]).to(DEV), cases.normal(tuple(ld.shape), 79, DT[prec]).to(DEV)
-        ((y * cy).sum() + (ld * cl).sum()).backward()
-        assert rel_err(xg.grad, g[f'{key}/gx']) < 100 * TOL[prec], key
-        with torch.no_grad():
-            xi, ldi = flow.inverse(torch.from_numpy(g[f'{key}/y']).to(DEV))
-        assert rel_err(xi, g[f'{key}/xinv']) < 100 * TOL[prec] and rel_err(ldi, g[f'{key}/ldinv']) < 100 * TOL[prec], key

@@ -125,3 +125,19 @@ def test_fep_estimator_known_answer():
     """Work ~ N(0, 1) => Delta f = -1/2 (reference tests/analysis/test_bootstrap.py:178-190)."""
     w = cases.normal((200000,), 17)
     assert abs(float(ao.fep_estimator(w)) + 0.5) < 0.02
+
+
+def test_kl_loss_matches_golden():
+    """oracle kl_loss (loss.py:76-140) on every argument / NaN combination the reference produced."""
+    g = golden('analysis.npz')
+    u, ld, lw = cases.normal((64,), 5), cases.normal((64,), 6), cases.normal((64,), 7)
+    un = u.clone()
+    un[[3, 17]] = float('nan')
+    assert rel_err(fo.kl_loss(u, ld), g['loss/mean']) == 0
+    assert rel_err(fo.kl_loss(u, ld, u * 0.5, lw), g['loss/weighted']) == 0
+    for nan in (0, 1):
+        for tag, ub in (('clean', u), ('nan', un)):
+            for weighted in (0, 1):
+                got = fo.kl_loss(ub, ld, u * 0.5, lw if weighted else None, ignore_nan=bool(nan))
+                want = torch.as_tensor(g[f'loss/{tag}_w{weighted}_ignore{nan}'])
+                assert torch.equal(torch.nan_to_num(got), torch.nan_to_num(want)) and bool(got.isnan() == want.isnan())

@@ -38,6 +38,12 @@ inline int check_launch(const char* what) {
 // Refuse to run anywhere but Blackwell datacenter parts: there is no fallback path.
 int require_sm100();
 int sm_count();
+// SMs the current context may use (green contexts / SM partitions give fewer than the device has)
+int sm_available();
+// min(wanted, CTAs of `kernel` that can be co-resident in the current context)
+int coresident_grid(const void* kernel, int threads, size_t smem, int wanted, int* grid);
+// cooperative launch of a kernel taking ONE by-value parameter struct: co-residency of the grid is enforced by the driver
+int launch_cooperative(const void* kernel, int grid, int threads, size_t smem, void* param, cudaStream_t stream);
 // raise the dynamic shared memory limit of `kernel` on the current device to at least `bytes` (cached)
 int ensure_dynamic_smem(const void* kernel, size_t bytes);
 

@@ -563,7 +563,8 @@ extern "C" int tfepb_maf_spline_inverse_bf16(const tfepb_fused_inv_args* a, tfep
     const bool mixed = a->mixed_splines != 0;      // some features are not circular: generic spline epilogue
     auto kernel = mixed ? finv::maf_spline_inv_kernel<true> : finv::maf_spline_inv_kernel<false>;
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), smem)) return rc;
-    const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
-    kernel<<<grid, finv::THREADS, smem, as_stream(stream)>>>(p);
+    int grid = 0;      // co-resident CTAs only (tile flags between CTAs), enforced by a cooperative launch
+    if (int rc = coresident_grid(reinterpret_cast<const void*>(kernel), finv::THREADS, smem, p.n_tiles, &grid)) return rc;
+    if (int rc = launch_cooperative(reinterpret_cast<const void*>(kernel), grid, finv::THREADS, smem, &p, as_stream(stream))) return rc;
     return check_launch("maf_spline_inv_kernel");
 }

@@ -39,6 +39,7 @@
 // log-det / publish, warps 4..19 = epilogue (four warpgroups of 128 threads: thread <-> sample row,
 // TMEM lane quadrant = warp % 4; the warpgroups split the columns of a hidden layer / the feature slots of
 // a chunk).
+#define TFEPB_INLINE_SLOW_WAIT 1
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -51,12 +52,13 @@ using namespace tc;
 
 constexpr int EPI_WGS = 4;                      // epilogue warpgroups
 constexpr int EPI_THREADS = EPI_WGS * 128;
+constexpr int EPI_WARPS = EPI_THREADS / 32;     // hand-over barriers count one arrival per epilogue WARP (lane 0, after a warp sync)
 constexpr int AUX_THREADS = 128;                // producer, MMA issuer, store warp, one idle warp
 constexpr int THREADS = AUX_THREADS + EPI_THREADS;
+constexpr int AUX_REGS = 32, EPI_REGS = 112;    // setmaxnreg budgets: the CTA starts with 96 per thread, 128 x (96 - 32) = 512 x (112 - 96)
 constexpr int STAGES = 3;
 constexpr int STAGE_BYTES = 49152;              // one weight block (<= 256 rows, bf16)
 constexpr int FEATS_PER_CHUNK = 4;
-constexpr int NPAR = 25;                        // circular spline, K = 8: 8 widths, 8 heights, 8 slopes, shift
 constexpr int PSTRIDE = 28;                     // accumulator columns per feature slot (25 used)
 constexpr int CHUNK_N = FEATS_PER_CHUNK * PSTRIDE;   // 112
 constexpr int ACC_BUFS = 3;                     // chunk accumulators in flight (3 x 112 = 336 columns)
@@ -85,16 +87,17 @@ enum : uint32_t {
     OP_HIDDEN = 128u,       // hidden-layer block: its group commits to hid_full[acc] (acc = column half) instead of acc_full[acc]
 };
 
-struct __align__(16) FeatConst {   // per sorted feature
-    int col;                // column in x / y, -1 = padding
-    float x0, L;
-    float invL, Rw, Rh, y0; // Rw = L - 8 min_bin, Rh = (yf - y0) - 8 min_bin
-    int kind;               // 0 circular (8 slopes + shift), 1 not circular (9 slopes, linear tails)
+struct __align__(16) FeatConst {   // per sorted feature, as the epilogue reads it from shared memory (built from
+                                   // tfepb_fused_feature at kernel start: the reciprocals are computed once per CTA)
+    int col_kind;           // column in x / y, -1 = padding; bit 24: not circular (9 slopes, linear tails)
+    float x0, L, invL;
+    float iRw, Rh, iRh, y0; // Rw = L - 8 min_bin, Rh = (yf - y0) - 8 min_bin; iRw = 1 / Rw, iRh = 1 / Rh
 };
+using FeatIn = tfepb_fused_feature;
 
 struct LayerP {
     const uint8_t* weights;     // packed bf16 weight blocks
-    const FeatConst* feats;     // n_chunks * FEATS_PER_CHUNK
+    const FeatIn* feats;        // n_chunks * FEATS_PER_CHUNK
     int op_base, n_ops, n_chunks;
     float min_bin, min_slope, slope_offset2;   // slope_offset2 = log2(e) * log(exp(1 - min_slope) - 1)
     const int* input_map;       // NULL, or per conditioner input column: x column | what enters << 16 (tfepb_fused_layer)
@@ -130,68 +133,91 @@ struct Smem {
     uint32_t pad[3];
 };
 
-// Spline epilogue for ONE feature of one sample.  r[0..24] = conditioner outputs of the feature (bias
-// included by the GEMM); widths r[0..7], heights r[8..15] and slopes r[16..] arrive pre-multiplied by
-// log2(e).  K = 8 bins (reference nn/transformers/spline.py:184-241, 319-417, 424-501, 546-650).
-//   circular (kind 0): 8 slopes + the shift r[24] (not pre-multiplied); after the wrap the far tails cannot be
+// Spline epilogue for ONE feature of one sample.  wh[0..7] / wh[8..15] = width / height logits, sl[0..8] = slope
+// logits and, for a circular feature, the shift in sl[8] (conditioner outputs, bias included by the GEMM; all but the
+// shift pre-multiplied by log2(e)).  K = 8 bins (reference nn/transformers/spline.py:184-241, 319-417, 424-501, 546-650).
+//   circular (kind 0): 8 slopes + the shift (not pre-multiplied); after the wrap the far tails cannot be
 //     reached, and x exactly on the first knot gives the same value through the first bin;
 //   not circular (kind 1, only in MIXED instantiations): 9 slopes; outside [x0, xf] the map is the linear
 //     continuation with the boundary slope (the reference's far-tail bins are exactly linear).
-template <bool MIXED>
-__device__ __forceinline__ float spline8(const uint32_t (&r)[32], float x, const FeatConst& fc, float min_bin,
-                                         float min_slope, float slope_offset2, float& y) {
-    float p[NPAR];
+// The walk over the knots runs in the UNNORMALISED domain of the softmax numerators: with a = sw / Rw the true knot
+// X_k = (sum_{i<k} ew_i) Rw / sw + k min_bin satisfies a X_k = cw_{k-1} + k (a min_bin), so the prefix sums that give
+// the softmax denominators also give the knots, neither the eight widths nor the eight heights are ever normalised
+// (only the selected bin is), and 1 / sw is not needed at all: 24 MUFU operations per feature (16 ex2 of the two
+// softmaxes, 2 x (ex2 + lg2) for the two softplus, rcp of the bin width, of sh and of the denominator, lg2 of dy/dx).
+// The logits enter ex2 WITHOUT subtracting their maximum (softmax is shift invariant and fp32 spans 2^+-126): a
+// feature whose sums leave [2^-100, 2^100] -- conditioner outputs beyond +-69 -- is recomputed with the maximum
+// subtracted (warp-uniform branch, never taken for sane weights).
+// Pipelining: `wh` is dead once the exponentials are taken; `handover()` (wait for the slopes, release the
+// accumulator, wait for the next one) runs there, and the next chunk's logits are requested into `wh` (next_addr)
+// after the knot walk, when the register pressure has dropped.
+template <bool MIXED, class Handover>
+__device__ __forceinline__ float spline8(uint32_t (&wh)[16], uint32_t (&sl)[9], float x, const FeatConst& fc,
+                                         float min_bin, float min_slope, float slope_offset2, float& y,
+                                         Handover&& handover, uint32_t next_addr, bool has_next) {
+    const bool circ = !MIXED || (fc.col_kind >> 24) == 0;
+    float ew[8], eh[8], cw[8], ch[8];
+    auto sums = [&](float mw, float mh) {
 #pragma unroll
-    for (int i = 0; i < NPAR; ++i) p[i] = __uint_as_float(r[i]);
-    const bool circ = !MIXED || fc.kind == 0;
+        for (int k = 0; k < 8; ++k) {
+            ew[k] = ex2(__uint_as_float(wh[k]) - mw);
+            eh[k] = ex2(__uint_as_float(wh[8 + k]) - mh);
+        }
+        cw[0] = ew[0]; ch[0] = eh[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) { cw[k] = cw[k - 1] + ew[k]; ch[k] = ch[k - 1] + eh[k]; }
+    };
+    sums(0.f, 0.f);
+    {
+        const float lo = fminf(cw[7], ch[7]), hi = fmaxf(cw[7], ch[7]);
+        if (__any_sync(0xffffffffu, !(lo > 7.9e-31f && hi < 1.3e30f))) {
+            float mw = __uint_as_float(wh[0]), mh = __uint_as_float(wh[8]);
+#pragma unroll
+            for (int k = 1; k < 8; ++k) { mw = fmaxf(mw, __uint_as_float(wh[k])); mh = fmaxf(mh, __uint_as_float(wh[8 + k])); }
+            sums(mw, mh);
+        }
+    }
+    handover();
     float t = x - fc.x0;
     if (circ) {
         // wrap: (x - x0 + shift) mod L, result in [0, L)
-        t += p[24];
+        t += __uint_as_float(sl[8]);
         t = t - fc.L * floorf(t * fc.invL);
         t = (t < 0.f) ? t + fc.L : t;
         t = (t >= fc.L) ? t - fc.L : t;
     }
-    // softmax numerators (log2 domain)
-    float mw = fmaxf(fmaxf(fmaxf(p[0], p[1]), fmaxf(p[2], p[3])), fmaxf(fmaxf(p[4], p[5]), fmaxf(p[6], p[7])));
-    float mh = fmaxf(fmaxf(fmaxf(p[8], p[9]), fmaxf(p[10], p[11])), fmaxf(fmaxf(p[12], p[13]), fmaxf(p[14], p[15])));
-    float ew[8], eh[8];
+    const float sw = cw[7], sh = ch[7];
+    const float a = sw * fc.iRw, b = sh * fc.iRh;
+    const float ts = t * a, mbs = min_bin * a, mbsh = min_bin * b;
+    // last knot below t, knots scaled by a (x side) / b (y side)
+    float Us = 0.f, Vs = 0.f, ews = ew[0], ehs = eh[0];
+    float raw0 = __uint_as_float(sl[0]), raw1 = __uint_as_float(sl[1]);
+    const float raw_last = (MIXED && !circ) ? __uint_as_float(sl[8]) : __uint_as_float(sl[0]);   // tied to knot 0 if circular
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        ew[k] = ex2(p[k] - mw);
-        eh[k] = ex2(p[8 + k] - mh);
+    for (int k = 1; k < 8; ++k) {
+        const float Uk = fmaf((float)k, mbs, cw[k - 1]);
+        const float Vk = fmaf((float)k, mbsh, ch[k - 1]);
+        const bool adv = ts > Uk;
+        Us = adv ? Uk : Us;
+        Vs = adv ? Vk : Vs;
+        ews = adv ? ew[k] : ews;
+        ehs = adv ? eh[k] : ehs;
+        raw0 = adv ? __uint_as_float(sl[k]) : raw0;
+        raw1 = adv ? (k == 7 ? raw_last : __uint_as_float(sl[k + 1])) : raw1;
     }
-    const float sw = ((ew[0] + ew[1]) + (ew[2] + ew[3])) + ((ew[4] + ew[5]) + (ew[6] + ew[7]));
-    const float sh = ((eh[0] + eh[1]) + (eh[2] + eh[3])) + ((eh[4] + eh[5]) + (eh[6] + eh[7]));
-    const float rw = fc.Rw * rcp(sw), rh = fc.Rh * rcp(sh);
-    // walk the knots (relative to x0 / y0): last bin whose left knot is below t
-    float wk = fmaf(ew[0], rw, min_bin), hk = fmaf(eh[0], rh, min_bin);
-    float left = wk, bottom = hk, w_sel = wk, h_sel = hk, xk = 0.f, yk = 0.f;
-    float raw0 = p[16], raw1 = p[17];
-    const float raw_last = (MIXED && !circ) ? p[24] : p[16];      // slope at the last knot: tied to knot 0 if circular
-#pragma unroll
-    for (int k = 0; k < 7; ++k) {
-        if (k > 0) { left += wk; bottom += hk; }
-        wk = fmaf(ew[k + 1], rw, min_bin);
-        hk = fmaf(eh[k + 1], rh, min_bin);
-        const bool adv = t > left;
-        w_sel = adv ? wk : w_sel;
-        h_sel = adv ? hk : h_sel;
-        xk = adv ? left : xk;
-        yk = adv ? bottom : yk;
-        raw0 = adv ? p[16 + k + 1] : raw0;
-        raw1 = adv ? (k == 6 ? raw_last : p[16 + k + 2]) : raw1;
-    }
+    if (has_next) tmem_ld16(next_addr, wh);      // in flight during the softplus / rational-quadratic tail
     const float dk = softplus_l2(raw0 + slope_offset2) + min_slope;
     const float dk1 = softplus_l2(raw1 + slope_offset2) + min_slope;
-    const float iw = rcp(w_sel);
-    const float e = (t - xk) * iw;
-    const float s = h_sel * iw;
+    const float iw = rcp(ews + mbs);                 // 1 / (a w)
+    const float g = fc.Rh * rcp(sh);                 // 1 / b
+    const float e = (ts - Us) * iw;
+    const float h_sel = (ehs + mbsh) * g;
+    const float s = h_sel * (iw * a);                // h / w
     const float ome = 1.f - e, u = e * ome, e2 = e * e;
     const float q = dk1 + dk - 2.f * s;
     const float den = fmaf(q, u, s);
     const float iden = rcp(den);
-    y = fc.y0 + yk + h_sel * fmaf(s, e2, dk * u) * iden;
+    y = fmaf(Vs, g, fc.y0) + h_sel * fmaf(s, e2, dk * u) * iden;
     const float nn = fmaf(dk1, e2, fmaf(2.f * s, u, dk * ome * ome));
     const float rr = s * iden;
     float ld = LN2 * lg2(nn * rr * rr);
@@ -240,15 +266,22 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
     // ---- one-time setup ----
     for (int l = 0; l < p.n_layers; ++l) {
         const int nf = p.layers[l].n_chunks * FEATS_PER_CHUNK;
-        for (int i = tid; i < nf; i += THREADS) sFeat[l * p.feat_stride + i] = p.layers[l].feats[i];
+        for (int i = tid; i < nf; i += THREADS) {
+            const FeatIn f = p.layers[l].feats[i];
+            FeatConst c;
+            c.col_kind = f.col < 0 ? -1 : (f.col | (f.kind << 24));
+            c.x0 = f.x0; c.L = f.period; c.invL = f.inv_period;
+            c.iRw = 1.f / f.rescaled_width; c.Rh = f.rescaled_height; c.iRh = 1.f / f.rescaled_height; c.y0 = f.y0;
+            sFeat[l * p.feat_stride + i] = c;
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&sm->w_full[s], 1); mbar_init(&sm->w_empty[s], 1); }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&sm->x_full[b], 1); mbar_init(&sm->x_empty[b], 1); mbar_init(&sm->y_ready[b], EPI_THREADS);
+            mbar_init(&sm->x_full[b], 1); mbar_init(&sm->x_empty[b], 1); mbar_init(&sm->y_ready[b], EPI_WARPS);
         }
-        mbar_init(&sm->a_ready, EPI_THREADS);
-        for (int b = 0; b < ACC_BUFS; ++b) { mbar_init(&sm->acc_full[b], 1); mbar_init(&sm->acc_empty[b], EPI_THREADS); }
+        mbar_init(&sm->a_ready, EPI_WARPS);
+        for (int b = 0; b < ACC_BUFS; ++b) { mbar_init(&sm->acc_full[b], 1); mbar_init(&sm->acc_empty[b], EPI_WARPS); }
         mbar_init(&sm->hid_full[0], 1); mbar_init(&sm->hid_full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -258,6 +291,11 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
     tc_fence_after();
     const uint32_t tmem = sm->tmem_base;
 
+    // Register budget per role (setmaxnreg moves registers between warpgroups): the four auxiliary warps need few,
+    // the epilogue warpgroups take what they give up (the CTA starts with 640 x 96; 128 x 32 + 512 x 112 is the same total).
+    // (One instruction per warpgroup, dominating the code it governs, so that the register allocator sees the budget.)
+    if (warp < AUX_THREADS / 32) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AUX_REGS));
     if (warp == 0) {
         // =========================== producer: x tiles + weight blocks ===========================
         // The whole warp walks the schedule (warp-uniform control flow); one elected lane issues the copies.
@@ -449,7 +487,9 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
             }
             trace<DEBUG>(p, 3, ts, 4001);
         }
-    } else if (warp >= AUX_THREADS / 32) {
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
         // =========================== epilogue warps ===========================
         const int et = tid - AUX_THREADS;         // 0..511
         const int wg = et >> 7;                   // warpgroup 0..3
@@ -503,7 +543,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
             }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&sm->a_ready);
+            if (lane == 0) mbar_arrive(&sm->a_ready);
             trace<DEBUG>(p, 2, ts, 3002);
             // ---- two hidden layers: ELU, bf16 -> A operand of the next GEMM (tensor memory) ----
             // Each layer is handed over in two column halves: GEMM2 of the first half (its rows only see the
@@ -538,7 +578,8 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
                         uint32_t q[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            q[i] = pack_bf16(elu_l2(__uint_as_float(r[2 * i]), l2e), elu_l2(__uint_as_float(r[2 * i + 1]), l2e));
+                            q[i] = (DEBUG && (dmode & 4)) ? pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]))
+                                                          : pack_bf16(elu_l2(__uint_as_float(r[2 * i]), l2e), elu_l2(__uint_as_float(r[2 * i + 1]), l2e));
                         tmem_st8(lane_addr + A_COL + c0 / 2, q);
                     };
                     int c0 = cbeg + wg * 16;
@@ -558,61 +599,94 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
                     }
                     tmem_st_wait();
                     tc_fence_before();
-                    mbar_arrive(&sm->a_ready);
+                    if (lane == 0) mbar_arrive(&sm->a_ready);
                     trace<DEBUG>(p, 2, ts, 3020 + 2 * hl + half);
                 }
             }
             // ---- output layer chunks: spline transformer straight out of TMEM ----
+            // Software pipeline over the chunks: the width / height logits of chunk c + 1 are requested from tensor
+            // memory as soon as those of chunk c have gone through ex2 (they are dead then), so their latency hides
+            // behind the knot walk of chunk c; the slopes of chunk c are requested right before its exponentials.
             float ld = 0.f;
-            const FeatConst* feat = sFeat + layer * p.feat_stride + wg;    // one feature slot per warpgroup
             const float min_bin = L.min_bin, min_slope = L.min_slope, slope_offset2 = L.slope_offset2;
             const int n_chunks = L.n_chunks;
+            // addresses of the loop, pinned in registers (the compiler would otherwise re-derive them from threadIdx and
+            // the kernel parameters in every iteration): this thread's TMEM lane + feature slot, its row of the x / y tile,
+            // the feature records of its slot, the accumulator barriers
+            const uint32_t t_slot = pinned(lane_addr + wg * PSTRIDE);
+            const uint32_t s_xrow = pinned(smem_u32(xrow));
+            uint32_t s_feat = pinned(smem_u32(sFeat + layer * p.feat_stride + wg));     // one feature slot per warpgroup
+            const uint32_t s_full = pinned(smem_u32(&sm->acc_full[0])), s_empty = pinned(smem_u32(&sm->acc_empty[0]));
+            const uint32_t is_lane0 = pinned(lane == 0 ? 1u : 0u);
             uint32_t b = 0;
-            for (int c = 0; c < n_chunks; ++c) {
-                mbar_wait(&sm->acc_full[b], (full_bits >> b) & 1u, p.error, 8);
-                full_bits ^= 1u << b;
-                tc_fence_after();
+            uint32_t wh[16], sl[9];
+            mbar_wait_s(s_full, full_bits & 1u, p.error, 8);
+            full_bits ^= 1u;
+            tc_fence_after();
+            tmem_ld16(t_slot, wh);
+#pragma unroll 1
+            for (int c = 0; c < n_chunks; ++c, s_feat += FEATS_PER_CHUNK * (uint32_t)sizeof(FeatConst)) {
                 trace<DEBUG>(p, 2, ts, 3100 + c);
+                const uint32_t a0 = t_slot + b * CHUNK_N;
+                tmem_wait8(wh); tmem_wait8(wh + 8);
+                tmem_ld8(a0 + 16, sl);
+                tmem_ld1(a0 + 24, sl + 8);
+                FeatConst fc;
                 {
-                    uint32_t r[32];
-                    if (dmode & 4) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) r[i] = 0x3c000000u + i * 1234567u + row;
-                    } else {
-                        const uint32_t a0 = lane_addr + b * CHUNK_N + wg * PSTRIDE;
-                        tmem_ld16(a0, r);                  // 25 parameters: 16 + 8 + 1 columns
-                        tmem_ld8(a0 + 16, r + 16);
-                        tmem_ld1(a0 + 24, r + 24);
-                        tmem_wait8(r); tmem_wait8(r + 8); tmem_wait8(r + 16); tmem_wait1(r + 24);
-                    }
-                    // the parameters are in registers: the accumulator can be refilled while the spline is evaluated
+                    uint32_t f0[4], f1[4];
+                    lds_v4(s_feat, f0);
+                    lds_v4(s_feat + 16, f1);
+                    fc.col_kind = (int)f0[0]; fc.x0 = __uint_as_float(f0[1]); fc.L = __uint_as_float(f0[2]); fc.invL = __uint_as_float(f0[3]);
+                    fc.iRw = __uint_as_float(f1[0]); fc.Rh = __uint_as_float(f1[1]); fc.iRh = __uint_as_float(f1[2]); fc.y0 = __uint_as_float(f1[3]);
+                }
+                const int col = fc.col_kind < 0 ? -1 : (fc.col_kind & 0xffffff);
+                const uint32_t bn = (b == ACC_BUFS - 1) ? 0u : b + 1u;
+                const bool has_next = c + 1 < n_chunks;
+                // hand the accumulator back once the slopes are in registers (TMEM loads are warp-collective: when
+                // lane 0 has its values, so has the warp), then wait for the next chunk's accumulator
+                auto handover = [&]() {
+                    tmem_wait8(sl); tmem_wait1(sl + 8);
                     tc_fence_before();
-                    mbar_arrive(&sm->acc_empty[b]);
-                    const FeatConst fc = feat[c * FEATS_PER_CHUNK];
-                    if (dmode & 2) {
-                        float acc = 0.f;
-#pragma unroll
-                        for (int i = 0; i < NPAR; ++i) acc += __uint_as_float(r[i]);
-                        ld += acc;
-                    } else if (fc.col >= 0) {
-                        if (DEBUG && p.debug_params != nullptr && !(dmode & 16) && row < rows && layer == 0) {
-                            float* dbg = p.debug_params + ((size_t)tile * TILE_M + row) * n_chunks * CHUNK_N + c * CHUNK_N +
-                                         wg * PSTRIDE;
-#pragma unroll
-                            for (int i = 0; i < NPAR; ++i) dbg[i] = __uint_as_float(r[i]);
-                        }
-                        float yv;
-                        ld += spline8<MIXED>(r, xrow[fc.col], fc, min_bin, min_slope, slope_offset2, yv);
-                        xrow[fc.col] = yv;
+                    if (is_lane0) mbar_arrive_s(s_empty + b * 8u);
+                    if (has_next) {
+                        mbar_wait_s(s_full + bn * 8u, (full_bits >> bn) & 1u, p.error, 8);
+                        full_bits ^= 1u << bn;
+                        tc_fence_after();
                     }
+                };
+                if (DEBUG && p.debug_params != nullptr && !(dmode & 16) && row < rows && layer == 0 && col >= 0) {
+                    float* dbg = p.debug_params + ((size_t)tile * TILE_M + row) * n_chunks * CHUNK_N + c * CHUNK_N + wg * PSTRIDE;
+                    tmem_wait8(sl); tmem_wait1(sl + 8);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) dbg[i] = __uint_as_float(wh[i]);
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) dbg[16 + i] = __uint_as_float(sl[i]);
+                }
+                if (DEBUG && (dmode & 2)) {                 // timing experiment: hand-over skeleton without the spline math
+                    handover();
+                    float acc = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) acc += __uint_as_float(sl[i]);
+                    ld += acc;
+                    if (has_next) tmem_ld16(t_slot + bn * CHUNK_N, wh);
+                } else if (col >= 0) {
+                    float yv;
+                    const uint32_t s_x = s_xrow + (uint32_t)col * 4u;
+                    ld += spline8<MIXED>(wh, sl, lds_f32(s_x), fc, min_bin, min_slope, slope_offset2, yv, handover,
+                                         t_slot + bn * CHUNK_N, has_next);
+                    sts_f32(s_x, yv);
+                } else {
+                    handover();
+                    if (has_next) tmem_ld16(t_slot + bn * CHUNK_N, wh);
                 }
                 trace<DEBUG>(p, 2, ts, 3200 + c);
-                b = (b == ACC_BUFS - 1) ? 0u : b + 1u;
+                b = bn;
             }
             // ---- hand the y tile and the log-det partials to the store warp ----
             sLd[xb * (EPI_WGS * TILE_M) + wg * TILE_M + row] = ld;
             fence_async_smem();                      // y tile writes -> visible to the bulk-copy engine
-            mbar_arrive(&sm->y_ready[xb]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm->y_ready[xb]);
             trace<DEBUG>(p, 2, ts, 3300);
         }
     }
@@ -637,7 +711,7 @@ size_t smem_bytes(const Params& p) {
 using namespace tfepb;
 
 static_assert(sizeof(fused::Op) == sizeof(tfepb_fused_op), "schedule entry layout mismatch");
-static_assert(sizeof(fused::FeatConst) == sizeof(tfepb_fused_feature), "feature table layout mismatch");
+static_assert(sizeof(fused::FeatConst) == 32 && sizeof(tfepb_fused_feature) == 32, "feature table layout");
 static_assert(sizeof(fused::Params) < 32000, "kernel parameter space");
 
 extern "C" int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_stream_t stream) {
@@ -671,7 +745,7 @@ extern "C" int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_st
         TFEPB_CHECK_ARG((uintptr_t)s.weights % 16 == 0, "layer %d: packed weights must be 16-byte aligned", l);
         fused::LayerP& d = p.layers[l];
         d.weights = (const uint8_t*)s.weights;
-        d.feats = (const fused::FeatConst*)s.feats;
+        d.feats = s.feats;
         d.op_base = op_base; d.n_ops = s.n_ops; d.n_chunks = s.n_chunks;
         d.min_bin = s.min_bin_size; d.min_slope = s.min_slope; d.slope_offset2 = s.slope_offset * fused::LOG2E;
         TFEPB_CHECK_ARG(s.input_map != nullptr || n_inputs == a->n_features, "layer %d: n_inputs > n_features needs an input_map", l);
@@ -700,8 +774,10 @@ extern "C" int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_st
     auto kernel = debug ? (mixed ? fused::maf_spline_fwd_kernel<true, true> : fused::maf_spline_fwd_kernel<true, false>)
                         : (mixed ? fused::maf_spline_fwd_kernel<false, true> : fused::maf_spline_fwd_kernel<false, false>);
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), smem)) return rc;
-    // one CTA per SM; never more CTAs than tiles, so that the items a CTA waits for belong to CTAs that run
-    const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
-    kernel<<<grid, fused::THREADS, smem, as_stream(stream)>>>(p);
+    // One CTA per SM, never more CTAs than tiles and never more than can be co-resident: the items a CTA waits for
+    // belong to CTAs that run (cooperative launch: the driver enforces it instead of a spin that ends in a trap).
+    int grid = 0;
+    if (int rc = coresident_grid(reinterpret_cast<const void*>(kernel), fused::THREADS, smem, p.n_tiles, &grid)) return rc;
+    if (int rc = launch_cooperative(reinterpret_cast<const void*>(kernel), grid, fused::THREADS, smem, &p, as_stream(stream))) return rc;
     return check_launch("maf_spline_fwd_kernel");
 }

@@ -35,6 +35,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug must end in a trap (error return), never in a hung GPU.
+// (Kernels that re-balance registers between warpgroups with setmaxnreg define TFEPB_INLINE_SLOW_WAIT: ptxas
+// cannot allocate registers across an ABI call inside a setmaxnreg region.)
+#ifdef TFEPB_INLINE_SLOW_WAIT
+static __device__ __forceinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int* error, int tag) {
+    uint32_t polls = 0;
+    long long t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++polls & 0xfffu) != 0) continue;
+        if (t0 == 0) t0 = clock64();
+        if ((uint64_t)(clock64() - t0) > WATCHDOG_CYCLES) {
+            if (error) atomicExch(error, tag);
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+#else
 static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int* error, int tag) {
     uint32_t polls = 0;
     long long t0 = 0;
@@ -48,9 +65,51 @@ static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parit
         }
     }
 }
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* error, int tag) {
     if (mbar_try_wait(bar, parity)) return;
     mbar_wait_slow(bar, parity, error, tag);
+}
+// Variants on a 32-bit shared-memory address held in a register (hot loops: no generic -> shared conversion per use).
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity, int* error, int tag) {
+    if (mbar_try_wait_s(bar, parity)) return;
+    uint32_t polls = 0;
+    long long t0 = 0;
+    while (!mbar_try_wait_s(bar, parity)) {
+        if ((++polls & 0xfffu) != 0) continue;
+        if (t0 == 0) t0 = clock64();
+        if ((uint64_t)(clock64() - t0) > WATCHDOG_CYCLES) {
+            if (error) atomicExch(error, tag);
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+// A value the compiler must keep in a register instead of re-deriving it from threadIdx / kernel parameters.
+__device__ __forceinline__ uint32_t pinned(uint32_t v) {
+    asm volatile("mov.u32 %0, %0;" : "+r"(v));
+    return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void lds_v4(uint32_t addr, uint32_t (&v)[4]) {
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -5,5 +5,4 @@ from .centroid import CenteredCentroidFlow
 from .maf import MAF
 from .oriented import OrientedFlow
 from .partial import PartialFlow
-from .pca import PCAWhitenedFlow
 from .sequential import SequentialFlow
