@@ -194,6 +194,11 @@ int64_t tfepb_tc_image_bytes(int64_t rows, int64_t k, int32_t block_rows);
 /* src fp32: element (row, k) at src[row * ld + k], or src[k * ld + row] if transpose */
 int tfepb_tc_pack(const float* src, int64_t ld, int32_t rows, int32_t k, int32_t block_rows, int32_t transpose,
                   void* image, tfepb_stream_t stream);
+/* Split-precision images: n_split (1, 2 or 3) consecutive images of tfepb_tc_image_bytes() bytes each, term t holding
+ * bf16(src - sum of the terms before it), i.e. 8 / 16 / 24 significant bits of every element (nn/masked.py:266-277 at
+ * fp32-class accuracy on bf16 tensor cores; see n_split of tfepb_tc_gemm_args). */
+int tfepb_tc_pack_split(const float* src, int64_t ld, int32_t rows, int32_t k, int32_t block_rows, int32_t transpose,
+                        int32_t n_split, void* image, tfepb_stream_t stream);
 /* One pass over src (rows x cols fp32): its image with 128-row blocks (or NULL), the image of its transpose with
  * t_block_rows = 128 / 256 (or NULL) and, if column_sums != NULL (zero-filled by the caller), += the sums over the rows. */
 int tfepb_tc_pack_dual(const float* src, int64_t ld, int32_t rows, int32_t cols, void* image, void* image_t,
@@ -219,6 +224,11 @@ typedef struct {
                                             needs, written by the epilogue instead of a separate pack launch */
     float* column_sums;                  /* NULL, or fp32 (n,), zero-filled by the caller: += sum over the m rows of the
                                             result (the bias gradient of nn/masked.py:298-300 when the result is grad_y) */
+    int32_t n_split;                     /* 0 / 1: plain bf16 operands.  2 / 3: a_image, b_image (and out_image) are
+                                            split-precision images (tfepb_tc_pack_split); every k-step accumulates the
+                                            3 / 6 products A_i B_j with i + j < n_split in fp32 -- operands carried to
+                                            16 / 24 significant bits (forward products only) */
+    int32_t reserved;
 } tfepb_tc_gemm_args;
 int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream);
 

@@ -222,3 +222,44 @@ def test_generic_statistic_against_scipy(method, batch):
     assert abs(float(ours['confidence_interval']['low']) - ref.confidence_interval.low) < 1e-1
     assert abs(float(ours['confidence_interval']['high']) - ref.confidence_interval.high) < 1e-1
     assert abs(float(ours['standard_deviation']) - ref.standard_error) < 1e-2
+
+
+@pytest.mark.parametrize('rng', ['mt19937', 'philox'])
+def test_bootstrap_wide_dynamic_range(rng):
+    """Work values spanning hundreds of kT (progressively trained maps, heavy tails): the reference takes a per-row
+    logsumexp (bootstrap.py:227-231) and stays finite; the fused table path must too -- with take_first_only the table
+    maximum must come from the first samples only, and a resample that misses the dominant samples is recomputed
+    against a lower reference (tfep_b200.analysis.bootstrap.repair_underflow)."""
+    from tfep_b200.analysis import bootstrap, fep_estimator
+    # 1. the early samples lie 1000 kT above the later ones; resamples only see the first 100
+    w = torch.cat([torch.full((100,), 1000.0), torch.full((900,), 5.0)]) + cases.normal((1000,), 3) * 0.1
+    kw = dict(n_resamples=50, bootstrap_sample_size=[100], take_first_only=True)
+    a = bootstrap(w.to(DEV), fep_estimator, generator=torch.Generator().manual_seed(1), rng=rng, **kw)
+    b = ao.bootstrap(w, ao.fep_estimator, generator=torch.Generator().manual_seed(1), **kw)
+    assert bool(torch.isfinite(a['mean'])) and abs(float(a['mean']) - 1000.0) < 1.0
+    if rng == 'mt19937':                  # same index stream: same statistics
+        assert rel_err(a['mean'], b['mean']) < 2e-6 and rel_err(a['confidence_interval']['low'], b['confidence_interval']['low']) < 2e-6
+    # 2. one dominant outlier 300 kT below everything else: ~37 % of the resamples miss it
+    w = cases.normal((2000,), 4) * 0.5
+    w[17] = -300.0
+    a = bootstrap(w.to(DEV), fep_estimator, n_resamples=200, batch=64, generator=torch.Generator().manual_seed(2), rng=rng)
+    b = ao.bootstrap(w, ao.fep_estimator, n_resamples=200, batch=64, generator=torch.Generator().manual_seed(2))
+    for k in ('mean', 'median', 'standard_deviation'):
+        assert bool(torch.isfinite(a[k])), k
+    if rng == 'mt19937':
+        assert rel_err(a['mean'], b['mean']) < 5e-6 and rel_err(a['median'], b['median']) < 5e-6
+        assert rel_err(a['standard_deviation'], b['standard_deviation']) < 1e-4
+    else:                                 # statistical parity: the missing fraction is binomial(200, 0.368)
+        from tfep_b200.analysis.bootstrap import _bootstrap_statistics
+        st = _bootstrap_statistics(w.to(DEV), fep_estimator, 400, 2000, False, 400, torch.Generator().manual_seed(5), 'philox')
+        miss = float((st > -100).float().mean())
+        assert 0.28 < miss < 0.46, miss
+        assert float(st[st > -100].max()) < 1.0 and float(st[st <= -100].min()) > -300.0 - 1.0
+
+
+def test_more_than_65535_resamples_per_call():
+    """n_resamples beyond the grid.y limit of one launch with the default batch (reference bootstrap.py:126-182)."""
+    from tfep_b200.analysis import bootstrap, fep_estimator
+    w = cases.normal((50,), 8).to(DEV)
+    r = bootstrap(w, fep_estimator, n_resamples=70000, generator=torch.Generator().manual_seed(1))
+    assert bool(torch.isfinite(r['mean'])) and float(r['standard_deviation']) > 0

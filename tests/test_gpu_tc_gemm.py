@@ -91,3 +91,35 @@ def test_dual_pack_equals_the_separate_packs(rows, cols, t_rows):
     i3, t3, _ = _ops.tc_pack_dual(wide[:, :cols], t_rows)
     assert torch.equal(i3, _ops.tc_pack(wide[:, :cols].contiguous(), 128))
     assert torch.equal(t3, _ops.tc_pack(wide[:, :cols].contiguous(), t_rows, transpose=True))
+
+
+@pytest.mark.parametrize('n_split,tol', [(2, 4e-5), (3, 2e-6)])
+@pytest.mark.parametrize('m,n,k', [(128, 256, 64), (1000, 670, 300), (257, 1650, 330), (5, 7, 9), (300, 512, 96)])
+def test_split_precision_products(m, n, k, n_split, tol):
+    """x = x_0 + x_1 (+ x_2) in bf16 terms, products A_i B_j with i + j < n_split (3 or 6 MMAs per k-step): against the
+    double-precision product of the UNROUNDED fp32 operands; the image of the result (split the same way by the
+    epilogue) chains into a second product; staircase k-ranges apply per 64-wide block as in the plain mode."""
+    x, w, b = _rand((m, k), 41), _rand((n, k), 42) / k ** 0.5, _rand((n,), 43)
+    ai, bi = _ops.tc_pack(x, 128, n_split=n_split), _ops.tc_pack(w, 256, n_split=n_split)
+    c, img = _ops.tc_gemm(ai, bi, m, n, k, c=True, bias=b, activation=_ops.ACT_ELU, out_image=True, n_split=n_split)
+    ref = torch.nn.functional.elu(x.double() @ w.double().T + b.double())
+    scale = 1 + float(ref.abs().max())
+    assert float((c.double() - ref).abs().max()) < tol * scale
+    n2 = 130
+    w2 = _rand((n2, n), 44) / n ** 0.5
+    c2, _ = _ops.tc_gemm(img, _ops.tc_pack(w2, 256, n_split=n_split), m, n2, n, c=True, n_split=n_split)
+    ref2 = c.double() @ w2.double().T
+    assert float((c2.double() - ref2).abs().max()) < tol * (1 + float(ref2.abs().max()))
+    # the first term of a split image IS the plain bf16 image
+    nbytes = _ops._lib.load().tfepb_tc_image_bytes(m, k, 128)
+    assert torch.equal(ai[:nbytes], _ops.tc_pack(x, 128))
+    if n >= 512 and k >= 96:
+        tiles = (n + 255) // 256                        # tile 0 sees k-block 0 only, the others k-block 1 only
+        ranges = torch.tensor([[0, 1]] + [[1, 2]] * (tiles - 1), dtype=torch.int32, device=DEV)
+        cr, _ = _ops.tc_gemm(ai, bi, m, n, k, c=True, k_block_ranges=ranges, n_split=n_split)
+        wm = w.clone()
+        wm[:256, 64:] = 0
+        wm[256:, :64] = 0
+        wm[256:, 128:] = 0
+        refr = x.double() @ wm.double().T
+        assert float((cr.double() - refr).abs().max()) < tol * (1 + float(refr.abs().max()))

@@ -291,6 +291,10 @@ def exp_table(w, scale, max_dev):
     return e
 
 
+#: resamples one tfepb_bootstrap_sums launch takes (they map to grid.y)
+MAX_RESAMPLES_PER_CALL = 65535
+
+
 def bootstrap_sums(e, max_idx, n_resamples, sample_size, idx=None, philox_seed=0, philox_offset=0, shard_lo=0,
                    sample_sizes=None):
     """Per-resample sums of the exp table ``e`` (the shard starting at global index ``shard_lo``).  ``sample_sizes``:
@@ -337,19 +341,24 @@ def mt19937_indices(state_dev, count, max_idx, out=None):
 # tensor-core GEMM (bf16 operand images, fp32 accumulation)
 # ---------------------------------------------------------------------------------------------
 
-def tc_pack(src, block_rows, transpose=False, out=None):
-    """bf16 operand image of a 2-D fp32 CUDA tensor (rows x k, or its transpose if ``transpose``); see tfepb_tc_pack."""
+def tc_pack(src, block_rows, transpose=False, out=None, n_split=1):
+    """bf16 operand image of a 2-D fp32 CUDA tensor (rows x k, or its transpose if ``transpose``); see tfepb_tc_pack.
+    ``n_split`` = 2 / 3: the consecutive images of the split-precision terms (tfepb_tc_pack_split)."""
     require_cuda(src)
     if src.dtype != torch.float32:
         raise _lib.TfepB200Error('tc_pack takes float32 tensors')
     src = _rows(src)
     rows, k = (src.shape[1], src.shape[0]) if transpose else (src.shape[0], src.shape[1])
     lib = _lib.load()
-    nbytes = lib.tfepb_tc_image_bytes(rows, k, block_rows)
+    nbytes = lib.tfepb_tc_image_bytes(rows, k, block_rows) * n_split
     img = out if out is not None else torch.empty(nbytes, dtype=torch.uint8, device=src.device)
     assert img.numel() >= nbytes
     with torch.cuda.device(src.device):
-        check(lib.tfepb_tc_pack(ptr(src), _ld(src), rows, k, block_rows, int(transpose), ptr(img), stream_ptr(src)))
+        if n_split == 1:
+            check(lib.tfepb_tc_pack(ptr(src), _ld(src), rows, k, block_rows, int(transpose), ptr(img), stream_ptr(src)))
+        else:
+            check(lib.tfepb_tc_pack_split(ptr(src), _ld(src), rows, k, block_rows, int(transpose), int(n_split), ptr(img),
+                                          stream_ptr(src)))
     return img
 
 
@@ -374,7 +383,7 @@ def tc_pack_dual(src, t_block_rows=None, column_sums=False, image=True):
 
 
 def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, aux=None, out_image=False,
-            k_block_ranges=None, row_ranges=None, split_k=1, error_flag=None, out_image_t=None, column_sums=False):
+            k_block_ranges=None, row_ranges=None, split_k=1, error_flag=None, out_image_t=None, column_sums=False, n_split=1):
     """C = act(A B^T + bias) [* ELU'(aux)] from operand images; returns (c, out_img).  ``c``: True to allocate, a
     tensor to write into (zero-filled by the caller when split_k > 1), None for no fp32 output.
     ``out_image_t`` = 128 / 256: also the image of the transposed result with that block_rows; ``column_sums``: also
@@ -386,7 +395,7 @@ def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, au
         c = (torch.zeros if split_k > 1 else torch.empty)((m, pad4), dtype=torch.float32, device=dev)[:, :n]
     img = None
     if out_image:
-        img = torch.empty(lib.tfepb_tc_image_bytes(m, n, 128), dtype=torch.uint8, device=dev)
+        img = torch.empty(lib.tfepb_tc_image_bytes(m, n, 128) * n_split, dtype=torch.uint8, device=dev)
     img_t = None
     if out_image_t:
         img_t = torch.empty(lib.tfepb_tc_image_bytes(n, m, int(out_image_t)), dtype=torch.uint8, device=dev)
@@ -401,7 +410,7 @@ def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, au
                         error_flag=None if error_flag is None else error_flag.data_ptr(),
                         row_ranges=None if row_ranges is None else row_ranges.data_ptr(),
                         out_image_t=None if img_t is None else img_t.data_ptr(),
-                        column_sums=None if sums is None else sums.data_ptr())
+                        column_sums=None if sums is None else sums.data_ptr(), n_split=int(n_split), reserved=0)
     with torch.cuda.device(dev):
         check(lib.tfepb_tc_gemm(ctypes.byref(a), stream_ptr(a_img)))
     if out_image_t or column_sums:
@@ -492,7 +501,24 @@ class MadeFunctionTC(torch.autograd.Function):
         return (gx, None, None, None, None, *gws, *gbs)
 
 
-def made_forward_tc(x, weights, biases, kb_fwd=None, kb_bwd=None, rr_w=None):
+def made_forward_tc(x, weights, biases, kb_fwd=None, kb_bwd=None, rr_w=None, n_split=1, weight_images=None):
+    """All layers of a MADE on the tensor cores.  ``n_split`` = 2 / 3: split-precision operands (3 / 6 bf16 products per
+    reduction step, fp32-class accuracy); an inference path -- under autograd use n_split = 1 or the exact kernels.
+    ``weight_images``: optional cached ``tc_pack(w, 256, n_split=n_split)`` of every layer."""
     if x.shape[0] == 0:                       # nothing to launch; zero-sized result tied to the inputs for autograd
         return x.new_zeros((0, weights[-1].shape[0])) + 0.0 * sum(w.sum() + b.sum() for w, b in zip(weights, biases))
-    return MadeFunctionTC.apply(x, len(weights), kb_fwd, kb_bwd, rr_w, *weights, *biases)
+    if n_split == 1:
+        return MadeFunctionTC.apply(x, len(weights), kb_fwd, kb_bwd, rr_w, *weights, *biases)
+    if torch.is_grad_enabled() and (x.requires_grad or any(t.requires_grad for t in (*weights, *biases))):
+        raise NotImplementedError("tfep_b200: the split-precision tensor-core conditioner (precision='bf16x3' / 'bf16x6') "
+                                  "is an inference path; use torch.no_grad(), or precision='fp32' / 'bf16' for training")
+    B = x.shape[0]
+    img = tc_pack(x.contiguous(), 128, n_split=n_split)
+    h = None
+    for l, (w, b) in enumerate(zip(weights, biases)):
+        last = l == len(weights) - 1
+        N, K = w.shape
+        wimg = weight_images[l] if weight_images is not None else tc_pack(w, 256, n_split=n_split)
+        h, img = tc_gemm(img, wimg, B, N, K, c=True if last else None, bias=b, activation=ACT_NONE if last else ACT_ELU,
+                         out_image=not last, k_block_ranges=None if kb_fwd is None else kb_fwd[l], n_split=n_split)
+    return h

@@ -141,20 +141,34 @@ def stratified_counts(n_resamples, sample_size, cells, total, seed):
     return rng.multinomial(int(sample_size), p / p.sum(), size=int(n_resamples)).astype(np.int64)
 
 
-def philox_cell_sums(e, e_lo, cells, mine, counts, seed, n_resamples=None, sample_size=None):
+def philox_cell_sums(e, e_lo, cells, mine, counts, seed, n_resamples=None, sample_size=None, rows=None):
     """Per-resample sums over the cells ``mine`` (indices into ``cells``) of the exp table ``e``, which holds the
-    entries [e_lo, e_lo + len(e)) of the global table.  Returns (n_resamples,) float64."""
+    entries [e_lo, e_lo + len(e)) of the global table.  Returns (n_resamples,) float64, or, with ``rows`` (a list of
+    resample numbers), the sums of those resamples only -- the same Philox counters, so the same draws."""
     if counts is None:                                   # a single cell: plain uniform draws over it
         (a, b), = cells
+        stride = (sample_size + 3) // 4
+        if rows is not None:
+            return torch.cat([_ops.bootstrap_sums(e[a - e_lo:b - e_lo], b - a, 1, sample_size, None, seed, r * stride)
+                              for r in rows]) if len(rows) else torch.empty(0, dtype=torch.float64, device=e.device)
         sums = torch.empty(n_resamples, dtype=torch.float64, device=e.device)
         for k in range(0, n_resamples, 65535):
             nb = min(65535, n_resamples - k)
-            sums[k:k + nb] = _ops.bootstrap_sums(e[a - e_lo:b - e_lo], b - a, nb, sample_size, None, seed,
-                                                 k * ((sample_size + 3) // 4))
+            sums[k:k + nb] = _ops.bootstrap_sums(e[a - e_lo:b - e_lo], b - a, nb, sample_size, None, seed, k * stride)
         return sums
     n_resamples = counts.shape[0]
     strides = (counts.max(axis=0) + 3) // 4               # Philox counters: a disjoint range per (cell, resample)
     offsets = np.concatenate([[0], np.cumsum(strides * n_resamples)])
+    if rows is not None:
+        out = torch.zeros(len(rows), dtype=torch.float64, device=e.device)
+        for c in mine:
+            a, b = cells[c]
+            for i, r in enumerate(rows):
+                if counts[r, c] > 0:
+                    size = torch.tensor([int(counts[r, c])], dtype=torch.int64, device=e.device)
+                    out[i:i + 1] += _ops.bootstrap_sums(e[a - e_lo:b - e_lo], b - a, 1, int(counts[:, c].max()), None, seed,
+                                                        int(offsets[c]) + r * int(strides[c]), sample_sizes=size)
+        return out
     sums = torch.zeros(n_resamples, dtype=torch.float64, device=e.device)
     for c in mine:
         a, b = cells[c]
@@ -166,34 +180,77 @@ def philox_cell_sums(e, e_lo, cells, mine, counts, seed, n_resamples=None, sampl
     return sums
 
 
+#: A resample whose sum of exp(v - reference) falls below this is recomputed against a lower reference (see
+#: repair_underflow): its draws all lie more than 69 below the reference, where the fp32 table runs out of range.
+UNDERFLOW = 1e-30
+LEVEL_STEP = 60.0       # < -log(UNDERFLOW): the entries such a resample drew stay below exp(-9) at the next level
+
+
+def repair_underflow(sums, ref0, values, scale, rerun):
+    """Make the fused path exact for data of ANY dynamic range.  ``sums[r] = sum_j exp(v[idx_rj] - ref0)`` comes from an
+    fp32 table that underflows for entries more than ~87 below the reference; the reference's per-row logsumexp
+    (bootstrap.py:227-231 with estimator.py:84-86) does not.  A resample that missed every dominant sample -- e.g. all
+    of them with ``take_first_only`` on progressively trained work values, or a resample of a heavy-tailed data set
+    that skips the outlier -- ends up with a sum of (almost) zero: those rows are recomputed with the same draws
+    against tables at references lowered in steps of 60 until they register (entries above a lowered reference
+    overflow to inf, but a row that needs the level drew none of them).  ``rerun(rows, table)`` returns the sums of
+    the resamples ``rows`` over ``table``.  Returns ``(sums, refs)``: per-row sums and the reference each is relative to.
+    """
+    refs = torch.full_like(sums, float(ref0))
+    bad = sums < UNDERFLOW
+    if not bool(bad.any()):
+        return sums, refs
+    vmin = float((values * scale).min())
+    ref = float(ref0)
+    while bool(bad.any()) and ref > vmin + LEVEL_STEP:
+        ref -= LEVEL_STEP
+        rows = bad.nonzero().flatten()
+        table = _ops.exp_table(values, scale, torch.tensor([ref], dtype=torch.float64, device=values.device))
+        sums[rows] = rerun(rows.tolist(), table)
+        refs[rows] = ref
+        bad = sums < UNDERFLOW
+    return sums, refs
+
+
 def bootstrap_partial_sums(data, kT, n_resamples, sample_size, max_idx, batch, generator, rng,
                            shard_offset=0, global_max=None):
-    """Per-resample ``sum_j exp(v[idx_rj] - max)`` over the draws that fall into this rank's shard.
+    """Per-resample ``sum_j exp(v[idx_rj] - ref_r)`` over the draws of every resample (``v = -data / kT``).
 
-    ``data`` is the local shard ``[shard_offset, shard_offset + len(data))`` of the global array; every rank
-    walks the same global index stream.  Returns ``(sums (n_resamples,) float64, max)``; sums of all ranks
-    add up to the single-GPU result (one all-reduce of ``n_resamples`` doubles).  Single GPU: shard = all.
+    The table the draws index is ``data[:max_idx]`` -- with ``take_first_only`` the resamples only see the first
+    ``bootstrap_sample_size`` samples (reference bootstrap.py:207-218), so its reference maximum must not come from
+    later ones.  Returns ``(sums (n_resamples,) float64, refs (n_resamples,) float64)``; ``refs`` is the table maximum
+    except for rows repaired by :func:`repair_underflow`.  Single GPU: shard = all; the sharded version lives in
+    tfep_b200.analysis.distributed.
     """
     if shard_offset != 0 or global_max is not None:
         raise NotImplementedError('sharded bootstrap: see tfep_b200.analysis.distributed')
     scale = -1.0 / kT
-    o = _ops.lse(data, scale)
-    e = _ops.exp_table(data, scale, o[:1])
-    sums = torch.empty(n_resamples, dtype=torch.float64, device=data.device)
+    values = data[:max_idx]
+    o = _ops.lse(values, scale)
+    e = _ops.exp_table(values, scale, o[:1])
     if rng == 'philox':
         seed = int(torch.randint(0, 2**62, (1,), generator=generator).item())
         cells = table_cells(0, max_idx)
         counts = stratified_counts(n_resamples, sample_size, cells, max_idx, seed)
-        return philox_cell_sums(e, 0, cells, range(len(cells)), counts, seed, n_resamples, sample_size), o[0]
+        everything = range(len(cells))
+        sums = philox_cell_sums(e, 0, cells, everything, counts, seed, n_resamples, sample_size)
+        return repair_underflow(sums, o[0], values, scale, lambda rows, table: philox_cell_sums(
+            table, 0, cells, everything, counts, seed, n_resamples, sample_size, rows=rows))
+    sums = torch.empty(n_resamples, dtype=torch.float64, device=data.device)
+    refs = torch.empty(n_resamples, dtype=torch.float64, device=data.device)
     gen = torch.default_generator if generator is None else generator
     state = _generator_to_state(gen).to(data.device)
-    idx = torch.empty(min(batch, n_resamples) * sample_size, dtype=torch.int32, device=data.device)
+    batch = max(1, min(batch, n_resamples, _ops.MAX_RESAMPLES_PER_CALL))
+    idx = torch.empty(batch * sample_size, dtype=torch.int32, device=data.device)
     for k in range(0, n_resamples, batch):
         nb = min(batch, n_resamples - k)
         _ops.mt19937_indices(state, nb * sample_size, max_idx, out=idx)
-        sums[k:k + nb] = _ops.bootstrap_sums(e, max_idx, nb, sample_size, idx[:nb * sample_size].view(nb, sample_size))
+        rows_idx = idx[:nb * sample_size].view(nb, sample_size)
+        part = _ops.bootstrap_sums(e, max_idx, nb, sample_size, rows_idx)
+        sums[k:k + nb], refs[k:k + nb] = repair_underflow(part, o[0], values, scale, lambda rows, table: _ops.bootstrap_sums(
+            table, max_idx, len(rows), sample_size, rows_idx[rows].contiguous()))
     _state_to_generator(gen, state)
-    return sums, o[0]
+    return sums, refs
 
 
 def _bootstrap_statistics(data, statistic, n_resamples, sample_size, take_first_only, batch, generator, rng):
@@ -203,8 +260,8 @@ def _bootstrap_statistics(data, statistic, n_resamples, sample_size, take_first_
     kT = _fused_kT(statistic)
     if kT is not None and data.dim() == 1:
         batch = max(1, min(batch, n_resamples, (1 << 28) // max(sample_size, 1) or 1))
-        sums, m = bootstrap_partial_sums(data, kT, n_resamples, sample_size, max_idx, batch, generator, rng)
-        return (-kT * (m + torch.log(sums) - _log_n(sample_size))).to(data.dtype)
+        sums, refs = bootstrap_partial_sums(data, kT, n_resamples, sample_size, max_idx, batch, generator, rng)
+        return (-kT * (refs + torch.log(sums) - _log_n(sample_size))).to(data.dtype)
 
     # generic statistic: indices from the same stream, gather, user callable on (batch, sample_size[, dim])
     gen = torch.default_generator if generator is None else generator

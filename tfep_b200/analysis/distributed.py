@@ -10,8 +10,8 @@ Every sample is independent through the flow, so nothing is exchanged until the 
 * bootstrap, Philox: the shards are cut into L2-sized cells, every rank draws the same Multinomial counts of
   draws per cell (same seed) and generates only the draws of its own cells (``stratified_counts``) -- no draw is
   generated twice, so the work divides by the number of ranks;
-* either way the per-resample sums are rescaled to the global maximum and added with ONE all-reduce of
-  ``n_resamples`` doubles (``combine_bootstrap_sums``).
+* either way the per-resample partial sums are combined in the log domain with a MAX and a SUM all-reduce of
+  ``n_resamples`` doubles (``combine_bootstrap_sums``), exact for data of any dynamic range.
 
 The collective helpers work on CPU tensors with the gloo backend too (that is how the host logic is tested
 without GPUs); the local reductions are CUDA kernels.
@@ -21,8 +21,8 @@ import torch
 import torch.distributed as dist
 
 from .. import _ops
-from .bootstrap import (_fused_kT, _generator_to_state, _state_to_generator, philox_cell_sums, stratified_counts,
-                        table_cells)
+from .bootstrap import (_fused_kT, _generator_to_state, _state_to_generator, philox_cell_sums, repair_underflow,
+                        stratified_counts, table_cells)
 from .estimator import _log_n, combine_partials
 
 
@@ -39,15 +39,19 @@ def combine_lse_partials(partial, group=None):
     return combine_partials(torch.stack(parts))
 
 
-def combine_bootstrap_sums(sums, local_max, group=None):
-    """``sums[r] = sum over this rank's shard of exp(v - local_max)`` -> global ``(sums, max)``."""
+def combine_bootstrap_sums(sums, local_ref, group=None):
+    """``sums[r] = sum over this rank's shard of exp(v - local_ref[r])`` (``local_ref``: a scalar or one reference per
+    resample) -> global ``(sums, ref)`` with one reference per resample.  Combined in the log domain -- a MAX and a SUM
+    all-reduce of ``n_resamples`` doubles -- so that a rank whose shard lies far below another's neither underflows nor
+    drags the others down (the reference takes a per-row logsumexp, bootstrap.py:227-231)."""
     if _world(group) == 1:
-        return sums, local_max
-    gmax = local_max.clone()
-    dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)
-    scaled = sums * torch.exp(local_max - gmax)
+        return sums, local_ref
+    log_local = torch.where(sums > 0, local_ref + torch.log(sums.clamp_min(1e-300)), torch.full_like(sums, -float('inf')))
+    ref = log_local.clone()
+    dist.all_reduce(ref, op=dist.ReduceOp.MAX, group=group)
+    scaled = torch.where(torch.isfinite(log_local), torch.exp(log_local - ref), torch.zeros_like(sums))
     dist.all_reduce(scaled, op=dist.ReduceOp.SUM, group=group)
-    return scaled, gmax
+    return scaled, ref
 
 
 def _total(n_local, device, group):
@@ -98,24 +102,31 @@ def bootstrap_statistics_sharded(work_shard, shard_offset, n_total, kT=1.0, n_re
     scale = -1.0 / kT
     o = _ops.lse(work_shard, scale)
     e = _ops.exp_table(work_shard, scale, o[:1])
-    sums = torch.empty(n_resamples, dtype=torch.float64, device=dev)
     if rng == 'philox':
         seed = int(torch.randint(0, 2**62, (1,), generator=generator).item())
         cells, owner = shard_cells(shard_offset, work_shard.numel(), n_total, dev, group)
         counts = stratified_counts(n_resamples, n_total, cells, n_total, seed)
         rank = dist.get_rank(group) if _world(group) > 1 else 0
-        sums = philox_cell_sums(e, shard_offset, cells, [i for i, o in enumerate(owner) if o == rank], counts, seed,
-                                n_resamples, n_total)
+        mine = [i for i, o_ in enumerate(owner) if o_ == rank]
+        sums = philox_cell_sums(e, shard_offset, cells, mine, counts, seed, n_resamples, n_total)
+        sums, refs = repair_underflow(sums, o[0], work_shard, scale, lambda rows, table: philox_cell_sums(
+            table, shard_offset, cells, mine, counts, seed, n_resamples, n_total, rows=rows))
     else:
+        sums = torch.empty(n_resamples, dtype=torch.float64, device=dev)
+        refs = torch.empty(n_resamples, dtype=torch.float64, device=dev)
         gen = torch.default_generator if generator is None else generator
         state = _generator_to_state(gen).to(dev)
-        batch = max(1, min(n_resamples if batch is None else batch, (1 << 28) // max(n_total, 1) or 1))
+        batch = max(1, min(n_resamples if batch is None else batch, (1 << 28) // max(n_total, 1) or 1,
+                           _ops.MAX_RESAMPLES_PER_CALL))
         idx = torch.empty(batch * n_total, dtype=torch.int32, device=dev)
         for k in range(0, n_resamples, batch):
             nb = min(batch, n_resamples - k)
             _ops.mt19937_indices(state, nb * n_total, n_total, out=idx)
-            sums[k:k + nb] = _ops.bootstrap_sums(e, n_total, nb, n_total, idx[:nb * n_total].view(nb, n_total),
-                                                 shard_lo=shard_offset)
+            rows_idx = idx[:nb * n_total].view(nb, n_total)
+            part = _ops.bootstrap_sums(e, n_total, nb, n_total, rows_idx, shard_lo=shard_offset)
+            # a resample without a draw in this shard keeps a sum of zero: repair_underflow stops at the shard's minimum
+            sums[k:k + nb], refs[k:k + nb] = repair_underflow(part, o[0], work_shard, scale, lambda rows, table: _ops.bootstrap_sums(
+                table, n_total, len(rows), n_total, rows_idx[rows].contiguous(), shard_lo=shard_offset))
         _state_to_generator(gen, state)
-    sums, gmax = combine_bootstrap_sums(sums, o[0], group)
-    return (-kT * (gmax + torch.log(sums) - _log_n(n_total))).to(work_shard.dtype)
+    sums, ref = combine_bootstrap_sums(sums, refs, group)
+    return (-kT * (ref + torch.log(sums) - _log_n(n_total))).to(work_shard.dtype)

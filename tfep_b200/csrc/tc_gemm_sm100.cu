@@ -19,6 +19,13 @@
 // the next layer (written coalesced: consecutive rows are consecutive 16-byte chunks of a slab).  A per-n-tile range
 // of k-blocks skips the all-zero part of a degree-sorted (staircase) masked weight; split-K with fp32 atomics serves
 // the weight gradient, whose reduction runs over the batch.
+//
+// SPLIT PRECISION (n_split = 2 or 3; the fp32-class conditioner on the tensor cores): every operand is
+// stored as n_split bf16 images x = x_0 + x_1 (+ x_2) with x_0 = bf16(x), x_1 = bf16(x - x_0), x_2 = bf16(x - x_0 - x_1)
+// (16 / 24 significant bits), and a k-step issues the products A_i B_j with i + j < n_split -- 3 or 6 MMAs, the dropped
+// cross terms are below 2^-16 / 2^-24 of the product -- into the same fp32 accumulator.  A ring stage then holds half a
+// k-block (32 k) of all images of both operands; the epilogue splits the activations it hands to the next layer the
+// same way.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -28,8 +35,8 @@ namespace tcg {
 using namespace tc;
 
 constexpr int BM = 128, BN = 256, KB = 64;
-constexpr int A_BLOCK = BM * KB * 2, B_BLOCK = BN * KB * 2, STAGE_BYTES = A_BLOCK + B_BLOCK;   // 16 + 32 KB
-constexpr int STAGES = 3;
+constexpr int A_BLOCK = BM * KB * 2, B_BLOCK = BN * KB * 2;   // 16 + 32 KB: one k-block of one image
+constexpr int MAX_STAGES = 3;
 constexpr int EPI_WARPS = 16;
 constexpr int XP_LD = 33;                                  // transposition buffer: [32 columns][33] floats per epilogue warp
 constexpr int XP_FLOATS = 32 * XP_LD;
@@ -37,6 +44,7 @@ constexpr int THREADS = 64 + EPI_WARPS * 32;
 
 struct Params {
     const uint8_t* a_img; const uint8_t* b_img;
+    int64_t a_split_stride, b_split_stride, out_split_stride;   // bytes between the images of the split terms
     int M, N, K, k_blocks;              // k_blocks = ceil(K / 64)
     float* C; int64_t ldc;              // fp32 output (row-major) or null
     const float* bias;                  // (N,) or null
@@ -55,7 +63,7 @@ struct Params {
 };
 
 struct Smem {
-    uint64_t full[STAGES], empty[STAGES];
+    uint64_t full[MAX_STAGES], empty[MAX_STAGES];
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
     uint32_t pad[3];
@@ -69,7 +77,20 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
 
+// Stage geometry per split count: one term -> a whole k-block (64 k) per stage, three stages; two terms -> half a
+// k-block of both terms (48 KB again), three stages; three terms -> 72 KB, two stages.
+template <int NSPLIT> struct Geo {
+    static constexpr int KS = NSPLIT == 1 ? KB : KB / 2;               // k extent of a stage
+    static constexpr int A_PART = BM * KS * 2, B_PART = BN * KS * 2;   // one term of one operand
+    static constexpr int STAGE = NSPLIT * (A_PART + B_PART);
+    static constexpr int N_STAGES = NSPLIT == 3 ? 2 : 3;
+    static constexpr int PARTS = KB / KS;                              // stages per k-block
+};
+
+template <int NSPLIT>
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_constant__ Params p) {
+    using G = Geo<NSPLIT>;
+    constexpr int STAGES = G::N_STAGES, STAGE_BYTES = G::STAGE;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* ring = smem_raw;
     float* xpose = reinterpret_cast<float*>(ring + (size_t)STAGES * STAGE_BYTES);
@@ -112,13 +133,19 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             if (skipped(tm, tn)) continue;
             int k0, k1;
             krange(tn, k0, k1);
-            for (int kb = k0; kb < k1; ++kb) {
+            for (int kp = k0 * G::PARTS; kp < k1 * G::PARTS; ++kp) {
+                const int kb = kp / G::PARTS, part = kp % G::PARTS;     // a stage = part `part` of k-block kb, all terms
                 mbar_wait(&sm->empty[stage], phase ^ 1, p.error, 1);
                 if (elect_one()) {
                     uint8_t* dst = ring + (size_t)stage * STAGE_BYTES;
                     mbar_expect_tx(&sm->full[stage], STAGE_BYTES);
-                    bulk_g2s(dst, p.a_img + ((size_t)tm * p.k_blocks + kb) * A_BLOCK, A_BLOCK, &sm->full[stage]);
-                    bulk_g2s(dst + A_BLOCK, p.b_img + ((size_t)tn * p.k_blocks + kb) * B_BLOCK, B_BLOCK, &sm->full[stage]);
+                    const uint8_t* a_src = p.a_img + ((size_t)tm * p.k_blocks + kb) * A_BLOCK + (size_t)part * G::A_PART;
+                    const uint8_t* b_src = p.b_img + ((size_t)tn * p.k_blocks + kb) * B_BLOCK + (size_t)part * G::B_PART;
+#pragma unroll
+                    for (int i = 0; i < NSPLIT; ++i) {
+                        bulk_g2s(dst + i * G::A_PART, a_src + i * p.a_split_stride, G::A_PART, &sm->full[stage]);
+                        bulk_g2s(dst + NSPLIT * G::A_PART + i * G::B_PART, b_src + i * p.b_split_stride, G::B_PART, &sm->full[stage]);
+                    }
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -140,19 +167,28 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             tc_fence_after();
             const uint32_t d_tmem = tmem + buf * BN;
             uint32_t accumulate = 0u;
-            for (int kb = k0; kb < k1; ++kb) {
+            for (int kp = k0 * G::PARTS; kp < k1 * G::PARTS; ++kp) {
                 mbar_wait(&sm->full[stage], phase, p.error, 3);
                 tc_fence_after();
                 const uint32_t a16 = ring16 + stage * (STAGE_BYTES >> 4);
-                const uint32_t b16 = a16 + (A_BLOCK >> 4);
+                const uint32_t b16 = a16 + ((NSPLIT * G::A_PART) >> 4);
                 if (elect_one()) {
+                    // terms A_i B_j with i + j < NSPLIT, the smallest first (they meet an accumulator of their own size)
 #pragma unroll
-                    for (uint32_t ks = 0; ks < KB / 16; ++ks) {
-                        // per K = 16 step two 8-k slabs: A slab = 128 rows x 16 B = 2 KB, B slab = 256 rows x 16 B = 4 KB
-                        const uint64_t da = ((uint64_t)DESC_HI << 32) | (a16 + ks * 256u + ((2048u >> 4) << 16));
-                        const uint64_t db = ((uint64_t)DESC_HI << 32) | (b16 + ks * 512u + ((4096u >> 4) << 16));
-                        umma_ss(d_tmem, da, db, idesc, accumulate);
-                        accumulate = 1u;
+                    for (int sum = NSPLIT - 1; sum >= 0; --sum) {
+#pragma unroll
+                        for (int i = 0; i <= sum; ++i) {
+                            const int j = sum - i;
+                            const uint32_t ai = a16 + i * (G::A_PART >> 4), bj = b16 + j * (G::B_PART >> 4);
+#pragma unroll
+                            for (uint32_t ks = 0; ks < G::KS / 16; ++ks) {
+                                // per K = 16 step two 8-k slabs: A slab = 128 rows x 16 B = 2 KB, B slab = 256 rows x 16 B = 4 KB
+                                const uint64_t da = ((uint64_t)DESC_HI << 32) | (ai + ks * 256u + ((2048u >> 4) << 16));
+                                const uint64_t db = ((uint64_t)DESC_HI << 32) | (bj + ks * 512u + ((4096u >> 4) << 16));
+                                umma_ss(d_tmem, da, db, idesc, accumulate);
+                                accumulate = 1u;
+                            }
+                        }
                     }
                     umma_commit(&sm->empty[stage]);
                 }
@@ -256,11 +292,25 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                         if (kblk < p.out_k_blocks) {
                             uint8_t* blk = p.out_img + ((size_t)tm * p.out_k_blocks + kblk) * A_BLOCK + (size_t)row * 16;
                             const int slab = (gn0 & 63) >> 3;
-                            uint4 q0, q1;
-                            q0.x = pack_bf16(v[0], v[1]); q0.y = pack_bf16(v[2], v[3]); q0.z = pack_bf16(v[4], v[5]); q0.w = pack_bf16(v[6], v[7]);
-                            q1.x = pack_bf16(v[8], v[9]); q1.y = pack_bf16(v[10], v[11]); q1.z = pack_bf16(v[12], v[13]); q1.w = pack_bf16(v[14], v[15]);
-                            *reinterpret_cast<uint4*>(blk + (size_t)slab * 2048) = q0;
-                            *reinterpret_cast<uint4*>(blk + (size_t)(slab + 1) * 2048) = q1;
+                            float res[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) res[i] = v[i];
+#pragma unroll
+                            for (int t = 0; t < NSPLIT; ++t) {
+                                // term t of the split: bf16 of what the previous terms left over
+                                uint32_t q[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    q[i] = pack_bf16(res[2 * i], res[2 * i + 1]);
+                                    if (t + 1 < NSPLIT) {
+                                        res[2 * i] -= __uint_as_float(q[i] << 16);
+                                        res[2 * i + 1] -= __uint_as_float(q[i] & 0xffff0000u);
+                                    }
+                                }
+                                uint8_t* dst = blk + (size_t)t * p.out_split_stride;
+                                *reinterpret_cast<uint4*>(dst + (size_t)slab * 2048) = make_uint4(q[0], q[1], q[2], q[3]);
+                                *reinterpret_cast<uint4*>(dst + (size_t)(slab + 1) * 2048) = make_uint4(q[4], q[5], q[6], q[7]);
+                            }
                         }
                     }
                 }
@@ -323,8 +373,22 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
 
 // fp32 row-major (or its transpose) -> bf16 image.  One CTA per (row block, k block); 256 threads.
 //   transpose == 0: element (row, k) = src[row * ld + k];  transpose == 1: element (row, k) = src[k * ld + row].
+// term `t` of the bf16 split of 8 values (in place: v becomes the remainder)
+__device__ __forceinline__ uint4 split_term(float (&v)[8], bool more) {
+    uint32_t q[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        q[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+        if (more) {
+            v[2 * i] -= __uint_as_float(q[i] << 16);
+            v[2 * i + 1] -= __uint_as_float(q[i] & 0xffff0000u);
+        }
+    }
+    return make_uint4(q[0], q[1], q[2], q[3]);
+}
+
 __global__ void __launch_bounds__(256) tc_pack_kernel(const float* __restrict__ src, int64_t ld, int rows, int K, int block_rows,
-                                                      int transpose, uint8_t* __restrict__ img) {
+                                                      int transpose, uint8_t* __restrict__ img, int n_split, int64_t split_stride) {
     __shared__ float tile[64][65];
     const int k_blocks = (K + KB - 1) / KB;
     const int rb = blockIdx.y, kb = blockIdx.x;
@@ -338,9 +402,9 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const float* __restrict__ 
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = (gr < rows && gk + j < K) ? __ldg(src + (int64_t)gr * ld + gk + j) : 0.f;
-            uint4 q;
-            q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]); q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
-            *reinterpret_cast<uint4*>(blk + (size_t)slab * block_rows * 16 + (size_t)row * 16) = q;
+            for (int t = 0; t < n_split; ++t)
+                *reinterpret_cast<uint4*>(blk + (size_t)t * split_stride + (size_t)slab * block_rows * 16 + (size_t)row * 16) =
+                    split_term(v, t + 1 < n_split);
         }
     } else {
         // 64 rows of the image at a time: read src[k][row] coalesced along rows, transpose through shared memory
@@ -353,12 +417,12 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const float* __restrict__ 
             __syncthreads();
             for (int i = threadIdx.x; i < 64 * 8; i += 256) {
                 const int rr = i % 64, slab = i / 64;
-                uint4 q;
-                q.x = pack_bf16(tile[slab * 8 + 0][rr], tile[slab * 8 + 1][rr]);
-                q.y = pack_bf16(tile[slab * 8 + 2][rr], tile[slab * 8 + 3][rr]);
-                q.z = pack_bf16(tile[slab * 8 + 4][rr], tile[slab * 8 + 5][rr]);
-                q.w = pack_bf16(tile[slab * 8 + 6][rr], tile[slab * 8 + 7][rr]);
-                *reinterpret_cast<uint4*>(blk + (size_t)slab * block_rows * 16 + (size_t)(rs + rr) * 16) = q;
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = tile[slab * 8 + j][rr];
+                for (int t = 0; t < n_split; ++t)
+                    *reinterpret_cast<uint4*>(blk + (size_t)t * split_stride + (size_t)slab * block_rows * 16 +
+                                              (size_t)(rs + rr) * 16) = split_term(v, t + 1 < n_split);
             }
             __syncthreads();
         }
@@ -423,6 +487,20 @@ extern "C" int64_t tfepb_tc_image_bytes(int64_t rows, int64_t k, int32_t block_r
     return rb * kb * (int64_t)block_rows * 128;
 }
 
+extern "C" int tfepb_tc_pack_split(const float* src, int64_t ld, int32_t rows, int32_t k, int32_t block_rows, int32_t transpose,
+                                   int32_t n_split, void* image, tfepb_stream_t stream) {
+    TFEPB_CHECK_ARG(src && image, "null buffer");
+    TFEPB_CHECK_ARG(rows > 0 && k > 0, "bad sizes");
+    TFEPB_CHECK_ARG(n_split >= 1 && n_split <= 3, "n_split must be 1, 2 or 3");
+    TFEPB_CHECK_ARG(block_rows == 128 || block_rows == 256, "block_rows must be 128 (A operand) or 256 (B operand)");
+    TFEPB_CHECK_ARG((reinterpret_cast<uintptr_t>(image) & 15) == 0, "the image must be 16-byte aligned");
+    if (int rc = require_sm100()) return rc;
+    dim3 grid((unsigned)((k + tcg::KB - 1) / tcg::KB), (unsigned)((rows + block_rows - 1) / block_rows));
+    tcg::tc_pack_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, ld, rows, k, block_rows, transpose, (uint8_t*)image, n_split,
+                                                            tfepb_tc_image_bytes(rows, k, block_rows));
+    return check_launch("tc_pack");
+}
+
 extern "C" int tfepb_tc_pack(const float* src, int64_t ld, int32_t rows, int32_t k, int32_t block_rows, int32_t transpose,
                              void* image, tfepb_stream_t stream) {
     TFEPB_CHECK_ARG(src && image, "null buffer");
@@ -431,7 +509,7 @@ extern "C" int tfepb_tc_pack(const float* src, int64_t ld, int32_t rows, int32_t
     TFEPB_CHECK_ARG((reinterpret_cast<uintptr_t>(image) & 15) == 0, "the image must be 16-byte aligned");
     if (int rc = require_sm100()) return rc;
     dim3 grid((unsigned)((k + tcg::KB - 1) / tcg::KB), (unsigned)((rows + block_rows - 1) / block_rows));
-    tcg::tc_pack_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, ld, rows, k, block_rows, transpose, (uint8_t*)image);
+    tcg::tc_pack_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, ld, rows, k, block_rows, transpose, (uint8_t*)image, 1, 0);
     return check_launch("tc_pack");
 }
 
@@ -485,13 +563,27 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
     p.atomic = splits > 1 ? 1 : 0;
     p.k_chunk_blocks = splits > 1 ? (p.k_blocks + splits - 1) / splits : 0;
     if (splits > 1) splits = (p.k_blocks + p.k_chunk_blocks - 1) / p.k_chunk_blocks;
-    const size_t smem = (size_t)tcg::STAGES * tcg::STAGE_BYTES + (size_t)tcg::EPI_WARPS * tcg::XP_FLOATS * 4 + sizeof(tcg::Smem) + 1024;
-    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(tcg::tc_gemm_kernel), smem)) return rc;
+    const int n_split = a->n_split > 1 ? a->n_split : 1;
+    TFEPB_CHECK_ARG(n_split <= 3, "n_split must be 1, 2 or 3");
+    TFEPB_CHECK_ARG(n_split == 1 || (a->out_image_t == nullptr && a->split_k <= 1),
+                    "split-precision products are forward products: no transposed image, no split-K");
+    p.a_split_stride = n_split > 1 ? tfepb_tc_image_bytes(a->m, a->k, 128) : 0;
+    p.b_split_stride = n_split > 1 ? tfepb_tc_image_bytes(a->n, a->k, 256) : 0;
+    p.out_split_stride = n_split > 1 ? tfepb_tc_image_bytes(a->m, a->n, 128) : 0;
+    const int stage_bytes = n_split == 1 ? tcg::Geo<1>::STAGE : n_split == 2 ? tcg::Geo<2>::STAGE : tcg::Geo<3>::STAGE;
+    const int stages = n_split == 3 ? tcg::Geo<3>::N_STAGES : tcg::Geo<1>::N_STAGES;
+    const size_t smem = (size_t)stages * stage_bytes + (size_t)tcg::EPI_WARPS * tcg::XP_FLOATS * 4 + sizeof(tcg::Smem) + 1024;
+    const void* kernel = n_split == 1 ? reinterpret_cast<const void*>(tcg::tc_gemm_kernel<1>)
+                       : n_split == 2 ? reinterpret_cast<const void*>(tcg::tc_gemm_kernel<2>)
+                                      : reinterpret_cast<const void*>(tcg::tc_gemm_kernel<3>);
+    if (int rc = ensure_dynamic_smem(kernel, smem)) return rc;
     const int tiles = p.tiles_m * p.tiles_n;
     int gx = sm_count() / splits;
     if (gx < 1) gx = 1;
     if (gx > tiles) gx = tiles;
     dim3 grid((unsigned)gx, (unsigned)splits);
-    tcg::tc_gemm_kernel<<<grid, tcg::THREADS, smem, as_stream(stream)>>>(p);
+    if (n_split == 1) tcg::tc_gemm_kernel<1><<<grid, tcg::THREADS, smem, as_stream(stream)>>>(p);
+    else if (n_split == 2) tcg::tc_gemm_kernel<2><<<grid, tcg::THREADS, smem, as_stream(stream)>>>(p);
+    else tcg::tc_gemm_kernel<3><<<grid, tcg::THREADS, smem, as_stream(stream)>>>(p);
     return check_launch("tc_gemm_kernel");
 }

@@ -105,6 +105,9 @@ class MADE(_conditioner.Conditioner):
         self._degree_chain = [d.clone() for d in chain]
         self._plan = MadePlan(self._degree_chain)       # hidden units degree-sorted, output in reference order
         self._packed_cache = {}
+        self._packed_epoch = 0
+        # loading a checkpoint writes the parameters in place: drop every packed copy derived from the old values
+        self.register_load_state_dict_post_hook(lambda module, incompatible_keys: module.invalidate_packed())
 
     # -- reference properties -------------------------------------------------------------------
     @property
@@ -133,7 +136,7 @@ class MADE(_conditioner.Conditioner):
         with torch.no_grad():
             (last.weight_g if self.weight_norm else last.weight).zero_()
         last.bias.data = output.to(last.bias.data)
-        self._packed_cache.clear()
+        self.invalidate_packed()
 
     # -- evaluation -----------------------------------------------------------------------------
     def _linear_layers(self):
@@ -150,8 +153,19 @@ class MADE(_conditioner.Conditioner):
             out.append((w, lin.bias))
         return out
 
+    def invalidate_packed(self):
+        """Forget every packed / padded / bf16 copy of the weights (this module's, the fused kernels' and the inverse
+        sweep's: they all key on :meth:`_param_versions`).  The caches notice ordinary in-place updates (optimizer steps,
+        ``copy_`` on the parameter, ``load_state_dict``) through the tensors' version counters; writes through ``.data``
+        (``p.data.copy_(ema)``, ``p.data.clamp_()``) bypass those counters and MUST be followed by this call."""
+        self._packed_epoch += 1
+        self._packed_cache.clear()
+
     def _param_versions(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        """Cache key of everything derived from the weights: parameters AND mask buffers (pointer, version) plus the
+        explicit invalidation epoch."""
+        tensors = list(self.parameters()) + [lin.mask for lin in self._linear_layers()]
+        return (self._packed_epoch,) + tuple((t.data_ptr(), t._version) for t in tensors)
 
     def packed_weights(self, plan=None):
         """Packed (degree-sorted) effective weights for ``plan``; cached while gradients are off."""
@@ -173,11 +187,21 @@ class MADE(_conditioner.Conditioner):
         """Conditioner output in the packed output order of ``plan``.  ``precision='bf16'``: the three products of
         every layer (forward, and both backward products under autograd) run on the tensor cores."""
         pw, pb = self.packed_weights(plan)
-        if precision == 'bf16':
+        if precision in ('bf16', 'bf16x3', 'bf16x6'):
             if x.dtype != torch.float32:
-                raise _ops._lib.TfepB200Error("precision='bf16' takes float32 inputs")
+                raise _ops._lib.TfepB200Error(f"precision={precision!r} takes float32 inputs")
             kb_fwd, kb_bwd, rr_w = plan.tc_ranges(x.device)
-            return _ops.made_forward_tc(x, pw, pb, kb_fwd, kb_bwd, rr_w)
+            n_split = {'bf16': 1, 'bf16x3': 2, 'bf16x6': 3}[precision]
+            images = None
+            if n_split > 1 and not (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
+                # split images of the packed weights, cached like the packed weights themselves
+                key = ('tc_images', id(plan), n_split, self._param_versions())
+                hit = self._packed_cache.get(key[:3])
+                if hit is None or hit[0] != key:
+                    hit = (key, [_ops.tc_pack(w, 256, n_split=n_split) for w in pw])
+                    self._packed_cache[key[:3]] = hit
+                images = hit[1]
+            return _ops.made_forward_tc(x, pw, pb, kb_fwd, kb_bwd, rr_w, n_split=n_split, weight_images=images)
         k_ranges, n_ranges, _ = plan.tables(x.device)
         return _ops.made_forward(x, pw, pb, k_ranges, n_ranges)
 

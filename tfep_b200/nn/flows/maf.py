@@ -28,6 +28,9 @@ from ..transformers.transformer import Transformer
 from .autoregressive import AutoregressiveFlow, _InverseFunction, _needs_grad
 
 
+PRECISIONS = ('fp32', 'bf16', 'bf16x3', 'bf16x6')
+
+
 class MAF(AutoregressiveFlow):
     """Masked Autoregressive Flow: an autoregressive flow with a MADE conditioner and any MAF transformer.
 
@@ -44,6 +47,13 @@ class MAF(AutoregressiveFlow):
         Applied to the conditioner input; must implement ``get_degrees_out(degrees_in)``.
     weight_norm : bool
     initialize_identity : bool
+    precision : str
+        The only argument the reference does not have (keyword only).  ``'fp32'`` (default): exact FFMA kernels, parity
+        <= 1e-5 with the reference.  ``'bf16'``: tensor cores with bf16 operands and fp32 accumulation (the fused
+        one-launch kernels where they cover the layer, else the general tcgen05 GEMM), stated tolerance in DESIGN.md.
+        ``'bf16x3'`` / ``'bf16x6'``: tensor cores with every operand split into two / three bf16 terms (3 / 6 products
+        per reduction step, fp32 accumulation): the conditioner at fp32-class accuracy on the tensor cores.
+        Also an attribute: ``maf.precision = ...`` switches an existing module.
     """
 
     def __init__(
@@ -54,7 +64,11 @@ class MAF(AutoregressiveFlow):
             embedding: Optional[torch.nn.Module] = None,
             weight_norm: bool = True,
             initialize_identity: bool = True,
+            *,
+            precision: str = 'fp32',
     ):
+        if precision not in PRECISIONS:
+            raise ValueError(f'precision must be one of {PRECISIONS}')
         if transformer is None:
             transformer = AffineTransformer()
         degrees_in = ensure_tensor_sequence(degrees_in)
@@ -81,9 +95,13 @@ class MAF(AutoregressiveFlow):
         self._packing = None
         self._fused = None
         self._sweep = None
-        #: 'fp32' (exact FFMA path, parity <= 1e-5 with the reference) or 'bf16' (fused tcgen05 tensor-core
-        #: kernel: bf16 operands, fp32 accumulation and epilogue; inference only, see tfep_b200/_fused.py)
-        self.precision = 'fp32'
+        #: see the class docstring; one of PRECISIONS
+        self.precision = precision
+
+    def invalidate_packed(self):
+        """Forget every packed copy of the conditioner weights; required after writing parameters through ``.data``
+        (see :meth:`tfep_b200.nn.conditioners.MADE.invalidate_packed`)."""
+        self._conditioner.invalidate_packed()
 
     def n_parameters(self) -> int:
         """The total number of (unmasked) parameters."""
@@ -138,8 +156,8 @@ class MAF(AutoregressiveFlow):
     def forward(self, x: torch.Tensor):
         """Returns ``(y, log_det_J)`` with shapes ``(batch, n_features)`` and ``(batch,)``."""
         pk = self._pack()
-        if self.precision not in ('fp32', 'bf16'):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if self.precision not in PRECISIONS:
+            raise ValueError(f'precision must be one of {PRECISIONS}')
         if self.precision == 'bf16' and self._use_fused(x):
             return self._forward_fused(x)
         if pk is False or self._n_conditioner_indices > 0:
