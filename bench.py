@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Benchmark of the MAF forward + log|det J| hot path (BASELINE.json metric) on 1..N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|bf16|bf16x3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--precision bf16|bf16x6|bf16x3|fp32] [--skip-secondary]
 
 One "step" = one forward pass of the BASELINE.json configuration cfg2 (4 x MAF, MADE conditioner 66->328->328->1650,
 circular neural spline K=8, D=66) over one batch of 65536 synthetic samples per GPU (weak scaling: contiguous
@@ -13,7 +14,12 @@ batch shards, no data-path collective).  Rank 0 prints ONE JSON line (contract i
              forward, device -> host copy of (y, log_det_J) inside the timed region;
   roofline   dominant kernel timed alone with CUDA events vs the measured tensor peak (MEASURED_PEAKS.json);
   cpu_baseline  the oracle (CPU restatement of the reference's PyTorch path, bit-identical to it) on the box's
-             host cores, bounded sample.
+             host cores, bounded sample; its outputs double as the parity check of the GPU arms (`parity`);
+  parity_path   the same forward at fp32-class accuracy on the tensor cores (precision='bf16x6': operands split into
+             three bf16 terms, six products per reduction step), timed beside the bf16 headline;
+  cfg3 / cfg4   the other BASELINE.json configurations that exchange data between ranks: the D=300 training step with
+             the data-parallel gradient all-reduce, and the estimator + 1000-resample bootstrap over 1e8 work values
+             with the (max, sum exp) and per-resample all-reduces (secondary objects, outside the headline timing).
 `--impl reference` times only that CPU path (the reference is pure Python on PyTorch; /root/reference does not
 exist on the GPU box, the oracle restates it bit for bit -- see oracle/check_against_reference.py).
 """
@@ -37,7 +43,6 @@ METRIC = 'MAF fwd+logdet samples/s (D=66, spline)'
 UNIT = 'samples/s'
 WORKLOAD = 'cfg2: 4xMAF circular spline K=8, D=66, MADE 66-328-328-1650, batch 65536 per GPU'
 BATCH = 65536
-CPU_SAMPLE = 16384
 
 
 def peaks():
@@ -146,35 +151,45 @@ def oracle_flow(state_dicts=None):
             for l, sd in enumerate(state_dicts)]
 
 
-def time_cpu_reference(steps, warmup, sample=CPU_SAMPLE, state_dicts=None):
+def product_state_dicts():
+    """The weights the GPU arm evaluates (build_flow: torch.manual_seed(1234)), as CPU state dicts with the reference's
+    key names: both arms and every leg of this file run the same parameters."""
+    return [{k: v.detach().cpu() for k, v in m.state_dict().items()} for m in build_flow(torch.device('cpu'))]
+
+
+def time_cpu_reference(steps, warmup, sample, state_dicts=None, keep_output=False):
     """The reference's CPU PyTorch path (oracle restatement), all host threads, no_grad."""
     from oracle import flow_oracle as fo
     mods = oracle_flow(state_dicts)
     x = cfg2_input(sample)
     torch.set_num_threads(os.cpu_count() or 1)
-    times = []
+    times, out = [], None
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            fo.sequential(mods, x)
+            out = fo.sequential(mods, x)
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
-    return sample, times, torch.get_num_threads()
+    return sample, times, torch.get_num_threads(), (out if keep_output else None)
 
 
 def run_reference(args, rank):
+    """Reference arm: the reference's own CPU implementation of the path (oracle port, bit-identical to it) on the
+    SAME configuration as the GPU arm -- batch 65536 per step, the same number of steps and warm-up steps, the same
+    weights."""
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    sample, times, cores = time_cpu_reference(steps, warmup)
+    steps, warmup = args.steps, args.warmup
+    sample, times, cores, _ = time_cpu_reference(steps, warmup, BATCH, state_dicts=product_state_dicts())
     total = sum(times)
     value = sample * len(times) / total
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': len(times),
         'warmup': warmup, 'ms_per_step': 1e3 * total / len(times), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'note': f'CPU reference arm: each step is a bounded sample of {sample} samples'},
+        'config': {'workload': WORKLOAD, 'note': 'CPU reference arm: every step is one forward of the full batch of 65536 '
+                                                 'samples with the weights of the GPU arm (seed 1234)'},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': f'{sample} samples per step of the cfg2 forward, fp32, torch.no_grad, '
                                    f'{cores} threads; oracle port, bit-identical to the reference on CPU'},
@@ -182,6 +197,185 @@ def run_reference(args, rank):
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def committed_traffic(kernel_name):
+    """(bytes per launch, source) of `kernel_name` from profiles/traffic.json -- dram__bytes_read.sum +
+    dram__bytes_write.sum of a committed `ncu --set full` capture at the bench workload -- or (None, None)."""
+    path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(path):
+        entry = json.load(open(path)).get(kernel_name)
+        if entry:
+            return entry['dram_bytes_per_launch'], entry['source']
+    return None, None
+
+
+def _errors(y, ld, y_ref, ld_ref):
+    """Relative errors |a - b| / (1 + |b|) against the CPU reference: y modulo the period of the circular splines."""
+    dy = (y.double().cpu() - y_ref.double()).abs()
+    dy = torch.minimum(dy, (2 * math.pi - dy).abs()) / (1 + y_ref.double().abs())
+    dy = dy.max(dim=1).values
+    dl = (ld.double().cpu() - ld_ref.double()).abs() / (1 + ld_ref.double().abs())
+    q = lambda t, p_: float(torch.quantile(t, p_))
+    return {'y': {'median': q(dy, 0.5), 'p999': q(dy, 0.999), 'max': float(dy.max()), 'frac_le_1e-5': float((dy <= 1e-5).double().mean())},
+            'log_det_J': {'median': q(dl, 0.5), 'p999': q(dl, 0.999), 'max': float(dl.max()),
+                          'frac_le_1e-5': float((dl <= 1e-5).double().mean())}}
+
+
+def parity_legs(seq, x, y_ref, ld_ref, headline_precision, plan, pk_peaks, flush):
+    """(parity of the headline arm, the fp32-class tensor-core path timed beside it): both against the CPU reference on
+    the full batch of 65536 samples with identical weights."""
+    with torch.no_grad():
+        y, ld = seq(x)
+    parity = {'against': 'CPU reference path (oracle port, fp32) on the same 65536 samples and weights',
+              'precision': headline_precision, **_errors(y, ld, y_ref, ld_ref)}
+    for maf in seq:
+        maf.precision = 'bf16x6'
+    try:
+        with torch.no_grad():
+            for _ in range(3):
+                y6, ld6 = seq(x)
+            ev = []
+            for _ in range(5):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                y6, ld6 = seq(x)
+                b.record()
+                ev.append((a, b))
+            torch.cuda.synchronize()
+        ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
+    finally:
+        for maf in seq:
+            maf.precision = headline_precision
+    tflops = 2.0 * plan.masked_macs * len(seq) * BATCH / (ms * 1e-3) / 1e12
+    path = {'precision': 'bf16x6', 'value': BATCH / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms,
+            'kernels': 'per layer: tc_pack (split images of x), 3 x tc_gemm_kernel<3> (six tcgen05 products per k-step, fp32 '
+                       'accumulation, ELU / split images of the activations in the epilogue), spline kernel',
+            'frac': tflops / pk_peaks['bf16_tflops'],
+            'frac_note': 'algorithmic masked FLOPs (one product per MAC) over the bf16 burst peak; the tensor cores issue 6x that',
+            **_errors(y6, ld6, y_ref, ld_ref)}
+    return parity, path
+
+
+def build_cfg3(dev):
+    """BASELINE.json cfg3: 6 MAF layers, D = 300 -- three SOS-polynomial layers and three Moebius layers (3-vectors,
+    degrees repeated per atom), ascending / descending degrees alternating."""
+    from tfep_b200.nn.conditioners.made import generate_degrees
+    from tfep_b200.nn.flows import MAF, SequentialFlow
+    from tfep_b200.nn.transformers import MoebiusTransformer, SOSPolynomialTransformer
+    torch.manual_seed(4321)
+    mafs = []
+    for l in range(6):
+        order = 'ascending' if l % 2 == 0 else 'descending'
+        if l < 3:
+            mafs.append(MAF(generate_degrees(300, order=order), SOSPolynomialTransformer(2), initialize_identity=False,
+                            precision='bf16'))
+        else:
+            mafs.append(MAF(generate_degrees(300, order=order, repeats=3), MoebiusTransformer(dimension=3),
+                            initialize_identity=False, precision='bf16'))
+    return SequentialFlow(*mafs).to(dev)
+
+
+def secondary_legs(dev, rank, world):
+    """cfg3 and cfg4 of BASELINE.json on the same ranks: the two paths that DO exchange data.  Device
+    timed, max over ranks; every rank must call this."""
+    import torch.distributed as dist
+    from tfep_b200.analysis import distributed as D
+    from tfep_b200.loss import BoltzmannKLDivLoss
+    from tfep_b200.utils.data_parallel import allreduce_gradients, broadcast_parameters
+
+    def sync():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    out = {}
+    # ---- cfg3: training step, batch 262144 per GPU, gradient all-reduce over the ranks ----
+    B3 = 262144
+    seq3 = build_cfg3(dev)
+    broadcast_parameters(seq3)
+    g = torch.Generator().manual_seed(100 + rank)
+    x3 = torch.randn(B3, 300, generator=g).to(dev)
+    opt = torch.optim.AdamW(seq3.parameters(), lr=1e-4)
+    loss_fn = BoltzmannKLDivLoss()
+    n_grad = sum(p.numel() for p in seq3.parameters())
+
+    def step3():
+        opt.zero_grad(set_to_none=True)
+        y, ld = seq3(x3)
+        u = 0.5 * ((y - 0.5) ** 2).sum(dim=1)                 # harmonic target potential (k = 1, mu = 0.5)
+        loss = loss_fn(u, ld)
+        loss.backward()
+        allreduce_gradients(seq3)                             # ONE flat NCCL all-reduce (no-op at N = 1)
+        opt.step()
+        return loss
+
+    for _ in range(2):
+        step3()
+    sync()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(3):
+        loss = step3()
+    b.record()
+    sync()
+    ms3 = max_over_ranks(a.elapsed_time(b) / 3)
+    out['cfg3'] = {'workload': 'cfg3: 6xMAF (3 SOS + 3 Moebius) D=300, batch 262144 per GPU, training step = forward + '
+                               'BoltzmannKLDivLoss + backward + gradient all-reduce + AdamW',
+                   'precision': 'bf16 (tcgen05 GEMMs forward and backward, fp32 accumulation)', 'ms_per_step': ms3,
+                   'samples_per_s': B3 * world / (ms3 * 1e-3), 'gradient_allreduce_elements': n_grad if world > 1 else 0,
+                   'loss': float(loss.detach())}
+    del seq3, opt, x3, loss
+    torch.cuda.empty_cache()
+
+    # ---- cfg4: estimator + 1000-resample bootstrap over 1e8 work values, contiguous shards ----
+    n = 100_000_000
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    gen = torch.Generator(device=dev).manual_seed(0)          # the same global array on every rank, then the shard
+    w = torch.randn(n, device=dev, generator=gen)[lo:hi].clone()
+    for _ in range(3):
+        df = D.fep_estimator_sharded(w)
+    sync()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10):
+        df = D.fep_estimator_sharded(w)                       # lse kernel + all-gather of (max, sum exp) pairs
+    b.record()
+    sync()
+    ms_e = max_over_ranks(a.elapsed_time(b) / 10)
+    sync()
+    t0 = time.perf_counter()
+    stats = D.bootstrap_statistics_sharded(w, lo, n, n_resamples=1000, generator=torch.Generator().manual_seed(1), rng='philox')
+    sync()
+    s_b = max_over_ranks(time.perf_counter() - t0)
+    # the reference's own index stream (MT19937, bit-exact indices), reduced to n = 1e6 as SURVEY.md 8d prescribes
+    n_small = 1_000_000
+    lo_s, hi_s = rank * n_small // world, (rank + 1) * n_small // world
+    ws = torch.randn(n_small, device=dev, generator=torch.Generator(device=dev).manual_seed(3))[lo_s:hi_s].clone()
+    sync()
+    t0 = time.perf_counter()
+    stats_mt = D.bootstrap_statistics_sharded(ws, lo_s, n_small, n_resamples=100, generator=torch.Generator().manual_seed(1))
+    sync()
+    s_mt = max_over_ranks(time.perf_counter() - t0)
+    q = torch.quantile(stats.double(), torch.tensor([0.025, 0.975], dtype=torch.float64, device=dev))
+    out['cfg4'] = {'workload': 'cfg4: fep_estimator + 1000-resample bootstrap over 1e8 work values ~ N(0,1), contiguous shards',
+                   'estimator_ms': ms_e, 'estimator_samples_per_s': n / (ms_e * 1e-3),
+                   'estimator_hbm_frac': 4.0 * (hi - lo) / (ms_e * 1e-3) / 1e9 / peaks()['hbm_gbs'],
+                   'delta_f': float(df), 'delta_f_analytic': -0.5,
+                   'bootstrap_s': s_b, 'bootstrap_draws_per_s': 1000.0 * n / s_b, 'rng': 'philox (stratified over L2-sized cells)',
+                   'ci95': [float(q[0]), float(q[1])],
+                   'collectives': 'all-gather of one (max, sum exp) pair per rank; MAX + SUM all-reduce of 1000 doubles',
+                   'mt19937_exact_stream': {'n': n_small, 'n_resamples': 100, 'seconds': s_mt,
+                                            'draws_per_s': 100.0 * n_small / s_mt, 'mean': float(stats_mt.double().mean())}}
+    return out
 
 
 def run_ours(args, rank, world, local_rank):
@@ -293,6 +487,8 @@ def run_ours(args, rank, world, local_rank):
                    'round_trip_median_abs_err': float(d.median()), 'round_trip_frac_below_1e-3': float((d < 1e-3).float().mean())}
 
     if rank != 0:
+        if not args.skip_secondary:
+            secondary_legs(dev, rank, world)       # collective legs: every rank takes part
         return
 
     pk_peaks = peaks()
@@ -341,21 +537,29 @@ def run_ours(args, rank, world, local_rank):
         kernel = 'gemm_kernel<float,true,true> (output layer 328->1650, fp32 FFMA, staircase-skipped)'
         launches_per_step = 16
     achieved = flops_per_launch / (k_ms * 1e-3) / 1e12
+    traffic, traffic_source = committed_traffic(kernel.split(' ')[0])
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': pk_peaks['bf16_tflops'], 'unit': 'TFLOP/s',
                 'frac': achieved / pk_peaks['bf16_tflops'],
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture of the
-                # bf16 chain launch at this workload (profiles/r01_ncu_fused_fwd_v8_chain_details.md): 21.08 MB read
-                # (x 17.3 MB + packed weights) + 0.15 MB written -- the 17.6 MB of y / logdet were still in L2 when
-                # the kernel ended; the algorithmic HBM bytes are 34.9 MB per launch
-                'traffic': 21.23e6 if (args.precision == 'bf16' and BATCH == 65536) else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this workload from the committed
+                # `ncu --set full` capture named in traffic_source (null if none is committed for this kernel); the
+                # algorithmic HBM bytes of the chain launch are 34.9 MB (x, y, log-det), y stays in L2 at kernel end
+                'traffic': traffic, 'traffic_source': traffic_source,
                 'kernel': kernel,
                 'kernel_ms': k_ms, 'peak_source': pk_peaks['source'] + ', bf16 burst',
                 'whole_step_frac': (2.0 * plan.masked_macs * 4 * BATCH * args.steps / (total_ms * 1e-3) / 1e12)
                 / pk_peaks['bf16_tflops_sustained']}
 
-    sample, times, cores = time_cpu_reference(2, 1, state_dicts=[{k: v.detach().cpu() for k, v in m.state_dict().items()}
-                                                                  for m in seq])
+    # CPU baseline = the reference's path on the host cores with the SAME weights, on the full batch; its outputs are
+    # the parity reference of the GPU arms below
+    sds = [{k: v.detach().cpu() for k, v in m.state_dict().items()} for m in seq]
+    sample, times, cores, (y_ref, ld_ref) = time_cpu_reference(2, 1, BATCH, state_dicts=sds, keep_output=True)
     cpu_value = sample * len(times) / sum(times)
+    x0_host = cfg2_input(BATCH)                     # the cpu sample = rank 0's shard at N = 1, the first shard otherwise
+    parity, parity_path = parity_legs(seq, x0_host.to(dev), y_ref, ld_ref, args.precision, plan, pk_peaks, flush)
+
+    secondary = {}
+    if not args.skip_secondary:
+        secondary = secondary_legs(dev, rank, world)
 
     value = BATCH * world * args.steps / (total_ms * 1e-3)
     line = {
@@ -373,8 +577,12 @@ def run_ours(args, rank, world, local_rank):
         'inverse': inv,
         'roofline': roofline,
         'cpu_baseline': {'value': cpu_value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': f'{sample} samples x {len(times)} passes of the same cfg2 forward, fp32, no_grad'},
+                         'sample': f'{sample} samples x {len(times)} passes of the same cfg2 forward with the same weights, '
+                                   'fp32, no_grad'},
+        'parity': parity,
+        'parity_path': parity_path,
     }
+    line.update(secondary)
     print(json.dumps(line), flush=True)
 
 
@@ -384,7 +592,8 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--precision', default='bf16', choices=['fp32', 'bf16'])
+    ap.add_argument('--precision', default='bf16', choices=['fp32', 'bf16', 'bf16x3', 'bf16x6'])
+    ap.add_argument('--skip-secondary', action='store_true', help='only the cfg2 headline (no cfg3 / cfg4 legs)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))

@@ -50,3 +50,15 @@ def test_measured_arm_line():
     assert d['gpu_launches'] == d['steps']                      # one chain launch per step
     assert set(d['clocks']) >= {'sm_mhz', 'sm_max_mhz', 'reasons'}
     assert d['value'] > 1000 * c['value']                      # the kernels, not a CPU fallback, produced the number
+    # parity of the headline arm and the fp32-class tensor-core path, both against the CPU reference on the full batch
+    assert d['parity']['precision'] == 'bf16' and d['parity']['y']['median'] < 5e-3
+    pp = d['parity_path']
+    assert pp['precision'] == 'bf16x6' and pp['value'] > 100 * c['value']
+    # (the maximum belongs to the odd sample whose intermediate value crosses the +-pi seam of the circular splines in
+    # one arithmetic and not in the other; the reference's own fp32 log-det is within 1e-5 of fp64 for 99.95 %)
+    assert pp['y']['p999'] < 1e-5 and pp['y']['frac_le_1e-5'] > 0.9999
+    assert pp['log_det_J']['p999'] < 2e-5 and pp['log_det_J']['frac_le_1e-5'] > 0.99
+    # the legs that exchange data between ranks (collectives are no-ops at N = 1)
+    assert d['cfg3']['ms_per_step'] > 0 and d['cfg3']['loss'] == d['cfg3']['loss']
+    assert abs(d['cfg4']['delta_f'] + 0.5) < 5e-3 and d['cfg4']['bootstrap_draws_per_s'] > 1e10
+    assert d['cfg4']['ci95'][0] < -0.5 < d['cfg4']['ci95'][1]

@@ -160,12 +160,23 @@ class MADE(_conditioner.Conditioner):
         (``p.data.copy_(ema)``, ``p.data.clamp_()``) bypass those counters and MUST be followed by this call."""
         self._packed_epoch += 1
         self._packed_cache.clear()
+        self.__dict__.pop('_key_tensors', None)
 
     def _param_versions(self):
         """Cache key of everything derived from the weights: parameters AND mask buffers (pointer, version) plus the
         explicit invalidation epoch."""
-        tensors = list(self.parameters()) + [lin.mask for lin in self._linear_layers()]
-        return (self._packed_epoch,) + tuple((t.data_ptr(), t._version) for t in tensors)
+        tensors = self.__dict__.get('_key_tensors')
+        if tensors is None:         # walked once: the module tree does not change after construction
+            tensors = list(self.parameters()) + [lin.mask for lin in self._linear_layers()]
+            self.__dict__['_key_tensors'] = tensors
+        return (self._packed_epoch, *[(t.data_ptr(), t._version) for t in tensors])
+
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .double() may REPLACE parameter and buffer tensors: forget the cached list of key tensors
+        self.__dict__.pop('_key_tensors', None)
+        out = super()._apply(fn, *args, **kwargs)
+        self.__dict__.pop('_key_tensors', None)
+        return out
 
     def packed_weights(self, plan=None):
         """Packed (degree-sorted) effective weights for ``plan``; cached while gradients are off."""
