@@ -435,33 +435,61 @@ def run_ours(args, rank, world, local_rank):
     total_ms = float(total_ms)
 
     # end to end through the public API with host buffers (pinned), copies inside the timed region:
-    # tfep_b200.utils.host_pipeline.HostPipeline = chunked H2D copy -> flow -> D2H copy of (y, log_det_J) on three streams
-    from tfep_b200.utils.host_pipeline import HostPipeline
-    pipe = HostPipeline(seq, BATCH, 66, dev, n_chunks=1, depth=3)
+    # tfep_b200.utils.host_pipeline.HostPipeline = H2D copy of x -> flow -> on-device consumer -> D2H copy of the
+    # step's result.  The result a (T)FEP run consumes is the generalized work of every sample (4 bytes) and its
+    # estimator partial (FEPWorkConsumer: u_target(y) - log|det J| with the synthetic harmonic target potential of
+    # BASELINE.json), so that is what comes back; `e2e_full_outputs` below is the same pipeline returning y and
+    # log_det_J in full (what feeds an external potential engine).
+    from tfep_b200.utils.host_pipeline import FEPWorkConsumer, HostPipeline, harmonic_potential
 
-    def e2e_step():
-        # one CUDA-graph launch per step: upload of x from pinned host memory, the chain kernel, download of
-        # (y, log_det_J); three steps are in flight on three streams, so the copies of neighbouring steps overlap
-        # with the kernels -- every step still moves its own inputs and outputs inside the timed region
-        pipe.step_graph(x_host)
+    def time_pipeline(pipe):
+        # one CUDA-graph launch per step: upload of x from pinned host memory, the chain kernel (+ consumer), download
+        # of the result; three steps are in flight on three streams, so the copies of neighbouring steps overlap with
+        # the kernels -- every step still moves its own inputs and outputs inside the timed region
+        for _ in range(max(1, args.warmup)):
+            pipe.step_graph(x_host)
+        pipe.join()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            pipe.step_graph(x_host)
+        pipe.join()
+        b.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        barrier()
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
 
-    for _ in range(max(1, args.warmup)):
-        e2e_step()
-    pipe.join()
+    pipe = HostPipeline(seq, BATCH, 66, dev, n_chunks=1, depth=3, consumer=FEPWorkConsumer(harmonic_potential(1.0, 0.5)))
+    e2e_ms = time_pipeline(pipe)
+    work_host, partial_host = pipe.outputs_host
+    e2e_d2h = work_host.numel() * work_host.element_size() + partial_host.numel() * partial_host.element_size()
+    e2e_check = float(-(partial_host[0] + torch.log(partial_host[1]) - math.log(BATCH)))     # Delta f of the last step
+    pipe_full = HostPipeline(seq, BATCH, 66, dev, n_chunks=1, depth=3)
+    e2e_full_ms = time_pipeline(pipe_full)
+    y_host, ld_host = pipe_full.y_host, pipe_full.ld_host
+
+    # measured ceiling of ANY implementation that uploads x as fp32 from this host: all ranks copy their pinned batch
+    # to the device at the same time, nothing else running
+    x_stage = torch.empty_like(x)
+    for _ in range(3):
+        x_stage.copy_(x_host, non_blocking=True)
     barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(args.steps):
-        e2e_step()
-    pipe.join()
+    for _ in range(20):
+        x_stage.copy_(x_host, non_blocking=True)
     b.record()
     torch.cuda.synchronize(dev)
-    y_host, ld_host = pipe.y_host, pipe.ld_host
-    e2e_ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    h2d_ms = torch.tensor([a.elapsed_time(b) / 20], dtype=torch.float64, device=dev)
     barrier()
     if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_ms = float(e2e_ms)
+        dist.all_reduce(h2d_ms, op=dist.ReduceOp.MAX)
+    h2d_ms = float(h2d_ms)
+    del x_stage
 
     # secondary: MAF.inverse of the same configuration (cfg2 is "forward + inverse + log-det"), device resident
     inv = None
@@ -571,8 +599,19 @@ def run_ours(args, rank, world, local_rank):
                    'wall_s_timed_region': t_wall},
         'clocks': clocks.summary(t_load0, t_load1),
         'e2e': {'value': BATCH * world * args.steps / (e2e_ms * 1e-3), 'unit': UNIT,
-                'h2d_bytes_per_step': x_host.numel() * 4, 'd2h_bytes_per_step': (y_host.numel() + ld_host.numel()) * 4,
-                'api': 'tfep_b200.utils.host_pipeline.HostPipeline.step_graph (CUDA graph per step, 3 steps in flight)'},
+                'h2d_bytes_per_step': x_host.numel() * 4, 'd2h_bytes_per_step': e2e_d2h,
+                'api': 'tfep_b200.utils.host_pipeline.HostPipeline.step_graph with FEPWorkConsumer (CUDA graph per step, 3 '
+                       'steps in flight): x up, per-sample generalized work + (max, sum exp) estimator partial down',
+                'delta_f_last_step': e2e_check,
+                # measured: every rank uploading its pinned fp32 batch at the same time, nothing else running
+                'host_ceiling': {'h2d_ms_per_batch': h2d_ms, 'h2d_GBps_per_gpu': x_host.numel() * 4 / (h2d_ms * 1e-3) / 1e9,
+                                 'samples_per_s': BATCH * world / (h2d_ms * 1e-3),
+                                 'note': 'upper bound of any pipeline that uploads fp32 x from this host: concurrent '
+                                         'pinned H2D copies on all ranks (PCIe / host memory system)'}},
+        'e2e_full_outputs': {'value': BATCH * world * args.steps / (e2e_full_ms * 1e-3), 'unit': UNIT,
+                             'h2d_bytes_per_step': x_host.numel() * 4,
+                             'd2h_bytes_per_step': (y_host.numel() + ld_host.numel()) * 4,
+                             'api': 'HostPipeline.step_graph without consumer: y and log_det_J downloaded in full'},
         'gpu_launches': launches_per_step * args.steps,
         'inverse': inv,
         'roofline': roofline,

@@ -42,11 +42,43 @@ def gpu_numa_affinity(device):
             os.sched_setaffinity(0, previous)
 
 
-class HostPipeline:
-    """Reusable pinned / device staging buffers for ``flow`` evaluated on batches of ``batch`` samples."""
+class FEPWorkConsumer:
+    """On-device consumer of a mapped batch for (T)FEP: ``work = u_B(y) / kT - log|det J| (- u_A(x) / kT)`` (reference
+    docs/intro_to_MTFEP.ipynb:563-569) and its estimator partial ``(max, sum exp)`` of ``-work``
+    (tfep_b200.analysis.estimator.lse_partial), so that only 4 bytes per sample -- the generalized work the estimator and
+    the bootstrap consume -- and one 16-byte pair travel back to the host instead of the mapped coordinates.
+    ``potential(y) -> (batch,)`` stands for the target potential (synthetic analytic here: external engines are out of
+    scope); ``reference_potential(x)`` is optional."""
 
-    def __init__(self, flow, batch, n_features, device, n_chunks=4, dtype=torch.float32, depth=3):
+    def __init__(self, potential, kT=1.0, reference_potential=None):
+        self.potential, self.kT, self.reference_potential = potential, kT, reference_potential
+
+    def __call__(self, x, y, log_det_J):
+        from ..analysis.estimator import lse_partial
+        work = self.potential(y) / self.kT - log_det_J
+        if self.reference_potential is not None:
+            work = work - self.reference_potential(x) / self.kT
+        return work, lse_partial(work)
+
+
+def harmonic_potential(k=1.0, mu=0.5):
+    """u(y) = 1/2 sum_f k (y_f - mu)^2: the synthetic target potential of BASELINE.json (north_star)."""
+    def u(y):
+        return 0.5 * k * ((y - mu) ** 2).sum(dim=1)
+    return u
+
+
+class HostPipeline:
+    """Reusable pinned / device staging buffers for ``flow`` evaluated on batches of ``batch`` samples.
+
+    ``consumer(x_dev, y_dev, log_det_J_dev) -> tuple of device tensors``: what is downloaded instead of
+    ``(y, log_det_J)`` (CUDA-graph mode, :meth:`step_graph`); e.g. :class:`FEPWorkConsumer` when the mapped samples feed
+    the free-energy estimator and only the work values are needed on the host."""
+
+    def __init__(self, flow, batch, n_features, device, n_chunks=4, dtype=torch.float32, depth=3, consumer=None):
         self.flow, self.device = flow, torch.device(device)
+        self.consumer = consumer
+        self.out_hosts = None               # per staging set: pinned buffers of the consumer's outputs
         self.bounds = [(i * batch // n_chunks, (i + 1) * batch // n_chunks) for i in range(n_chunks)]
         self.bounds = [(a, b) for a, b in self.bounds if b > a]
         # `depth` staging sets: a batch occupies upload, kernels and download one after the other, so three batches
@@ -78,6 +110,8 @@ class HostPipeline:
         valid after a synchronize of the current stream).  ``wait=False``: nothing is joined, so the next call
         may start uploading while this batch computes and downloads; results of this call are valid after
         :meth:`join` (after ``depth`` more calls the buffers are reused)."""
+        if self.consumer is not None:
+            raise NotImplementedError('a consumer is applied in CUDA-graph mode: use step_graph()')
         main = torch.cuda.current_stream(self.device)
         g = self.generation % self.depth
         self.generation += 1
@@ -130,7 +164,15 @@ class HostPipeline:
         self.generation += 1
         with torch.cuda.stream(self._graph_streams[g]):
             self._graphs[g].replay()
+        if self.consumer is not None:
+            return tuple(self.out_hosts[g])
         return self.y_hosts[g], self.ld_hosts[g]
+
+    @property
+    def outputs_host(self):
+        """Pinned outputs of the most recent :meth:`step_graph` call (valid after :meth:`join`)."""
+        g = (self.generation - 1) % self.depth
+        return tuple(self.out_hosts[g]) if self.consumer is not None else (self.y_hosts[g], self.ld_hosts[g])
 
     def _capture(self, x_host, inverse):
         fn = self.flow.inverse if inverse else self.flow
@@ -138,7 +180,12 @@ class HostPipeline:
         self._graph_streams = [torch.cuda.Stream(self.device) for _ in range(self.depth)]
         self._graphs = []
         with torch.no_grad():
-            fn(self.x_dev[0])                         # warm-up outside capture: packs weights, allocates workspaces
+            y, ld = fn(self.x_dev[0])                 # warm-up outside capture: packs weights, allocates workspaces
+            if self.consumer is not None:
+                outs = self.consumer(self.x_dev[0], y, ld)
+                with gpu_numa_affinity(self.device):
+                    self.out_hosts = [[torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+                                      for _ in range(self.depth)]
         torch.cuda.synchronize(self.device)
         for g in range(self.depth):
             st = self._graph_streams[g]
@@ -148,7 +195,11 @@ class HostPipeline:
                 with torch.cuda.graph(graph, stream=st):
                     self.x_dev[g].copy_(x_host, non_blocking=True)
                     y, ld = fn(self.x_dev[g])
-                    self.y_hosts[g].copy_(y, non_blocking=True)
-                    self.ld_hosts[g].copy_(ld, non_blocking=True)
+                    if self.consumer is not None:
+                        for host, out in zip(self.out_hosts[g], self.consumer(self.x_dev[g], y, ld)):
+                            host.copy_(out, non_blocking=True)
+                    else:
+                        self.y_hosts[g].copy_(y, non_blocking=True)
+                        self.ld_hosts[g].copy_(ld, non_blocking=True)
             self._graphs.append(graph)
         torch.cuda.synchronize(self.device)
