@@ -446,16 +446,19 @@ def run_ours(args, rank, world, local_rank):
         # one CUDA-graph launch per step: upload of x from pinned host memory, the chain kernel (+ consumer), download
         # of the result; three steps are in flight on three streams, so the copies of neighbouring steps overlap with
         # the kernels -- every step still moves its own inputs and outputs inside the timed region
-        for _ in range(max(1, args.warmup)):
-            pipe.step_graph(x_host)
+        # Timed: from the completion of the last warm-up step to the completion of the K-th step after it (events on
+        # the streams those steps run on), i.e. K steps of the running pipeline, not its fill and drain.
+        pipe.step_graph(x_host)
         pipe.join()
         barrier()
+        for _ in range(max(3, args.warmup)):
+            pipe.step_graph(x_host)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
+        a.record(pipe.last_stream)
         for _ in range(args.steps):
             pipe.step_graph(x_host)
+        b.record(pipe.last_stream)
         pipe.join()
-        b.record()
         torch.cuda.synchronize(dev)
         t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
         barrier()

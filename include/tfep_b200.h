@@ -463,6 +463,16 @@ int tfepb_mt19937_seed(uint32_t seed, uint32_t* state625_host);
 int tfepb_mt19937_indices(uint32_t* state625_dev, int64_t count, uint32_t max_idx, int32_t* idx,
                           tfepb_stream_t stream);
 
+/* The same stream generated by all SMs (MT19937 jump-ahead, tfep_b200/csrc/mt19937_jump.cu): the request is cut into
+ * at most n_streams sub-streams whose start states are obtained from `state` by polynomial jumps (t^J mod the
+ * characteristic polynomial, evaluated at the state transition on the device), one CTA per sub-stream; idx and the
+ * updated `state` are bit-identical to tfepb_mt19937_indices.  `workspace`: tfepb_mt19937_parallel_workspace_bytes(
+ * n_streams) bytes on the device.  tfepb_mt19937_jump_polynomial (host only) returns t^steps mod phi as 19968 bits. */
+int64_t tfepb_mt19937_parallel_workspace_bytes(int32_t n_streams);
+int tfepb_mt19937_indices_parallel(uint32_t* state625_dev, int64_t count, uint32_t max_idx, int32_t* idx,
+                                   int32_t n_streams, void* workspace, tfepb_stream_t stream);
+int tfepb_mt19937_jump_polynomial(uint64_t steps, uint32_t* poly624_host);
+
 /* Fused resample + exponential average: for resample r (row r of idx, or a counter-based Philox
  * stream when idx == NULL) out_sums[r] = sum_j e[idx[r, j]] in double, where e_i = exp(v_i - max)
  * was produced by tfepb_exp_table.  analysis/bootstrap.py:185-233 with statistic = fep_estimator.

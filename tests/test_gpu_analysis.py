@@ -263,3 +263,43 @@ def test_more_than_65535_resamples_per_call():
     w = cases.normal((50,), 8).to(DEV)
     r = bootstrap(w, fep_estimator, n_resamples=70000, generator=torch.Generator().manual_seed(1))
     assert bool(torch.isfinite(r['mean'])) and float(r['standard_deviation']) > 0
+
+
+@pytest.mark.parametrize('count,n_streams', [(1, 2), (624 * 3 + 5, 3), (100003, 7), (1 << 20, 148), (3000017, 592), (50000, 4096)])
+def test_parallel_mt19937_stream_is_bit_identical(count, n_streams):
+    """Jump-ahead sub-streams on all SMs (tfepb_mt19937_indices_parallel) against the single-CTA walk and the numpy
+    restatement of torch.randint's CPU stream: same indices, same generator state afterwards, from any position."""
+    from tfep_b200 import _ops
+    n = 1000003
+    for seed, pre in ((42, 0), (7, 1000)):
+        a, b = _ops.mt19937_seed(seed).to(DEV), _ops.mt19937_seed(seed).to(DEV)
+        if pre:
+            _ops.mt19937_indices(a, pre, n, n_streams=1)
+            _ops.mt19937_indices(b, pre, n, n_streams=1)
+        seq = _ops.mt19937_indices(a, count, n, n_streams=1)
+        par = _ops.mt19937_indices(b, count, n, n_streams=n_streams)
+        assert torch.equal(seq, par)
+        assert np.array_equal(par.cpu().numpy(), ao.resample_indices(seed, 1, count, n, skip=pre)[0])
+        # both generators continue identically (the state itself may be a different window of the same sequence)
+        assert torch.equal(_ops.mt19937_indices(a, 2000, n, n_streams=1), _ops.mt19937_indices(b, 2000, n, n_streams=1))
+
+
+def test_parallel_mt19937_is_the_default_for_large_requests_and_fast():
+    from tfep_b200 import _ops
+    count = 1 << 28
+    st = _ops.mt19937_seed(123).to(DEV)
+    idx = torch.empty(count, dtype=torch.int32, device=DEV)
+    _ops.mt19937_indices(st, count, 100000000, out=idx)             # warm-up: polynomials cached per sub-stream length
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    _ops.mt19937_indices(st, count, 100000000, out=idx)
+    b.record()
+    torch.cuda.synchronize()
+    rate = count / (a.elapsed_time(b) * 1e-3)
+    print(f'parallel MT19937: {rate / 1e9:.1f} G draws/s')
+    assert rate > 3e10
+    # the default path of a request of 2^24 draws is the parallel one: compare it with the forced single-CTA walk
+    s1, s2 = _ops.mt19937_seed(5).to(DEV), _ops.mt19937_seed(5).to(DEV)
+    assert torch.equal(_ops.mt19937_indices(s1, 1 << 24, 77777777), _ops.mt19937_indices(s2, 1 << 24, 77777777, n_streams=1))
+    assert torch.equal(_ops.mt19937_indices(s1, 5000, 3), _ops.mt19937_indices(s2, 5000, 3))

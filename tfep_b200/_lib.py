@@ -168,6 +168,9 @@ SYMBOLS = {
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'tfepb_mt19937_seed': (c_int32, [c_uint32, c_void_p]),
     'tfepb_mt19937_indices': (c_int32, [c_void_p, c_int64, c_uint32, c_void_p, c_void_p]),
+    'tfepb_mt19937_parallel_workspace_bytes': (c_int64, [c_int32]),
+    'tfepb_mt19937_indices_parallel': (c_int32, [c_void_p, c_int64, c_uint32, c_void_p, c_int32, c_void_p, c_void_p]),
+    'tfepb_mt19937_jump_polynomial': (c_int32, [c_uint64, c_void_p]),
     'tfepb_exp_table': (c_int32, [c_int32, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p]),
     'tfepb_bayesian_bootstrap_sums': (c_int32, [c_void_p, c_int64, c_int32, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p]),
     'tfepb_bootstrap_sums': (c_int32, [c_void_p, c_int64, c_int64, c_uint32, c_void_p, c_int64, c_int32, c_int64, c_uint64,

@@ -326,14 +326,43 @@ def mt19937_seed(seed):
     return st
 
 
-def mt19937_indices(state_dev, count, max_idx, out=None):
+#: requests of at least this many draws are generated by all SMs (jump-ahead); below it one CTA walks the stream
+MT_PARALLEL_MIN = 1 << 22
+MT_DRAWS_PER_STREAM_MIN = 64 * 624
+_MT_WORKSPACES = {}
+
+
+def mt19937_jump_polynomial(steps):
+    """t^steps mod the characteristic polynomial of MT19937: 624 uint32 words (host computation, no GPU needed)."""
+    import numpy as np
+    out = np.zeros(624, dtype=np.uint32)
+    check(_lib.load().tfepb_mt19937_jump_polynomial(ctypes.c_uint64(int(steps)), out.ctypes.data_as(ctypes.c_void_p)))
+    return out
+
+
+def mt19937_indices(state_dev, count, max_idx, out=None, n_streams=None):
     """Next ``count`` draws ``u32 % max_idx`` of the MT19937 stream held in ``state_dev`` (625 int32 on the
-    device, updated in place)."""
+    device, updated in place).  Large requests are split into sub-streams by jump-ahead and generated by all SMs
+    (tfepb_mt19937_indices_parallel), bit-identical to the sequential walk; ``n_streams`` forces the split."""
     require_cuda(state_dev)
     idx = out if out is not None else torch.empty(count, dtype=torch.int32, device=state_dev.device)
+    lib = _lib.load()
+    if n_streams is None:
+        n_streams = 1
+        if count >= MT_PARALLEL_MIN:
+            sms = torch.cuda.get_device_properties(state_dev.device).multi_processor_count
+            n_streams = max(1, min(4 * sms, int(count) // MT_DRAWS_PER_STREAM_MIN))
     with torch.cuda.device(state_dev.device):
-        check(_lib.load().tfepb_mt19937_indices(ptr(state_dev), int(count), int(max_idx), ptr(idx),
-                                                stream_ptr(state_dev)))
+        if n_streams <= 1:
+            check(lib.tfepb_mt19937_indices(ptr(state_dev), int(count), int(max_idx), ptr(idx), stream_ptr(state_dev)))
+        else:
+            key = (str(state_dev.device), torch.cuda.current_stream(state_dev.device).cuda_stream)
+            ws = _MT_WORKSPACES.get(key)
+            need = lib.tfepb_mt19937_parallel_workspace_bytes(int(n_streams))
+            if ws is None or ws.numel() < need:
+                ws = _MT_WORKSPACES[key] = torch.empty(need, dtype=torch.uint8, device=state_dev.device)
+            check(lib.tfepb_mt19937_indices_parallel(ptr(state_dev), int(count), int(max_idx), ptr(idx), int(n_streams),
+                                                     ptr(ws), stream_ptr(state_dev)))
     return idx
 
 

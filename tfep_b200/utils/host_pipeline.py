@@ -169,6 +169,12 @@ class HostPipeline:
         return self.y_hosts[g], self.ld_hosts[g]
 
     @property
+    def last_stream(self):
+        """The stream the most recent :meth:`step_graph` call was replayed on (an event recorded there fires when that
+        step's download has finished)."""
+        return self._graph_streams[(self.generation - 1) % self.depth]
+
+    @property
     def outputs_host(self):
         """Pinned outputs of the most recent :meth:`step_graph` call (valid after :meth:`join`)."""
         g = (self.generation - 1) % self.depth
