@@ -356,13 +356,11 @@ def secondary_legs(dev, rank, world):
     stats = D.bootstrap_statistics_sharded(w, lo, n, n_resamples=1000, generator=torch.Generator().manual_seed(1), rng='philox')
     sync()
     s_b = max_over_ranks(time.perf_counter() - t0)
-    # the reference's own index stream (MT19937, bit-exact indices), reduced to n = 1e6 as SURVEY.md 8d prescribes
-    n_small = 1_000_000
-    lo_s, hi_s = rank * n_small // world, (rank + 1) * n_small // world
-    ws = torch.randn(n_small, device=dev, generator=torch.Generator(device=dev).manual_seed(3))[lo_s:hi_s].clone()
+    # the reference's own index stream (MT19937, bit-exact indices; jump-ahead sub-streams on all SMs): 20 resamples of
+    # the full 1e8 samples -- every rank walks the whole stream and sums the draws that fall into its shard
     sync()
     t0 = time.perf_counter()
-    stats_mt = D.bootstrap_statistics_sharded(ws, lo_s, n_small, n_resamples=100, generator=torch.Generator().manual_seed(1))
+    stats_mt = D.bootstrap_statistics_sharded(w, lo, n, n_resamples=20, generator=torch.Generator().manual_seed(1))
     sync()
     s_mt = max_over_ranks(time.perf_counter() - t0)
     q = torch.quantile(stats.double(), torch.tensor([0.025, 0.975], dtype=torch.float64, device=dev))
@@ -373,8 +371,8 @@ def secondary_legs(dev, rank, world):
                    'bootstrap_s': s_b, 'bootstrap_draws_per_s': 1000.0 * n / s_b, 'rng': 'philox (stratified over L2-sized cells)',
                    'ci95': [float(q[0]), float(q[1])],
                    'collectives': 'all-gather of one (max, sum exp) pair per rank; MAX + SUM all-reduce of 1000 doubles',
-                   'mt19937_exact_stream': {'n': n_small, 'n_resamples': 100, 'seconds': s_mt,
-                                            'draws_per_s': 100.0 * n_small / s_mt, 'mean': float(stats_mt.double().mean())}}
+                   'mt19937_exact_stream': {'n': n, 'n_resamples': 20, 'seconds': s_mt,
+                                            'draws_per_s': 20.0 * n / s_mt, 'mean': float(stats_mt.double().mean())}}
     return out
 
 

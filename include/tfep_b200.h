@@ -442,6 +442,15 @@ typedef struct {
     int32_t max_group_weight_elems;              /* max over groups of the elements of all weight rows the group uses
                                                     (rows x leading dimension, output + hidden layers); 0 = unknown:
                                                     the kernel then reads weights through L1 instead of staging them */
+    /* Blocked sweeps of wide conditioners (tfep_b200/_blocked.py: the degrees are cut into blocks, the kernel runs the
+     * sequential part INSIDE a block on the block's own small weight matrices, plain GEMMs supply what earlier blocks
+     * contribute): */
+    const void* extra[TFEPB_SWEEP_MAX_LINEAR];   /* per linear layer l: NULL, or (batch, n_out[l]) added to the
+                                                    pre-activations of the layer (before ELU / the transformer) */
+    int64_t ldextra[TFEPB_SWEEP_MAX_LINEAR];
+    void* act_out[TFEPB_SWEEP_MAX_LINEAR];       /* per hidden layer l >= 1: NULL, or (batch, n_out[l - 1]) receiving the
+                                                    activations of the layer */
+    int64_t ldact_out[TFEPB_SWEEP_MAX_LINEAR];
 } tfepb_sweep_args;
 int tfepb_maf_inverse_sweep(const tfepb_sweep_args* a, tfepb_stream_t stream);
 

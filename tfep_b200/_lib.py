@@ -123,7 +123,8 @@ class SweepArgs(Structure):
                 ('groups', c_void_p), ('n_groups', c_int32), ('max_params', c_int32),
                 ('parts', c_void_p), ('group_parts', c_void_p), ('ids', c_void_p), ('fixed_cols', c_void_p),
                 ('n_fixed', c_int32), ('n_embedded', c_int32), ('emb_out_col', c_void_p), ('emb_periodic', c_void_p),
-                ('emb_lower', c_double), ('emb_scale', c_double), ('reserved', c_int32), ('max_group_weight_elems', c_int32)]
+                ('emb_lower', c_double), ('emb_scale', c_double), ('reserved', c_int32), ('max_group_weight_elems', c_int32),
+                ('extra', c_void_p * 5), ('ldextra', c_int64 * 5), ('act_out', c_void_p * 5), ('ldact_out', c_int64 * 5)]
 
 
 # every symbol include/tfep_b200.h declares: name -> (restype, argtypes)

@@ -259,7 +259,7 @@ def _bootstrap_statistics(data, statistic, n_resamples, sample_size, take_first_
     max_idx = sample_size if take_first_only else n_samples
     kT = _fused_kT(statistic)
     if kT is not None and data.dim() == 1:
-        batch = max(1, min(batch, n_resamples, (1 << 28) // max(sample_size, 1) or 1))
+        batch = max(1, min(batch, n_resamples, (1 << 29) // max(sample_size, 1) or 1))
         sums, refs = bootstrap_partial_sums(data, kT, n_resamples, sample_size, max_idx, batch, generator, rng)
         return (-kT * (refs + torch.log(sums) - _log_n(sample_size))).to(data.dtype)
 

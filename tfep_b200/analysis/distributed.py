@@ -116,7 +116,7 @@ def bootstrap_statistics_sharded(work_shard, shard_offset, n_total, kT=1.0, n_re
         refs = torch.empty(n_resamples, dtype=torch.float64, device=dev)
         gen = torch.default_generator if generator is None else generator
         state = _generator_to_state(gen).to(dev)
-        batch = max(1, min(n_resamples if batch is None else batch, (1 << 28) // max(n_total, 1) or 1,
+        batch = max(1, min(n_resamples if batch is None else batch, (1 << 29) // max(n_total, 1) or 1,
                            _ops.MAX_RESAMPLES_PER_CALL))
         idx = torch.empty(batch * n_total, dtype=torch.int32, device=dev)
         for k in range(0, n_resamples, batch):

@@ -63,6 +63,12 @@ struct Params {
     const int* emb_out_col; const int* emb_periodic;
     T emb_lower, emb_scale;
     int E, xs_ld;
+    int n_hidden[MAXL];               // [l] = units of hidden layer l (= n_out of linear layer l - 1)
+    // blocked sweeps of wide conditioners (tfep_b200/_blocked.py): per linear layer an optional per-sample term added to
+    // the pre-activations (what the units of EARLIER degree blocks contribute, computed by a plain GEMM), and optional
+    // global buffers that receive the hidden activations of the tile (the inputs of the LATER blocks' GEMMs)
+    const T* extra[MAXL]; int64_t ldextra[MAXL];
+    T* act_out[MAXL]; int64_t ldact_out[MAXL];
 };
 
 // out[s][ocol0 + (r - r0)] = act(bias[r] + sum_k W[r][k] in[s][k]) for r in [r0, r1), all TS samples of the tile.
@@ -70,7 +76,9 @@ struct Params {
 // activations that do not exist yet are zero.
 template <typename T, int TS, int THREADS, bool WSMEM = false>
 __device__ void gemv_stage(const T* __restrict__ W, int ldw, const T* __restrict__ bias, int r0, int r1, int K,
-                           const T* in, int ldin, T* out, int ldout, int ocol0, bool act, T* scratch) {
+                           const T* in, int ldin, T* out, int ldout, int ocol0, bool act, T* scratch,
+                           const T* __restrict__ extra = nullptr, int64_t ldextra = 0, int rows = TS) {
+    // `extra` (already offset to the first sample of the tile): extra[s * ldextra + r] is added to row r of sample s
     using V = typename Vec<T>::type;
     constexpr int NV = Vec<T>::N;
     constexpr int SG = TS / 32;                  // warps side by side over the samples
@@ -113,7 +121,8 @@ __device__ void gemv_stage(const T* __restrict__ W, int ldw, const T* __restrict
 #pragma unroll
             for (int j = 0; j < RB; ++j) {
                 if (j < nr) {
-                    const T v = acc[j] + bias[ra + j];
+                    T v = acc[j] + bias[ra + j];
+                    if (extra != nullptr && s < rows) v += extra[(int64_t)s * ldextra + ra + j];
                     out[(size_t)s * ldout + ocol0 + (ra - r0) + j] = act ? tfepb::elu(v) : v;
                 }
             }
@@ -129,6 +138,7 @@ __device__ void gemv_stage(const T* __restrict__ W, int ldw, const T* __restrict
             const int r = o / TS, ss = o - r * TS;
             const int rb = r / rbs, j = r - rb * rbs;
             T v = bias[r0 + r];
+            if (extra != nullptr && ss < rows) v += extra[(int64_t)ss * ldextra + r0 + r];
             for (int ks = 0; ks < nks; ++ks) v += scratch[((size_t)(rb * nks + ks) * RB + j) * TS + ss];
             out[(size_t)ss * ldout + ocol0 + r] = act ? tfepb::elu(v) : v;
         }
@@ -245,12 +255,22 @@ __global__ void __launch_bounds__(THREADS) maf_inverse_sweep_kernel(const Params
             const tfepb_sweep_group g = p.groups[gi];
             if (g.out_r1 > g.out_r0) {
                 gemv_stage<T, TS, THREADS>(p.w[L - 1], p.ldw[L - 1], p.b[L - 1], g.out_r0, g.out_r1, g.out_k, act[L - 1], p.act_ld[L - 1],
-                                  par, p.par_ld, 0, false, scratch);
+                                  par, p.par_ld, 0, false, scratch,
+                                  p.extra[L - 1] ? p.extra[L - 1] + tile0 * p.ldextra[L - 1] : nullptr, p.ldextra[L - 1], rows);
                 transform_stage<T, TS, THREADS>(p, g, tile0, rows, xs, act[0], par, ldacc);
             }
             for (int l = 1; l < L; ++l)
                 gemv_stage<T, TS, THREADS>(p.w[l - 1], p.ldw[l - 1], p.b[l - 1], g.h_a[l - 1], g.h_b[l - 1], g.h_k[l - 1], act[l - 1],
-                                  p.act_ld[l - 1], act[l], p.act_ld[l], g.h_a[l - 1], true, scratch);
+                                  p.act_ld[l - 1], act[l], p.act_ld[l], g.h_a[l - 1], true, scratch,
+                                  p.extra[l - 1] ? p.extra[l - 1] + tile0 * p.ldextra[l - 1] : nullptr, p.ldextra[l - 1], rows);
+        }
+        for (int l = 1; l < L; ++l) {           // hidden activations of the tile -> global (blocked sweeps)
+            if (p.act_out[l] == nullptr) continue;
+            const int width = p.n_hidden[l];
+            for (int i = threadIdx.x; i < rows * width; i += THREADS) {
+                const int s = i / width, c = i - s * width;
+                p.act_out[l][(tile0 + s) * p.ldact_out[l] + c] = act[l][(size_t)s * p.act_ld[l] + c];
+            }
         }
         // ---- write the tile ----
         for (int i = threadIdx.x; i < rows * p.D; i += THREADS) {
@@ -335,17 +355,29 @@ __global__ void __launch_bounds__(THREADS, 1) maf_inverse_sweep_staged_kernel(co
             ++waited;
             if (g.out_r1 > g.out_r0) {
                 gemv_stage<T, TS, THREADS, true>(wsm - (size_t)g.out_r0 * p.ldw[L - 1], p.ldw[L - 1], p.b[L - 1], g.out_r0, g.out_r1,
-                                                 g.out_k, act[L - 1], p.act_ld[L - 1], par, p.par_ld, 0, false, scratch);
+                                                 g.out_k, act[L - 1], p.act_ld[L - 1], par, p.par_ld, 0, false, scratch,
+                                                 p.extra[L - 1] ? p.extra[L - 1] + tile0 * p.ldextra[L - 1] : nullptr,
+                                                 p.ldextra[L - 1], rows);
                 transform_stage<T, TS, THREADS>(p, g, tile0, rows, xs, act[0], par, ldacc);
             }
             const T* wh = wsm + (size_t)(g.out_r1 - g.out_r0) * p.ldw[L - 1];
             for (int l = 1; l < L; ++l) {
                 gemv_stage<T, TS, THREADS, true>(wh - (size_t)g.h_a[l - 1] * p.ldw[l - 1], p.ldw[l - 1], p.b[l - 1], g.h_a[l - 1],
                                                  g.h_b[l - 1], g.h_k[l - 1], act[l - 1], p.act_ld[l - 1], act[l], p.act_ld[l],
-                                                 g.h_a[l - 1], true, scratch);
+                                                 g.h_a[l - 1], true, scratch,
+                                                 p.extra[l - 1] ? p.extra[l - 1] + tile0 * p.ldextra[l - 1] : nullptr,
+                                                 p.ldextra[l - 1], rows);
                 wh += (size_t)(g.h_b[l - 1] - g.h_a[l - 1]) * p.ldw[l - 1];
             }
             __syncthreads();
+        }
+        for (int l = 1; l < L; ++l) {           // hidden activations of the tile -> global (blocked sweeps)
+            if (p.act_out[l] == nullptr) continue;
+            const int width = p.n_hidden[l];
+            for (int i = threadIdx.x; i < rows * width; i += THREADS) {
+                const int s = i / width, c = i - s * width;
+                p.act_out[l][(tile0 + s) * p.ldact_out[l] + c] = act[l][(size_t)s * p.act_ld[l] + c];
+            }
         }
         for (int i = threadIdx.x; i < rows * p.D; i += THREADS) {
             const int s = i / p.D, c = i - s * p.D;
@@ -390,6 +422,14 @@ int launch(const tfepb_sweep_args* a, cudaStream_t stream) {
         const int width = l == 0 ? (a->emb_out_col ? a->n_embedded : a->n_features) : a->n_out[l - 1];
         TFEPB_CHECK_ARG(a->ldw[l] >= width, "layer %d: leading dimension smaller than the input width", l);
         p.act_ld[l] = padded_ld<T>(a->ldw[l] > width ? a->ldw[l] : width);
+    }
+    for (int l = 0; l < a->n_linear; ++l) {
+        p.extra[l] = (const T*)a->extra[l]; p.ldextra[l] = a->ldextra[l];
+        p.act_out[l] = (T*)a->act_out[l]; p.ldact_out[l] = a->ldact_out[l];
+        p.n_hidden[l] = l == 0 ? 0 : a->n_out[l - 1];
+        TFEPB_CHECK_ARG(a->extra[l] == nullptr || a->ldextra[l] >= a->n_out[l], "layer %d: leading dimension of `extra`", l);
+        TFEPB_CHECK_ARG(a->act_out[l] == nullptr || (l > 0 && a->ldact_out[l] >= a->n_out[l - 1]),
+                        "layer %d: act_out receives hidden layer l (l >= 1) with a leading dimension >= its width", l);
     }
     p.par_ld = a->max_params < 1 ? 1 : a->max_params;
     p.groups = a->groups; p.n_groups = a->n_groups; p.parts = a->parts; p.gparts = a->group_parts; p.ids = a->ids;

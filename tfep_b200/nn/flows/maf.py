@@ -95,6 +95,9 @@ class MAF(AutoregressiveFlow):
         self._packing = None
         self._fused = None
         self._sweep = None
+        self._blocked = None
+        #: degrees per block of the blocked inverse sweep of wide conditioners (tfep_b200/_blocked.py)
+        self.inverse_block_degrees = 64
         #: see the class docstring; one of PRECISIONS
         self.precision = precision
 
@@ -219,12 +222,20 @@ class MAF(AutoregressiveFlow):
             if plan is not None and plan.inverse_eligibility(self) is None:
                 return _fused.run_inverse_chain([(plan, self)], y)
             # (flows the tensor-core sweep does not cover are inverted by the exact sweep below)
-        from ... import _sweep
+        from ... import _blocked, _sweep
         if _sweep.eligibility(self, pk) is not None:
             return self._inverse_host_sweep(y)
+        layouts, _ = self._packed_tables(y.device)
+        if _blocked.needs_blocking(self, pk) and self._embedding is None and not self.has_fixed_indices:
+            # wide conditioner (the activations of a sample tile do not fit an SM): degree blocks, GEMM panels between
+            # them, the persistent sweep inside them (tfep_b200/_blocked.py)
+            if self._blocked is None:
+                self._blocked = _blocked.BlockedSweepPlan(self, pk, block_degrees=self.inverse_block_degrees)
+            panels = self.precision if (self.precision != 'fp32' and y.dtype == torch.float32) else 'fp32'
+            with torch.no_grad():
+                return self._blocked.inverse(self, y, layouts, panel_precision=panels)
         if self._sweep is None:
             self._sweep = _sweep.SweepPlan(self, pk)
-        layouts, _ = self._packed_tables(y.device)
         with torch.no_grad():
             return self._sweep.inverse(self, y, layouts)
 
