@@ -42,7 +42,7 @@ def test_measured_arm_line():
     e = d['e2e']
     assert 0 < e['value'] <= d['value'] and e['h2d_bytes_per_step'] == 65536 * 66 * 4
     assert e['d2h_bytes_per_step'] == 65536 * 4 + 16 and e['unit'] == 'samples/s'       # per-sample work + estimator partial
-    assert e['value'] <= 1.02 * e['host_ceiling']['samples_per_s'] and e['delta_f_last_step'] == e['delta_f_last_step']
+    assert e['value'] <= 1.05 * e['host_ceiling']['samples_per_s'] and e['delta_f_last_step'] == e['delta_f_last_step']
     f = d['e2e_full_outputs']
     assert 0 < f['value'] <= d['value'] and f['d2h_bytes_per_step'] == 65536 * 67 * 4
     r = d['roofline']

@@ -402,3 +402,34 @@ def test_empty_batches_through_the_fused_paths():
         wrapped = CenteredCentroidFlow(OrientedFlow(seq), space_dimension=3).to(DEV)
         y, ld = wrapped(torch.empty(0, 72, device=DEV))
         assert y.shape == (0, 72) and ld.shape == (0,)
+
+
+def test_protocol_stress_is_deterministic():
+    """compute-sanitizer is closed on this pool (profiles/README.md), so the hand-rolled synchronisation of the chain
+    kernels -- mbarrier rings, TMEM hand-overs, inter-CTA tile flags with per-launch epochs, cooperative co-residency -- is
+    exercised the hard way: 150 back-to-back launches over batch sizes that give ragged tiles, fewer tiles than SMs, one
+    tile per SM and many rounds, forward and inverse, every result bit-identical to the first run of its shape (a lost or
+    early hand-over shows up as a wrong or non-reproducible tile; a dead-lock trips the kernels' clock watchdog)."""
+    seq, _ = cfg_flow_modules('cfg2', DEV)
+    for maf in seq:
+        maf.precision = 'bf16'
+    shapes = [1, 127, 129, 128 * 37 + 5, 128 * 148, 128 * 148 + 1, 128 * 400 + 77, 65536]
+    xs = {b: cases.cfg_input('cfg2', b).to(DEV) for b in shapes}
+    first = {}
+    with torch.no_grad():
+        for it in range(150):
+            b = shapes[(it * 5) % len(shapes)]
+            y, ld = seq(xs[b])
+            if it % 3 == 0:
+                xi, ldi = seq.inverse(y)
+            else:
+                xi = ldi = None
+            if b not in first:
+                first[b] = [y.clone(), ld.clone(), None, None]
+            ref = first[b]
+            assert torch.equal(y, ref[0]) and torch.equal(ld, ref[1]), (it, b)
+            if xi is not None:
+                if ref[2] is None:
+                    ref[2], ref[3] = xi.clone(), ldi.clone()
+                assert torch.equal(xi, ref[2]) and torch.equal(ldi, ref[3]), (it, b)
+    torch.cuda.synchronize()

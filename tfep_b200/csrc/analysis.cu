@@ -402,6 +402,7 @@ extern "C" int64_t tfepb_lse_workspace_bytes(void) { return (int64_t)LSE_MAX_BLO
 
 extern "C" int tfepb_lse(int32_t dtype, const void* w, const void* logw, int64_t n, double scale, void* partials,
                          double* out2, tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(n > 0, "empty data");
     TFEPB_CHECK_ARG(w && partials && out2, "null buffer");
     if (int rc = require_sm100()) return rc;
@@ -425,6 +426,7 @@ extern "C" int tfepb_lse(int32_t dtype, const void* w, const void* logw, int64_t
 
 extern "C" int tfepb_exp_table(int32_t dtype, const void* w, int64_t n, double scale, const double* max_dev, float* e,
                                tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(n > 0, "empty data");
     TFEPB_CHECK_ARG(w && max_dev && e, "null buffer");
     if (int rc = require_sm100()) return rc;
@@ -444,6 +446,7 @@ extern "C" int tfepb_bootstrap_sums(const float* e, int64_t n, int64_t shard_lo,
                                     int64_t ldidx, int32_t n_resamples, int64_t sample_size, uint64_t philox_seed,
                                     uint64_t philox_offset, const int64_t* sample_sizes, double* out_sums,
                                     tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(e && out_sums, "null buffer");
     TFEPB_CHECK_ARG(sample_sizes == nullptr || idx == nullptr, "per-resample sizes go with the Philox stream only");
     TFEPB_CHECK_ARG(n_resamples > 0 && sample_size > 0, "bad sizes");
@@ -461,6 +464,7 @@ extern "C" int tfepb_bootstrap_sums(const float* e, int64_t n, int64_t shard_lo,
 extern "C" int tfepb_bayesian_bootstrap_sums(const float* e, int64_t n, int32_t n_resamples, uint64_t philox_seed,
                                              uint64_t philox_offset, double* out_sums, double* out_weight_sums,
                                              tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(e && out_sums && out_weight_sums, "null buffer");
     TFEPB_CHECK_ARG(n > 0 && n_resamples > 0, "bad sizes");
     TFEPB_CHECK_ARG(n_resamples <= 65535, "at most 65535 resamples per call");
@@ -484,6 +488,7 @@ extern "C" int tfepb_mt19937_seed(uint32_t seed, uint32_t* state625_host) {
 
 extern "C" int tfepb_mt19937_indices(uint32_t* state625_dev, int64_t count, uint32_t max_idx, int32_t* idx,
                                      tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(state625_dev && idx, "null buffer");
     TFEPB_CHECK_ARG(count >= 0 && max_idx > 0, "bad sizes");
     TFEPB_CHECK_ARG(max_idx <= 0x7fffffffu, "indices are int32: max_idx must be below 2^31");

@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <stdarg.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/tfep_b200.h"
 #include "hd_math.cuh"
 
@@ -48,6 +50,16 @@ int launch_cooperative(const void* kernel, int grid, int threads, size_t smem, v
 int ensure_dynamic_smem(const void* kernel, size_t bytes);
 
 inline cudaStream_t as_stream(tfepb_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// NVTX range around every entry point of the C ABI (header-only NVTX 3: free unless a profiler is attached), so that
+// nsys / ncu timelines show which call of the boundary enqueued which kernels.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define TFEPB_NVTX() ::tfepb::NvtxRange nvtx_range__(__func__)
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

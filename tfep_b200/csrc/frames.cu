@@ -276,6 +276,7 @@ static int check_centroid(const tfepb_centroid_args* a, bool post) {
 }
 
 extern "C" int tfepb_centroid_pre(const tfepb_centroid_args* a, tfepb_stream_t stream) {
+    TFEPB_NVTX();
     if (int rc = check_centroid(a, false)) return rc;
     if (int rc = require_sm100()) return rc;
     if (a->batch == 0) return 0;
@@ -283,6 +284,7 @@ extern "C" int tfepb_centroid_pre(const tfepb_centroid_args* a, tfepb_stream_t s
 }
 
 extern "C" int tfepb_centroid_post(const tfepb_centroid_args* a, tfepb_stream_t stream) {
+    TFEPB_NVTX();
     if (int rc = check_centroid(a, true)) return rc;
     if (int rc = require_sm100()) return rc;
     if (a->batch == 0) return 0;
@@ -303,6 +305,7 @@ static int check_oriented(const tfepb_oriented_args* a, bool post) {
 }
 
 extern "C" int tfepb_oriented_pre(const tfepb_oriented_args* a, tfepb_stream_t stream) {
+    TFEPB_NVTX();
     if (int rc = check_oriented(a, false)) return rc;
     if (int rc = require_sm100()) return rc;
     if (a->batch == 0) return 0;
@@ -310,6 +313,7 @@ extern "C" int tfepb_oriented_pre(const tfepb_oriented_args* a, tfepb_stream_t s
 }
 
 extern "C" int tfepb_oriented_post(const tfepb_oriented_args* a, tfepb_stream_t stream) {
+    TFEPB_NVTX();
     if (int rc = check_oriented(a, true)) return rc;
     if (int rc = require_sm100()) return rc;
     if (a->batch == 0) return 0;

@@ -433,6 +433,7 @@ int bwd_weight_t(const tfepb_linear_bwd_weight_args* a, cudaStream_t s) {
 using namespace tfepb;
 
 extern "C" int tfepb_masked_linear_forward(const tfepb_linear_fwd_args* a, tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(a != nullptr, "null argument struct");
     TFEPB_CHECK_ARG(a->batch >= 0 && a->in_features >= 0 && a->out_features > 0, "bad sizes");
     TFEPB_CHECK_ARG((a->in_features == 0 || (a->x && a->w)) && a->y, "null buffer");
@@ -445,6 +446,7 @@ extern "C" int tfepb_masked_linear_forward(const tfepb_linear_fwd_args* a, tfepb
 }
 
 extern "C" int tfepb_masked_linear_backward_input(const tfepb_linear_bwd_input_args* a, tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(a != nullptr, "null argument struct");
     TFEPB_CHECK_ARG(a->batch >= 0 && a->in_features > 0 && a->out_features > 0, "bad sizes");
     TFEPB_CHECK_ARG(a->grad_y && a->w && a->grad_x, "null buffer");
@@ -457,6 +459,7 @@ extern "C" int tfepb_masked_linear_backward_input(const tfepb_linear_bwd_input_a
 }
 
 extern "C" int tfepb_masked_linear_backward_weight(const tfepb_linear_bwd_weight_args* a, tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(a != nullptr, "null argument struct");
     TFEPB_CHECK_ARG(a->batch >= 0 && a->in_features > 0 && a->out_features > 0, "bad sizes");
     TFEPB_CHECK_ARG(a->grad_y && a->x && a->grad_w, "null buffer");

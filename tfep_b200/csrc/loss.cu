@@ -166,6 +166,7 @@ extern "C" int64_t tfepb_kl_loss_workspace_bytes(void) { return (int64_t)KL_MAX_
 extern "C" int tfepb_kl_loss(int32_t dtype, const void* target_potentials, const void* log_det_J, const void* ref_potentials,
                              const void* log_weights, int64_t n, int32_t ignore_nan, void* workspace, double* out5,
                              tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(n > 0, "empty batch");
     TFEPB_CHECK_ARG(target_potentials && workspace && out5, "null buffer");
     if (int rc = require_sm100()) return rc;
@@ -190,6 +191,7 @@ extern "C" int tfepb_kl_loss_backward(int32_t dtype, const void* target_potentia
                                       const void* ref_potentials, const void* log_weights, int64_t n, int32_t ignore_nan,
                                       const double* stats5, const void* grad_out, void* grad_target, void* grad_log_det_J,
                                       void* grad_ref, void* grad_log_weights, tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(n > 0, "empty batch");
     TFEPB_CHECK_ARG(target_potentials && stats5 && grad_out, "null buffer");
     if (int rc = require_sm100()) return rc;

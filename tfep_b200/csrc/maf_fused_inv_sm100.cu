@@ -97,38 +97,57 @@ __device__ __forceinline__ float spline8_inverse(const uint32_t (&r)[32], float 
     const float Ly = fmaf(8.f, min_bin, fc.Rh);                  // yf - y0
     const float t0 = yv - fc.y0;
     const float t = fminf(fmaxf(t0, 0.f), Ly);
-    float mw = fmaxf(fmaxf(fmaxf(p[0], p[1]), fmaxf(p[2], p[3])), fmaxf(fmaxf(p[4], p[5]), fmaxf(p[6], p[7])));
-    float mh = fmaxf(fmaxf(fmaxf(p[8], p[9]), fmaxf(p[10], p[11])), fmaxf(fmaxf(p[12], p[13]), fmaxf(p[14], p[15])));
-    float ew[8], eh[8];
+    // The knots are built EXACTLY as in the forward kernel (maf_fused_sm100.cu, spline8): exponentials without the
+    // maximum subtracted (same fallback), prefix sums, knots in the unnormalised domain -- a X_k = cw_{k-1} + k a min_bin
+    // with a = sw / Rw, b Y_k = ch_{k-1} + k b min_bin with b = sh / Rh -- so that both directions see bit-identical
+    // bin parameters and the round trip closes to rounding.
+    float ew[8], eh[8], cw[8], ch[8];
+    auto sums = [&](float mw, float mh) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        ew[k] = ex2(p[k] - mw);
-        eh[k] = ex2(p[8 + k] - mh);
+        for (int k = 0; k < 8; ++k) {
+            ew[k] = ex2(p[k] - mw);
+            eh[k] = ex2(p[8 + k] - mh);
+        }
+        cw[0] = ew[0]; ch[0] = eh[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) { cw[k] = cw[k - 1] + ew[k]; ch[k] = ch[k - 1] + eh[k]; }
+    };
+    sums(0.f, 0.f);
+    {
+        const float lo = fminf(cw[7], ch[7]), hi = fmaxf(cw[7], ch[7]);
+        if (__any_sync(0xffffffffu, !(lo > 7.9e-31f && hi < 1.3e30f))) {
+            float mw = p[0], mh = p[8];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) { mw = fmaxf(mw, p[k]); mh = fmaxf(mh, p[8 + k]); }
+            sums(mw, mh);
+        }
     }
-    const float sw = ((ew[0] + ew[1]) + (ew[2] + ew[3])) + ((ew[4] + ew[5]) + (ew[6] + ew[7]));
-    const float sh = ((eh[0] + eh[1]) + (eh[2] + eh[3])) + ((eh[4] + eh[5]) + (eh[6] + eh[7]));
-    const float rw = fc.Rw * rcp(sw), rh = fc.Rh * rcp(sh);
-    // walk the knots along y: last bin whose bottom knot is below t (same knot arithmetic as the forward kernel)
-    float wk = fmaf(ew[0], rw, min_bin), hk = fmaf(eh[0], rh, min_bin);
-    float left = wk, bottom = hk, w_sel = wk, h_sel = hk, xk = 0.f, yk = 0.f;
+    const float sw = cw[7], sh = ch[7];
+    const float sa = sw * (1.f / fc.Rw), sb = sh * (1.f / fc.Rh);
+    const float ty = t * sb, mbs = min_bin * sa, mbsh = min_bin * sb;
+    // walk the knots along y: last bin whose bottom knot is below t
+    float Us = 0.f, Vs = 0.f, ews = ew[0], ehs = eh[0];
     float raw0 = p[16], raw1 = p[17];
     const float raw_last = (MIXED && !circ) ? p[24] : p[16];
 #pragma unroll
-    for (int k = 0; k < 7; ++k) {
-        if (k > 0) { left += wk; bottom += hk; }
-        wk = fmaf(ew[k + 1], rw, min_bin);
-        hk = fmaf(eh[k + 1], rh, min_bin);
-        const bool adv = t > bottom;
-        w_sel = adv ? wk : w_sel;
-        h_sel = adv ? hk : h_sel;
-        xk = adv ? left : xk;
-        yk = adv ? bottom : yk;
-        raw0 = adv ? p[16 + k + 1] : raw0;
-        raw1 = adv ? (k == 6 ? raw_last : p[16 + k + 2]) : raw1;
+    for (int k = 1; k < 8; ++k) {
+        const float Uk = fmaf((float)k, mbs, cw[k - 1]);
+        const float Vk = fmaf((float)k, mbsh, ch[k - 1]);
+        const bool adv = ty > Vk;
+        Us = adv ? Uk : Us;
+        Vs = adv ? Vk : Vs;
+        ews = adv ? ew[k] : ews;
+        ehs = adv ? eh[k] : ehs;
+        raw0 = adv ? p[16 + k] : raw0;
+        raw1 = adv ? (k == 7 ? raw_last : p[16 + k + 1]) : raw1;
     }
+    const float iw = rcp(ews + mbs);                 // 1 / (a w)
+    const float g = fc.Rh * rcp(sh);                 // 1 / b
+    const float h_sel = (ehs + mbsh) * g;
+    const float s = h_sel * (iw * sa);               // h / w
+    const float yk = Vs * g;
     const float dk = softplus_l2(raw0 + slope_offset2) + min_slope;
     const float dk1 = softplus_l2(raw1 + slope_offset2) + min_slope;
-    const float s = h_sel * rcp(w_sel);
     const float yr = t - yk;
     const float q = dk1 + dk - 2.f * s;
     const float a = fmaf(h_sel, s - dk, yr * q);
@@ -141,7 +160,7 @@ __device__ __forceinline__ float spline8_inverse(const uint32_t (&r)[32], float 
     const float iden = rcp(den);
     const float nn = fmaf(dk1, e2, fmaf(2.f * s, u, dk * ome * ome));
     const float rr = s * iden;
-    float xr = fmaf(e, w_sel, xk);
+    float xr = fmaf(e, ews + mbs, Us) * rcp(sa);     // (a x_k + e a w) / a
     float ld = -LN2 * lg2(nn * rr * rr);
     if (circ) {
         // un-shift and wrap into [x0, x0 + L)
@@ -521,6 +540,7 @@ static_assert(sizeof(finv::Op) == sizeof(tfepb_fused_op), "schedule entry layout
 static_assert(sizeof(finv::Step) == sizeof(tfepb_fused_inv_step), "step table layout mismatch");
 
 extern "C" int tfepb_maf_spline_inverse_bf16(const tfepb_fused_inv_args* a, tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(a != nullptr, "null argument struct");
     TFEPB_CHECK_ARG(a->y && a->x && a->logdet && a->layers, "null buffer");
     TFEPB_CHECK_ARG(a->batch >= 0 && a->n_features > 0, "bad sizes");

@@ -715,6 +715,7 @@ static_assert(sizeof(fused::FeatConst) == 32 && sizeof(tfepb_fused_feature) == 3
 static_assert(sizeof(fused::Params) < 32000, "kernel parameter space");
 
 extern "C" int tfepb_maf_spline_forward_bf16(const tfepb_fused_args* a, tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(a != nullptr, "null argument struct");
     TFEPB_CHECK_ARG(a->x && a->y && a->logdet && a->layers, "null buffer");
     TFEPB_CHECK_ARG(a->batch >= 0 && a->n_features > 0, "bad sizes");

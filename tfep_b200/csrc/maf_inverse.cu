@@ -468,6 +468,7 @@ int launch(const tfepb_sweep_args* a, cudaStream_t stream) {
 using namespace tfepb;
 
 extern "C" int tfepb_maf_inverse_sweep(const tfepb_sweep_args* a, tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(a != nullptr, "null argument struct");
     TFEPB_CHECK_ARG(a->dtype == TFEPB_F32 || a->dtype == TFEPB_F64, "unknown dtype %d", a->dtype);
     TFEPB_CHECK_ARG(a->batch >= 0 && a->n_features > 0, "bad sizes");

@@ -489,6 +489,7 @@ extern "C" int64_t tfepb_tc_image_bytes(int64_t rows, int64_t k, int32_t block_r
 
 extern "C" int tfepb_tc_pack_split(const float* src, int64_t ld, int32_t rows, int32_t k, int32_t block_rows, int32_t transpose,
                                    int32_t n_split, void* image, tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(src && image, "null buffer");
     TFEPB_CHECK_ARG(rows > 0 && k > 0, "bad sizes");
     TFEPB_CHECK_ARG(n_split >= 1 && n_split <= 3, "n_split must be 1, 2 or 3");
@@ -503,6 +504,7 @@ extern "C" int tfepb_tc_pack_split(const float* src, int64_t ld, int32_t rows, i
 
 extern "C" int tfepb_tc_pack(const float* src, int64_t ld, int32_t rows, int32_t k, int32_t block_rows, int32_t transpose,
                              void* image, tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(src && image, "null buffer");
     TFEPB_CHECK_ARG(rows > 0 && k > 0, "bad sizes");
     TFEPB_CHECK_ARG(block_rows == 128 || block_rows == 256, "block_rows must be 128 (A operand) or 256 (B operand)");
@@ -515,6 +517,7 @@ extern "C" int tfepb_tc_pack(const float* src, int64_t ld, int32_t rows, int32_t
 
 extern "C" int tfepb_tc_pack_dual(const float* src, int64_t ld, int32_t rows, int32_t cols, void* image, void* image_t,
                                   int32_t t_block_rows, float* column_sums, tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(src != nullptr && (image != nullptr || image_t != nullptr), "null buffer");
     TFEPB_CHECK_ARG(rows > 0 && cols > 0 && ld >= cols, "bad sizes");
     TFEPB_CHECK_ARG(image_t == nullptr || t_block_rows == 128 || t_block_rows == 256, "t_block_rows must be 128 or 256");
@@ -530,6 +533,7 @@ extern "C" int tfepb_tc_pack_dual(const float* src, int64_t ld, int32_t rows, in
 }
 
 extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(a != nullptr, "null argument struct");
     TFEPB_CHECK_ARG(a->a_image && a->b_image, "null operand image");
     TFEPB_CHECK_ARG(a->m > 0 && a->n > 0 && a->k > 0, "bad sizes");

@@ -171,6 +171,7 @@ using namespace tfepb;
 extern "C" int tfepb_periodic_embedding(int32_t dtype, const void* x, int64_t ldx, int32_t batch, int32_t n_in,
                                         const int32_t* out_col, const int32_t* periodic, double lower, double scale,
                                         void* out, int64_t ldo, tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(dtype == TFEPB_F32 || dtype == TFEPB_F64, "unknown dtype %d", dtype);
     TFEPB_CHECK_ARG(batch >= 0 && n_in > 0, "bad sizes");
     TFEPB_CHECK_ARG(x && out && out_col && periodic, "null buffer");
@@ -192,6 +193,7 @@ extern "C" int tfepb_periodic_embedding_backward(int32_t dtype, const void* x, i
                                                  const int32_t* out_col, const int32_t* periodic, double lower, double scale,
                                                  const void* grad_out, int64_t ldgo, void* grad_x, int64_t ldgx,
                                                  tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(dtype == TFEPB_F32 || dtype == TFEPB_F64, "unknown dtype %d", dtype);
     TFEPB_CHECK_ARG(batch >= 0 && n_in > 0, "bad sizes");
     TFEPB_CHECK_ARG(x && grad_out && grad_x && out_col && periodic, "null buffer");
@@ -212,12 +214,14 @@ extern "C" int tfepb_periodic_embedding_backward(int32_t dtype, const void* x, i
 }
 
 extern "C" int tfepb_affine(const tfepb_tx_io* io, tfepb_stream_t stream) {
+    TFEPB_NVTX();
     if (int rc = check_io(io, nullptr)) return rc;
     if (io->dtype == TFEPB_F32) return run<float>(io, nullptr, AffineOp<float>{}, as_stream(stream), "affine");
     return run<double>(io, nullptr, AffineOp<double>{}, as_stream(stream), "affine");
 }
 
 extern "C" int tfepb_affine_backward(const tfepb_tx_io* io, const tfepb_tx_grads* g, tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(g != nullptr, "null gradient struct");
     if (int rc = check_io(io, g)) return rc;
     if (io->dtype == TFEPB_F32) return run<float>(io, g, AffineOp<float>{}, as_stream(stream), "affine_backward");
@@ -225,6 +229,7 @@ extern "C" int tfepb_affine_backward(const tfepb_tx_io* io, const tfepb_tx_grads
 }
 
 extern "C" int tfepb_shift(const tfepb_tx_io* io, const void* period, const void* lower, tfepb_stream_t stream) {
+    TFEPB_NVTX();
     if (int rc = check_io(io, nullptr)) return rc;
     TFEPB_CHECK_ARG(period && lower, "null period / lower table");
     if (io->dtype == TFEPB_F32)
@@ -234,6 +239,7 @@ extern "C" int tfepb_shift(const tfepb_tx_io* io, const void* period, const void
 
 extern "C" int tfepb_shift_backward(const tfepb_tx_io* io, const void* period, const void* lower, const tfepb_tx_grads* g,
                                     tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(g != nullptr, "null gradient struct");
     if (int rc = check_io(io, g)) return rc;
     TFEPB_CHECK_ARG(period && lower, "null period / lower table");
@@ -244,6 +250,7 @@ extern "C" int tfepb_shift_backward(const tfepb_tx_io* io, const void* period, c
 }
 
 extern "C" int tfepb_sos(const tfepb_tx_io* io, int32_t n_polynomials, tfepb_stream_t stream) {
+    TFEPB_NVTX();
     if (int rc = check_io(io, nullptr)) return rc;
     TFEPB_CHECK_ARG(n_polynomials >= 2, "n_polynomials must be strictly greater than 1.");
     TFEPB_CHECK_ARG(io->inverse == 0, "Inversion of SOS polynomial transformer has not been implemented yet.");
@@ -253,6 +260,7 @@ extern "C" int tfepb_sos(const tfepb_tx_io* io, int32_t n_polynomials, tfepb_str
 
 extern "C" int tfepb_sos_backward(const tfepb_tx_io* io, int32_t n_polynomials, const tfepb_tx_grads* g,
                                   tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(g != nullptr, "null gradient struct");
     if (int rc = check_io(io, g)) return rc;
     TFEPB_CHECK_ARG(n_polynomials >= 2, "n_polynomials must be strictly greater than 1.");
@@ -263,6 +271,7 @@ extern "C" int tfepb_sos_backward(const tfepb_tx_io* io, int32_t n_polynomials, 
 
 extern "C" int tfepb_moebius(const tfepb_tx_io* io, int32_t dimension, double max_radius, int32_t unit_sphere,
                              tfepb_stream_t stream) {
+    TFEPB_NVTX();
     if (int rc = check_io(io, nullptr)) return rc;
     TFEPB_CHECK_ARG(dimension >= 1 && dimension <= 16, "dimension must be in [1, 16]");
     TFEPB_CHECK_ARG(io->n_features % dimension == 0, "n_features must be a multiple of the vector dimension");
@@ -274,6 +283,7 @@ extern "C" int tfepb_moebius(const tfepb_tx_io* io, int32_t dimension, double ma
 
 extern "C" int tfepb_moebius_backward(const tfepb_tx_io* io, int32_t dimension, double max_radius, int32_t unit_sphere,
                                       const tfepb_tx_grads* g, tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(g != nullptr, "null gradient struct");
     if (int rc = check_io(io, g)) return rc;
     TFEPB_CHECK_ARG(dimension >= 1 && dimension <= 16, "dimension must be in [1, 16]");
@@ -286,6 +296,7 @@ extern "C" int tfepb_moebius_backward(const tfepb_tx_io* io, int32_t dimension, 
 }
 
 extern "C" int tfepb_spline(const tfepb_tx_io* io, const tfepb_spline_cfg* cfg, tfepb_stream_t stream) {
+    TFEPB_NVTX();
     if (int rc = check_io(io, nullptr)) return rc;
     if (int rc = check_spline(io, cfg)) return rc;
     if (io->dtype == TFEPB_F32) return spline_dispatch<float>(io, cfg, nullptr, as_stream(stream));
@@ -294,6 +305,7 @@ extern "C" int tfepb_spline(const tfepb_tx_io* io, const tfepb_spline_cfg* cfg, 
 
 extern "C" int tfepb_spline_backward(const tfepb_tx_io* io, const tfepb_spline_cfg* cfg, const tfepb_tx_grads* g,
                                      tfepb_stream_t stream) {
+    TFEPB_NVTX();
     TFEPB_CHECK_ARG(g != nullptr, "null gradient struct");
     if (int rc = check_io(io, g)) return rc;
     if (int rc = check_spline(io, cfg)) return rc;
