@@ -26,6 +26,7 @@ def prec(request):
 
 def test_forward_and_inverse_against_golden(prec):
     g = golden(f'maf_{prec}.npz')
+    g64 = golden('maf_f64.npz')
     for name, case in cases.maf_cases(DT[prec]).items():
         _, sd = cases.build_oracle(case, DT[prec])
         maf = to_maf(case, sd, DEV, DT[prec])
@@ -39,8 +40,16 @@ def test_forward_and_inverse_against_golden(prec):
             continue
         with torch.no_grad():
             xi, ldi = maf.inverse(torch.from_numpy(g[f'{name}/y']).to(DEV))
-        assert rel_err(xi, g[f'{name}/xinv']) < 20 * TOL[prec], name
-        assert rel_err(ldi, g[f'{name}/ldinv']) < 20 * TOL[prec], name
+        # The inverse divides by dy/dx, so its error is the forward tolerance times the conditioning of the case.  The
+        # yardstick for that is the reference itself: how far its fp32 inverse lies from its fp64 inverse (golden files of
+        # both precisions share the seeds).  fp32: within 2e-5, or 4 x the reference's own fp32 error where that is larger.
+        tol_x = tol_ld = 2 * TOL[prec]
+        if prec == 'f32':
+            tol_x = max(tol_x, 4 * rel_err(g[f'{name}/xinv'], g64[f'{name}/xinv']))
+            tol_ld = max(tol_ld, 4 * rel_err(g[f'{name}/ldinv'], g64[f'{name}/ldinv']))
+            assert tol_x < 20 * TOL[prec] and tol_ld < 20 * TOL[prec], name          # never looser than before
+        assert rel_err(xi, g[f'{name}/xinv']) < tol_x, (name, tol_x)
+        assert rel_err(ldi, g[f'{name}/ldinv']) < tol_ld, (name, tol_ld)
 
 
 def test_generic_autoregressive_flow_matches_packed_path():

@@ -96,8 +96,13 @@ class SweepPlan:
         self._dev = {}
 
     def _tables(self, maf, dtype, device, layouts):
-        key = (str(device), dtype)
+        # the part records hold raw pointers to the splines' domain tensors: re-derive them when those buffers change
+        dom = tuple((t.data_ptr(), t._version) for part in self.parts if part.kind == 'spline'
+                    for t in (part.spec.x0, part.spec.xf, part.spec._y0, part.spec._yf))
+        key = (str(device), dtype, dom)
         if key not in self._dev:
+            for stale in [k for k in self._dev if k[:2] == key[:2]]:
+                del self._dev[stale]
             recs = np.zeros(len(self.parts), dtype=PART_DTYPE)
             keep = []
             for i, (part, lay) in enumerate(zip(self.parts, layouts)):

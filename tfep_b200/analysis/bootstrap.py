@@ -267,12 +267,15 @@ def _bootstrap_statistics(data, statistic, n_resamples, sample_size, take_first_
     gen = torch.default_generator if generator is None else generator
     stats = torch.empty(n_resamples, dtype=data.dtype, device=data.device)
     state = _generator_to_state(gen).to(data.device) if rng == 'mt19937' else None
+    dev_gen = None
+    if rng == 'philox':        # the caller's generator seeds the device stream: reproducible, and its state advances
+        dev_gen = torch.Generator(device=data.device).manual_seed(int(torch.randint(0, 2**62, (1,), generator=generator).item()))
     for k in range(0, n_resamples, batch):
         nb = min(batch, n_resamples - k)
         if rng == 'mt19937':
             idx = _ops.mt19937_indices(state, nb * sample_size, max_idx).view(nb, sample_size).long()
         else:
-            idx = torch.randint(0, max_idx, (nb, sample_size), device=data.device)
+            idx = torch.randint(0, max_idx, (nb, sample_size), device=data.device, generator=dev_gen)
         expanded = data.expand((nb, *data.shape))
         if data.dim() > 1:
             idx = idx.unsqueeze(-1).expand(nb, sample_size, data.shape[1])

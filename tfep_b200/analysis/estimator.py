@@ -76,5 +76,15 @@ def fep_estimator(data, kT=1.0, weights=None, vectorized=False):
 
     if rows is None:
         return one(work, bias, weights)
+    if rows > 4:
+        # many rows (the generic-statistic route of bootstrap: `statistic(samples, vectorized=True)`): one batched
+        # reduction over the (rows, n) matrix instead of two kernel launches per row
+        v = -work / kT
+        if bias is not None:
+            v = v + torch.log_softmax(bias / kT, dim=-1)
+            return (-kT * torch.logsumexp(v, dim=-1)).to(work.dtype)
+        if weights is not None:
+            return (-kT * torch.logsumexp(v + torch.log(weights), dim=-1)).to(work.dtype)
+        return (-kT * (torch.logsumexp(v, dim=-1) - _log_n(work.shape[-1]))).to(work.dtype)
     return torch.stack([one(work[r], None if bias is None else bias[r], None if weights is None else weights[r])
                         for r in range(rows)])

@@ -90,9 +90,9 @@ class PeriodicEmbedding(MAFEmbedding):
         self.register_buffer('_nonperiodic_indices', all_idx[~torch.isin(all_idx, periodic_indices)])
         self.n_features_in = int(n_features_in)
         self.n_features_out = int(n_features_in + len(periodic_indices))
-        lim = self.limits.detach().double().cpu()
-        self._lower = float(lim[0])
-        self._scale = float(2 * math.pi / (lim[1] - lim[0]))
+        self._refresh_limits()
+        # `limits` is a buffer: a checkpoint built with other limits must change the constants the kernels receive
+        self.register_load_state_dict_post_hook(lambda module, incompatible_keys: module._refresh_limits())
         # per input column: first output column and whether it is lifted
         out_col = torch.empty(n_features_in, dtype=torch.int32)
         periodic = torch.zeros(n_features_in, dtype=torch.int32)
@@ -104,6 +104,12 @@ class PeriodicEmbedding(MAFEmbedding):
             periodic[c] = 1
         self._host_tables = (out_col, periodic)
         self._dev = {}
+
+    def _refresh_limits(self):
+        """Kernel constants of the lift, from the `limits` buffer (host floats: read once per change, not per call)."""
+        lim = self.limits.detach().double().cpu()
+        self._lower = float(lim[0])
+        self._scale = float(2 * math.pi / (lim[1] - lim[0]))
 
     def _tables(self, device):
         key = str(device)
