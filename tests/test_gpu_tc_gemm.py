@@ -93,7 +93,7 @@ def test_dual_pack_equals_the_separate_packs(rows, cols, t_rows):
     assert torch.equal(t3, _ops.tc_pack(wide[:, :cols].contiguous(), t_rows, transpose=True))
 
 
-@pytest.mark.parametrize('n_split,tol', [(2, 4e-5), (3, 5e-6)])
+@pytest.mark.parametrize('n_split,tol', [(2, 4e-5), (3, 1.5e-5)])
 @pytest.mark.parametrize('m,n,k', [(128, 256, 64), (1000, 670, 300), (257, 1650, 330), (5, 7, 9), (300, 512, 96)])
 def test_split_precision_products(m, n, k, n_split, tol):
     """x = x_0 + x_1 (+ x_2) in bf16 terms, products A_i B_j with i + j < n_split (3 or 6 MMAs per k-step): against the
