@@ -32,11 +32,18 @@ def _world(group):
 
 def combine_lse_partials(partial, group=None):
     """All-gather the ``(max, sum)`` pair of every rank and combine: returns ``(max, sum)`` of the union."""
-    if _world(group) == 1:
+    world = _world(group)
+    if world == 1:
         return partial[0], partial[1]
-    parts = [torch.empty_like(partial) for _ in range(_world(group))]
-    dist.all_gather(parts, partial.contiguous(), group=group)
-    return combine_partials(torch.stack(parts))
+    # one collective into one tensor (the call is latency bound: 16 bytes per rank)
+    parts = torch.empty((world, 2), dtype=partial.dtype, device=partial.device)
+    if partial.is_cuda:
+        dist.all_gather_into_tensor(parts, partial.contiguous(), group=group)
+    else:                                  # gloo (CPU tests) has no all_gather_into_tensor
+        chunks = list(parts.unbind(0))
+        dist.all_gather(chunks, partial.contiguous(), group=group)
+        parts = torch.stack(chunks)
+    return combine_partials(parts)
 
 
 def combine_bootstrap_sums(sums, local_ref, group=None):
