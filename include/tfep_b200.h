@@ -203,6 +203,38 @@ int tfepb_tc_pack_split(const float* src, int64_t ld, int32_t rows, int32_t k, i
  * t_block_rows = 128 / 256 (or NULL) and, if column_sums != NULL (zero-filled by the caller), += the sums over the rows. */
 int tfepb_tc_pack_dual(const float* src, int64_t ld, int32_t rows, int32_t cols, void* image, void* image_t,
                        int32_t t_block_rows, float* column_sums, tfepb_stream_t stream);
+/* Transformer fused into the epilogue of the OUTPUT-layer product of a MAF (AutoregressiveFlow.forward,
+ * nn/flows/autoregressive.py:144-177: parameters = conditioner(x); y, log_det = transformer(x, parameters)) so that the
+ * (batch x n_parameters) matrix never reaches memory.  The n output columns of the product are 16-column chunks; chunk q
+ * holds the parameters of units q * U .. q * U + U - 1, P consecutive columns per unit, pad columns after them:
+ *   TFEPB_TCTX_AFFINE   U = 8 features, P = 2 (shift, log_scale)                 affine.py:83-117
+ *   TFEPB_TCTX_SOS2     U = 3 features, P = 5 (a0, a10, a11, a20, a21), 1 pad    sos.py:163-268
+ *   TFEPB_TCTX_MOEBIUS3 U = 5 three-vectors, P = 3 (the vector w), 1 pad         moebius.py:120-260 (variants 0 / 1 of
+ *                                                                                tfepb_moebius' unit_sphere argument)
+ * (the caller permutes / pads the rows of the packed weight and bias; pad rows are zero).
+ * backward == 0: y[:, cols] = T(x[:, cols]; parameters), logdet[b] += log|det J| (atomic: zero-fill or carry the sum of
+ * earlier layers); the product needs no c / out_image.
+ * backward == 1: the product is recomputed, grad_x[:, cols] = direct term of the VJP, and the values handed to
+ * out_image / out_image_t / column_sums are the parameter cotangents (zero in pad columns): the operands of the
+ * backward-input and weight-gradient products of the output layer and its bias gradient (nn/masked.py:279-302). */
+#define TFEPB_TCTX_AFFINE 1
+#define TFEPB_TCTX_SOS2 2
+#define TFEPB_TCTX_MOEBIUS3 3
+typedef struct {
+    int32_t kind;                        /* TFEPB_TCTX_* */
+    int32_t backward;
+    int32_t n_units;                     /* features (3-vectors for Moebius) */
+    int32_t unit_sphere;                 /* Moebius: 0 sphere of radius |x|, 1 unit sphere */
+    double max_radius;                   /* Moebius */
+    const int32_t* cols;                 /* device (n_units * x columns per unit): columns of x / y of every unit */
+    const void* x; int64_t ldx;          /* fp32 */
+    void* y; int64_t ldy;                /* forward */
+    float* logdet;                       /* forward, or NULL */
+    const void* grad_y; int64_t ldgy;    /* backward */
+    const float* grad_logdet;            /* backward, or NULL (ignored by SOS: sos.py:233) */
+    void* grad_x; int64_t ldgx;          /* backward */
+} tfepb_tc_tx;
+
 typedef struct {
     const void* a_image; const void* b_image;
     int32_t m, n, k;
@@ -229,6 +261,8 @@ typedef struct {
                                             3 / 6 products A_i B_j with i + j < n_split in fp32 -- operands carried to
                                             16 / 24 significant bits (forward products only) */
     int32_t reserved;
+    const tfepb_tc_tx* tx;               /* NULL, or the transformer fused into the epilogue (n_split <= 1, no split_k,
+                                            n a multiple of 16, activation NONE, no aux) */
 } tfepb_tc_gemm_args;
 int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream);
 

@@ -91,12 +91,20 @@ class FusedInvArgs(Structure):
                 ('error_flag', c_void_p)]
 
 
+class TcTx(Structure):
+    _fields_ = [('kind', c_int32), ('backward', c_int32), ('n_units', c_int32), ('unit_sphere', c_int32),
+                ('max_radius', c_double), ('cols', c_void_p), ('x', c_void_p), ('ldx', c_int64), ('y', c_void_p),
+                ('ldy', c_int64), ('logdet', c_void_p), ('grad_y', c_void_p), ('ldgy', c_int64), ('grad_logdet', c_void_p),
+                ('grad_x', c_void_p), ('ldgx', c_int64)]
+
+
 class TcGemmArgs(Structure):
     _fields_ = [('a_image', c_void_p), ('b_image', c_void_p), ('m', c_int32), ('n', c_int32), ('k', c_int32),
                 ('activation', c_int32), ('c', c_void_p), ('ldc', c_int64), ('bias', c_void_p), ('aux', c_void_p),
                 ('ldaux', c_int64), ('out_image', c_void_p), ('k_block_ranges', c_void_p), ('split_k', c_int32),
                 ('out_image_t_rows', c_int32), ('error_flag', c_void_p), ('row_ranges', c_void_p),
-                ('out_image_t', c_void_p), ('column_sums', c_void_p), ('n_split', c_int32), ('reserved', c_int32)]
+                ('out_image_t', c_void_p), ('column_sums', c_void_p), ('n_split', c_int32), ('reserved', c_int32),
+                ('tx', POINTER(TcTx))]
 
 
 class CentroidArgs(Structure):

@@ -411,12 +411,42 @@ def tc_pack_dual(src, t_block_rows=None, column_sums=False, image=True):
     return img, img_t, sums
 
 
+TCTX_KINDS = {'affine': 1, 'sos': 2, 'moebius': 3}
+TCTX_UNITS_PER_CHUNK = {'affine': 8, 'sos': 3, 'moebius': 5}       # units per 16-column chunk (tfepb_tc_tx)
+TCTX_COLUMNS_PER_UNIT = {'affine': 2, 'sos': 5, 'moebius': 3}
+
+
+class TcTx:
+    """The transformer fused into the epilogue of an output-layer product (tfepb_tc_tx).  ``cols``: int32 device tensor,
+    the x / y columns of every unit in chunk order.  Forward: ``y`` / ``logdet`` (accumulated into); backward:
+    ``grad_y``, ``grad_logdet`` (or None), ``grad_x``."""
+
+    def __init__(self, kind, cols, x, *, y=None, logdet=None, grad_y=None, grad_logdet=None, grad_x=None,
+                 max_radius=0.0, unit_sphere=0):
+        self.kind, self.cols, self.x = kind, cols, x
+        self.y, self.logdet, self.grad_y, self.grad_logdet, self.grad_x = y, logdet, grad_y, grad_logdet, grad_x
+        self.max_radius, self.unit_sphere = float(max_radius), int(unit_sphere)
+        self.backward = grad_x is not None
+
+    def struct(self):
+        xcols = 3 if self.kind == 'moebius' else 1
+        opt = lambda t: None if t is None else t.data_ptr()
+        ld = lambda t: 0 if t is None else _ld(t)
+        return _lib.TcTx(kind=TCTX_KINDS[self.kind], backward=int(self.backward), n_units=self.cols.numel() // xcols,
+                         unit_sphere=self.unit_sphere, max_radius=self.max_radius, cols=self.cols.data_ptr(),
+                         x=self.x.data_ptr(), ldx=_ld(self.x), y=opt(self.y), ldy=ld(self.y), logdet=opt(self.logdet),
+                         grad_y=opt(self.grad_y), ldgy=ld(self.grad_y), grad_logdet=opt(self.grad_logdet),
+                         grad_x=opt(self.grad_x), ldgx=ld(self.grad_x))
+
+
 def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, aux=None, out_image=False,
-            k_block_ranges=None, row_ranges=None, split_k=1, error_flag=None, out_image_t=None, column_sums=False, n_split=1):
+            k_block_ranges=None, row_ranges=None, split_k=1, error_flag=None, out_image_t=None, column_sums=False, n_split=1,
+            tx=None):
     """C = act(A B^T + bias) [* ELU'(aux)] from operand images; returns (c, out_img).  ``c``: True to allocate, a
     tensor to write into (zero-filled by the caller when split_k > 1), None for no fp32 output.
     ``out_image_t`` = 128 / 256: also the image of the transposed result with that block_rows; ``column_sums``: also
-    the sums over the m rows; with either, returns (c, out_img, out_img_t, column_sums)."""
+    the sums over the m rows; with either, returns (c, out_img, out_img_t, column_sums).  ``tx``: a :class:`TcTx`, the
+    transformer applied by the epilogue (the columns are then parameter chunks, see tfepb_tc_tx)."""
     lib = _lib.load()
     dev = a_img.device
     if c is True:
@@ -440,6 +470,9 @@ def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, au
                         row_ranges=None if row_ranges is None else row_ranges.data_ptr(),
                         out_image_t=None if img_t is None else img_t.data_ptr(),
                         column_sums=None if sums is None else sums.data_ptr(), n_split=int(n_split), reserved=0)
+    if tx is not None:
+        txs = tx.struct()                 # kept alive until the launch returns
+        a.tx = ctypes.pointer(txs)
     with torch.cuda.device(dev):
         check(lib.tfepb_tc_gemm(ctypes.byref(a), stream_ptr(a_img)))
     if out_image_t or column_sums:
@@ -493,41 +526,126 @@ class MadeFunctionTC(torch.autograd.Function):
         L = ctx.n_layers
         saved = ctx.saved_tensors
         acts, ws = saved[:L], saved[L:]
-        B = grad_out.shape[0]
         g = _rows(grad_out.contiguous())
         # image of g, image of g^T (A operand of the weight gradient) and the bias gradient: one pass over grad_out for the
         # top layer, written by the epilogue of the backward-input product for the layers below
         top = ctx.needs_input_grad[5 + L - 1] or ctx.needs_input_grad[5 + 2 * L - 1]
         gimg, gimg_t, gb = tc_pack_dual(g, 128 if top else None, column_sums=top)
-        gws, gbs = [None] * L, [None] * L
-        gx = None
-        n_sm = torch.cuda.get_device_properties(g.device).multi_processor_count
-        for l in range(L - 1, -1, -1):
-            N, K = ws[l].shape
-            if ctx.needs_input_grad[5 + l] or ctx.needs_input_grad[5 + L + l]:
-                # dW[N x K] = dY^T X: reduction over the batch, split so that the grid fills the machine
-                tiles = ((N + 127) // 128) * ((K + 255) // 256)
-                split = max(1, min((B + 63) // 64, (2 * n_sm + tiles - 1) // tiles))
-                a_t = gimg_t if gimg_t is not None else tc_pack(g, 128, transpose=True)
-                b_t = ctx.acts_t[l] if ctx.acts_t[l] is not None else tc_pack(acts[l], 256, transpose=True)
-                gws[l], _ = tc_gemm(a_t, b_t, N, K, B, c=True, split_k=split,
-                                    row_ranges=None if ctx.rr_w is None else ctx.rr_w[l])
-                gbs[l] = gb if gb is not None else g.sum(dim=0)
-            gimg_t, gb = None, None
-            if l > 0 or ctx.needs_input_grad[0]:
-                wt = tc_pack(ws[l], 256, transpose=True)            # rows = inputs of the layer, k = its outputs
-                below = l > 0 and (ctx.needs_input_grad[5 + l - 1] or ctx.needs_input_grad[5 + L + l - 1])
-                if below:
-                    g, gimg, gimg_t, gb = tc_gemm(gimg, wt, B, K, N, c=True, aux=acts[l], out_image=True, out_image_t=128,
-                                                  column_sums=True,
-                                                  k_block_ranges=None if ctx.kb_bwd is None else ctx.kb_bwd[l])
-                else:
-                    g, gimg = tc_gemm(gimg, wt, B, K, N, c=True, aux=acts[l] if l > 0 else None, out_image=l > 0,
-                                      k_block_ranges=None if ctx.kb_bwd is None else ctx.kb_bwd[l])
-                if l == 0:
-                    gx = g
+        need_w = [ctx.needs_input_grad[5 + l] or ctx.needs_input_grad[5 + L + l] for l in range(L)]
+        gx, gws, gbs = _made_tc_backward_layers(acts, ctx.acts_t, ws, ctx.kb_bwd, ctx.rr_w, need_w, ctx.needs_input_grad[0],
+                                                g, gimg, gimg_t, gb)
         ctx.acts_t = None
         return (gx, None, None, None, None, *gws, *gbs)
+
+
+def _made_tc_backward_layers(acts, acts_t, ws, kb_bwd, rr_w, need_w, need_x, g, gimg, gimg_t, gb):
+    """Backward pass of the layers of a MADE on the tensor cores, given the cotangent of the output layer's result as
+    operand images (``gimg``: A operand of the backward-input product; ``gimg_t``: A operand of the weight gradient, or
+    None -> packed from the fp32 ``g``; ``gb``: its column sums, or None).  Returns (grad_x or None, grad_ws, grad_bs)."""
+    L = len(ws)
+    B = acts[0].shape[0]
+    gws, gbs = [None] * L, [None] * L
+    gx = None
+    n_sm = torch.cuda.get_device_properties(acts[0].device).multi_processor_count
+    for l in range(L - 1, -1, -1):
+        N, K = ws[l].shape
+        if need_w[l]:
+            # dW[N x K] = dY^T X: reduction over the batch, split so that the grid fills the machine
+            tiles = ((N + 127) // 128) * ((K + 255) // 256)
+            split = max(1, min((B + 63) // 64, (2 * n_sm + tiles - 1) // tiles))
+            a_t = gimg_t if gimg_t is not None else tc_pack(g, 128, transpose=True)
+            b_t = acts_t[l] if acts_t[l] is not None else tc_pack(acts[l], 256, transpose=True)
+            gws[l], _ = tc_gemm(a_t, b_t, N, K, B, c=True, split_k=split, row_ranges=None if rr_w is None else rr_w[l])
+            gbs[l] = gb if gb is not None else g.sum(dim=0)
+        gimg_t, gb = None, None
+        if l > 0 or need_x:
+            wt = tc_pack(ws[l], 256, transpose=True)            # rows = inputs of the layer, k = its outputs
+            below = l > 0 and need_w[l - 1]
+            if below:
+                g, gimg, gimg_t, gb = tc_gemm(gimg, wt, B, K, N, c=True, aux=acts[l], out_image=True, out_image_t=128,
+                                              column_sums=True, k_block_ranges=None if kb_bwd is None else kb_bwd[l])
+            else:
+                g, gimg = tc_gemm(gimg, wt, B, K, N, c=True, aux=acts[l] if l > 0 else None, out_image=l > 0,
+                                  k_block_ranges=None if kb_bwd is None else kb_bwd[l])
+            if l == 0:
+                gx = g
+    return gx, gws, gbs
+
+
+class MadeTxFunctionTC(torch.autograd.Function):
+    """(y, log_det) = transformer(x, MADE(x)) with the transformer fused into the output-layer product (tfepb_tc_tx): the
+    conditioner output is never written.  ``ws[-1]`` / ``bs[-1]`` are the output layer in the padded chunk layout of the
+    transformer kind (tfep_b200/_txfused.py), the range tables of that layer refer to the same layout.  Backward: the
+    output-layer product is recomputed from the saved image of the last hidden activation and its epilogue emits the
+    parameter cotangents as the operand images of the two products below (no fp32 cotangent matrix either), then the
+    layers follow as in :class:`MadeFunctionTC`."""
+
+    @staticmethod
+    def forward(ctx, x, n_layers, kb_fwd, kb_bwd, rr_w, spec, *wb):
+        ws, bs = wb[:n_layers], wb[n_layers:]
+        L = n_layers
+        B = x.shape[0]
+        train = any(ctx.needs_input_grad[6:6 + 2 * L])
+        img, x_t, _ = tc_pack_dual(x, 256 if train else None)
+        acts, acts_t = [x], [x_t]
+        for l in range(L - 1):
+            N, K = ws[l].shape
+            wimg = tc_pack(ws[l], 256)
+            if train:
+                h, img, img_t, _ = tc_gemm(img, wimg, B, N, K, c=True, bias=bs[l], activation=ACT_ELU, out_image=True,
+                                           out_image_t=256, k_block_ranges=None if kb_fwd is None else kb_fwd[l])
+            else:
+                need_h = ctx.needs_input_grad[0]                 # only grad_x wanted: ELU' still needs h
+                h, img = tc_gemm(img, wimg, B, N, K, c=True if need_h else None, bias=bs[l], activation=ACT_ELU,
+                                 out_image=True, k_block_ranges=None if kb_fwd is None else kb_fwd[l])
+                img_t = None
+            acts.append(h)
+            acts_t.append(img_t)
+        N, K = ws[-1].shape
+        y = torch.empty_like(x)
+        logdet = torch.zeros(B, dtype=torch.float32, device=x.device)
+        tc_gemm(img, tc_pack(ws[-1], 256), B, N, K, bias=bs[-1], k_block_ranges=None if kb_fwd is None else kb_fwd[-1],
+                tx=TcTx(spec['kind'], spec['cols'], x, y=y, logdet=logdet, max_radius=spec['max_radius'],
+                        unit_sphere=spec['unit_sphere']))
+        keep = any(ctx.needs_input_grad)
+        ctx.save_for_backward(*[a for a in acts if a is not None], *ws, bs[-1], *([img] if keep else []))
+        ctx.have_acts = [a is not None for a in acts]
+        ctx.acts_t = acts_t if keep else None
+        ctx.meta = (L, kb_fwd, kb_bwd, rr_w, spec)
+        if spec['kind'] == 'sos':
+            ctx.mark_non_differentiable(logdet)                  # the reference's SOS log-det carries no gradient (sos.py:233)
+        return y, logdet
+
+    @staticmethod
+    def backward(ctx, grad_y, grad_ld):
+        L, kb_fwd, kb_bwd, rr_w, spec = ctx.meta
+        saved = list(ctx.saved_tensors)
+        acts = [saved.pop(0) if have else None for have in ctx.have_acts]
+        ws, b_last, last_img = saved[:L], saved[L], saved[L + 1]
+        x = acts[0]
+        B = x.shape[0]
+        grad_y = torch.zeros_like(x) if grad_y is None else _rows(grad_y.contiguous())
+        if grad_ld is not None:
+            grad_ld = grad_ld.contiguous()
+        need_w = [ctx.needs_input_grad[6 + l] or ctx.needs_input_grad[6 + L + l] for l in range(L)]
+        gx = torch.empty_like(x)
+        N, K = ws[-1].shape
+        _, gimg, gimg_t, gb = tc_gemm(last_img, tc_pack(ws[-1], 256), B, N, K, bias=b_last, out_image=True,
+                                      out_image_t=128 if need_w[-1] else None, column_sums=True,
+                                      k_block_ranges=None if kb_fwd is None else kb_fwd[-1],
+                                      tx=TcTx(spec['kind'], spec['cols'], x, grad_y=grad_y, grad_logdet=grad_ld, grad_x=gx,
+                                              max_radius=spec['max_radius'], unit_sphere=spec['unit_sphere']))
+        gx_made, gws, gbs = _made_tc_backward_layers(acts, ctx.acts_t, ws, kb_bwd, rr_w, need_w, ctx.needs_input_grad[0],
+                                                     None, gimg, gimg_t, gb)
+        ctx.acts_t = None
+        if gx_made is not None:
+            gx += gx_made
+        return (gx if ctx.needs_input_grad[0] else None, None, None, None, None, None, *gws, *gbs)
+
+
+def made_tx_forward_tc(x, weights, biases, kb_fwd, kb_bwd, rr_w, spec):
+    """See :class:`MadeTxFunctionTC`; ``spec``: dict(kind, cols, max_radius, unit_sphere)."""
+    return MadeTxFunctionTC.apply(x, len(weights), kb_fwd, kb_bwd, rr_w, spec, *weights, *biases)
 
 
 def made_forward_tc(x, weights, biases, kb_fwd=None, kb_bwd=None, rr_w=None, n_split=1, weight_images=None):

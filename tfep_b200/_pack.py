@@ -80,6 +80,19 @@ class MadePlan:
                                        [p.to(device) for p in self.perms])
         return self._device_cache[key]
 
+    @staticmethod
+    def tc_ranges_of_mask(mask, device):
+        """(forward k-block ranges, backward-input k-block ranges, weight-gradient row ranges) of one masked layer for the
+        tensor-core GEMM; see :meth:`tc_ranges`.  ``mask``: (outputs, inputs) bool."""
+        out = []
+        for m in (mask, mask.t()):
+            r = _ranges(m, 256, axis=0)                    # per 256-row tile: bounding column range
+            kb = torch.stack([r[:, 0] // 64, (r[:, 1] + 63) // 64], dim=1).to(torch.int32)
+            out.append(kb.contiguous().to(device))
+        # weight gradient (rows = outputs, tiles of 256 input columns): rows the mask leaves non-zero per tile
+        out.append(_ranges(mask, 256, axis=1).contiguous().to(device))
+        return tuple(out)
+
     def tc_ranges(self, device):
         """Per layer, for the tensor-core GEMM (tiles of 256 output columns, k-blocks of 64): the non-zero k-block
         range [first, end) of every tile, forward (tiles over the layer's outputs, k over its inputs) and backward
@@ -92,12 +105,10 @@ class MadePlan:
                 d_in, d_out = self.packed_degrees[l], self.packed_degrees[l + 1]
                 strict = l == self.n_layers - 1
                 mask = (d_out[:, None] > d_in[None, :]) if strict else (d_out[:, None] >= d_in[None, :])
-                for m, dst in ((mask, fwd), (mask.t(), bwd)):
-                    r = _ranges(m, 256, axis=0)                    # per 256-row tile: bounding column range
-                    kb = torch.stack([r[:, 0] // 64, (r[:, 1] + 63) // 64], dim=1).to(torch.int32)
-                    dst.append(kb.contiguous().to(device))
-                # weight gradient (rows = outputs, tiles of 256 input columns): rows the mask leaves non-zero per tile
-                roww.append(_ranges(mask, 256, axis=1).contiguous().to(device))
+                f, b, r = self.tc_ranges_of_mask(mask, device)
+                fwd.append(f)
+                bwd.append(b)
+                roww.append(r)
             self._device_cache[key] = (fwd, bwd, roww)
         return self._device_cache[key]
 

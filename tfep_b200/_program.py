@@ -88,9 +88,13 @@ class ProgramFunction(torch.autograd.Function):
             raise NotImplementedError('tfep_b200: gradients through the inverse direction are not implemented')
         dev = x.device
         grad_y = torch.zeros_like(x) if grad_y is None else grad_y.contiguous()
-        gx = grad_y.clone() if passthrough else torch.zeros_like(x)
-        gpar = torch.zeros((par.shape[0], par.stride(0) if par.shape[0] > 1 else par.shape[1]), dtype=par.dtype,
-                           device=par.device)[:, :par.shape[1]]    # same leading dimension as par (possibly a padded view)
+        # every kernel writes all the entries it owns: zero-fill only what no part covers (without passthrough the parts
+        # map every column of x, as in forward where y starts uninitialised)
+        gx = grad_y.clone() if passthrough else torch.empty_like(x)
+        covered = n_parameters(parts) == par.shape[1]
+        gpar = (torch.empty if covered else torch.zeros)(
+            (par.shape[0], par.stride(0) if par.shape[0] > 1 else par.shape[1]), dtype=par.dtype,
+            device=par.device)[:, :par.shape[1]]    # same leading dimension as par (possibly a padded view)
         for part, layout in zip(parts, layouts):
             _ops.transformer_vjp(part.kind, part.spec, x, par, layout, part.n_features, grad_y, grad_ld,
                                  cols=part.cols_on(dev), grad_x=gx, grad_par=gpar)

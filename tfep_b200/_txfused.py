@@ -1,0 +1,109 @@
+"""Transformer fused into the output-layer product of the tensor-core conditioner (``precision='bf16'``; tfepb_tc_tx).
+
+For a MAF whose transformer is ONE elementary kernel of kind affine / SOS with two polynomials / Moebius on 3-vectors over
+all features, the reference's ``parameters = conditioner(x); y, log_det = transformer(x, parameters)``
+(nn/flows/autoregressive.py:144-177) runs as: hidden layers on tfepb_tc_gemm, then the output-layer product whose
+epilogue applies the transformer to the accumulators -- the (batch x n_parameters) matrix, the largest tensor of the
+layer, is neither written nor read, forward or backward (``_ops.MadeTxFunctionTC``).
+
+The epilogue wants the parameters of whole units inside 16-column chunks (8 affine features x 2, 3 SOS features x 5 + 1 pad
+column, 5 Moebius vectors x 3 + 1 pad column).  This module derives that layout from the degree-sorted feature-major packing
+of ``MAF._pack`` (units stay in degree order, so the staircase ranges survive): the row index map of the padded output
+layer, the x / y columns of every unit and the k-block / row ranges of the padded layer.
+"""
+
+import torch
+
+from . import _ops
+from ._pack import MadePlan
+
+
+def eligibility(maf, pk):
+    """None if the fused epilogue covers the layer, else the reason (a string)."""
+    if pk is False:
+        return 'the transformer is not a native program'
+    if maf._n_conditioner_indices > 0 or maf.has_fixed_indices:
+        return 'conditioning / fixed features'
+    if maf._embedding is not None:
+        return 'the conditioner input goes through an embedding'
+    parts = pk['parts']
+    if len(parts) != 1:
+        return 'mixed transformer'
+    part = parts[0]
+    if part.n_features != len(maf._degrees_in_host) or sorted(part.x_columns().tolist()) != list(range(part.n_features)):
+        return 'the transformer does not map every feature'
+    if part.kind == 'affine':
+        pass
+    elif part.kind == 'sos':
+        if part.spec.n_polynomials != 2:
+            return 'SOS transformer with more than two polynomials'
+    elif part.kind == 'moebius':
+        if part.spec.dimension != 3 or part.spec.unit_sphere not in (0, 1):
+            return 'Moebius transformer other than 3-vectors (plain variants)'
+        base = pk['bases'][0].long()
+        b3 = base.view(-1, 3)
+        if not (torch.equal(b3[:, 1], b3[:, 0] + 1) and torch.equal(b3[:, 2], b3[:, 0] + 2) and bool((b3[:, 0] % 3 == 0).all())):
+            return 'the features of a Moebius vector are not consecutive in degree order'
+    else:
+        return f'transformer kind {part.kind!r}'
+    if pk['plan'].n_layers < 2:
+        return 'conditioner without hidden layers'
+    return None
+
+
+class TcTxPlan:
+    """Padded chunk layout of the output layer of ``maf`` and the tables of the fused epilogue."""
+
+    def __init__(self, maf, pk):
+        part = pk['parts'][0]
+        plan = pk['plan']
+        self.kind = part.kind
+        upc, ppu = _ops.TCTX_UNITS_PER_CHUNK[self.kind], _ops.TCTX_COLUMNS_PER_UNIT[self.kind]
+        n_rows = part.n_features * part.n_params                 # rows of the packed output layer
+        assert n_rows == len(plan.perms[-1])
+        n_units = n_rows // ppu
+        n_chunks = (n_units + upc - 1) // upc
+        self.n_padded = n_chunks * 16
+        # padded row -> packed row (n_rows = the appended zero row): units are consecutive runs of `ppu` packed rows
+        t = torch.arange(self.n_padded)
+        within, chunk = t % 16, t // 16
+        src = chunk * (upc * ppu) + within
+        valid = (within < upc * ppu) & (src < n_rows)
+        self.row_map = torch.where(valid, src, torch.full_like(src, n_rows))
+        # x / y columns of every unit, in unit (= packed) order
+        base = pk['bases'][0].long()
+        xcols = part.x_columns().long()
+        if self.kind == 'moebius':
+            order = torch.argsort(base.view(-1, 3)[:, 0])
+            self.cols = xcols.view(-1, 3)[order].reshape(-1).to(torch.int32)
+        else:
+            order = torch.argsort(base)
+            self.cols = xcols[order].to(torch.int32)
+        assert torch.equal(base[order] if self.kind != 'moebius' else base.view(-1, 3)[order, 0],
+                           torch.arange(n_units) * ppu)
+        # staircase ranges of the padded layer: pad rows are all-zero rows of the mask
+        d_in = plan.packed_degrees[plan.n_layers - 1]
+        d_out = torch.cat([plan.packed_degrees[plan.n_layers], torch.tensor([-(1 << 30)])])[self.row_map]
+        self.mask = (d_out[:, None] > d_in[None, :]) & valid[:, None]
+        self.max_radius = float(getattr(part.spec, 'max_radius', 0.0))
+        self.unit_sphere = int(getattr(part.spec, 'unit_sphere', 0))
+        self._dev = {}
+
+    def tables(self, plan, device):
+        key = str(device)
+        if key not in self._dev:
+            fwd, bwd, roww = plan.tc_ranges(device)
+            f, b, r = MadePlan.tc_ranges_of_mask(self.mask, device)
+            self._dev[key] = (fwd[:-1] + [f], bwd[:-1] + [b], roww[:-1] + [r], self.row_map.to(device),
+                              dict(kind=self.kind, cols=self.cols.to(device), max_radius=self.max_radius,
+                                   unit_sphere=self.unit_sphere))
+        return self._dev[key]
+
+    def forward(self, maf, pk, x):
+        plan = pk['plan']
+        kb_fwd, kb_bwd, rr_w, row_map, spec = self.tables(plan, x.device)
+        pw, pb = maf._conditioner.packed_weights(plan)
+        w, b = pw[-1], pb[-1]
+        w_pad = torch.cat([w, w.new_zeros(1, w.shape[1])]).index_select(0, row_map)
+        b_pad = torch.cat([b, b.new_zeros(1)]).index_select(0, row_map)
+        return _ops.made_tx_forward_tc(x, list(pw[:-1]) + [w_pad], list(pb[:-1]) + [b_pad], kb_fwd, kb_bwd, rr_w, spec)

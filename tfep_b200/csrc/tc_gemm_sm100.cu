@@ -26,8 +26,17 @@
 // cross terms are below 2^-16 / 2^-24 of the product -- into the same fp32 accumulator.  A ring stage then holds half a
 // k-block (32 k) of all images of both operands; the epilogue splits the activations it hands to the next layer the
 // same way.
+//
+// FUSED TRANSFORMER (tfepb_tc_tx; the output layer of a MAF whose transformer is affine / SOS (2 polynomials) / Moebius on
+// 3-vectors): the output columns are laid out in 16-column chunks that hold the parameters of 8 / 3 / 5 whole units (the
+// caller pads the packed weight rows accordingly), so the 16 accumulator values an epilogue thread reads are complete
+// parameter sets of its sample.  Forward: the thread applies the transformer to its row of x, writes y and adds the
+// log-det -- the (batch x parameters) matrix never exists in memory.  Backward: the same product is recomputed and the
+// epilogue replaces the parameters by their cotangents (tx_math.cuh VJPs) before the usual image / transposed image /
+// column-sum outputs, i.e. it emits grad_parameters directly as the bf16 operands of the two products below it.
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include "tx_math.cuh"
 
 namespace tfepb {
 namespace tcg {
@@ -60,7 +69,135 @@ struct Params {
     int k_chunk_blocks;                 // split-K: k-blocks per blockIdx.y slice, 0 = no split
     int tiles_m, tiles_n;
     int* error;
+    // fused transformer (TX != 0)
+    int tx_units, tx_unit_sphere;
+    float tx_max_radius;
+    const int* tx_cols;
+    const float* tx_x; int64_t tx_ldx;
+    float* tx_y; int64_t tx_ldy;
+    float* tx_logdet;
+    const float* tx_gy; int64_t tx_ldgy;
+    const float* tx_gl;
+    float* tx_gx; int64_t tx_ldgx;
 };
+
+// TX template argument: 0 = plain product, else 2 * kind + backward with kind = TFEPB_TCTX_*
+__host__ __device__ constexpr int tx_kind(int TX) { return TX >> 1; }
+__host__ __device__ constexpr bool tx_bwd(int TX) { return (TX & 1) != 0; }
+
+template <int TX> struct TxGeo {
+    static constexpr int KIND = tx_kind(TX);
+    static constexpr int UPC = KIND == TFEPB_TCTX_AFFINE ? 8 : KIND == TFEPB_TCTX_SOS2 ? 3 : 5;     // units per 16-column chunk
+    static constexpr int PPU = KIND == TFEPB_TCTX_AFFINE ? 2 : KIND == TFEPB_TCTX_SOS2 ? 5 : 3;     // parameter columns per unit
+    static constexpr int XPU = KIND == TFEPB_TCTX_MOEBIUS3 ? 3 : 1;                                // x columns per unit
+    static constexpr int XPC = UPC * XPU;                                                          // x columns per chunk
+    // chunks per staging group of the transposition buffer (32 columns): forward x only, backward x and grad_y (and the
+    // buffer is needed again for the transposed image after every sub-tile of two chunks)
+    static constexpr int GF = 4 * XPC <= 32 ? 4 : 2;
+    static constexpr int GB = 4 * XPC <= 32 ? 2 : 1;
+};
+
+// The epilogue thread owns one ROW (sample) but row-major x / y want a warp instruction to cover a row segment: the
+// columns cols[c0 .. c0 + XC) of the warp's 32 rows travel through buf[column][row] (pitch XP_LD).  A warp instruction
+// covers 32 / CW rows x CW columns (CW = XC rounded up to a power of two).
+template <int XC>
+__device__ __forceinline__ void tx_stage_in(const float* __restrict__ src, int64_t ld, int gm0, int M, const int* __restrict__ cols,
+                                            int c0, int cn, float* buf, int lane) {
+    constexpr int CW = XC <= 4 ? 4 : XC <= 8 ? 8 : XC <= 16 ? 16 : 32;
+    const int c = lane % CW, r0 = lane / CW;
+    if (c < XC) {
+        const int col = c0 + c < cn ? __ldg(cols + c0 + c) : -1;
+#pragma unroll
+        for (int r = r0; r < 32; r += 32 / CW)
+            buf[c * XP_LD + r] = (col >= 0 && gm0 + r < M) ? __ldg(src + (int64_t)(gm0 + r) * ld + col) : 0.f;
+    }
+}
+
+template <int XC>
+__device__ __forceinline__ void tx_stage_out(float* __restrict__ dst, int64_t ld, int gm0, int M, const int* __restrict__ cols,
+                                             int c0, int cn, const float* buf, int lane) {
+    constexpr int CW = XC <= 4 ? 4 : XC <= 8 ? 8 : XC <= 16 ? 16 : 32;
+    const int c = lane % CW, r0 = lane / CW;
+    if (c < XC && c0 + c < cn) {
+        const int col = __ldg(cols + c0 + c);
+#pragma unroll
+        for (int r = r0; r < 32; r += 32 / CW)
+            if (gm0 + r < M) dst[(int64_t)(gm0 + r) * ld + col] = buf[c * XP_LD + r];
+    }
+}
+
+// One 16-column chunk of one row: v holds the parameters (bias added) of the chunk's units; xs / gs: the staged x (and, for
+// the backward direction, grad_y) columns of the chunk, [column][row].  Forward: y replaces x in its slot, the log-det is
+// accumulated.  Backward: grad_x replaces grad_y in its slot and v becomes the parameter cotangents (zeros in pad columns,
+// for units beyond n_units and for rows beyond M).
+template <int TX>
+__device__ __forceinline__ void tx_chunk(const Params& p, float (&v)[16], float* xs, float* gs, int lane, float gl, bool row_ok,
+                                         int chunk, float& ld_acc) {
+    using G = TxGeo<TX>;
+    constexpr int KIND = G::KIND, UPC = G::UPC, PPU = G::PPU;
+    constexpr bool BWD = tx_bwd(TX);
+#pragma unroll
+    for (int j = 0; j < UPC; ++j) {
+        const int u = chunk * UPC + j;
+        const bool on = row_ok && u < p.tx_units;
+        if (on) {
+            if constexpr (KIND == TFEPB_TCTX_MOEBIUS3) {
+                float x3[3], w3[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    x3[i] = xs[(3 * j + i) * XP_LD + lane];
+                    w3[i] = v[3 * j + i];
+                }
+                if constexpr (!BWD) {
+                    float y3[3];
+                    ld_acc += moebius_eval<float>(x3, 1, w3, 1, 1.f, 3, p.tx_max_radius, p.tx_unit_sphere != 0, y3, 1);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) xs[(3 * j + i) * XP_LD + lane] = y3[i];
+                } else {
+                    float gy3[3], gx3[3], gv3[3];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) gy3[i] = gs[(3 * j + i) * XP_LD + lane];
+                    moebius_vjp<float>(x3, 1, w3, 1, 3, p.tx_max_radius, p.tx_unit_sphere != 0, gy3, 1, gl, gx3, 1, gv3, 1);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        gs[(3 * j + i) * XP_LD + lane] = gx3[i];
+                        v[3 * j + i] = gv3[i];
+                    }
+                }
+            } else {
+                const float x = xs[j * XP_LD + lane];
+                float par[PPU];
+#pragma unroll
+                for (int i = 0; i < PPU; ++i) par[i] = v[PPU * j + i];
+                if constexpr (!BWD) {
+                    float y, ld;
+                    if constexpr (KIND == TFEPB_TCTX_SOS2) sos_eval<float>(ParIn<float>{par, 1}, 2, x, y, ld);
+                    else affine_eval<float, false>(ParIn<float>{par, 1}, x, y, ld);
+                    xs[j * XP_LD + lane] = y;
+                    ld_acc += ld;
+                } else {
+                    const float gy = gs[j * XP_LD + lane];
+                    float gx, gpar[PPU];
+                    if constexpr (KIND == TFEPB_TCTX_SOS2) {
+                        sos_vjp<float>(ParIn<float>{par, 1}, 2, x, gy, gx, ParOut<float>{gpar, 1});     // no log-det cotangent (sos.py:233)
+                    } else {
+                        affine_vjp<float>(ParIn<float>{par, 1}, x, gy, gl, gx, ParOut<float>{gpar, 1});
+                    }
+                    gs[j * XP_LD + lane] = gx;
+#pragma unroll
+                    for (int i = 0; i < PPU; ++i) v[PPU * j + i] = gpar[i];
+                }
+            }
+        } else if constexpr (BWD) {
+#pragma unroll
+            for (int i = 0; i < PPU; ++i) v[PPU * j + i] = 0.f;
+        }
+    }
+    if constexpr (BWD && UPC * PPU < 16) {
+#pragma unroll
+        for (int i = UPC * PPU; i < 16; ++i) v[i] = 0.f;
+    }
+}
 
 struct Smem {
     uint64_t full[MAX_STAGES], empty[MAX_STAGES];
@@ -87,14 +224,15 @@ template <int NSPLIT> struct Geo {
     static constexpr int PARTS = KB / KS;                              // stages per k-block
 };
 
-template <int NSPLIT>
+template <int NSPLIT, int TX = 0>
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_constant__ Params p) {
     using G = Geo<NSPLIT>;
     constexpr int STAGES = G::N_STAGES, STAGE_BYTES = G::STAGE;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* ring = smem_raw;
     float* xpose = reinterpret_cast<float*>(ring + (size_t)STAGES * STAGE_BYTES);
-    Smem* sm = reinterpret_cast<Smem*>(xpose + EPI_WARPS * XP_FLOATS);
+    float* bias_s = xpose + EPI_WARPS * XP_FLOATS;                 // per epilogue warp: the bias of its 64 columns
+    Smem* sm = reinterpret_cast<Smem*>(bias_s + EPI_WARPS * 64);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_tiles = p.tiles_m * p.tiles_n;
 
@@ -212,154 +350,238 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             int k0, k1;
             krange(tn, k0, k1);
             const uint32_t buf = tcount & 1;
-            mbar_wait(&sm->acc_full[buf], (tcount >> 1) & 1, p.error, 4);
-            tc_fence_after();
-            // Every warp owns 32 rows (its TMEM lane quadrant) x 64 columns, processed as two sub-tiles of 32 columns
-            // that go through a per-warp transposition buffer: a thread holds one ROW of the accumulator, but global
-            // memory wants a warp instruction to cover one row segment (128 contiguous bytes), both for the ELU'
-            // operand coming in and for the fp32 result going out.
+            // Every warp owns 32 rows (its TMEM lane quadrant) x 64 columns = four chunks of 16 columns, processed as two
+            // sub-tiles of 32 columns that go through a per-warp transposition buffer: a thread holds one ROW of the
+            // accumulator, but global memory wants a warp instruction to cover one row segment (128 contiguous bytes), both
+            // for the ELU' operand coming in and for the fp32 result going out.
             float* xp = xpose + ew * XP_FLOATS;
+            float* bias_w = bias_s + ew * 64;
             const int gm0 = tm * BM + (warp & 3) * 32;         // first row of this warp
             const int gm = gm0 + lane;
             const bool row_ok = gm < p.M;
             const bool empty = k1 <= k0;                       // nothing was accumulated: the tile is all zeros
+            const int gnw = tn * BN + cgroup * 64;             // first column of this warp
+            // What does not depend on the accumulator is fetched BEFORE waiting for it: the bias of the warp's columns and,
+            // for a fused transformer, the first staging group of x (and grad_y).
+            const bool with_bias = !p.atomic && p.bias != nullptr;
+            if (with_bias) {
+                bias_w[lane] = gnw + lane < p.N ? __ldg(p.bias + gnw + lane) : 0.f;
+                bias_w[lane + 32] = gnw + 32 + lane < p.N ? __ldg(p.bias + gnw + 32 + lane) : 0.f;
+            }
+            using TG = TxGeo<TX>;
+            [[maybe_unused]] const int chunk0 = gnw >> 4;                       // first parameter chunk of this warp
+            [[maybe_unused]] const int tx_cn = p.tx_units * TG::XPU;            // x columns in the table
+            [[maybe_unused]] float gl = 0.f;
+            if constexpr (TX != 0 && !tx_bwd(TX)) {
+                tx_stage_in<TG::GF * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, chunk0 * TG::XPC, tx_cn, xp, lane);
+            } else if constexpr (TX != 0) {
+                tx_stage_in<TG::GB * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, chunk0 * TG::XPC, tx_cn, xp, lane);
+                tx_stage_in<TG::GB * TG::XPC>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, chunk0 * TG::XPC, tx_cn,
+                                               xp + TG::GB * TG::XPC * XP_LD, lane);
+                if (p.tx_gl != nullptr && row_ok) gl = __ldg(p.tx_gl + gm);
+            }
+            mbar_wait(&sm->acc_full[buf], (tcount >> 1) & 1, p.error, 4);
+            tc_fence_after();
+            __syncwarp();
+            // accumulator chunks q, q + 1 (16 columns each) of this thread's row, bias added
+            auto load_pair = [&](int q, float (&va)[16], float (&vb)[16]) {
+                uint32_t ra[16], rb[16];
+                if (!empty) {
+                    tmem_ld16(lane_addr + buf * BN + cgroup * 64 + q * 16, ra);
+                    tmem_ld16(lane_addr + buf * BN + cgroup * 64 + q * 16 + 16, rb);
+                    tmem_wait8(ra); tmem_wait8(ra + 8); tmem_wait8(rb); tmem_wait8(rb + 8);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) ra[i] = rb[i] = 0u;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { va[i] = __uint_as_float(ra[i]); vb[i] = __uint_as_float(rb[i]); }
+                if (with_bias) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 a4 = *reinterpret_cast<const float4*>(bias_w + q * 16 + 4 * i);
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias_w + q * 16 + 16 + 4 * i);
+                        va[4 * i] += a4.x; va[4 * i + 1] += a4.y; va[4 * i + 2] += a4.z; va[4 * i + 3] += a4.w;
+                        vb[4 * i] += b4.x; vb[4 * i + 1] += b4.y; vb[4 * i + 2] += b4.z; vb[4 * i + 3] += b4.w;
+                    }
+                }
+            };
+            // activation / ELU' / padding, then the chunk goes to the transposition buffer and to the image of the result
+            auto emit_chunk = [&](int q, float (&v)[16]) {
+                const int c16 = q & 1;
+                const int gn0 = gnw + q * 16;
+                if (!p.atomic) {
+                    if (p.act == TFEPB_ACT_ELU) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], ex2(fminf(v[i], 0.f) * LOG2E) - 1.f);
+                    }
+                    if (p.aux != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] *= fminf(xp[(c16 * 16 + i) * XP_LD + lane], 0.f) + 1.f;
+                    }
+                    if (gn0 + 15 >= p.N) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (gn0 + i >= p.N) v[i] = 0.f;
+                    }
+                }
+                if (p.C != nullptr || p.out_img_t != nullptr || p.colsum != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) xp[(c16 * 16 + i) * XP_LD + lane] = v[i];
+                }
+                if (p.out_img != nullptr) {
+                    // columns are the reduction index of the next product: k-block = gn / 64, slab = (gn % 64) / 8;
+                    // consecutive rows are consecutive 16-byte chunks of a slab (coalesced as is)
+                    const int kblk = gn0 >> 6;
+                    if (kblk < p.out_k_blocks) {
+                        uint8_t* blk = p.out_img + ((size_t)tm * p.out_k_blocks + kblk) * A_BLOCK + (size_t)row * 16;
+                        const int slab = (gn0 & 63) >> 3;
+                        float res[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) res[i] = v[i];
+#pragma unroll
+                        for (int t = 0; t < NSPLIT; ++t) {
+                            // term t of the split: bf16 of what the previous terms left over
+                            uint32_t q8[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                q8[i] = pack_bf16(res[2 * i], res[2 * i + 1]);
+                                if (t + 1 < NSPLIT) {
+                                    res[2 * i] -= __uint_as_float(q8[i] << 16);
+                                    res[2 * i + 1] -= __uint_as_float(q8[i] & 0xffff0000u);
+                                }
+                            }
+                            uint8_t* dst = blk + (size_t)t * p.out_split_stride;
+                            *reinterpret_cast<uint4*>(dst + (size_t)slab * 2048) = make_uint4(q8[0], q8[1], q8[2], q8[3]);
+                            *reinterpret_cast<uint4*>(dst + (size_t)(slab + 1) * 2048) = make_uint4(q8[4], q8[5], q8[6], q8[7]);
+                        }
+                    }
+                }
+            };
+            if constexpr (TX != 0 && !tx_bwd(TX)) {
+                // ---- fused transformer, forward: x comes in and y goes out through the (otherwise idle) transposition buffer,
+                // GF chunks per staging group; y and the log-det are the only outputs ----
+                float ld_acc = 0.f;
 #pragma unroll 1
-            for (int sub = 0; sub < 2; ++sub) {
-                const int scol = cgroup * 64 + sub * 32;       // first column of the sub-tile inside the tile
-                const int gns = tn * BN + scol;
-                if (gns >= p.N && p.out_img == nullptr && (p.out_img_t == nullptr || gns >= p.t_rows_padded)) continue;   // warp-uniform
-                if (p.aux != nullptr && !p.atomic) {
-                    // coalesced load of the 32 x 32 ELU' operand: lane = column, transposed into the buffer
+                for (int g = 0; g < 4 / TG::GF; ++g) {
+                    if (gnw + g * TG::GF * 16 >= p.N) break;                                   // warp-uniform
+                    const int c0 = (chunk0 + g * TG::GF) * TG::XPC;
+                    if (g > 0) {
+                        tx_stage_in<TG::GF * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, xp, lane);
+                        __syncwarp();
+                    }
+#pragma unroll 1
+                    for (int pr = 0; pr < TG::GF / 2; ++pr) {
+                        const int q = g * TG::GF + 2 * pr;
+                        if (gnw + q * 16 >= p.N) break;
+                        float va[16], vb[16];
+                        load_pair(q, va, vb);
+                        tx_chunk<TX>(p, va, xp + (2 * pr) * TG::XPC * XP_LD, nullptr, lane, 0.f, row_ok, chunk0 + q, ld_acc);
+                        tx_chunk<TX>(p, vb, xp + (2 * pr + 1) * TG::XPC * XP_LD, nullptr, lane, 0.f, row_ok, chunk0 + q + 1, ld_acc);
+                    }
+                    __syncwarp();
+                    tx_stage_out<TG::GF * TG::XPC>(p.tx_y, p.tx_ldy, gm0, p.M, p.tx_cols, c0, tx_cn, xp, lane);
+                    __syncwarp();
+                }
+                if (row_ok && p.tx_logdet != nullptr) atomicAdd(p.tx_logdet + gm, ld_acc);
+            } else {
+#pragma unroll 1
+                for (int sub = 0; sub < 2; ++sub) {
+                    const int gns = gnw + sub * 32;                // first column of the sub-tile
+                    if (gns >= p.N && p.out_img == nullptr && (p.out_img_t == nullptr || gns >= p.t_rows_padded)) continue;   // warp-uniform
+                    if (p.aux != nullptr && !p.atomic) {
+                        // coalesced load of the 32 x 32 ELU' operand: lane = column, transposed into the buffer
 #pragma unroll 8
-                    for (int r = 0; r < 32; ++r) {
-                        const int grow = gm0 + r;
-                        xp[lane * XP_LD + r] = (grow < p.M && gns + lane < p.N) ? __ldg(p.aux + (int64_t)grow * p.ldaux + gns + lane) : 0.f;
+                        for (int r = 0; r < 32; ++r) {
+                            const int grow = gm0 + r;
+                            xp[lane * XP_LD + r] = (grow < p.M && gns + lane < p.N) ? __ldg(p.aux + (int64_t)grow * p.ldaux + gns + lane) : 0.f;
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
-                }
-#pragma unroll 1
-                for (int c16 = 0; c16 < 2; ++c16) {
-                    const int col0 = scol + c16 * 16;
-                    const int gn0 = tn * BN + col0;
-                    uint32_t r[16];
-                    if (!empty) {
-                        tmem_ld16(lane_addr + buf * BN + col0, r);
-                        tmem_wait8(r); tmem_wait8(r + 8);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) r[i] = 0u;
-                    }
-                    float v[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-                    if (!p.atomic) {
-                        const bool full = gn0 + 15 < p.N;
-                        if (p.bias != nullptr) {
-                            if (full && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gn0) + i);
-                                    v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
-                                }
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i)
-                                    if (gn0 + i < p.N) v[i] += __ldg(p.bias + gn0 + i);
+                    float va[16], vb[16];
+                    load_pair(2 * sub, va, vb);
+                    if constexpr (TX != 0) {
+                        // ---- fused transformer, backward: the chunks become parameter cotangents (x and grad_y staged GB
+                        // chunks at a time, grad_x leaves through the slots of grad_y), then they take the usual way out ----
+                        float unused = 0.f;
+                        constexpr int XG = TG::GB * TG::XPC;                                       // x columns per staging group
+                        if constexpr (TG::GB == 2) {
+                            const int c0 = (chunk0 + 2 * sub) * TG::XPC;
+                            if (sub > 0) {
+                                tx_stage_in<XG>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, xp, lane);
+                                tx_stage_in<XG>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, c0, tx_cn, xp + XG * XP_LD, lane);
+                                __syncwarp();
                             }
-                        }
-                        if (p.act == TFEPB_ACT_ELU) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], ex2(fminf(v[i], 0.f) * LOG2E) - 1.f);
-                        }
-                        if (p.aux != nullptr) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] *= fminf(xp[(c16 * 16 + i) * XP_LD + lane], 0.f) + 1.f;
-                        }
-                        if (!full) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (gn0 + i >= p.N) v[i] = 0.f;
-                        }
-                    }
-                    if (p.C != nullptr || p.out_img_t != nullptr || p.colsum != nullptr) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) xp[(c16 * 16 + i) * XP_LD + lane] = v[i];
-                    }
-                    if (p.out_img != nullptr) {
-                        // columns are the reduction index of the next product: k-block = gn / 64, slab = (gn % 64) / 8;
-                        // consecutive rows are consecutive 16-byte chunks of a slab (coalesced as is)
-                        const int kblk = gn0 >> 6;
-                        if (kblk < p.out_k_blocks) {
-                            uint8_t* blk = p.out_img + ((size_t)tm * p.out_k_blocks + kblk) * A_BLOCK + (size_t)row * 16;
-                            const int slab = (gn0 & 63) >> 3;
-                            float res[16];
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) res[i] = v[i];
-#pragma unroll
-                            for (int t = 0; t < NSPLIT; ++t) {
-                                // term t of the split: bf16 of what the previous terms left over
-                                uint32_t q[8];
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    q[i] = pack_bf16(res[2 * i], res[2 * i + 1]);
-                                    if (t + 1 < NSPLIT) {
-                                        res[2 * i] -= __uint_as_float(q[i] << 16);
-                                        res[2 * i + 1] -= __uint_as_float(q[i] & 0xffff0000u);
-                                    }
-                                }
-                                uint8_t* dst = blk + (size_t)t * p.out_split_stride;
-                                *reinterpret_cast<uint4*>(dst + (size_t)slab * 2048) = make_uint4(q[0], q[1], q[2], q[3]);
-                                *reinterpret_cast<uint4*>(dst + (size_t)(slab + 1) * 2048) = make_uint4(q[4], q[5], q[6], q[7]);
-                            }
-                        }
-                    }
-                }
-                if (p.out_img_t != nullptr || p.colsum != nullptr) {
-                    // lane = column of C = row of the transposed image; its 32 k-values (rows gm0 .. gm0 + 31 of C) are
-                    // four 16-byte chunks of consecutive slabs, and consecutive lanes write consecutive chunks
-                    __syncwarp();
-                    const int n = gns + lane;
-                    const int nrows = min(32, p.M - gm0);              // rows beyond M carry the bias only: zero them
-                    float cs = 0.f;
-                    uint32_t q[16];
-#pragma unroll
-                    for (int r = 0; r < 32; r += 2) {
-                        const float v0 = r < nrows ? xp[lane * XP_LD + r] : 0.f;
-                        const float v1 = r + 1 < nrows ? xp[lane * XP_LD + r + 1] : 0.f;
-                        cs += v0 + v1;
-                        q[r >> 1] = pack_bf16(v0, v1);
-                    }
-                    if (p.out_img_t != nullptr && n < p.t_rows_padded && (gm0 >> 6) < p.t_k_blocks) {
-                        const size_t block_bytes = (size_t)p.t_rows * 128;
-                        uint8_t* blk = p.out_img_t + ((size_t)(n / p.t_rows) * p.t_k_blocks + (gm0 >> 6)) * block_bytes +
-                                       (size_t)(n % p.t_rows) * 16;
-                        const int slab0 = (gm0 & 63) >> 3;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<uint4*>(blk + (size_t)(slab0 + j) * p.t_rows * 16) =
-                                make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
-                    }
-                    if (p.colsum != nullptr && n < p.N) atomicAdd(p.colsum + n, cs);
-                    if (p.C == nullptr) __syncwarp();
-                }
-                if (p.C != nullptr) {
-                    __syncwarp();
-                    const bool c0 = gns + lane < p.N;
-                    if (c0 && !(p.atomic && empty)) {
-                        const int nrows = min(32, p.M - gm0);
-                        float* cptr = p.C + (int64_t)gm0 * p.ldc + gns + lane;
-                        if (p.atomic) {
-#pragma unroll 4
-                            for (int r = 0; r < nrows; ++r) atomicAdd(cptr + (int64_t)r * p.ldc, xp[lane * XP_LD + r]);
+                            tx_chunk<TX>(p, va, xp, xp + XG * XP_LD, lane, gl, row_ok, chunk0 + 2 * sub, unused);
+                            tx_chunk<TX>(p, vb, xp + TG::XPC * XP_LD, xp + (XG + TG::XPC) * XP_LD, lane, gl, row_ok,
+                                         chunk0 + 2 * sub + 1, unused);
+                            __syncwarp();
+                            tx_stage_out<XG>(p.tx_gx, p.tx_ldgx, gm0, p.M, p.tx_cols, c0, tx_cn, xp + XG * XP_LD, lane);
+                            __syncwarp();
                         } else {
-#pragma unroll 8
-                            for (int r = 0; r < nrows; ++r) cptr[(int64_t)r * p.ldc] = xp[lane * XP_LD + r];
+#pragma unroll
+                            for (int c16 = 0; c16 < 2; ++c16) {
+                                const int c0 = (chunk0 + 2 * sub + c16) * TG::XPC;
+                                if (sub > 0 || c16 > 0) {
+                                    tx_stage_in<XG>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, xp, lane);
+                                    tx_stage_in<XG>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, c0, tx_cn, xp + XG * XP_LD, lane);
+                                    __syncwarp();
+                                }
+                                tx_chunk<TX>(p, c16 == 0 ? va : vb, xp, xp + XG * XP_LD, lane, gl, row_ok, chunk0 + 2 * sub + c16, unused);
+                                __syncwarp();
+                                tx_stage_out<XG>(p.tx_gx, p.tx_ldgx, gm0, p.M, p.tx_cols, c0, tx_cn, xp + XG * XP_LD, lane);
+                                __syncwarp();
+                            }
                         }
                     }
-                    __syncwarp();
+                    emit_chunk(2 * sub, va);
+                    emit_chunk(2 * sub + 1, vb);
+                    if (p.out_img_t != nullptr || p.colsum != nullptr) {
+                        // lane = column of C = row of the transposed image; its 32 k-values (rows gm0 .. gm0 + 31 of C) are
+                        // four 16-byte chunks of consecutive slabs, and consecutive lanes write consecutive chunks
+                        __syncwarp();
+                        const int n = gns + lane;
+                        const int nrows = min(32, p.M - gm0);              // rows beyond M carry the bias only: zero them
+                        float cs = 0.f;
+                        uint32_t q[16];
+#pragma unroll
+                        for (int r = 0; r < 32; r += 2) {
+                            const float v0 = r < nrows ? xp[lane * XP_LD + r] : 0.f;
+                            const float v1 = r + 1 < nrows ? xp[lane * XP_LD + r + 1] : 0.f;
+                            cs += v0 + v1;
+                            q[r >> 1] = pack_bf16(v0, v1);
+                        }
+                        if (p.out_img_t != nullptr && n < p.t_rows_padded && (gm0 >> 6) < p.t_k_blocks) {
+                            const size_t block_bytes = (size_t)p.t_rows * 128;
+                            uint8_t* blk = p.out_img_t + ((size_t)(n / p.t_rows) * p.t_k_blocks + (gm0 >> 6)) * block_bytes +
+                                           (size_t)(n % p.t_rows) * 16;
+                            const int slab0 = (gm0 & 63) >> 3;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<uint4*>(blk + (size_t)(slab0 + j) * p.t_rows * 16) =
+                                    make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
+                        }
+                        if (p.colsum != nullptr && n < p.N) atomicAdd(p.colsum + n, cs);
+                        if (p.C == nullptr) __syncwarp();
+                    }
+                    if (p.C != nullptr) {
+                        __syncwarp();
+                        const bool c0 = gns + lane < p.N;
+                        if (c0 && !(p.atomic && empty)) {
+                            const int nrows = min(32, p.M - gm0);
+                            float* cptr = p.C + (int64_t)gm0 * p.ldc + gns + lane;
+                            if (p.atomic) {
+#pragma unroll 4
+                                for (int r = 0; r < nrows; ++r) atomicAdd(cptr + (int64_t)r * p.ldc, xp[lane * XP_LD + r]);
+                            } else {
+#pragma unroll 8
+                                for (int r = 0; r < nrows; ++r) cptr[(int64_t)r * p.ldc] = xp[lane * XP_LD + r];
+                            }
+                        }
+                        __syncwarp();
+                    }
                 }
             }
-            (void)row_ok;
             tc_fence_before();
             mbar_arrive(&sm->acc_empty[buf]);
             ++tcount;
@@ -537,7 +759,26 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
     TFEPB_CHECK_ARG(a != nullptr, "null argument struct");
     TFEPB_CHECK_ARG(a->a_image && a->b_image, "null operand image");
     TFEPB_CHECK_ARG(a->m > 0 && a->n > 0 && a->k > 0, "bad sizes");
-    TFEPB_CHECK_ARG(a->c != nullptr || a->out_image != nullptr || a->out_image_t != nullptr, "no output");
+    const tfepb_tc_tx* tx = a->tx;
+    TFEPB_CHECK_ARG(a->c != nullptr || a->out_image != nullptr || a->out_image_t != nullptr || (tx != nullptr && !tx->backward),
+                    "no output");
+    if (tx != nullptr) {
+        TFEPB_CHECK_ARG(tx->kind >= TFEPB_TCTX_AFFINE && tx->kind <= TFEPB_TCTX_MOEBIUS3, "unknown fused transformer kind %d", tx->kind);
+        TFEPB_CHECK_ARG(a->n_split <= 1 && a->split_k <= 1 && a->aux == nullptr && a->activation == TFEPB_ACT_NONE && a->n % 16 == 0,
+                        "fused transformer: plain bf16 product without split-K / aux / activation, n a multiple of 16");
+        const int upc = tx->kind == TFEPB_TCTX_AFFINE ? 8 : tx->kind == TFEPB_TCTX_SOS2 ? 3 : 5;
+        TFEPB_CHECK_ARG(tx->n_units > 0 && (int64_t)a->n >= ((int64_t)tx->n_units + upc - 1) / upc * 16,
+                        "fused transformer: n = %d columns do not hold %d units", a->n, tx->n_units);
+        TFEPB_CHECK_ARG(tx->cols != nullptr && tx->x != nullptr, "fused transformer: null buffer");
+        TFEPB_CHECK_ARG(tx->unit_sphere == 0 || tx->unit_sphere == 1, "fused transformer: Moebius variant must be 0 or 1");
+        if (!tx->backward) {
+            TFEPB_CHECK_ARG(tx->y != nullptr, "fused transformer: null y");
+            TFEPB_CHECK_ARG(a->c == nullptr && a->out_image == nullptr && a->out_image_t == nullptr && a->column_sums == nullptr,
+                            "fused transformer, forward: the product has no output of its own");
+        } else {
+            TFEPB_CHECK_ARG(tx->grad_y != nullptr && tx->grad_x != nullptr, "fused transformer: null gradient buffer");
+        }
+    }
     TFEPB_CHECK_ARG(a->out_image_t == nullptr || a->out_image_t_rows == 128 || a->out_image_t_rows == 256,
                     "out_image_t_rows must be 128 or 256");
     TFEPB_CHECK_ARG((uintptr_t)a->out_image_t % 16 == 0, "operand images must be 16-byte aligned");
@@ -562,6 +803,16 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
     p.row_ranges = a->row_ranges;
     p.tiles_m = (a->m + tcg::BM - 1) / tcg::BM; p.tiles_n = (a->n + tcg::BN - 1) / tcg::BN;
     p.error = a->error_flag;
+    if (tx != nullptr) {
+        p.tx_units = tx->n_units; p.tx_unit_sphere = tx->unit_sphere; p.tx_max_radius = (float)tx->max_radius;
+        p.tx_cols = tx->cols;
+        p.tx_x = (const float*)tx->x; p.tx_ldx = tx->ldx;
+        p.tx_y = (float*)tx->y; p.tx_ldy = tx->ldy;
+        p.tx_logdet = tx->logdet;
+        p.tx_gy = (const float*)tx->grad_y; p.tx_ldgy = tx->ldgy;
+        p.tx_gl = tx->grad_logdet;
+        p.tx_gx = (float*)tx->grad_x; p.tx_ldgx = tx->ldgx;
+    }
     int splits = a->split_k > 1 ? a->split_k : 1;
     if (splits > p.k_blocks) splits = p.k_blocks;
     p.atomic = splits > 1 ? 1 : 0;
@@ -576,18 +827,22 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
     p.out_split_stride = n_split > 1 ? tfepb_tc_image_bytes(a->m, a->n, 128) : 0;
     const int stage_bytes = n_split == 1 ? tcg::Geo<1>::STAGE : n_split == 2 ? tcg::Geo<2>::STAGE : tcg::Geo<3>::STAGE;
     const int stages = n_split == 3 ? tcg::Geo<3>::N_STAGES : tcg::Geo<1>::N_STAGES;
-    const size_t smem = (size_t)stages * stage_bytes + (size_t)tcg::EPI_WARPS * tcg::XP_FLOATS * 4 + sizeof(tcg::Smem) + 1024;
-    const void* kernel = n_split == 1 ? reinterpret_cast<const void*>(tcg::tc_gemm_kernel<1>)
-                       : n_split == 2 ? reinterpret_cast<const void*>(tcg::tc_gemm_kernel<2>)
-                                      : reinterpret_cast<const void*>(tcg::tc_gemm_kernel<3>);
-    if (int rc = ensure_dynamic_smem(kernel, smem)) return rc;
+    const size_t smem = (size_t)stages * stage_bytes + (size_t)tcg::EPI_WARPS * (tcg::XP_FLOATS + 64) * 4 + sizeof(tcg::Smem) + 1024;
+    using kernel_t = void (*)(const tcg::Params);
+    kernel_t kernel = n_split == 1 ? tcg::tc_gemm_kernel<1> : n_split == 2 ? tcg::tc_gemm_kernel<2> : tcg::tc_gemm_kernel<3>;
+    if (tx != nullptr) {
+        static const kernel_t fused[6] = {
+            tcg::tc_gemm_kernel<1, 2 * TFEPB_TCTX_AFFINE>,   tcg::tc_gemm_kernel<1, 2 * TFEPB_TCTX_AFFINE + 1>,
+            tcg::tc_gemm_kernel<1, 2 * TFEPB_TCTX_SOS2>,     tcg::tc_gemm_kernel<1, 2 * TFEPB_TCTX_SOS2 + 1>,
+            tcg::tc_gemm_kernel<1, 2 * TFEPB_TCTX_MOEBIUS3>, tcg::tc_gemm_kernel<1, 2 * TFEPB_TCTX_MOEBIUS3 + 1>};
+        kernel = fused[2 * (tx->kind - 1) + (tx->backward ? 1 : 0)];
+    }
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), smem)) return rc;
     const int tiles = p.tiles_m * p.tiles_n;
     int gx = sm_count() / splits;
     if (gx < 1) gx = 1;
     if (gx > tiles) gx = tiles;
     dim3 grid((unsigned)gx, (unsigned)splits);
-    if (n_split == 1) tcg::tc_gemm_kernel<1><<<grid, tcg::THREADS, smem, as_stream(stream)>>>(p);
-    else if (n_split == 2) tcg::tc_gemm_kernel<2><<<grid, tcg::THREADS, smem, as_stream(stream)>>>(p);
-    else tcg::tc_gemm_kernel<3><<<grid, tcg::THREADS, smem, as_stream(stream)>>>(p);
+    kernel<<<grid, tcg::THREADS, smem, as_stream(stream)>>>(p);
     return check_launch("tc_gemm_kernel");
 }

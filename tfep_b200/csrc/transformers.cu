@@ -104,6 +104,15 @@ int spline_dispatch(const tfepb_tx_io* io, const tfepb_spline_cfg* cfg, const tf
         op.min_bin = (T)cfg->min_bin_size; op.min_slope = (T)cfg->min_slope;
         op.bins = cfg->bins_out; op.ldbins = cfg->ldbins;
     };
+    if (cfg->n_bins == 8 && io->par_stride_p == 1 && !cfg->identity_boundary_slopes && !cfg->learn_lower_bound &&
+        !cfg->learn_upper_bound && cfg->bins_out == nullptr) {
+        // packed layout of the MAF paths: compile-time bin count and parameter stride (same arithmetic)
+        SplinePackedOp<T, 8> op;
+        op.circular = cfg->circular;
+        op.x0 = (const T*)cfg->x0; op.xf = (const T*)cfg->xf; op.y0 = (const T*)cfg->y0; op.yf = (const T*)cfg->yf;
+        op.min_bin = (T)cfg->min_bin_size; op.min_slope = (T)cfg->min_slope;
+        return run<T>(io, g, op, s, "spline_packed");
+    }
     if (cfg->n_bins <= 8) { SplineOp<T, 8> op; fill(op); return run<T>(io, g, op, s, "spline"); }
     if (cfg->n_bins <= 16) { SplineOp<T, 16> op; fill(op); return run<T>(io, g, op, s, "spline"); }
     if (cfg->n_bins <= 32) { SplineOp<T, 32> op; fill(op); return run<T>(io, g, op, s, "spline"); }
@@ -254,6 +263,10 @@ extern "C" int tfepb_sos(const tfepb_tx_io* io, int32_t n_polynomials, tfepb_str
     if (int rc = check_io(io, nullptr)) return rc;
     TFEPB_CHECK_ARG(n_polynomials >= 2, "n_polynomials must be strictly greater than 1.");
     TFEPB_CHECK_ARG(io->inverse == 0, "Inversion of SOS polynomial transformer has not been implemented yet.");
+    if (n_polynomials == 2 && io->par_stride_p == 1) {
+        if (io->dtype == TFEPB_F32) return run<float>(io, nullptr, SosPackedOp<float, 2>{}, as_stream(stream), "sos_packed");
+        return run<double>(io, nullptr, SosPackedOp<double, 2>{}, as_stream(stream), "sos_packed");
+    }
     if (io->dtype == TFEPB_F32) return run<float>(io, nullptr, SosOp<float>{n_polynomials}, as_stream(stream), "sos");
     return run<double>(io, nullptr, SosOp<double>{n_polynomials}, as_stream(stream), "sos");
 }
@@ -264,6 +277,10 @@ extern "C" int tfepb_sos_backward(const tfepb_tx_io* io, int32_t n_polynomials, 
     TFEPB_CHECK_ARG(g != nullptr, "null gradient struct");
     if (int rc = check_io(io, g)) return rc;
     TFEPB_CHECK_ARG(n_polynomials >= 2, "n_polynomials must be strictly greater than 1.");
+    if (n_polynomials == 2 && io->par_stride_p == 1) {
+        if (io->dtype == TFEPB_F32) return run<float>(io, g, SosPackedOp<float, 2>{}, as_stream(stream), "sos_packed_backward");
+        return run<double>(io, g, SosPackedOp<double, 2>{}, as_stream(stream), "sos_packed_backward");
+    }
     if (io->dtype == TFEPB_F32)
         return run<float>(io, g, SosOp<float>{n_polynomials}, as_stream(stream), "sos_backward");
     return run<double>(io, g, SosOp<double>{n_polynomials}, as_stream(stream), "sos_backward");
@@ -276,6 +293,11 @@ extern "C" int tfepb_moebius(const tfepb_tx_io* io, int32_t dimension, double ma
     TFEPB_CHECK_ARG(dimension >= 1 && dimension <= 16, "dimension must be in [1, 16]");
     TFEPB_CHECK_ARG(io->n_features % dimension == 0, "n_features must be a multiple of the vector dimension");
     TFEPB_CHECK_ARG(unit_sphere >= 0 && unit_sphere <= 2, "unit_sphere (variant) must be 0, 1 or 2");
+    if (dimension == 3 && unit_sphere != 2) {
+        if (io->dtype == TFEPB_F32)
+            return run<float>(io, nullptr, MoebiusPackedOp<float, 3>{(float)max_radius, unit_sphere}, as_stream(stream), "moebius3");
+        return run<double>(io, nullptr, MoebiusPackedOp<double, 3>{max_radius, unit_sphere}, as_stream(stream), "moebius3");
+    }
     if (io->dtype == TFEPB_F32)
         return run<float>(io, nullptr, MoebiusOp<float>{dimension, (float)max_radius, unit_sphere}, as_stream(stream), "moebius");
     return run<double>(io, nullptr, MoebiusOp<double>{dimension, max_radius, unit_sphere}, as_stream(stream), "moebius");
@@ -289,6 +311,12 @@ extern "C" int tfepb_moebius_backward(const tfepb_tx_io* io, int32_t dimension, 
     TFEPB_CHECK_ARG(dimension >= 1 && dimension <= 16, "dimension must be in [1, 16]");
     TFEPB_CHECK_ARG(io->n_features % dimension == 0, "n_features must be a multiple of the vector dimension");
     TFEPB_CHECK_ARG(unit_sphere >= 0 && unit_sphere <= 2, "unit_sphere (variant) must be 0, 1 or 2");
+    if (dimension == 3 && unit_sphere != 2) {
+        if (io->dtype == TFEPB_F32)
+            return run<float>(io, g, MoebiusPackedOp<float, 3>{(float)max_radius, unit_sphere}, as_stream(stream),
+                              "moebius3_backward");
+        return run<double>(io, g, MoebiusPackedOp<double, 3>{max_radius, unit_sphere}, as_stream(stream), "moebius3_backward");
+    }
     if (io->dtype == TFEPB_F32)
         return run<float>(io, g, MoebiusOp<float>{dimension, (float)max_radius, unit_sphere}, as_stream(stream),
                           "moebius_backward");

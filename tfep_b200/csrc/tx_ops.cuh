@@ -148,6 +148,120 @@ struct MoebiusOp {
     }
 };
 
+// ------------------------------------------------------------------------------------------
+// Fast variants for the PACKED parameter layout of the MAF paths (stride_p == 1: the parameters of a feature are
+// consecutive): they are copied into registers once, the sizes are compile-time constants, so after inlining every
+// index of the SOS / Moebius math is a constant and nothing is re-read from memory (splines: constant stride only).  The generic operators above do
+// 64-bit strided address arithmetic per parameter access and re-read parameters inside their loops (ncu, r02: 200
+// issued instructions per SOS feature, 1250 per spline feature, issue bound); the arithmetic itself is the same code.
+// ------------------------------------------------------------------------------------------
+template <typename T, int NPOLY>
+struct SosPackedOp {
+    static constexpr int P = 1 + 2 * NPOLY;
+    __device__ int units(int F) const { return F; }
+    __device__ T apply(const TxView<T>& v, int b, int u) const {
+        const int f = v.fid(u), c = v.col(f);
+        const T* p0 = v.par + v.poffset(b, f);
+        T loc[P];
+#pragma unroll
+        for (int i = 0; i < P; ++i) loc[i] = p0[i];
+        T out, ld;
+        sos_eval<T>(ParIn<T>{loc, 1}, NPOLY, v.x[(int64_t)b * v.ldx + c], out, ld);
+        v.y[(int64_t)b * v.ldy + c] = out;
+        return ld;
+    }
+    __device__ void backward(const TxView<T>& v, int b, int u, T) const {
+        const int f = v.fid(u), c = v.col(f);
+        const int64_t off = v.poffset(b, f);
+        const T* p0 = v.par + off;
+        T loc[P], gloc[P];
+#pragma unroll
+        for (int i = 0; i < P; ++i) loc[i] = p0[i];
+        T gx;
+        sos_vjp<T>(ParIn<T>{loc, 1}, NPOLY, v.x[(int64_t)b * v.ldx + c], v.gy[(int64_t)b * v.ldgy + c], gx, ParOut<T>{gloc, 1});
+        v.gx[(int64_t)b * v.ldgx + c] = gx;
+        T* g0 = v.gpar + off;
+#pragma unroll
+        for (int i = 0; i < P; ++i) g0[i] = gloc[i];
+    }
+};
+
+template <typename T, int D>
+struct MoebiusPackedOp {                 // variants 0 / 1 (not the symmetrized map)
+    T max_radius;
+    int unit_sphere;
+    __device__ int units(int F) const { return F / D; }
+    __device__ T apply(const TxView<T>& v, int b, int u) const {
+        const int f0 = v.fid(u * D);
+        T xs[D], vs[D], ys[D];
+        int cs[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            cs[i] = v.col(f0 + i);
+            xs[i] = v.x[(int64_t)b * v.ldx + cs[i]];
+            vs[i] = v.par[v.poffset(b, f0 + i)];
+        }
+        const T ld = moebius_eval<T>(xs, 1, vs, 1, v.inverse ? T(-1) : T(1), D, max_radius, unit_sphere != 0, ys, 1);
+#pragma unroll
+        for (int i = 0; i < D; ++i) v.y[(int64_t)b * v.ldy + cs[i]] = ys[i];
+        return ld;
+    }
+    __device__ void backward(const TxView<T>& v, int b, int u, T gl) const {
+        const int f0 = v.fid(u * D);
+        T xs[D], vs[D], gys[D], gxs[D], gvs[D];
+        int cs[D];
+        int64_t po[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            cs[i] = v.col(f0 + i);
+            po[i] = v.poffset(b, f0 + i);
+            xs[i] = v.x[(int64_t)b * v.ldx + cs[i]];
+            gys[i] = v.gy[(int64_t)b * v.ldgy + cs[i]];
+            vs[i] = v.par[po[i]];
+        }
+        moebius_vjp<T>(xs, 1, vs, 1, D, max_radius, unit_sphere != 0, gys, 1, gl, gxs, 1, gvs, 1);
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            v.gx[(int64_t)b * v.ldgx + cs[i]] = gxs[i];
+            v.gpar[po[i]] = gvs[i];
+        }
+    }
+};
+
+template <typename T, int KBINS>
+struct SplinePackedOp {                  // K bins, free boundary slopes, fixed limits (circular or not); the slope
+                                         // parameters are indexed by the bin found at run time, so they stay in memory
+    int circular;
+    const T *x0, *xf, *y0, *yf;
+    T min_bin, min_slope;
+    __device__ int units(int F) const { return F; }
+    __device__ SplineFeat<T> feat(int f) const {
+        SplineFeat<T> c;
+        c.K = KBINS; c.circular = circular; c.idslopes = 0; c.learn_lo = 0; c.learn_hi = 0;
+        c.x0 = x0[f]; c.xf = xf[f]; c.y0 = y0[f]; c.yf = yf[f];
+        c.min_bin = min_bin; c.min_slope = min_slope;
+        return c;
+    }
+    __device__ T apply(const TxView<T>& v, int b, int u) const {
+        const int f = v.fid(u), col = v.col(f);
+        const ParIn<T> pin{v.par + v.poffset(b, f), 1};
+        T out, ld;
+        int bin;
+        if (v.inverse) spline_eval<T, KBINS, true>(feat(f), pin, v.x[(int64_t)b * v.ldx + col], out, ld, bin);
+        else spline_eval<T, KBINS, false>(feat(f), pin, v.x[(int64_t)b * v.ldx + col], out, ld, bin);
+        v.y[(int64_t)b * v.ldy + col] = out;
+        return ld;
+    }
+    __device__ void backward(const TxView<T>& v, int b, int u, T gl) const {
+        const int f = v.fid(u), col = v.col(f);
+        const int64_t off = v.poffset(b, f);
+        T gx;
+        spline_vjp<T, KBINS>(feat(f), ParIn<T>{v.par + off, 1}, v.x[(int64_t)b * v.ldx + col], v.gy[(int64_t)b * v.ldgy + col],
+                             gl, gx, ParOut<T>{v.gpar + off, 1});
+        v.gx[(int64_t)b * v.ldgx + col] = gx;
+    }
+};
+
 template <typename T, int MAXK>
 struct SplineOp {
     int K, circular, idslopes, learn_lo, learn_hi;

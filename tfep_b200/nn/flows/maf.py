@@ -96,6 +96,9 @@ class MAF(AutoregressiveFlow):
         self._fused = None
         self._sweep = None
         self._blocked = None
+        self._tctx = None
+        #: False: keep the transformer kernels separate from the tensor-core conditioner (precision='bf16')
+        self.fuse_transformer = True
         #: degrees per block of the blocked inverse sweep of wide conditioners (tfep_b200/_blocked.py)
         self.inverse_block_degrees = 64
         #: see the class docstring; one of PRECISIONS
@@ -165,12 +168,28 @@ class MAF(AutoregressiveFlow):
             return self._forward_fused(x)
         if pk is False or self._n_conditioner_indices > 0:
             return super().forward(x)
+        if self.precision == 'bf16' and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[0] > 0:
+            # tensor-core conditioner with the transformer applied by the epilogue of its output layer, forward and
+            # backward (affine / SOS / Moebius; tfep_b200/_txfused.py)
+            txp = self._tc_tx_plan() if self.fuse_transformer else None
+            if txp is not None:
+                return txp.forward(self, pk, x.contiguous())
         layouts, _ = self._packed_tables(x.device)
         xc = x if self._embedding is None else self._embedding(x)
         # precision='bf16' outside the fused kernel (other transformers, training): the MADE conditioner runs on the
         # general tensor-core GEMM, forward and backward; the transformer kernels stay exact
         par = self._conditioner.run_plan(xc.contiguous(), pk['plan'], precision=self.precision)
         return _program.run(pk['parts'], x.contiguous(), par, layouts, passthrough=self.has_fixed_indices)
+
+    def _tc_tx_plan(self):
+        """Plan of the fused transformer epilogue of the general tensor-core path, or None (``_tctx_why`` says why)."""
+        if self._tctx is None:
+            from ... import _txfused
+            pk = self._pack()
+            why = _txfused.eligibility(self, pk)
+            self._tctx = _txfused.TcTxPlan(self, pk) if why is None else False
+            self._tctx_why = why
+        return self._tctx or None
 
     def _use_fused(self, x):
         """The one-launch fused kernel serves inference of the splines it covers; everything else that asks for
