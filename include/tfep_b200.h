@@ -263,6 +263,9 @@ typedef struct {
     int32_t reserved;
     const tfepb_tc_tx* tx;               /* NULL, or the transformer fused into the epilogue (n_split <= 1, no split_k,
                                             n a multiple of 16, activation NONE, no aux) */
+    const void* aux_image;               /* alternative to aux: the same (m, n) operand h given as its bf16 image (block_rows =
+                                            128, k = n; e.g. the out_image a forward product wrote): the result is multiplied
+                                            by ELU'(h) of the bf16 values -- no fp32 copy of the activations is needed */
 } tfepb_tc_gemm_args;
 int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream);
 

@@ -441,12 +441,13 @@ class TcTx:
 
 def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, aux=None, out_image=False,
             k_block_ranges=None, row_ranges=None, split_k=1, error_flag=None, out_image_t=None, column_sums=False, n_split=1,
-            tx=None):
+            tx=None, aux_image=None):
     """C = act(A B^T + bias) [* ELU'(aux)] from operand images; returns (c, out_img).  ``c``: True to allocate, a
     tensor to write into (zero-filled by the caller when split_k > 1), None for no fp32 output.
     ``out_image_t`` = 128 / 256: also the image of the transposed result with that block_rows; ``column_sums``: also
     the sums over the m rows; with either, returns (c, out_img, out_img_t, column_sums).  ``tx``: a :class:`TcTx`, the
-    transformer applied by the epilogue (the columns are then parameter chunks, see tfepb_tc_tx)."""
+    transformer applied by the epilogue (the columns are then parameter chunks, see tfepb_tc_tx).  ``aux_image``: the
+    ELU' operand as the bf16 image a forward product wrote (instead of the fp32 ``aux``)."""
     lib = _lib.load()
     dev = a_img.device
     if c is True:
@@ -473,6 +474,8 @@ def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, au
     if tx is not None:
         txs = tx.struct()                 # kept alive until the launch returns
         a.tx = ctypes.pointer(txs)
+    if aux_image is not None:
+        a.aux_image = aux_image.data_ptr()
     with torch.cuda.device(dev):
         check(lib.tfepb_tc_gemm(ctypes.byref(a), stream_ptr(a_img)))
     if out_image_t or column_sums:
@@ -497,6 +500,7 @@ class MadeFunctionTC(torch.autograd.Function):
         train = any(ctx.needs_input_grad[5:5 + 2 * n_layers])      # weight gradients wanted: keep transposed images
         # x: one pass gives the A operand of the first product and, for training, the B operand of its weight gradient
         img, x_t, _ = tc_pack_dual(x, 256 if train else None)
+        # hidden activations exist as bf16 images only: operand of the next product, ELU' operand of the backward pass
         acts, acts_t = [x], [x_t]
         h = x
         for l in range(n_layers):
@@ -505,15 +509,16 @@ class MadeFunctionTC(torch.autograd.Function):
             wimg = tc_pack(ws[l], 256)
             if train and not last:
                 # the epilogue also writes the image of h^T: the B operand of the next layer's weight gradient
-                h, img, img_t, _ = tc_gemm(img, wimg, B, N, K, c=True, bias=bs[l], activation=ACT_ELU, out_image=True,
+                _, img, img_t, _ = tc_gemm(img, wimg, B, N, K, bias=bs[l], activation=ACT_ELU, out_image=True,
                                            out_image_t=256, k_block_ranges=None if kb_fwd is None else kb_fwd[l])
                 acts_t.append(img_t)
             else:
-                h, img = tc_gemm(img, wimg, B, N, K, c=True, bias=bs[l], activation=ACT_NONE if last else ACT_ELU,
-                                 out_image=not last, k_block_ranges=None if kb_fwd is None else kb_fwd[l])
+                h, img = tc_gemm(img, wimg, B, N, K, c=True if last else None, bias=bs[l],
+                                 activation=ACT_NONE if last else ACT_ELU, out_image=not last,
+                                 k_block_ranges=None if kb_fwd is None else kb_fwd[l])
                 acts_t.append(None)
             if not last:
-                acts.append(h)
+                acts.append(img)
         ctx.save_for_backward(*acts, *ws)
         ctx.acts_t = acts_t[:n_layers]
         ctx.n_layers = n_layers
@@ -541,7 +546,8 @@ class MadeFunctionTC(torch.autograd.Function):
 def _made_tc_backward_layers(acts, acts_t, ws, kb_bwd, rr_w, need_w, need_x, g, gimg, gimg_t, gb):
     """Backward pass of the layers of a MADE on the tensor cores, given the cotangent of the output layer's result as
     operand images (``gimg``: A operand of the backward-input product; ``gimg_t``: A operand of the weight gradient, or
-    None -> packed from the fp32 ``g``; ``gb``: its column sums, or None).  Returns (grad_x or None, grad_ws, grad_bs)."""
+    None -> packed from the fp32 ``g``; ``gb``: its column sums, or None).  ``acts``: the input x (fp32) followed by the
+    bf16 images of the hidden activations.  Returns (grad_x or None, grad_ws, grad_bs)."""
     L = len(ws)
     B = acts[0].shape[0]
     gws, gbs = [None] * L, [None] * L
@@ -560,15 +566,16 @@ def _made_tc_backward_layers(acts, acts_t, ws, kb_bwd, rr_w, need_w, need_x, g, 
         gimg_t, gb = None, None
         if l > 0 or need_x:
             wt = tc_pack(ws[l], 256, transpose=True)            # rows = inputs of the layer, k = its outputs
-            below = l > 0 and need_w[l - 1]
-            if below:
-                g, gimg, gimg_t, gb = tc_gemm(gimg, wt, B, K, N, c=True, aux=acts[l], out_image=True, out_image_t=128,
-                                              column_sums=True, k_block_ranges=None if kb_bwd is None else kb_bwd[l])
-            else:
-                g, gimg = tc_gemm(gimg, wt, B, K, N, c=True, aux=acts[l] if l > 0 else None, out_image=l > 0,
-                                  k_block_ranges=None if kb_bwd is None else kb_bwd[l])
+            kb = None if kb_bwd is None else kb_bwd[l]
             if l == 0:
-                gx = g
+                gx, _ = tc_gemm(gimg, wt, B, K, N, c=True, k_block_ranges=kb)
+            elif need_w[l - 1]:
+                # the cotangent of a hidden activation exists as operand images (and column sums) only
+                _, gimg, gimg_t, gb = tc_gemm(gimg, wt, B, K, N, aux_image=acts[l], out_image=True, out_image_t=128,
+                                              column_sums=True, k_block_ranges=kb)
+            else:
+                _, gimg = tc_gemm(gimg, wt, B, K, N, aux_image=acts[l], out_image=True, k_block_ranges=kb)
+            g = None
     return gx, gws, gbs
 
 
@@ -592,14 +599,13 @@ class MadeTxFunctionTC(torch.autograd.Function):
             N, K = ws[l].shape
             wimg = tc_pack(ws[l], 256)
             if train:
-                h, img, img_t, _ = tc_gemm(img, wimg, B, N, K, c=True, bias=bs[l], activation=ACT_ELU, out_image=True,
+                _, img, img_t, _ = tc_gemm(img, wimg, B, N, K, bias=bs[l], activation=ACT_ELU, out_image=True,
                                            out_image_t=256, k_block_ranges=None if kb_fwd is None else kb_fwd[l])
             else:
-                need_h = ctx.needs_input_grad[0]                 # only grad_x wanted: ELU' still needs h
-                h, img = tc_gemm(img, wimg, B, N, K, c=True if need_h else None, bias=bs[l], activation=ACT_ELU,
-                                 out_image=True, k_block_ranges=None if kb_fwd is None else kb_fwd[l])
+                _, img = tc_gemm(img, wimg, B, N, K, bias=bs[l], activation=ACT_ELU, out_image=True,
+                                 k_block_ranges=None if kb_fwd is None else kb_fwd[l])
                 img_t = None
-            acts.append(h)
+            acts.append(img)                                     # bf16 image: next operand and ELU' operand of the backward pass
             acts_t.append(img_t)
         N, K = ws[-1].shape
         y = torch.empty_like(x)
@@ -608,8 +614,7 @@ class MadeTxFunctionTC(torch.autograd.Function):
                 tx=TcTx(spec['kind'], spec['cols'], x, y=y, logdet=logdet, max_radius=spec['max_radius'],
                         unit_sphere=spec['unit_sphere']))
         keep = any(ctx.needs_input_grad)
-        ctx.save_for_backward(*[a for a in acts if a is not None], *ws, bs[-1], *([img] if keep else []))
-        ctx.have_acts = [a is not None for a in acts]
+        ctx.save_for_backward(*(acts if keep else acts[:1]), *ws, bs[-1])
         ctx.acts_t = acts_t if keep else None
         ctx.meta = (L, kb_fwd, kb_bwd, rr_w, spec)
         if spec['kind'] == 'sos':
@@ -620,9 +625,8 @@ class MadeTxFunctionTC(torch.autograd.Function):
     def backward(ctx, grad_y, grad_ld):
         L, kb_fwd, kb_bwd, rr_w, spec = ctx.meta
         saved = list(ctx.saved_tensors)
-        acts = [saved.pop(0) if have else None for have in ctx.have_acts]
-        ws, b_last, last_img = saved[:L], saved[L], saved[L + 1]
-        x = acts[0]
+        acts, ws, b_last = saved[:L], saved[L:2 * L], saved[2 * L]
+        x, last_img = acts[0], acts[-1]
         B = x.shape[0]
         grad_y = torch.zeros_like(x) if grad_y is None else _rows(grad_y.contiguous())
         if grad_ld is not None:

@@ -59,6 +59,7 @@ struct Params {
     const float* bias;                  // (N,) or null
     int act;                            // TFEPB_ACT_*
     const float* aux; int64_t ldaux;    // multiply by ELU'(aux) = (h > 0 ? 1 : h + 1), or null
+    const uint8_t* aux_img; int aux_k_blocks;   // the same operand h as its bf16 image (128-row blocks, k = column), or null
     uint8_t* out_img; int out_k_blocks; // bf16 image (128-row blocks, k = column index) of the result, or null
     uint8_t* out_img_t;                 // bf16 image of the transposed result (rows = columns of C, k = rows of C), or null
     int t_rows, t_k_blocks, t_rows_padded;   // its block_rows (128 / 256), ceil(M / 64), rows rounded up to block_rows
@@ -386,6 +387,17 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             // accumulator chunks q, q + 1 (16 columns each) of this thread's row, bias added
             auto load_pair = [&](int q, float (&va)[16], float (&vb)[16]) {
                 uint32_t ra[16], rb[16];
+                // ELU' operand from the image of h: this row's 32 columns are four 16-byte pieces of consecutive slabs
+                // (consecutive rows = consecutive pieces: coalesced as is); requested together with the accumulator
+                uint4 h4[4];
+                const bool with_aux_img = p.aux_img != nullptr && !p.atomic && ((gnw + q * 16) >> 6) < p.aux_k_blocks;
+                if (with_aux_img) {
+                    const int gn0 = gnw + q * 16;
+                    const uint8_t* blk = p.aux_img + ((size_t)tm * p.aux_k_blocks + (gn0 >> 6)) * A_BLOCK + (size_t)row * 16 +
+                                         (size_t)((gn0 & 63) >> 3) * 2048;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) h4[j] = __ldg(reinterpret_cast<const uint4*>(blk + (size_t)j * 2048));
+                }
                 if (!empty) {
                     tmem_ld16(lane_addr + buf * BN + cgroup * 64 + q * 16, ra);
                     tmem_ld16(lane_addr + buf * BN + cgroup * 64 + q * 16 + 16, rb);
@@ -403,6 +415,17 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                         const float4 b4 = *reinterpret_cast<const float4*>(bias_w + q * 16 + 16 + 4 * i);
                         va[4 * i] += a4.x; va[4 * i + 1] += a4.y; va[4 * i + 2] += a4.z; va[4 * i + 3] += a4.w;
                         vb[4 * i] += b4.x; vb[4 * i + 1] += b4.y; vb[4 * i + 2] += b4.z; vb[4 * i + 3] += b4.w;
+                    }
+                }
+                if (with_aux_img) {
+                    const uint32_t hw[16] = {h4[0].x, h4[0].y, h4[0].z, h4[0].w, h4[1].x, h4[1].y, h4[1].z, h4[1].w,
+                                             h4[2].x, h4[2].y, h4[2].z, h4[2].w, h4[3].x, h4[3].y, h4[3].z, h4[3].w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        va[2 * i] *= fminf(__uint_as_float(hw[i] << 16), 0.f) + 1.f;
+                        va[2 * i + 1] *= fminf(__uint_as_float(hw[i] & 0xffff0000u), 0.f) + 1.f;
+                        vb[2 * i] *= fminf(__uint_as_float(hw[8 + i] << 16), 0.f) + 1.f;
+                        vb[2 * i + 1] *= fminf(__uint_as_float(hw[8 + i] & 0xffff0000u), 0.f) + 1.f;
                     }
                 }
             };
@@ -764,7 +787,8 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
                     "no output");
     if (tx != nullptr) {
         TFEPB_CHECK_ARG(tx->kind >= TFEPB_TCTX_AFFINE && tx->kind <= TFEPB_TCTX_MOEBIUS3, "unknown fused transformer kind %d", tx->kind);
-        TFEPB_CHECK_ARG(a->n_split <= 1 && a->split_k <= 1 && a->aux == nullptr && a->activation == TFEPB_ACT_NONE && a->n % 16 == 0,
+        TFEPB_CHECK_ARG(a->n_split <= 1 && a->split_k <= 1 && a->aux == nullptr && a->aux_image == nullptr &&
+                            a->activation == TFEPB_ACT_NONE && a->n % 16 == 0,
                         "fused transformer: plain bf16 product without split-K / aux / activation, n a multiple of 16");
         const int upc = tx->kind == TFEPB_TCTX_AFFINE ? 8 : tx->kind == TFEPB_TCTX_SOS2 ? 3 : 5;
         TFEPB_CHECK_ARG(tx->n_units > 0 && (int64_t)a->n >= ((int64_t)tx->n_units + upc - 1) / upc * 16,
@@ -784,17 +808,22 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
     TFEPB_CHECK_ARG((uintptr_t)a->out_image_t % 16 == 0, "operand images must be 16-byte aligned");
     TFEPB_CHECK_ARG(a->c == nullptr || a->ldc >= a->n, "leading dimension smaller than the row length");
     TFEPB_CHECK_ARG(!(a->split_k > 1) || (a->c != nullptr && a->out_image == nullptr && a->out_image_t == nullptr &&
-                                          a->column_sums == nullptr && a->bias == nullptr && a->aux == nullptr &&
+                                          a->column_sums == nullptr && a->bias == nullptr && a->aux == nullptr && a->aux_image == nullptr &&
                                           a->activation == TFEPB_ACT_NONE),
                     "split-K accumulates raw products into a zero-filled fp32 C only");
     TFEPB_CHECK_ARG(((uintptr_t)a->a_image % 16 == 0) && ((uintptr_t)a->b_image % 16 == 0) && ((uintptr_t)a->out_image % 16 == 0),
                     "operand images must be 16-byte aligned");
+    TFEPB_CHECK_ARG(a->aux_image == nullptr || (a->aux == nullptr && (uintptr_t)a->aux_image % 16 == 0),
+                    "aux and aux_image are alternatives; images are 16-byte aligned");
+    TFEPB_CHECK_ARG(a->aux_image == nullptr || (a->activation == TFEPB_ACT_NONE && a->n_split <= 1),
+                    "aux_image: plain bf16 product without activation");
     if (int rc = require_sm100()) return rc;
     tcg::Params p{};
     p.a_img = (const uint8_t*)a->a_image; p.b_img = (const uint8_t*)a->b_image;
     p.M = a->m; p.N = a->n; p.K = a->k; p.k_blocks = (a->k + tcg::KB - 1) / tcg::KB;
     p.C = (float*)a->c; p.ldc = a->ldc; p.bias = (const float*)a->bias; p.act = a->activation;
     p.aux = (const float*)a->aux; p.ldaux = a->ldaux;
+    p.aux_img = (const uint8_t*)a->aux_image; p.aux_k_blocks = (a->n + tcg::KB - 1) / tcg::KB;
     p.out_img = (uint8_t*)a->out_image; p.out_k_blocks = (a->n + tcg::KB - 1) / tcg::KB;
     p.out_img_t = (uint8_t*)a->out_image_t; p.t_rows = a->out_image_t != nullptr ? a->out_image_t_rows : 128;
     p.t_k_blocks = (a->m + tcg::KB - 1) / tcg::KB; p.t_rows_padded = (a->n + p.t_rows - 1) / p.t_rows * p.t_rows;
