@@ -36,8 +36,9 @@ for fuse in modes:
         with torch.no_grad():
             return seq3(x3)
 
-    for name, fn, n in (('train_step_ms', step3, 3), ('forward_only_ms', fwd, 5)):
-        for _ in range(2):
+    quick = os.environ.get('DEV_CFG3_QUICK') == '1'
+    for name, fn, n in ((('train_step_ms', step3, 1),) if quick else (('train_step_ms', step3, 3), ('forward_only_ms', fwd, 5))):
+        for _ in range(1 if quick else 2):
             out = fn()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -47,7 +48,8 @@ for fuse in modes:
         b.record()
         torch.cuda.synchronize()
         res[f'{"fused" if fuse else "separate"}_{name}'] = a.elapsed_time(b) / n
-    res[f'{"fused" if fuse else "separate"}_loss'] = float(step3().detach())
+    if not quick:
+        res[f'{"fused" if fuse else "separate"}_loss'] = float(step3().detach())
     res[f'{"fused" if fuse else "separate"}_peak_gb'] = torch.cuda.max_memory_allocated() / 2**30
     del seq3, opt
     torch.cuda.empty_cache()

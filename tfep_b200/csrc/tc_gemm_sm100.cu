@@ -105,12 +105,23 @@ template <int XC>
 __device__ __forceinline__ void tx_stage_in(const float* __restrict__ src, int64_t ld, int gm0, int M, const int* __restrict__ cols,
                                             int c0, int cn, float* buf, int lane) {
     constexpr int CW = XC <= 4 ? 4 : XC <= 8 ? 8 : XC <= 16 ? 16 : 32;
+    constexpr int RPI = 32 / CW;                                    // rows per warp instruction
     const int c = lane % CW, r0 = lane / CW;
     if (c < XC) {
         const int col = c0 + c < cn ? __ldg(cols + c0 + c) : -1;
+        float* dst = buf + c * XP_LD + r0;
+        if (col >= 0 && gm0 + 32 <= M) {                            // all 32 rows exist: no per-row test, running pointer
+            const float* s = src + (int64_t)(gm0 + r0) * ld + col;
+            const int64_t step = (int64_t)RPI * ld;
 #pragma unroll
-        for (int r = r0; r < 32; r += 32 / CW)
-            buf[c * XP_LD + r] = (col >= 0 && gm0 + r < M) ? __ldg(src + (int64_t)(gm0 + r) * ld + col) : 0.f;
+            for (int i = 0; i < CW; ++i, s += step) dst[i * RPI] = __ldg(s);
+        } else {
+#pragma unroll
+            for (int i = 0; i < CW; ++i) {
+                const int r = r0 + i * RPI;
+                dst[i * RPI] = (col >= 0 && gm0 + r < M) ? __ldg(src + (int64_t)(gm0 + r) * ld + col) : 0.f;
+            }
+        }
     }
 }
 
@@ -118,12 +129,21 @@ template <int XC>
 __device__ __forceinline__ void tx_stage_out(float* __restrict__ dst, int64_t ld, int gm0, int M, const int* __restrict__ cols,
                                              int c0, int cn, const float* buf, int lane) {
     constexpr int CW = XC <= 4 ? 4 : XC <= 8 ? 8 : XC <= 16 ? 16 : 32;
+    constexpr int RPI = 32 / CW;
     const int c = lane % CW, r0 = lane / CW;
     if (c < XC && c0 + c < cn) {
         const int col = __ldg(cols + c0 + c);
+        const float* s = buf + c * XP_LD + r0;
+        float* d = dst + (int64_t)(gm0 + r0) * ld + col;
+        const int64_t step = (int64_t)RPI * ld;
+        if (gm0 + 32 <= M) {
 #pragma unroll
-        for (int r = r0; r < 32; r += 32 / CW)
-            if (gm0 + r < M) dst[(int64_t)(gm0 + r) * ld + col] = buf[c * XP_LD + r];
+            for (int i = 0; i < CW; ++i, d += step) *d = s[i * RPI];
+        } else {
+#pragma unroll
+            for (int i = 0; i < CW; ++i, d += step)
+                if (gm0 + r0 + i * RPI < M) *d = s[i * RPI];
+        }
     }
 }
 
@@ -361,23 +381,31 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             const int gm = gm0 + lane;
             const bool row_ok = gm < p.M;
             const bool empty = k1 <= k0;                       // nothing was accumulated: the tile is all zeros
-            const int gnw = tn * BN + cgroup * 64;             // first column of this warp
+            // The warp's two sub-tiles are INTERLEAVED over the tile (sub-tile s of the warp = 32-column block s * 4 + cgroup
+            // of the tile): a last tile with few valid columns still spreads over all four column groups.
+            const int gn_sub0 = tn * BN + cgroup * 32, gn_sub1 = gn_sub0 + 128;
+            auto gcol = [&](int q) { return (q < 2 ? gn_sub0 : gn_sub1) + (q & 1) * 16; };     // first column of chunk q (0..3)
             // What does not depend on the accumulator is fetched BEFORE waiting for it: the bias of the warp's columns and,
             // for a fused transformer, the first staging group of x (and grad_y).
             const bool with_bias = !p.atomic && p.bias != nullptr;
             if (with_bias) {
-                bias_w[lane] = gnw + lane < p.N ? __ldg(p.bias + gnw + lane) : 0.f;
-                bias_w[lane + 32] = gnw + 32 + lane < p.N ? __ldg(p.bias + gnw + 32 + lane) : 0.f;
+                bias_w[lane] = gn_sub0 + lane < p.N ? __ldg(p.bias + gn_sub0 + lane) : 0.f;
+                bias_w[lane + 32] = gn_sub1 + lane < p.N ? __ldg(p.bias + gn_sub1 + lane) : 0.f;
             }
             using TG = TxGeo<TX>;
-            [[maybe_unused]] const int chunk0 = gnw >> 4;                       // first parameter chunk of this warp
             [[maybe_unused]] const int tx_cn = p.tx_units * TG::XPU;            // x columns in the table
             [[maybe_unused]] float gl = 0.f;
             if constexpr (TX != 0 && !tx_bwd(TX)) {
-                tx_stage_in<TG::GF * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, chunk0 * TG::XPC, tx_cn, xp, lane);
+                // x of the first sub-tile's two chunks, and of the second one's where the buffer holds both (GF == 4)
+                tx_stage_in<2 * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, (gn_sub0 >> 4) * TG::XPC, tx_cn, xp, lane);
+                if constexpr (TG::GF == 4) {
+                    if (gn_sub1 < p.N)
+                        tx_stage_in<2 * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, (gn_sub1 >> 4) * TG::XPC, tx_cn,
+                                                 xp + 2 * TG::XPC * XP_LD, lane);
+                }
             } else if constexpr (TX != 0) {
-                tx_stage_in<TG::GB * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, chunk0 * TG::XPC, tx_cn, xp, lane);
-                tx_stage_in<TG::GB * TG::XPC>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, chunk0 * TG::XPC, tx_cn,
+                tx_stage_in<TG::GB * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, (gn_sub0 >> 4) * TG::XPC, tx_cn, xp, lane);
+                tx_stage_in<TG::GB * TG::XPC>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, (gn_sub0 >> 4) * TG::XPC, tx_cn,
                                                xp + TG::GB * TG::XPC * XP_LD, lane);
                 if (p.tx_gl != nullptr && row_ok) gl = __ldg(p.tx_gl + gm);
             }
@@ -390,17 +418,18 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                 // ELU' operand from the image of h: this row's 32 columns are four 16-byte pieces of consecutive slabs
                 // (consecutive rows = consecutive pieces: coalesced as is); requested together with the accumulator
                 uint4 h4[4];
-                const bool with_aux_img = p.aux_img != nullptr && !p.atomic && ((gnw + q * 16) >> 6) < p.aux_k_blocks;
+                const bool with_aux_img = p.aux_img != nullptr && !p.atomic && (gcol(q) >> 6) < p.aux_k_blocks;
                 if (with_aux_img) {
-                    const int gn0 = gnw + q * 16;
+                    const int gn0 = gcol(q);
                     const uint8_t* blk = p.aux_img + ((size_t)tm * p.aux_k_blocks + (gn0 >> 6)) * A_BLOCK + (size_t)row * 16 +
                                          (size_t)((gn0 & 63) >> 3) * 2048;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) h4[j] = __ldg(reinterpret_cast<const uint4*>(blk + (size_t)j * 2048));
                 }
                 if (!empty) {
-                    tmem_ld16(lane_addr + buf * BN + cgroup * 64 + q * 16, ra);
-                    tmem_ld16(lane_addr + buf * BN + cgroup * 64 + q * 16 + 16, rb);
+                    const uint32_t tcol = buf * BN + (uint32_t)(gcol(q) - tn * BN);
+                    tmem_ld16(lane_addr + tcol, ra);
+                    tmem_ld16(lane_addr + tcol + 16, rb);
                     tmem_wait8(ra); tmem_wait8(ra + 8); tmem_wait8(rb); tmem_wait8(rb + 8);
                 } else {
 #pragma unroll
@@ -432,7 +461,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             // activation / ELU' / padding, then the chunk goes to the transposition buffer and to the image of the result
             auto emit_chunk = [&](int q, float (&v)[16]) {
                 const int c16 = q & 1;
-                const int gn0 = gnw + q * 16;
+                const int gn0 = gcol(q);
                 if (!p.atomic) {
                     if (p.act == TFEPB_ACT_ELU) {
 #pragma unroll
@@ -486,31 +515,28 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                 // GF chunks per staging group; y and the log-det are the only outputs ----
                 float ld_acc = 0.f;
 #pragma unroll 1
-                for (int g = 0; g < 4 / TG::GF; ++g) {
-                    if (gnw + g * TG::GF * 16 >= p.N) break;                                   // warp-uniform
-                    const int c0 = (chunk0 + g * TG::GF) * TG::XPC;
-                    if (g > 0) {
-                        tx_stage_in<TG::GF * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, xp, lane);
+                for (int sub = 0; sub < 2; ++sub) {
+                    const int gns = sub == 0 ? gn_sub0 : gn_sub1;
+                    if (gns >= p.N) break;                                                     // warp-uniform
+                    const int c0 = (gns >> 4) * TG::XPC;
+                    float* xs = xp + (TG::GF == 4 ? sub * 2 * TG::XPC * XP_LD : 0);
+                    if (TG::GF != 4 && sub > 0) {
+                        tx_stage_in<2 * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, xs, lane);
                         __syncwarp();
                     }
-#pragma unroll 1
-                    for (int pr = 0; pr < TG::GF / 2; ++pr) {
-                        const int q = g * TG::GF + 2 * pr;
-                        if (gnw + q * 16 >= p.N) break;
-                        float va[16], vb[16];
-                        load_pair(q, va, vb);
-                        tx_chunk<TX>(p, va, xp + (2 * pr) * TG::XPC * XP_LD, nullptr, lane, 0.f, row_ok, chunk0 + q, ld_acc);
-                        tx_chunk<TX>(p, vb, xp + (2 * pr + 1) * TG::XPC * XP_LD, nullptr, lane, 0.f, row_ok, chunk0 + q + 1, ld_acc);
-                    }
+                    float va[16], vb[16];
+                    load_pair(2 * sub, va, vb);
+                    tx_chunk<TX>(p, va, xs, nullptr, lane, 0.f, row_ok, gns >> 4, ld_acc);
+                    tx_chunk<TX>(p, vb, xs + TG::XPC * XP_LD, nullptr, lane, 0.f, row_ok, (gns >> 4) + 1, ld_acc);
                     __syncwarp();
-                    tx_stage_out<TG::GF * TG::XPC>(p.tx_y, p.tx_ldy, gm0, p.M, p.tx_cols, c0, tx_cn, xp, lane);
+                    tx_stage_out<2 * TG::XPC>(p.tx_y, p.tx_ldy, gm0, p.M, p.tx_cols, c0, tx_cn, xs, lane);
                     __syncwarp();
                 }
                 if (row_ok && p.tx_logdet != nullptr) atomicAdd(p.tx_logdet + gm, ld_acc);
             } else {
 #pragma unroll 1
                 for (int sub = 0; sub < 2; ++sub) {
-                    const int gns = gnw + sub * 32;                // first column of the sub-tile
+                    const int gns = sub == 0 ? gn_sub0 : gn_sub1;  // first column of the sub-tile
                     if (gns >= p.N && p.out_img == nullptr && (p.out_img_t == nullptr || gns >= p.t_rows_padded)) continue;   // warp-uniform
                     if (p.aux != nullptr && !p.atomic) {
                         // coalesced load of the 32 x 32 ELU' operand: lane = column, transposed into the buffer
@@ -529,28 +555,28 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                         float unused = 0.f;
                         constexpr int XG = TG::GB * TG::XPC;                                       // x columns per staging group
                         if constexpr (TG::GB == 2) {
-                            const int c0 = (chunk0 + 2 * sub) * TG::XPC;
+                            const int c0 = (gns >> 4) * TG::XPC;
                             if (sub > 0) {
                                 tx_stage_in<XG>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, xp, lane);
                                 tx_stage_in<XG>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, c0, tx_cn, xp + XG * XP_LD, lane);
                                 __syncwarp();
                             }
-                            tx_chunk<TX>(p, va, xp, xp + XG * XP_LD, lane, gl, row_ok, chunk0 + 2 * sub, unused);
+                            tx_chunk<TX>(p, va, xp, xp + XG * XP_LD, lane, gl, row_ok, gns >> 4, unused);
                             tx_chunk<TX>(p, vb, xp + TG::XPC * XP_LD, xp + (XG + TG::XPC) * XP_LD, lane, gl, row_ok,
-                                         chunk0 + 2 * sub + 1, unused);
+                                         (gns >> 4) + 1, unused);
                             __syncwarp();
                             tx_stage_out<XG>(p.tx_gx, p.tx_ldgx, gm0, p.M, p.tx_cols, c0, tx_cn, xp + XG * XP_LD, lane);
                             __syncwarp();
                         } else {
 #pragma unroll
                             for (int c16 = 0; c16 < 2; ++c16) {
-                                const int c0 = (chunk0 + 2 * sub + c16) * TG::XPC;
+                                const int c0 = ((gns >> 4) + c16) * TG::XPC;
                                 if (sub > 0 || c16 > 0) {
                                     tx_stage_in<XG>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, xp, lane);
                                     tx_stage_in<XG>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, c0, tx_cn, xp + XG * XP_LD, lane);
                                     __syncwarp();
                                 }
-                                tx_chunk<TX>(p, c16 == 0 ? va : vb, xp, xp + XG * XP_LD, lane, gl, row_ok, chunk0 + 2 * sub + c16, unused);
+                                tx_chunk<TX>(p, c16 == 0 ? va : vb, xp, xp + XG * XP_LD, lane, gl, row_ok, (gns >> 4) + c16, unused);
                                 __syncwarp();
                                 tx_stage_out<XG>(p.tx_gx, p.tx_ldgx, gm0, p.M, p.tx_cols, c0, tx_cn, xp + XG * XP_LD, lane);
                                 __syncwarp();
@@ -567,12 +593,21 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                         const int nrows = min(32, p.M - gm0);              // rows beyond M carry the bias only: zero them
                         float cs = 0.f;
                         uint32_t q[16];
+                        if (nrows == 32) {
 #pragma unroll
-                        for (int r = 0; r < 32; r += 2) {
-                            const float v0 = r < nrows ? xp[lane * XP_LD + r] : 0.f;
-                            const float v1 = r + 1 < nrows ? xp[lane * XP_LD + r + 1] : 0.f;
-                            cs += v0 + v1;
-                            q[r >> 1] = pack_bf16(v0, v1);
+                            for (int r = 0; r < 32; r += 2) {
+                                const float v0 = xp[lane * XP_LD + r], v1 = xp[lane * XP_LD + r + 1];
+                                cs += v0 + v1;
+                                q[r >> 1] = pack_bf16(v0, v1);
+                            }
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < 32; r += 2) {
+                                const float v0 = r < nrows ? xp[lane * XP_LD + r] : 0.f;
+                                const float v1 = r + 1 < nrows ? xp[lane * XP_LD + r + 1] : 0.f;
+                                cs += v0 + v1;
+                                q[r >> 1] = pack_bf16(v0, v1);
+                            }
                         }
                         if (p.out_img_t != nullptr && n < p.t_rows_padded && (gm0 >> 6) < p.t_k_blocks) {
                             const size_t block_bytes = (size_t)p.t_rows * 128;

@@ -25,6 +25,25 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Up to 256 polls in a four-instruction loop (try_wait itself suspends the warp for a hardware-defined time): the
+// bookkeeping of the watchdog runs once per burst, not once per poll (ncu, r02: the polling loops of the waiting warps
+// were a fifth of all issued instructions of the epilogue-bound tc_gemm kernels).
+__device__ __forceinline__ bool mbar_poll_burst(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n\t"
+        "POLL_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.lt.u32 q, n, 256;\n\t"
+        "@q bra POLL_%=;\n\t"
+        "DONE_%=:\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -53,10 +72,11 @@ static __device__ __forceinline__ void mbar_wait_slow(uint64_t* bar, uint32_t pa
 }
 #else
 static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int* error, int tag) {
-    uint32_t polls = 0;
+    uint32_t bursts = 0;
     long long t0 = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++polls & 0xfffu) != 0) continue;          // look at the clock every 4096 failed polls only
+    const uint32_t addr = smem_u32(bar);
+    while (!mbar_poll_burst(addr, parity)) {
+        if ((++bursts & 0xfu) != 0) continue;           // look at the clock every 4096 failed polls only
         if (t0 == 0) t0 = clock64();
         if ((uint64_t)(clock64() - t0) > WATCHDOG_CYCLES) {
             if (error) atomicExch(error, tag);
