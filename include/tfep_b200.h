@@ -180,6 +180,24 @@ int tfepb_moebius_backward(const tfepb_tx_io* io, int32_t dimension, double max_
                            const tfepb_tx_grads* g, tfepb_stream_t stream);
 
 /* ----------------------------------------------------------------------------------------------
+ * Packed effective weight of a weight-normalised masked linear layer, one launch (fp32).  Replaces, for the training path,
+ * MaskedWeightNorm.compute_weight + _ApplyMask + the mask multiply of MaskedLinearFunc.forward (nn/masked.py:369-371,
+ * 433-439, 270) followed by the row / column permutation of the degree-sorted conditioner, and their autograd backward:
+ *   out[r][c] = mask[i][j] v[i][j] g[i] / s_i,  i = row_perm[r] (-1: a zero row), j = col_perm[c] (NULL: c),
+ *   s_i = |v[i]| over all `cols` columns (1 if the norm is zero); columns [cols, out_cols) of `out` are zero padding;
+ *   bias_out[r] = bias[i] (both NULL to skip).
+ * Backward: grad_v (rows x cols, ldgv), grad_g (rows), grad_bias (rows) from grad_out (out_rows x cols, ldgo) and
+ * grad_bias_out; rows of v that no packed row refers to are left untouched (zero-fill them if row_perm is not onto).
+ * -------------------------------------------------------------------------------------------- */
+int tfepb_wn_pack(const float* v, int64_t ldv, const float* g, const float* mask, int64_t ldm, const float* bias,
+                  int32_t rows, int32_t cols, const int32_t* row_perm, int32_t out_rows, const int32_t* col_perm,
+                  float* out, int64_t ldo, int32_t out_cols, float* bias_out, tfepb_stream_t stream);
+int tfepb_wn_pack_backward(const float* v, int64_t ldv, const float* g, const float* mask, int64_t ldm, int32_t rows,
+                           int32_t cols, const int32_t* row_perm, int32_t out_rows, const int32_t* col_perm,
+                           const float* grad_out, int64_t ldgo, const float* grad_bias_out, float* grad_v, int64_t ldgv,
+                           float* grad_g, float* grad_bias, tfepb_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------------
  * General masked linear layers on the tensor cores (tcgen05, bf16 operands, fp32 accumulation): any MADE shape,
  * forward and backward.  C[m x n] = A[m x k] . B[n x k]^T with operand IMAGES made by tfepb_tc_pack: blocks of
  * (block_rows x 64 k) bf16, block (rb, kb) at (rb * ceil(k / 64) + kb) * block_rows * 128 bytes, inside a block the
@@ -260,7 +278,7 @@ typedef struct {
                                             split-precision images (tfepb_tc_pack_split); every k-step accumulates the
                                             3 / 6 products A_i B_j with i + j < n_split in fp32 -- operands carried to
                                             16 / 24 significant bits (forward products only) */
-    int32_t reserved;
+    int32_t c_accumulate;                /* != 0: c += result instead of c = result (without split_k, which always adds) */
     const tfepb_tc_tx* tx;               /* NULL, or the transformer fused into the epilogue (n_split <= 1, no split_k,
                                             n a multiple of 16, activation NONE, no aux) */
     const void* aux_image;               /* alternative to aux: the same (m, n) operand h given as its bf16 image (block_rows =

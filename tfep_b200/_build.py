@@ -18,7 +18,7 @@ LIBPATH = os.path.join(LIBDIR, 'libtfep_b200.so')
 OBJDIR = os.path.join(HERE, 'build')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
-SOURCES = ['core.cu', 'gemm_simt.cu', 'transformers.cu', 'analysis.cu', 'maf_fused_sm100.cu', 'maf_fused_inv_sm100.cu', 'maf_inverse.cu', 'tc_gemm_sm100.cu', 'frames.cu', 'loss.cu', 'mt19937_jump.cu']
+SOURCES = ['core.cu', 'gemm_simt.cu', 'transformers.cu', 'analysis.cu', 'maf_fused_sm100.cu', 'maf_fused_inv_sm100.cu', 'maf_inverse.cu', 'tc_gemm_sm100.cu', 'frames.cu', 'loss.cu', 'mt19937_jump.cu', 'weights.cu']
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',

@@ -103,7 +103,7 @@ class TcGemmArgs(Structure):
                 ('activation', c_int32), ('c', c_void_p), ('ldc', c_int64), ('bias', c_void_p), ('aux', c_void_p),
                 ('ldaux', c_int64), ('out_image', c_void_p), ('k_block_ranges', c_void_p), ('split_k', c_int32),
                 ('out_image_t_rows', c_int32), ('error_flag', c_void_p), ('row_ranges', c_void_p),
-                ('out_image_t', c_void_p), ('column_sums', c_void_p), ('n_split', c_int32), ('reserved', c_int32),
+                ('out_image_t', c_void_p), ('column_sums', c_void_p), ('n_split', c_int32), ('c_accumulate', c_int32),
                 ('tx', POINTER(TcTx)), ('aux_image', c_void_p)]
 
 
@@ -158,6 +158,10 @@ SYMBOLS = {
     'tfepb_tc_pack_split': (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     'tfepb_tc_pack_dual': (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     'tfepb_tc_gemm': (c_int32, [POINTER(TcGemmArgs), c_void_p]),
+    'tfepb_wn_pack': (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_int32,
+                                c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
+    'tfepb_wn_pack_backward': (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32,
+                                         c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     'tfepb_centroid_pre': (c_int32, [POINTER(CentroidArgs), c_void_p]),
     'tfepb_centroid_post': (c_int32, [POINTER(CentroidArgs), c_void_p]),
     'tfepb_oriented_pre': (c_int32, [POINTER(OrientedArgs), c_void_p]),

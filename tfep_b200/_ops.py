@@ -146,6 +146,55 @@ class MadeFunction(torch.autograd.Function):
         return (gx, None, None, None, *gws, *gbs)
 
 
+class PackedWeightFunction(torch.autograd.Function):
+    """(W_packed, b_packed) of a weight-normalised masked layer in one launch, with its VJP in one launch (tfepb_wn_pack):
+    ``W_packed[r, c] = (M o g v / |v|)[row_perm[r], col_perm[c]]`` (row_perm -1 = zero row), leading dimension padded to
+    16 bytes.  Same values and gradients as ``masked.effective_weight`` followed by ``MadePlan.pack``."""
+
+    @staticmethod
+    def forward(ctx, v, g, bias, mask, row_perm, col_perm, onto):
+        R0, C = v.shape
+        R = R0 if row_perm is None else row_perm.numel()
+        ldo = (C + 3) // 4 * 4
+        out = torch.empty((R, ldo), dtype=torch.float32, device=v.device)
+        b_out = torch.empty(R, dtype=torch.float32, device=v.device) if bias is not None else None
+        with torch.cuda.device(v.device):
+            check(_lib.load().tfepb_wn_pack(ptr(v), _ld(v), ptr(g), ptr(mask), 0 if mask is None else _ld(mask), ptr(bias), R0, C,
+                                            ptr(row_perm), R, ptr(col_perm), ptr(out), ldo, ldo, ptr(b_out), stream_ptr(v)))
+        ctx.save_for_backward(v, g, mask, row_perm, col_perm)
+        ctx.onto, ctx.has_bias = onto, bias is not None
+        w = out[:, :C]
+        return w, b_out
+
+    @staticmethod
+    def backward(ctx, gw, gb):
+        v, g, mask, row_perm, col_perm = ctx.saved_tensors
+        R0, C = v.shape
+        R = R0 if row_perm is None else row_perm.numel()
+        gw = _rows(gw.contiguous() if gw.stride(1) != 1 else gw)
+        alloc = torch.empty if ctx.onto else torch.zeros
+        gv = alloc((R0, C), dtype=torch.float32, device=v.device)
+        gg = alloc(g.shape, dtype=torch.float32, device=v.device)
+        want_b = ctx.has_bias and gb is not None
+        gbias = alloc(R0, dtype=torch.float32, device=v.device) if want_b else None
+        with torch.cuda.device(v.device):
+            check(_lib.load().tfepb_wn_pack_backward(ptr(v), _ld(v), ptr(g), ptr(mask), 0 if mask is None else _ld(mask), R0, C,
+                                                     ptr(row_perm), R, ptr(col_perm), ptr(gw), _ld(gw),
+                                                     ptr(gb.contiguous()) if want_b else None, ptr(gv), C, ptr(gg), ptr(gbias),
+                                                     stream_ptr(v)))
+        return gv, gg, gbias, None, None, None, None
+
+
+def wn_pack(v, g, bias, mask, row_perm=None, col_perm=None, onto=True):
+    """See :class:`PackedWeightFunction`.  ``onto``: every row of ``v`` is referred to by ``row_perm`` (else the gradients of
+    the other rows are zero-filled)."""
+    require_cuda(v, g, bias, mask)
+    if v.dtype != torch.float32:
+        raise _lib.TfepB200Error('wn_pack takes float32 parameters')
+    return PackedWeightFunction.apply(v.contiguous(), g.contiguous(), None if bias is None else bias.contiguous(),
+                                      None if mask is None else _rows(mask), row_perm, col_perm, onto)
+
+
 def made_forward(x, weights, biases, k_ranges=None, n_ranges=None):
     return MadeFunction.apply(x, len(weights), k_ranges, n_ranges, *weights, *biases)
 
@@ -441,13 +490,14 @@ class TcTx:
 
 def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, aux=None, out_image=False,
             k_block_ranges=None, row_ranges=None, split_k=1, error_flag=None, out_image_t=None, column_sums=False, n_split=1,
-            tx=None, aux_image=None):
+            tx=None, aux_image=None, accumulate=False):
     """C = act(A B^T + bias) [* ELU'(aux)] from operand images; returns (c, out_img).  ``c``: True to allocate, a
     tensor to write into (zero-filled by the caller when split_k > 1), None for no fp32 output.
     ``out_image_t`` = 128 / 256: also the image of the transposed result with that block_rows; ``column_sums``: also
     the sums over the m rows; with either, returns (c, out_img, out_img_t, column_sums).  ``tx``: a :class:`TcTx`, the
     transformer applied by the epilogue (the columns are then parameter chunks, see tfepb_tc_tx).  ``aux_image``: the
-    ELU' operand as the bf16 image a forward product wrote (instead of the fp32 ``aux``)."""
+    ELU' operand as the bf16 image a forward product wrote (instead of the fp32 ``aux``).  ``accumulate``: ``c`` (a tensor)
+    += the result."""
     lib = _lib.load()
     dev = a_img.device
     if c is True:
@@ -470,7 +520,8 @@ def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, au
                         error_flag=None if error_flag is None else error_flag.data_ptr(),
                         row_ranges=None if row_ranges is None else row_ranges.data_ptr(),
                         out_image_t=None if img_t is None else img_t.data_ptr(),
-                        column_sums=None if sums is None else sums.data_ptr(), n_split=int(n_split), reserved=0)
+                        column_sums=None if sums is None else sums.data_ptr(), n_split=int(n_split),
+                        c_accumulate=int(bool(accumulate)))
     if tx is not None:
         txs = tx.struct()                 # kept alive until the launch returns
         a.tx = ctypes.pointer(txs)
@@ -543,7 +594,7 @@ class MadeFunctionTC(torch.autograd.Function):
         return (gx, None, None, None, None, *gws, *gbs)
 
 
-def _made_tc_backward_layers(acts, acts_t, ws, kb_bwd, rr_w, need_w, need_x, g, gimg, gimg_t, gb):
+def _made_tc_backward_layers(acts, acts_t, ws, kb_bwd, rr_w, need_w, need_x, g, gimg, gimg_t, gb, gx_into=None):
     """Backward pass of the layers of a MADE on the tensor cores, given the cotangent of the output layer's result as
     operand images (``gimg``: A operand of the backward-input product; ``gimg_t``: A operand of the weight gradient, or
     None -> packed from the fp32 ``g``; ``gb``: its column sums, or None).  ``acts``: the input x (fp32) followed by the
@@ -568,7 +619,9 @@ def _made_tc_backward_layers(acts, acts_t, ws, kb_bwd, rr_w, need_w, need_x, g, 
             wt = tc_pack(ws[l], 256, transpose=True)            # rows = inputs of the layer, k = its outputs
             kb = None if kb_bwd is None else kb_bwd[l]
             if l == 0:
-                gx, _ = tc_gemm(gimg, wt, B, K, N, c=True, k_block_ranges=kb)
+                # ``gx_into``: the cotangent of x is ADDED to that tensor (the direct term of a fused transformer)
+                gx, _ = tc_gemm(gimg, wt, B, K, N, c=True if gx_into is None else gx_into, accumulate=gx_into is not None,
+                                k_block_ranges=kb)
             elif need_w[l - 1]:
                 # the cotangent of a hidden activation exists as operand images (and column sums) only
                 _, gimg, gimg_t, gb = tc_gemm(gimg, wt, B, K, N, aux_image=acts[l], out_image=True, out_image_t=128,
@@ -639,11 +692,9 @@ class MadeTxFunctionTC(torch.autograd.Function):
                                       k_block_ranges=None if kb_fwd is None else kb_fwd[-1],
                                       tx=TcTx(spec['kind'], spec['cols'], x, grad_y=grad_y, grad_logdet=grad_ld, grad_x=gx,
                                               max_radius=spec['max_radius'], unit_sphere=spec['unit_sphere']))
-        gx_made, gws, gbs = _made_tc_backward_layers(acts, ctx.acts_t, ws, kb_bwd, rr_w, need_w, ctx.needs_input_grad[0],
-                                                     None, gimg, gimg_t, gb)
+        _, gws, gbs = _made_tc_backward_layers(acts, ctx.acts_t, ws, kb_bwd, rr_w, need_w, ctx.needs_input_grad[0],
+                                               None, gimg, gimg_t, gb, gx_into=gx)
         ctx.acts_t = None
-        if gx_made is not None:
-            gx += gx_made
         return (gx if ctx.needs_input_grad[0] else None, None, None, None, None, None, *gws, *gbs)
 
 

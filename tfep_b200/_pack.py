@@ -56,7 +56,12 @@ class MadePlan:
         for l in range(1, self.n_layers):
             self.perms.append(_stable_argsort(chain[l]))
         self.perms.append(torch.arange(len(chain[-1])) if out_order is None else torch.as_tensor(out_order).long().cpu())
-        self.packed_degrees = [chain[l][self.perms[l]] for l in range(self.n_layers + 1)]
+        # out_order may hold -1 entries: all-zero padding rows of the packed output layer (tfep_b200/_txfused.py); their
+        # "degree" is below every input degree, so the masks, ranges and counts below see them as empty rows
+        last = self.perms[-1]
+        self.has_padding = bool((last < 0).any())
+        self.packed_degrees = [chain[l][self.perms[l]] for l in range(self.n_layers)]
+        self.packed_degrees.append(torch.where(last >= 0, chain[-1][last.clamp(min=0)], torch.full_like(last, -(1 << 30))))
         self.k_ranges, self.n_ranges, self.nnz = [], [], []
         for l in range(self.n_layers):
             d_in, d_out = self.packed_degrees[l], self.packed_degrees[l + 1]
@@ -76,8 +81,11 @@ class MadePlan:
         """(k_ranges, n_ranges) as lists of int32 device tensors."""
         key = str(device)
         if key not in self._device_cache:
-            self._device_cache[key] = ([r.to(device) for r in self.k_ranges], [r.to(device) for r in self.n_ranges],
-                                       [p.to(device) for p in self.perms])
+            perms = [p.to(device) for p in self.perms]
+            if self.has_padding:
+                n_out = len(self.perms[-1]) - int((self.perms[-1] < 0).sum())      # = index of the appended zero row
+                perms[-1] = torch.where(perms[-1] >= 0, perms[-1], torch.full_like(perms[-1], n_out))
+            self._device_cache[key] = ([r.to(device) for r in self.k_ranges], [r.to(device) for r in self.n_ranges], perms)
         return self._device_cache[key]
 
     @staticmethod
@@ -112,12 +120,26 @@ class MadePlan:
             self._device_cache[key] = (fwd, bwd, roww)
         return self._device_cache[key]
 
+    def perm_tables(self, device):
+        """int32 device copies of the permutations for tfepb_wn_pack: rows of layer l are ``[l + 1]`` (-1 = zero row),
+        columns ``[l]`` (None for the identity of the input layer)."""
+        key = ('perm32', str(device))
+        if key not in self._device_cache:
+            t = [p.to(device=device, dtype=torch.int32) for p in self.perms]
+            t[0] = None
+            self._device_cache[key] = t
+        return self._device_cache[key]
+
     def pack(self, weights, biases):
         """Permute effective weights / biases given in the reference's order into packed order."""
         device = weights[0].device
         perms = self.tables(device)[2]
         pw, pb = [], []
         for l, (w, b) in enumerate(zip(weights, biases)):
+            if l == self.n_layers - 1 and self.has_padding:
+                # -1 entries select an appended zero row
+                w = torch.cat([w, w.new_zeros(1, w.shape[1])])
+                b = torch.cat([b, b.new_zeros(1)])
             w = w.index_select(0, perms[l + 1])
             if l > 0:
                 w = w.index_select(1, perms[l])

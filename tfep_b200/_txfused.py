@@ -64,12 +64,14 @@ class TcTxPlan:
         n_units = n_rows // ppu
         n_chunks = (n_units + upc - 1) // upc
         self.n_padded = n_chunks * 16
-        # padded row -> packed row (n_rows = the appended zero row): units are consecutive runs of `ppu` packed rows
+        # padded position -> packed row (-1 = zero row): units are consecutive runs of `ppu` packed rows
         t = torch.arange(self.n_padded)
         within, chunk = t % 16, t // 16
         src = chunk * (upc * ppu) + within
         valid = (within < upc * ppu) & (src < n_rows)
-        self.row_map = torch.where(valid, src, torch.full_like(src, n_rows))
+        out_order = torch.where(valid, plan.perms[-1][src.clamp(max=n_rows - 1)], torch.full_like(src, -1))
+        #: the degree-sorted plan of the conditioner with its output layer in the padded chunk layout
+        self.plan = MadePlan(maf._conditioner._degree_chain, out_order=out_order)
         # x / y columns of every unit, in unit (= packed) order
         base = pk['bases'][0].long()
         xcols = part.x_columns().long()
@@ -81,29 +83,18 @@ class TcTxPlan:
             self.cols = xcols[order].to(torch.int32)
         assert torch.equal(base[order] if self.kind != 'moebius' else base.view(-1, 3)[order, 0],
                            torch.arange(n_units) * ppu)
-        # staircase ranges of the padded layer: pad rows are all-zero rows of the mask
-        d_in = plan.packed_degrees[plan.n_layers - 1]
-        d_out = torch.cat([plan.packed_degrees[plan.n_layers], torch.tensor([-(1 << 30)])])[self.row_map]
-        self.mask = (d_out[:, None] > d_in[None, :]) & valid[:, None]
         self.max_radius = float(getattr(part.spec, 'max_radius', 0.0))
         self.unit_sphere = int(getattr(part.spec, 'unit_sphere', 0))
         self._dev = {}
 
-    def tables(self, plan, device):
+    def tables(self, device):
         key = str(device)
         if key not in self._dev:
-            fwd, bwd, roww = plan.tc_ranges(device)
-            f, b, r = MadePlan.tc_ranges_of_mask(self.mask, device)
-            self._dev[key] = (fwd[:-1] + [f], bwd[:-1] + [b], roww[:-1] + [r], self.row_map.to(device),
-                              dict(kind=self.kind, cols=self.cols.to(device), max_radius=self.max_radius,
-                                   unit_sphere=self.unit_sphere))
+            self._dev[key] = dict(kind=self.kind, cols=self.cols.to(device), max_radius=self.max_radius,
+                                  unit_sphere=self.unit_sphere)
         return self._dev[key]
 
     def forward(self, maf, pk, x):
-        plan = pk['plan']
-        kb_fwd, kb_bwd, rr_w, row_map, spec = self.tables(plan, x.device)
-        pw, pb = maf._conditioner.packed_weights(plan)
-        w, b = pw[-1], pb[-1]
-        w_pad = torch.cat([w, w.new_zeros(1, w.shape[1])]).index_select(0, row_map)
-        b_pad = torch.cat([b, b.new_zeros(1)]).index_select(0, row_map)
-        return _ops.made_tx_forward_tc(x, list(pw[:-1]) + [w_pad], list(pb[:-1]) + [b_pad], kb_fwd, kb_bwd, rr_w, spec)
+        kb_fwd, kb_bwd, rr_w = self.plan.tc_ranges(x.device)
+        pw, pb = maf._conditioner.packed_weights(self.plan)
+        return _ops.made_tx_forward_tc(x, list(pw), list(pb), kb_fwd, kb_bwd, rr_w, self.tables(x.device))

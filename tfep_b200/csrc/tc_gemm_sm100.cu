@@ -67,6 +67,7 @@ struct Params {
     const int* kranges;                 // per n-tile: [first, end) k-block, or null
     const int* row_ranges;              // per n-tile: rows [begin, end) of C that can be non-zero; other tiles are skipped, or null
     int atomic;                         // atomicAdd into C (split-K)
+    int c_add;                          // C += result (no split-K)
     int k_chunk_blocks;                 // split-K: k-blocks per blockIdx.y slice, 0 = no split
     int tiles_m, tiles_n;
     int* error;
@@ -471,6 +472,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] *= fminf(xp[(c16 * 16 + i) * XP_LD + lane], 0.f) + 1.f;
                     }
+                    if (p.c_add) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] += xp[(c16 * 16 + i) * XP_LD + lane];
+                    }
                     if (gn0 + 15 >= p.N) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
@@ -544,6 +549,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                         for (int r = 0; r < 32; ++r) {
                             const int grow = gm0 + r;
                             xp[lane * XP_LD + r] = (grow < p.M && gns + lane < p.N) ? __ldg(p.aux + (int64_t)grow * p.ldaux + gns + lane) : 0.f;
+                        }
+                        __syncwarp();
+                    }
+                    if (p.c_add) {
+                        // C += result: the old values come in like the ELU' operand (requested before the accumulator is read)
+#pragma unroll 8
+                        for (int r = 0; r < 32; ++r) {
+                            const int grow = gm0 + r;
+                            xp[lane * XP_LD + r] = (grow < p.M && gns + lane < p.N) ? p.C[(int64_t)grow * p.ldc + gns + lane] : 0.f;
                         }
                         __syncwarp();
                     }
@@ -852,6 +866,8 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
                     "aux and aux_image are alternatives; images are 16-byte aligned");
     TFEPB_CHECK_ARG(a->aux_image == nullptr || (a->activation == TFEPB_ACT_NONE && a->n_split <= 1),
                     "aux_image: plain bf16 product without activation");
+    TFEPB_CHECK_ARG(!a->c_accumulate || (a->aux == nullptr && a->tx == nullptr),
+                    "c_accumulate shares the staging buffer of aux and of the fused transformer (use aux_image)");
     if (int rc = require_sm100()) return rc;
     tcg::Params p{};
     p.a_img = (const uint8_t*)a->a_image; p.b_img = (const uint8_t*)a->b_image;
@@ -880,6 +896,7 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
     int splits = a->split_k > 1 ? a->split_k : 1;
     if (splits > p.k_blocks) splits = p.k_blocks;
     p.atomic = splits > 1 ? 1 : 0;
+    p.c_add = (a->c_accumulate != 0 && splits <= 1 && a->c != nullptr) ? 1 : 0;
     p.k_chunk_blocks = splits > 1 ? (p.k_blocks + splits - 1) / splits : 0;
     if (splits > 1) splits = (p.k_blocks + p.k_chunk_blocks - 1) / p.k_chunk_blocks;
     const int n_split = a->n_split > 1 ? a->n_split : 1;
