@@ -594,6 +594,23 @@ class MadeFunctionTC(torch.autograd.Function):
         return (gx, None, None, None, None, *gws, *gbs)
 
 
+def _weight_gradient_split(n, k, batch, n_sm):
+    """Split of the batch reduction of dW[n x k]: the kernel runs n_sm // split CTAs per slice, each walking
+    ceil(tiles / (n_sm // split)) tiles over batch / split samples -- pick the split with the shortest critical path (a split
+    that leaves a partial last round of tiles wastes up to half the machine: 39 tiles on 18 CTAs = 3 rounds for 2.2)."""
+    tiles = ((n + 127) // 128) * ((k + 255) // 256)
+    k_blocks = (batch + 63) // 64
+    best, best_cost = 1, None
+    for split in range(1, min(k_blocks, n_sm) + 1):
+        ctas = n_sm // split
+        rounds = (tiles + ctas - 1) // ctas
+        chunk = (k_blocks + split - 1) // split
+        cost = rounds * (chunk + 4)                  # + per-tile epilogue (atomics) in units of k-blocks
+        if best_cost is None or cost < best_cost:
+            best, best_cost = split, cost
+    return best
+
+
 def _made_tc_backward_layers(acts, acts_t, ws, kb_bwd, rr_w, need_w, need_x, g, gimg, gimg_t, gb, gx_into=None):
     """Backward pass of the layers of a MADE on the tensor cores, given the cotangent of the output layer's result as
     operand images (``gimg``: A operand of the backward-input product; ``gimg_t``: A operand of the weight gradient, or
@@ -608,8 +625,7 @@ def _made_tc_backward_layers(acts, acts_t, ws, kb_bwd, rr_w, need_w, need_x, g, 
         N, K = ws[l].shape
         if need_w[l]:
             # dW[N x K] = dY^T X: reduction over the batch, split so that the grid fills the machine
-            tiles = ((N + 127) // 128) * ((K + 255) // 256)
-            split = max(1, min((B + 63) // 64, (2 * n_sm + tiles - 1) // tiles))
+            split = _weight_gradient_split(N, K, B, n_sm)
             a_t = gimg_t if gimg_t is not None else tc_pack(g, 128, transpose=True)
             b_t = acts_t[l] if acts_t[l] is not None else tc_pack(acts[l], 256, transpose=True)
             gws[l], _ = tc_gemm(a_t, b_t, N, K, B, c=True, split_k=split, row_ranges=None if rr_w is None else rr_w[l])

@@ -158,57 +158,76 @@ __device__ __forceinline__ void tx_chunk(const Params& p, float (&v)[16], float*
     using G = TxGeo<TX>;
     constexpr int KIND = G::KIND, UPC = G::UPC, PPU = G::PPU;
     constexpr bool BWD = tx_bwd(TX);
+    if constexpr (KIND == TFEPB_TCTX_MOEBIUS3) {
+        // The Moebius bodies are long (three square roots, divisions, a logarithm; the VJP twice that): five unrolled
+        // copies per chunk overflow the instruction cache (ncu, r02: 22 % of the stall samples were instruction fetch).
+        // One rolled loop instead; the unit's three parameters are selected out of / merged into the register array.
+#pragma unroll 1
+        for (int j = 0; j < UPC; ++j) {
+            const int u = chunk * UPC + j;
+            const bool on = row_ok && u < p.tx_units;
+            float w3[3], r3[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < UPC; ++j) {
-        const int u = chunk * UPC + j;
-        const bool on = row_ok && u < p.tx_units;
-        if (on) {
-            if constexpr (KIND == TFEPB_TCTX_MOEBIUS3) {
-                float x3[3], w3[3];
+            for (int i = 0; i < 3; ++i) {
+                w3[i] = v[i];
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    x3[i] = xs[(3 * j + i) * XP_LD + lane];
-                    w3[i] = v[3 * j + i];
-                }
+                for (int jj = 1; jj < UPC; ++jj) w3[i] = j == jj ? v[3 * jj + i] : w3[i];
+            }
+            if (on) {
+                float x3[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) x3[i] = xs[(3 * j + i) * XP_LD + lane];
                 if constexpr (!BWD) {
                     float y3[3];
                     ld_acc += moebius_eval<float>(x3, 1, w3, 1, 1.f, 3, p.tx_max_radius, p.tx_unit_sphere != 0, y3, 1);
 #pragma unroll
                     for (int i = 0; i < 3; ++i) xs[(3 * j + i) * XP_LD + lane] = y3[i];
                 } else {
-                    float gy3[3], gx3[3], gv3[3];
+                    float gy3[3], gx3[3];
 #pragma unroll
                     for (int i = 0; i < 3; ++i) gy3[i] = gs[(3 * j + i) * XP_LD + lane];
-                    moebius_vjp<float>(x3, 1, w3, 1, 3, p.tx_max_radius, p.tx_unit_sphere != 0, gy3, 1, gl, gx3, 1, gv3, 1);
+                    moebius_vjp<float>(x3, 1, w3, 1, 3, p.tx_max_radius, p.tx_unit_sphere != 0, gy3, 1, gl, gx3, 1, r3, 1);
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        gs[(3 * j + i) * XP_LD + lane] = gx3[i];
-                        v[3 * j + i] = gv3[i];
-                    }
+                    for (int i = 0; i < 3; ++i) gs[(3 * j + i) * XP_LD + lane] = gx3[i];
                 }
+            }
+            if constexpr (BWD) {
+#pragma unroll
+                for (int jj = 0; jj < UPC; ++jj) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) v[3 * jj + i] = j == jj ? r3[i] : v[3 * jj + i];
+                }
+            }
+        }
+        if constexpr (BWD) v[15] = 0.f;
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < UPC; ++j) {
+        const int u = chunk * UPC + j;
+        const bool on = row_ok && u < p.tx_units;
+        if (on) {
+            const float x = xs[j * XP_LD + lane];
+            float par[PPU];
+#pragma unroll
+            for (int i = 0; i < PPU; ++i) par[i] = v[PPU * j + i];
+            if constexpr (!BWD) {
+                float y, ld;
+                if constexpr (KIND == TFEPB_TCTX_SOS2) sos_eval<float>(ParIn<float>{par, 1}, 2, x, y, ld);
+                else affine_eval<float, false>(ParIn<float>{par, 1}, x, y, ld);
+                xs[j * XP_LD + lane] = y;
+                ld_acc += ld;
             } else {
-                const float x = xs[j * XP_LD + lane];
-                float par[PPU];
-#pragma unroll
-                for (int i = 0; i < PPU; ++i) par[i] = v[PPU * j + i];
-                if constexpr (!BWD) {
-                    float y, ld;
-                    if constexpr (KIND == TFEPB_TCTX_SOS2) sos_eval<float>(ParIn<float>{par, 1}, 2, x, y, ld);
-                    else affine_eval<float, false>(ParIn<float>{par, 1}, x, y, ld);
-                    xs[j * XP_LD + lane] = y;
-                    ld_acc += ld;
+                const float gy = gs[j * XP_LD + lane];
+                float gx, gpar[PPU];
+                if constexpr (KIND == TFEPB_TCTX_SOS2) {
+                    sos_vjp<float>(ParIn<float>{par, 1}, 2, x, gy, gx, ParOut<float>{gpar, 1});     // no log-det cotangent (sos.py:233)
                 } else {
-                    const float gy = gs[j * XP_LD + lane];
-                    float gx, gpar[PPU];
-                    if constexpr (KIND == TFEPB_TCTX_SOS2) {
-                        sos_vjp<float>(ParIn<float>{par, 1}, 2, x, gy, gx, ParOut<float>{gpar, 1});     // no log-det cotangent (sos.py:233)
-                    } else {
-                        affine_vjp<float>(ParIn<float>{par, 1}, x, gy, gl, gx, ParOut<float>{gpar, 1});
-                    }
-                    gs[j * XP_LD + lane] = gx;
-#pragma unroll
-                    for (int i = 0; i < PPU; ++i) v[PPU * j + i] = gpar[i];
+                    affine_vjp<float>(ParIn<float>{par, 1}, x, gy, gl, gx, ParOut<float>{gpar, 1});
                 }
+                gs[j * XP_LD + lane] = gx;
+#pragma unroll
+                for (int i = 0; i < PPU; ++i) v[PPU * j + i] = gpar[i];
             }
         } else if constexpr (BWD) {
 #pragma unroll
