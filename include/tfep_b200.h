@@ -217,10 +217,12 @@ int tfepb_tc_pack(const float* src, int64_t ld, int32_t rows, int32_t k, int32_t
  * fp32-class accuracy on bf16 tensor cores; see n_split of tfepb_tc_gemm_args). */
 int tfepb_tc_pack_split(const float* src, int64_t ld, int32_t rows, int32_t k, int32_t block_rows, int32_t transpose,
                         int32_t n_split, void* image, tfepb_stream_t stream);
-/* One pass over src (rows x cols fp32): its image with 128-row blocks (or NULL), the image of its transpose with
- * t_block_rows = 128 / 256 (or NULL) and, if column_sums != NULL (zero-filled by the caller), += the sums over the rows. */
-int tfepb_tc_pack_dual(const float* src, int64_t ld, int32_t rows, int32_t cols, void* image, void* image_t,
-                       int32_t t_block_rows, float* column_sums, tfepb_stream_t stream);
+/* One pass over src (rows x cols fp32): its image with block_rows = 128 / 256 (or NULL), the image of its transpose with
+ * t_block_rows = 128 / 256 (or NULL) and, if column_sums != NULL (zero-filled by the caller), += the sums over the rows.
+ * (x and grad_y of a layer: 128 / 256 or 128 / 128; a weight matrix: 256 / 256 = the B operands of the forward and of the
+ * backward-input product.) */
+int tfepb_tc_pack_dual(const float* src, int64_t ld, int32_t rows, int32_t cols, void* image, int32_t block_rows,
+                       void* image_t, int32_t t_block_rows, float* column_sums, tfepb_stream_t stream);
 /* Transformer fused into the epilogue of the OUTPUT-layer product of a MAF (AutoregressiveFlow.forward,
  * nn/flows/autoregressive.py:144-177: parameters = conditioner(x); y, log_det = transformer(x, parameters)) so that the
  * (batch x n_parameters) matrix never reaches memory.  The n output columns of the product are 16-column chunks; chunk q

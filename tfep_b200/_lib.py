@@ -156,7 +156,8 @@ SYMBOLS = {
     'tfepb_tc_image_bytes': (c_int64, [c_int64, c_int64, c_int32]),
     'tfepb_tc_pack': (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     'tfepb_tc_pack_split': (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
-    'tfepb_tc_pack_dual': (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    'tfepb_tc_pack_dual': (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p,
+                                     c_void_p]),
     'tfepb_tc_gemm': (c_int32, [POINTER(TcGemmArgs), c_void_p]),
     'tfepb_wn_pack': (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_int32,
                                 c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),

@@ -440,8 +440,8 @@ def tc_pack(src, block_rows, transpose=False, out=None, n_split=1):
     return img
 
 
-def tc_pack_dual(src, t_block_rows=None, column_sums=False, image=True):
-    """One pass over a 2-D fp32 CUDA tensor: (its image with 128-row blocks, the image of its transpose with
+def tc_pack_dual(src, t_block_rows=None, column_sums=False, image=True, block_rows=128):
+    """One pass over a 2-D fp32 CUDA tensor: (its image with ``block_rows`` = 128 / 256, the image of its transpose with
     ``t_block_rows`` = 128 / 256, its column sums); see tfepb_tc_pack_dual.  Parts not asked for are None."""
     require_cuda(src)
     if src.dtype != torch.float32:
@@ -449,14 +449,14 @@ def tc_pack_dual(src, t_block_rows=None, column_sums=False, image=True):
     src = _rows(src)
     rows, cols = src.shape
     lib = _lib.load()
-    img = torch.empty(lib.tfepb_tc_image_bytes(rows, cols, 128), dtype=torch.uint8, device=src.device) if image else None
+    img = torch.empty(lib.tfepb_tc_image_bytes(rows, cols, int(block_rows)), dtype=torch.uint8, device=src.device) if image else None
     img_t = None
     if t_block_rows:
         img_t = torch.empty(lib.tfepb_tc_image_bytes(cols, rows, int(t_block_rows)), dtype=torch.uint8, device=src.device)
     sums = torch.zeros(cols, dtype=torch.float32, device=src.device) if column_sums else None
     with torch.cuda.device(src.device):
-        check(lib.tfepb_tc_pack_dual(ptr(src), _ld(src), rows, cols, ptr(img), ptr(img_t), int(t_block_rows or 0), ptr(sums),
-                                     stream_ptr(src)))
+        check(lib.tfepb_tc_pack_dual(ptr(src), _ld(src), rows, cols, ptr(img), int(block_rows), ptr(img_t), int(t_block_rows or 0),
+                                     ptr(sums), stream_ptr(src)))
     return img, img_t, sums
 
 
@@ -554,10 +554,13 @@ class MadeFunctionTC(torch.autograd.Function):
         # hidden activations exist as bf16 images only: operand of the next product, ELU' operand of the backward pass
         acts, acts_t = [x], [x_t]
         h = x
+        keep = any(ctx.needs_input_grad)
+        wts = []
         for l in range(n_layers):
             last = l == n_layers - 1
             N, K = ws[l].shape
-            wimg = tc_pack(ws[l], 256)
+            wimg, wt = _weight_images(ws[l], keep and (l > 0 or ctx.needs_input_grad[0]))
+            wts.append(wt)
             if train and not last:
                 # the epilogue also writes the image of h^T: the B operand of the next layer's weight gradient
                 _, img, img_t, _ = tc_gemm(img, wimg, B, N, K, bias=bs[l], activation=ACT_ELU, out_image=True,
@@ -572,6 +575,7 @@ class MadeFunctionTC(torch.autograd.Function):
                 acts.append(img)
         ctx.save_for_backward(*acts, *ws)
         ctx.acts_t = acts_t[:n_layers]
+        ctx.wts = wts
         ctx.n_layers = n_layers
         ctx.kb_bwd = kb_bwd
         ctx.rr_w = rr_w
@@ -589,8 +593,8 @@ class MadeFunctionTC(torch.autograd.Function):
         gimg, gimg_t, gb = tc_pack_dual(g, 128 if top else None, column_sums=top)
         need_w = [ctx.needs_input_grad[5 + l] or ctx.needs_input_grad[5 + L + l] for l in range(L)]
         gx, gws, gbs = _made_tc_backward_layers(acts, ctx.acts_t, ws, ctx.kb_bwd, ctx.rr_w, need_w, ctx.needs_input_grad[0],
-                                                g, gimg, gimg_t, gb)
-        ctx.acts_t = None
+                                                g, gimg, gimg_t, gb, wts=ctx.wts)
+        ctx.acts_t = ctx.wts = None
         return (gx, None, None, None, None, *gws, *gbs)
 
 
@@ -605,13 +609,22 @@ def _weight_gradient_split(n, k, batch, n_sm):
         ctas = n_sm // split
         rounds = (tiles + ctas - 1) // ctas
         chunk = (k_blocks + split - 1) // split
-        cost = rounds * (chunk + 4)                  # + per-tile epilogue (atomics) in units of k-blocks
+        cost = rounds * (chunk + 8)                  # + per-tile epilogue (atomics) in units of k-blocks
         if best_cost is None or cost < best_cost:
             best, best_cost = split, cost
     return best
 
 
-def _made_tc_backward_layers(acts, acts_t, ws, kb_bwd, rr_w, need_w, need_x, g, gimg, gimg_t, gb, gx_into=None):
+def _weight_images(w, both):
+    """(image of w, image of w^T or None): the B operands of the forward and of the backward-input product of a layer, in ONE
+    pass over the packed weight when the backward pass will run."""
+    if both:
+        img, img_t, _ = tc_pack_dual(w, 256, block_rows=256)
+        return img, img_t
+    return tc_pack(w, 256), None
+
+
+def _made_tc_backward_layers(acts, acts_t, ws, kb_bwd, rr_w, need_w, need_x, g, gimg, gimg_t, gb, gx_into=None, wts=None):
     """Backward pass of the layers of a MADE on the tensor cores, given the cotangent of the output layer's result as
     operand images (``gimg``: A operand of the backward-input product; ``gimg_t``: A operand of the weight gradient, or
     None -> packed from the fp32 ``g``; ``gb``: its column sums, or None).  ``acts``: the input x (fp32) followed by the
@@ -632,7 +645,8 @@ def _made_tc_backward_layers(acts, acts_t, ws, kb_bwd, rr_w, need_w, need_x, g, 
             gbs[l] = gb if gb is not None else g.sum(dim=0)
         gimg_t, gb = None, None
         if l > 0 or need_x:
-            wt = tc_pack(ws[l], 256, transpose=True)            # rows = inputs of the layer, k = its outputs
+            # rows = inputs of the layer, k = its outputs (packed by the forward pass together with the forward operand)
+            wt = wts[l] if wts is not None and wts[l] is not None else tc_pack(ws[l], 256, transpose=True)
             kb = None if kb_bwd is None else kb_bwd[l]
             if l == 0:
                 # ``gx_into``: the cotangent of x is ADDED to that tensor (the direct term of a fused transformer)
@@ -664,9 +678,12 @@ class MadeTxFunctionTC(torch.autograd.Function):
         train = any(ctx.needs_input_grad[6:6 + 2 * L])
         img, x_t, _ = tc_pack_dual(x, 256 if train else None)
         acts, acts_t = [x], [x_t]
+        keep = any(ctx.needs_input_grad)
+        wts = []
         for l in range(L - 1):
             N, K = ws[l].shape
-            wimg = tc_pack(ws[l], 256)
+            wimg, wt = _weight_images(ws[l], keep and (l > 0 or ctx.needs_input_grad[0]))
+            wts.append(wt)
             if train:
                 _, img, img_t, _ = tc_gemm(img, wimg, B, N, K, bias=bs[l], activation=ACT_ELU, out_image=True,
                                            out_image_t=256, k_block_ranges=None if kb_fwd is None else kb_fwd[l])
@@ -679,12 +696,14 @@ class MadeTxFunctionTC(torch.autograd.Function):
         N, K = ws[-1].shape
         y = torch.empty_like(x)
         logdet = torch.zeros(B, dtype=torch.float32, device=x.device)
-        tc_gemm(img, tc_pack(ws[-1], 256), B, N, K, bias=bs[-1], k_block_ranges=None if kb_fwd is None else kb_fwd[-1],
+        wimg, wt = _weight_images(ws[-1], keep)
+        wts.append(wt)
+        tc_gemm(img, wimg, B, N, K, bias=bs[-1], k_block_ranges=None if kb_fwd is None else kb_fwd[-1],
                 tx=TcTx(spec['kind'], spec['cols'], x, y=y, logdet=logdet, max_radius=spec['max_radius'],
                         unit_sphere=spec['unit_sphere']))
-        keep = any(ctx.needs_input_grad)
-        ctx.save_for_backward(*(acts if keep else acts[:1]), *ws, bs[-1])
+        ctx.save_for_backward(*(acts if keep else acts[:1]), *ws, bs[-1], *([wimg] if keep else []))
         ctx.acts_t = acts_t if keep else None
+        ctx.wts = wts if keep else None
         ctx.meta = (L, kb_fwd, kb_bwd, rr_w, spec)
         if spec['kind'] == 'sos':
             ctx.mark_non_differentiable(logdet)                  # the reference's SOS log-det carries no gradient (sos.py:233)
@@ -694,7 +713,7 @@ class MadeTxFunctionTC(torch.autograd.Function):
     def backward(ctx, grad_y, grad_ld):
         L, kb_fwd, kb_bwd, rr_w, spec = ctx.meta
         saved = list(ctx.saved_tensors)
-        acts, ws, b_last = saved[:L], saved[L:2 * L], saved[2 * L]
+        acts, ws, b_last, w_last_img = saved[:L], saved[L:2 * L], saved[2 * L], saved[2 * L + 1]
         x, last_img = acts[0], acts[-1]
         B = x.shape[0]
         grad_y = torch.zeros_like(x) if grad_y is None else _rows(grad_y.contiguous())
@@ -703,14 +722,14 @@ class MadeTxFunctionTC(torch.autograd.Function):
         need_w = [ctx.needs_input_grad[6 + l] or ctx.needs_input_grad[6 + L + l] for l in range(L)]
         gx = torch.empty_like(x)
         N, K = ws[-1].shape
-        _, gimg, gimg_t, gb = tc_gemm(last_img, tc_pack(ws[-1], 256), B, N, K, bias=b_last, out_image=True,
+        _, gimg, gimg_t, gb = tc_gemm(last_img, w_last_img, B, N, K, bias=b_last, out_image=True,
                                       out_image_t=128 if need_w[-1] else None, column_sums=True,
                                       k_block_ranges=None if kb_fwd is None else kb_fwd[-1],
                                       tx=TcTx(spec['kind'], spec['cols'], x, grad_y=grad_y, grad_logdet=grad_ld, grad_x=gx,
                                               max_radius=spec['max_radius'], unit_sphere=spec['unit_sphere']))
         _, gws, gbs = _made_tc_backward_layers(acts, ctx.acts_t, ws, kb_bwd, rr_w, need_w, ctx.needs_input_grad[0],
-                                               None, gimg, gimg_t, gb, gx_into=gx)
-        ctx.acts_t = None
+                                               None, gimg, gimg_t, gb, gx_into=gx, wts=ctx.wts)
+        ctx.acts_t = ctx.wts = None
         return (gx if ctx.needs_input_grad[0] else None, None, None, None, None, None, *gws, *gbs)
 
 

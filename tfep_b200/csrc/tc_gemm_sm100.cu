@@ -485,7 +485,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                 if (!p.atomic) {
                     if (p.act == TFEPB_ACT_ELU) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], ex2(fminf(v[i], 0.f) * LOG2E) - 1.f);
+                        for (int i = 0; i < 16; ++i) {
+                            // four instructions per element (FMUL, MUFU.EX2, FSETP, predicated FADD); ex2 of a large positive
+                            // argument is +inf and unused
+                            const float e = ex2(v[i] * LOG2E);
+                            if (v[i] <= 0.f) v[i] = e - 1.f;
+                        }
                     }
                     if (p.aux != nullptr) {
 #pragma unroll
@@ -747,8 +752,8 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const float* __restrict__ 
 // needs of grad_y (operand of the backward-input product, operand of the weight gradient, bias gradient) and the forward
 // pass of x.  One CTA per 64 x 64 tile; every block of both images is written completely (zero padding included).
 __global__ void __launch_bounds__(256) tc_pack_dual_kernel(const float* __restrict__ src, int64_t ld, int R, int C,
-                                                           uint8_t* __restrict__ img, uint8_t* __restrict__ img_t, int t_rows,
-                                                           float* __restrict__ colsum) {
+                                                           uint8_t* __restrict__ img, int a_rows, uint8_t* __restrict__ img_t,
+                                                           int t_rows, float* __restrict__ colsum) {
     __shared__ float tile[64][65];
     const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
     for (int i = threadIdx.x; i < 64 * 64; i += 256) {
@@ -758,7 +763,7 @@ __global__ void __launch_bounds__(256) tc_pack_dual_kernel(const float* __restri
     __syncthreads();
     const int kb_a = (C + KB - 1) / KB, kb_t = (R + KB - 1) / KB;
     if (img != nullptr && blockIdx.x < kb_a) {
-        uint8_t* blk = img + ((size_t)(r0 >> 7) * kb_a + blockIdx.x) * A_BLOCK;
+        uint8_t* blk = img + ((size_t)(r0 / a_rows) * kb_a + blockIdx.x) * (size_t)a_rows * 128;
         for (int i = threadIdx.x; i < 64 * 8; i += 256) {
             const int rr = i & 63, slab = i >> 6;
             uint4 q;
@@ -766,7 +771,7 @@ __global__ void __launch_bounds__(256) tc_pack_dual_kernel(const float* __restri
             q.y = pack_bf16(tile[rr][slab * 8 + 2], tile[rr][slab * 8 + 3]);
             q.z = pack_bf16(tile[rr][slab * 8 + 4], tile[rr][slab * 8 + 5]);
             q.w = pack_bf16(tile[rr][slab * 8 + 6], tile[rr][slab * 8 + 7]);
-            *reinterpret_cast<uint4*>(blk + (size_t)slab * 2048 + (size_t)((r0 & 127) + rr) * 16) = q;
+            *reinterpret_cast<uint4*>(blk + (size_t)slab * a_rows * 16 + (size_t)((r0 % a_rows) + rr) * 16) = q;
         }
     }
     if (img_t != nullptr && blockIdx.y < kb_t) {
@@ -828,20 +833,22 @@ extern "C" int tfepb_tc_pack(const float* src, int64_t ld, int32_t rows, int32_t
     return check_launch("tc_pack");
 }
 
-extern "C" int tfepb_tc_pack_dual(const float* src, int64_t ld, int32_t rows, int32_t cols, void* image, void* image_t,
-                                  int32_t t_block_rows, float* column_sums, tfepb_stream_t stream) {
+extern "C" int tfepb_tc_pack_dual(const float* src, int64_t ld, int32_t rows, int32_t cols, void* image, int32_t block_rows,
+                                  void* image_t, int32_t t_block_rows, float* column_sums, tfepb_stream_t stream) {
     TFEPB_NVTX();
     TFEPB_CHECK_ARG(src != nullptr && (image != nullptr || image_t != nullptr), "null buffer");
     TFEPB_CHECK_ARG(rows > 0 && cols > 0 && ld >= cols, "bad sizes");
     TFEPB_CHECK_ARG(image_t == nullptr || t_block_rows == 128 || t_block_rows == 256, "t_block_rows must be 128 or 256");
+    TFEPB_CHECK_ARG(image == nullptr || block_rows == 128 || block_rows == 256, "block_rows must be 128 or 256");
     TFEPB_CHECK_ARG(((uintptr_t)image % 16 == 0) && ((uintptr_t)image_t % 16 == 0), "operand images must be 16-byte aligned");
     if (int rc = require_sm100()) return rc;
     const int tr = image_t != nullptr ? t_block_rows : 128;
-    // cover every block of both images: rows up to a multiple of 128, columns up to a multiple of the transposed block
-    const unsigned gy = (unsigned)((rows + 127) / 128 * 2);
+    const int ar = image != nullptr ? block_rows : 128;
+    // cover every block of both images: rows up to a multiple of the block, columns up to a multiple of the transposed block
+    const unsigned gy = (unsigned)((rows + ar - 1) / ar * (ar / 64));
     const unsigned gx = (unsigned)((cols + tr - 1) / tr * (tr / 64));
-    tcg::tc_pack_dual_kernel<<<dim3(gx, gy), 256, 0, as_stream(stream)>>>(src, ld, rows, cols, (uint8_t*)image, (uint8_t*)image_t,
-                                                                         tr, column_sums);
+    tcg::tc_pack_dual_kernel<<<dim3(gx, gy), 256, 0, as_stream(stream)>>>(src, ld, rows, cols, (uint8_t*)image, ar,
+                                                                         (uint8_t*)image_t, tr, column_sums);
     return check_launch("tc_pack_dual");
 }
 
