@@ -283,6 +283,14 @@ typedef struct {
     int32_t c_accumulate;                /* != 0: c += result instead of c = result (without split_k, which always adds) */
     const tfepb_tc_tx* tx;               /* NULL, or the transformer fused into the epilogue (n_split <= 1, no split_k,
                                             n a multiple of 16, activation NONE, no aux) */
+    int32_t mn_major;                    /* != 0: a_image / b_image are the ROW images (block_rows = 128) of a (k x m) and a (k x n)
+                                            matrix and the product reduces over their rows: C = A^T B read MN-major, e.g. the
+                                            weight gradient dW = dY^T X straight from the images of dY and X that the other
+                                            products use -- no transposed images.  Rows >= k of the images must be zero
+                                            (tfepb_tc_pack / out_image write them so).  The product is ADDED to c (fp32 atomics,
+                                            zero-fill c first); split_k cuts the reduction in blocks of 128 rows; row_ranges
+                                            applies; no bias / activation / images. */
+    int32_t reserved2;
     const void* aux_image;               /* alternative to aux: the same (m, n) operand h given as its bf16 image (block_rows =
                                             128, k = n; e.g. the out_image a forward product wrote): the result is multiplied
                                             by ELU'(h) of the bf16 values -- no fp32 copy of the activations is needed */

@@ -123,3 +123,25 @@ def test_split_precision_products(m, n, k, n_split, tol):
         wm[256:, 128:] = 0
         refr = x.double() @ wm.double().T
         assert float((cr.double() - refr).abs().max()) < tol * (1 + float(refr.abs().max()))
+
+
+@pytest.mark.parametrize('batch,n_out,n_in,split', [(5000, 300, 200, 16), (130, 1600, 670, 3), (64, 7, 9, 1), (1000, 670, 300, 5)])
+def test_weight_gradient_from_row_images_mn_major(batch, n_out, n_in, split):
+    """dW = dY^T X read MN-major out of the SAME row images that the forward / backward-input products use (no transposed
+    images): reduction over the rows of both images, batch sizes that end inside a 64-row k-block and inside a 128-row
+    image block, output sizes that end inside a 128-row / 256-column tile; also from an image written by a product's
+    epilogue (its rows beyond the batch must be zero)."""
+    gy, x = _rand((batch, n_out), 20), _rand((batch, n_in), 21)
+    gw, _ = _ops.tc_gemm(_ops.tc_pack(gy, 128), _ops.tc_pack(x, 128), n_out, n_in, batch, c=True, split_k=split, mn_major=True)
+    ref = _bf(gy).T @ _bf(x)
+    assert gw.shape == (n_out, n_in)
+    assert float((gw.double() - ref).abs().max()) < 3e-4 * (1 + float(ref.abs().max()))
+    # the image of an activation as the forward epilogue writes it (bias makes the padding rows non-zero before masking)
+    k0 = 100
+    z, w, b = _rand((batch, k0), 22), _rand((n_in, k0), 23) / k0 ** 0.5, _rand((n_in,), 24) + 1.0
+    _, himg = _ops.tc_gemm(_ops.tc_pack(z, 128), _ops.tc_pack(w, 256), batch, n_in, k0, bias=b, activation=_ops.ACT_ELU,
+                           out_image=True)
+    h = torch.nn.functional.elu(_bf(z) @ _bf(w).T + b.double())
+    gw2, _ = _ops.tc_gemm(_ops.tc_pack(gy, 128), himg, n_out, n_in, batch, c=True, split_k=split, mn_major=True)
+    ref2 = _bf(gy).T @ _bf(h.float())
+    assert float((gw2.double() - ref2).abs().max()) < 3e-4 * (1 + float(ref2.abs().max()))

@@ -490,19 +490,20 @@ class TcTx:
 
 def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, aux=None, out_image=False,
             k_block_ranges=None, row_ranges=None, split_k=1, error_flag=None, out_image_t=None, column_sums=False, n_split=1,
-            tx=None, aux_image=None, accumulate=False):
+            tx=None, aux_image=None, accumulate=False, mn_major=False):
     """C = act(A B^T + bias) [* ELU'(aux)] from operand images; returns (c, out_img).  ``c``: True to allocate, a
     tensor to write into (zero-filled by the caller when split_k > 1), None for no fp32 output.
     ``out_image_t`` = 128 / 256: also the image of the transposed result with that block_rows; ``column_sums``: also
     the sums over the m rows; with either, returns (c, out_img, out_img_t, column_sums).  ``tx``: a :class:`TcTx`, the
     transformer applied by the epilogue (the columns are then parameter chunks, see tfepb_tc_tx).  ``aux_image``: the
     ELU' operand as the bf16 image a forward product wrote (instead of the fp32 ``aux``).  ``accumulate``: ``c`` (a tensor)
-    += the result."""
+    += the result.  ``mn_major``: ``a_img`` / ``b_img`` are the ROW images of a (k x m) and a (k x n) matrix, C = A^T B
+    (the weight gradient straight from the images of grad_y and x)."""
     lib = _lib.load()
     dev = a_img.device
     if c is True:
         pad4 = (n + 3) // 4 * 4
-        c = (torch.zeros if split_k > 1 else torch.empty)((m, pad4), dtype=torch.float32, device=dev)[:, :n]
+        c = (torch.zeros if split_k > 1 or mn_major else torch.empty)((m, pad4), dtype=torch.float32, device=dev)[:, :n]
     img = None
     if out_image:
         img = torch.empty(lib.tfepb_tc_image_bytes(m, n, 128) * n_split, dtype=torch.uint8, device=dev)
@@ -527,6 +528,7 @@ def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, au
         a.tx = ctypes.pointer(txs)
     if aux_image is not None:
         a.aux_image = aux_image.data_ptr()
+    a.mn_major = int(bool(mn_major))
     with torch.cuda.device(dev):
         check(lib.tfepb_tc_gemm(ctypes.byref(a), stream_ptr(a_img)))
     if out_image_t or column_sums:
@@ -548,11 +550,11 @@ class MadeFunctionTC(torch.autograd.Function):
     def forward(ctx, x, n_layers, kb_fwd, kb_bwd, rr_w, *wb):
         ws, bs = wb[:n_layers], wb[n_layers:]
         B = x.shape[0]
-        train = any(ctx.needs_input_grad[5:5 + 2 * n_layers])      # weight gradients wanted: keep transposed images
-        # x: one pass gives the A operand of the first product and, for training, the B operand of its weight gradient
-        img, x_t, _ = tc_pack_dual(x, 256 if train else None)
-        # hidden activations exist as bf16 images only: operand of the next product, ELU' operand of the backward pass
-        acts, acts_t = [x], [x_t]
+        # Every activation exists as ONE bf16 row image: operand of the next product, ELU' operand of the backward pass and
+        # (read MN-major) operand of the weight gradient.
+        img = tc_pack(x, 128)
+        acts = [x]
+        imgs = [img]
         h = x
         keep = any(ctx.needs_input_grad)
         wts = []
@@ -561,20 +563,13 @@ class MadeFunctionTC(torch.autograd.Function):
             N, K = ws[l].shape
             wimg, wt = _weight_images(ws[l], keep and (l > 0 or ctx.needs_input_grad[0]))
             wts.append(wt)
-            if train and not last:
-                # the epilogue also writes the image of h^T: the B operand of the next layer's weight gradient
-                _, img, img_t, _ = tc_gemm(img, wimg, B, N, K, bias=bs[l], activation=ACT_ELU, out_image=True,
-                                           out_image_t=256, k_block_ranges=None if kb_fwd is None else kb_fwd[l])
-                acts_t.append(img_t)
-            else:
-                h, img = tc_gemm(img, wimg, B, N, K, c=True if last else None, bias=bs[l],
-                                 activation=ACT_NONE if last else ACT_ELU, out_image=not last,
-                                 k_block_ranges=None if kb_fwd is None else kb_fwd[l])
-                acts_t.append(None)
+            h, img = tc_gemm(img, wimg, B, N, K, c=True if last else None, bias=bs[l],
+                             activation=ACT_NONE if last else ACT_ELU, out_image=not last,
+                             k_block_ranges=None if kb_fwd is None else kb_fwd[l])
             if not last:
                 acts.append(img)
-        ctx.save_for_backward(*acts, *ws)
-        ctx.acts_t = acts_t[:n_layers]
+                imgs.append(img)
+        ctx.save_for_backward(*acts, *ws, imgs[0])
         ctx.wts = wts
         ctx.n_layers = n_layers
         ctx.kb_bwd = kb_bwd
@@ -585,31 +580,31 @@ class MadeFunctionTC(torch.autograd.Function):
     def backward(ctx, grad_out):
         L = ctx.n_layers
         saved = ctx.saved_tensors
-        acts, ws = saved[:L], saved[L:]
+        acts, ws, x_img = saved[:L], saved[L:2 * L], saved[2 * L]
         g = _rows(grad_out.contiguous())
         # image of g, image of g^T (A operand of the weight gradient) and the bias gradient: one pass over grad_out for the
         # top layer, written by the epilogue of the backward-input product for the layers below
         top = ctx.needs_input_grad[5 + L - 1] or ctx.needs_input_grad[5 + 2 * L - 1]
-        gimg, gimg_t, gb = tc_pack_dual(g, 128 if top else None, column_sums=top)
+        gimg, _, gb = tc_pack_dual(g, None, column_sums=top)
         need_w = [ctx.needs_input_grad[5 + l] or ctx.needs_input_grad[5 + L + l] for l in range(L)]
-        gx, gws, gbs = _made_tc_backward_layers(acts, ctx.acts_t, ws, ctx.kb_bwd, ctx.rr_w, need_w, ctx.needs_input_grad[0],
-                                                g, gimg, gimg_t, gb, wts=ctx.wts)
-        ctx.acts_t = ctx.wts = None
+        gx, gws, gbs = _made_tc_backward_layers(g.shape[0], [x_img] + list(acts[1:]), ws, ctx.kb_bwd, ctx.rr_w, need_w,
+                                                ctx.needs_input_grad[0], gimg, gb, wts=ctx.wts)
+        ctx.wts = None
         return (gx, None, None, None, None, *gws, *gbs)
 
 
-def _weight_gradient_split(n, k, batch, n_sm):
+def _weight_gradient_split(n, k, batch, n_sm, block=128):
     """Split of the batch reduction of dW[n x k]: the kernel runs n_sm // split CTAs per slice, each walking
     ceil(tiles / (n_sm // split)) tiles over batch / split samples -- pick the split with the shortest critical path (a split
     that leaves a partial last round of tiles wastes up to half the machine: 39 tiles on 18 CTAs = 3 rounds for 2.2)."""
     tiles = ((n + 127) // 128) * ((k + 255) // 256)
-    k_blocks = (batch + 63) // 64
+    k_blocks = (batch + block - 1) // block          # reduction blocks (128 image rows per ring stage)
     best, best_cost = 1, None
     for split in range(1, min(k_blocks, n_sm) + 1):
         ctas = n_sm // split
         rounds = (tiles + ctas - 1) // ctas
         chunk = (k_blocks + split - 1) // split
-        cost = rounds * (chunk + 8)                  # + per-tile epilogue (atomics) in units of k-blocks
+        cost = rounds * (chunk + 4)                  # + per-tile epilogue (atomics) in units of reduction blocks
         if best_cost is None or cost < best_cost:
             best, best_cost = split, cost
     return best
@@ -624,41 +619,38 @@ def _weight_images(w, both):
     return tc_pack(w, 256), None
 
 
-def _made_tc_backward_layers(acts, acts_t, ws, kb_bwd, rr_w, need_w, need_x, g, gimg, gimg_t, gb, gx_into=None, wts=None):
-    """Backward pass of the layers of a MADE on the tensor cores, given the cotangent of the output layer's result as
-    operand images (``gimg``: A operand of the backward-input product; ``gimg_t``: A operand of the weight gradient, or
-    None -> packed from the fp32 ``g``; ``gb``: its column sums, or None).  ``acts``: the input x (fp32) followed by the
-    bf16 images of the hidden activations.  Returns (grad_x or None, grad_ws, grad_bs)."""
+def _made_tc_backward_layers(B, imgs, ws, kb_bwd, rr_w, need_w, need_x, gimg, gb, gx_into=None, wts=None):
+    """Backward pass of the layers of a MADE on the tensor cores.  ``imgs``: the bf16 row images of the input of every layer (x,
+    then the hidden activations); ``gimg`` / ``gb``: the row image of the cotangent of the output layer's result and its column
+    sums.  Every matrix exists as ONE image: the backward-input product reads ``gimg`` K-major, the weight gradient
+    dW = dY^T X reads ``gimg`` and ``imgs[l]`` MN-major (reduction over their rows), ELU' reads ``imgs[l]``.  Returns
+    (grad_x or None, grad_ws, grad_bs).  ``B``: the batch size."""
     L = len(ws)
-    B = acts[0].shape[0]
+    dev = gimg.device
     gws, gbs = [None] * L, [None] * L
     gx = None
-    n_sm = torch.cuda.get_device_properties(acts[0].device).multi_processor_count
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
     for l in range(L - 1, -1, -1):
         N, K = ws[l].shape
         if need_w[l]:
             # dW[N x K] = dY^T X: reduction over the batch, split so that the grid fills the machine
             split = _weight_gradient_split(N, K, B, n_sm)
-            a_t = gimg_t if gimg_t is not None else tc_pack(g, 128, transpose=True)
-            b_t = acts_t[l] if acts_t[l] is not None else tc_pack(acts[l], 256, transpose=True)
-            gws[l], _ = tc_gemm(a_t, b_t, N, K, B, c=True, split_k=split, row_ranges=None if rr_w is None else rr_w[l])
-            gbs[l] = gb if gb is not None else g.sum(dim=0)
-        gimg_t, gb = None, None
+            gws[l], _ = tc_gemm(gimg, imgs[l], N, K, B, c=True, split_k=split, row_ranges=None if rr_w is None else rr_w[l],
+                                mn_major=True)
+            gbs[l] = gb
+        gb = None
         if l > 0 or need_x:
             # rows = inputs of the layer, k = its outputs (packed by the forward pass together with the forward operand)
             wt = wts[l] if wts is not None and wts[l] is not None else tc_pack(ws[l], 256, transpose=True)
             kb = None if kb_bwd is None else kb_bwd[l]
             if l == 0:
                 # ``gx_into``: the cotangent of x is ADDED to that tensor (the direct term of a fused transformer)
-                gx, _ = tc_gemm(gimg, wt, B, K, N, c=True if gx_into is None else gx_into, accumulate=gx_into is not None,
-                                k_block_ranges=kb)
-            elif need_w[l - 1]:
-                # the cotangent of a hidden activation exists as operand images (and column sums) only
-                _, gimg, gimg_t, gb = tc_gemm(gimg, wt, B, K, N, aux_image=acts[l], out_image=True, out_image_t=128,
-                                              column_sums=True, k_block_ranges=kb)
+                gx, _ = tc_gemm(gimg, wt, B, K, N, c=True if gx_into is None else gx_into,
+                                accumulate=gx_into is not None, k_block_ranges=kb)
             else:
-                _, gimg = tc_gemm(gimg, wt, B, K, N, aux_image=acts[l], out_image=True, k_block_ranges=kb)
-            g = None
+                # the cotangent of a hidden activation exists as its row image (and column sums) only
+                out = tc_gemm(gimg, wt, B, K, N, aux_image=imgs[l], out_image=True, column_sums=need_w[l - 1], k_block_ranges=kb)
+                gimg, gb = out[1], (out[3] if need_w[l - 1] else None)
     return gx, gws, gbs
 
 
@@ -667,32 +659,24 @@ class MadeTxFunctionTC(torch.autograd.Function):
     conditioner output is never written.  ``ws[-1]`` / ``bs[-1]`` are the output layer in the padded chunk layout of the
     transformer kind (tfep_b200/_txfused.py), the range tables of that layer refer to the same layout.  Backward: the
     output-layer product is recomputed from the saved image of the last hidden activation and its epilogue emits the
-    parameter cotangents as the operand images of the two products below (no fp32 cotangent matrix either), then the
-    layers follow as in :class:`MadeFunctionTC`."""
+    parameter cotangents as the operand image of the products below (no fp32 cotangent matrix either), then the layers
+    follow as in :class:`MadeFunctionTC`."""
 
     @staticmethod
     def forward(ctx, x, n_layers, kb_fwd, kb_bwd, rr_w, spec, *wb):
         ws, bs = wb[:n_layers], wb[n_layers:]
         L = n_layers
         B = x.shape[0]
-        train = any(ctx.needs_input_grad[6:6 + 2 * L])
-        img, x_t, _ = tc_pack_dual(x, 256 if train else None)
-        acts, acts_t = [x], [x_t]
         keep = any(ctx.needs_input_grad)
-        wts = []
+        img = tc_pack(x, 128)
+        imgs, wts = [img], []
         for l in range(L - 1):
             N, K = ws[l].shape
             wimg, wt = _weight_images(ws[l], keep and (l > 0 or ctx.needs_input_grad[0]))
             wts.append(wt)
-            if train:
-                _, img, img_t, _ = tc_gemm(img, wimg, B, N, K, bias=bs[l], activation=ACT_ELU, out_image=True,
-                                           out_image_t=256, k_block_ranges=None if kb_fwd is None else kb_fwd[l])
-            else:
-                _, img = tc_gemm(img, wimg, B, N, K, bias=bs[l], activation=ACT_ELU, out_image=True,
-                                 k_block_ranges=None if kb_fwd is None else kb_fwd[l])
-                img_t = None
-            acts.append(img)                                     # bf16 image: next operand and ELU' operand of the backward pass
-            acts_t.append(img_t)
+            _, img = tc_gemm(img, wimg, B, N, K, bias=bs[l], activation=ACT_ELU, out_image=True,
+                             k_block_ranges=None if kb_fwd is None else kb_fwd[l])
+            imgs.append(img)                 # bf16 row image: next operand, ELU' operand and weight-gradient operand
         N, K = ws[-1].shape
         y = torch.empty_like(x)
         logdet = torch.zeros(B, dtype=torch.float32, device=x.device)
@@ -701,8 +685,7 @@ class MadeTxFunctionTC(torch.autograd.Function):
         tc_gemm(img, wimg, B, N, K, bias=bs[-1], k_block_ranges=None if kb_fwd is None else kb_fwd[-1],
                 tx=TcTx(spec['kind'], spec['cols'], x, y=y, logdet=logdet, max_radius=spec['max_radius'],
                         unit_sphere=spec['unit_sphere']))
-        ctx.save_for_backward(*(acts if keep else acts[:1]), *ws, bs[-1], *([wimg] if keep else []))
-        ctx.acts_t = acts_t if keep else None
+        ctx.save_for_backward(x, *(imgs if keep else []), *ws, bs[-1], *([wimg] if keep else []))
         ctx.wts = wts if keep else None
         ctx.meta = (L, kb_fwd, kb_bwd, rr_w, spec)
         if spec['kind'] == 'sos':
@@ -713,8 +696,7 @@ class MadeTxFunctionTC(torch.autograd.Function):
     def backward(ctx, grad_y, grad_ld):
         L, kb_fwd, kb_bwd, rr_w, spec = ctx.meta
         saved = list(ctx.saved_tensors)
-        acts, ws, b_last, w_last_img = saved[:L], saved[L:2 * L], saved[2 * L], saved[2 * L + 1]
-        x, last_img = acts[0], acts[-1]
+        x, imgs, ws, b_last, w_last_img = saved[0], saved[1:1 + L], saved[1 + L:1 + 2 * L], saved[1 + 2 * L], saved[2 + 2 * L]
         B = x.shape[0]
         grad_y = torch.zeros_like(x) if grad_y is None else _rows(grad_y.contiguous())
         if grad_ld is not None:
@@ -722,14 +704,13 @@ class MadeTxFunctionTC(torch.autograd.Function):
         need_w = [ctx.needs_input_grad[6 + l] or ctx.needs_input_grad[6 + L + l] for l in range(L)]
         gx = torch.empty_like(x)
         N, K = ws[-1].shape
-        _, gimg, gimg_t, gb = tc_gemm(last_img, w_last_img, B, N, K, bias=b_last, out_image=True,
-                                      out_image_t=128 if need_w[-1] else None, column_sums=True,
-                                      k_block_ranges=None if kb_fwd is None else kb_fwd[-1],
-                                      tx=TcTx(spec['kind'], spec['cols'], x, grad_y=grad_y, grad_logdet=grad_ld, grad_x=gx,
-                                              max_radius=spec['max_radius'], unit_sphere=spec['unit_sphere']))
-        _, gws, gbs = _made_tc_backward_layers(acts, ctx.acts_t, ws, kb_bwd, rr_w, need_w, ctx.needs_input_grad[0],
-                                               None, gimg, gimg_t, gb, gx_into=gx, wts=ctx.wts)
-        ctx.acts_t = ctx.wts = None
+        _, gimg, _, gb = tc_gemm(imgs[-1], w_last_img, B, N, K, bias=b_last, out_image=True, column_sums=True,
+                                 k_block_ranges=None if kb_fwd is None else kb_fwd[-1],
+                                 tx=TcTx(spec['kind'], spec['cols'], x, grad_y=grad_y, grad_logdet=grad_ld, grad_x=gx,
+                                         max_radius=spec['max_radius'], unit_sphere=spec['unit_sphere']))
+        _, gws, gbs = _made_tc_backward_layers(B, imgs, ws, kb_bwd, rr_w, need_w, ctx.needs_input_grad[0], gimg, gb, gx_into=gx,
+                                               wts=ctx.wts)
+        ctx.wts = None
         return (gx if ctx.needs_input_grad[0] else None, None, None, None, None, None, *gws, *gbs)
 
 

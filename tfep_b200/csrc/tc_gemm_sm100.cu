@@ -68,6 +68,7 @@ struct Params {
     const int* row_ranges;              // per n-tile: rows [begin, end) of C that can be non-zero; other tiles are skipped, or null
     int atomic;                         // atomicAdd into C (split-K)
     int c_add;                          // C += result (no split-K)
+    int mn_major, a_kblocks, b_kblocks; // operands are read MN-major out of row images (weight gradient), their k-block counts
     int k_chunk_blocks;                 // split-K: k-blocks per blockIdx.y slice, 0 = no split
     int tiles_m, tiles_n;
     int* error;
@@ -511,6 +512,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                     for (int i = 0; i < 16; ++i) xp[(c16 * 16 + i) * XP_LD + lane] = v[i];
                 }
                 if (p.out_img != nullptr) {
+                    if (!row_ok) {
+                        // rows beyond M carry the bias only; a weight-gradient product reads the image MN-major and reduces
+                        // over its rows, so they must be zero
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                    }
                     // columns are the reduction index of the next product: k-block = gn / 64, slab = (gn % 64) / 8;
                     // consecutive rows are consecutive 16-byte chunks of a slab (coalesced as is)
                     const int kblk = gn0 >> 6;
@@ -675,6 +682,169 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                             }
                         }
                         __syncwarp();
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&sm->acc_empty[buf]);
+            ++tcount;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------
+// Weight gradient straight from ROW images: dW[m x n] = dY^T X with dY given as the (k x m) row image the backward-input
+// product reads K-major and X as the (k x n) row image the forward product read -- here both are read MN-major and the
+// reduction runs over their rows, so no transposed copy of any activation or cotangent exists.
+//
+// In a row image the 128 rows of a row block are contiguous inside every 8-column slab (2 KB) and the slabs of a row block
+// follow each other across its k-blocks, i.e. the operand of a 128-row reduction block is ONE contiguous run: 16 slabs =
+// 32 KB for 128 output rows (A), 32 slabs = 64 KB for 256 output columns (B).  A ring stage is therefore a whole 128-row
+// block of both operands (96 KB, two stages, two bulk copies per stage; a first version that took 64-row half slabs as 48
+// separate 1 KB copies per stage ran 3.3 x slower: the copy engine is bound by the number of copies).  MN-major no-swizzle
+// descriptors (cute/atom/mma_traits_sm100.hpp, canonical INTERLEAVE layouts): a core matrix is 8 k x 16 bytes of MN,
+// leading offset = 128 B between 8-k groups, stride offset = 2 KB between 8-element MN groups; instruction descriptor
+// bits 15 / 16 = A / B MN-major.  Split-K over the row blocks, fp32 vector atomics straight from the accumulator rows.
+// ------------------------------------------------------------------------------------------
+constexpr int WG_STAGE = 2 * A_BLOCK + 2 * B_BLOCK;       // 32 + 64 KB
+constexpr int WG_STAGES = 2;
+
+__global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(const __grid_constant__ Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* ring = smem_raw;
+    Smem* sm = reinterpret_cast<Smem*>(ring + (size_t)WG_STAGES * WG_STAGE);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_tiles = p.tiles_m * p.tiles_n;
+    const int row_blocks = (p.K + 127) / 128;             // reduction blocks of 128 image rows
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&sm->acc_full[b], 1); mbar_init(&sm->acc_empty[b], EPI_WARPS * 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(&sm->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm->tmem_base;
+
+    auto skipped = [&](int tm, int tn) -> bool {
+        if (p.row_ranges == nullptr) return false;
+        const int rb = p.row_ranges[2 * tn], re = p.row_ranges[2 * tn + 1];
+        return tm * BM + BM <= rb || tm * BM >= re;
+    };
+    // this CTA's slice of the reduction (k_chunk_blocks counts 128-row blocks here)
+    int r0 = 0, r1 = row_blocks;
+    if (p.k_chunk_blocks > 0) {
+        r0 = min(row_blocks, (int)blockIdx.y * p.k_chunk_blocks);
+        r1 = min(row_blocks, r0 + p.k_chunk_blocks);
+    }
+    const int a_slabs = p.a_kblocks * 8, b_slabs = p.b_kblocks * 8;     // slabs per row block of the two images
+
+    if (warp == 0) {
+        uint32_t stage = 0, phase = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+            if (skipped(tm, tn)) continue;
+            // slabs of the tile that exist in the images (the rest of the stage keeps stale bytes: they only feed rows /
+            // columns of C beyond m / n, which are never stored)
+            const uint32_t a_bytes = (uint32_t)min(16, a_slabs - tm * 16) * 2048u;
+            const uint32_t b_bytes = (uint32_t)min(32, b_slabs - tn * 32) * 2048u;
+            for (int rb = r0; rb < r1; ++rb) {
+                mbar_wait(&sm->empty[stage], phase ^ 1, p.error, 1);
+                if (elect_one()) {
+                    uint8_t* dst = ring + (size_t)stage * WG_STAGE;
+                    mbar_expect_tx(&sm->full[stage], a_bytes + b_bytes);
+                    bulk_g2s(dst, p.a_img + ((size_t)rb * a_slabs + (size_t)tm * 16) * 2048, a_bytes, &sm->full[stage]);
+                    bulk_g2s(dst + 2 * A_BLOCK, p.b_img + ((size_t)rb * b_slabs + (size_t)tn * 32) * 2048, b_bytes, &sm->full[stage]);
+                }
+                __syncwarp();
+                if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        uint32_t stage = 0, phase = 0, tcount = 0;
+        const uint32_t ring16 = smem_u32(ring) >> 4;
+        // kind::f16, A = B = bf16, D = fp32, both MN-major, M = 128, N = 256
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
+                               ((uint32_t)(BM >> 4) << 24);
+        constexpr uint32_t HI_MN = (2048u >> 4) | (1u << 14);            // stride offset 2 KB, descriptor version 1
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+            if (skipped(tm, tn)) continue;
+            const uint32_t buf = tcount & 1;
+            mbar_wait(&sm->acc_empty[buf], ((tcount >> 1) & 1) ^ 1, p.error, 2);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem + buf * BN;
+            uint32_t accumulate = 0u;
+            for (int rb = r0; rb < r1; ++rb) {
+                mbar_wait(&sm->full[stage], phase, p.error, 3);
+                tc_fence_after();
+                const uint32_t a16 = ring16 + stage * (WG_STAGE >> 4);
+                const uint32_t b16 = a16 + ((2 * A_BLOCK) >> 4);
+                if (elect_one()) {
+#pragma unroll
+                    for (uint32_t ks = 0; ks < 128 / 16; ++ks) {
+                        // K = 16 step = two 8-row groups = 256 B further into every slab
+                        const uint64_t da = ((uint64_t)HI_MN << 32) | (a16 + ks * 16u + ((128u >> 4) << 16));
+                        const uint64_t db = ((uint64_t)HI_MN << 32) | (b16 + ks * 16u + ((128u >> 4) << 16));
+                        umma_ss(d_tmem, da, db, idesc, accumulate);
+                        accumulate = 1u;
+                    }
+                    umma_commit(&sm->empty[stage]);
+                }
+                __syncwarp();
+                if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (elect_one()) umma_commit(&sm->acc_full[buf]);
+            __syncwarp();
+            ++tcount;
+        }
+    } else {
+        // epilogue: the warp's 32 rows x 64 columns go to C with 16-byte vector atomics (a thread owns a row)
+        const int ew = warp - 2;
+        const int cgroup = ew >> 2;
+        const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const bool vec = (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (p.ldc & 3) == 0;
+        uint32_t tcount = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+            if (skipped(tm, tn)) continue;
+            const uint32_t buf = tcount & 1;
+            mbar_wait(&sm->acc_full[buf], (tcount >> 1) & 1, p.error, 4);
+            tc_fence_after();
+            const int gm = tm * BM + (warp & 3) * 32 + lane;
+            if (r1 > r0) {
+#pragma unroll 1
+                for (int q = 0; q < 4; q += 2) {
+                    const int gn0 = tn * BN + cgroup * 64 + q * 16;
+                    if (gn0 >= p.N) break;                               // warp-uniform
+                    uint32_t ra[16], rb16[16];
+                    tmem_ld16(lane_addr + buf * BN + cgroup * 64 + q * 16, ra);
+                    tmem_ld16(lane_addr + buf * BN + cgroup * 64 + q * 16 + 16, rb16);
+                    tmem_wait8(ra); tmem_wait8(ra + 8); tmem_wait8(rb16); tmem_wait8(rb16 + 8);
+                    if (gm < p.M) {
+                        float* crow = p.C + (int64_t)gm * p.ldc + gn0;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint32_t* r = h == 0 ? ra : rb16;
+                            const int gnh = gn0 + h * 16;
+                            if (vec && gnh + 15 < p.N) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+                                    atomicAdd(reinterpret_cast<float4*>(crow + h * 16) + i,
+                                              make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                                          __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    if (gnh + i < p.N) atomicAdd(crow + h * 16 + i, __uint_as_float(r[i]));
+                            }
+                        }
                     }
                 }
             }
@@ -892,6 +1062,11 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
                     "aux and aux_image are alternatives; images are 16-byte aligned");
     TFEPB_CHECK_ARG(a->aux_image == nullptr || (a->activation == TFEPB_ACT_NONE && a->n_split <= 1),
                     "aux_image: plain bf16 product without activation");
+    TFEPB_CHECK_ARG(!a->mn_major || (a->n_split <= 1 && a->tx == nullptr && a->k_block_ranges == nullptr && a->c != nullptr &&
+                                     a->out_image == nullptr && a->out_image_t == nullptr && a->column_sums == nullptr &&
+                                     a->bias == nullptr && a->aux == nullptr && a->aux_image == nullptr &&
+                                     a->activation == TFEPB_ACT_NONE),
+                    "mn_major: the raw product of two row images is ADDED to c (zero-filled by the caller), nothing else");
     TFEPB_CHECK_ARG(!a->c_accumulate || (a->aux == nullptr && a->tx == nullptr),
                     "c_accumulate shares the staging buffer of aux and of the fused transformer (use aux_image)");
     if (int rc = require_sm100()) return rc;
@@ -923,6 +1098,26 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
     if (splits > p.k_blocks) splits = p.k_blocks;
     p.atomic = splits > 1 ? 1 : 0;
     p.c_add = (a->c_accumulate != 0 && splits <= 1 && a->c != nullptr) ? 1 : 0;
+    p.mn_major = a->mn_major != 0 ? 1 : 0;
+    p.a_kblocks = (a->m + tcg::KB - 1) / tcg::KB;        // row images: a_image holds (k x m), b_image (k x n)
+    p.b_kblocks = (a->n + tcg::KB - 1) / tcg::KB;
+    if (p.mn_major) {
+        // dedicated kernel: the reduction is cut in blocks of 128 image rows; always accumulates into C with atomics
+        const int row_blocks = (a->k + 127) / 128;
+        int sp = a->split_k > 1 ? a->split_k : 1;
+        if (sp > row_blocks) sp = row_blocks;
+        p.k_chunk_blocks = (row_blocks + sp - 1) / sp;
+        sp = (row_blocks + p.k_chunk_blocks - 1) / p.k_chunk_blocks;
+        p.atomic = 1;
+        const size_t wg_smem = (size_t)tcg::WG_STAGES * tcg::WG_STAGE + sizeof(tcg::Smem) + 256;
+        if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(tcg::tc_wgrad_kernel), wg_smem)) return rc;
+        const int wg_tiles = p.tiles_m * p.tiles_n;
+        int wgx = sm_count() / sp;
+        if (wgx < 1) wgx = 1;
+        if (wgx > wg_tiles) wgx = wg_tiles;
+        tcg::tc_wgrad_kernel<<<dim3((unsigned)wgx, (unsigned)sp), tcg::THREADS, wg_smem, as_stream(stream)>>>(p);
+        return check_launch("tc_wgrad_kernel");
+    }
     p.k_chunk_blocks = splits > 1 ? (p.k_blocks + splits - 1) / splits : 0;
     if (splits > 1) splits = (p.k_blocks + p.k_chunk_blocks - 1) / p.k_chunk_blocks;
     const int n_split = a->n_split > 1 ? a->n_split : 1;
