@@ -584,8 +584,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                         __syncwarp();
                     }
                     if (p.c_add) {
-                        // C += result: the old values come in like the ELU' operand (requested before the accumulator is read)
-#pragma unroll 8
+                        // C += result: the old values come in like the ELU' operand (requested before the accumulator is read;
+                        // all 32 loads of the lane in flight together)
+#pragma unroll
                         for (int r = 0; r < 32; ++r) {
                             const int grow = gm0 + r;
                             xp[lane * XP_LD + r] = (grow < p.M && gns + lane < p.N) ? p.C[(int64_t)grow * p.ldc + gns + lane] : 0.f;
@@ -888,8 +889,15 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const float* __restrict__ 
             const int row = i % block_rows, slab = i / block_rows;
             const int gr = r0 + row, gk = k0 + slab * 8;
             float v[8];
+            if (gr < rows && gk + 7 < K && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+                // 32 contiguous, 16-byte aligned bytes of the row: two vector loads instead of eight scalar ones
+                const float4* s4 = reinterpret_cast<const float4*>(src + (int64_t)gr * ld + gk);
+                const float4 lo = __ldg(s4), hi = __ldg(s4 + 1);
+                v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+            } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = (gr < rows && gk + j < K) ? __ldg(src + (int64_t)gr * ld + gk + j) : 0.f;
+                for (int j = 0; j < 8; ++j) v[j] = (gr < rows && gk + j < K) ? __ldg(src + (int64_t)gr * ld + gk + j) : 0.f;
+            }
             for (int t = 0; t < n_split; ++t)
                 *reinterpret_cast<uint4*>(blk + (size_t)t * split_stride + (size_t)slab * block_rows * 16 + (size_t)row * 16) =
                     split_term(v, t + 1 < n_split);
