@@ -540,10 +540,11 @@ class MadeFunctionTC(torch.autograd.Function):
     """All layers of a MADE conditioner on the tensor cores (tfepb_tc_gemm), as one autograd node.
 
     Same contract as :class:`MadeFunction` (packed effective weights in, dense gradients out) with bf16 operands and
-    fp32 accumulation: the forward pass chains the bf16 image of every hidden activation into the next product; the
-    backward pass runs dX = (dY W) * ELU'(h) and dW = dY^T X (split over the batch, fp32 atomics) on the same kernel
-    from images of dY, W^T and the transposed activations.  ``kb_fwd[l]`` / ``kb_bwd[l]`` are the per-256-column-tile
-    ranges of non-zero 64-wide k-blocks of the staircase masks (or None).
+    fp32 accumulation: the forward pass chains the bf16 row image of every hidden activation into the next product; the
+    backward pass runs dX = (dY W) * ELU'(h) on the same kernel (ELU' read from the image of h) and dW = dY^T X on the
+    MN-major weight-gradient kernel, which reduces over the rows of the SAME images of dY and X (split over the batch,
+    fp32 atomics).  ``kb_fwd[l]`` / ``kb_bwd[l]`` are the per-256-column-tile ranges of non-zero 64-wide k-blocks of the
+    staircase masks (or None).
     """
 
     @staticmethod
