@@ -149,6 +149,22 @@ __device__ __forceinline__ void tx_stage_out(float* __restrict__ dst, int64_t ld
     }
 }
 
+// Sums over the 32 rows (lanes) of the 16 columns a chunk holds, without shared memory: recursive halving -- every step a lane
+// keeps one half of its columns, sends the other half to the partner that keeps it, and adds what it receives (16 shuffles);
+// lane l ends with the sum of column (l >> 1) & 15 (both lanes of a pair hold it).
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
+    float a[8], b[4], c[2];
+    const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = (h4 ? v[8 + i] : v[i]) + __shfl_xor_sync(0xffffffffu, h4 ? v[i] : v[8 + i], 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) b[i] = (h3 ? a[4 + i] : a[i]) + __shfl_xor_sync(0xffffffffu, h3 ? a[i] : a[4 + i], 8);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) c[i] = (h2 ? b[2 + i] : b[i]) + __shfl_xor_sync(0xffffffffu, h2 ? b[i] : b[2 + i], 4);
+    const float d = (h1 ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, h1 ? c[0] : c[1], 2);
+    return d + __shfl_xor_sync(0xffffffffu, d, 1);
+}
+
 // One 16-column chunk of one row: v holds the parameters (bias added) of the chunk's units; xs / gs: the staged x (and, for
 // the backward direction, grad_y) columns of the chunk, [column][row].  Forward: y replaces x in its slot, the log-det is
 // accumulated.  Backward: grad_x replaces grad_y in its slot and v becomes the parameter cotangents (zeros in pad columns,
@@ -416,6 +432,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             using TG = TxGeo<TX>;
             [[maybe_unused]] const int tx_cn = p.tx_units * TG::XPU;            // x columns in the table
             [[maybe_unused]] float gl = 0.f;
+            [[maybe_unused]] const bool xp_free = p.C == nullptr && p.out_img_t == nullptr;   // transposition buffer not needed
             if constexpr (TX != 0 && !tx_bwd(TX)) {
                 // x of the first sub-tile's two chunks, and of the second one's where the buffer holds both (GF == 4)
                 tx_stage_in<2 * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, (gn_sub0 >> 4) * TG::XPC, tx_cn, xp, lane);
@@ -428,6 +445,16 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                 tx_stage_in<TG::GB * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, (gn_sub0 >> 4) * TG::XPC, tx_cn, xp, lane);
                 tx_stage_in<TG::GB * TG::XPC>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, (gn_sub0 >> 4) * TG::XPC, tx_cn,
                                                xp + TG::GB * TG::XPC * XP_LD, lane);
+                if constexpr (TG::GB == 2 && 8 * TG::XPC <= 32) {
+                    // the second sub-tile's operands too, when the buffer holds both and nothing else needs it (the column sums
+                    // of the VJP variants are reduced with shuffles)
+                    if (xp_free && gn_sub1 < p.N) {
+                        tx_stage_in<2 * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, (gn_sub1 >> 4) * TG::XPC, tx_cn,
+                                                 xp + 4 * TG::XPC * XP_LD, lane);
+                        tx_stage_in<2 * TG::XPC>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, (gn_sub1 >> 4) * TG::XPC, tx_cn,
+                                                 xp + 6 * TG::XPC * XP_LD, lane);
+                    }
+                }
                 if (p.tx_gl != nullptr && row_ok) gl = __ldg(p.tx_gl + gm);
             }
             mbar_wait(&sm->acc_full[buf], (tcount >> 1) & 1, p.error, 4);
@@ -507,7 +534,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                             if (gn0 + i >= p.N) v[i] = 0.f;
                     }
                 }
-                if (p.C != nullptr || p.out_img_t != nullptr || p.colsum != nullptr) {
+                if (p.C != nullptr || p.out_img_t != nullptr || (TX == 0 && p.colsum != nullptr)) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) xp[(c16 * 16 + i) * XP_LD + lane] = v[i];
                 }
@@ -602,16 +629,18 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                         constexpr int XG = TG::GB * TG::XPC;                                       // x columns per staging group
                         if constexpr (TG::GB == 2) {
                             const int c0 = (gns >> 4) * TG::XPC;
-                            if (sub > 0) {
-                                tx_stage_in<XG>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, xp, lane);
-                                tx_stage_in<XG>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, c0, tx_cn, xp + XG * XP_LD, lane);
+                            const bool both = 8 * TG::XPC <= 32 && xp_free;          // both sub-tiles were staged before the wait
+                            float* xs = xp + ((both && sub > 0) ? 2 * XG * XP_LD : 0);
+                            if (sub > 0 && !both) {
+                                tx_stage_in<XG>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, xs, lane);
+                                tx_stage_in<XG>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, c0, tx_cn, xs + XG * XP_LD, lane);
                                 __syncwarp();
                             }
-                            tx_chunk<TX>(p, va, xp, xp + XG * XP_LD, lane, gl, row_ok, gns >> 4, unused);
-                            tx_chunk<TX>(p, vb, xp + TG::XPC * XP_LD, xp + (XG + TG::XPC) * XP_LD, lane, gl, row_ok,
+                            tx_chunk<TX>(p, va, xs, xs + XG * XP_LD, lane, gl, row_ok, gns >> 4, unused);
+                            tx_chunk<TX>(p, vb, xs + TG::XPC * XP_LD, xs + (XG + TG::XPC) * XP_LD, lane, gl, row_ok,
                                          (gns >> 4) + 1, unused);
                             __syncwarp();
-                            tx_stage_out<XG>(p.tx_gx, p.tx_ldgx, gm0, p.M, p.tx_cols, c0, tx_cn, xp + XG * XP_LD, lane);
+                            tx_stage_out<XG>(p.tx_gx, p.tx_ldgx, gm0, p.M, p.tx_cols, c0, tx_cn, xs + XG * XP_LD, lane);
                             __syncwarp();
                         } else {
 #pragma unroll
@@ -629,9 +658,20 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                             }
                         }
                     }
+                    if constexpr (TX != 0) {
+                        // bias gradient: column sums of the cotangents by shuffles (rows beyond M and pad columns are zero)
+                        if (p.colsum != nullptr) {
+                            const float sa = warp_colsum16(va, lane), sb = warp_colsum16(vb, lane);
+                            const int n = gns + ((lane >> 1) & 15);
+                            if ((lane & 1) == 0) {
+                                if (n < p.N) atomicAdd(p.colsum + n, sa);
+                                if (n + 16 < p.N) atomicAdd(p.colsum + n + 16, sb);
+                            }
+                        }
+                    }
                     emit_chunk(2 * sub, va);
                     emit_chunk(2 * sub + 1, vb);
-                    if (p.out_img_t != nullptr || p.colsum != nullptr) {
+                    if (p.out_img_t != nullptr || (TX == 0 && p.colsum != nullptr)) {
                         // lane = column of C = row of the transposed image; its 32 k-values (rows gm0 .. gm0 + 31 of C) are
                         // four 16-byte chunks of consecutive slabs, and consecutive lanes write consecutive chunks
                         __syncwarp();
@@ -665,7 +705,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                                 *reinterpret_cast<uint4*>(blk + (size_t)(slab0 + j) * p.t_rows * 16) =
                                     make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
                         }
-                        if (p.colsum != nullptr && n < p.N) atomicAdd(p.colsum + n, cs);
+                        if (TX == 0 && p.colsum != nullptr && n < p.N) atomicAdd(p.colsum + n, cs);
                         if (p.C == nullptr) __syncwarp();
                     }
                     if (p.C != nullptr) {
