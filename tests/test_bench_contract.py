@@ -43,7 +43,8 @@ def test_measured_arm_line():
     # (the pipelined e2e loop neither flushes L2 nor pays per-step event gaps: it may come out a little above `value`)
     assert 0 < e['value'] <= 1.15 * d['value'] and e['h2d_bytes_per_step'] == 65536 * 66 * 4
     assert e['d2h_bytes_per_step'] == 65536 * 4 + 16 and e['unit'] == 'samples/s'       # per-sample work + estimator partial
-    assert e['value'] <= 1.1 * e['host_ceiling']['samples_per_s'] and e['delta_f_last_step'] == e['delta_f_last_step']
+    # (the ceiling is itself a measurement on a shared host: 15 % of slack)
+    assert e['value'] <= 1.15 * e['host_ceiling']['samples_per_s'] and e['delta_f_last_step'] == e['delta_f_last_step']
     f = d['e2e_full_outputs']
     assert 0 < f['value'] <= 1.15 * d['value'] and f['d2h_bytes_per_step'] == 65536 * 67 * 4
     r = d['roofline']
