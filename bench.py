@@ -663,6 +663,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        # stdout carries ONE JSON line: NCCL's own log (e.g. the version banner of NCCL_DEBUG=VERSION) goes to stderr
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     try:
         run_ours(args, rank, world, local_rank)
