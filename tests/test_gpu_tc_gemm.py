@@ -125,7 +125,8 @@ def test_split_precision_products(m, n, k, n_split, tol):
         assert float((cr.double() - refr).abs().max()) < tol * (1 + float(refr.abs().max()))
 
 
-@pytest.mark.parametrize('batch,n_out,n_in,split', [(5000, 300, 200, 16), (130, 1600, 670, 3), (64, 7, 9, 1), (1000, 670, 300, 5)])
+@pytest.mark.parametrize('batch,n_out,n_in,split', [(5000, 300, 200, 16), (130, 1600, 670, 3), (64, 7, 9, 1), (1000, 670, 300, 5),
+                                                    (5, 33, 300, 4), (129, 128, 256, 2)])
 def test_weight_gradient_from_row_images_mn_major(batch, n_out, n_in, split):
     """dW = dY^T X read MN-major out of the SAME row images that the forward / backward-input products use (no transposed
     images): reduction over the rows of both images, batch sizes that end inside a 64-row k-block and inside a 128-row

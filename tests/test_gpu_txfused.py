@@ -136,3 +136,31 @@ def test_fused_epilogue_in_a_training_step():
         out.append((float(loss), torch.cat([p.detach().flatten() for p in flow.parameters()])))
     assert abs(out[0][0] - out[1][0]) < 1e-4 * (1 + abs(out[0][0]))
     assert _rel(out[1][1], out[0][1]) < 1e-5
+
+
+@pytest.mark.parametrize('kind,n_features', [('sos', 21), ('moebius', 27), ('affine', 10)])
+@pytest.mark.parametrize('batch', [1, 3, 129])
+@pytest.mark.parametrize('which', ['x', 'parameters'])
+def test_fused_epilogue_partial_gradients_and_tiny_batches(kind, n_features, batch, which):
+    """Only x, or only the parameters, require a gradient (frozen conditioner / plain training step), on batches smaller than
+    one reduction block of the weight gradient: same results as the separate kernels."""
+    maf = _flow(kind, n_features, 'ascending', seed=11)
+    maf.precision = 'bf16'
+    for p in maf.parameters():
+        p.requires_grad_(which == 'parameters')
+    x = _input(kind, batch, n_features, 12)
+    g = torch.Generator().manual_seed(13)
+    cy = torch.randn(batch, n_features, generator=g).to(DEV)
+    out = []
+    for fuse in (False, True):
+        maf.fuse_transformer = fuse
+        maf.zero_grad(set_to_none=True)
+        xg = x.clone().requires_grad_(which == 'x')
+        y, ld = maf(xg)
+        ((y * cy).sum() + (ld.sum() if ld.requires_grad else 0.0)).backward()
+        grads = [xg.grad] if which == 'x' else [p.grad for p in maf.parameters()]
+        assert all(gr is not None and torch.isfinite(gr).all() for gr in grads)
+        out.append((y.detach(), ld.detach(), torch.cat([gr.flatten() for gr in grads])))
+    assert _rel(out[1][0], out[0][0]) < 1e-5
+    assert float((out[1][1] - out[0][1]).abs().max()) < 1e-4 * (1 + float(out[0][1].abs().max()))
+    assert _rel(out[1][2], out[0][2]) < 2e-4
