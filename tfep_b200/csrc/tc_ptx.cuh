@@ -58,10 +58,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // cannot allocate registers across an ABI call inside a setmaxnreg region.)
 #ifdef TFEPB_INLINE_SLOW_WAIT
 static __device__ __forceinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int* error, int tag) {
-    uint32_t polls = 0;
+    uint32_t bursts = 0;
     long long t0 = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++polls & 0xfffu) != 0) continue;
+    const uint32_t addr = smem_u32(bar);
+    while (!mbar_poll_burst(addr, parity)) {
+        if ((++bursts & 0xfu) != 0) continue;
         if (t0 == 0) t0 = clock64();
         if ((uint64_t)(clock64() - t0) > WATCHDOG_CYCLES) {
             if (error) atomicExch(error, tag);
@@ -105,10 +106,10 @@ __device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity, int* error, int tag) {
     if (mbar_try_wait_s(bar, parity)) return;
-    uint32_t polls = 0;
+    uint32_t bursts = 0;
     long long t0 = 0;
-    while (!mbar_try_wait_s(bar, parity)) {
-        if ((++polls & 0xfffu) != 0) continue;
+    while (!mbar_poll_burst(bar, parity)) {
+        if ((++bursts & 0xfu) != 0) continue;
         if (t0 == 0) t0 = clock64();
         if ((uint64_t)(clock64() - t0) > WATCHDOG_CYCLES) {
             if (error) atomicExch(error, tag);
