@@ -179,6 +179,56 @@ def test_packing_plan_is_a_relabelling():
         assert pos == maf._conditioner.dimension_out
 
 
+def test_padded_chunk_layout_of_the_fused_transformer_epilogue():
+    """tfep_b200/_txfused.py: the output layer of an SOS / Moebius / affine MAF in 16-column chunks of whole units (host logic):
+    the padded plan is the packed plan with all-zero rows in the pad columns, units stay in degree order (the staircase
+    ranges of the padded layer never exceed those of the unpadded rows they hold) and the column table lists the x columns
+    of every unit."""
+    from tfep_b200 import _txfused
+    from tfep_b200.nn.transformers import MoebiusTransformer, SOSPolynomialTransformer
+    torch.manual_seed(0)
+    for maf, upc, ppu in (
+            (MAF(generate_degrees(40, order='descending'), SOSPolynomialTransformer(2), initialize_identity=False), 3, 5),
+            (MAF(generate_degrees(33, repeats=3), MoebiusTransformer(dimension=3), initialize_identity=False), 5, 3),
+            (MAF(generate_degrees(19), initialize_identity=False), 8, 2)):
+        pk = maf._pack()
+        assert _txfused.eligibility(maf, pk) is None
+        txp = _txfused.TcTxPlan(maf, pk)
+        made = maf._conditioner
+        with torch.no_grad():
+            pw, pb = made.packed_weights(pk['plan'])
+            qw, qb = made.packed_weights(txp.plan)
+        n_rows = pw[-1].shape[0]
+        n_units = n_rows // ppu
+        assert txp.n_padded == -(-n_units // upc) * 16 == qw[-1].shape[0]
+        for u in range(n_units):
+            r0 = (u // upc) * 16 + (u % upc) * ppu
+            assert torch.equal(qw[-1][r0:r0 + ppu], pw[-1][u * ppu:(u + 1) * ppu])
+            assert torch.equal(qb[-1][r0:r0 + ppu], pb[-1][u * ppu:(u + 1) * ppu])
+        pad = torch.ones(txp.n_padded, dtype=torch.bool)
+        for u in range(n_units):
+            r0 = (u // upc) * 16 + (u % upc) * ppu
+            pad[r0:r0 + ppu] = False
+        assert float(qw[-1][pad].abs().sum()) == 0.0 and float(qb[-1][pad].abs().sum()) == 0.0
+        for l in range(len(pw) - 1):
+            assert torch.equal(qw[l], pw[l])
+        # x columns of the units in chunk order = the columns of the degree-sorted features
+        part = pk['parts'][0]
+        order = torch.argsort(pk['bases'][0].view(-1, 3 if ppu == 3 else 1)[:, 0])
+        cols = part.x_columns().view(-1, 3 if ppu == 3 else 1)[order].reshape(-1)
+        assert torch.equal(txp.cols.long(), cols)
+        # staircase: everything outside the forward k-block range of a 256-row tile of the padded layer is zero
+        fwd = txp.plan.tc_ranges('cpu')[0][-1]
+        for t, (kb, ke) in enumerate(fwd.tolist()):
+            tile = qw[-1][t * 256:(t + 1) * 256]
+            assert float(tile[:, :kb * 64].abs().sum()) == 0.0 and float(tile[:, ke * 64:].abs().sum()) == 0.0
+    # flows the epilogue does not cover say why
+    sos3 = MAF(generate_degrees(8), SOSPolynomialTransformer(3), initialize_identity=False)
+    assert 'polynomials' in _txfused.eligibility(sos3, sos3._pack())
+    cond = MAF([-1] + generate_degrees(6).tolist(), initialize_identity=False)
+    assert _txfused.eligibility(cond, cond._pack()) is not None
+
+
 def test_staircase_skips_about_half_of_the_headline_config():
     maf = MAF(generate_degrees(66), NeuralSplineTransformer(torch.zeros(66), torch.ones(66), 8, circular=True))
     plan = maf._pack()['plan']

@@ -53,7 +53,9 @@ class MAF(AutoregressiveFlow):
         one-launch kernels where they cover the layer, else the general tcgen05 GEMM), stated tolerance in DESIGN.md.
         ``'bf16x3'`` / ``'bf16x6'``: tensor cores with every operand split into two / three bf16 terms (3 / 6 products
         per reduction step, fp32 accumulation): the conditioner at fp32-class accuracy on the tensor cores.
-        Also an attribute: ``maf.precision = ...`` switches an existing module.
+        Also an attribute: ``maf.precision = ...`` switches an existing module.  With ``'bf16'`` and an affine / SOS (two
+        polynomials) / Moebius (3-vectors) transformer over all features, the transformer and its VJP run in the epilogue of
+        the output-layer product, forward and backward (``maf.fuse_transformer = False`` keeps the separate kernels).
     """
 
     def __init__(
