@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             using TG = TxGeo<TX>;
             [[maybe_unused]] const int tx_cn = p.tx_units * TG::XPU;            // x columns in the table
             [[maybe_unused]] float gl = 0.f;
-            [[maybe_unused]] const bool xp_free = p.C == nullptr && p.out_img_t == nullptr;   // transposition buffer not needed
+            [[maybe_unused]] constexpr bool xp_free = true;   // the VJP variants never use the transposition buffer for anything else
             if constexpr (TX != 0 && !tx_bwd(TX)) {
                 // x of the first sub-tile's two chunks, and of the second one's where the buffer holds both (GF == 4)
                 tx_stage_in<2 * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, (gn_sub0 >> 4) * TG::XPC, tx_cn, xp, lane);
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                 // ELU' operand from the image of h: this row's 32 columns are four 16-byte pieces of consecutive slabs
                 // (consecutive rows = consecutive pieces: coalesced as is); requested together with the accumulator
                 uint4 h4[4];
-                const bool with_aux_img = p.aux_img != nullptr && !p.atomic && (gcol(q) >> 6) < p.aux_k_blocks;
+                const bool with_aux_img = TX == 0 && p.aux_img != nullptr && !p.atomic && (gcol(q) >> 6) < p.aux_k_blocks;
                 if (with_aux_img) {
                     const int gn0 = gcol(q);
                     const uint8_t* blk = p.aux_img + ((size_t)tm * p.aux_k_blocks + (gn0 >> 6)) * A_BLOCK + (size_t)row * 16 +
@@ -506,11 +506,33 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                     }
                 }
             };
+            // one chunk (fused-transformer variants with long per-unit bodies go chunk by chunk through ONE copy of the code)
+            [[maybe_unused]] auto load_one = [&](int q, float (&v)[16]) {
+                uint32_t r[16];
+                if (!empty) {
+                    tmem_ld16(lane_addr + buf * BN + (uint32_t)(gcol(q) - tn * BN), r);
+                    tmem_wait8(r); tmem_wait8(r + 8);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) r[i] = 0u;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+                if (with_bias) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 a4 = *reinterpret_cast<const float4*>(bias_w + q * 16 + 4 * i);
+                        v[4 * i] += a4.x; v[4 * i + 1] += a4.y; v[4 * i + 2] += a4.z; v[4 * i + 3] += a4.w;
+                    }
+                }
+            };
             // activation / ELU' / padding, then the chunk goes to the transposition buffer and to the image of the result
             auto emit_chunk = [&](int q, float (&v)[16]) {
                 const int c16 = q & 1;
                 const int gn0 = gcol(q);
-                if (!p.atomic) {
+                // (the fused-transformer variants have no activation, ELU' operand, fp32 output or transposed image: compiled
+                // out there, their instruction footprint decides how much of the epilogue stays in the instruction cache)
+                if (TX == 0 && !p.atomic) {
                     if (p.act == TFEPB_ACT_ELU) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
@@ -534,7 +556,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                             if (gn0 + i >= p.N) v[i] = 0.f;
                     }
                 }
-                if (p.C != nullptr || p.out_img_t != nullptr || (TX == 0 && p.colsum != nullptr)) {
+                if (TX == 0 && (p.C != nullptr || p.out_img_t != nullptr || p.colsum != nullptr)) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) xp[(c16 * 16 + i) * XP_LD + lane] = v[i];
                 }
@@ -587,10 +609,19 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                         tx_stage_in<2 * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, xs, lane);
                         __syncwarp();
                     }
-                    float va[16], vb[16];
-                    load_pair(2 * sub, va, vb);
-                    tx_chunk<TX>(p, va, xs, nullptr, lane, 0.f, row_ok, gns >> 4, ld_acc);
-                    tx_chunk<TX>(p, vb, xs + TG::XPC * XP_LD, nullptr, lane, 0.f, row_ok, (gns >> 4) + 1, ld_acc);
+                    if constexpr (TG::KIND == TFEPB_TCTX_MOEBIUS3) {
+#pragma unroll 1
+                        for (int c16 = 0; c16 < 2; ++c16) {
+                            float v[16];
+                            load_one(2 * sub + c16, v);
+                            tx_chunk<TX>(p, v, xs + c16 * TG::XPC * XP_LD, nullptr, lane, 0.f, row_ok, (gns >> 4) + c16, ld_acc);
+                        }
+                    } else {
+                        float va[16], vb[16];
+                        load_pair(2 * sub, va, vb);
+                        tx_chunk<TX>(p, va, xs, nullptr, lane, 0.f, row_ok, gns >> 4, ld_acc);
+                        tx_chunk<TX>(p, vb, xs + TG::XPC * XP_LD, nullptr, lane, 0.f, row_ok, (gns >> 4) + 1, ld_acc);
+                    }
                     __syncwarp();
                     tx_stage_out<2 * TG::XPC>(p.tx_y, p.tx_ldy, gm0, p.M, p.tx_cols, c0, tx_cn, xs, lane);
                     __syncwarp();
@@ -601,7 +632,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                 for (int sub = 0; sub < 2; ++sub) {
                     const int gns = sub == 0 ? gn_sub0 : gn_sub1;  // first column of the sub-tile
                     if (gns >= p.N && p.out_img == nullptr && (p.out_img_t == nullptr || gns >= p.t_rows_padded)) continue;   // warp-uniform
-                    if (p.aux != nullptr && !p.atomic) {
+                    if (TX == 0 && p.aux != nullptr && !p.atomic) {
                         // coalesced load of the 32 x 32 ELU' operand: lane = column, transposed into the buffer
 #pragma unroll 8
                         for (int r = 0; r < 32; ++r) {
@@ -610,7 +641,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                         }
                         __syncwarp();
                     }
-                    if (p.c_add) {
+                    if (TX == 0 && p.c_add) {
                         // C += result: the old values come in like the ELU' operand (requested before the accumulator is read;
                         // all 32 loads of the lane in flight together)
 #pragma unroll
@@ -620,45 +651,56 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                         }
                         __syncwarp();
                     }
+                    if constexpr (TX != 0 && TG::GB == 1) {
+                        // ---- fused transformer, backward, one chunk at a time (x and grad_y of a chunk fill the staging buffer):
+                        // accumulator -> parameter cotangents -> bias gradient (shuffles) -> image; ONE copy of the long body ----
+                        constexpr int XG = TG::XPC;
+#pragma unroll 1
+                        for (int c16 = 0; c16 < 2; ++c16) {
+                            const int q = 2 * sub + c16;
+                            const int c0 = ((gns >> 4) + c16) * TG::XPC;
+                            float unused = 0.f;
+                            float v[16];
+                            if (q > 0) {
+                                tx_stage_in<XG>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, xp, lane);
+                                tx_stage_in<XG>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, c0, tx_cn, xp + XG * XP_LD, lane);
+                            }
+                            load_one(q, v);
+                            __syncwarp();
+                            tx_chunk<TX>(p, v, xp, xp + XG * XP_LD, lane, gl, row_ok, (gns >> 4) + c16, unused);
+                            __syncwarp();
+                            tx_stage_out<XG>(p.tx_gx, p.tx_ldgx, gm0, p.M, p.tx_cols, c0, tx_cn, xp + XG * XP_LD, lane);
+                            if (p.colsum != nullptr) {
+                                const float sa = warp_colsum16(v, lane);
+                                const int n = gns + c16 * 16 + ((lane >> 1) & 15);
+                                if ((lane & 1) == 0 && n < p.N) atomicAdd(p.colsum + n, sa);
+                            }
+                            emit_chunk(q, v);
+                            __syncwarp();
+                        }
+                        continue;
+                    }
                     float va[16], vb[16];
                     load_pair(2 * sub, va, vb);
                     if constexpr (TX != 0) {
-                        // ---- fused transformer, backward: the chunks become parameter cotangents (x and grad_y staged GB
-                        // chunks at a time, grad_x leaves through the slots of grad_y), then they take the usual way out ----
+                        // ---- fused transformer, backward: the chunks become parameter cotangents (x and grad_y staged two chunks
+                        // at a time, grad_x leaves through the slots of grad_y), then they take the usual way out ----
                         float unused = 0.f;
                         constexpr int XG = TG::GB * TG::XPC;                                       // x columns per staging group
-                        if constexpr (TG::GB == 2) {
-                            const int c0 = (gns >> 4) * TG::XPC;
-                            const bool both = 8 * TG::XPC <= 32 && xp_free;          // both sub-tiles were staged before the wait
-                            float* xs = xp + ((both && sub > 0) ? 2 * XG * XP_LD : 0);
-                            if (sub > 0 && !both) {
-                                tx_stage_in<XG>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, xs, lane);
-                                tx_stage_in<XG>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, c0, tx_cn, xs + XG * XP_LD, lane);
-                                __syncwarp();
-                            }
-                            tx_chunk<TX>(p, va, xs, xs + XG * XP_LD, lane, gl, row_ok, gns >> 4, unused);
-                            tx_chunk<TX>(p, vb, xs + TG::XPC * XP_LD, xs + (XG + TG::XPC) * XP_LD, lane, gl, row_ok,
-                                         (gns >> 4) + 1, unused);
+                        const int c0 = (gns >> 4) * TG::XPC;
+                        const bool both = 8 * TG::XPC <= 32 && xp_free;          // both sub-tiles were staged before the wait
+                        float* xs = xp + ((both && sub > 0) ? 2 * XG * XP_LD : 0);
+                        if (sub > 0 && !both) {
+                            tx_stage_in<XG>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, xs, lane);
+                            tx_stage_in<XG>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, c0, tx_cn, xs + XG * XP_LD, lane);
                             __syncwarp();
-                            tx_stage_out<XG>(p.tx_gx, p.tx_ldgx, gm0, p.M, p.tx_cols, c0, tx_cn, xs + XG * XP_LD, lane);
-                            __syncwarp();
-                        } else {
-#pragma unroll
-                            for (int c16 = 0; c16 < 2; ++c16) {
-                                const int c0 = ((gns >> 4) + c16) * TG::XPC;
-                                if (sub > 0 || c16 > 0) {
-                                    tx_stage_in<XG>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, xp, lane);
-                                    tx_stage_in<XG>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, c0, tx_cn, xp + XG * XP_LD, lane);
-                                    __syncwarp();
-                                }
-                                tx_chunk<TX>(p, c16 == 0 ? va : vb, xp, xp + XG * XP_LD, lane, gl, row_ok, (gns >> 4) + c16, unused);
-                                __syncwarp();
-                                tx_stage_out<XG>(p.tx_gx, p.tx_ldgx, gm0, p.M, p.tx_cols, c0, tx_cn, xp + XG * XP_LD, lane);
-                                __syncwarp();
-                            }
                         }
-                    }
-                    if constexpr (TX != 0) {
+                        tx_chunk<TX>(p, va, xs, xs + XG * XP_LD, lane, gl, row_ok, gns >> 4, unused);
+                        tx_chunk<TX>(p, vb, xs + TG::XPC * XP_LD, xs + (XG + TG::XPC) * XP_LD, lane, gl, row_ok,
+                                     (gns >> 4) + 1, unused);
+                        __syncwarp();
+                        tx_stage_out<XG>(p.tx_gx, p.tx_ldgx, gm0, p.M, p.tx_cols, c0, tx_cn, xs + XG * XP_LD, lane);
+                        __syncwarp();
                         // bias gradient: column sums of the cotangents by shuffles (rows beyond M and pad columns are zero)
                         if (p.colsum != nullptr) {
                             const float sa = warp_colsum16(va, lane), sb = warp_colsum16(vb, lane);
@@ -671,7 +713,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                     }
                     emit_chunk(2 * sub, va);
                     emit_chunk(2 * sub + 1, vb);
-                    if (p.out_img_t != nullptr || (TX == 0 && p.colsum != nullptr)) {
+                    if (TX == 0 && (p.out_img_t != nullptr || p.colsum != nullptr)) {
                         // lane = column of C = row of the transposed image; its 32 k-values (rows gm0 .. gm0 + 31 of C) are
                         // four 16-byte chunks of consecutive slabs, and consecutive lanes write consecutive chunks
                         __syncwarp();
@@ -708,7 +750,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                         if (TX == 0 && p.colsum != nullptr && n < p.N) atomicAdd(p.colsum + n, cs);
                         if (p.C == nullptr) __syncwarp();
                     }
-                    if (p.C != nullptr) {
+                    if (TX == 0 && p.C != nullptr) {
                         __syncwarp();
                         const bool c0 = gns + lane < p.N;
                         if (c0 && !(p.atomic && empty)) {
@@ -1094,6 +1136,8 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
                             "fused transformer, forward: the product has no output of its own");
         } else {
             TFEPB_CHECK_ARG(tx->grad_y != nullptr && tx->grad_x != nullptr, "fused transformer: null gradient buffer");
+            TFEPB_CHECK_ARG(a->c == nullptr && a->out_image_t == nullptr && a->out_image != nullptr,
+                            "fused transformer, backward: the parameter cotangents leave as out_image (+ column_sums) only");
         }
     }
     TFEPB_CHECK_ARG(a->out_image_t == nullptr || a->out_image_t_rows == 128 || a->out_image_t_rows == 256,
