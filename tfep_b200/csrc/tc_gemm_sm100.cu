@@ -651,25 +651,48 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                         }
                         __syncwarp();
                     }
-                    if constexpr (TX != 0 && TG::GB == 1) {
-                        // ---- fused transformer, backward, one chunk at a time (x and grad_y of a chunk fill the staging buffer):
-                        // accumulator -> parameter cotangents -> bias gradient (shuffles) -> image; ONE copy of the long body ----
-                        constexpr int XG = TG::XPC;
+                    if constexpr (TX != 0) {
+                        // ---- fused transformer, backward, one chunk at a time through ONE copy of the code (the size of the
+                        // epilogue loop decides how much of it the instruction cache holds): accumulator -> parameter cotangents
+                        // (x and grad_y wait in the staging buffer, grad_x leaves through the slots of grad_y) -> bias gradient
+                        // (shuffles) -> image.  Staging: GB == 1 one chunk at a time; GB == 2 a sub-tile at a time, both
+                        // sub-tiles before the accumulator wait where the buffer holds them (8 XPC <= 32) ----
+                        constexpr int XPC = TG::XPC;
+                        constexpr bool BOTH = TG::GB == 2 && 8 * XPC <= 32;
 #pragma unroll 1
                         for (int c16 = 0; c16 < 2; ++c16) {
                             const int q = 2 * sub + c16;
-                            const int c0 = ((gns >> 4) + c16) * TG::XPC;
                             float unused = 0.f;
                             float v[16];
-                            if (q > 0) {
-                                tx_stage_in<XG>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, xp, lane);
-                                tx_stage_in<XG>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, c0, tx_cn, xp + XG * XP_LD, lane);
+                            float *xs, *gs;
+                            if constexpr (TG::GB == 1) {
+                                xs = xp; gs = xp + XPC * XP_LD;
+                                if (q > 0) {
+                                    const int c0 = ((gns >> 4) + c16) * XPC;
+                                    tx_stage_in<XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, xs, lane);
+                                    tx_stage_in<XPC>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, c0, tx_cn, gs, lane);
+                                }
+                            } else {
+                                float* base = xp + ((BOTH && sub > 0) ? 4 * XPC * XP_LD : 0);
+                                if (!BOTH && sub > 0 && c16 == 0) {
+                                    const int c0 = (gns >> 4) * XPC;
+                                    tx_stage_in<2 * XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, base, lane);
+                                    tx_stage_in<2 * XPC>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, c0, tx_cn, base + 2 * XPC * XP_LD, lane);
+                                }
+                                xs = base + c16 * XPC * XP_LD;
+                                gs = xs + 2 * XPC * XP_LD;
                             }
                             load_one(q, v);
                             __syncwarp();
-                            tx_chunk<TX>(p, v, xp, xp + XG * XP_LD, lane, gl, row_ok, (gns >> 4) + c16, unused);
-                            __syncwarp();
-                            tx_stage_out<XG>(p.tx_gx, p.tx_ldgx, gm0, p.M, p.tx_cols, c0, tx_cn, xp + XG * XP_LD, lane);
+                            tx_chunk<TX>(p, v, xs, gs, lane, gl, row_ok, (gns >> 4) + c16, unused);
+                            if (TG::GB == 1 || c16 == 1) {
+                                __syncwarp();
+                                if constexpr (TG::GB == 1)
+                                    tx_stage_out<XPC>(p.tx_gx, p.tx_ldgx, gm0, p.M, p.tx_cols, ((gns >> 4) + c16) * XPC, tx_cn, gs, lane);
+                                else
+                                    tx_stage_out<2 * XPC>(p.tx_gx, p.tx_ldgx, gm0, p.M, p.tx_cols, (gns >> 4) * XPC, tx_cn,
+                                                          gs - XPC * XP_LD, lane);
+                            }
                             if (p.colsum != nullptr) {
                                 const float sa = warp_colsum16(v, lane);
                                 const int n = gns + c16 * 16 + ((lane >> 1) & 15);
@@ -682,35 +705,6 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                     }
                     float va[16], vb[16];
                     load_pair(2 * sub, va, vb);
-                    if constexpr (TX != 0) {
-                        // ---- fused transformer, backward: the chunks become parameter cotangents (x and grad_y staged two chunks
-                        // at a time, grad_x leaves through the slots of grad_y), then they take the usual way out ----
-                        float unused = 0.f;
-                        constexpr int XG = TG::GB * TG::XPC;                                       // x columns per staging group
-                        const int c0 = (gns >> 4) * TG::XPC;
-                        const bool both = 8 * TG::XPC <= 32 && xp_free;          // both sub-tiles were staged before the wait
-                        float* xs = xp + ((both && sub > 0) ? 2 * XG * XP_LD : 0);
-                        if (sub > 0 && !both) {
-                            tx_stage_in<XG>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, xs, lane);
-                            tx_stage_in<XG>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, c0, tx_cn, xs + XG * XP_LD, lane);
-                            __syncwarp();
-                        }
-                        tx_chunk<TX>(p, va, xs, xs + XG * XP_LD, lane, gl, row_ok, gns >> 4, unused);
-                        tx_chunk<TX>(p, vb, xs + TG::XPC * XP_LD, xs + (XG + TG::XPC) * XP_LD, lane, gl, row_ok,
-                                     (gns >> 4) + 1, unused);
-                        __syncwarp();
-                        tx_stage_out<XG>(p.tx_gx, p.tx_ldgx, gm0, p.M, p.tx_cols, c0, tx_cn, xs + XG * XP_LD, lane);
-                        __syncwarp();
-                        // bias gradient: column sums of the cotangents by shuffles (rows beyond M and pad columns are zero)
-                        if (p.colsum != nullptr) {
-                            const float sa = warp_colsum16(va, lane), sb = warp_colsum16(vb, lane);
-                            const int n = gns + ((lane >> 1) & 15);
-                            if ((lane & 1) == 0) {
-                                if (n < p.N) atomicAdd(p.colsum + n, sa);
-                                if (n + 16 < p.N) atomicAdd(p.colsum + n + 16, sb);
-                            }
-                        }
-                    }
                     emit_chunk(2 * sub, va);
                     emit_chunk(2 * sub + 1, vb);
                     if (TX == 0 && (p.out_img_t != nullptr || p.colsum != nullptr)) {
