@@ -127,6 +127,38 @@ __device__ __forceinline__ void tx_stage_in(const float* __restrict__ src, int64
     }
 }
 
+// The same through the asynchronous copy unit (global -> shared without a register round trip; invalid rows / columns are
+// zero-filled): the copies are in flight while the warp waits for the accumulator or reads tensor memory; the caller
+// waits (cp_async_wait_all) and synchronises the warp before the first use.
+template <int XC>
+__device__ __forceinline__ void tx_stage_in_async(const float* __restrict__ src, int64_t ld, int gm0, int M, const int* __restrict__ cols,
+                                                  int c0, int cn, float* buf, int lane) {
+    constexpr int CW = XC <= 4 ? 4 : XC <= 8 ? 8 : XC <= 16 ? 16 : 32;
+    constexpr int RPI = 32 / CW;
+    const int c = lane % CW, r0 = lane / CW;
+    if (c < XC) {
+        const int col = c0 + c < cn ? __ldg(cols + c0 + c) : -1;
+        const uint32_t dst = smem_u32(buf + c * XP_LD + r0);
+        const float* s = src + (int64_t)(gm0 + r0) * ld + (col >= 0 ? col : 0);
+        const int64_t step = (int64_t)RPI * ld;
+        if (col >= 0 && gm0 + 32 <= M) {
+#pragma unroll
+            for (int i = 0; i < CW; ++i, s += step)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (uint32_t)(i * RPI * 4)), "l"(s) : "memory");
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < CW; ++i) {
+                const bool ok = col >= 0 && gm0 + r0 + i * RPI < M;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + (uint32_t)(i * RPI * 4)),
+                             "l"(ok ? s + i * step : src), "r"(ok ? 4 : 0) : "memory");
+            }
+        }
+    }
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_newest() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
 template <int XC>
 __device__ __forceinline__ void tx_stage_out(float* __restrict__ dst, int64_t ld, int gm0, int M, const int* __restrict__ cols,
                                              int c0, int cn, const float* buf, int lane) {
@@ -433,25 +465,43 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             [[maybe_unused]] const int tx_cn = p.tx_units * TG::XPU;            // x columns in the table
             [[maybe_unused]] float gl = 0.f;
             [[maybe_unused]] constexpr bool xp_free = true;   // the VJP variants never use the transposition buffer for anything else
+            // forward: where the buffer holds the x columns of TWO tiles (8 XPC <= 32) the copies run one tile ahead
+            [[maybe_unused]] constexpr bool FWD_AHEAD = TX != 0 && !tx_bwd(TX) && TG::GF == 4 && 8 * TG::XPC <= 32;
+            [[maybe_unused]] float* xs_tile = xp + ((FWD_AHEAD && (tcount & 1)) ? 4 * TG::XPC * XP_LD : 0);
             if constexpr (TX != 0 && !tx_bwd(TX)) {
                 // x of the first sub-tile's two chunks, and of the second one's where the buffer holds both (GF == 4)
-                tx_stage_in<2 * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, (gn_sub0 >> 4) * TG::XPC, tx_cn, xp, lane);
-                if constexpr (TG::GF == 4) {
-                    if (gn_sub1 < p.N)
-                        tx_stage_in<2 * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, (gn_sub1 >> 4) * TG::XPC, tx_cn,
-                                                 xp + 2 * TG::XPC * XP_LD, lane);
+                auto stage_tile = [&](int tt, float* dst) {
+                    const int tm2 = tt / p.tiles_n, tn2 = tt - tm2 * p.tiles_n;
+                    const int g0 = tm2 * BM + (warp & 3) * 32, s0 = tn2 * BN + cgroup * 32, s1 = s0 + 128;
+                    tx_stage_in_async<2 * TG::XPC>(p.tx_x, p.tx_ldx, g0, p.M, p.tx_cols, (s0 >> 4) * TG::XPC, tx_cn, dst, lane);
+                    if constexpr (TG::GF == 4) {
+                        if (s1 < p.N)
+                            tx_stage_in_async<2 * TG::XPC>(p.tx_x, p.tx_ldx, g0, p.M, p.tx_cols, (s1 >> 4) * TG::XPC, tx_cn,
+                                                           dst + 2 * TG::XPC * XP_LD, lane);
+                    }
+                };
+                if (!FWD_AHEAD || tcount == 0) {
+                    stage_tile(t, xs_tile);
+                    cp_async_commit();
+                }
+                if constexpr (FWD_AHEAD) {
+                    // the NEXT tile of this CTA into the other half of the buffer (its previous user, the tile before this
+                    // one, is finished); one commit group per tile, the wait below leaves this newest group pending
+                    const int t2 = t + (int)gridDim.x;
+                    if (t2 < n_tiles) stage_tile(t2, xp + ((tcount & 1) ? 0 : 4 * TG::XPC * XP_LD));
+                    cp_async_commit();
                 }
             } else if constexpr (TX != 0) {
-                tx_stage_in<TG::GB * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, (gn_sub0 >> 4) * TG::XPC, tx_cn, xp, lane);
-                tx_stage_in<TG::GB * TG::XPC>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, (gn_sub0 >> 4) * TG::XPC, tx_cn,
+                tx_stage_in_async<TG::GB * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, (gn_sub0 >> 4) * TG::XPC, tx_cn, xp, lane);
+                tx_stage_in_async<TG::GB * TG::XPC>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, (gn_sub0 >> 4) * TG::XPC, tx_cn,
                                                xp + TG::GB * TG::XPC * XP_LD, lane);
                 if constexpr (TG::GB == 2 && 8 * TG::XPC <= 32) {
                     // the second sub-tile's operands too, when the buffer holds both and nothing else needs it (the column sums
                     // of the VJP variants are reduced with shuffles)
                     if (xp_free && gn_sub1 < p.N) {
-                        tx_stage_in<2 * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, (gn_sub1 >> 4) * TG::XPC, tx_cn,
+                        tx_stage_in_async<2 * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, (gn_sub1 >> 4) * TG::XPC, tx_cn,
                                                  xp + 4 * TG::XPC * XP_LD, lane);
-                        tx_stage_in<2 * TG::XPC>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, (gn_sub1 >> 4) * TG::XPC, tx_cn,
+                        tx_stage_in_async<2 * TG::XPC>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, (gn_sub1 >> 4) * TG::XPC, tx_cn,
                                                  xp + 6 * TG::XPC * XP_LD, lane);
                     }
                 }
@@ -459,6 +509,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             }
             mbar_wait(&sm->acc_full[buf], (tcount >> 1) & 1, p.error, 4);
             tc_fence_after();
+            if constexpr (FWD_AHEAD) cp_async_wait_but_newest();
+            else if constexpr (TX != 0) cp_async_wait_all();   // the staged operands travelled during the wait
             __syncwarp();
             // accumulator chunks q, q + 1 (16 columns each) of this thread's row, bias added
             auto load_pair = [&](int q, float (&va)[16], float (&vb)[16]) {
@@ -604,21 +656,21 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                     const int gns = sub == 0 ? gn_sub0 : gn_sub1;
                     if (gns >= p.N) break;                                                     // warp-uniform
                     const int c0 = (gns >> 4) * TG::XPC;
-                    float* xs = xp + (TG::GF == 4 ? sub * 2 * TG::XPC * XP_LD : 0);
-                    if (TG::GF != 4 && sub > 0) {
-                        tx_stage_in<2 * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, xs, lane);
-                        __syncwarp();
-                    }
+                    float* xs = xs_tile + (TG::GF == 4 ? sub * 2 * TG::XPC * XP_LD : 0);
+                    const bool staged = TG::GF != 4 && sub > 0;
+                    if (staged) tx_stage_in_async<2 * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, xs, lane);
                     if constexpr (TG::KIND == TFEPB_TCTX_MOEBIUS3) {
 #pragma unroll 1
                         for (int c16 = 0; c16 < 2; ++c16) {
                             float v[16];
                             load_one(2 * sub + c16, v);
+                            if (staged && c16 == 0) { cp_async_wait_all(); __syncwarp(); }
                             tx_chunk<TX>(p, v, xs + c16 * TG::XPC * XP_LD, nullptr, lane, 0.f, row_ok, (gns >> 4) + c16, ld_acc);
                         }
                     } else {
                         float va[16], vb[16];
                         load_pair(2 * sub, va, vb);
+                        if (staged) { cp_async_wait_all(); __syncwarp(); }
                         tx_chunk<TX>(p, va, xs, nullptr, lane, 0.f, row_ok, gns >> 4, ld_acc);
                         tx_chunk<TX>(p, vb, xs + TG::XPC * XP_LD, nullptr, lane, 0.f, row_ok, (gns >> 4) + 1, ld_acc);
                     }
@@ -669,20 +721,21 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                                 xs = xp; gs = xp + XPC * XP_LD;
                                 if (q > 0) {
                                     const int c0 = ((gns >> 4) + c16) * XPC;
-                                    tx_stage_in<XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, xs, lane);
-                                    tx_stage_in<XPC>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, c0, tx_cn, gs, lane);
+                                    tx_stage_in_async<XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, xs, lane);
+                                    tx_stage_in_async<XPC>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, c0, tx_cn, gs, lane);
                                 }
                             } else {
                                 float* base = xp + ((BOTH && sub > 0) ? 4 * XPC * XP_LD : 0);
                                 if (!BOTH && sub > 0 && c16 == 0) {
                                     const int c0 = (gns >> 4) * XPC;
-                                    tx_stage_in<2 * XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, base, lane);
-                                    tx_stage_in<2 * XPC>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, c0, tx_cn, base + 2 * XPC * XP_LD, lane);
+                                    tx_stage_in_async<2 * XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, base, lane);
+                                    tx_stage_in_async<2 * XPC>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, c0, tx_cn, base + 2 * XPC * XP_LD, lane);
                                 }
                                 xs = base + c16 * XPC * XP_LD;
                                 gs = xs + 2 * XPC * XP_LD;
                             }
                             load_one(q, v);
+                            cp_async_wait_all();                   // (the copies overlapped the tensor-memory load)
                             __syncwarp();
                             tx_chunk<TX>(p, v, xs, gs, lane, gl, row_ok, (gns >> 4) + c16, unused);
                             if (TG::GB == 1 || c16 == 1) {
