@@ -290,7 +290,9 @@ typedef struct {
                                             (tfepb_tc_pack / out_image write them so).  The product is ADDED to c (fp32 atomics,
                                             zero-fill c first); split_k cuts the reduction in blocks of 128 rows; row_ranges
                                             applies; no bias / activation / images. */
-    int32_t reserved2;
+    int32_t cluster;                     /* != 0: launch as clusters of two CTAs that work on two m-tiles of the same n-tile and share
+                                            the B operand (each fetches half of every B block, multicast to both): -33 % L2 -> SM
+                                            traffic; plain bf16 products without split_k / row_ranges, else ignored */
     const void* aux_image;               /* alternative to aux: the same (m, n) operand h given as its bf16 image (block_rows =
                                             128, k = n; e.g. the out_image a forward product wrote): the result is multiplied
                                             by ELU'(h) of the bf16 values -- no fp32 copy of the activations is needed */

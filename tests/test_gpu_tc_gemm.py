@@ -146,3 +146,17 @@ def test_weight_gradient_from_row_images_mn_major(batch, n_out, n_in, split):
     gw2, _ = _ops.tc_gemm(_ops.tc_pack(gy, 128), himg, n_out, n_in, batch, c=True, split_k=split, mn_major=True)
     ref2 = _bf(gy).T @ _bf(h.float())
     assert float((gw2.double() - ref2).abs().max()) < 3e-4 * (1 + float(ref2.abs().max()))
+
+
+@pytest.mark.parametrize('m,n,k', [(1000, 670, 300), (257, 1500, 670), (129, 40, 70), (128 * 9, 256, 64)])
+def test_cluster_mode_shares_the_b_operand(m, n, k):
+    """Clusters of two CTAs, each fetching half of every B block and multicasting it to both: bit-identical results to the
+    plain launch (same products in the same order), for even and odd numbers of m-tiles (an odd count leaves a ghost half
+    that only keeps the hand-shakes going) and more tiles than clusters."""
+    x, w, b = _rand((m, k), 31), _rand((n, k), 32) / k ** 0.5, _rand((n,), 33)
+    ai, bi = _ops.tc_pack(x, 128), _ops.tc_pack(w, 256)
+    c0, i0 = _ops.tc_gemm(ai, bi, m, n, k, c=True, bias=b, activation=_ops.ACT_ELU, out_image=True, cluster=False)
+    c1, i1 = _ops.tc_gemm(ai, bi, m, n, k, c=True, bias=b, activation=_ops.ACT_ELU, out_image=True, cluster=True)
+    assert torch.equal(c0, c1) and torch.equal(i0, i1)
+    ref = torch.nn.functional.elu(_bf(x) @ _bf(w).T + b.double())
+    assert float((c1.double() - ref).abs().max()) < 2e-4 * (1 + float(ref.abs().max()))

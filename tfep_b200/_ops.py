@@ -460,6 +460,10 @@ def tc_pack_dual(src, t_block_rows=None, column_sums=False, image=True, block_ro
     return img, img_t, sums
 
 
+#: launch the tensor-core products as clusters of two CTAs that share the B operand (tfepb_tc_gemm_args.cluster): a third less
+#: L2 -> SM traffic, same speed on an otherwise idle B200; off by default
+TC_CLUSTER = False
+
 TCTX_KINDS = {'affine': 1, 'sos': 2, 'moebius': 3}
 TCTX_UNITS_PER_CHUNK = {'affine': 8, 'sos': 3, 'moebius': 5}       # units per 16-column chunk (tfepb_tc_tx)
 TCTX_COLUMNS_PER_UNIT = {'affine': 2, 'sos': 5, 'moebius': 3}
@@ -490,7 +494,7 @@ class TcTx:
 
 def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, aux=None, out_image=False,
             k_block_ranges=None, row_ranges=None, split_k=1, error_flag=None, out_image_t=None, column_sums=False, n_split=1,
-            tx=None, aux_image=None, accumulate=False, mn_major=False):
+            tx=None, aux_image=None, accumulate=False, mn_major=False, cluster=None):
     """C = act(A B^T + bias) [* ELU'(aux)] from operand images; returns (c, out_img).  ``c``: True to allocate, a
     tensor to write into (zero-filled by the caller when split_k > 1), None for no fp32 output.
     ``out_image_t`` = 128 / 256: also the image of the transposed result with that block_rows; ``column_sums``: also
@@ -498,7 +502,7 @@ def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, au
     transformer applied by the epilogue (the columns are then parameter chunks, see tfepb_tc_tx).  ``aux_image``: the
     ELU' operand as the bf16 image a forward product wrote (instead of the fp32 ``aux``).  ``accumulate``: ``c`` (a tensor)
     += the result.  ``mn_major``: ``a_img`` / ``b_img`` are the ROW images of a (k x m) and a (k x n) matrix, C = A^T B
-    (the weight gradient straight from the images of grad_y and x)."""
+    (the weight gradient straight from the images of grad_y and x).  ``cluster``: see :data:`TC_CLUSTER`."""
     lib = _lib.load()
     dev = a_img.device
     if c is True:
@@ -529,6 +533,7 @@ def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, au
     if aux_image is not None:
         a.aux_image = aux_image.data_ptr()
     a.mn_major = int(bool(mn_major))
+    a.cluster = int(TC_CLUSTER if cluster is None else bool(cluster))
     with torch.cuda.device(dev):
         check(lib.tfepb_tc_gemm(ctypes.byref(a), stream_ptr(a_img)))
     if out_image_t or column_sums:

@@ -69,6 +69,7 @@ struct Params {
     int atomic;                         // atomicAdd into C (split-K)
     int c_add;                          // C += result (no split-K)
     int mn_major, a_kblocks, b_kblocks; // operands are read MN-major out of row images (weight gradient), their k-block counts
+    int cluster;                        // launched as clusters of two CTAs that share the B operand (multicast)
     int k_chunk_blocks;                 // split-K: k-blocks per blockIdx.y slice, 0 = no split
     int tiles_m, tiles_n;
     int* error;
@@ -326,16 +327,39 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_tiles = p.tiles_m * p.tiles_n;
 
+    // CLUSTER MODE (p.cluster, opt-in): every operand byte is fetched from L2 per CTA (ncu, r02: 11.1 of the 11.8 TB/s the L2
+    // can send on the fused SOS forward product).  Here two CTAs form a cluster that works on two m-tiles of the SAME n-tile
+    // at a time: each fetches its own A block and HALF of the B block (four of the eight k slabs, 16 KB contiguous),
+    // multicast into both CTAs -- 32 KB instead of 48 KB read from L2 per CTA and k-block.  A stage may only be refilled when
+    // both CTAs have consumed it: the MMA commit arrives on the `empty` barrier of both.  Measured: L2 -> SM traffic
+    // 11.1 -> 7.6 TB/s, same run time (0.50 ms) -- the products are bound by the dependent-instruction latency of the
+    // row-per-thread epilogue on 16 warps, not by the operand feed; kept as an option for hosts that share the L2.
+    const bool cl = p.cluster != 0;
+    const uint32_t cl_rank = cl ? cluster_ctarank() : 0u;
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&sm->full[s], 1); mbar_init(&sm->empty[s], cl ? 2 : 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&sm->acc_full[b], 1); mbar_init(&sm->acc_empty[b], EPI_WARPS * 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(&sm->tmem_base, 512);
     tc_fence_before();
     __syncthreads();
+    if (cl) cluster_sync_all();               // the peer's barriers exist before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem = sm->tmem_base;
+    // Tile walk.  Plain: tile t = blockIdx.x, += gridDim.x, (tm, tn) = (t / tiles_n, t % tiles_n).  Cluster mode: the
+    // cluster walks (m-tile PAIR, n-tile) items and this CTA takes m-tile 2 * pair + rank; with an odd number of m-tiles
+    // the last pair has a GHOST half that loads, multiplies and hands over like any other (its peer needs the B half and
+    // the barrier arrivals) but stores nothing.
+    const int t_first = cl ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int t_step = cl ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int t_count = cl ? ((p.tiles_m + 1) >> 1) * p.tiles_n : n_tiles;
+    auto decode = [&](int t, int& tm, int& tn) -> bool {
+        const int q = t / p.tiles_n;
+        tn = t - q * p.tiles_n;
+        tm = cl ? 2 * q + (int)cl_rank : q;
+        return tm >= p.tiles_m;               // ghost
+    };
 
     // k-block range of a tile (staircase range of its n-tile, intersected with this CTA's split-K slice)
     auto skipped = [&](int tm, int tn) -> bool {
@@ -356,15 +380,25 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     if (warp == 0) {
         // =========================== producer ===========================
         uint32_t stage = 0, phase = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+        for (int t = t_first; t < t_count; t += t_step) {
+            int tm, tn;
+            if (decode(t, tm, tn)) tm = p.tiles_m - 1;                  // ghost: any valid A block
             if (skipped(tm, tn)) continue;
             int k0, k1;
             krange(tn, k0, k1);
             for (int kp = k0 * G::PARTS; kp < k1 * G::PARTS; ++kp) {
                 const int kb = kp / G::PARTS, part = kp % G::PARTS;     // a stage = part `part` of k-block kb, all terms
                 mbar_wait(&sm->empty[stage], phase ^ 1, p.error, 1);
-                if (elect_one()) {
+                if (cl) {
+                    if (elect_one()) {
+                        uint8_t* dst = ring + (size_t)stage * STAGE_BYTES;
+                        mbar_expect_tx(&sm->full[stage], STAGE_BYTES);      // own A + both halves of B
+                        bulk_g2s(dst, p.a_img + ((size_t)tm * p.k_blocks + kb) * A_BLOCK, A_BLOCK, &sm->full[stage]);
+                        const size_t half = (size_t)cl_rank * (B_BLOCK / 2);
+                        bulk_g2s_multicast(dst + A_BLOCK + half, p.b_img + ((size_t)tn * p.k_blocks + kb) * B_BLOCK + half, B_BLOCK / 2,
+                                           &sm->full[stage], (uint16_t)3);
+                    }
+                } else if (elect_one()) {
                     uint8_t* dst = ring + (size_t)stage * STAGE_BYTES;
                     mbar_expect_tx(&sm->full[stage], STAGE_BYTES);
                     const uint8_t* a_src = p.a_img + ((size_t)tm * p.k_blocks + kb) * A_BLOCK + (size_t)part * G::A_PART;
@@ -382,11 +416,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
         uint32_t stage = 0, phase = 0, tcount = 0;
-        const uint32_t ring16 = smem_u32(ring) >> 4;
+        // start-address field of the shared-memory descriptors: 14 bits of (address >> 4).  In a cluster launch the shared
+        // window address of a CTA carries its rank in the upper bits; unmasked they spill into the leading-offset field
+        // (first cluster version: every tile of the rank-1 CTAs came out as deterministic garbage).
+        const uint32_t ring16 = (smem_u32(ring) >> 4) & 0x3fffu;
         // kind::f16, A = B = bf16, D = fp32, both K-major, M = 128, N = 256
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+        for (int t = t_first; t < t_count; t += t_step) {
+            int tm, tn;
+            if (decode(t, tm, tn)) tm = p.tiles_m - 1;
             if (skipped(tm, tn)) continue;
             int k0, k1;
             krange(tn, k0, k1);
@@ -418,7 +456,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                             }
                         }
                     }
-                    umma_commit(&sm->empty[stage]);
+                    if (cl) umma_commit_multicast(&sm->empty[stage], (uint16_t)3);
+                    else umma_commit(&sm->empty[stage]);
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -434,12 +473,21 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
         const int row = (warp & 3) * 32 + lane;        // TMEM lane = row of the tile
         const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t tcount = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
-            if (skipped(tm, tn)) continue;
+        for (int t = t_first; t < t_count; t += t_step) {
+            int tm, tn;
+            const bool ghost = decode(t, tm, tn);
+            if (!ghost && skipped(tm, tn)) continue;
             int k0, k1;
             krange(tn, k0, k1);
             const uint32_t buf = tcount & 1;
+            if (ghost) {
+                // cluster mode, odd number of m-tiles: this half of the last pair only keeps the hand-shakes going
+                mbar_wait(&sm->acc_full[buf], (tcount >> 1) & 1, p.error, 4);
+                tc_fence_before();
+                mbar_arrive(&sm->acc_empty[buf]);
+                ++tcount;
+                continue;
+            }
             // Every warp owns 32 rows (its TMEM lane quadrant) x 64 columns = four chunks of 16 columns, processed as two
             // sub-tiles of 32 columns that go through a per-warp transposition buffer: a thread holds one ROW of the
             // accumulator, but global memory wants a warp instruction to cover one row segment (128 contiguous bytes), both
@@ -471,7 +519,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             if constexpr (TX != 0 && !tx_bwd(TX)) {
                 // x of the first sub-tile's two chunks, and of the second one's where the buffer holds both (GF == 4)
                 auto stage_tile = [&](int tt, float* dst) {
-                    const int tm2 = tt / p.tiles_n, tn2 = tt - tm2 * p.tiles_n;
+                    int tm2, tn2;
+                    if (decode(tt, tm2, tn2)) return;
                     const int g0 = tm2 * BM + (warp & 3) * 32, s0 = tn2 * BN + cgroup * 32, s1 = s0 + 128;
                     tx_stage_in_async<2 * TG::XPC>(p.tx_x, p.tx_ldx, g0, p.M, p.tx_cols, (s0 >> 4) * TG::XPC, tx_cn, dst, lane);
                     if constexpr (TG::GF == 4) {
@@ -487,8 +536,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                 if constexpr (FWD_AHEAD) {
                     // the NEXT tile of this CTA into the other half of the buffer (its previous user, the tile before this
                     // one, is finished); one commit group per tile, the wait below leaves this newest group pending
-                    const int t2 = t + (int)gridDim.x;
-                    if (t2 < n_tiles) stage_tile(t2, xp + ((tcount & 1) ? 0 : 4 * TG::XPC * XP_LD));
+                    const int t2 = t + t_step;
+                    if (t2 < t_count) stage_tile(t2, xp + ((tcount & 1) ? 0 : 4 * TG::XPC * XP_LD));
                     cp_async_commit();
                 }
             } else if constexpr (TX != 0) {
@@ -823,6 +872,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
 
     tc_fence_before();
     __syncthreads();
+    if (cl) cluster_sync_all();               // no multicast / remote arrival may find this CTA gone
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
@@ -1280,6 +1330,25 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
     }
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), smem)) return rc;
     const int tiles = p.tiles_m * p.tiles_n;
+    // clusters of two CTAs sharing the B operand (opt-in, a->cluster): plain bf16 products without split-K / row ranges (the
+    // pairs walk the tiles in lock step)
+    p.cluster = (a->cluster != 0 && n_split == 1 && splits == 1 && a->row_ranges == nullptr && p.tiles_m >= 2 && sm_count() >= 2) ? 1 : 0;
+    if (p.cluster) {
+        const int pairs = ((p.tiles_m + 1) / 2) * p.tiles_n;
+        int gx = sm_count() / 2;
+        if (gx > pairs) gx = pairs;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)(2 * gx)); cfg.blockDim = dim3((unsigned)tcg::THREADS);
+        cfg.dynamicSmemBytes = smem; cfg.stream = as_stream(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        void* args[] = {&p};
+        TFEPB_CUDA(cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(kernel), args));
+        return check_launch("tc_gemm_kernel (clusters)");
+    }
     int gx = sm_count() / splits;
     if (gx < 1) gx = 1;
     if (gx > tiles) gx = tiles;
