@@ -50,6 +50,7 @@ constexpr int EPI_WARPS = 16;
 constexpr int XP_LD = 33;                                  // transposition buffer: [32 columns][33] floats per epilogue warp
 constexpr int XP_FLOATS = 32 * XP_LD;
 constexpr int THREADS = 64 + EPI_WARPS * 32;
+constexpr int TX_COLS_SMEM = 2048;                         // fused transformer: x-column table kept in shared memory up to this size
 
 struct Params {
     const uint8_t* a_img; const uint8_t* b_img;
@@ -111,7 +112,7 @@ __device__ __forceinline__ void tx_stage_in(const float* __restrict__ src, int64
     constexpr int RPI = 32 / CW;                                    // rows per warp instruction
     const int c = lane % CW, r0 = lane / CW;
     if (c < XC) {
-        const int col = c0 + c < cn ? __ldg(cols + c0 + c) : -1;
+        const int col = c0 + c < cn ? cols[c0 + c] : -1;
         float* dst = buf + c * XP_LD + r0;
         if (col >= 0 && gm0 + 32 <= M) {                            // all 32 rows exist: no per-row test, running pointer
             const float* s = src + (int64_t)(gm0 + r0) * ld + col;
@@ -138,7 +139,7 @@ __device__ __forceinline__ void tx_stage_in_async(const float* __restrict__ src,
     constexpr int RPI = 32 / CW;
     const int c = lane % CW, r0 = lane / CW;
     if (c < XC) {
-        const int col = c0 + c < cn ? __ldg(cols + c0 + c) : -1;
+        const int col = c0 + c < cn ? cols[c0 + c] : -1;
         const uint32_t dst = smem_u32(buf + c * XP_LD + r0);
         const float* s = src + (int64_t)(gm0 + r0) * ld + (col >= 0 ? col : 0);
         const int64_t step = (int64_t)RPI * ld;
@@ -167,7 +168,7 @@ __device__ __forceinline__ void tx_stage_out(float* __restrict__ dst, int64_t ld
     constexpr int RPI = 32 / CW;
     const int c = lane % CW, r0 = lane / CW;
     if (c < XC && c0 + c < cn) {
-        const int col = __ldg(cols + c0 + c);
+        const int col = cols[c0 + c];
         const float* s = buf + c * XP_LD + r0;
         float* d = dst + (int64_t)(gm0 + r0) * ld + col;
         const int64_t step = (int64_t)RPI * ld;
@@ -323,8 +324,19 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     uint8_t* ring = smem_raw;
     float* xpose = reinterpret_cast<float*>(ring + (size_t)STAGES * STAGE_BYTES);
     float* bias_s = xpose + EPI_WARPS * XP_FLOATS;                 // per epilogue warp: the bias of its 64 columns
-    Smem* sm = reinterpret_cast<Smem*>(bias_s + EPI_WARPS * 64);
+    int* cols_s = reinterpret_cast<int*>(bias_s + EPI_WARPS * 64);  // fused transformer: the x-column table (else empty)
+    Smem* sm = reinterpret_cast<Smem*>(cols_s + (TX != 0 ? TX_COLS_SMEM : 0));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // The column of every unit is looked up before each staging copy: from global memory that lookup was 15-25 % of the
+    // stall samples of the fused epilogues (address -> copy dependency); the table is tiny, keep it in shared memory.
+    [[maybe_unused]] const int* tx_cols = p.tx_cols;
+    if constexpr (TX != 0) {
+        const int n_cols = p.tx_units * TxGeo<TX>::XPU;
+        if (n_cols <= TX_COLS_SMEM) {
+            for (int i = tid; i < n_cols; i += THREADS) cols_s[i] = p.tx_cols[i];
+            tx_cols = cols_s;                 // (visible after the __syncthreads below)
+        }
+    }
     const int n_tiles = p.tiles_m * p.tiles_n;
 
     // CLUSTER MODE (p.cluster, opt-in): every operand byte is fetched from L2 per CTA (ncu, r02: 11.1 of the 11.8 TB/s the L2
@@ -522,10 +534,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                     int tm2, tn2;
                     if (decode(tt, tm2, tn2)) return;
                     const int g0 = tm2 * BM + (warp & 3) * 32, s0 = tn2 * BN + cgroup * 32, s1 = s0 + 128;
-                    tx_stage_in_async<2 * TG::XPC>(p.tx_x, p.tx_ldx, g0, p.M, p.tx_cols, (s0 >> 4) * TG::XPC, tx_cn, dst, lane);
+                    tx_stage_in_async<2 * TG::XPC>(p.tx_x, p.tx_ldx, g0, p.M, tx_cols, (s0 >> 4) * TG::XPC, tx_cn, dst, lane);
                     if constexpr (TG::GF == 4) {
                         if (s1 < p.N)
-                            tx_stage_in_async<2 * TG::XPC>(p.tx_x, p.tx_ldx, g0, p.M, p.tx_cols, (s1 >> 4) * TG::XPC, tx_cn,
+                            tx_stage_in_async<2 * TG::XPC>(p.tx_x, p.tx_ldx, g0, p.M, tx_cols, (s1 >> 4) * TG::XPC, tx_cn,
                                                            dst + 2 * TG::XPC * XP_LD, lane);
                     }
                 };
@@ -541,16 +553,16 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                     cp_async_commit();
                 }
             } else if constexpr (TX != 0) {
-                tx_stage_in_async<TG::GB * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, (gn_sub0 >> 4) * TG::XPC, tx_cn, xp, lane);
-                tx_stage_in_async<TG::GB * TG::XPC>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, (gn_sub0 >> 4) * TG::XPC, tx_cn,
+                tx_stage_in_async<TG::GB * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, tx_cols, (gn_sub0 >> 4) * TG::XPC, tx_cn, xp, lane);
+                tx_stage_in_async<TG::GB * TG::XPC>(p.tx_gy, p.tx_ldgy, gm0, p.M, tx_cols, (gn_sub0 >> 4) * TG::XPC, tx_cn,
                                                xp + TG::GB * TG::XPC * XP_LD, lane);
                 if constexpr (TG::GB == 2 && 8 * TG::XPC <= 32) {
                     // the second sub-tile's operands too, when the buffer holds both and nothing else needs it (the column sums
                     // of the VJP variants are reduced with shuffles)
                     if (xp_free && gn_sub1 < p.N) {
-                        tx_stage_in_async<2 * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, (gn_sub1 >> 4) * TG::XPC, tx_cn,
+                        tx_stage_in_async<2 * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, tx_cols, (gn_sub1 >> 4) * TG::XPC, tx_cn,
                                                  xp + 4 * TG::XPC * XP_LD, lane);
-                        tx_stage_in_async<2 * TG::XPC>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, (gn_sub1 >> 4) * TG::XPC, tx_cn,
+                        tx_stage_in_async<2 * TG::XPC>(p.tx_gy, p.tx_ldgy, gm0, p.M, tx_cols, (gn_sub1 >> 4) * TG::XPC, tx_cn,
                                                  xp + 6 * TG::XPC * XP_LD, lane);
                     }
                 }
@@ -707,7 +719,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                     const int c0 = (gns >> 4) * TG::XPC;
                     float* xs = xs_tile + (TG::GF == 4 ? sub * 2 * TG::XPC * XP_LD : 0);
                     const bool staged = TG::GF != 4 && sub > 0;
-                    if (staged) tx_stage_in_async<2 * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, xs, lane);
+                    if (staged) tx_stage_in_async<2 * TG::XPC>(p.tx_x, p.tx_ldx, gm0, p.M, tx_cols, c0, tx_cn, xs, lane);
                     if constexpr (TG::KIND == TFEPB_TCTX_MOEBIUS3) {
 #pragma unroll 1
                         for (int c16 = 0; c16 < 2; ++c16) {
@@ -724,7 +736,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                         tx_chunk<TX>(p, vb, xs + TG::XPC * XP_LD, nullptr, lane, 0.f, row_ok, (gns >> 4) + 1, ld_acc);
                     }
                     __syncwarp();
-                    tx_stage_out<2 * TG::XPC>(p.tx_y, p.tx_ldy, gm0, p.M, p.tx_cols, c0, tx_cn, xs, lane);
+                    tx_stage_out<2 * TG::XPC>(p.tx_y, p.tx_ldy, gm0, p.M, tx_cols, c0, tx_cn, xs, lane);
                     __syncwarp();
                 }
                 if (row_ok && p.tx_logdet != nullptr) atomicAdd(p.tx_logdet + gm, ld_acc);
@@ -770,15 +782,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                                 xs = xp; gs = xp + XPC * XP_LD;
                                 if (q > 0) {
                                     const int c0 = ((gns >> 4) + c16) * XPC;
-                                    tx_stage_in_async<XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, xs, lane);
-                                    tx_stage_in_async<XPC>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, c0, tx_cn, gs, lane);
+                                    tx_stage_in_async<XPC>(p.tx_x, p.tx_ldx, gm0, p.M, tx_cols, c0, tx_cn, xs, lane);
+                                    tx_stage_in_async<XPC>(p.tx_gy, p.tx_ldgy, gm0, p.M, tx_cols, c0, tx_cn, gs, lane);
                                 }
                             } else {
                                 float* base = xp + ((BOTH && sub > 0) ? 4 * XPC * XP_LD : 0);
                                 if (!BOTH && sub > 0 && c16 == 0) {
                                     const int c0 = (gns >> 4) * XPC;
-                                    tx_stage_in_async<2 * XPC>(p.tx_x, p.tx_ldx, gm0, p.M, p.tx_cols, c0, tx_cn, base, lane);
-                                    tx_stage_in_async<2 * XPC>(p.tx_gy, p.tx_ldgy, gm0, p.M, p.tx_cols, c0, tx_cn, base + 2 * XPC * XP_LD, lane);
+                                    tx_stage_in_async<2 * XPC>(p.tx_x, p.tx_ldx, gm0, p.M, tx_cols, c0, tx_cn, base, lane);
+                                    tx_stage_in_async<2 * XPC>(p.tx_gy, p.tx_ldgy, gm0, p.M, tx_cols, c0, tx_cn, base + 2 * XPC * XP_LD, lane);
                                 }
                                 xs = base + c16 * XPC * XP_LD;
                                 gs = xs + 2 * XPC * XP_LD;
@@ -790,9 +802,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                             if (TG::GB == 1 || c16 == 1) {
                                 __syncwarp();
                                 if constexpr (TG::GB == 1)
-                                    tx_stage_out<XPC>(p.tx_gx, p.tx_ldgx, gm0, p.M, p.tx_cols, ((gns >> 4) + c16) * XPC, tx_cn, gs, lane);
+                                    tx_stage_out<XPC>(p.tx_gx, p.tx_ldgx, gm0, p.M, tx_cols, ((gns >> 4) + c16) * XPC, tx_cn, gs, lane);
                                 else
-                                    tx_stage_out<2 * XPC>(p.tx_gx, p.tx_ldgx, gm0, p.M, p.tx_cols, (gns >> 4) * XPC, tx_cn,
+                                    tx_stage_out<2 * XPC>(p.tx_gx, p.tx_ldgx, gm0, p.M, tx_cols, (gns >> 4) * XPC, tx_cn,
                                                           gs - XPC * XP_LD, lane);
                             }
                             if (p.colsum != nullptr) {
@@ -1318,7 +1330,8 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
     p.out_split_stride = n_split > 1 ? tfepb_tc_image_bytes(a->m, a->n, 128) : 0;
     const int stage_bytes = n_split == 1 ? tcg::Geo<1>::STAGE : n_split == 2 ? tcg::Geo<2>::STAGE : tcg::Geo<3>::STAGE;
     const int stages = n_split == 3 ? tcg::Geo<3>::N_STAGES : tcg::Geo<1>::N_STAGES;
-    const size_t smem = (size_t)stages * stage_bytes + (size_t)tcg::EPI_WARPS * (tcg::XP_FLOATS + 64) * 4 + sizeof(tcg::Smem) + 1024;
+    const size_t smem = (size_t)stages * stage_bytes + (size_t)tcg::EPI_WARPS * (tcg::XP_FLOATS + 64) * 4 +
+                        (tx != nullptr ? (size_t)tcg::TX_COLS_SMEM * 4 : 0) + sizeof(tcg::Smem) + 256;
     using kernel_t = void (*)(const tcg::Params);
     kernel_t kernel = n_split == 1 ? tcg::tc_gemm_kernel<1> : n_split == 2 ? tcg::tc_gemm_kernel<2> : tcg::tc_gemm_kernel<3>;
     if (tx != nullptr) {
