@@ -50,6 +50,7 @@ constexpr int EPI_WARPS = 16;
 constexpr int XP_LD = 33;                                  // transposition buffer: [32 columns][33] floats per epilogue warp
 constexpr int XP_FLOATS = 32 * XP_LD;
 constexpr int THREADS = 64 + EPI_WARPS * 32;
+constexpr int KR_SMEM = 1024;                              // k-block ranges of up to 512 n-tiles kept in shared memory
 constexpr int TX_COLS_SMEM = 2048;                         // fused transformer: x-column table kept in shared memory up to this size
 
 struct Params {
@@ -325,10 +326,16 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     float* xpose = reinterpret_cast<float*>(ring + (size_t)STAGES * STAGE_BYTES);
     float* bias_s = xpose + EPI_WARPS * XP_FLOATS;                 // per epilogue warp: the bias of its 64 columns
     int* cols_s = reinterpret_cast<int*>(bias_s + EPI_WARPS * 64);  // fused transformer: the x-column table (else empty)
-    Smem* sm = reinterpret_cast<Smem*>(cols_s + (TX != 0 ? TX_COLS_SMEM : 0));
+    int* kr_s = cols_s + (TX != 0 ? TX_COLS_SMEM : 0);             // per n-tile [first, end) k-block (looked up by all three roles per tile)
+    Smem* sm = reinterpret_cast<Smem*>(kr_s + KR_SMEM);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // The column of every unit is looked up before each staging copy: from global memory that lookup was 15-25 % of the
     // stall samples of the fused epilogues (address -> copy dependency); the table is tiny, keep it in shared memory.
+    const int* kranges = p.kranges;
+    if (p.kranges != nullptr && 2 * p.tiles_n <= KR_SMEM) {
+        for (int i = threadIdx.x; i < 2 * p.tiles_n; i += THREADS) kr_s[i] = p.kranges[i];
+        kranges = kr_s;
+    }
     [[maybe_unused]] const int* tx_cols = p.tx_cols;
     if constexpr (TX != 0) {
         const int n_cols = p.tx_units * TxGeo<TX>::XPU;
@@ -381,7 +388,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     };
     auto krange = [&](int tn, int& k0, int& k1) {
         k0 = 0; k1 = p.k_blocks;
-        if (p.kranges != nullptr) { k0 = max(0, p.kranges[2 * tn]); k1 = min(p.k_blocks, p.kranges[2 * tn + 1]); }
+        if (kranges != nullptr) { k0 = max(0, kranges[2 * tn]); k1 = min(p.k_blocks, kranges[2 * tn + 1]); }
         if (p.k_chunk_blocks > 0) {
             k0 = max(k0, (int)blockIdx.y * p.k_chunk_blocks);
             k1 = min(k1, ((int)blockIdx.y + 1) * p.k_chunk_blocks);
@@ -1331,7 +1338,7 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
     const int stage_bytes = n_split == 1 ? tcg::Geo<1>::STAGE : n_split == 2 ? tcg::Geo<2>::STAGE : tcg::Geo<3>::STAGE;
     const int stages = n_split == 3 ? tcg::Geo<3>::N_STAGES : tcg::Geo<1>::N_STAGES;
     const size_t smem = (size_t)stages * stage_bytes + (size_t)tcg::EPI_WARPS * (tcg::XP_FLOATS + 64) * 4 +
-                        (tx != nullptr ? (size_t)tcg::TX_COLS_SMEM * 4 : 0) + sizeof(tcg::Smem) + 256;
+                        (tx != nullptr ? (size_t)tcg::TX_COLS_SMEM * 4 : 0) + (size_t)tcg::KR_SMEM * 4 + sizeof(tcg::Smem) + 256;
     using kernel_t = void (*)(const tcg::Params);
     kernel_t kernel = n_split == 1 ? tcg::tc_gemm_kernel<1> : n_split == 2 ? tcg::tc_gemm_kernel<2> : tcg::tc_gemm_kernel<3>;
     if (tx != nullptr) {
