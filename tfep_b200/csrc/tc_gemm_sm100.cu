@@ -523,17 +523,22 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             auto gcol = [&](int q) { return (q < 2 ? gn_sub0 : gn_sub1) + (q & 1) * 16; };     // first column of chunk q (0..3)
             // What does not depend on the accumulator is fetched BEFORE waiting for it: the bias of the warp's columns and,
             // for a fused transformer, the first staging group of x (and grad_y).
+            using TG = TxGeo<TX>;
+            // forward: where the buffer holds the x columns of TWO tiles (8 XPC <= 32) the copies run one tile ahead
+            [[maybe_unused]] constexpr bool FWD_AHEAD = TX != 0 && !tx_bwd(TX) && TG::GF == 4 && 8 * TG::XPC <= 32;
             const bool with_bias = !p.atomic && p.bias != nullptr;
             if (with_bias) {
-                bias_w[lane] = gn_sub0 + lane < p.N ? __ldg(p.bias + gn_sub0 + lane) : 0.f;
-                bias_w[lane + 32] = gn_sub1 + lane < p.N ? __ldg(p.bias + gn_sub1 + lane) : 0.f;
+                // asynchronous copies (zero-filled beyond N): in flight during the accumulator wait, no register round trip
+                const bool ok0 = gn_sub0 + lane < p.N, ok1 = gn_sub1 + lane < p.N;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(bias_w + lane)),
+                             "l"(ok0 ? p.bias + gn_sub0 + lane : p.bias), "r"(ok0 ? 4 : 0) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(bias_w + lane + 32)),
+                             "l"(ok1 ? p.bias + gn_sub1 + lane : p.bias), "r"(ok1 ? 4 : 0) : "memory");
+                if constexpr (FWD_AHEAD) cp_async_commit();   // (a group of its own: the wait below leaves only the NEXT tile's pending)
             }
-            using TG = TxGeo<TX>;
             [[maybe_unused]] const int tx_cn = p.tx_units * TG::XPU;            // x columns in the table
             [[maybe_unused]] float gl = 0.f;
             [[maybe_unused]] constexpr bool xp_free = true;   // the VJP variants never use the transposition buffer for anything else
-            // forward: where the buffer holds the x columns of TWO tiles (8 XPC <= 32) the copies run one tile ahead
-            [[maybe_unused]] constexpr bool FWD_AHEAD = TX != 0 && !tx_bwd(TX) && TG::GF == 4 && 8 * TG::XPC <= 32;
             [[maybe_unused]] float* xs_tile = xp + ((FWD_AHEAD && (tcount & 1)) ? 4 * TG::XPC * XP_LD : 0);
             if constexpr (TX != 0 && !tx_bwd(TX)) {
                 // x of the first sub-tile's two chunks, and of the second one's where the buffer holds both (GF == 4)
@@ -578,7 +583,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             mbar_wait(&sm->acc_full[buf], (tcount >> 1) & 1, p.error, 4);
             tc_fence_after();
             if constexpr (FWD_AHEAD) cp_async_wait_but_newest();
-            else if constexpr (TX != 0) cp_async_wait_all();   // the staged operands travelled during the wait
+            else cp_async_wait_all();                          // bias / staged operands travelled during the wait
             __syncwarp();
             // accumulator chunks q, q + 1 (16 columns each) of this thread's row, bias added
             auto load_pair = [&](int q, float (&va)[16], float (&vb)[16]) {
