@@ -293,6 +293,10 @@ typedef struct {
     int32_t cluster;                     /* != 0: launch as clusters of two CTAs that work on two m-tiles of the same n-tile and share
                                             the B operand (each fetches half of every B block, multicast to both): -33 % L2 -> SM
                                             traffic; plain bf16 products without split_k / row_ranges, else ignored */
+    const int32_t* tile_list;            /* mn_major only: NULL, or device (n_tile_list, 2) = the (128-row tile, 256-column tile) pairs of
+                                            c that the mask leaves non-zero; only those are computed, evenly spread over the CTAs
+                                            (instead of row_ranges, whose skipped tiles leave CTAs idle) */
+    int32_t n_tile_list; int32_t reserved3;
     const void* aux_image;               /* alternative to aux: the same (m, n) operand h given as its bf16 image (block_rows =
                                             128, k = n; e.g. the out_image a forward product wrote): the result is multiplied
                                             by ELU'(h) of the bf16 values -- no fp32 copy of the activations is needed */

@@ -104,7 +104,8 @@ class TcGemmArgs(Structure):
                 ('ldaux', c_int64), ('out_image', c_void_p), ('k_block_ranges', c_void_p), ('split_k', c_int32),
                 ('out_image_t_rows', c_int32), ('error_flag', c_void_p), ('row_ranges', c_void_p),
                 ('out_image_t', c_void_p), ('column_sums', c_void_p), ('n_split', c_int32), ('c_accumulate', c_int32),
-                ('tx', POINTER(TcTx)), ('mn_major', c_int32), ('cluster', c_int32), ('aux_image', c_void_p)]
+                ('tx', POINTER(TcTx)), ('mn_major', c_int32), ('cluster', c_int32), ('tile_list', c_void_p),
+                ('n_tile_list', c_int32), ('reserved3', c_int32), ('aux_image', c_void_p)]
 
 
 class CentroidArgs(Structure):

@@ -494,7 +494,7 @@ class TcTx:
 
 def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, aux=None, out_image=False,
             k_block_ranges=None, row_ranges=None, split_k=1, error_flag=None, out_image_t=None, column_sums=False, n_split=1,
-            tx=None, aux_image=None, accumulate=False, mn_major=False, cluster=None):
+            tx=None, aux_image=None, accumulate=False, mn_major=False, cluster=None, tile_list=None):
     """C = act(A B^T + bias) [* ELU'(aux)] from operand images; returns (c, out_img).  ``c``: True to allocate, a
     tensor to write into (zero-filled by the caller when split_k > 1), None for no fp32 output.
     ``out_image_t`` = 128 / 256: also the image of the transposed result with that block_rows; ``column_sums``: also
@@ -534,6 +534,8 @@ def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, au
         a.aux_image = aux_image.data_ptr()
     a.mn_major = int(bool(mn_major))
     a.cluster = int(TC_CLUSTER if cluster is None else bool(cluster))
+    if tile_list is not None:
+        a.tile_list, a.n_tile_list = tile_list.data_ptr(), tile_list.shape[0]
     with torch.cuda.device(dev):
         check(lib.tfepb_tc_gemm(ctypes.byref(a), stream_ptr(a_img)))
     if out_image_t or column_sums:
@@ -599,11 +601,20 @@ class MadeFunctionTC(torch.autograd.Function):
         return (gx, None, None, None, None, *gws, *gbs)
 
 
-def _weight_gradient_split(n, k, batch, n_sm, block=128):
+class WgTiles:
+    """The (128-row, 256-column) tiles of a weight gradient that its mask leaves non-zero: int32 device tensor (n, 2)."""
+
+    def __init__(self, tiles):
+        self.tiles, self.n = tiles, int(tiles.shape[0])
+
+
+def _weight_gradient_split(n, k, batch, n_sm, block=128, tiles=None):
     """Split of the batch reduction of dW[n x k]: the kernel runs n_sm // split CTAs per slice, each walking
     ceil(tiles / (n_sm // split)) tiles over batch / split samples -- pick the split with the shortest critical path (a split
     that leaves a partial last round of tiles wastes up to half the machine: 39 tiles on 18 CTAs = 3 rounds for 2.2)."""
-    tiles = ((n + 127) // 128) * ((k + 255) // 256)
+    if tiles is None:
+        tiles = ((n + 127) // 128) * ((k + 255) // 256)
+    tiles = max(tiles, 1)
     k_blocks = (batch + block - 1) // block          # reduction blocks (128 image rows per ring stage)
     best, best_cost = 1, None
     for split in range(1, min(k_blocks, n_sm) + 1):
@@ -640,9 +651,14 @@ def _made_tc_backward_layers(B, imgs, ws, kb_bwd, rr_w, need_w, need_x, gimg, gb
         N, K = ws[l].shape
         if need_w[l]:
             # dW[N x K] = dY^T X: reduction over the batch, split so that the grid fills the machine
-            split = _weight_gradient_split(N, K, B, n_sm)
-            gws[l], _ = tc_gemm(gimg, imgs[l], N, K, B, c=True, split_k=split, row_ranges=None if rr_w is None else rr_w[l],
-                                mn_major=True)
+            rr = None if rr_w is None else rr_w[l]
+            if isinstance(rr, WgTiles):
+                # only the tiles the mask leaves non-zero, as a list: every CTA carries the same number of real tiles
+                split = _weight_gradient_split(N, K, B, n_sm, tiles=rr.n)
+                gws[l], _ = tc_gemm(gimg, imgs[l], N, K, B, c=True, split_k=split, mn_major=True, tile_list=rr.tiles)
+            else:
+                split = _weight_gradient_split(N, K, B, n_sm)
+                gws[l], _ = tc_gemm(gimg, imgs[l], N, K, B, c=True, split_k=split, row_ranges=rr, mn_major=True)
             gbs[l] = gb
         gb = None
         if l > 0 or need_x:

@@ -97,15 +97,19 @@ class MadePlan:
             r = _ranges(m, 256, axis=0)                    # per 256-row tile: bounding column range
             kb = torch.stack([r[:, 0] // 64, (r[:, 1] + 63) // 64], dim=1).to(torch.int32)
             out.append(kb.contiguous().to(device))
-        # weight gradient (rows = outputs, tiles of 256 input columns): rows the mask leaves non-zero per tile
-        out.append(_ranges(mask, 256, axis=1).contiguous().to(device))
+        # weight gradient: the (128-output-row, 256-input-column) tiles the mask leaves non-zero, as a list
+        from ._ops import WgTiles
+        n_out, n_in = mask.shape
+        tiles = [(tm, tn) for tm in range((n_out + 127) // 128) for tn in range((n_in + 255) // 256)
+                 if bool(mask[tm * 128:(tm + 1) * 128, tn * 256:(tn + 1) * 256].any())]
+        out.append(WgTiles(torch.tensor(tiles, dtype=torch.int32).reshape(-1, 2).contiguous().to(device)))
         return tuple(out)
 
     def tc_ranges(self, device):
         """Per layer, for the tensor-core GEMM (tiles of 256 output columns, k-blocks of 64): the non-zero k-block
         range [first, end) of every tile, forward (tiles over the layer's outputs, k over its inputs) and backward
         input (tiles over the inputs, k over the outputs), and for the weight gradient the row range of every tile of 256
-        input columns.  Lists of int32 (tiles, 2) device tensors."""
+        input columns (as ``_ops.WgTiles``: the list of non-zero tiles).  Lists of int32 (tiles, 2) device tensors."""
         key = ('tc', str(device))
         if key not in self._device_cache:
             fwd, bwd, roww = [], [], []

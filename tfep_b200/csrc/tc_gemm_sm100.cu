@@ -72,6 +72,7 @@ struct Params {
     int c_add;                          // C += result (no split-K)
     int mn_major, a_kblocks, b_kblocks; // operands are read MN-major out of row images (weight gradient), their k-block counts
     int cluster;                        // launched as clusters of two CTAs that share the B operand (multicast)
+    const int* tile_list; int n_list;   // weight gradient: the (tm, tn) tiles the mask leaves non-zero, or null
     int k_chunk_blocks;                 // split-K: k-blocks per blockIdx.y slice, 0 = no split
     int tiles_m, tiles_n;
     int* error;
@@ -922,7 +923,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(const __grid_const
     uint8_t* ring = smem_raw;
     Smem* sm = reinterpret_cast<Smem*>(ring + (size_t)WG_STAGES * WG_STAGE);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_tiles = p.tiles_m * p.tiles_n;
+    const int n_tiles = p.tile_list != nullptr ? p.n_list : p.tiles_m * p.tiles_n;
     const int row_blocks = (p.K + 127) / 128;             // reduction blocks of 128 image rows
 
     if (warp == 1 && lane == 0) {
@@ -936,8 +937,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(const __grid_const
     tc_fence_after();
     const uint32_t tmem = sm->tmem_base;
 
+    // tile t: from the compact list of tiles the mask leaves non-zero (all CTAs then carry the same number of real tiles), or
+    // the full grid with the row-range test
+    auto tile_of = [&](int t, int& tm, int& tn) {
+        if (p.tile_list != nullptr) { tm = p.tile_list[2 * t]; tn = p.tile_list[2 * t + 1]; }
+        else { tm = t / p.tiles_n; tn = t - tm * p.tiles_n; }
+    };
     auto skipped = [&](int tm, int tn) -> bool {
-        if (p.row_ranges == nullptr) return false;
+        if (p.row_ranges == nullptr || p.tile_list != nullptr) return false;
         const int rb = p.row_ranges[2 * tn], re = p.row_ranges[2 * tn + 1];
         return tm * BM + BM <= rb || tm * BM >= re;
     };
@@ -952,7 +959,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(const __grid_const
     if (warp == 0) {
         uint32_t stage = 0, phase = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+            int tm, tn;
+            tile_of(t, tm, tn);
             if (skipped(tm, tn)) continue;
             // slabs of the tile that exist in the images (the rest of the stage keeps stale bytes: they only feed rows /
             // columns of C beyond m / n, which are never stored)
@@ -978,7 +986,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(const __grid_const
                                ((uint32_t)(BM >> 4) << 24);
         constexpr uint32_t HI_MN = (2048u >> 4) | (1u << 14);            // stride offset 2 KB, descriptor version 1
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+            int tm, tn;
+            tile_of(t, tm, tn);
             if (skipped(tm, tn)) continue;
             const uint32_t buf = tcount & 1;
             mbar_wait(&sm->acc_empty[buf], ((tcount >> 1) & 1) ^ 1, p.error, 2);
@@ -1016,7 +1025,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(const __grid_const
         const bool vec = (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (p.ldc & 3) == 0;
         uint32_t tcount = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+            int tm, tn;
+            tile_of(t, tm, tn);
             if (skipped(tm, tn)) continue;
             const uint32_t buf = tcount & 1;
             mbar_wait(&sm->acc_full[buf], (tcount >> 1) & 1, p.error, 4);
@@ -1280,6 +1290,7 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
                                      a->bias == nullptr && a->aux == nullptr && a->aux_image == nullptr &&
                                      a->activation == TFEPB_ACT_NONE),
                     "mn_major: the raw product of two row images is ADDED to c (zero-filled by the caller), nothing else");
+    TFEPB_CHECK_ARG(a->tile_list == nullptr || (a->mn_major && a->n_tile_list >= 0), "tile_list goes with mn_major");
     TFEPB_CHECK_ARG(!a->c_accumulate || (a->aux == nullptr && a->tx == nullptr),
                     "c_accumulate shares the staging buffer of aux and of the fused transformer (use aux_image)");
     if (int rc = require_sm100()) return rc;
@@ -1324,7 +1335,9 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
         p.atomic = 1;
         const size_t wg_smem = (size_t)tcg::WG_STAGES * tcg::WG_STAGE + sizeof(tcg::Smem) + 256;
         if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(tcg::tc_wgrad_kernel), wg_smem)) return rc;
-        const int wg_tiles = p.tiles_m * p.tiles_n;
+        p.tile_list = a->tile_list; p.n_list = a->n_tile_list;
+        const int wg_tiles = a->tile_list != nullptr ? a->n_tile_list : p.tiles_m * p.tiles_n;
+        if (wg_tiles == 0) return 0;                         // everything masked: c stays as it is
         int wgx = sm_count() / sp;
         if (wgx < 1) wgx = 1;
         if (wgx > wg_tiles) wgx = wg_tiles;
