@@ -98,8 +98,7 @@ template <int TX> struct TxGeo {
     static constexpr int PPU = KIND == TFEPB_TCTX_AFFINE ? 2 : KIND == TFEPB_TCTX_SOS2 ? 5 : 3;     // parameter columns per unit
     static constexpr int XPU = KIND == TFEPB_TCTX_MOEBIUS3 ? 3 : 1;                                // x columns per unit
     static constexpr int XPC = UPC * XPU;                                                          // x columns per chunk
-    // chunks per staging group of the transposition buffer (32 columns): forward x only, backward x and grad_y (and the
-    // buffer is needed again for the transposed image after every sub-tile of two chunks)
+    // chunks per staging group of the transposition buffer (32 columns): forward x only, backward x and grad_y
     static constexpr int GF = 4 * XPC <= 32 ? 4 : 2;
     static constexpr int GB = 4 * XPC <= 32 ? 2 : 1;
 };
@@ -107,33 +106,9 @@ template <int TX> struct TxGeo {
 // The epilogue thread owns one ROW (sample) but row-major x / y want a warp instruction to cover a row segment: the
 // columns cols[c0 .. c0 + XC) of the warp's 32 rows travel through buf[column][row] (pitch XP_LD).  A warp instruction
 // covers 32 / CW rows x CW columns (CW = XC rounded up to a power of two).
-template <int XC>
-__device__ __forceinline__ void tx_stage_in(const float* __restrict__ src, int64_t ld, int gm0, int M, const int* __restrict__ cols,
-                                            int c0, int cn, float* buf, int lane) {
-    constexpr int CW = XC <= 4 ? 4 : XC <= 8 ? 8 : XC <= 16 ? 16 : 32;
-    constexpr int RPI = 32 / CW;                                    // rows per warp instruction
-    const int c = lane % CW, r0 = lane / CW;
-    if (c < XC) {
-        const int col = c0 + c < cn ? cols[c0 + c] : -1;
-        float* dst = buf + c * XP_LD + r0;
-        if (col >= 0 && gm0 + 32 <= M) {                            // all 32 rows exist: no per-row test, running pointer
-            const float* s = src + (int64_t)(gm0 + r0) * ld + col;
-            const int64_t step = (int64_t)RPI * ld;
-#pragma unroll
-            for (int i = 0; i < CW; ++i, s += step) dst[i * RPI] = __ldg(s);
-        } else {
-#pragma unroll
-            for (int i = 0; i < CW; ++i) {
-                const int r = r0 + i * RPI;
-                dst[i * RPI] = (col >= 0 && gm0 + r < M) ? __ldg(src + (int64_t)(gm0 + r) * ld + col) : 0.f;
-            }
-        }
-    }
-}
-
-// The same through the asynchronous copy unit (global -> shared without a register round trip; invalid rows / columns are
+// In: through the asynchronous copy unit (global -> shared without a register round trip; invalid rows / columns are
 // zero-filled): the copies are in flight while the warp waits for the accumulator or reads tensor memory; the caller
-// waits (cp_async_wait_all) and synchronises the warp before the first use.
+// waits (cp_async_wait_all) and synchronises the warp before the first use.  Out: plain loads / stores.
 template <int XC>
 __device__ __forceinline__ void tx_stage_in_async(const float* __restrict__ src, int64_t ld, int gm0, int M, const int* __restrict__ cols,
                                                   int c0, int cn, float* buf, int lane) {
