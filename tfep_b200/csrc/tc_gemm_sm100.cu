@@ -3,22 +3,27 @@
 //     forward         Y  = act(X W^T + b)
 //     backward input  dX = (dY W) * ELU'(H_prev)
 //     backward weight dW += dY^T X
-// are all C[M x N] = A[M x K] . B[N x K]^T with both operands K-major, so ONE kernel serves them; what differs is
-// how the operand IMAGES are produced (tfepb_tc_pack: fp32 row-major matrix, optionally transposed, -> bf16 blocks
-// that are exact images of the shared-memory operand layout, so a block moves with one bulk copy).
+// The first two are C[M x N] = A[M x K] . B[N x K]^T with both operands K-major (tc_gemm_kernel); the weight gradient reduces
+// over the batch and reads the SAME row images MN-major (tc_wgrad_kernel, further down), so every activation and every
+// cotangent exists as ONE bf16 image.  Operand IMAGES (tfepb_tc_pack, or the epilogue of the producing product): bf16 blocks
+// that are exact images of the shared-memory operand layout, so a block moves with one bulk copy.
 //
 // Image of an operand with R rows and K reduction elements, blocked (BR rows x 64 k), BR = 128 (A) or 256 (B):
 //     block (rb, kb) at byte offset (rb * ceil(K / 64) + kb) * BR * 128;
 //     inside a block: for each slab s of 8 k-values (8 slabs): BR rows x 16 bytes (K-major core matrices, no swizzle).
 //
 // Kernel: persistent CTAs walk the (m-tile of 128 rows, n-tile of 256 columns) output tiles, n fastest (the A rows
-// of an m-tile stay in L2 across its n-tiles).  Warp 0 streams (A block, B block) stages of 48 KB through a 4-deep
+// of an m-tile stay in L2 across its n-tiles).  Warp 0 streams (A block, B block) stages of 48 KB through a 3-deep
 // mbarrier ring with bulk copies; warp 1 issues tcgen05.mma (M = 128, N = 256, K = 16, both operands from shared
-// memory) into one of TWO 256-column accumulators in tensor memory; warps 2-9 drain the other accumulator:
-// bias, ELU or ELU' multiplier, fp32 store, and optionally the bf16 image of the result, which is the A operand of
-// the next layer (written coalesced: consecutive rows are consecutive 16-byte chunks of a slab).  A per-n-tile range
-// of k-blocks skips the all-zero part of a degree-sorted (staircase) masked weight; split-K with fp32 atomics serves
-// the weight gradient, whose reduction runs over the batch.
+// memory) into one of TWO 256-column accumulators in tensor memory; warps 2-17 (four TMEM lane quadrants x four column
+// groups; a warp's two 32-column sub-tiles are interleaved over the tile) drain the other accumulator: bias, ELU or ELU'
+// multiplier (read from the fp32 activations or from their bf16 image), fp32 store through a per-warp transposition buffer,
+// and optionally the bf16 image of the result = the A operand of the next layer (written coalesced: consecutive rows are
+// consecutive 16-byte chunks of a slab), the image of the transposed result, the column sums.  What does not depend on the
+// accumulator (bias, staged operands of a fused transformer) travels by cp.async during the accumulator wait; per-tile
+// tables (k-block ranges, column table) live in shared memory.  A per-n-tile range of k-blocks skips the all-zero part of a
+// degree-sorted (staircase) masked weight; split-K with fp32 atomics serves K-major weight gradients.  Opt-in cluster mode:
+// two CTAs share the B operand by multicast (see the kernel).
 //
 // SPLIT PRECISION (n_split = 2 or 3; the fp32-class conditioner on the tensor cores): every operand is
 // stored as n_split bf16 images x = x_0 + x_1 (+ x_2) with x_0 = bf16(x), x_1 = bf16(x - x_0), x_2 = bf16(x - x_0 - x_1)
@@ -32,8 +37,9 @@
 // caller pads the packed weight rows accordingly), so the 16 accumulator values an epilogue thread reads are complete
 // parameter sets of its sample.  Forward: the thread applies the transformer to its row of x, writes y and adds the
 // log-det -- the (batch x parameters) matrix never exists in memory.  Backward: the same product is recomputed and the
-// epilogue replaces the parameters by their cotangents (tx_math.cuh VJPs) before the usual image / transposed image /
-// column-sum outputs, i.e. it emits grad_parameters directly as the bf16 operands of the two products below it.
+// epilogue replaces the parameters by their cotangents (tx_math.cuh VJPs), one chunk at a time, before writing them as
+// the bf16 row image (+ column sums by warp shuffles), i.e. it emits grad_parameters directly as the operand of the two
+// products below it.  These variants are compiled without the code paths they never take (instruction-cache footprint).
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "tx_math.cuh"
