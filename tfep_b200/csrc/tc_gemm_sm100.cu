@@ -749,14 +749,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                         __syncwarp();
                     }
                     if (TX == 0 && p.c_add) {
-                        // C += result: the old values come in like the ELU' operand (requested before the accumulator is read;
-                        // all 32 loads of the lane in flight together)
+                        // C += result: the old values come in through the transposition buffer (asynchronous copies, all 32 of the
+                        // lane in flight while the accumulator is read; waited for right before the chunks are emitted)
 #pragma unroll
                         for (int r = 0; r < 32; ++r) {
                             const int grow = gm0 + r;
-                            xp[lane * XP_LD + r] = (grow < p.M && gns + lane < p.N) ? p.C[(int64_t)grow * p.ldc + gns + lane] : 0.f;
+                            const bool ok = grow < p.M && gns + lane < p.N;
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(xp + lane * XP_LD + r)),
+                                         "l"(ok ? p.C + (int64_t)grow * p.ldc + gns + lane : p.C), "r"(ok ? 4 : 0) : "memory");
                         }
-                        __syncwarp();
                     }
                     if constexpr (TX != 0) {
                         // ---- fused transformer, backward, one chunk at a time through ONE copy of the code (the size of the
@@ -813,6 +814,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                     }
                     float va[16], vb[16];
                     load_pair(2 * sub, va, vb);
+                    if (TX == 0 && p.c_add) { cp_async_wait_all(); __syncwarp(); }
                     emit_chunk(2 * sub, va);
                     emit_chunk(2 * sub + 1, vb);
                     if (TX == 0 && (p.out_img_t != nullptr || p.colsum != nullptr)) {
