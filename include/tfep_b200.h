@@ -240,6 +240,8 @@ int tfepb_tc_pack_dual(const float* src, int64_t ld, int32_t rows, int32_t cols,
 #define TFEPB_TCTX_AFFINE 1
 #define TFEPB_TCTX_SOS2 2
 #define TFEPB_TCTX_MOEBIUS3 3
+#define TFEPB_TCTX_SPLINE8 4             /* neural spline with 8 bins (spline.py:184-241; circular or not, identity boundary slopes,
+                                            learnable bounds): one feature per 32 columns = its 23..27 parameters + padding */
 typedef struct {
     int32_t kind;                        /* TFEPB_TCTX_* */
     int32_t backward;
@@ -253,6 +255,11 @@ typedef struct {
     const void* grad_y; int64_t ldgy;    /* backward */
     const float* grad_logdet;            /* backward, or NULL (ignored by SOS: sos.py:233) */
     void* grad_x; int64_t ldgx;          /* backward */
+    /* TFEPB_TCTX_SPLINE8 only: domain [x0, xf] -> [y0, yf] of every unit (fp32, n_units each, unit order) and the options */
+    const float* spline_x0; const float* spline_xf; const float* spline_y0; const float* spline_yf;
+    int32_t spline_flags;                /* bit 0 circular, 1 identity_boundary_slopes, 2 learn_lower_bound, 3 learn_upper_bound */
+    float spline_min_bin_size, spline_min_slope;
+    int32_t reserved;
 } tfepb_tc_tx;
 
 typedef struct {

@@ -1,5 +1,5 @@
 """Transformer fused into the output-layer product of the tensor-core conditioner (tfepb_tc_tx; precision='bf16' for
-affine / SOS / Moebius flows, forward and backward).
+affine / SOS / Moebius / neural-spline flows, forward and backward).
 
 The fused and the separate paths run the SAME products on the same bf16 operand images with fp32 accumulation, and the
 epilogue calls the same device math as the transformer kernels, so they must agree to summation order (the log-det is
@@ -19,8 +19,15 @@ DEV = 'cuda:0'
 def _flow(kind, n_features, order, hidden=2, seed=0):
     from tfep_b200.nn.conditioners.made import generate_degrees
     from tfep_b200.nn.flows import MAF
-    from tfep_b200.nn.transformers import AffineTransformer, MoebiusTransformer, SOSPolynomialTransformer
+    from tfep_b200.nn.transformers import AffineTransformer, MoebiusTransformer, NeuralSplineTransformer, SOSPolynomialTransformer
     torch.manual_seed(seed)
+    if kind.startswith('spline'):
+        lo, hi = -torch.ones(n_features) * 2.0, torch.ones(n_features) * 2.5
+        opts = {'spline': dict(circular=True), 'spline_open': dict(), 'spline_id': dict(identity_boundary_slopes=True),
+                'spline_learn': dict(learn_lower_bound=True, learn_upper_bound=True),
+                'spline_circ_id': dict(circular=True, identity_boundary_slopes=True)}[kind]
+        return MAF(generate_degrees(n_features, order=order), NeuralSplineTransformer(lo, hi, 8, **opts), hidden_layers=hidden,
+                   initialize_identity=False).to(DEV)
     if kind == 'affine':
         return MAF(generate_degrees(n_features, order=order), AffineTransformer(), hidden_layers=hidden,
                    initialize_identity=False).to(DEV)
@@ -58,7 +65,9 @@ def _rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-20))
 
 
-CASES = [('affine', 37, 'ascending', 300), ('affine', 64, 'descending', 128), ('sos', 40, 'ascending', 300),
+CASES = [('spline', 23, 'ascending', 300), ('spline_open', 9, 'descending', 200), ('spline_id', 12, 'ascending', 129),
+         ('spline_learn', 10, 'descending', 260), ('spline_circ_id', 8, 'ascending', 64), ('spline', 66, 'ascending', 1000),
+         ('affine', 37, 'ascending', 300), ('affine', 64, 'descending', 128), ('sos', 40, 'ascending', 300),
          ('sos', 9, 'descending', 77), ('sos', 300, 'ascending', 1000), ('moebius', 36, 'ascending', 300),
          ('moebius', 33, 'descending', 513), ('moebius_unit', 30, 'ascending', 200), ('moebius', 300, 'descending', 700)]
 
@@ -74,9 +83,12 @@ def test_fused_epilogue_matches_the_separate_kernels(kind, n_features, order, ba
     y1, ld1, gx1, gp1 = _run(maf, x, cy, cl, 'bf16', fuse=True)
     assert _rel(y1, y0) < 1e-5 and float((ld1 - ld0).abs().max()) < 1e-4 * (1 + float(ld0.abs().max()))
     # gradients: the cotangent of the parameters reaches the products below as the same bf16 image in both paths
-    assert _rel(gx1, gx0) < 1e-4, _rel(gx1, gx0)
+    # (the spline VJP has long cancellation-prone expressions: its fast-math evaluation in the epilogue differs from the exact
+    # kernel by ~1e-6 relative per cotangent, which flips bf16 roundings of the operand image)
+    tol = 1e-3 if kind.startswith('spline') else 1e-4
+    assert _rel(gx1, gx0) < tol, _rel(gx1, gx0)
     for k in gp0:
-        assert _rel(gp1[k], gp0[k]) < 1e-4, (k, _rel(gp1[k], gp0[k]))
+        assert _rel(gp1[k], gp0[k]) < tol, (k, _rel(gp1[k], gp0[k]))
     # and against the exact path: bf16 operand rounding
     y32, ld32, gx32, gp32 = _run(maf, x, cy, cl, 'fp32', fuse=False)
     # (the log-det is a sum over the features: the tolerance scales with its size)

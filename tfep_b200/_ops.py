@@ -464,7 +464,7 @@ def tc_pack_dual(src, t_block_rows=None, column_sums=False, image=True, block_ro
 #: L2 -> SM traffic, same speed on an otherwise idle B200; off by default
 TC_CLUSTER = False
 
-TCTX_KINDS = {'affine': 1, 'sos': 2, 'moebius': 3}
+TCTX_KINDS = {'affine': 1, 'sos': 2, 'moebius': 3, 'spline': 4}
 TCTX_UNITS_PER_CHUNK = {'affine': 8, 'sos': 3, 'moebius': 5}       # units per 16-column chunk (tfepb_tc_tx)
 TCTX_COLUMNS_PER_UNIT = {'affine': 2, 'sos': 5, 'moebius': 3}
 
@@ -475,8 +475,10 @@ class TcTx:
     ``grad_y``, ``grad_logdet`` (or None), ``grad_x``."""
 
     def __init__(self, kind, cols, x, *, y=None, logdet=None, grad_y=None, grad_logdet=None, grad_x=None,
-                 max_radius=0.0, unit_sphere=0):
+                 max_radius=0.0, unit_sphere=0, spline=None):
         self.kind, self.cols, self.x = kind, cols, x
+        #: kind 'spline': dict(x0, xf, y0, yf (float32 device tensors in unit order), flags, min_bin_size, min_slope)
+        self.spline = spline
         self.y, self.logdet, self.grad_y, self.grad_logdet, self.grad_x = y, logdet, grad_y, grad_logdet, grad_x
         self.max_radius, self.unit_sphere = float(max_radius), int(unit_sphere)
         self.backward = grad_x is not None
@@ -485,11 +487,17 @@ class TcTx:
         xcols = 3 if self.kind == 'moebius' else 1
         opt = lambda t: None if t is None else t.data_ptr()
         ld = lambda t: 0 if t is None else _ld(t)
-        return _lib.TcTx(kind=TCTX_KINDS[self.kind], backward=int(self.backward), n_units=self.cols.numel() // xcols,
-                         unit_sphere=self.unit_sphere, max_radius=self.max_radius, cols=self.cols.data_ptr(),
-                         x=self.x.data_ptr(), ldx=_ld(self.x), y=opt(self.y), ldy=ld(self.y), logdet=opt(self.logdet),
-                         grad_y=opt(self.grad_y), ldgy=ld(self.grad_y), grad_logdet=opt(self.grad_logdet),
-                         grad_x=opt(self.grad_x), ldgx=ld(self.grad_x))
+        st = _lib.TcTx(kind=TCTX_KINDS[self.kind], backward=int(self.backward), n_units=self.cols.numel() // xcols,
+                       unit_sphere=self.unit_sphere, max_radius=self.max_radius, cols=self.cols.data_ptr(),
+                       x=self.x.data_ptr(), ldx=_ld(self.x), y=opt(self.y), ldy=ld(self.y), logdet=opt(self.logdet),
+                       grad_y=opt(self.grad_y), ldgy=ld(self.grad_y), grad_logdet=opt(self.grad_logdet),
+                       grad_x=opt(self.grad_x), ldgx=ld(self.grad_x))
+        if self.spline is not None:
+            sp = self.spline
+            st.spline_x0, st.spline_xf = sp['x0'].data_ptr(), sp['xf'].data_ptr()
+            st.spline_y0, st.spline_yf = sp['y0'].data_ptr(), sp['yf'].data_ptr()
+            st.spline_flags, st.spline_min_bin_size, st.spline_min_slope = sp['flags'], sp['min_bin_size'], sp['min_slope']
+        return st
 
 
 def tc_gemm(a_img, b_img, m, n, k, *, c=None, bias=None, activation=ACT_NONE, aux=None, out_image=False,
@@ -706,7 +714,7 @@ class MadeTxFunctionTC(torch.autograd.Function):
         wts.append(wt)
         tc_gemm(img, wimg, B, N, K, bias=bs[-1], k_block_ranges=None if kb_fwd is None else kb_fwd[-1],
                 tx=TcTx(spec['kind'], spec['cols'], x, y=y, logdet=logdet, max_radius=spec['max_radius'],
-                        unit_sphere=spec['unit_sphere']))
+                        unit_sphere=spec['unit_sphere'], spline=spec.get('spline')))
         ctx.save_for_backward(x, *(imgs if keep else []), *ws, bs[-1], *([wimg] if keep else []))
         ctx.wts = wts if keep else None
         ctx.meta = (L, kb_fwd, kb_bwd, rr_w, spec)
@@ -729,7 +737,8 @@ class MadeTxFunctionTC(torch.autograd.Function):
         _, gimg, _, gb = tc_gemm(imgs[-1], w_last_img, B, N, K, bias=b_last, out_image=True, column_sums=True,
                                  k_block_ranges=None if kb_fwd is None else kb_fwd[-1],
                                  tx=TcTx(spec['kind'], spec['cols'], x, grad_y=grad_y, grad_logdet=grad_ld, grad_x=gx,
-                                         max_radius=spec['max_radius'], unit_sphere=spec['unit_sphere']))
+                                         max_radius=spec['max_radius'], unit_sphere=spec['unit_sphere'],
+                                         spline=spec.get('spline')))
         _, gws, gbs = _made_tc_backward_layers(B, imgs, ws, kb_bwd, rr_w, need_w, ctx.needs_input_grad[0], gimg, gb, gx_into=gx,
                                                wts=ctx.wts)
         ctx.wts = None

@@ -92,7 +92,23 @@ struct Params {
     const float* tx_gy; int64_t tx_ldgy;
     const float* tx_gl;
     float* tx_gx; int64_t tx_ldgx;
+    // neural spline (TFEPB_TCTX_SPLINE8): domain of every unit, in unit order, and the options of spline.py:166-182
+    const float *sp_x0, *sp_xf, *sp_y0, *sp_yf;
+    int sp_flags;                       // bit 0 circular, 1 identity boundary slopes, 2 / 3 learnable lower / upper bound
+    float sp_min_bin, sp_min_slope;
 };
+
+// Neural spline transformer, 8 bins: one unit = the 32 columns of a sub-tile (<= 27 parameters + padding).  The unit's
+// parameters go to the thread's own slots of the transposition buffer (the spline math indexes them by the bin found at run
+// time), x / grad_y are read and y / grad_x written directly (one element per row and unit).
+__device__ __forceinline__ SplineFeat<float> tx_spline_feat(const Params& p, int u) {
+    SplineFeat<float> c;
+    c.K = 8;
+    c.circular = p.sp_flags & 1; c.idslopes = (p.sp_flags >> 1) & 1; c.learn_lo = (p.sp_flags >> 2) & 1; c.learn_hi = (p.sp_flags >> 3) & 1;
+    c.x0 = __ldg(p.sp_x0 + u); c.xf = __ldg(p.sp_xf + u); c.y0 = __ldg(p.sp_y0 + u); c.yf = __ldg(p.sp_yf + u);
+    c.min_bin = p.sp_min_bin; c.min_slope = p.sp_min_slope;
+    return c;
+}
 
 // TX template argument: 0 = plain product, else 2 * kind + backward with kind = TFEPB_TCTX_*
 __host__ __device__ constexpr int tx_kind(int TX) { return TX >> 1; }
@@ -104,6 +120,7 @@ template <int TX> struct TxGeo {
     static constexpr int PPU = KIND == TFEPB_TCTX_AFFINE ? 2 : KIND == TFEPB_TCTX_SOS2 ? 5 : 3;     // parameter columns per unit
     static constexpr int XPU = KIND == TFEPB_TCTX_MOEBIUS3 ? 3 : 1;                                // x columns per unit
     static constexpr int XPC = UPC * XPU;                                                          // x columns per chunk
+    static constexpr bool SPLINE = KIND == TFEPB_TCTX_SPLINE8;      // one unit per 32-column sub-tile, no staging (see below)
     // chunks per staging group of the transposition buffer (32 columns): forward x only, backward x and grad_y
     static constexpr int GF = 4 * XPC <= 32 ? 4 : 2;
     static constexpr int GB = 4 * XPC <= 32 ? 2 : 1;
@@ -522,7 +539,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             [[maybe_unused]] float gl = 0.f;
             [[maybe_unused]] constexpr bool xp_free = true;   // the VJP variants never use the transposition buffer for anything else
             [[maybe_unused]] float* xs_tile = xp + ((FWD_AHEAD && (tcount & 1)) ? 4 * TG::XPC * XP_LD : 0);
-            if constexpr (TX != 0 && !tx_bwd(TX)) {
+            if constexpr (TX != 0 && TG::SPLINE) {
+                if (tx_bwd(TX) && p.tx_gl != nullptr && row_ok) gl = __ldg(p.tx_gl + gm);
+            } else if constexpr (TX != 0 && !tx_bwd(TX)) {
                 // x of the first sub-tile's two chunks, and of the second one's where the buffer holds both (GF == 4)
                 auto stage_tile = [&](int tt, float* dst) {
                     int tm2, tn2;
@@ -710,6 +729,23 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                 for (int sub = 0; sub < 2; ++sub) {
                     const int gns = sub == 0 ? gn_sub0 : gn_sub1;
                     if (gns >= p.N) break;                                                     // warp-uniform
+                    if constexpr (TG::SPLINE) {
+                        float va[16], vb[16];
+                        load_pair(2 * sub, va, vb);
+                        const int u = gns >> 5;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { xp[i * XP_LD + lane] = va[i]; xp[(16 + i) * XP_LD + lane] = vb[i]; }
+                        if (row_ok && u < p.tx_units) {
+                            const int col = tx_cols[u];
+                            float y, ld;
+                            int bin;
+                            spline_eval<float, 8, false>(tx_spline_feat(p, u), ParIn<float>{xp + lane, XP_LD},
+                                                         __ldg(p.tx_x + (int64_t)gm * p.tx_ldx + col), y, ld, bin);
+                            p.tx_y[(int64_t)gm * p.tx_ldy + col] = y;
+                            ld_acc += ld;
+                        }
+                        continue;
+                    }
                     const int c0 = (gns >> 4) * TG::XPC;
                     float* xs = xs_tile + (TG::GF == 4 ? sub * 2 * TG::XPC * XP_LD : 0);
                     const bool staged = TG::GF != 4 && sub > 0;
@@ -758,6 +794,43 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                             asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(xp + lane * XP_LD + r)),
                                          "l"(ok ? p.C + (int64_t)grow * p.ldc + gns + lane : p.C), "r"(ok ? 4 : 0) : "memory");
                         }
+                    }
+                    if constexpr (TX != 0 && TG::SPLINE) {
+                        // ---- neural spline, backward: the sub-tile is one unit; parameters -> cotangents in place in the
+                        // thread's slots of the buffer (spline_vjp reads every parameter before it overwrites its range) ----
+                        float va[16], vb[16];
+                        load_pair(2 * sub, va, vb);
+                        const int u = gns >> 5;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { xp[i * XP_LD + lane] = va[i]; xp[(16 + i) * XP_LD + lane] = vb[i]; }
+                        const bool on = row_ok && u < p.tx_units;
+                        int n_par = 0;
+                        if (on) {
+                            const SplineFeat<float> feat = tx_spline_feat(p, u);
+                            n_par = feat.n_params();
+                            const int col = tx_cols[u];
+                            float gx;
+                            spline_vjp<float, 8>(feat, ParIn<float>{xp + lane, XP_LD}, __ldg(p.tx_x + (int64_t)gm * p.tx_ldx + col),
+                                                 __ldg(p.tx_gy + (int64_t)gm * p.tx_ldgy + col), gl, gx, ParOut<float>{xp + lane, XP_LD});
+                            p.tx_gx[(int64_t)gm * p.tx_ldgx + col] = gx;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            va[i] = i < n_par ? xp[i * XP_LD + lane] : 0.f;
+                            vb[i] = 16 + i < n_par ? xp[(16 + i) * XP_LD + lane] : 0.f;
+                        }
+                        if (p.colsum != nullptr) {
+                            const float sa = warp_colsum16(va, lane), sb = warp_colsum16(vb, lane);
+                            const int n = gns + ((lane >> 1) & 15);
+                            if ((lane & 1) == 0) {
+                                if (n < p.N) atomicAdd(p.colsum + n, sa);
+                                if (n + 16 < p.N) atomicAdd(p.colsum + n + 16, sb);
+                            }
+                        }
+                        emit_chunk(2 * sub, va);
+                        emit_chunk(2 * sub + 1, vb);
+                        __syncwarp();
+                        continue;
                     }
                     if constexpr (TX != 0) {
                         // ---- fused transformer, backward, one chunk at a time through ONE copy of the code (the size of the
@@ -1235,13 +1308,20 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
     TFEPB_CHECK_ARG(a->c != nullptr || a->out_image != nullptr || a->out_image_t != nullptr || (tx != nullptr && !tx->backward),
                     "no output");
     if (tx != nullptr) {
-        TFEPB_CHECK_ARG(tx->kind >= TFEPB_TCTX_AFFINE && tx->kind <= TFEPB_TCTX_MOEBIUS3, "unknown fused transformer kind %d", tx->kind);
+        TFEPB_CHECK_ARG(tx->kind >= TFEPB_TCTX_AFFINE && tx->kind <= TFEPB_TCTX_SPLINE8, "unknown fused transformer kind %d", tx->kind);
         TFEPB_CHECK_ARG(a->n_split <= 1 && a->split_k <= 1 && a->aux == nullptr && a->aux_image == nullptr &&
                             a->activation == TFEPB_ACT_NONE && a->n % 16 == 0,
                         "fused transformer: plain bf16 product without split-K / aux / activation, n a multiple of 16");
         const int upc = tx->kind == TFEPB_TCTX_AFFINE ? 8 : tx->kind == TFEPB_TCTX_SOS2 ? 3 : 5;
-        TFEPB_CHECK_ARG(tx->n_units > 0 && (int64_t)a->n >= ((int64_t)tx->n_units + upc - 1) / upc * 16,
-                        "fused transformer: n = %d columns do not hold %d units", a->n, tx->n_units);
+        if (tx->kind == TFEPB_TCTX_SPLINE8) {
+            TFEPB_CHECK_ARG(tx->n_units > 0 && (int64_t)a->n >= (int64_t)tx->n_units * 32,
+                            "fused spline transformer: n = %d columns do not hold %d units of 32 columns", a->n, tx->n_units);
+            TFEPB_CHECK_ARG(tx->spline_x0 && tx->spline_xf && tx->spline_y0 && tx->spline_yf, "fused spline transformer: null domain");
+            TFEPB_CHECK_ARG(!((tx->spline_flags & 1) && (tx->spline_flags & 12)), "Cannot instantiate a circular spline with learnable limits.");
+        } else {
+            TFEPB_CHECK_ARG(tx->n_units > 0 && (int64_t)a->n >= ((int64_t)tx->n_units + upc - 1) / upc * 16,
+                            "fused transformer: n = %d columns do not hold %d units", a->n, tx->n_units);
+        }
         TFEPB_CHECK_ARG(tx->cols != nullptr && tx->x != nullptr, "fused transformer: null buffer");
         TFEPB_CHECK_ARG(tx->unit_sphere == 0 || tx->unit_sphere == 1, "fused transformer: Moebius variant must be 0 or 1");
         if (!tx->backward) {
@@ -1300,6 +1380,8 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
         p.tx_gy = (const float*)tx->grad_y; p.tx_ldgy = tx->ldgy;
         p.tx_gl = tx->grad_logdet;
         p.tx_gx = (float*)tx->grad_x; p.tx_ldgx = tx->ldgx;
+        p.sp_x0 = tx->spline_x0; p.sp_xf = tx->spline_xf; p.sp_y0 = tx->spline_y0; p.sp_yf = tx->spline_yf;
+        p.sp_flags = tx->spline_flags; p.sp_min_bin = tx->spline_min_bin_size; p.sp_min_slope = tx->spline_min_slope;
     }
     int splits = a->split_k > 1 ? a->split_k : 1;
     if (splits > p.k_blocks) splits = p.k_blocks;
@@ -1343,10 +1425,11 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
     using kernel_t = void (*)(const tcg::Params);
     kernel_t kernel = n_split == 1 ? tcg::tc_gemm_kernel<1> : n_split == 2 ? tcg::tc_gemm_kernel<2> : tcg::tc_gemm_kernel<3>;
     if (tx != nullptr) {
-        static const kernel_t fused[6] = {
+        static const kernel_t fused[8] = {
             tcg::tc_gemm_kernel<1, 2 * TFEPB_TCTX_AFFINE>,   tcg::tc_gemm_kernel<1, 2 * TFEPB_TCTX_AFFINE + 1>,
             tcg::tc_gemm_kernel<1, 2 * TFEPB_TCTX_SOS2>,     tcg::tc_gemm_kernel<1, 2 * TFEPB_TCTX_SOS2 + 1>,
-            tcg::tc_gemm_kernel<1, 2 * TFEPB_TCTX_MOEBIUS3>, tcg::tc_gemm_kernel<1, 2 * TFEPB_TCTX_MOEBIUS3 + 1>};
+            tcg::tc_gemm_kernel<1, 2 * TFEPB_TCTX_MOEBIUS3>, tcg::tc_gemm_kernel<1, 2 * TFEPB_TCTX_MOEBIUS3 + 1>,
+            tcg::tc_gemm_kernel<1, 2 * TFEPB_TCTX_SPLINE8>,  tcg::tc_gemm_kernel<1, 2 * TFEPB_TCTX_SPLINE8 + 1>};
         kernel = fused[2 * (tx->kind - 1) + (tx->backward ? 1 : 0)];
     }
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), smem)) return rc;

@@ -619,8 +619,8 @@ TFEPB_HD void spline_vjp(const SplineFeat<T>& c, const ParIn<T>& par, T x, T gy,
             gpar.set(k, st.ew[k] * (gw[k] * st.Rw - dotw));
             gpar.set(K + k, st.eh[k] * (gh[k] * st.Rh - doth));
         }
-    // slopes
-    for (int i = 2 * K; i < st.P; ++i) gpar.set(i, T(0));
+    // slopes (the parameters are read BEFORE the first cotangent of their range is written: gpar may alias par, as in the
+    // fused epilogue of tc_gemm_sm100.cu where both live in the same shared-memory column)
     {
         // accumulate in parameter space (circular splines tie knot K to knot 0)
         const int ia = ja >= 0 ? c.slope_param(ja) : -1;
@@ -628,6 +628,7 @@ TFEPB_HD void spline_vjp(const SplineFeat<T>& c, const ParIn<T>& par, T x, T gy,
         T ga = T(0), gb = T(0);
         if (ia >= 0) ga = gda * (par[ia] + st.offset > T(20) ? T(1) : sigmoid(par[ia] + st.offset));
         if (ib >= 0) gb = gdb * (par[ib] + st.offset > T(20) ? T(1) : sigmoid(par[ib] + st.offset));
+        for (int i = 2 * K; i < st.P; ++i) gpar.set(i, T(0));
         if (ia >= 0 && ia == ib) {
             gpar.set(ia, ga + gb);
         } else {
