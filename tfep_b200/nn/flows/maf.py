@@ -54,7 +54,7 @@ class MAF(AutoregressiveFlow):
         ``'bf16x3'`` / ``'bf16x6'``: tensor cores with every operand split into two / three bf16 terms (3 / 6 products
         per reduction step, fp32 accumulation): the conditioner at fp32-class accuracy on the tensor cores.
         Also an attribute: ``maf.precision = ...`` switches an existing module.  With ``'bf16'`` and an affine / SOS (two
-        polynomials) / Moebius (3-vectors) transformer over all features, the transformer and its VJP run in the epilogue of
+        polynomials) / Moebius (3-vectors) / neural-spline (8 bins) transformer over all features, the transformer and its VJP run in the epilogue of
         the output-layer product, forward and backward (``maf.fuse_transformer = False`` keeps the separate kernels).
     """
 
