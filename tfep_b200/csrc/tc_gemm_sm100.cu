@@ -33,7 +33,7 @@
 // same way.
 //
 // FUSED TRANSFORMER (tfepb_tc_tx; the output layer of a MAF whose transformer is affine / SOS (2 polynomials) / Moebius on
-// 3-vectors): the output columns are laid out in 16-column chunks that hold the parameters of 8 / 3 / 5 whole units (the
+// 3-vectors; the 8-bin neural spline takes a 32-column sub-tile per feature, see tx_spline_feat): the output columns are laid out in 16-column chunks that hold the parameters of 8 / 3 / 5 whole units (the
 // caller pads the packed weight rows accordingly), so the 16 accumulator values an epilogue thread reads are complete
 // parameter sets of its sample.  Forward: the thread applies the transformer to its row of x, writes y and adds the
 // log-det -- the (batch x parameters) matrix never exists in memory.  Backward: the same product is recomputed and the
