@@ -336,6 +336,40 @@ def secondary_legs(dev, rank, world):
     del seq3, opt, x3, loss
     torch.cuda.empty_cache()
 
+    # ---- cfg2 as a TRAINING step (the headline flow under autograd): spline transformer + VJP in the GEMM epilogue ----
+    seq2 = build_flow(dev)
+    for m in seq2:
+        m.precision = 'bf16'
+    broadcast_parameters(seq2)
+    x2 = cfg2_input(BATCH, seed=200 + rank).to(dev)
+    opt2 = torch.optim.AdamW(seq2.parameters(), lr=1e-4)
+
+    def step2():
+        opt2.zero_grad(set_to_none=True)
+        y, ld = seq2(x2)
+        loss = loss_fn(0.5 * (y * y).sum(dim=1), ld)
+        loss.backward()
+        allreduce_gradients(seq2)
+        opt2.step()
+        return loss
+
+    for _ in range(2):
+        step2()
+    sync()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        loss2 = step2()
+    b.record()
+    sync()
+    ms2 = max_over_ranks(a.elapsed_time(b) / 5)
+    out['cfg2_train'] = {'workload': 'cfg2 (4xMAF circular spline K=8, D=66), batch 65536 per GPU, training step = forward + '
+                                     'BoltzmannKLDivLoss + backward + gradient all-reduce + AdamW',
+                         'precision': 'bf16 (tcgen05 GEMMs, spline transformer and its VJP in the epilogue of the output product)',
+                         'ms_per_step': ms2, 'samples_per_s': BATCH * world / (ms2 * 1e-3), 'loss': float(loss2.detach())}
+    del seq2, opt2, x2, loss2
+    torch.cuda.empty_cache()
+
     # ---- cfg4: estimator + 1000-resample bootstrap over 1e8 work values, contiguous shards ----
     n = 100_000_000
     lo, hi = rank * n // world, (rank + 1) * n // world

@@ -66,5 +66,6 @@ def test_measured_arm_line():
     assert pp['log_det_J']['p999'] < 2e-5 and pp['log_det_J']['frac_le_1e-5'] > 0.99
     # the legs that exchange data between ranks (collectives are no-ops at N = 1)
     assert d['cfg3']['ms_per_step'] > 0 and d['cfg3']['loss'] == d['cfg3']['loss']
+    assert d['cfg2_train']['ms_per_step'] > 0 and d['cfg2_train']['loss'] == d['cfg2_train']['loss']
     assert abs(d['cfg4']['delta_f'] + 0.5) < 5e-3 and d['cfg4']['bootstrap_draws_per_s'] > 1e10
     assert d['cfg4']['ci95'][0] < -0.5 < d['cfg4']['ci95'][1]
