@@ -255,11 +255,10 @@ typedef struct {
     const void* grad_y; int64_t ldgy;    /* backward */
     const float* grad_logdet;            /* backward, or NULL (ignored by SOS: sos.py:233) */
     void* grad_x; int64_t ldgx;          /* backward */
-    /* TFEPB_TCTX_SPLINE8 only: domain [x0, xf] -> [y0, yf] of every unit (fp32, n_units each, unit order) and the options */
-    const float* spline_x0; const float* spline_xf; const float* spline_y0; const float* spline_yf;
-    int32_t spline_flags;                /* bit 0 circular, 1 identity_boundary_slopes, 2 learn_lower_bound, 3 learn_upper_bound */
-    float spline_min_bin_size, spline_min_slope;
-    int32_t reserved;
+    /* TFEPB_TCTX_SPLINE8 only: device, 16-byte aligned, 8 floats per unit (unit order) = x0, xf, y0, yf (domain [x0, xf] ->
+     * [y0, yf]), min_bin_size, min_slope, flags as int32 bits (0 circular, 1 identity_boundary_slopes, 2 learn_lower_bound,
+     * 3 learn_upper_bound), unused: the units of a MixedTransformer of splines may differ in every option */
+    const float* spline_table;
 } tfepb_tc_tx;
 
 typedef struct {

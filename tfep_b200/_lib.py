@@ -95,9 +95,7 @@ class TcTx(Structure):
     _fields_ = [('kind', c_int32), ('backward', c_int32), ('n_units', c_int32), ('unit_sphere', c_int32),
                 ('max_radius', c_double), ('cols', c_void_p), ('x', c_void_p), ('ldx', c_int64), ('y', c_void_p),
                 ('ldy', c_int64), ('logdet', c_void_p), ('grad_y', c_void_p), ('ldgy', c_int64), ('grad_logdet', c_void_p),
-                ('grad_x', c_void_p), ('ldgx', c_int64), ('spline_x0', c_void_p), ('spline_xf', c_void_p),
-                ('spline_y0', c_void_p), ('spline_yf', c_void_p), ('spline_flags', c_int32), ('spline_min_bin_size', c_float),
-                ('spline_min_slope', c_float), ('reserved', c_int32)]
+                ('grad_x', c_void_p), ('ldgx', c_int64), ('spline_table', c_void_p)]
 
 
 class TcGemmArgs(Structure):

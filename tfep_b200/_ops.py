@@ -477,7 +477,7 @@ class TcTx:
     def __init__(self, kind, cols, x, *, y=None, logdet=None, grad_y=None, grad_logdet=None, grad_x=None,
                  max_radius=0.0, unit_sphere=0, spline=None):
         self.kind, self.cols, self.x = kind, cols, x
-        #: kind 'spline': dict(x0, xf, y0, yf (float32 device tensors in unit order), flags, min_bin_size, min_slope)
+        #: kind 'spline': float32 device tensor (n_units, 8) = x0, xf, y0, yf, min_bin_size, min_slope, flags (int bits), 0
         self.spline = spline
         self.y, self.logdet, self.grad_y, self.grad_logdet, self.grad_x = y, logdet, grad_y, grad_logdet, grad_x
         self.max_radius, self.unit_sphere = float(max_radius), int(unit_sphere)
@@ -493,10 +493,7 @@ class TcTx:
                        grad_y=opt(self.grad_y), ldgy=ld(self.grad_y), grad_logdet=opt(self.grad_logdet),
                        grad_x=opt(self.grad_x), ldgx=ld(self.grad_x))
         if self.spline is not None:
-            sp = self.spline
-            st.spline_x0, st.spline_xf = sp['x0'].data_ptr(), sp['xf'].data_ptr()
-            st.spline_y0, st.spline_yf = sp['y0'].data_ptr(), sp['yf'].data_ptr()
-            st.spline_flags, st.spline_min_bin_size, st.spline_min_slope = sp['flags'], sp['min_bin_size'], sp['min_slope']
+            st.spline_table = self.spline.data_ptr()
         return st
 
 

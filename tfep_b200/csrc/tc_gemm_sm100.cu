@@ -92,10 +92,9 @@ struct Params {
     const float* tx_gy; int64_t tx_ldgy;
     const float* tx_gl;
     float* tx_gx; int64_t tx_ldgx;
-    // neural spline (TFEPB_TCTX_SPLINE8): domain of every unit, in unit order, and the options of spline.py:166-182
-    const float *sp_x0, *sp_xf, *sp_y0, *sp_yf;
-    int sp_flags;                       // bit 0 circular, 1 identity boundary slopes, 2 / 3 learnable lower / upper bound
-    float sp_min_bin, sp_min_slope;
+    // neural spline (TFEPB_TCTX_SPLINE8): per unit 8 floats = x0, xf, y0, yf, min_bin_size, min_slope, flags (int bits: 0
+    // circular, 1 identity boundary slopes, 2 / 3 learnable lower / upper bound; spline.py:166-182), unused
+    const float* sp_table;
 };
 
 // Neural spline transformer, 8 bins: one unit = the 32 columns of a sub-tile (<= 27 parameters + padding).  The unit's
@@ -103,10 +102,12 @@ struct Params {
 // time), x / grad_y are read and y / grad_x written directly (one element per row and unit).
 __device__ __forceinline__ SplineFeat<float> tx_spline_feat(const Params& p, int u) {
     SplineFeat<float> c;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.sp_table) + 2 * u), b = __ldg(reinterpret_cast<const float4*>(p.sp_table) + 2 * u + 1);
+    const int flags = __float_as_int(b.z);
     c.K = 8;
-    c.circular = p.sp_flags & 1; c.idslopes = (p.sp_flags >> 1) & 1; c.learn_lo = (p.sp_flags >> 2) & 1; c.learn_hi = (p.sp_flags >> 3) & 1;
-    c.x0 = __ldg(p.sp_x0 + u); c.xf = __ldg(p.sp_xf + u); c.y0 = __ldg(p.sp_y0 + u); c.yf = __ldg(p.sp_yf + u);
-    c.min_bin = p.sp_min_bin; c.min_slope = p.sp_min_slope;
+    c.circular = flags & 1; c.idslopes = (flags >> 1) & 1; c.learn_lo = (flags >> 2) & 1; c.learn_hi = (flags >> 3) & 1;
+    c.x0 = a.x; c.xf = a.y; c.y0 = a.z; c.yf = a.w;
+    c.min_bin = b.x; c.min_slope = b.y;
     return c;
 }
 
@@ -1316,8 +1317,8 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
         if (tx->kind == TFEPB_TCTX_SPLINE8) {
             TFEPB_CHECK_ARG(tx->n_units > 0 && (int64_t)a->n >= (int64_t)tx->n_units * 32,
                             "fused spline transformer: n = %d columns do not hold %d units of 32 columns", a->n, tx->n_units);
-            TFEPB_CHECK_ARG(tx->spline_x0 && tx->spline_xf && tx->spline_y0 && tx->spline_yf, "fused spline transformer: null domain");
-            TFEPB_CHECK_ARG(!((tx->spline_flags & 1) && (tx->spline_flags & 12)), "Cannot instantiate a circular spline with learnable limits.");
+            TFEPB_CHECK_ARG(tx->spline_table != nullptr && ((uintptr_t)tx->spline_table & 15) == 0,
+                            "fused spline transformer: null / misaligned unit table");
         } else {
             TFEPB_CHECK_ARG(tx->n_units > 0 && (int64_t)a->n >= ((int64_t)tx->n_units + upc - 1) / upc * 16,
                             "fused transformer: n = %d columns do not hold %d units", a->n, tx->n_units);
@@ -1380,8 +1381,7 @@ extern "C" int tfepb_tc_gemm(const tfepb_tc_gemm_args* a, tfepb_stream_t stream)
         p.tx_gy = (const float*)tx->grad_y; p.tx_ldgy = tx->ldgy;
         p.tx_gl = tx->grad_logdet;
         p.tx_gx = (float*)tx->grad_x; p.tx_ldgx = tx->ldgx;
-        p.sp_x0 = tx->spline_x0; p.sp_xf = tx->spline_xf; p.sp_y0 = tx->spline_y0; p.sp_yf = tx->spline_yf;
-        p.sp_flags = tx->spline_flags; p.sp_min_bin = tx->spline_min_bin_size; p.sp_min_slope = tx->spline_min_slope;
+        p.sp_table = tx->spline_table;
     }
     int splits = a->split_k > 1 ? a->split_k : 1;
     if (splits > p.k_blocks) splits = p.k_blocks;
