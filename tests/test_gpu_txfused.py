@@ -21,6 +21,19 @@ def _flow(kind, n_features, order, hidden=2, seed=0):
     from tfep_b200.nn.flows import MAF
     from tfep_b200.nn.transformers import AffineTransformer, MoebiusTransformer, NeuralSplineTransformer, SOSPolynomialTransformer
     torch.manual_seed(seed)
+    if kind == 'spline_embedded':
+        # the reference's MixedMAFMap in full: the periodic features enter the conditioner as (cos, sin) through a
+        # PeriodicEmbedding, circular splines map them, open splines the rest
+        from tfep_b200.nn.embeddings import PeriodicEmbedding
+        from tfep_b200.nn.transformers import MixedTransformer
+        ia = [i for i in range(n_features) if i % 2 == 0]
+        ib = [i for i in range(n_features) if i % 2 == 1]
+        pi = 3.141592653589793
+        ta = NeuralSplineTransformer(-torch.ones(len(ia)) * pi, torch.ones(len(ia)) * pi, 8, circular=True)
+        tb = NeuralSplineTransformer(-torch.ones(len(ib)) * 2.0, torch.ones(len(ib)) * 2.5, 8)
+        emb = PeriodicEmbedding(n_features, [-pi, pi], periodic_indices=ia)
+        return MAF(generate_degrees(n_features, order=order), MixedTransformer([ta, tb], [ia, ib]), hidden_layers=hidden,
+                   embedding=emb, initialize_identity=False).to(DEV)
     if kind == 'spline_mixed':
         # the reference's MixedMAFMap shape: circular splines on some features, open splines (other options, another domain)
         # on the rest, interleaved
@@ -77,7 +90,7 @@ def _rel(a, b):
 
 CASES = [('spline', 23, 'ascending', 300), ('spline_open', 9, 'descending', 200), ('spline_id', 12, 'ascending', 129),
          ('spline_learn', 10, 'descending', 260), ('spline_circ_id', 8, 'ascending', 64), ('spline', 66, 'ascending', 1000),
-         ('spline_mixed', 20, 'ascending', 300), ('spline_mixed', 66, 'descending', 500),
+         ('spline_mixed', 20, 'ascending', 300), ('spline_mixed', 66, 'descending', 500), ('spline_embedded', 24, 'ascending', 300),
          ('affine', 37, 'ascending', 300), ('affine', 64, 'descending', 128), ('sos', 40, 'ascending', 300),
          ('sos', 9, 'descending', 77), ('sos', 300, 'ascending', 1000), ('moebius', 36, 'ascending', 300),
          ('moebius', 33, 'descending', 513), ('moebius_unit', 30, 'ascending', 200), ('moebius', 300, 'descending', 700)]

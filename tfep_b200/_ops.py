@@ -690,16 +690,18 @@ class MadeTxFunctionTC(torch.autograd.Function):
     follow as in :class:`MadeFunctionTC`."""
 
     @staticmethod
-    def forward(ctx, x, n_layers, kb_fwd, kb_bwd, rr_w, spec, *wb):
+    def forward(ctx, x, xc, n_layers, kb_fwd, kb_bwd, rr_w, spec, *wb):
+        # ``xc``: the conditioner input where it differs from x (an embedding layer in front of the MADE), else None
         ws, bs = wb[:n_layers], wb[n_layers:]
         L = n_layers
         B = x.shape[0]
         keep = any(ctx.needs_input_grad)
-        img = tc_pack(x, 128)
+        need_cx = ctx.needs_input_grad[0] if xc is None else ctx.needs_input_grad[1]
+        img = tc_pack(x if xc is None else xc, 128)
         imgs, wts = [img], []
         for l in range(L - 1):
             N, K = ws[l].shape
-            wimg, wt = _weight_images(ws[l], keep and (l > 0 or ctx.needs_input_grad[0]))
+            wimg, wt = _weight_images(ws[l], keep and (l > 0 or need_cx))
             wts.append(wt)
             _, img = tc_gemm(img, wimg, B, N, K, bias=bs[l], activation=ACT_ELU, out_image=True,
                              k_block_ranges=None if kb_fwd is None else kb_fwd[l])
@@ -714,21 +716,21 @@ class MadeTxFunctionTC(torch.autograd.Function):
                         unit_sphere=spec['unit_sphere'], spline=spec.get('spline')))
         ctx.save_for_backward(x, *(imgs if keep else []), *ws, bs[-1], *([wimg] if keep else []))
         ctx.wts = wts if keep else None
-        ctx.meta = (L, kb_fwd, kb_bwd, rr_w, spec)
+        ctx.meta = (L, kb_fwd, kb_bwd, rr_w, spec, xc is not None)
         if spec['kind'] == 'sos':
             ctx.mark_non_differentiable(logdet)                  # the reference's SOS log-det carries no gradient (sos.py:233)
         return y, logdet
 
     @staticmethod
     def backward(ctx, grad_y, grad_ld):
-        L, kb_fwd, kb_bwd, rr_w, spec = ctx.meta
+        L, kb_fwd, kb_bwd, rr_w, spec, embedded = ctx.meta
         saved = list(ctx.saved_tensors)
         x, imgs, ws, b_last, w_last_img = saved[0], saved[1:1 + L], saved[1 + L:1 + 2 * L], saved[1 + 2 * L], saved[2 + 2 * L]
         B = x.shape[0]
         grad_y = torch.zeros_like(x) if grad_y is None else _rows(grad_y.contiguous())
         if grad_ld is not None:
             grad_ld = grad_ld.contiguous()
-        need_w = [ctx.needs_input_grad[6 + l] or ctx.needs_input_grad[6 + L + l] for l in range(L)]
+        need_w = [ctx.needs_input_grad[7 + l] or ctx.needs_input_grad[7 + L + l] for l in range(L)]
         gx = torch.empty_like(x)
         N, K = ws[-1].shape
         _, gimg, _, gb = tc_gemm(imgs[-1], w_last_img, B, N, K, bias=b_last, out_image=True, column_sums=True,
@@ -736,15 +738,21 @@ class MadeTxFunctionTC(torch.autograd.Function):
                                  tx=TcTx(spec['kind'], spec['cols'], x, grad_y=grad_y, grad_logdet=grad_ld, grad_x=gx,
                                          max_radius=spec['max_radius'], unit_sphere=spec['unit_sphere'],
                                          spline=spec.get('spline')))
-        _, gws, gbs = _made_tc_backward_layers(B, imgs, ws, kb_bwd, rr_w, need_w, ctx.needs_input_grad[0], gimg, gb, gx_into=gx,
-                                               wts=ctx.wts)
+        if embedded:
+            # the cotangent of the embedded conditioner input goes back through the embedding's own graph
+            gxc, gws, gbs = _made_tc_backward_layers(B, imgs, ws, kb_bwd, rr_w, need_w, ctx.needs_input_grad[1], gimg, gb, wts=ctx.wts)
+        else:
+            gxc = None
+            _, gws, gbs = _made_tc_backward_layers(B, imgs, ws, kb_bwd, rr_w, need_w, ctx.needs_input_grad[0], gimg, gb, gx_into=gx,
+                                                   wts=ctx.wts)
         ctx.wts = None
-        return (gx if ctx.needs_input_grad[0] else None, None, None, None, None, None, *gws, *gbs)
+        return (gx if ctx.needs_input_grad[0] else None, gxc, None, None, None, None, None, *gws, *gbs)
 
 
-def made_tx_forward_tc(x, weights, biases, kb_fwd, kb_bwd, rr_w, spec):
-    """See :class:`MadeTxFunctionTC`; ``spec``: dict(kind, cols, max_radius, unit_sphere)."""
-    return MadeTxFunctionTC.apply(x, len(weights), kb_fwd, kb_bwd, rr_w, spec, *weights, *biases)
+def made_tx_forward_tc(x, weights, biases, kb_fwd, kb_bwd, rr_w, spec, xc=None):
+    """See :class:`MadeTxFunctionTC`; ``spec``: dict(kind, cols, max_radius, unit_sphere[, spline]); ``xc``: the conditioner
+    input if an embedding layer sits in front of the MADE."""
+    return MadeTxFunctionTC.apply(x, xc, len(weights), kb_fwd, kb_bwd, rr_w, spec, *weights, *biases)
 
 
 def made_forward_tc(x, weights, biases, kb_fwd=None, kb_bwd=None, rr_w=None, n_split=1, weight_images=None):

@@ -24,8 +24,6 @@ def eligibility(maf, pk):
         return 'the transformer is not a native program'
     if maf._n_conditioner_indices > 0 or maf.has_fixed_indices:
         return 'conditioning / fixed features'
-    if maf._embedding is not None:
-        return 'the conditioner input goes through an embedding'
     parts = pk['parts']
     n_in = len(maf._degrees_in_host)
     columns = sorted(c for p in parts for c in p.x_columns().tolist())
@@ -140,4 +138,12 @@ class TcTxPlan:
     def forward(self, maf, pk, x):
         kb_fwd, kb_bwd, rr_w = self.plan.tc_ranges(x.device)
         pw, pb = maf._conditioner.packed_weights(self.plan)
-        return _ops.made_tx_forward_tc(x, list(pw), list(pb), kb_fwd, kb_bwd, rr_w, self.tables(x.device))
+        xc = None
+        if maf._embedding is not None:
+            # an embedding layer in front of the MADE (e.g. PeriodicEmbedding): the conditioner reads the embedded features, the
+            # transformer maps x itself
+            xc = maf._embedding(x)
+            if xc.dtype != torch.float32:
+                raise _ops._lib.TfepB200Error("precision='bf16' takes float32 inputs")
+            xc = xc.contiguous()
+        return _ops.made_tx_forward_tc(x, list(pw), list(pb), kb_fwd, kb_bwd, rr_w, self.tables(x.device), xc=xc)
