@@ -225,8 +225,8 @@ def test_padded_chunk_layout_of_the_fused_transformer_epilogue():
     # flows the epilogue does not cover say why
     sos3 = MAF(generate_degrees(8), SOSPolynomialTransformer(3), initialize_identity=False)
     assert 'polynomials' in _txfused.eligibility(sos3, sos3._pack())
-    cond = MAF([-1] + generate_degrees(6).tolist(), initialize_identity=False)
-    assert _txfused.eligibility(cond, cond._pack()) is not None
+    cond = MAF([-1] + generate_degrees(6).tolist(), initialize_identity=False)      # conditioning features pass through
+    assert _txfused.eligibility(cond, cond._pack()) is None and _txfused.TcTxPlan(cond, cond._pack()).passthrough
 
 
 def test_staircase_skips_about_half_of_the_headline_config():

@@ -707,7 +707,8 @@ class MadeTxFunctionTC(torch.autograd.Function):
                              k_block_ranges=None if kb_fwd is None else kb_fwd[l])
             imgs.append(img)                 # bf16 row image: next operand, ELU' operand and weight-gradient operand
         N, K = ws[-1].shape
-        y = torch.empty_like(x)
+        # (conditioning features are not mapped by any unit: they pass through)
+        y = x.clone() if spec.get('passthrough') else torch.empty_like(x)
         logdet = torch.zeros(B, dtype=torch.float32, device=x.device)
         wimg, wt = _weight_images(ws[-1], keep)
         wts.append(wt)
@@ -731,7 +732,7 @@ class MadeTxFunctionTC(torch.autograd.Function):
         if grad_ld is not None:
             grad_ld = grad_ld.contiguous()
         need_w = [ctx.needs_input_grad[7 + l] or ctx.needs_input_grad[7 + L + l] for l in range(L)]
-        gx = torch.empty_like(x)
+        gx = grad_y.clone() if spec.get('passthrough') else torch.empty_like(x)
         N, K = ws[-1].shape
         _, gimg, _, gb = tc_gemm(imgs[-1], w_last_img, B, N, K, bias=b_last, out_image=True, column_sums=True,
                                  k_block_ranges=None if kb_fwd is None else kb_fwd[-1],

@@ -22,13 +22,12 @@ def eligibility(maf, pk):
     """None if the fused epilogue covers the layer, else the reason (a string)."""
     if pk is False:
         return 'the transformer is not a native program'
-    if maf._n_conditioner_indices > 0 or maf.has_fixed_indices:
-        return 'conditioning / fixed features'
+    if maf._n_conditioner_indices > 0:
+        return 'the conditioner reads a subset of the features'
     parts = pk['parts']
-    n_in = len(maf._degrees_in_host)
     columns = sorted(c for p in parts for c in p.x_columns().tolist())
-    if columns != list(range(n_in)):
-        return 'the transformer does not map every feature'
+    if columns != sorted(maf._mapped_host.tolist()):
+        return 'the transformer program does not cover the mapped features'
     if len(parts) > 1:
         # a MixedTransformer is covered when all its children are 8-bin splines (any options: the table is per unit)
         if not all(p.kind == 'spline' and p.spec.n_bins_int == 8 for p in parts):
@@ -108,6 +107,8 @@ class TcTxPlan:
         self.plan = MadePlan(maf._conditioner._degree_chain, out_order=out_order)
         self.max_radius = float(getattr(parts[0].spec, 'max_radius', 0.0))
         self.unit_sphere = int(getattr(parts[0].spec, 'unit_sphere', 0))
+        #: conditioning features (degree -1): read by the conditioner, copied through by the flow
+        self.passthrough = bool(maf.has_fixed_indices)
         self._parts = parts
         self._dev = {}
 
@@ -115,7 +116,7 @@ class TcTxPlan:
         key = str(device)
         if key not in self._dev:
             self._dev[key] = dict(kind=self.kind, cols=self.cols.to(device), max_radius=self.max_radius,
-                                  unit_sphere=self.unit_sphere)
+                                  unit_sphere=self.unit_sphere, passthrough=self.passthrough)
         spec = self._dev[key]
         if self.kind == 'spline':
             # per unit: domain, minimum bin size / slope and option bits (re-derived when a child's domain buffers change)
