@@ -128,6 +128,11 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ void lds_v4(uint32_t addr, uint32_t (&v)[4]) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
@@ -284,9 +289,41 @@ __device__ __forceinline__ float rcp(float v) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
 }
+// Packed fp32 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, two IEEE round-to-nearest operations per issue slot on an aligned
+// register pair; the results are those of the scalar instructions bit for bit).  The epilogues are bound by issue slots, not
+// by the FMA pipe, so every pair of identical operations on two independent values is worth packing.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 // ELU in the log2 domain: t = log2(e) h  ->  log2(e) ELU(h) = t > 0 ? t : log2(e) (2^t - 1)
 // Branch-free: g(t) = log2(e) (2^min(t, 0) - 1) is 0 for t >= 0 and >= t for t <= 0, so the result is max(t, g).
 __device__ __forceinline__ float elu_l2(float t, float l2e) { return fmaxf(t, fmaf(ex2(fminf(t, 0.f)), l2e, -LOG2E)); }
+// two of them with ONE packed fma (l2e2 = (l2e, l2e), ml2e2 = (-log2(e), -log2(e))); same values as elu_l2
+__device__ __forceinline__ void elu_l2x2(float t0, float t1, f32x2 l2e2, f32x2 ml2e2, float& r0, float& r1) {
+    float g0, g1;
+    unpack2(fma2(pack2(ex2(fminf(t0, 0.f)), ex2(fminf(t1, 0.f))), l2e2, ml2e2), g0, g1);
+    r0 = fmaxf(t0, g0);
+    r1 = fmaxf(t1, g1);
+}
 // softplus of a log2-domain argument z = log2(e) * v: log(1 + e^v) = ln2 * lg2(1 + 2^z)
 __device__ __forceinline__ float softplus_l2(float z) { return z > 28.85f ? z * LN2 : LN2 * lg2(1.f + ex2(z)); }
 
