@@ -53,14 +53,6 @@ using namespace tc;
 constexpr int EPI_WGS = 4;                      // epilogue warpgroups
 constexpr int EPI_THREADS = EPI_WGS * 128;
 constexpr int EPI_WARPS = EPI_THREADS / 32;     // hand-over barriers count one arrival per epilogue WARP (lane 0, after a warp sync)
-#ifndef TFEPB_EPI_PAIR
-#define TFEPB_EPI_PAIR 0
-#endif
-// Output chunks: with TFEPB_EPI_PAIR the four epilogue warpgroups form two TEAMS of two; team 0 takes the even chunks, team 1
-// the odd ones, and every thread evaluates TWO features of its chunk as one interleaved instruction stream (two independent
-// dependency chains per warp: the spline tail is a ~25-deep chain of fixed-latency and MUFU instructions, and four warps per
-// scheduler that run in phase cannot hide it).  A chunk accumulator is then drained by the eight warps of one team.
-constexpr int CHUNK_WARPS = TFEPB_EPI_PAIR ? EPI_WARPS / 2 : EPI_WARPS;
 constexpr int AUX_THREADS = 128;                // producer, MMA issuer, store warp, one idle warp
 constexpr int THREADS = AUX_THREADS + EPI_THREADS;
 constexpr int AUX_REGS = 32, EPI_REGS = 112;    // setmaxnreg budgets: the CTA starts with 96 per thread, 128 x (96 - 32) = 512 x (112 - 96)
@@ -251,123 +243,6 @@ __device__ __forceinline__ float spline8(uint32_t (&wh)[16], uint32_t (&sl)[9], 
     return ld;
 }
 
-// Two features of one sample per thread (TFEPB_EPI_PAIR).  The mathematics is that of spline8 and the knots are its knots bit for
-// bit; to fit the register budget the exponentials are not kept: the walk selects the scaled knots on both sides of the bin
-// and the bin width / height are their differences (a w = U_{k+1} - U_k), which moves them by an ulp of the knot, the error
-// the numerator ts - U_k carries anyway.  What changes is the schedule.  The front of a feature (exponentials, prefix
-// sums, wrap, knot walk) has instruction-level parallelism of its own and a large live set (wh, ew, eh, cw, ch, sl), so the
-// two fronts run one after the other; the TAIL (two softplus, three reciprocals, the rational-quadratic map and the
-// logarithm: a ~25-deep chain of fixed-latency and MUFU instructions on a dozen live values) is written for both features
-// at once, so that the compiler interleaves the two chains.
-struct SplineCarry {
-    float t, ts, a, Us, Vs, wsum, hsum, sh, raw0, raw1, Rh, y0, L;
-    bool circ;
-};
-template <bool MIXED, class Handover>
-__device__ __forceinline__ void spline8_front(uint32_t (&wh)[16], uint32_t (&sl)[9], float x, uint32_t s_feat, float min_bin,
-                                              SplineCarry& o, uint32_t cur_addr, Handover&& after_sums) {
-    float cw[8], ch[8];
-    auto sums = [&](float mw, float mh) {
-        cw[0] = ex2(__uint_as_float(wh[0]) - mw);
-        ch[0] = ex2(__uint_as_float(wh[8]) - mh);
-#pragma unroll
-        for (int k = 1; k < 8; ++k) {
-            cw[k] = cw[k - 1] + ex2(__uint_as_float(wh[k]) - mw);
-            ch[k] = ch[k - 1] + ex2(__uint_as_float(wh[8 + k]) - mh);
-        }
-    };
-    sums(0.f, 0.f);
-    {
-        const float lo = fminf(cw[7], ch[7]), hi = fmaxf(cw[7], ch[7]);
-        if (__any_sync(0xffffffffu, !(lo > 7.9e-31f && hi < 1.3e30f))) {
-            // cold path: the logits are read again from the accumulator (the caller still owns it), so that they need not
-            // stay in registers next to the prefix sums
-            tmem_ld16(cur_addr, wh);
-            tmem_wait8(wh); tmem_wait8(wh + 8);
-            float mw = __uint_as_float(wh[0]), mh = __uint_as_float(wh[8]);
-#pragma unroll
-            for (int k = 1; k < 8; ++k) { mw = fmaxf(mw, __uint_as_float(wh[k])); mh = fmaxf(mh, __uint_as_float(wh[8 + k])); }
-            sums(mw, mh);
-        }
-    }
-    FeatConst fc;
-    {
-        uint32_t f0[4], f1[4];
-        lds_v4(s_feat, f0);
-        lds_v4(s_feat + 16, f1);
-        fc.col_kind = (int)f0[0]; fc.x0 = __uint_as_float(f0[1]); fc.L = __uint_as_float(f0[2]); fc.invL = __uint_as_float(f0[3]);
-        fc.iRw = __uint_as_float(f1[0]); fc.iRh = __uint_as_float(f1[1]); fc.Rh = __uint_as_float(f1[2]); fc.y0 = __uint_as_float(f1[3]);
-    }
-    after_sums();                   // wh is dead here; sl must be valid when this returns
-    const bool circ = !MIXED || (fc.col_kind >> 24) == 0;
-    float t = x - fc.x0;
-    if (circ) {
-        t += __uint_as_float(sl[8]);
-        t = t - fc.L * floorf(t * fc.invL);
-        t = (t < 0.f) ? t + fc.L : t;
-        t = (t >= fc.L) ? t - fc.L : t;
-    }
-    const float sw = cw[7], sh = ch[7];
-    const float a = sw * fc.iRw, b = sh * fc.iRh;
-    const float ts = t * a, mbs = min_bin * a, mbsh = min_bin * b;
-    // the walk keeps the scaled knots on both sides of the bin: a w = U_{k+1} - U_k, b h = V_{k+1} - V_k
-    float Us = 0.f, Vs = 0.f, Un = cw[0] + mbs, Vn = ch[0] + mbsh;
-    float raw0 = __uint_as_float(sl[0]), raw1 = __uint_as_float(sl[1]);
-    const float raw_last = (MIXED && !circ) ? __uint_as_float(sl[8]) : __uint_as_float(sl[0]);
-    float Uk = Un, Vk = Vn;
-#pragma unroll
-    for (int k = 1; k < 8; ++k) {
-        const float Uk1 = fmaf((float)(k + 1), mbs, cw[k]);
-        const float Vk1 = fmaf((float)(k + 1), mbsh, ch[k]);
-        const bool adv = ts > Uk;
-        Us = adv ? Uk : Us;
-        Un = adv ? Uk1 : Un;
-        Vs = adv ? Vk : Vs;
-        Vn = adv ? Vk1 : Vn;
-        raw0 = adv ? __uint_as_float(sl[k]) : raw0;
-        raw1 = adv ? (k == 7 ? raw_last : __uint_as_float(sl[k + 1])) : raw1;
-        Uk = Uk1; Vk = Vk1;
-    }
-    o.t = t; o.ts = ts; o.a = a; o.Us = Us; o.Vs = Vs; o.wsum = Un - Us; o.hsum = Vn - Vs; o.sh = sh;
-    o.raw0 = raw0; o.raw1 = raw1; o.Rh = fc.Rh; o.y0 = fc.y0; o.L = fc.L; o.circ = circ;
-}
-template <bool MIXED>
-__device__ __forceinline__ void spline8_tail2(const SplineCarry (&c)[2], float min_bin, float min_slope, float slope_offset2,
-                                              float (&y)[2], float (&ldo)[2]) {
-    float dk[2], dk1[2], iw[2], g[2], e[2], h_sel[2], s[2], ome[2], u[2], e2[2], den[2], iden[2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        dk[j] = softplus_l2(c[j].raw0 + slope_offset2) + min_slope;
-        dk1[j] = softplus_l2(c[j].raw1 + slope_offset2) + min_slope;
-        iw[j] = rcp(c[j].wsum);                    // 1 / (a w)
-        g[j] = c[j].Rh * rcp(c[j].sh);             // 1 / b
-    }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        e[j] = (c[j].ts - c[j].Us) * iw[j];
-        h_sel[j] = c[j].hsum * g[j];
-        s[j] = h_sel[j] * (iw[j] * c[j].a);        // h / w
-        ome[j] = 1.f - e[j]; u[j] = e[j] * ome[j]; e2[j] = e[j] * e[j];
-        const float q = dk1[j] + dk[j] - 2.f * s[j];
-        den[j] = fmaf(q, u[j], s[j]);
-        iden[j] = rcp(den[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        y[j] = fmaf(c[j].Vs, g[j], c[j].y0) + h_sel[j] * fmaf(s[j], e2[j], dk[j] * u[j]) * iden[j];
-        const float nn = fmaf(dk1[j], e2[j], fmaf(2.f * s[j], u[j], dk[j] * ome[j] * ome[j]));
-        const float rr = s[j] * iden[j];
-        ldo[j] = LN2 * lg2(nn * rr * rr);
-        if (MIXED && !c[j].circ) {
-            const bool lo = c[j].t < 0.f, hi = c[j].t > c[j].L;
-            const float yt = lo ? fmaf(dk[j], c[j].t, c[j].y0) : fmaf(dk1[j], c[j].t - c[j].L, c[j].y0 + fmaf(8.f, min_bin, c[j].Rh));
-            const float lt = LN2 * lg2(lo ? dk[j] : dk1[j]);
-            y[j] = (lo || hi) ? yt : y[j];
-            ldo[j] = (lo || hi) ? lt : ldo[j];
-        }
-    }
-}
-
 // development aid: CTA 0 stamps clock64() of key events into debug_params (as long long) when debug_mode & 16
 template <bool DEBUG>
 __device__ __forceinline__ void trace(const Params& p, int role, int& slot, int tag) {
@@ -417,7 +292,7 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
             mbar_init(&sm->x_full[b], 1); mbar_init(&sm->x_empty[b], 1); mbar_init(&sm->y_ready[b], EPI_WARPS);
         }
         mbar_init(&sm->a_ready, EPI_WARPS);
-        for (int b = 0; b < ACC_BUFS; ++b) { mbar_init(&sm->acc_full[b], 1); mbar_init(&sm->acc_empty[b], CHUNK_WARPS); }
+        for (int b = 0; b < ACC_BUFS; ++b) { mbar_init(&sm->acc_full[b], 1); mbar_init(&sm->acc_empty[b], EPI_WARPS); }
         mbar_init(&sm->hid_full[0], 1); mbar_init(&sm->hid_full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -544,12 +419,6 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
                 const uint32_t empty_par = ((empty_bits >> acc) & 1u) ^ 1u;
                 if (flags & OP_WAIT_EMPTY) empty_bits ^= 1u << acc;      // every use of the buffer, whoever issues it
                 if ((flags & OP_OWNER1) != me) {
-#if TFEPB_EPI_PAIR
-                    // The two epilogue teams drain the accumulators out of order, so an issuer that only counted the other
-                    // issuer's chunks could wait for a phase two ahead of the barrier and pass on the stale one: both issuers
-                    // observe every drain (the parity of a wait is only valid one phase ahead).
-                    if (flags & OP_WAIT_EMPTY) mbar_wait(&sm->acc_empty[acc], empty_par, p.error, 4);
-#endif
                     if (++stage == STAGES) { stage = 0; wphase ^= 1; }
                     continue;
                 }
@@ -762,109 +631,6 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
             // addresses of the loop, pinned in registers (the compiler would otherwise re-derive them from threadIdx and
             // the kernel parameters in every iteration): this thread's TMEM lane + feature slot, its row of the x / y tile,
             // the feature records of its slot, the accumulator barriers
-#if TFEPB_EPI_PAIR
-            // Team t = wg / 2 takes the chunks c = t, t + 2, ...; a thread owns the slots 2 (wg & 1) and 2 (wg & 1) + 1 of its
-            // chunks.  Chunk c lives in accumulator c % ACC_BUFS; `full_bits` (the parity to wait for, per accumulator) is
-            // flipped for EVERY chunk, also those of the other team, so that both teams keep the same count.
-            const uint32_t team = (uint32_t)wg >> 1;
-            const uint32_t t_slot = pinned(lane_addr + (wg & 1) * 2 * PSTRIDE);
-            const uint32_t s_xrow = pinned(smem_u32(xrow));
-            uint32_t s_feat = pinned(smem_u32(sFeat + layer * p.feat_stride + team * FEATS_PER_CHUNK + (wg & 1) * 2));
-            const uint32_t s_full = pinned(smem_u32(&sm->acc_full[0])), s_empty = pinned(smem_u32(&sm->acc_empty[0]));
-            const uint32_t is_lane0 = pinned(lane == 0 ? 1u : 0u);
-            // Every thread WAITS for every chunk, also the other team's (then only flips the bit): a parity wait is valid one
-            // phase ahead, and the teams are not in step with each other.
-            auto pass_chunk = [&](uint32_t buf) {
-                mbar_wait_s(s_full + buf * 8u, (full_bits >> buf) & 1u, p.error, 8);
-                full_bits ^= 1u << buf;
-            };
-            if ((int)team >= n_chunks) {
-                for (int c = 0; c < n_chunks; ++c) pass_chunk((uint32_t)(c % ACC_BUFS));
-            } else {
-                uint32_t b = team;
-                uint32_t wh[2][16], sl[2][9];
-                if (team == 1) pass_chunk(0u);            // chunk 0 belongs to the other team
-                mbar_wait_s(s_full + b * 8u, (full_bits >> b) & 1u, p.error, 8);
-                full_bits ^= 1u << b;
-                tc_fence_after();
-                tmem_ld16(t_slot + b * CHUNK_N, wh[0]);
-#pragma unroll 1
-                for (int c = team; c < n_chunks; c += 2, s_feat += 2 * FEATS_PER_CHUNK * (uint32_t)sizeof(FeatConst)) {
-                    trace<DEBUG>(p, 2, ts, 3100 + c);
-                    const uint32_t a0 = t_slot + b * CHUNK_N;
-                    // Register budget: only the first feature's logits are prefetched; the second feature's parameters are
-                    // requested once the first one's exponentials are taken, and land during its knot walk.
-                    tmem_wait8(wh[0]); tmem_wait8(wh[0] + 8);
-                    tmem_ld8(a0 + 16, sl[0]);
-                    tmem_ld1(a0 + 24, sl[0] + 8);
-                    auto load_second = [&]() {
-                        tmem_wait8(sl[0]); tmem_wait1(sl[0] + 8);
-                        tmem_ld16(a0 + PSTRIDE, wh[1]);
-                        tmem_ld8(a0 + PSTRIDE + 16, sl[1]);
-                        tmem_ld1(a0 + PSTRIDE + 24, sl[1] + 8);
-                    };
-                    const int ck0 = (int)lds_u32(s_feat), ck1 = (int)lds_u32(s_feat + (uint32_t)sizeof(FeatConst));
-                    const bool v0 = ck0 >= 0, v1 = ck1 >= 0;
-                    const uint32_t s_x0 = s_xrow + (v0 ? (uint32_t)(ck0 & 0xffffff) * 4u : 0u);
-                    const uint32_t s_x1 = s_xrow + (v1 ? (uint32_t)(ck1 & 0xffffff) * 4u : 0u);
-                    const uint32_t b1 = (b == ACC_BUFS - 1) ? 0u : b + 1u;      // accumulator of chunk c + 1 (other team)
-                    const uint32_t b2 = (b1 == ACC_BUFS - 1) ? 0u : b1 + 1u;    // accumulator of chunk c + 2 (this team's next)
-                    const bool has_mid = c + 1 < n_chunks, has_next = c + 2 < n_chunks;
-                    auto handover = [&]() {          // all 50 parameters of the two slots are in registers (the wait covers
-                        tmem_wait8(sl[1]); tmem_wait1(sl[1] + 8);      // every load this thread has issued)
-                        tc_fence_before();
-                        if (is_lane0) mbar_arrive_s(s_empty + b * 8u);
-                        if (has_mid) pass_chunk(b1);
-                        if (has_next) {
-                            mbar_wait_s(s_full + b2 * 8u, (full_bits >> b2) & 1u, p.error, 8);
-                            full_bits ^= 1u << b2;
-                            tc_fence_after();
-                        }
-                    };
-                    if (DEBUG && p.debug_params != nullptr && !(dmode & 16) && row < rows && layer == 0) {
-                        float* dbg = p.debug_params + ((size_t)tile * TILE_M + row) * n_chunks * CHUNK_N + c * CHUNK_N + (wg & 1) * 2 * PSTRIDE;
-                        uint32_t dw[16], ds[9];
-#pragma unroll 1
-                        for (int j = 0; j < 2; ++j) {
-                            tmem_ld16(a0 + j * PSTRIDE, dw); tmem_ld8(a0 + j * PSTRIDE + 16, ds); tmem_ld1(a0 + j * PSTRIDE + 24, ds + 8);
-                            tmem_wait8(dw); tmem_wait8(dw + 8); tmem_wait8(ds); tmem_wait1(ds + 8);
-                            if (j == 0 ? v0 : v1) {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) dbg[j * PSTRIDE + i] = __uint_as_float(dw[i]);
-#pragma unroll
-                                for (int i = 0; i < 9; ++i) dbg[j * PSTRIDE + 16 + i] = __uint_as_float(ds[i]);
-                            }
-                        }
-                    }
-                    if (DEBUG && (dmode & 2)) {                 // timing experiment: hand-over skeleton without the spline math
-                        load_second();
-                        handover();
-                        float acc = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 9; ++i) acc += __uint_as_float(sl[0][i]) + __uint_as_float(sl[1][i]);
-                        ld += acc;
-                        if (has_next) tmem_ld16(t_slot + b2 * CHUNK_N, wh[0]);
-                    } else if (v0 || v1) {
-                        const float xin[2] = {lds_f32(s_x0), lds_f32(s_x1)};
-                        float yv[2], ldv[2];
-                        SplineCarry carry[2];
-                        spline8_front<MIXED>(wh[0], sl[0], xin[0], s_feat, min_bin, carry[0], a0, load_second);
-                        tmem_wait8(wh[1]); tmem_wait8(wh[1] + 8);
-                        spline8_front<MIXED>(wh[1], sl[1], xin[1], s_feat + (uint32_t)sizeof(FeatConst), min_bin, carry[1], a0 + PSTRIDE, handover);
-                        if (has_next) tmem_ld16(t_slot + b2 * CHUNK_N, wh[0]);      // in flight during the tails
-                        spline8_tail2<MIXED>(carry, min_bin, min_slope, slope_offset2, yv, ldv);
-                        if (v0) { sts_f32(s_x0, yv[0]); ld += ldv[0]; }
-                        if (v1) { sts_f32(s_x1, yv[1]); ld += ldv[1]; }
-                    } else {
-                        load_second();
-                        handover();
-                        if (has_next) tmem_ld16(t_slot + b2 * CHUNK_N, wh[0]);
-                    }
-                    trace<DEBUG>(p, 2, ts, 3200 + c);
-                    b = b2;
-                }
-            }
-#else
             const uint32_t t_slot = pinned(lane_addr + wg * PSTRIDE);
             const uint32_t s_xrow = pinned(smem_u32(xrow));
             uint32_t s_feat = pinned(smem_u32(sFeat + layer * p.feat_stride + wg));     // one feature slot per warpgroup
@@ -934,7 +700,6 @@ __global__ void __launch_bounds__(THREADS, 1) maf_spline_fwd_kernel(const __grid
                 trace<DEBUG>(p, 2, ts, 3200 + c);
                 b = bn;
             }
-#endif
             // ---- hand the y tile and the log-det partials to the store warp ----
             sLd[xb * (EPI_WGS * TILE_M) + wg * TILE_M + row] = ld;
             fence_async_smem();                      // y tile writes -> visible to the bulk-copy engine
