@@ -56,3 +56,19 @@ def test_invalid_arguments_are_reported_without_a_gpu(lib):
     assert lib.tfepb_masked_linear_forward(None, None) < 0
     lib.tfepb_last_error.restype = ctypes.c_char_p
     assert b'null' in lib.tfepb_last_error()
+
+
+def test_library_holds_blackwell_tensor_core_code(lib):
+    """The hot kernels are sm_100a tensor-core code, not a recompiled SIMT fallback: the SASS of the built library holds
+    tcgen05 MMAs (UTCHMMA), tensor-memory loads / stores (LDTM / STTM), bulk copies of the TMA engine (UBLKCP), their
+    mbarrier commits (UTCBAR) and, in the fused forward kernel, packed fp32 arithmetic (FFMA2)."""
+    import shutil
+    import subprocess
+    exe = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(exe):
+        pytest.skip('cuobjdump not available')
+    sass = subprocess.run([exe, '-sass', '-fun', '_ZN5tfepb5fused21maf_spline_fwd_kernelILb0ELb0EEEvNS0_6ParamsE', _build.LIBPATH],
+                          capture_output=True, text=True, check=True).stdout
+    assert 'sm_100a' in sass or 'SM100' in sass.upper()
+    for op in ('UTCHMMA', 'LDTM', 'STTM', 'UBLKCP', 'UTCBAR', 'FFMA2', 'MUFU.EX2'):
+        assert op in sass, f'{op} missing from the fused forward kernel'
