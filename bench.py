@@ -376,12 +376,12 @@ def secondary_legs(dev, rank, world):
     gen = torch.Generator(device=dev).manual_seed(0)          # the same global array on every rank, then the shard
     w = torch.randn(n, device=dev, generator=gen)[lo:hi].clone()
     for _ in range(3):
-        df = D.fep_estimator_sharded(w)
+        df = D.fep_estimator_sharded(w, n_total=n)
     sync()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(10):
-        df = D.fep_estimator_sharded(w)                       # lse kernel + all-gather of (max, sum exp) pairs
+        df = D.fep_estimator_sharded(w, n_total=n)                       # lse kernel + all-gather of (max, sum exp) pairs
     b.record()
     sync()
     ms_e = max_over_ranks(a.elapsed_time(b) / 10)

@@ -53,7 +53,7 @@ def timed(fn, reps):
 
 # raw kernel: 20 back-to-back launches (host overhead amortised), one read of the shard each
 ms_k, _ = timed(lambda: _ops.lse(w, -1.0), 20)
-ms_e, df = timed(lambda: D.fep_estimator_sharded(w), 10)
+ms_e, df = timed(lambda: D.fep_estimator_sharded(w, n_total=n), 10)
 t0 = time.perf_counter()
 stats = D.bootstrap_statistics_sharded(w, lo, n, n_resamples=R, generator=torch.Generator().manual_seed(1), rng='philox')
 sync()

@@ -192,6 +192,19 @@ def test_sharded_partials_add_up_on_one_gpu():
     assert rel_err(stats, ref) < 2e-6
 
 
+def test_sharded_estimator_single_process_entry_points():
+    """fep_estimator_sharded without a process group is the plain estimator, with or without the known total."""
+    from tfep_b200.analysis import distributed as D
+    from tfep_b200.analysis import fep_estimator
+    w = (cases.normal((40001,), 11) * 1.5).to(DEV)
+    ref = ao.fep_estimator(w.cpu().double())
+    for kT in (1.0, 2.5):
+        ref = ao.fep_estimator(w.cpu().double(), kT=kT)
+        assert rel_err(D.fep_estimator_sharded(w, kT=kT), ref) < 1e-6
+        assert rel_err(D.fep_estimator_sharded(w, kT=kT, n_total=w.numel()), ref) < 1e-6
+        assert torch.equal(D.fep_estimator_sharded(w, kT=kT, n_total=w.numel()), fep_estimator(w, kT=kT))
+
+
 def test_estimator_unaligned_views_and_sizes():
     """Vector loads with scalar head / tail: any offset and length gives the oracle's value."""
     from tfep_b200.analysis import fep_estimator

@@ -91,11 +91,16 @@ def shard_cells(shard_offset, shard_len, n_total, device, group=None):
     return cells, owner
 
 
-def fep_estimator_sharded(work_shard, kT=1.0, group=None):
-    """``-kT logsumexp(-w / kT - log n)`` over the union of all ranks' shards (same value on every rank)."""
+def fep_estimator_sharded(work_shard, kT=1.0, group=None, n_total=None):
+    """``-kT logsumexp(-w / kT - log n)`` over the union of all ranks' shards (same value on every rank).
+
+    ``n_total`` is the global number of samples; a caller that knows it (as ``bootstrap_statistics_sharded``'s caller
+    does) saves the all-reduce of the shard lengths and the host synchronisation that reading its result back costs:
+    the call is then asynchronous (one streaming kernel, one 16-byte all-gather, a handful of scalar kernels)."""
     m, s = combine_lse_partials(_ops.lse(work_shard, -1.0 / kT), group)
-    n = _total(work_shard.numel(), work_shard.device, group)
-    return (-kT * (m + torch.log(s) - _log_n(n))).to(work_shard.dtype)
+    if n_total is None:
+        n_total = work_shard.numel() if _world(group) == 1 else _total(work_shard.numel(), work_shard.device, group)
+    return (-kT * (m + torch.log(s) - _log_n(int(n_total)))).to(work_shard.dtype)
 
 
 def bootstrap_statistics_sharded(work_shard, shard_offset, n_total, kT=1.0, n_resamples=9999, batch=None, generator=None,
