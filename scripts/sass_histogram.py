@@ -8,7 +8,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, 'tfep_b200', 'lib', 'libtfep_b200.so')
-BLACKWELL = ('UTCHMMA', 'UTCBAR', 'LDTM', 'STTM', 'UBLKCP', 'UTMALDG', 'UTMASTG', 'SYNCS', 'UTCATOMSWS', 'MUFU', 'ELECT', 'USETMAXREG')
+BLACKWELL = ('UTCHMMA', 'UTCBAR', 'LDTM', 'STTM', 'UBLKCP', 'UTMALDG', 'UTMASTG', 'SYNCS', 'UTCATOMSWS', 'MUFU', 'ELECT', 'USETMAXREG', 'FFMA2', 'FADD2', 'FMUL2')
 
 
 def kernels():
@@ -48,7 +48,7 @@ if __name__ == '__main__':
     meaning = {'UTCHMMA': 'tcgen05.mma (kind::f16)', 'UTCBAR': 'tcgen05.commit -> mbarrier', 'LDTM': 'tcgen05.ld (TMEM -> registers)',
                'STTM': 'tcgen05.st (registers -> TMEM)', 'UBLKCP': 'cp.async.bulk (TMA engine, linear)', 'SYNCS': 'mbarrier operations',
                'MUFU': 'special-function unit (ex2 / lg2 / rcp ...)', 'ELECT': 'elect.sync', 'USETMAXREG': 'setmaxnreg',
-               'UTCATOMSWS': 'tcgen05.alloc / dealloc', 'UTMALDG': 'cp.async.bulk.tensor load', 'UTMASTG': 'cp.async.bulk.tensor store'}
+               'UTCATOMSWS': 'tcgen05.alloc / dealloc', 'FFMA2': 'fma.rn.f32x2 (packed fp32)', 'FADD2': 'add.rn.f32x2', 'FMUL2': 'mul.rn.f32x2', 'UTMALDG': 'cp.async.bulk.tensor load', 'UTMASTG': 'cp.async.bulk.tensor store'}
     for op in BLACKWELL:
         if total[op]:
             print(f'| `{op}` | {total[op]} | {meaning.get(op, "")} |')
