@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TFEPB_ABI_VERSION 4
+#define TFEPB_ABI_VERSION 5
 
 enum { TFEPB_F32 = 0, TFEPB_F64 = 1 };
 enum { TFEPB_ACT_NONE = 0, TFEPB_ACT_ELU = 1 };
@@ -541,6 +541,12 @@ int tfepb_maf_inverse_sweep(const tfepb_sweep_args* a, tfepb_stream_t stream);
 int64_t tfepb_lse_workspace_bytes(void);
 int tfepb_lse(int32_t dtype, const void* w, const void* logw, int64_t n, double scale,
               void* partials, double* out2, tfepb_stream_t stream);
+/* The estimator in one call (analysis/estimator.py:61-86): the pass above with scale = -1 / kT, and its final reduction
+ * also writes result[0] = -kT ((max + log sum) - log_norm) in the dtype of w -- log_norm = log n for plain work values, 0
+ * with log-weights (Bayesian bootstrap), logsumexp(bias / kT) for biased data.  out2 receives (max, sum) as in
+ * tfepb_lse.  Two launches, no scalar tensor arithmetic on the host side. */
+int tfepb_fep_estimate(int32_t dtype, const void* w, const void* logw, int64_t n, double kT, double log_norm,
+                       void* partials, double* out2, void* result, tfepb_stream_t stream);
 
 /* Raw MT19937 stream of torch's CPU generator (analysis/bootstrap.py:214-218 draws its indices from
  * it): fills idx[i] = u32[skip + i] % max_idx for i < count, continuing from `state` (624 words +

@@ -334,3 +334,24 @@ def test_generic_statistic_philox_is_seeded_and_vectorized_estimator_is_batched(
     assert rel_err(fep_estimator(rows.to(DEV), vectorized=True), ao.fep_estimator(rows, vectorized=True)) < 2e-6
     biased = torch.stack([cases.normal((40, 500), 12), cases.normal((40, 500), 13) * 0.3], dim=-1)
     assert rel_err(fep_estimator(biased.to(DEV), kT=1.5, vectorized=True), ao.fep_estimator(biased, kT=1.5, vectorized=True)) < 2e-6
+
+
+def test_fused_estimate_entry_point_equals_the_two_step_evaluation():
+    """tfepb_fep_estimate (estimate evaluated by the final reduction kernel) against tfepb_lse + the host-side formula of
+    estimator.py:75-86, fp32 and fp64 data, with and without log-weights, and against the CPU reference."""
+    from tfep_b200 import _ops
+    from tfep_b200.analysis.estimator import _log_n
+    for dtype, tol in ((torch.float32, 1e-6), (torch.float64, 1e-12)):
+        w = (cases.normal((30011,), 21) * 1.7).to(dtype).to(DEV)
+        for kT in (1.0, 0.6):
+            log_n = _log_n(w.numel())
+            res, pair = _ops.fep_estimate(w, kT, log_n)
+            o = _ops.lse(w, -1.0 / kT)
+            assert torch.equal(pair, o) and res.dtype == dtype and res.dim() == 0
+            two_step = (-kT * (o[0] + torch.log(o[1]) - log_n)).to(dtype)
+            assert rel_err(res, two_step) <= (1e-7 if dtype == torch.float32 else 1e-15)
+            assert rel_err(res, ao.fep_estimator(w.cpu().double(), kT=kT)) < max(tol, 1e-6 if dtype == torch.float32 else 1e-7)
+        lw = torch.log_softmax(cases.normal((30011,), 22).to(dtype), dim=0).to(DEV)
+        res, _ = _ops.fep_estimate(w, 1.0, 0.0, lw)
+        o = _ops.lse(w, -1.0, lw)
+        assert rel_err(res, (-(o[0] + torch.log(o[1]))).to(dtype)) <= (1e-7 if dtype == torch.float32 else 1e-15)

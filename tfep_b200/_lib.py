@@ -15,7 +15,7 @@ from . import _build
 F32, F64 = 0, 1
 ACT_NONE, ACT_ELU = 0, 1
 GEMM_TILE_N = 64
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class TfepB200Error(RuntimeError):
@@ -177,6 +177,8 @@ SYMBOLS = {
     'tfepb_maf_inverse_sweep': (c_int32, [POINTER(SweepArgs), c_void_p]),
     'tfepb_lse_workspace_bytes': (c_int64, []),
     'tfepb_lse': (c_int32, [c_int32, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p]),
+    'tfepb_fep_estimate': (c_int32, [c_int32, c_void_p, c_void_p, c_int64, c_double, c_double, c_void_p, c_void_p, c_void_p,
+                                     c_void_p]),
     'tfepb_kl_loss_workspace_bytes': (c_int64, []),
     'tfepb_kl_loss': (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     'tfepb_kl_loss_backward': (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p,

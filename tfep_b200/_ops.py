@@ -330,6 +330,23 @@ def lse(w, scale, logw=None):
     return out
 
 
+def fep_estimate(w, kT, log_norm, logw=None):
+    """``-kT (logsumexp(-w / kT (+ logw)) - log_norm)`` as a 0-dim tensor of ``w``'s dtype, and the ``(max, sum)`` pair of the
+    pass as a (2,) float64 tensor: one streaming kernel and one final reduction that also evaluates the estimate."""
+    require_cuda(w, logw)
+    w = w.contiguous()
+    if logw is not None:
+        logw = logw.contiguous().to(w.dtype)
+    lib = _lib.load()
+    ws = torch.empty(lib.tfepb_lse_workspace_bytes() // 8, dtype=torch.float64, device=w.device)
+    out = torch.empty(2, dtype=torch.float64, device=w.device)
+    res = torch.empty((), dtype=w.dtype, device=w.device)
+    with torch.cuda.device(w.device):
+        check(lib.tfepb_fep_estimate(dtype_code(w), ptr(w), ptr(logw), w.numel(), float(kT), float(log_norm), ptr(ws), ptr(out),
+                                     ptr(res), stream_ptr(w)))
+    return res, out
+
+
 def exp_table(w, scale, max_dev):
     require_cuda(w, max_dev)
     w = w.contiguous()

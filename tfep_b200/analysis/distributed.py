@@ -97,6 +97,10 @@ def fep_estimator_sharded(work_shard, kT=1.0, group=None, n_total=None):
     ``n_total`` is the global number of samples; a caller that knows it (as ``bootstrap_statistics_sharded``'s caller
     does) saves the all-reduce of the shard lengths and the host synchronisation that reading its result back costs:
     the call is then asynchronous (one streaming kernel, one 16-byte all-gather, a handful of scalar kernels)."""
+    if _world(group) == 1:
+        n = work_shard.numel() if n_total is None else int(n_total)
+        if work_shard.is_cuda and work_shard.dtype in (torch.float32, torch.float64):
+            return _ops.fep_estimate(work_shard, kT, _log_n(n))[0]      # estimate evaluated by the final reduction kernel
     m, s = combine_lse_partials(_ops.lse(work_shard, -1.0 / kT), group)
     if n_total is None:
         n_total = work_shard.numel() if _world(group) == 1 else _total(work_shard.numel(), work_shard.device, group)

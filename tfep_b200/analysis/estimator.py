@@ -33,6 +33,9 @@ def lse_partial(work, kT=1.0, log_weights=None):
 
 
 def _row_estimate(work, kT, log_weights, log_norm):
+    if not torch.is_tensor(log_norm) and work.dtype in (torch.float32, torch.float64):
+        # the usual case: the final reduction of the kernel evaluates the estimate itself (two launches in all)
+        return _ops.fep_estimate(work, kT, log_norm, log_weights)[0]
     o = lse_partial(work, kT, log_weights)
     return (-kT * (o[0] + torch.log(o[1]) - log_norm)).to(work.dtype)
 

@@ -186,6 +186,22 @@ __global__ void __launch_bounds__(LSE_THREADS) lse_final_kernel(const double* __
     }
 }
 
+// The same final reduction, and the estimate itself: result = -kT ((max + log sum) - log_norm) in the dtype of the data
+// (what analysis/estimator.py:75-86 evaluates with five scalar tensor operations after the logsumexp).
+template <typename T>
+__global__ void __launch_bounds__(LSE_THREADS) lse_final_estimate_kernel(const double* __restrict__ partials, int nparts,
+                                                                         double* __restrict__ out2, double neg_kT, double log_norm,
+                                                                         T* __restrict__ result) {
+    MS v{0.0, 0.0};
+    for (int i = threadIdx.x; i < nparts; i += LSE_THREADS) v = ms_combine(v, MS{partials[2 * i], partials[2 * i + 1]});
+    v = ms_block_reduce(v);
+    if (threadIdx.x == 0) {
+        out2[0] = v.m;
+        out2[1] = v.s;
+        result[0] = (T)(neg_kT * ((v.m + log(v.s)) - log_norm));
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) exp_table_kernel(const T* __restrict__ w, int64_t n, T scale,
                                                         const double* __restrict__ max_dev, float* __restrict__ e) {
@@ -400,17 +416,12 @@ using namespace tfepb;
 
 extern "C" int64_t tfepb_lse_workspace_bytes(void) { return (int64_t)LSE_MAX_BLOCKS * 2 * sizeof(double); }
 
-extern "C" int tfepb_lse(int32_t dtype, const void* w, const void* logw, int64_t n, double scale, void* partials,
-                         double* out2, tfepb_stream_t stream) {
-    TFEPB_NVTX();
-    TFEPB_CHECK_ARG(n > 0, "empty data");
-    TFEPB_CHECK_ARG(w && partials && out2, "null buffer");
-    if (int rc = require_sm100()) return rc;
+// first pass of tfepb_lse / tfepb_fep_estimate: per-block (max, sum) pairs into `partials`; returns the number of blocks (< 0: error)
+static int launch_lse_partial(int32_t dtype, const void* w, const void* logw, int64_t n, double scale, void* partials, cudaStream_t s) {
     int64_t blocks = (n + (int64_t)LSE_THREADS * 16 - 1) / ((int64_t)LSE_THREADS * 16);
     // one wave of co-resident blocks (4 per SM by the launch bounds): no tail wave
     const int64_t cap = (int64_t)sm_count() * 4 < LSE_MAX_BLOCKS ? (int64_t)sm_count() * 4 : LSE_MAX_BLOCKS;
     if (blocks > cap) blocks = cap;
-    cudaStream_t s = as_stream(stream);
     if (dtype == TFEPB_F32)
         lse_partial_kernel<float><<<(int)blocks, LSE_THREADS, 0, s>>>((const float*)w, (const float*)logw, n, (float)scale,
                                                                       (double*)partials);
@@ -419,9 +430,38 @@ extern "C" int tfepb_lse(int32_t dtype, const void* w, const void* logw, int64_t
                                                                        (double*)partials);
     else
         return fail(-1, "unknown dtype %d", dtype);
-    if (int rc = check_launch("lse_partial")) return rc;
-    lse_final_kernel<<<1, LSE_THREADS, 0, s>>>((const double*)partials, (int)blocks, out2);
+    if (check_launch("lse_partial")) return -1;
+    return (int)blocks;
+}
+
+extern "C" int tfepb_lse(int32_t dtype, const void* w, const void* logw, int64_t n, double scale, void* partials,
+                         double* out2, tfepb_stream_t stream) {
+    TFEPB_NVTX();
+    TFEPB_CHECK_ARG(n > 0, "empty data");
+    TFEPB_CHECK_ARG(w && partials && out2, "null buffer");
+    if (int rc = require_sm100()) return rc;
+    cudaStream_t s = as_stream(stream);
+    const int blocks = launch_lse_partial(dtype, w, logw, n, scale, partials, s);
+    if (blocks < 0) return -1;
+    lse_final_kernel<<<1, LSE_THREADS, 0, s>>>((const double*)partials, blocks, out2);
     return check_launch("lse_final");
+}
+
+extern "C" int tfepb_fep_estimate(int32_t dtype, const void* w, const void* logw, int64_t n, double kT, double log_norm,
+                                  void* partials, double* out2, void* result, tfepb_stream_t stream) {
+    TFEPB_NVTX();
+    TFEPB_CHECK_ARG(n > 0, "empty data");
+    TFEPB_CHECK_ARG(w && partials && out2 && result, "null buffer");
+    TFEPB_CHECK_ARG(kT > 0.0, "kT must be positive");
+    if (int rc = require_sm100()) return rc;
+    cudaStream_t s = as_stream(stream);
+    const int blocks = launch_lse_partial(dtype, w, logw, n, -1.0 / kT, partials, s);
+    if (blocks < 0) return -1;
+    if (dtype == TFEPB_F32)
+        lse_final_estimate_kernel<float><<<1, LSE_THREADS, 0, s>>>((const double*)partials, blocks, out2, -kT, log_norm, (float*)result);
+    else
+        lse_final_estimate_kernel<double><<<1, LSE_THREADS, 0, s>>>((const double*)partials, blocks, out2, -kT, log_norm, (double*)result);
+    return check_launch("lse_final_estimate");
 }
 
 extern "C" int tfepb_exp_table(int32_t dtype, const void* w, int64_t n, double scale, const double* max_dev, float* e,
